@@ -1,0 +1,251 @@
+/*
+ * mtgv.h - C ABI of libmtgv.so, the B200 (sm_100a) synthetic-sample generator that
+ * replaces the cv2/numpy hot path of nmichlo/mtg-vision.
+ *
+ * The reference has no FFI of its own: its seam is three Python surfaces
+ * (SyntheticBgFgMtgImages statics, RanMtgEncDecDataset, Gen - SURVEY.md section 8b).
+ * The Python drop-ins in mtgvision_b200/ keep those surfaces and bind the entry points
+ * below with ctypes.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root, file:line).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative mtgv_status; the message for
+ *     the last failure on a context is returned by mtgv_last_error();
+ *   - all image/label/tape/param pointers are DEVICE pointers owned by the caller
+ *     (PyTorch tensors) unless the parameter name ends in `_host`;
+ *   - work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed
+ *     as void*); the library never synchronises except in mtgv_create/destroy and the
+ *     pool setters;
+ *   - one mtgv_ctx per device; calls on one ctx are not re-entrant; different ctxs are
+ *     independent (one process per GPU, no collectives: samples are independent).
+ *   - sizes are (H, W) like the reference (mtgvision/util/image.py:295).
+ */
+#ifndef MTGV_H_
+#define MTGV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTGV_ABI_VERSION 1
+
+typedef struct mtgv_ctx mtgv_ctx;
+
+typedef enum {
+  MTGV_OK = 0,
+  MTGV_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  MTGV_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  MTGV_ERR_STATE = -3,     /* pools / config not set */
+  MTGV_ERR_LIMIT = -4      /* a documented size limit was exceeded */
+} mtgv_status;
+
+typedef enum { MTGV_OUT_F16 = 0, MTGV_OUT_U8 = 1, MTGV_OUT_F32 = 2 } mtgv_out_dtype;
+
+/* ------------------------------------------------------------------------------------ */
+/* Tape: the sampled choices and magnitudes of ONE augmented sample, exactly the values  */
+/* the reference draws from `random` / `np.random`.  In parity     */
+/* tests the tape is recorded from the reference/oracle run; in production it is written  */
+/* by mtgv_sample_encoder_tape() from a Philox counter stream.                            */
+/* ------------------------------------------------------------------------------------ */
+
+typedef enum {
+  MTGV_OP_NONE = 0,
+  MTGV_OP_DOWNUP = 1,       /* Mutate.downscale_upscale  encoder_datasets.py:142-163
+                               i[0]=n, i[1]=interp_down, i[2]=interp_up (cv2 codes 0/1/2)   */
+  MTGV_OP_WARP = 2,         /* Mutate.warp               :94-111   d[0..7]=np.random.rand(4,2) */
+  MTGV_OP_AFFINE = 3,       /* Mutate.affine_transform   :353-375  d[0]=angle d[1]=tx d[2]=ty
+                               d[3]=scale d[4]=shear; i[0]=1 -> d[5],d[6] hold the host-libm
+                               alpha=cos*scale, beta=sin*scale of getRotationMatrix2D         */
+  MTGV_OP_PERSPECTIVE = 4,  /* Mutate.perspective_transform :377-403  d[0..7]=uniform(-.1,.1) */
+  MTGV_OP_TINT = 5,         /* Mutate.tint               :165-171  d[0..2]=np.random.random()  */
+  MTGV_OP_FADE_BLACK = 6,   /* Mutate.fade_black         :180-185  d[0]=np.random.random()     */
+  MTGV_OP_FADE_WHITE = 7,   /* Mutate.fade_white         :173-178  d[0]=np.random.random()     */
+  MTGV_OP_BC = 8,           /* Mutate.brightness_contrast :187-193 d[0]=contrast draw, d[1]=brightness draw */
+  MTGV_OP_FLIP = 9,         /* Mutate.flip               :73-80    i[0]=horr, i[1]=vert         */
+  MTGV_OP_ROTATE = 10,      /* Mutate.rotate_bounded     :82-87 + util/image.py:380-398
+                               d[0]=np.random.random() (deg=360*d[0]); i[0]=1 -> d[1],d[2]=alpha,beta */
+  MTGV_OP_WARP_INV = 11,    /* Mutate.warp_inv           :113-116  d[0..7]=np.random.rand(4,2) */
+  MTGV_OP_BLUR = 12,        /* Mutate.blur               :136-140  i[0]=ksize (1 or 3)          */
+  MTGV_OP_SHARPEN = 13,     /* Mutate.sharpen            :242-247                               */
+  MTGV_OP_NOISE = 14,       /* Mutate.noise              :118-134  i[0]=kind 0 speckle 1 gaussian
+                               2 salt&pepper 3 poisson; d[0]=ratio draw; field (+field2)       */
+  MTGV_OP_GAUSS_NOISE = 15, /* Mutate.gaussian_noise     :222-226  field                        */
+  MTGV_OP_SALT_PEPPER = 16, /* Mutate.salt_pepper_noise  :228-240  field=salt, field2=pepper    */
+  MTGV_OP_ERASE = 17,       /* Mutate.random_erasing     :273-351  d[0]=scale d[1]=aspect d[2]=flip draw,
+                               i[0]=stage (0 returned before centre draw, 1 empty rect, 2 filled),
+                               i[1]=cx i[2]=cy i[3]=colour mode (0 random 1 uniform_random 2 zeros
+                               3 ones 4 mean), d[3..5]=uniform_random colour; field=random block;
+                               i[4]=1 -> i[5],i[6]=host-computed block_w, block_h              */
+  MTGV_OP_CUTOUT = 18       /* Mutate.cutout             :259-271  i[2k],i[2k+1]=(y,x) of hole k */
+} mtgv_tape_opcode;
+
+#define MTGV_FIELD_PHILOX (-1) /* `field` value: generate the random field on device */
+
+typedef struct {
+  int32_t code;
+  int32_t n_field;  /* salt count (SALT_PEPPER / NOISE kind 2) */
+  int32_t n_field2; /* pepper count */
+  int32_t _pad;
+  int32_t i[16];
+  double d[8];
+  int64_t field;  /* offset (in 4-byte words) into the `fields` buffer, or MTGV_FIELD_PHILOX */
+  int64_t field2;
+} mtgv_tape_op; /* 160 bytes */
+
+#define MTGV_TAPE_MAX_OPS 18
+
+typedef enum { MTGV_KIND_VIRTUAL = 0, MTGV_KIND_CROPPED = 1 } mtgv_sample_kind;
+
+typedef struct {
+  int32_t kind;        /* mtgv_sample_kind: make_virtual (encoder_datasets.py:786) or
+                          make_cropped (:733) when the target-is-input draw fired
+                          (encoder_train.py:178)                                        */
+  int32_t card;        /* base card pool index (ran_card, encoder_datasets.py:662)      */
+  int32_t swap_choice; /* hard negative (encoder_train.py:217-221): index drawn by
+                          random.choice over the same-name group minus self, -1 = none  */
+  int32_t bg;          /* background pool index                                         */
+  int32_t upsidedown;  /* ApplyChoice(upsidedown, None) result (encoder_datasets.py:801) */
+  int32_t n_fg, n_bg, n_vrtl; /* ops[] holds fg ops, then bg ops, then vrtl ops, each in
+                                 the order the reference executed them                   */
+  uint64_t seed;       /* Philox key for device-generated fields                         */
+  mtgv_tape_op ops[MTGV_TAPE_MAX_OPS];
+} mtgv_enc_tape;
+
+/* ------------------------------------------------------------------------------------ */
+/* Params: the tape expanded into kernel-ready form (inverse homographies, fixed-point    */
+/* affine, integer geometry, float32 coefficients).  Opaque to callers except for tests.  */
+/* ------------------------------------------------------------------------------------ */
+
+typedef enum {
+  MTGV_X_NONE = 0,
+  MTGV_X_ELEM = 1,        /* y = a*x + b (separate roundings), optional clip; f[0..3]=a, f[4..7]=b per
+                             channel RGBA, i[0]=channel mask, i[1]=clip                            */
+  MTGV_X_DOWNUP = 2,      /* i[0]=n i[1]=down i[2]=up                                              */
+  MTGV_X_WARP_PERSP = 3,  /* d[0..8] = cv::invert(M) as used by cv::warpPerspective                */
+  MTGV_X_WARP_AFFINE = 4, /* d[0..5] = inverted 2x3 as used by cv::warpAffine                      */
+  MTGV_X_BLUR3 = 5,
+  MTGV_X_SHARPEN = 6,
+  MTGV_X_NOISE = 7,       /* i[0]=kind, f[0]=ratio f[1]=1-ratio                                    */
+  MTGV_X_GAUSS_NOISE = 8,
+  MTGV_X_SALT_PEPPER = 9,
+  MTGV_X_ERASE = 10,      /* i[0..3]=y0,y1,x0,x1 i[4]=mode f[0..2]=colour                          */
+  MTGV_X_CUTOUT = 11      /* i[0..15]                                                              */
+} mtgv_x_opcode;
+
+typedef struct {
+  int32_t code;
+  int32_t n_field, n_field2;
+  int32_t _pad;
+  int32_t i[16];
+  float f[8];
+  double d[9];
+  int64_t field, field2;
+} mtgv_x_op; /* 200 bytes */
+
+#define MTGV_X_MAX_OPS 16
+
+typedef struct {
+  int32_t kind, card, bg, upsidedown;
+  int32_t out_h, out_w;
+  int32_t card_h, card_w;
+  /* foreground / cropped geometry: crop_to_size(pad=True) (util/image.py:349-377) or
+     remove_border_resized (:337-346) */
+  int32_t src_y0, src_x0, src_h, src_w; /* source window of the card that is area-resized */
+  int32_t fg_rh, fg_rw, fg_y0, fg_x0;   /* resized size and paste offset inside (out_h,out_w) */
+  /* background chain: flip -> rotate_bounded -> warp_inv -> crop_to_size */
+  int32_t bg_h, bg_w, flip_h, flip_v;
+  int32_t rot_nh, rot_nw;
+  int32_t bg_rh, bg_rw, bg_y0, bg_x0;
+  int32_t n_fg, n_pre, n_post, n_vrtl; /* ops[]: fg | bg elementwise before G0 | after G0 | vrtl */
+  double rot_inv[6];
+  double winv[9];
+  uint64_t seed;
+  int32_t status; /* 0 ok, else mtgv_status raised by the expansion of this sample */
+  int32_t _pad;
+  mtgv_x_op ops[MTGV_X_MAX_OPS];
+} mtgv_enc_params;
+
+typedef struct {
+  int32_t out_h, out_w;          /* x_size_hw (encoder_train.py:98)                     */
+  int32_t y_h, y_w;              /* y_size_hw (:99)                                      */
+  double target_is_input_prob;   /* :101 */
+  double similar_neg_prob;       /* :102 */
+  int32_t half_upsidedown;       /* :100 */
+  int32_t paired;                /* :96  */
+  int32_t targets;               /* :97  */
+  int32_t _pad;
+} mtgv_enc_config;
+
+/* ------------------------------------------------------------------------------------ */
+/* Context and pools                                                                     */
+/* ------------------------------------------------------------------------------------ */
+
+int mtgv_abi_version(void);
+mtgv_ctx* mtgv_create(int device);
+void mtgv_destroy(mtgv_ctx* ctx);
+const char* mtgv_last_error(const mtgv_ctx* ctx);
+
+/* Card pool: replaces SyntheticBgFgMtgImages._load_card_image / _init_ label tables
+ * (encoder_datasets.py:557-590, 633-634).  cards: [N,H,W,3] uint8 RGB (device).  The
+ * library keeps its own planar copy.  labels3: [N,3] int32 (id,name,set ranks, :586-590);
+ * grp_off [N+1], grp_mem: CSR of same-name groups in insertion order (:570, :619-630).
+ * Also builds the static rounded-rect alpha (make_masked :755-772, round_rect_mask
+ * util/image.py:406-425) for (H,W). */
+int mtgv_set_card_pool(mtgv_ctx* ctx, const uint8_t* cards, int n, int h, int w, const int32_t* labels3,
+                       const int32_t* grp_off, const int32_t* grp_mem, int n_mem);
+
+/* Background pool: replaces IlsvrcImages._load_image (encoder_datasets.py:457-474).
+ * bgs: concatenated HWC uint8 images (device); offsets[n] byte offsets; hw[n][2]. */
+int mtgv_set_bg_pool(mtgv_ctx* ctx, const uint8_t* bgs, const int64_t* offsets_host, const int32_t* hw_host, int n);
+
+int mtgv_set_encoder_config(mtgv_ctx* ctx, const mtgv_enc_config* cfg_host);
+
+/* ------------------------------------------------------------------------------------ */
+/* Encoder path                                                                          */
+/* ------------------------------------------------------------------------------------ */
+
+/* Production sampler: writes the tapes of `n_pairs` x-samples followed by `n_pairs`
+ * x2-samples (when paired) for global sample indices [first_index, first_index+n_pairs),
+ * drawing what RanMtgEncDecDataset._random_image_batch/_make_image_batch draw
+ * (encoder_train.py:149-156,189-230) from Philox4x32-10 keyed by (seed, index). */
+int mtgv_sample_encoder_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n_pairs, mtgv_enc_tape* tape,
+                             void* stream);
+
+/* Subsystem (1): tape -> params.  Replaces cv2.getPerspectiveTransform / getRotationMatrix2D /
+ * the matrix inversions inside cv2.warp* / crop_to_size geometry for every sample
+ * (encoder_datasets.py:94-111,353-403; util/image.py:349-398).  Also resolves the
+ * hard-negative card (encoder_datasets.py:619-630) and writes labels [n,3] int64
+ * (card_get_labels :586-590) when `labels` is not NULL. */
+int mtgv_expand_params(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels,
+                       void* stream);
+
+/* Subsystems (2)(3)(5): runs n samples; out is [n,3,out_h,out_w] NCHW of out_dtype.
+ * Replaces make_virtual / make_cropped + np.stack + image_to_tensor
+ * (encoder_datasets.py:733-813, encoder_train.py:143,228).  `fields` may be NULL when
+ * every field offset is MTGV_FIELD_PHILOX. */
+int mtgv_encoder_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype,
+                       const void* fields, void* stream);
+
+/* make_cropped targets y (encoder_train.py:171-173): out [n,3,y_h,y_w] for cards[n] (device int32). */
+int mtgv_encoder_targets(mtgv_ctx* ctx, const int32_t* cards, int n, void* out, int out_dtype, void* stream);
+
+/* Parity entry: cv2.warpPerspective(src f32 HWC, M, (dw,dh), INTER_LINEAR, BORDER_CONSTANT 0)
+ * for n images (encoder_datasets.py:111,403; od_datasets.py:82).  src [n,sh,sw,c] f32,
+ * M [n,9] f64 (forward matrix, inverted on device like cv2), dst [n,dh,dw,c] f32. */
+int mtgv_warp_perspective(mtgv_ctx* ctx, const float* src, int n, int sh, int sw, int c, const double* M, float* dst,
+                          int dh, int dw, void* stream);
+
+/* Parity/debug entry: run a list of expanded ops on float32 HWC images with the same
+ * plane interpreter the batch kernel uses.  img [n,h,w,c] f32 in/out (c = 3 or 4). */
+int mtgv_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops,
+                       const void* fields, uint64_t seed, void* stream);
+
+/* Number of kernels launched by this context since creation (bench bookkeeping). */
+int64_t mtgv_launch_count(const mtgv_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTGV_H_ */

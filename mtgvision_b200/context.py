@@ -1,0 +1,163 @@
+"""Thin object wrapper over the C ABI: one `Context` per GPU.
+
+PyTorch is plumbing here (device memory, streams); every pixel and label is produced by
+libmtgv.so.  All tensors returned live on the context's device.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+_TORCH_OUT = {abi.OUT_F16: torch.float16, abi.OUT_U8: torch.uint8, abi.OUT_F32: torch.float32}
+
+
+def _ptr(t: torch.Tensor | None):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+class Context:
+    def __init__(self, device: int | torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise abi.MtgvError("mtgvision_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = abi.load_library()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else device.index or 0)
+        self._h = self.lib.mtgv_create(self.device.index)
+        if not self._h:
+            raise abi.MtgvError(f"mtgv_create({self.device.index}) failed")
+        self.cfg: abi.EncConfig | None = None
+        self.n_cards = 0
+        self.n_bgs = 0
+        self.card_hw = (0, 0)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mtgv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.mtgv_last_error(self._h)
+            raise abi.MtgvError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self) -> int:
+        return int(self.lib.mtgv_launch_count(self._h))
+
+    # ------------------------------------------------------------------ pools
+    def set_card_pool(self, images, labels3, grp_off, grp_mem):
+        """images: (N,H,W,3) uint8 numpy array or CUDA tensor."""
+        if isinstance(images, np.ndarray):
+            images = torch.from_numpy(np.ascontiguousarray(images))
+        if images.dtype != torch.uint8 or images.ndim != 4 or images.shape[-1] != 3:
+            raise ValueError("card images must be (N,H,W,3) uint8")
+        n, h, w, _ = images.shape
+        # ingest in chunks so the HWC staging copy stays small next to the planar pool
+        dev = images.to(self.device, non_blocking=False).contiguous()
+        lab = torch.as_tensor(np.ascontiguousarray(labels3, dtype=np.int32)).to(self.device)
+        off = torch.as_tensor(np.ascontiguousarray(grp_off, dtype=np.int32)).to(self.device)
+        mem = torch.as_tensor(np.ascontiguousarray(grp_mem, dtype=np.int32)).to(self.device)
+        if lab.shape != (n, 3) or off.numel() != n + 1:
+            raise ValueError("labels3 must be (N,3) and grp_off (N+1,)")
+        rc = self.lib.mtgv_set_card_pool(self._h, _ptr(dev), n, h, w, _ptr(lab), _ptr(off), _ptr(mem), mem.numel())
+        self._check(rc, "mtgv_set_card_pool")
+        self.n_cards, self.card_hw = n, (h, w)
+
+    def set_bg_pool(self, images):
+        """images: list of (h,w,3) uint8 numpy arrays (sizes may differ)."""
+        hw = np.asarray([im.shape[:2] for im in images], dtype=np.int32)
+        sizes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
+        offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        flat = np.concatenate([np.ascontiguousarray(im, dtype=np.uint8).reshape(-1) for im in images])
+        dev = torch.from_numpy(flat).to(self.device)
+        rc = self.lib.mtgv_set_bg_pool(self._h, _ptr(dev), offsets.ctypes.data_as(C.c_void_p),
+                                       hw.ctypes.data_as(C.c_void_p), len(images))
+        self._check(rc, "mtgv_set_bg_pool")
+        self.n_bgs = len(images)
+
+    def set_encoder_config(self, *, x_size_hw=(192, 128), y_size_hw=(192, 128), target_is_input_prob=0.05,
+                           similar_neg_prob=0.2, half_upsidedown=False, paired=True, targets=False):
+        cfg = abi.EncConfig(int(x_size_hw[0]), int(x_size_hw[1]), int(y_size_hw[0]), int(y_size_hw[1]),
+                            float(target_is_input_prob), float(similar_neg_prob), int(half_upsidedown), int(paired),
+                            int(targets), 0)
+        self._check(self.lib.mtgv_set_encoder_config(self._h, C.byref(cfg)), "mtgv_set_encoder_config")
+        self.cfg = cfg
+
+    # ------------------------------------------------------------------ encoder path
+    def sample_encoder_tape(self, seed: int, first_index: int, n_pairs: int) -> torch.Tensor:
+        n = n_pairs * (2 if self.cfg.paired else 1)
+        tape = torch.empty((n, abi.TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        rc = self.lib.mtgv_sample_encoder_tape(self._h, C.c_uint64(seed & (2**64 - 1)), C.c_int64(first_index), n_pairs,
+                                               _ptr(tape), self._stream())
+        self._check(rc, "mtgv_sample_encoder_tape")
+        return tape
+
+    def upload_tape(self, tape_np: np.ndarray) -> torch.Tensor:
+        assert tape_np.dtype == abi.TAPE_DTYPE
+        return torch.from_numpy(tape_np.view(np.uint8).reshape(len(tape_np), -1).copy()).to(self.device)
+
+    def expand_params(self, tape: torch.Tensor, want_labels: bool = True):
+        n = tape.shape[0]
+        params = torch.empty((n, abi.PARAMS_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        labels = torch.empty((n, 3), dtype=torch.int64, device=self.device) if want_labels else None
+        rc = self.lib.mtgv_expand_params(self._h, _ptr(tape), n, _ptr(params), _ptr(labels), self._stream())
+        self._check(rc, "mtgv_expand_params")
+        return params, labels
+
+    def encoder_batch(self, params: torch.Tensor, out_dtype: int = abi.OUT_F16, fields: torch.Tensor | None = None,
+                      out: torch.Tensor | None = None) -> torch.Tensor:
+        n = params.shape[0]
+        shape = (n, 3, self.cfg.out_h, self.cfg.out_w)
+        if out is None:
+            out = torch.empty(shape, dtype=_TORCH_OUT[out_dtype], device=self.device)
+        else:
+            assert out.shape == shape and out.dtype == _TORCH_OUT[out_dtype] and out.is_contiguous()
+        rc = self.lib.mtgv_encoder_batch(self._h, _ptr(params), n, _ptr(out), out_dtype, _ptr(fields), self._stream())
+        self._check(rc, "mtgv_encoder_batch")
+        return out
+
+    def encoder_targets(self, cards: torch.Tensor, out_dtype: int = abi.OUT_F16) -> torch.Tensor:
+        cards = cards.to(self.device, dtype=torch.int32).contiguous()
+        n = cards.numel()
+        out = torch.empty((n, 3, self.cfg.y_h, self.cfg.y_w), dtype=_TORCH_OUT[out_dtype], device=self.device)
+        rc = self.lib.mtgv_encoder_targets(self._h, _ptr(cards), n, _ptr(out), out_dtype, self._stream())
+        self._check(rc, "mtgv_encoder_targets")
+        return out
+
+    # ------------------------------------------------------------------ parity / debug entries
+    def warp_perspective(self, src: torch.Tensor, M: torch.Tensor, dsize_hw) -> torch.Tensor:
+        """src (n,h,w,c) float32, M (n,3,3) float64 -> (n,dh,dw,c) float32, cv2.warpPerspective semantics."""
+        src = src.to(self.device, dtype=torch.float32).contiguous()
+        M = M.to(self.device, dtype=torch.float64).contiguous()
+        n, sh, sw, c = src.shape
+        dh, dw = dsize_hw
+        dst = torch.empty((n, dh, dw, c), dtype=torch.float32, device=self.device)
+        rc = self.lib.mtgv_warp_perspective(self._h, _ptr(src), n, sh, sw, c, _ptr(M), _ptr(dst), dh, dw, self._stream())
+        self._check(rc, "mtgv_warp_perspective")
+        return dst
+
+    def run_plane_ops(self, img: torch.Tensor, ops_np: np.ndarray, fields: torch.Tensor | None = None, seed: int = 0):
+        """img (n,h,w,c) float32 (modified in place and returned); ops_np: array of abi.XOP_DTYPE."""
+        assert ops_np.dtype == abi.XOP_DTYPE
+        img = img.to(self.device, dtype=torch.float32).contiguous()
+        n, h, w, c = img.shape
+        ops = torch.from_numpy(ops_np.view(np.uint8).reshape(len(ops_np), -1).copy()).to(self.device)
+        rc = self.lib.mtgv_run_plane_ops(self._h, _ptr(img), n, h, w, c, _ptr(ops), len(ops_np), _ptr(fields),
+                                         C.c_uint64(seed), self._stream())
+        self._check(rc, "mtgv_run_plane_ops")
+        return img

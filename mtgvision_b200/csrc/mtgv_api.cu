@@ -1,0 +1,205 @@
+// mtgv_api.cu - C ABI of libmtgv.so (include/mtgv.h): context, pools, entry points.
+#include <math.h>
+
+#include <vector>
+
+#include "mtgv_internal.cuh"
+
+using namespace mtgv;
+
+namespace mtgv {
+int det_destroy(mtgv_ctx* ctx);
+}
+
+extern "C" {
+
+int mtgv_abi_version(void) { return MTGV_ABI_VERSION; }
+
+mtgv_ctx* mtgv_create(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  mtgv_ctx* ctx = new mtgv_ctx();
+  ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (cudaMalloc(&ctx->cfg_dev, sizeof(mtgv_enc_config)) != cudaSuccess) {
+    delete ctx;
+    return nullptr;
+  }
+  return ctx;
+}
+
+static void free_cards(mtgv_ctx* ctx) {
+  cudaFree(ctx->card_planes); cudaFree(ctx->labels3); cudaFree(ctx->grp_off); cudaFree(ctx->grp_mem);
+  cudaFree(ctx->mask_enc); cudaFree(ctx->mask_det);
+  ctx->card_planes = nullptr; ctx->labels3 = ctx->grp_off = ctx->grp_mem = nullptr;
+  ctx->mask_enc = ctx->mask_det = nullptr;
+  ctx->n_cards = 0;
+}
+static void free_bgs(mtgv_ctx* ctx) {
+  cudaFree(ctx->bg_planes); cudaFree(ctx->bg_off); cudaFree(ctx->bg_hw);
+  ctx->bg_planes = nullptr; ctx->bg_off = nullptr; ctx->bg_hw = nullptr; ctx->n_bgs = 0;
+}
+
+void mtgv_destroy(mtgv_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  det_destroy(ctx);
+  free_cards(ctx);
+  free_bgs(ctx);
+  cudaFree(ctx->cfg_dev); cudaFree(ctx->alpha0); cudaFree(ctx->alpha_scratch); cudaFree(ctx->sync_words);
+  cudaFree(ctx->tmp_params);
+  delete ctx;
+}
+
+const char* mtgv_last_error(const mtgv_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t mtgv_launch_count(const mtgv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mtgv_set_card_pool(mtgv_ctx* ctx, const uint8_t* cards, int n, int h, int w, const int32_t* labels3, const int32_t* grp_off,
+                       const int32_t* grp_mem, int n_mem) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!cards || n <= 0 || h < 8 || w < 8 || !labels3 || !grp_off || !grp_mem || n_mem < n)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_set_card_pool: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  free_cards(ctx);
+  ctx->card_h = h; ctx->card_w = w; ctx->card_pitch = round_up(w, 16);
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->card_planes, (size_t)n * 3 * h * ctx->card_pitch));
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->labels3, (size_t)n * 3 * 4));
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->grp_off, ((size_t)n + 1) * 4));
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->grp_mem, (size_t)n_mem * 4));
+  MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->labels3, labels3, (size_t)n * 3 * 4, cudaMemcpyDefault));
+  MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->grp_off, grp_off, ((size_t)n + 1) * 4, cudaMemcpyDefault));
+  MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->grp_mem, grp_mem, (size_t)n_mem * 4, cudaMemcpyDefault));
+  int rc = pool_planarize(ctx, cards, ctx->card_planes, n, h, w, ctx->card_pitch, 0);
+  if (rc) return rc;
+  // static masks: make_masked uses radius_ratio 0.05 (encoder_datasets.py:763), make_card_with_mask 0.046
+  // (od_datasets.py:223,234); radius = ceil(max(h,w)*ratio) (util/image.py:413-414)
+  std::vector<float> m((size_t)h * w);
+  const int hw_max = h > w ? h : w;
+  const double ratios[2] = {0.05, 0.046};
+  float** dst[2] = {&ctx->mask_enc, &ctx->mask_det};
+  for (int k = 0; k < 2; k++) {
+    int radius = (int)ceil((double)hw_max * ratios[k]);
+    if (2 * radius > h || 2 * radius > w) return fail(ctx, MTGV_ERR_LIMIT, "card too small for the rounded-corner mask");
+    host_round_rect_mask(h, w, radius, m.data());
+    MTGV_CUDA_OK(ctx, cudaMalloc(dst[k], (size_t)h * w * 4));
+    MTGV_CUDA_OK(ctx, cudaMemcpy(*dst[k], m.data(), (size_t)h * w * 4, cudaMemcpyHostToDevice));
+  }
+  ctx->n_cards = n;
+  rc = enc_build_static_alpha(ctx, 0);
+  if (rc) return rc;
+  MTGV_CUDA_OK(ctx, cudaDeviceSynchronize());
+  return MTGV_OK;
+}
+
+int mtgv_set_bg_pool(mtgv_ctx* ctx, const uint8_t* bgs, const int64_t* offsets_host, const int32_t* hw_host, int n) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!bgs || !offsets_host || !hw_host || n <= 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_set_bg_pool: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  free_bgs(ctx);
+  std::vector<int64_t> off(n);
+  size_t total = 0;
+  for (int j = 0; j < n; j++) {
+    int h = hw_host[2 * j], w = hw_host[2 * j + 1];
+    if (h < 2 || w < 2) return fail(ctx, MTGV_ERR_INVALID, "mtgv_set_bg_pool: image smaller than 2x2");
+    off[j] = (int64_t)total;
+    total += (size_t)3 * h * round_up(w, 16);
+  }
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_planes, total));
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_off, (size_t)n * 8));
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_hw, (size_t)n * 2 * 4));
+  MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->bg_off, off.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->bg_hw, hw_host, (size_t)n * 2 * 4, cudaMemcpyHostToDevice));
+  // runs of equally-sized, contiguous images are ingested with one launch each
+  int j = 0;
+  while (j < n) {
+    int h = hw_host[2 * j], w = hw_host[2 * j + 1], k = j + 1;
+    while (k < n && hw_host[2 * k] == h && hw_host[2 * k + 1] == w &&
+           offsets_host[k] == offsets_host[k - 1] + (int64_t)h * w * 3)
+      k++;
+    int rc = pool_planarize(ctx, bgs + offsets_host[j], ctx->bg_planes + off[j], k - j, h, w, round_up(w, 16), 0);
+    if (rc) return rc;
+    j = k;
+  }
+  ctx->n_bgs = n;
+  MTGV_CUDA_OK(ctx, cudaDeviceSynchronize());
+  return MTGV_OK;
+}
+
+int mtgv_set_encoder_config(mtgv_ctx* ctx, const mtgv_enc_config* cfg) {
+  if (!ctx || !cfg) return MTGV_ERR_INVALID;
+  if (cfg->out_h < 8 || cfg->out_w < 8 || cfg->y_h < 8 || cfg->y_w < 8)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_set_encoder_config: sizes must be >= 8");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  ctx->cfg = *cfg;
+  ctx->cfg_set = true;
+  MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->cfg_dev, cfg, sizeof(*cfg), cudaMemcpyHostToDevice));
+  int rc = enc_build_static_alpha(ctx, 0);
+  if (rc) return rc;
+  MTGV_CUDA_OK(ctx, cudaDeviceSynchronize());
+  return MTGV_OK;
+}
+
+static int need_encoder(mtgv_ctx* ctx, bool need_bg) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!ctx->cfg_set) return fail(ctx, MTGV_ERR_STATE, "encoder config not set (mtgv_set_encoder_config)");
+  if (!ctx->n_cards) return fail(ctx, MTGV_ERR_STATE, "card pool not set (mtgv_set_card_pool)");
+  if (need_bg && !ctx->n_bgs) return fail(ctx, MTGV_ERR_STATE, "background pool not set (mtgv_set_bg_pool)");
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return fail(ctx, MTGV_ERR_CUDA, cudaGetErrorString(e));
+  return MTGV_OK;
+}
+
+int mtgv_sample_encoder_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n_pairs, mtgv_enc_tape* tape, void* stream) {
+  int rc = need_encoder(ctx, true);
+  if (rc) return rc;
+  if (!tape || n_pairs < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_sample_encoder_tape: bad arguments");
+  return enc_sample_tape(ctx, seed, first_index, n_pairs, tape, (cudaStream_t)stream);
+}
+
+int mtgv_expand_params(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels, void* stream) {
+  int rc = need_encoder(ctx, true);
+  if (rc) return rc;
+  if (!tape || !params || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_expand_params: bad arguments");
+  return enc_expand(ctx, tape, n, params, labels, (cudaStream_t)stream);
+}
+
+int mtgv_encoder_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
+                       void* stream) {
+  int rc = need_encoder(ctx, true);
+  if (rc) return rc;
+  if (!params || !out || n < 0 || out_dtype < 0 || out_dtype > 2)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_encoder_batch: bad arguments");
+  return enc_batch(ctx, params, n, out, out_dtype, fields, (cudaStream_t)stream);
+}
+
+int mtgv_encoder_targets(mtgv_ctx* ctx, const int32_t* cards, int n, void* out, int out_dtype, void* stream) {
+  int rc = need_encoder(ctx, false);
+  if (rc) return rc;
+  if (!cards || !out || n < 0 || out_dtype < 0 || out_dtype > 2)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_encoder_targets: bad arguments");
+  return enc_targets(ctx, cards, n, out, out_dtype, (cudaStream_t)stream);
+}
+
+int mtgv_warp_perspective(mtgv_ctx* ctx, const float* src, int n, int sh, int sw, int c, const double* M, float* dst, int dh,
+                          int dw, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!src || !M || !dst || n < 0 || sh < 1 || sw < 1 || dh < 1 || dw < 1 || c < 1 || c > 4)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_warp_perspective: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return enc_warp_perspective(ctx, src, n, sh, sw, c, M, dst, dh, dw, (cudaStream_t)stream);
+}
+
+int mtgv_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops, const void* fields,
+                       uint64_t seed, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!img || !ops || n < 0 || n_ops < 0 || h < 2 || w < 2)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_run_plane_ops: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return enc_run_plane_ops(ctx, img, n, h, w, c, ops, n_ops, fields, seed, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,1253 @@
+// mtgv_enc.cu - encoder-pair generator kernels for sm_100a.
+//
+// One persistent CTA per SM walks a work queue of (sample, plane) items.  A plane is one
+// channel of one augmented sample held entirely in shared memory as float32
+// (2 ping-pong planes of out_h*out_w*4 B = 2*96 KiB for 192x128): every stage of the
+// reference pipeline (area resize -> downscale/upscale -> warp -> photometrics ->
+// background chain -> composite -> shuffled post-augments) runs on-chip and the only HBM
+// traffic is the uint8 card/background source read and the NCHW fp16/u8 plane write.
+// The three colour planes and the alpha plane of a sample are independent except at the
+// composite, where colour CTAs consume the alpha plane published by the alpha CTA
+// (L2 scratch + release/acquire flag; the queue order guarantees the producer is running).
+//
+// Reference semantics (mtgvision/encoder_datasets.py, mtgvision/util/image.py) are cited
+// at each stage; the cv2 arithmetic follows SURVEY.md section 8a-notes and is restated in
+// oracle/cv2_restate.py.  Compiled with -fmad=false: every float multiply/add below is a
+// separate rounding, as in the reference's numpy / OpenCV scalar code.
+#include <cuda_fp16.h>
+
+#include "mtgv_internal.cuh"
+
+namespace mtgv {
+
+constexpr int kThreads = 512;
+
+// ------------------------------------------------------------------------------------ //
+// small device helpers                                                                  //
+// ------------------------------------------------------------------------------------ //
+
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+__device__ __forceinline__ float bilinear_weights_sum(float v0, float v1, float v2, float v3, int ax, int ay) {
+  // initInterTab2D(INTER_LINEAR): w = (1-fy|fy)*(1-fx|fx), fx = ax/32 -> all products exact
+  float fx = (float)ax * 0.03125f, fy = (float)ay * 0.03125f;
+  float gx = 1.f - fx, gy = 1.f - fy;
+  float s = __fmul_rn(v0, gy * gx);
+  s = __fadd_rn(s, __fmul_rn(v1, gy * fx));
+  s = __fadd_rn(s, __fmul_rn(v2, fy * gx));
+  s = __fadd_rn(s, __fmul_rn(v3, fy * fx));
+  return s;
+}
+
+// remapBilinear<float>, BORDER_CONSTANT 0, source = float plane (shared or global)
+__device__ __forceinline__ float bilinear_plane(const float* __restrict__ S, int H, int W, int X, int Y) {
+  int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+  bool x0 = (unsigned)sx < (unsigned)W, x1 = (unsigned)(sx + 1) < (unsigned)W;
+  bool y0 = (unsigned)sy < (unsigned)H, y1 = (unsigned)(sy + 1) < (unsigned)H;
+  const float* p = S + sy * W + sx;
+  float v0 = (y0 && x0) ? p[0] : 0.f;
+  float v1 = (y0 && x1) ? p[1] : 0.f;
+  float v2 = (y1 && x0) ? p[W] : 0.f;
+  float v3 = (y1 && x1) ? p[W + 1] : 0.f;
+  return bilinear_weights_sum(v0, v1, v2, v3, X & 31, Y & 31);
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float u32_to_unit(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+
+// per-pixel Philox draw for device-generated random fields: (seed, op slot) key, (pixel, channel) counter
+__device__ __forceinline__ void field_draw(uint64_t seed, int slot, uint32_t pixel, uint32_t chan, uint32_t sub, uint32_t* r) {
+  Philox ph;
+  ph.key[0] = (uint32_t)seed ^ (0x9E3779B9u * (uint32_t)(slot + 1));
+  ph.key[1] = (uint32_t)(seed >> 32);
+  ph(pixel, chan, sub, 0x6d746776u, r);
+}
+__device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
+  float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  float u2 = u32_to_unit(b);
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+// ------------------------------------------------------------------------------------ //
+// plane interpreter                                                                     //
+// ------------------------------------------------------------------------------------ //
+
+struct Vm {
+  float* P[2];
+  int cur;
+  int H, W;
+  int chan;  // 0..2 colour, 3 alpha
+  const uint32_t* fields;
+  uint64_t seed;
+  __device__ float* cur_p() const { return P[cur]; }
+  __device__ float* oth_p() const { return P[cur ^ 1]; }
+};
+
+// cv2.resize restated per destination pixel (oracle/cv2_restate.py resize_nearest/linear/cubic)
+__device__ __forceinline__ void cubic_coeffs(float x, float* c) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1.f) - 5.f * A) * (x + 1.f) + 8.f * A) * (x + 1.f) - 4.f * A;
+  c[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  c[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+__device__ __forceinline__ void linear_ofs(int d, int ssize, double scale, int* s, float* f) {
+  float fx = (float)(((double)d + 0.5) * scale - 0.5);
+  int sx = (int)floorf(fx);
+  fx -= (float)sx;
+  if (sx < 0) { sx = 0; fx = 0.f; }
+  if (sx >= ssize - 1) { sx = ssize - 1; fx = 0.f; }
+  *s = sx;
+  *f = fx;
+}
+
+__device__ float resize_px(const float* __restrict__ S, int sh, int sw, int dh, int dw, int interp, int y, int x) {
+  if (interp == 0) {  // INTER_NEAREST
+    double ifx = 1.0 / ((double)dw / (double)sw), ify = 1.0 / ((double)dh / (double)sh);
+    int sx = min((int)floor((double)x * ifx), sw - 1), sy = min((int)floor((double)y * ify), sh - 1);
+    return S[sy * sw + sx];
+  }
+  double scx = 1.0 / ((double)dw / (double)sw), scy = 1.0 / ((double)dh / (double)sh);  // cv::resize: 1./inv_scale
+  if (interp == 1) {  // INTER_LINEAR
+    int sx, sy;
+    float fx, fy;
+    linear_ofs(x, sw, scx, &sx, &fx);
+    linear_ofs(y, sh, scy, &sy, &fy);
+    int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+    float gx = 1.f - fx, gy = 1.f - fy;
+    float r0 = S[sy * sw + sx] * gx + S[sy * sw + sx1] * fx;
+    float r1 = S[sy1 * sw + sx] * gx + S[sy1 * sw + sx1] * fx;
+    return r0 * gy + r1 * fy;
+  }
+  // INTER_CUBIC
+  float fx = (float)(((double)x + 0.5) * scx - 0.5), fy = (float)(((double)y + 0.5) * scy - 0.5);
+  int sx = (int)floorf(fx), sy = (int)floorf(fy);
+  fx -= (float)sx;
+  fy -= (float)sy;
+  float cx[4], cy[4];
+  cubic_coeffs(fx, cx);
+  cubic_coeffs(fy, cy);
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int yy = min(max(sy - 1 + j, 0), sh - 1);
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int xx = min(max(sx - 1 + i, 0), sw - 1);
+      r = r + S[yy * sw + xx] * cx[i];
+    }
+    acc = acc + r * cy[j];
+  }
+  return acc;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+// Executes one expanded op on the current plane.  Block-cooperative; returns with all
+// writes visible (trailing __syncthreads).
+__device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
+  const int H = vm.H, W = vm.W, HW = H * W, c = vm.chan;
+  float* cur = vm.cur_p();
+  float* oth = vm.oth_p();
+  const int tid = threadIdx.x, nt = blockDim.x;
+  switch (op.code) {
+    case MTGV_X_ELEM: {
+      if (!((op.i[0] >> c) & 1)) break;
+      const float a = op.f[c], b = op.f[4 + c];
+      const bool clip = op.i[1] != 0;
+      for (int i = tid; i < HW; i += nt) {
+        float v = __fadd_rn(__fmul_rn(a, cur[i]), b);
+        cur[i] = clip ? clip01(v) : v;
+      }
+      break;
+    }
+    case MTGV_X_DOWNUP: {  // Mutate.downscale_upscale: two cv2.resize calls
+      const int n = op.i[0], h2 = H >> n, w2 = W >> n;
+      for (int i = tid; i < h2 * w2; i += nt) oth[i] = resize_px(cur, H, W, h2, w2, op.i[1], i / w2, i % w2);
+      __syncthreads();
+      for (int i = tid; i < HW; i += nt) cur[i] = resize_px(oth, h2, w2, H, W, op.i[2], i / W, i % W);
+      break;
+    }
+    case MTGV_X_WARP_PERSP: {  // cv2.warpPerspective, same size
+      const int bw0 = persp_block_w(H, W);
+      for (int i = tid; i < HW; i += nt) {
+        int X, Y;
+        persp_coord(op.d, i % W, i / W, bw0, &X, &Y);
+        oth[i] = bilinear_plane(cur, H, W, X, Y);
+      }
+      vm.cur ^= 1;
+      break;
+    }
+    case MTGV_X_WARP_AFFINE: {  // cv2.warpAffine, same size
+      for (int i = tid; i < HW; i += nt) {
+        int x = i % W, y = i / W;
+        int X = (affine_row_origin(op.d[1], op.d[2], y) + affine_col_delta(op.d[0], x)) >> 5;
+        int Y = (affine_row_origin(op.d[4], op.d[5], y) + affine_col_delta(op.d[3], x)) >> 5;
+        oth[i] = bilinear_plane(cur, H, W, X, Y);
+      }
+      vm.cur ^= 1;
+      break;
+    }
+    case MTGV_X_BLUR3: {  // cv2.GaussianBlur((3,3),0): [1/4,1/2,1/4] separable, REFLECT_101
+      for (int i = tid; i < HW; i += nt) {
+        int x = i % W, y = i / W;
+        int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+        float r[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float* row = cur + reflect101(y - 1 + j, H) * W;
+          r[j] = row[xm] * 0.25f + row[x] * 0.5f + row[xp] * 0.25f;
+        }
+        oth[i] = r[0] * 0.25f + r[1] * 0.5f + r[2] * 0.25f;
+      }
+      vm.cur ^= 1;
+      break;
+    }
+    case MTGV_X_SHARPEN: {  // filter2D [[0,-1,0],[-1,5,-1],[0,-1,0]] + clip (Mutate.sharpen)
+      for (int i = tid; i < HW; i += nt) {
+        int x = i % W, y = i / W;
+        float v = 5.f * cur[i] - cur[reflect101(y - 1, H) * W + x] - cur[y * W + reflect101(x - 1, W)] -
+                  cur[y * W + reflect101(x + 1, W)] - cur[reflect101(y + 1, H) * W + x];
+        oth[i] = clip01(v);
+      }
+      vm.cur ^= 1;
+      break;
+    }
+    case MTGV_X_NOISE: {  // Mutate.noise: noisy variant blended by ratio into channels :3
+      if (c > 2) break;
+      const int kind = op.i[0];
+      const float ra = op.f[0], rb = op.f[1];
+      const bool inj = op.field != MTGV_FIELD_PHILOX;
+      if (kind == 2) {  // noise_salt_pepper(strength .1, svp .5) -> clip -> blend
+        for (int i = tid; i < HW; i += nt) oth[i] = cur[i];
+        __syncthreads();
+        for (int pass = 0; pass < 2; pass++) {
+          const int npts = pass ? op.n_field2 : op.n_field;
+          const int32_t* pts = inj ? (const int32_t*)(vm.fields + (pass ? op.field2 : op.field)) : nullptr;
+          for (int k = tid; k < npts; k += nt) {
+            int py, px, pc;
+            if (inj) {
+              py = pts[3 * k], px = pts[3 * k + 1], pc = pts[3 * k + 2];
+            } else {  // np.random.randint(0, i-1) per axis of (H, W, 3)
+              uint32_t r[4];
+              field_draw(vm.seed, slot, (uint32_t)k, 0, 10 + pass, r);
+              py = (int)(((uint64_t)r[0] * (uint32_t)(H - 1)) >> 32);
+              px = (int)(((uint64_t)r[1] * (uint32_t)(W - 1)) >> 32);
+              pc = (int)(r[2] & 1u);
+            }
+            if (pc == c) oth[py * W + px] = pass ? 0.f : 1.f;
+          }
+          __syncthreads();
+        }
+        for (int i = tid; i < HW; i += nt) cur[i] = __fadd_rn(__fmul_rn(ra, clip01(oth[i])), __fmul_rn(rb, cur[i]));
+        break;
+      }
+      const float* fld = inj ? (const float*)(vm.fields + op.field) : nullptr;
+      for (int i = tid; i < HW; i += nt) {
+        float x = cur[i], noisy;
+        float g = 0.f;
+        if (inj) {
+          g = fld[(size_t)i * 3 + c];
+        } else {
+          uint32_t r[4];
+          field_draw(vm.seed, slot, (uint32_t)i, (uint32_t)c, 0, r);
+          if (kind == 3) {  // Poisson(lam = clip(x)*0.8) by inversion
+            float lam = clip01(x) * 0.8f, p = expf(-lam), F = p, u = u32_to_unit(r[0]);
+            int k = 0;
+            while (u > F && k < 32) {
+              k++;
+              p *= lam / (float)k;
+              F += p;
+            }
+            g = (float)k;
+          } else {
+            g = normal_from(r[0], r[1]);
+            if (kind == 1) g *= 0.22360679774997896f;  // sqrt(var=0.05)
+          }
+        }
+        if (kind == 0)  // noise_speckle(strength 0.3): x * (1 + g*0.3)
+          noisy = clip01(__fmul_rn(x, __fadd_rn(1.f, __fmul_rn(g, 0.3f))));
+        else if (kind == 1)  // noise_gaussian(var 0.05)
+          noisy = clip01(__fadd_rn(x, g));
+        else {  // noise_poisson(peak .8, amount .5): clip(.5*clip(x) + .5*(counts/.8))
+          float xs = clip01(x);
+          noisy = clip01(__fadd_rn(__fmul_rn(0.5f, xs), __fmul_rn(0.5f, (float)((double)g / 0.8))));
+        }
+        cur[i] = __fadd_rn(__fmul_rn(ra, noisy), __fmul_rn(rb, x));
+      }
+      break;
+    }
+    case MTGV_X_GAUSS_NOISE: {  // Mutate.gaussian_noise(sigma .25): clip(img + noise)
+      const bool inj = op.field != MTGV_FIELD_PHILOX;
+      const float* fld = inj ? (const float*)(vm.fields + op.field) : nullptr;
+      const int nc = 3;
+      if (c > 2) break;
+      for (int i = tid; i < HW; i += nt) {
+        float g;
+        if (inj) {
+          g = fld[(size_t)i * nc + c];
+        } else {
+          uint32_t r[4];
+          field_draw(vm.seed, slot, (uint32_t)i, (uint32_t)c, 0, r);
+          g = normal_from(r[0], r[1]) * 0.25f;
+        }
+        cur[i] = clip01(__fadd_rn(cur[i], g));
+      }
+      break;
+    }
+    case MTGV_X_SALT_PEPPER: {  // Mutate.salt_pepper_noise: all channels, salt then pepper
+      if (c > 2) break;
+      const bool inj = op.field != MTGV_FIELD_PHILOX;
+      for (int pass = 0; pass < 2; pass++) {
+        const int npts = pass ? op.n_field2 : op.n_field;
+        const int32_t* pts = inj ? (const int32_t*)(vm.fields + (pass ? op.field2 : op.field)) : nullptr;
+        for (int k = tid; k < npts; k += nt) {
+          int py, px;
+          if (inj) {
+            py = pts[2 * k], px = pts[2 * k + 1];
+          } else {
+            uint32_t r[4];
+            field_draw(vm.seed, slot, (uint32_t)k, 0, 10 + pass, r);
+            py = (int)(((uint64_t)r[0] * (uint32_t)(H - 1)) >> 32);
+            px = (int)(((uint64_t)r[1] * (uint32_t)(W - 1)) >> 32);
+          }
+          cur[py * W + px] = pass ? 0.f : 1.f;
+        }
+        __syncthreads();
+      }
+      break;
+    }
+    case MTGV_X_ERASE: {  // Mutate.random_erasing
+      if (c > 2) break;
+      const int y0 = op.i[0], y1 = op.i[1], x0 = op.i[2], x1 = op.i[3], mode = op.i[4];
+      const int bw = x1 - x0, n = (y1 - y0) * bw;
+      float fill = op.f[c];
+      if (mode == 4) {  // block mean (float32)
+        float part = 0.f;
+        for (int k = tid; k < n; k += nt) part += cur[(y0 + k / bw) * W + x0 + k % bw];
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __syncthreads();
+        if ((tid & 31) == 0) oth[tid >> 5] = part;
+        __syncthreads();
+        float tot = 0.f;
+        for (int k = 0; k < (nt >> 5); k++) tot += oth[k];
+        fill = tot / (float)n;
+        __syncthreads();
+      }
+      const bool inj = op.field != MTGV_FIELD_PHILOX;
+      const float* fld = (mode == 0 && inj) ? (const float*)(vm.fields + op.field) : nullptr;
+      for (int k = tid; k < n; k += nt) {
+        float v = fill;
+        if (mode == 0) {
+          if (inj) {
+            v = fld[(size_t)k * 3 + c];
+          } else {
+            uint32_t r[4];
+            field_draw(vm.seed, slot, (uint32_t)k, (uint32_t)c, 3, r);
+            v = u32_to_unit(r[0]);
+          }
+        }
+        cur[(y0 + k / bw) * W + x0 + k % bw] = v;
+      }
+      break;
+    }
+    case MTGV_X_CUTOUT: {  // Mutate.cutout: 8 holes [y-4,y+4)x[x-4,x+4) -> 0
+      if (c > 2) break;
+      for (int k = tid; k < 8 * 64; k += nt) {
+        int hole = k >> 6, dy = (k >> 3) & 7, dx = k & 7;
+        int y = op.i[2 * hole] - 4 + dy, x = op.i[2 * hole + 1] - 4 + dx;
+        if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) cur[y * W + x] = 0.f;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------ //
+// INTER_AREA tables in shared memory                                                    //
+// ------------------------------------------------------------------------------------ //
+
+struct AreaTabs {
+  int* xs; int* xn; float* xw;  // per destination column: first source index, tap count, weights[8]
+  int* ys; int* yn; float* yw;
+};
+
+// tables for destination indices [d0, d0+count) of a ssize -> dsize INTER_AREA resize
+__device__ void build_area_axis(int* s, int* n, float* w, int ssize, int dsize, int d0, int count) {
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    int st;
+    float ww[kAreaMaxTaps];
+    int nn = area_taps(ssize, dsize, d0 + k, &st, ww);
+    s[k] = st;
+    n[k] = nn;
+    for (int j = 0; j < kAreaMaxTaps; j++) w[k * kAreaMaxTaps + j] = j < nn ? ww[j] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// stage F0: card -> area-resized plane (crop_to_size(pad=True) / remove_border_resized)  //
+// ------------------------------------------------------------------------------------ //
+
+struct EncLaunch {
+  const mtgv_enc_params* params;
+  int n;
+  const uint8_t* card_planes;
+  int card_pitch;
+  const uint8_t* bg_planes;
+  const int64_t* bg_off;
+  const float* alpha0;
+  float* alpha_scratch;
+  int* sync_words;
+  void* out;
+  int out_dtype;
+  const uint32_t* fields;
+};
+
+__device__ void stage_card_area(float* dst, const mtgv_enc_params& sp, const uint8_t* __restrict__ plane, int pitch,
+                                const float* lut, const AreaTabs& t) {
+  const int OH = sp.out_h, OW = sp.out_w;
+  const bool flip_src = sp.upsidedown && sp.kind == MTGV_KIND_VIRTUAL;   // rot180 of the card before masking
+  const bool flip_dst = sp.upsidedown && sp.kind == MTGV_KIND_CROPPED;   // rot180 of the resized crop
+  for (int i = threadIdx.x; i < OH * OW; i += blockDim.x) {
+    int y = i / OW, x = i % OW;
+    int ry = y - sp.fg_y0, rx = x - sp.fg_x0;
+    float v = 0.f;
+    if ((unsigned)ry < (unsigned)sp.fg_rh && (unsigned)rx < (unsigned)sp.fg_rw) {
+      const int y0 = t.ys[ry], ny = t.yn[ry], x0 = t.xs[rx], nx = t.xn[rx];
+      const float* wx = t.xw + rx * kAreaMaxTaps;
+      const float* wy = t.yw + ry * kAreaMaxTaps;
+      float sum = 0.f;
+      for (int j = 0; j < ny; j++) {
+        int sy = sp.src_y0 + y0 + j;
+        if (flip_src) sy = sp.card_h - 1 - sy;
+        const uint8_t* row = plane + (size_t)sy * pitch;
+        float h = 0.f;
+        for (int k = 0; k < nx; k++) {
+          int sx = sp.src_x0 + x0 + k;
+          if (flip_src) sx = sp.card_w - 1 - sx;
+          h = __fadd_rn(h, __fmul_rn(lut[__ldg(row + sx)], wx[k]));
+        }
+        sum = j == 0 ? __fmul_rn(wy[0], h) : __fadd_rn(sum, __fmul_rn(wy[j], h));
+      }
+      v = clip01(sum);
+    }
+    int o = flip_dst ? (OH - 1 - y) * OW + (OW - 1 - x) : i;
+    dst[o] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// background chain + composite (make_bg + rgba_over_rgb)                                //
+// ------------------------------------------------------------------------------------ //
+
+struct BgCtx {
+  const uint8_t* src;
+  int h, w, pitch, fh, fv, nh, nw, bw0;
+  const double* rinv;
+  const double* winv;
+  const int *adelta, *bdelta, *rowX, *rowY;
+  const float* lut;
+  const float* rtile;
+  int rx0, ry0, rtw, rth;
+};
+
+__device__ __forceinline__ float bg_src(const BgCtx& b, int y, int x) {
+  if ((unsigned)y >= (unsigned)b.h || (unsigned)x >= (unsigned)b.w) return 0.f;  // BORDER_CONSTANT
+  int yy = b.fv ? b.h - 1 - y : y, xx = b.fh ? b.w - 1 - x : x;                   // cv2.flip folded in
+  return b.lut[__ldg(b.src + (size_t)yy * b.pitch + xx)];
+}
+
+// one pixel of uimg.rotate_bounded's warpAffine output (canvas nh x nw)
+__device__ __forceinline__ float bg_rot(const BgCtx& b, int ry, int rx) {
+  int X = (b.rowX[ry] + b.adelta[rx]) >> 5, Y = (b.rowY[ry] + b.bdelta[rx]) >> 5;
+  int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+  float v0 = bg_src(b, sy, sx), v1 = bg_src(b, sy, sx + 1), v2 = bg_src(b, sy + 1, sx), v3 = bg_src(b, sy + 1, sx + 1);
+  return bilinear_weights_sum(v0, v1, v2, v3, X & 31, Y & 31);
+}
+
+__device__ __forceinline__ float bg_rot_cached(const BgCtx& b, int ry, int rx) {
+  if ((unsigned)ry >= (unsigned)b.nh || (unsigned)rx >= (unsigned)b.nw) return 0.f;
+  int ty = ry - b.ry0, tx = rx - b.rx0;
+  if ((unsigned)ty < (unsigned)b.rth && (unsigned)tx < (unsigned)b.rtw) return b.rtile[ty * b.rtw + tx];
+  return bg_rot(b, ry, rx);  // outside the staged tile: recompute (keeps tiling a pure optimisation)
+}
+
+// one pixel of Mutate.warp_inv's warpPerspective output
+__device__ __forceinline__ float bg_warp(const BgCtx& b, int wy, int wx) {
+  int X, Y;
+  persp_coord(b.winv, wx, wy, b.bw0, &X, &Y);
+  int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+  float v0 = bg_rot_cached(b, sy, sx), v1 = bg_rot_cached(b, sy, sx + 1);
+  float v2 = bg_rot_cached(b, sy + 1, sx), v3 = bg_rot_cached(b, sy + 1, sx + 1);
+  return bilinear_weights_sum(v0, v1, v2, v3, X & 31, Y & 31);
+}
+
+struct TileInfo {
+  int rx0, ry0, rtw, rth;
+};
+
+// cur holds the finished foreground plane; on return cur = clip(bg*(1-a) + fg*a).
+// `scratch` is the other plane (HW floats): int tables | warp tile | rotate tile.
+__device__ void stage_bg_composite(float* cur, float* scratch, const mtgv_enc_params& sp, int chan,
+                                   const uint8_t* __restrict__ bgplane, int pitch, float* lut, const AreaTabs& t,
+                                   const float* __restrict__ alpha, TileInfo* s_tile) {
+  const int OH = sp.out_h, OW = sp.out_w, HW = OH * OW;
+  const int nh = sp.rot_nh, nw = sp.rot_nw;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  // LUT: uint8 -> float32/255 -> elementwise ops scheduled before the geometric group
+  for (int b = tid; b < 256; b += nt) {
+    float v = __fdiv_rn((float)b, 255.f);
+    for (int k = 0; k < sp.n_pre; k++) {
+      const mtgv_x_op& op = sp.ops[sp.n_fg + k];
+      if ((op.i[0] >> chan) & 1) {
+        v = __fadd_rn(__fmul_rn(op.f[chan], v), op.f[4 + chan]);
+        if (op.i[1]) v = clip01(v);
+      }
+    }
+    lut[b] = v;
+  }
+  int* adelta = (int*)scratch;
+  int* bdelta = adelta + nw;
+  int* rowX = bdelta + nw;
+  int* rowY = rowX + nh;
+  float* wtile = (float*)(rowY + nh);
+  float* rtile = wtile + kWTileCap;
+  const int rcap = HW - 2 * (nw + nh) - kWTileCap;
+  for (int x = tid; x < nw; x += nt) {
+    adelta[x] = affine_col_delta(sp.rot_inv[0], x);
+    bdelta[x] = affine_col_delta(sp.rot_inv[3], x);
+  }
+  for (int y = tid; y < nh; y += nt) {
+    rowX[y] = affine_row_origin(sp.rot_inv[1], sp.rot_inv[2], y);
+    rowY[y] = affine_row_origin(sp.rot_inv[4], sp.rot_inv[5], y);
+  }
+  // crop_to_size: INTER_AREA (nh,nw)->(bg_rh,bg_rw), centre crop at (bg_y0,bg_x0)
+  build_area_axis(t.xs, t.xn, t.xw, nw, sp.bg_rw, sp.bg_x0, OW);
+  build_area_axis(t.ys, t.yn, t.yw, nh, sp.bg_rh, sp.bg_y0, OH);
+
+  BgCtx b;
+  b.src = bgplane; b.h = sp.bg_h; b.w = sp.bg_w; b.pitch = pitch; b.fh = sp.flip_h; b.fv = sp.flip_v;
+  b.nh = nh; b.nw = nw; b.bw0 = persp_block_w(nh, nw);
+  b.rinv = sp.rot_inv; b.winv = sp.winv;
+  b.adelta = adelta; b.bdelta = bdelta; b.rowX = rowX; b.rowY = rowY; b.lut = lut; b.rtile = rtile;
+
+  // tile shape: shrink until the warp_inv window of a tile fits the staging buffer
+  int TR = 16, TC = 32;
+  {
+    double sy = (double)nh / sp.bg_rh, sx = (double)nw / sp.bg_rw;
+    while (TR * TC > 1) {
+      int wh = (int)(TR * sy) + 3, ww = (int)(TC * sx) + 3;
+      if (wh * ww <= kWTileCap) break;
+      if (TC * sx >= TR * sy && TC > 1) TC >>= 1; else if (TR > 1) TR >>= 1; else TC >>= 1;
+    }
+  }
+  const int n_post = sp.n_post;
+  const mtgv_x_op* post = sp.ops + sp.n_fg + sp.n_pre;
+  __syncthreads();
+
+  for (int ty0 = 0; ty0 < OH; ty0 += TR) {
+    for (int tx0 = 0; tx0 < OW; tx0 += TC) {
+      const int ty1 = min(ty0 + TR, OH), tx1 = min(tx0 + TC, OW);
+      const int wy0 = t.ys[ty0], wy1 = t.ys[ty1 - 1] + t.yn[ty1 - 1];
+      const int wx0 = t.xs[tx0], wx1 = t.xs[tx1 - 1] + t.xn[tx1 - 1];
+      const int WH = wy1 - wy0, WW = wx1 - wx0;
+      if (tid == 0) {
+        // bounding box, in rotate-canvas pixels, of the window's image under the inverse homography
+        int minx = 1 << 30, maxx = -(1 << 30), miny = 1 << 30, maxy = -(1 << 30);
+        for (int k = 0; k < 4; k++) {
+          int X, Y;
+          persp_coord(b.winv, (k & 1) ? wx1 - 1 : wx0, (k & 2) ? wy1 - 1 : wy0, b.bw0, &X, &Y);
+          int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+          minx = min(minx, sx); maxx = max(maxx, sx); miny = min(miny, sy); maxy = max(maxy, sy);
+        }
+        int x0 = max(minx - 1, 0), x1 = min(maxx + 3, nw), y0 = max(miny - 1, 0), y1 = min(maxy + 3, nh);
+        TileInfo ti;
+        ti.rx0 = x0; ti.ry0 = y0; ti.rtw = max(x1 - x0, 0); ti.rth = max(y1 - y0, 0);
+        if ((long long)ti.rtw * ti.rth > rcap || WH * WW > kWTileCap) { ti.rtw = 0; ti.rth = 0; }
+        *s_tile = ti;
+      }
+      __syncthreads();
+      b.rx0 = s_tile->rx0; b.ry0 = s_tile->ry0; b.rtw = s_tile->rtw; b.rth = s_tile->rth;
+      // rotate_bounded output for the tile's footprint
+      {
+        const int n = b.rtw * b.rth;
+        for (int k = tid; k < n; k += nt) rtile[k] = bg_rot(b, b.ry0 + k / b.rtw, b.rx0 + k % b.rtw);
+      }
+      __syncthreads();
+      const bool staged_w = WH * WW <= kWTileCap;
+      if (staged_w) {
+        // warp_inv output + elementwise ops scheduled after the geometric group
+        for (int k = tid; k < WH * WW; k += nt) {
+          float v = bg_warp(b, wy0 + k / WW, wx0 + k % WW);
+          for (int q = 0; q < n_post; q++) {
+            if ((post[q].i[0] >> chan) & 1) {
+              v = __fadd_rn(__fmul_rn(post[q].f[chan], v), post[q].f[4 + chan]);
+              if (post[q].i[1]) v = clip01(v);
+            }
+          }
+          wtile[k] = v;
+        }
+      }
+      __syncthreads();
+      // INTER_AREA reduction, clip, alpha composite (util/image.py:278-289)
+      const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
+      for (int k = tid; k < npx; k += nt) {
+        const int y = ty0 + k / tw, x = tx0 + k % tw;
+        const int y0 = t.ys[y], ny = t.yn[y], x0 = t.xs[x], nx = t.xn[x];
+        const float* wx = t.xw + x * kAreaMaxTaps;
+        const float* wy = t.yw + y * kAreaMaxTaps;
+        float sum = 0.f;
+        for (int j = 0; j < ny; j++) {
+          float h = 0.f;
+          for (int i = 0; i < nx; i++) {
+            float v;
+            if (staged_w) {
+              v = wtile[(y0 + j - wy0) * WW + (x0 + i - wx0)];
+            } else {
+              v = bg_warp(b, y0 + j, x0 + i);
+              for (int q = 0; q < n_post; q++) {
+                if ((post[q].i[0] >> chan) & 1) {
+                  v = __fadd_rn(__fmul_rn(post[q].f[chan], v), post[q].f[4 + chan]);
+                  if (post[q].i[1]) v = clip01(v);
+                }
+              }
+            }
+            h = __fadd_rn(h, __fmul_rn(v, wx[i]));
+          }
+          sum = j == 0 ? __fmul_rn(wy[0], h) : __fadd_rn(sum, __fmul_rn(wy[j], h));
+        }
+        const float bgv = clip01(sum);
+        const int o = y * OW + x;
+        const float a = __ldcg(alpha + o);
+        const float fgv = cur[o];
+        cur[o] = clip01(__fadd_rn(__fmul_rn(bgv, __fsub_rn(1.f, a)), __fmul_rn(fgv, a)));
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// plane store (subsystem 5): NCHW fp16 / uint8 / fp32, 16-byte vectors                  //
+// ------------------------------------------------------------------------------------ //
+
+__device__ void store_plane(const float* __restrict__ P, int HW, void* out, size_t plane_index, int dtype) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (dtype == MTGV_OUT_F16) {
+    __half* o = (__half*)out + plane_index * HW;
+    if ((HW & 7) == 0) {
+      for (int i = tid * 8; i < HW; i += nt * 8) {
+        __half2 h0 = __floats2half2_rn(P[i], P[i + 1]), h1 = __floats2half2_rn(P[i + 2], P[i + 3]);
+        __half2 h2 = __floats2half2_rn(P[i + 4], P[i + 5]), h3 = __floats2half2_rn(P[i + 6], P[i + 7]);
+        uint4 v;
+        v.x = *(uint32_t*)&h0; v.y = *(uint32_t*)&h1; v.z = *(uint32_t*)&h2; v.w = *(uint32_t*)&h3;
+        *(uint4*)(o + i) = v;
+      }
+    } else {
+      for (int i = tid; i < HW; i += nt) o[i] = __float2half_rn(P[i]);
+    }
+  } else if (dtype == MTGV_OUT_U8) {
+    uint8_t* o = (uint8_t*)out + plane_index * HW;
+    if ((HW & 15) == 0) {
+      for (int i = tid * 16; i < HW; i += nt * 16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint32_t acc = 0;
+#pragma unroll
+          for (int r = 0; r < 4; r++) acc |= (uint32_t)__float2int_rn(clip01(P[i + 4 * q + r]) * 255.f) << (8 * r);
+          w[q] = acc;
+        }
+        *(uint4*)(o + i) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      for (int i = tid; i < HW; i += nt) o[i] = (uint8_t)__float2int_rn(clip01(P[i]) * 255.f);
+    }
+  } else {
+    float* o = (float*)out + plane_index * HW;
+    for (int i = tid; i < HW; i += nt) o[i] = P[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// the persistent encoder kernel                                                         //
+// ------------------------------------------------------------------------------------ //
+
+__device__ __forceinline__ bool op_touches_alpha(const mtgv_x_op& op) {
+  switch (op.code) {
+    case MTGV_X_ELEM: return (op.i[0] >> 3) & 1;
+    case MTGV_X_DOWNUP:
+    case MTGV_X_WARP_PERSP:
+    case MTGV_X_WARP_AFFINE: return true;
+    default: return false;
+  }
+}
+
+struct SmemLayout {
+  float* P0; float* P1; float* lut; AreaTabs tabs; mtgv_enc_params* sp; TileInfo* tile; int* item;
+};
+
+__host__ __device__ inline size_t enc_smem_bytes(int OH, int OW) {
+  size_t HW = (size_t)OH * OW;
+  size_t b = 2 * HW * 4 + 256 * 4;
+  b += (size_t)OW * (8 + 4 * kAreaMaxTaps) + (size_t)OH * (8 + 4 * kAreaMaxTaps);
+  b = (b + 15) & ~(size_t)15;
+  b += sizeof(mtgv_enc_params);
+  b = (b + 15) & ~(size_t)15;
+  b += 64;
+  return b;
+}
+
+__device__ inline SmemLayout carve(unsigned char* raw, int OH, int OW) {
+  SmemLayout s;
+  size_t HW = (size_t)OH * OW;
+  float* f = (float*)raw;
+  s.P0 = f; f += HW;
+  s.P1 = f; f += HW;
+  s.lut = f; f += 256;
+  s.tabs.xs = (int*)f; f += OW;
+  s.tabs.xn = (int*)f; f += OW;
+  s.tabs.xw = f; f += (size_t)OW * kAreaMaxTaps;
+  s.tabs.ys = (int*)f; f += OH;
+  s.tabs.yn = (int*)f; f += OH;
+  s.tabs.yw = f; f += (size_t)OH * kAreaMaxTaps;
+  size_t off = ((unsigned char*)f - raw + 15) & ~(size_t)15;
+  s.sp = (mtgv_enc_params*)(raw + off);
+  off = (off + sizeof(mtgv_enc_params) + 15) & ~(size_t)15;
+  s.tile = (TileInfo*)(raw + off);
+  s.item = (int*)(raw + off + 32);
+  return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, int OW) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemLayout S = carve(smem_raw, OH, OW);
+  const int tid = threadIdx.x, nt = blockDim.x, HW = OH * OW;
+  int* counter = L.sync_words;
+  int* flags = L.sync_words + 1;
+
+  for (;;) {
+    if (tid == 0) *S.item = atomicAdd(counter, 1);
+    __syncthreads();
+    const int item = *S.item;
+    if (item >= 4 * L.n) break;
+    const int s = item >> 2, plane = (item & 3) - 1;  // -1: alpha plane, 0..2: R,G,B
+    {  // stage the sample's parameters
+      const uint32_t* src = (const uint32_t*)(L.params + s);
+      uint32_t* dst = (uint32_t*)S.sp;
+      for (int k = tid; k < (int)(sizeof(mtgv_enc_params) / 4); k += nt) dst[k] = src[k];
+    }
+    __syncthreads();
+    const mtgv_enc_params& sp = *S.sp;
+    const bool bad = sp.status != 0 || sp.out_h != OH || sp.out_w != OW;
+    bool alpha_static = true;
+    for (int k = 0; k < sp.n_fg; k++) alpha_static = alpha_static && !op_touches_alpha(sp.ops[k]);
+
+    if (plane < 0) {
+      // ---- alpha plane: static rounded-rect alpha through the geometric foreground ops ----
+      if (!bad && sp.kind == MTGV_KIND_VIRTUAL && !alpha_static) {
+        for (int i = tid; i < HW; i += nt) S.P0[i] = L.alpha0[i];
+        __syncthreads();
+        Vm vm{{S.P0, S.P1}, 0, OH, OW, 3, L.fields, sp.seed};
+        for (int k = 0; k < sp.n_fg; k++) vm_run_op(vm, sp.ops[k], k);
+        float* dst = L.alpha_scratch + (size_t)s * HW;
+        const float* srcp = vm.cur_p();
+        for (int i = tid; i < HW; i += nt) __stcg(dst + i, srcp[i]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(flags + s, 1);
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- colour plane ----
+    if (bad) {
+      for (int i = tid; i < HW; i += nt) S.P0[i] = 0.f;
+      __syncthreads();
+      store_plane(S.P0, HW, L.out, (size_t)s * 3 + plane, L.out_dtype);
+      __syncthreads();
+      continue;
+    }
+    const uint8_t* cplane = L.card_planes + ((size_t)sp.card * 3 + plane) * sp.card_h * L.card_pitch;
+    for (int b = tid; b < 256; b += nt) S.lut[b] = __fdiv_rn((float)b, 255.f);  // img_float32: u8/255
+    build_area_axis(S.tabs.xs, S.tabs.xn, S.tabs.xw, sp.src_w, sp.fg_rw, 0, sp.fg_rw);
+    build_area_axis(S.tabs.ys, S.tabs.yn, S.tabs.yw, sp.src_h, sp.fg_rh, 0, sp.fg_rh);
+    __syncthreads();
+    stage_card_area(S.P0, sp, cplane, L.card_pitch, S.lut, S.tabs);
+    __syncthreads();
+    Vm vm{{S.P0, S.P1}, 0, OH, OW, plane, L.fields, sp.seed};
+    if (sp.kind == MTGV_KIND_VIRTUAL) {
+      for (int k = 0; k < sp.n_fg; k++) vm_run_op(vm, sp.ops[k], k);
+      const float* alpha = L.alpha0;
+      if (!alpha_static) {
+        alpha = L.alpha_scratch + (size_t)s * HW;
+        if (tid == 0)
+          while (ld_acquire(flags + s) == 0) __nanosleep(200);
+        __syncthreads();
+      }
+      const int bpitch = (sp.bg_w + 15) & ~15;
+      const uint8_t* bplane = L.bg_planes + L.bg_off[sp.bg] + (size_t)plane * sp.bg_h * bpitch;
+      stage_bg_composite(vm.cur_p(), vm.oth_p(), sp, plane, bplane, bpitch, S.lut, S.tabs, alpha, S.tile);
+      const int base = sp.n_fg + sp.n_pre + sp.n_post;
+      for (int k = 0; k < sp.n_vrtl; k++) vm_run_op(vm, sp.ops[base + k], base + k);
+    }
+    store_plane(vm.cur_p(), HW, L.out, (size_t)s * 3 + plane, L.out_dtype);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// static alpha: pad(INTER_AREA(round_rect_mask)) for (card_hw -> out_hw)                //
+// ------------------------------------------------------------------------------------ //
+
+__global__ void k_static_alpha(const float* __restrict__ mask, int ch, int cw, int OH, int OW, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OH * OW) return;
+  int rh, rw, y0, x0;
+  if (ch == OH && cw == OW) { rh = OH; rw = OW; y0 = x0 = 0; }
+  else crop_geometry(ch, cw, OH, OW, true, &rh, &rw, &y0, &x0);
+  int ry = i / OW - y0, rx = i % OW - x0;
+  float v = 0.f;
+  if ((unsigned)ry < (unsigned)rh && (unsigned)rx < (unsigned)rw) {
+    int sy0, sx0;
+    float wy[kAreaMaxTaps], wx[kAreaMaxTaps];
+    int ny = area_taps(ch, rh, ry, &sy0, wy), nx = area_taps(cw, rw, rx, &sx0, wx);
+    float sum = 0.f;
+    for (int j = 0; j < ny; j++) {
+      float h = 0.f;
+      for (int k = 0; k < nx; k++) h = __fadd_rn(h, __fmul_rn(mask[(size_t)(sy0 + j) * cw + sx0 + k], wx[k]));
+      sum = j == 0 ? __fmul_rn(wy[0], h) : __fadd_rn(sum, __fmul_rn(wy[j], h));
+    }
+    v = clip01(sum);
+  }
+  out[i] = v;
+}
+
+int enc_build_static_alpha(mtgv_ctx* ctx, cudaStream_t st) {
+  if (!ctx->cfg_set || !ctx->mask_enc) return MTGV_OK;
+  const int OH = ctx->cfg.out_h, OW = ctx->cfg.out_w;
+  if (ctx->alpha0) cudaFree(ctx->alpha0);
+  MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->alpha0, (size_t)OH * OW * 4));
+  k_static_alpha<<<(OH * OW + 255) / 256, 256, 0, st>>>(ctx->mask_enc, ctx->card_h, ctx->card_w, OH, OW, ctx->alpha0);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+// ------------------------------------------------------------------------------------ //
+// pool ingest: HWC uint8 -> planar rows padded to 16 B                                  //
+// ------------------------------------------------------------------------------------ //
+
+__global__ void k_planarize(const uint8_t* __restrict__ hwc, uint8_t* __restrict__ planes, int h, int w, int pitch) {
+  const size_t img = blockIdx.y;
+  const uint8_t* src = hwc + img * (size_t)h * w * 3;
+  uint8_t* dst = planes + img * (size_t)3 * h * pitch;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)h * pitch; i += (size_t)gridDim.x * blockDim.x) {
+    int y = (int)(i / pitch), x = (int)(i % pitch);
+#pragma unroll
+    for (int c = 0; c < 3; c++) dst[((size_t)c * h + y) * pitch + x] = x < w ? src[((size_t)y * w + x) * 3 + c] : 0;
+  }
+}
+
+int pool_planarize(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* planes, int n, int h, int w, int pitch, cudaStream_t st) {
+  if (n <= 0) return MTGV_OK;
+  for (int i0 = 0; i0 < n; i0 += 32768) {
+    int cnt = n - i0 < 32768 ? n - i0 : 32768;
+    dim3 grid(64, cnt);
+    k_planarize<<<grid, 256, 0, st>>>(hwc + (size_t)i0 * h * w * 3, planes + (size_t)i0 * 3 * h * pitch, h, w, pitch);
+    ctx->launches++;
+  }
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+// ------------------------------------------------------------------------------------ //
+// subsystem (1): tape -> params                                                         //
+// ------------------------------------------------------------------------------------ //
+
+__global__ void k_expand(const mtgv_enc_tape* tape, int n, const mtgv_enc_config* cfg, PoolMeta pm, mtgv_enc_params* params,
+                         int64_t* labels) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  expand_encoder_sample(&tape[s], cfg, pm, &params[s]);
+  if (labels) {
+    int card = params[s].card;
+    bool ok = params[s].status == 0 && card >= 0 && card < pm.n_cards;
+    for (int k = 0; k < 3; k++) labels[(size_t)s * 3 + k] = ok ? (int64_t)pm.labels3[card * 3 + k] : -1;
+  }
+}
+
+static PoolMeta pool_meta(const mtgv_ctx* ctx) {
+  PoolMeta pm;
+  pm.card_h = ctx->card_h; pm.card_w = ctx->card_w; pm.n_cards = ctx->n_cards; pm.n_bgs = ctx->n_bgs;
+  pm.labels3 = ctx->labels3; pm.grp_off = ctx->grp_off; pm.grp_mem = ctx->grp_mem; pm.bg_hw = ctx->bg_hw;
+  return pm;
+}
+
+int enc_expand(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels, cudaStream_t st) {
+  if (n <= 0) return MTGV_OK;
+  k_expand<<<(n + 63) / 64, 64, 0, st>>>(tape, n, ctx->cfg_dev, pool_meta(ctx), params, labels);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+// ------------------------------------------------------------------------------------ //
+// production sampler (Philox): what _random_image_batch/_make_image_batch/make_virtual   //
+// draw from `random` / `np.random`, one thread per pair           //
+// ------------------------------------------------------------------------------------ //
+
+struct Rng {
+  Philox ph;
+  uint32_t c0, c1, c2;
+  uint32_t ctr;
+  uint32_t buf[4];
+  int have;
+  __device__ Rng(uint64_t seed, uint64_t index, uint32_t stream) {
+    ph.key[0] = (uint32_t)seed; ph.key[1] = (uint32_t)(seed >> 32);
+    c0 = (uint32_t)index; c1 = (uint32_t)(index >> 32); c2 = stream; ctr = 0; have = 0;
+  }
+  __device__ uint32_t u32() {
+    if (!have) { ph(c0, c1, c2, ctr++, buf); have = 4; }
+    return buf[--have];
+  }
+  __device__ double uniform() {  // 53-bit like random.random()
+    uint32_t a = u32() >> 5, b = u32() >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+  }
+  __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * uniform(); }
+  __device__ int below(int n) { return (int)(((uint64_t)u32() * (uint32_t)n) >> 32); }
+};
+
+__device__ void tape_op_init(mtgv_tape_op* o, int code) {
+  o->code = code; o->n_field = o->n_field2 = 0; o->_pad = 0;
+  for (int k = 0; k < 16; k++) o->i[k] = 0;
+  for (int k = 0; k < 8; k++) o->d[k] = 0.0;
+  o->field = o->field2 = MTGV_FIELD_PHILOX;
+}
+
+__device__ int sample_fade(Rng& r, mtgv_tape_op* o) {  // ApplyChoice(fade_black, fade_white, brightness_contrast, None)
+  int c = r.below(4);
+  if (c == 3) return 0;
+  if (c == 0) { tape_op_init(o, MTGV_OP_FADE_BLACK); o->d[0] = r.uniform(); }
+  else if (c == 1) { tape_op_init(o, MTGV_OP_FADE_WHITE); o->d[0] = r.uniform(); }
+  else { tape_op_init(o, MTGV_OP_BC); o->d[0] = r.uniform(-0.2, 0.2); o->d[1] = r.uniform(-0.2, 0.2); }
+  return 1;
+}
+__device__ int sample_tint(Rng& r, mtgv_tape_op* o) {  // ApplyChoice(tint, None)
+  if (r.below(2) != 0) return 0;
+  tape_op_init(o, MTGV_OP_TINT);
+  for (int k = 0; k < 3; k++) o->d[k] = r.uniform();
+  return 1;
+}
+__device__ int sample_downup(Rng& r, mtgv_tape_op* o) {  // ApplyChoice(downscale_upscale, None, None, None)
+  if (r.below(4) != 0) return 0;
+  tape_op_init(o, MTGV_OP_DOWNUP);
+  o->i[0] = r.below(3); o->i[1] = r.below(3); o->i[2] = r.below(3);
+  return 1;
+}
+__device__ int sample_noise6(Rng& r, mtgv_tape_op* o, int H, int W) {
+  int c = r.below(6);
+  switch (c) {
+    case 0: tape_op_init(o, MTGV_OP_NOISE); o->i[0] = r.below(4); o->d[0] = r.uniform(); return 1;
+    case 1: tape_op_init(o, MTGV_OP_GAUSS_NOISE); return 1;
+    case 2: tape_op_init(o, MTGV_OP_SALT_PEPPER); return 1;
+    case 3: {
+      tape_op_init(o, MTGV_OP_ERASE);
+      o->d[0] = r.uniform(0.2, 0.4); o->d[1] = r.uniform(1.0, 3.0); o->d[2] = r.uniform();
+      double area = o->d[0] * (double)(H * W), aspect = o->d[1];
+      if (o->d[2] < 0.5) aspect = 1.0 / aspect;
+      int bw = (int)sqrt(area / aspect), bh = (int)sqrt(area * aspect);
+      o->i[4] = 1; o->i[5] = bw; o->i[6] = bh;
+      int mx = -(bw / 2), Mx = W + bw / 2, my = -(bh / 2), My = H + bh / 2;
+      if (Mx <= mx || My <= my) { o->i[0] = 0; return 1; }
+      int cx = mx + r.below(Mx - mx), cy = my + r.below(My - my);
+      o->i[1] = cx; o->i[2] = cy;
+      int x0 = max(0, cx - bw / 2), y0 = max(0, cy - bh / 2), x1 = min(W, cx + bw / 2), y1 = min(H, cy + bh / 2);
+      if (y1 <= y0 || x1 <= x0) { o->i[0] = 1; return 1; }
+      o->i[0] = 2;
+      o->i[3] = r.below(5);
+      if (o->i[3] == 1) for (int k = 0; k < 3; k++) o->d[3 + k] = r.uniform();
+      return 1;
+    }
+    case 4:
+      tape_op_init(o, MTGV_OP_CUTOUT);
+      for (int k = 0; k < 8; k++) { o->i[2 * k] = r.below(H); o->i[2 * k + 1] = r.below(W); }
+      return 1;
+    default: return 0;
+  }
+}
+
+__device__ void shuffle_n(Rng& r, int* idx, int n) {  // random.shuffle (Fisher-Yates from the end)
+  for (int i = n - 1; i >= 1; i--) { int j = r.below(i + 1); int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
+}
+
+__device__ void sample_virtual(Rng& r, mtgv_enc_tape* t, const mtgv_enc_config* cfg) {
+  const int H = cfg->out_h, W = cfg->out_w;
+  t->upsidedown = cfg->half_upsidedown ? (r.below(2) == 0) : 0;
+  int n = 0;
+  // _RAN_FG
+  n += sample_downup(r, &t->ops[n]);
+  {
+    int c = r.below(4);
+    if (c == 0) { tape_op_init(&t->ops[n], MTGV_OP_WARP); for (int k = 0; k < 8; k++) t->ops[n].d[k] = r.uniform(); n++; }
+    else if (c == 1) {
+      mtgv_tape_op* o = &t->ops[n++];
+      tape_op_init(o, MTGV_OP_AFFINE);
+      o->d[0] = r.uniform(-5.0, 5.0); o->d[1] = r.uniform(-10.0, 10.0); o->d[2] = r.uniform(-10.0, 10.0);
+      double s = fmin(1.0 + 0.1, 1.0 / (1.0 + 0.1));
+      o->d[3] = r.uniform(s, 1.0 / s); o->d[4] = r.uniform(-0.3, 0.3);
+    } else if (c == 2) {
+      tape_op_init(&t->ops[n], MTGV_OP_PERSPECTIVE);
+      for (int k = 0; k < 8; k++) t->ops[n].d[k] = r.uniform(-0.1, 0.1);
+      n++;
+    }
+  }
+  n += sample_tint(r, &t->ops[n]);
+  n += sample_fade(r, &t->ops[n]);
+  t->n_fg = n;
+  // _RAN_BG
+  int g3[3] = {0, 1, 2};
+  shuffle_n(r, g3, 3);
+  for (int q = 0; q < 3; q++) {
+    if (g3[q] == 0) {
+      tape_op_init(&t->ops[n], MTGV_OP_FLIP);
+      t->ops[n].i[0] = r.uniform() >= 0.5; t->ops[n].i[1] = r.uniform() >= 0.5; n++;
+      tape_op_init(&t->ops[n], MTGV_OP_ROTATE); t->ops[n].d[0] = r.uniform(); n++;
+      tape_op_init(&t->ops[n], MTGV_OP_WARP_INV); for (int k = 0; k < 8; k++) t->ops[n].d[k] = r.uniform(); n++;
+    } else if (g3[q] == 1) n += sample_tint(r, &t->ops[n]);
+    else n += sample_fade(r, &t->ops[n]);
+  }
+  t->n_bg = n - t->n_fg;
+  // _RAN_VRTL
+  int g7[7] = {0, 1, 2, 3, 4, 5, 6};
+  shuffle_n(r, g7, 7);
+  const int base = n;
+  for (int q = 0; q < 7; q++) {
+    switch (g7[q]) {
+      case 0: n += sample_downup(r, &t->ops[n]); break;
+      case 1: if (r.below(3) == 0) { tape_op_init(&t->ops[n], MTGV_OP_BLUR); t->ops[n].i[0] = r.below(2) * 2 + 1; n++; } break;
+      case 2: if (r.below(3) == 0) { tape_op_init(&t->ops[n], MTGV_OP_SHARPEN); n++; } break;
+      case 3: n += sample_noise6(r, &t->ops[n], H, W); break;
+      case 4: if (r.below(2) == 0) n += sample_noise6(r, &t->ops[n], H, W); break;
+      case 5: n += sample_tint(r, &t->ops[n]); break;
+      default: n += sample_fade(r, &t->ops[n]); break;
+    }
+  }
+  t->n_vrtl = n - base;
+}
+
+__global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const mtgv_enc_config* cfg, PoolMeta pm,
+                              mtgv_enc_tape* tape) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const uint64_t g = (uint64_t)(first + i);
+  Rng sel(seed, g, 1);  // card / background selection stream (re-derivable by other samples)
+  const int card = sel.below(pm.n_cards), bg = sel.below(pm.n_bgs);
+  const int n_x = cfg->paired ? 2 : 1;
+  for (int which = 0; which < n_x; which++) {
+    mtgv_enc_tape* t = &tape[which * n_pairs + i];
+    Rng r(seed, g, 2 + which);
+    t->card = card; t->bg = bg; t->swap_choice = -1; t->upsidedown = 0;
+    t->n_fg = t->n_bg = t->n_vrtl = 0;
+    t->seed = seed ^ (0x9E3779B97F4A7C15ull * (2 * g + which + 1));
+    if (which == 1) {
+      // hard negative (encoder_train.py:217-221) and bg1 = random.choice(bg_imgs) (:224)
+      if (r.uniform() < cfg->similar_neg_prob) {
+        int m = pm.grp_off[card + 1] - pm.grp_off[card] - 1;
+        if (m > 0) t->swap_choice = r.below(m);
+      }
+      int slot = r.below(n_pairs);
+      Rng other(seed, (uint64_t)(first + slot), 1);
+      other.below(pm.n_cards);
+      t->bg = other.below(pm.n_bgs);
+    }
+    if (r.uniform() < cfg->target_is_input_prob) {
+      t->kind = MTGV_KIND_CROPPED;
+    } else {
+      t->kind = MTGV_KIND_VIRTUAL;
+      sample_virtual(r, t, cfg);
+    }
+  }
+}
+
+int enc_sample_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first, int n_pairs, mtgv_enc_tape* tape, cudaStream_t st) {
+  if (n_pairs <= 0) return MTGV_OK;
+  k_sample_tape<<<(n_pairs + 63) / 64, 64, 0, st>>>(seed, first, n_pairs, ctx->cfg_dev, pool_meta(ctx), tape);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+// ------------------------------------------------------------------------------------ //
+// batch launch                                                                          //
+// ------------------------------------------------------------------------------------ //
+
+static int ensure_scratch(mtgv_ctx* ctx, int n) {
+  const size_t HW = (size_t)ctx->cfg.out_h * ctx->cfg.out_w;
+  if ((size_t)n > ctx->alpha_cap) {
+    if (ctx->alpha_scratch) cudaFree(ctx->alpha_scratch);
+    ctx->alpha_scratch = nullptr;
+    ctx->alpha_cap = 0;
+    MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->alpha_scratch, (size_t)n * HW * 4));
+    ctx->alpha_cap = n;
+  }
+  if ((size_t)n + 1 > ctx->sync_cap) {
+    if (ctx->sync_words) cudaFree(ctx->sync_words);
+    ctx->sync_words = nullptr;
+    ctx->sync_cap = 0;
+    MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->sync_words, ((size_t)n + 1) * 4));
+    ctx->sync_cap = (size_t)n + 1;
+  }
+  return MTGV_OK;
+}
+
+int enc_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
+              cudaStream_t st) {
+  if (n <= 0) return MTGV_OK;
+  const int OH = ctx->cfg.out_h, OW = ctx->cfg.out_w;
+  const size_t smem = enc_smem_bytes(OH, OW);
+  if ((int)smem > ctx->max_smem_optin)
+    return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw too large: two float32 planes must fit in 227 KB of shared memory");
+  int rc = ensure_scratch(ctx, n);
+  if (rc) return rc;
+  MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->sync_words, 0, ((size_t)n + 1) * 4, st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+    attr_set = true;
+  }
+  EncLaunch L;
+  L.params = params; L.n = n; L.card_planes = ctx->card_planes; L.card_pitch = ctx->card_pitch;
+  L.bg_planes = ctx->bg_planes; L.bg_off = ctx->bg_off; L.alpha0 = ctx->alpha0; L.alpha_scratch = ctx->alpha_scratch;
+  L.sync_words = ctx->sync_words; L.out = out; L.out_dtype = out_dtype; L.fields = (const uint32_t*)fields;
+  int grid = 4 * n < ctx->sm_count ? 4 * n : ctx->sm_count;
+  k_encoder<<<grid, kThreads, smem, st>>>(L, OH, OW);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+__global__ void k_target_params(const int32_t* cards, int n, const mtgv_enc_config* cfg, PoolMeta pm, mtgv_enc_params* params) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  mtgv_enc_tape t;
+  t.kind = MTGV_KIND_CROPPED; t.card = cards[s]; t.swap_choice = -1; t.bg = 0; t.upsidedown = 0;
+  t.n_fg = t.n_bg = t.n_vrtl = 0; t.seed = 0;
+  mtgv_enc_config c = *cfg;
+  c.out_h = cfg->y_h; c.out_w = cfg->y_w;
+  expand_encoder_sample(&t, &c, pm, &params[s]);
+}
+
+int enc_targets(mtgv_ctx* ctx, const int32_t* cards, int n, void* out, int out_dtype, cudaStream_t st) {
+  if (n <= 0) return MTGV_OK;
+  if (ctx->cfg.y_h != ctx->cfg.out_h || ctx->cfg.y_w != ctx->cfg.out_w)
+    return fail(ctx, MTGV_ERR_LIMIT, "y_size_hw != x_size_hw is not supported yet");
+  if ((size_t)n > ctx->tmp_params_cap) {
+    if (ctx->tmp_params) cudaFree(ctx->tmp_params);
+    ctx->tmp_params = nullptr; ctx->tmp_params_cap = 0;
+    MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->tmp_params, (size_t)n * sizeof(mtgv_enc_params)));
+    ctx->tmp_params_cap = n;
+  }
+  k_target_params<<<(n + 63) / 64, 64, 0, st>>>(cards, n, ctx->cfg_dev, pool_meta(ctx), ctx->tmp_params);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return enc_batch(ctx, ctx->tmp_params, n, out, out_dtype, nullptr, st);
+}
+
+// ------------------------------------------------------------------------------------ //
+// parity / debug entries                                                                //
+// ------------------------------------------------------------------------------------ //
+
+__global__ void k_warp_perspective(const float* __restrict__ src, int sh, int sw, int c, const double* __restrict__ M,
+                                   float* __restrict__ dst, int dh, int dw) {
+  __shared__ double Mi[9];
+  const int img = blockIdx.y;
+  if (threadIdx.x == 0) invert3x3(M + (size_t)img * 9, Mi);  // cv::invert inside cv::warpPerspective
+  __syncthreads();
+  const int bw0 = persp_block_w(dh, dw);
+  const float* S = src + (size_t)img * sh * sw * c;
+  float* D = dst + (size_t)img * dh * dw * c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dh * dw; i += gridDim.x * blockDim.x) {
+    int X, Y;
+    persp_coord(Mi, i % dw, i / dw, bw0, &X, &Y);
+    int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+    bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
+    bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;
+    const float* p = S + ((size_t)sy * sw + sx) * c;
+    for (int k = 0; k < c; k++) {
+      float v0 = (y0 && x0) ? p[k] : 0.f, v1 = (y0 && x1) ? p[c + k] : 0.f;
+      float v2 = (y1 && x0) ? p[(size_t)sw * c + k] : 0.f, v3 = (y1 && x1) ? p[(size_t)sw * c + c + k] : 0.f;
+      D[(size_t)i * c + k] = bilinear_weights_sum(v0, v1, v2, v3, X & 31, Y & 31);
+    }
+  }
+}
+
+int enc_warp_perspective(mtgv_ctx* ctx, const float* src, int n, int sh, int sw, int c, const double* M, float* dst, int dh,
+                         int dw, cudaStream_t st) {
+  if (n <= 0) return MTGV_OK;
+  dim3 grid((dh * dw + 255) / 256 < 592 ? (dh * dw + 255) / 256 : 592, n);
+  k_warp_perspective<<<grid, 256, 0, st>>>(src, sh, sw, c, M, dst, dh, dw);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_run_plane_ops(float* img, int h, int w, int c, const mtgv_x_op* ops, int n_ops,
+                                                              const uint32_t* fields, uint64_t seed) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int HW = h * w;
+  float* P0 = (float*)smem_raw;
+  float* P1 = P0 + HW;
+  mtgv_x_op* sop = (mtgv_x_op*)(P1 + HW);
+  const int im = blockIdx.x / c, ch = blockIdx.x % c;
+  float* base = img + (size_t)im * HW * c;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) P0[i] = base[(size_t)i * c + ch];
+  Vm vm{{P0, P1}, 0, h, w, ch, fields, seed + (uint64_t)im};
+  __syncthreads();
+  for (int k = 0; k < n_ops; k++) {
+    for (int q = threadIdx.x; q < (int)(sizeof(mtgv_x_op) / 4); q += blockDim.x) ((uint32_t*)sop)[q] = ((const uint32_t*)(ops + k))[q];
+    __syncthreads();
+    vm_run_op(vm, *sop, k);
+  }
+  const float* r = vm.cur_p();
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) base[(size_t)i * c + ch] = r[i];
+}
+
+int enc_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops,
+                      const void* fields, uint64_t seed, cudaStream_t st) {
+  if (n <= 0) return MTGV_OK;
+  size_t smem = (size_t)2 * h * w * 4 + sizeof(mtgv_x_op) + 16;
+  if ((int)smem > ctx->max_smem_optin) return fail(ctx, MTGV_ERR_LIMIT, "image too large for the plane interpreter");
+  if (c < 1 || c > 4) return fail(ctx, MTGV_ERR_INVALID, "channels must be 1..4");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_run_plane_ops, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+    attr_set = true;
+  }
+  k_run_plane_ops<<<n * c, kThreads, smem, st>>>(img, h, w, c, ops, n_ops, (const uint32_t*)fields, seed);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+}  // namespace mtgv

@@ -293,7 +293,7 @@ def warp_affine(src: np.ndarray, A: np.ndarray, dsize_wh) -> np.ndarray:
 
 def area_tab(ssize: int, dsize: int):
     """computeResizeAreaTab: list of (dst index, src index, float32 weight)."""
-    scale = ssize / dsize
+    scale = 1.0 / (dsize / ssize)  # cv::resize passes scale = 1./inv_scale
     tab = []
     for dx in range(dsize):
         fsx1 = dx * scale
@@ -351,7 +351,7 @@ def resize_nearest(src: np.ndarray, dsize_wh) -> np.ndarray:
 
 
 def _linear_ofs(ssize: int, dsize: int):
-    scale = ssize / dsize  # double
+    scale = 1.0 / (dsize / ssize)  # double, cv::resize: 1./inv_scale
     sx = np.empty(dsize, dtype=np.int64)
     fx = np.empty(dsize, dtype=np.float32)
     for d in range(dsize):
@@ -396,7 +396,7 @@ def _cubic_coeffs(x: np.float32) -> np.ndarray:
 
 
 def _cubic_ofs(ssize: int, dsize: int):
-    scale = ssize / dsize
+    scale = 1.0 / (dsize / ssize)
     idx = np.empty((dsize, 4), dtype=np.int64)
     cf = np.empty((dsize, 4), dtype=np.float32)
     for d in range(dsize):

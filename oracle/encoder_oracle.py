@@ -514,7 +514,7 @@ def make_virtual(card_f32, bg_f32, size_hw, half_upsidedown=False, tape=None):
     virtual = rgba_over_rgb(fg, bg)
     virtual = ran_vrtl(virtual, v_ops)
     assert virtual.shape[:2] == tuple(size_hw)
-    t.update(kind="virtual", upsidedown=bool(ud), size_hw=tuple(size_hw), fg=fg_ops, bg=bg_ops, vrtl=v_ops,
+    t.update(kind="virtual", upsidedown=bool(ud), size_hw=tuple(size_hw), fg_ops=fg_ops, bg_ops=bg_ops, vrtl_ops=v_ops,
              card_hw=tuple(card_f32.shape[:2]), bg_hw=tuple(bg_f32.shape[:2]))
     return virtual
 
@@ -557,7 +557,8 @@ class BatchOracle:
         """get_similar_card (encoder_datasets.py:619-630): same-name group minus self."""
         group = [j for j in self.cards.group_of(k) if j != k]
         if group:
-            return group[_choice(len(group))]
+            c = _choice(len(group))
+            return group[c], c
         return None
 
     def make_image_batch(self, card_idx, bg_idx, *, target_in_prob=None, similar_neg_prob=None):
@@ -578,14 +579,15 @@ class BatchOracle:
             if self.paired:
                 pk, pair_img = k, card_img
                 u = random.random()
-                swapped = False
+                swapped, swap_choice = False, -1
                 if u < (similar_neg_prob or self.similar_neg_prob):
-                    j = self.similar_card(k)
-                    if j is not None:
-                        pk, pair_img, swapped = j, u8_to_f32(self.cards.images[j]), True
+                    hit = self.similar_card(k)
+                    if hit is not None:
+                        pk, swap_choice = hit
+                        pair_img, swapped = u8_to_f32(self.cards.images[pk]), True
                 b = _choice(len(bg_imgs))  # bg1 = random.choice(bg_imgs)
                 t2 = {"card": int(pk), "bg": int(bg_idx[b]), "u_similar_neg": u, "swapped": swapped,
-                      "base_card": int(k), "bg_slot": int(b)}
+                      "device_card": int(k), "swap_choice": int(swap_choice), "bg_slot": int(b)}
                 imgs["x2"].append(self._make_x(pair_img, bg_imgs[b], target_in_prob, t2))
                 tapes["x2"].append(t2)
                 lbls["x2_labels"].append(tuple(int(v) for v in self.cards.labels3[pk]))
