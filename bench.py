@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 synthetic-sample generator.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU generator (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): encoder training batches of 512 positive pairs with
+hard-negative same-name swaps, synthetic 488x680 cards and 500x375 backgrounds,
+x/x2 [512,3,192,128] fp16 NCHW + [512,3] int64 labels.  One step = one batch
+(1024 augmented x-samples) per GPU; N GPUs run N independent shards (weak scaling,
+no collective on the data path).  Metric = augmented x-samples/s, whole job.
+One JSON line is printed by rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "augmented samples/sec (encoder pairs)"
+UNIT = "x-samples/s"
+PAIRS = 512
+X_HW = (192, 128)
+CARD_HW = (680, 488)
+BG_HW = (375, 500)
+BYTES_CARD = CARD_HW[0] * CARD_HW[1] * 3
+BYTES_BG = BG_HW[0] * BG_HW[1] * 3
+BYTES_OUT_F16 = 3 * X_HW[0] * X_HW[1] * 2
+
+
+def workload_config(args, extra=None):
+    cfg = {
+        "workload": "encoder training batches: 512 positive pairs (x, x2) with hard-negative same-name swaps, "
+                    "synthetic 680x488 cards + 375x500 backgrounds -> [512,3,192,128] fp16 NCHW + int64 labels",
+        "pairs_per_step": PAIRS,
+        "x_samples_per_step_per_gpu": 2 * PAIRS,
+        "card_pool": args.pool_cards,
+        "bg_pool": args.pool_bgs,
+        "target_is_input_prob": 0.05,
+        "similar_neg_prob": 0.2,
+        "parallelism": f"{args.gpus} independent shard(s), one process per GPU, no collective",
+        "l2": "inputs larger than L2: each step reads ~1000 distinct cards (~1 GB) of a multi-GB resident pool; no flush",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------- #
+# reference arm / cpu_baseline: the oracle port on host cores                              #
+# --------------------------------------------------------------------------------------- #
+
+_CPU_STATE = {}
+
+
+def _cpu_worker(args):
+    wid, n_pairs, batch = args
+    import random
+
+    import cv2
+    import numpy as np
+
+    from oracle import encoder_oracle as EO
+
+    cv2.setNumThreads(1)
+    random.seed(1000 + wid)
+    np.random.seed(1000 + wid)
+    EO.reset_shuffle_state()
+    bo = EO.BatchOracle(_CPU_STATE["cards"], _CPU_STATE["bgs"], paired=True, targets=False, x_size_hw=X_HW,
+                        target_is_input_prob=0.05, similar_neg_prob=0.2)
+    done = 0
+    t0 = time.perf_counter()
+    while done < n_pairs:
+        b = min(batch, n_pairs - done)
+        imgs, _, _ = bo.random_image_batch(b)
+        done += b
+        assert imgs["x"].shape == (b, X_HW[0], X_HW[1], 3)
+    return 2 * done, time.perf_counter() - t0
+
+
+def cpu_generator_throughput(pairs_per_worker: int, workers: int | None = None, pool_cards: int = 64, pool_bgs: int = 64):
+    """The reference generator (oracle port: same cv2/numpy calls in the same order as
+    mtgvision/encoder_datasets.py + encoder_train.py:189-230) with one process per host core,
+    like the reference's DataLoader workers (encoder_train.py:517-523).  Returns
+    (x_samples_per_s, workers, x_samples, wall_s)."""
+    import multiprocessing as mp
+
+    from mtgvision_b200 import synth
+
+    workers = workers or os.cpu_count() or 1
+    if "cards" not in _CPU_STATE:
+        _CPU_STATE["cards"] = synth.make_card_pool(pool_cards)
+        _CPU_STATE["bgs"] = synth.make_bg_pool(pool_bgs)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker, [(w, 2, 2) for w in range(workers)])  # warm-up: imports, page-in
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(w, pairs_per_worker, 16) for w in range(workers)])
+        wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    return total / wall, workers, total, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    workers = os.cpu_count() or 1
+    pairs = max(4, args.ref_pairs_per_worker)
+    total = 0
+    t_all = time.perf_counter()
+    for step in range(args.warmup + args.steps):
+        v, workers, n, wall = cpu_generator_throughput(pairs, workers)
+        if step >= args.warmup:
+            vals.append((n, wall))
+            total += n
+    n_sum = sum(n for n, _ in vals)
+    w_sum = sum(w for _, w in vals)
+    value = n_sum / w_sum
+    sample = (f"{pairs} pairs per worker per step x {workers} workers, batch 16, pools of 64 synthetic cards/backgrounds "
+              f"(same generator as the GPU arm's pools); {n_sum} x-samples in {w_sum:.1f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * w_sum / max(1, len(vals)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, {"note": "reference CPU generator (oracle port, cv2/numpy), all host cores"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- #
+# clocks                                                                                   #
+# --------------------------------------------------------------------------------------- #
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, row in self.rows:
+            if t < t0 or t > t1 + 0.1:
+                continue
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- #
+# CUDA arm                                                                                 #
+# --------------------------------------------------------------------------------------- #
+
+
+def run_cuda(args):
+    import numpy as np
+    import torch
+
+    from mtgvision_b200 import abi, synth
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from mtgvision_b200.encoder_train import RanMtgEncDecDataset
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    # ---- resident pools (setup, untimed) ----
+    host_workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    t_setup = time.perf_counter()
+    cards = synth.make_card_pool(args.pool_cards, workers=host_workers)
+    bgs = synth.make_bg_pool(args.pool_bgs, workers=host_workers)
+    ds = RanMtgEncDecDataset(PAIRS, paired=True, targets=False, x_size_hw=X_HW, y_size_hw=X_HW, half_upsidedown=False,
+                             target_is_input_prob=0.05, similar_neg_prob=0.2,
+                             mtg=SyntheticBgFgMtgImages(pool=cards), ilsvrc=IlsvrcImages(images=bgs),
+                             device=local_rank, out_dtype="float16", seed=20261018, rank=rank, world_size=world)
+    ctx = ds.ctx
+    t_setup = time.perf_counter() - t_setup
+    n_x = 2 * PAIRS
+
+    # preallocated per-step buffers (the public API allocates through torch's caching allocator;
+    # here the same three C-ABI calls are issued with explicit events around the plane kernel)
+    total_steps = args.warmup + args.steps
+    tape = torch.empty((n_x, abi.TAPE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    params = [torch.empty((n_x, abi.PARAMS_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in range(args.steps)]
+    labels = torch.empty((n_x, 3), dtype=torch.int64, device=dev)
+    out = torch.empty((n_x, 3, X_HW[0], X_HW[1]), dtype=torch.float16, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step(i, timed_idx=None):
+        first = (i * world + rank) * PAIRS
+        ctx.sample_encoder_tape(ds.seed, first, PAIRS, out=tape)
+        p = params[timed_idx] if timed_idx is not None else params[0]
+        ctx.expand_params(tape, params=p, labels=labels)
+        if timed_idx is not None:
+            ev[timed_idx][0].record()
+        ctx.encoder_batch(p, abi.OUT_F16, out=out)
+        if timed_idx is not None:
+            ev[timed_idx][1].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.25)
+    launches0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    e_start.record()
+    for k in range(args.steps):
+        step(args.warmup + k, k)
+    e_end.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    launches = ctx.launch_count() - launches0
+    ms_total = e_start.elapsed_time(e_end)
+    clk = clocks.stop(t0, t1)
+    barrier()
+    ms_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    value = world * n_x * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_encoder), live CUDA events on its stream ----
+    k_ms = [a.elapsed_time(b) for a, b in ev]
+    kinds = np.concatenate([p.cpu().numpy().view(abi.PARAMS_DTYPE).reshape(-1)["kind"] for p in params])
+    status = np.concatenate([p.cpu().numpy().view(abi.PARAMS_DTYPE).reshape(-1)["status"] for p in params])
+    n_virtual = int((kinds == abi.KIND_VIRTUAL).sum())
+    n_cropped = int((kinds == abi.KIND_CROPPED).sum())
+    alg_bytes = n_virtual * (BYTES_CARD + BYTES_BG + BYTES_OUT_F16) + n_cropped * (BYTES_CARD + BYTES_OUT_F16)
+    alg_per_launch = alg_bytes / args.steps
+    k_avg_ms = sum(k_ms) / len(k_ms)
+    achieved = alg_per_launch / (k_avg_ms * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        mp_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp_["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_encoder_dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_encoder", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_avg_ms,
+                "kernel_share_of_step": k_avg_ms * args.steps / ms_total}
+
+    # ---- e2e: host buffers in -> host buffers out through the public dataset API ----
+    e2e = None
+    if not args.no_e2e:
+        hc = torch.from_numpy(cards.images[:PAIRS]).pin_memory()
+        hb = torch.from_numpy(np.stack(bgs[:PAIRS])).pin_memory()
+        for _ in range(2):
+            ds.host_tensor_batch(hc, hb)
+        barrier()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = max(3, min(args.steps, 10))
+        es.record()
+        for _ in range(e2e_steps):
+            res = ds.host_tensor_batch(hc, hb)
+        ee.record()
+        torch.cuda.synchronize()
+        e_ms = torch.tensor([es.elapsed_time(ee)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        d2h = sum(v.numel() * v.element_size() for v in res.values())
+        e2e = {"value": world * n_x * e2e_steps / (float(e_ms.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(hc.numel() + hb.numel()), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "api": "RanMtgEncDecDataset.host_tensor_batch (pinned uint8 cards+backgrounds in, pinned fp16 x/x2 + int64 labels out)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, w, n, wall = cpu_generator_throughput(args.cpu_pairs_per_worker)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": w, "kind": "port",
+                        "sample": f"{args.cpu_pairs_per_worker} pairs per worker x {w} worker processes (cv2 threads=1), batch 16, "
+                                  f"64-card/64-bg synthetic pools: {n} x-samples in {wall:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, {"out_dtype": "fp16 NCHW", "setup_s": round(t_setup, 1),
+                                             "virtual": n_virtual, "cropped": n_cropped,
+                                             "failed_samples": int((status != 0).sum())}),
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--pool-cards", type=int, default=2048)
+    ap.add_argument("--pool-bgs", type=int, default=1024)
+    ap.add_argument("--cpu-pairs-per-worker", type=int, default=48)
+    ap.add_argument("--ref-pairs-per-worker", type=int, default=16)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,7 +96,11 @@ typedef struct {
 
 #define MTGV_TAPE_MAX_OPS 18
 
-typedef enum { MTGV_KIND_VIRTUAL = 0, MTGV_KIND_CROPPED = 1 } mtgv_sample_kind;
+typedef enum {
+  MTGV_KIND_VIRTUAL = 0, /* make_virtual  (encoder_datasets.py:786-813) */
+  MTGV_KIND_CROPPED = 1, /* make_cropped  (:733-753)                    */
+  MTGV_KIND_BG_ONLY = 2  /* make_bg       (:774-784): only the bg ops of the tape are used */
+} mtgv_sample_kind;
 
 typedef struct {
   int32_t kind;        /* mtgv_sample_kind: make_virtual (encoder_datasets.py:786) or
@@ -183,6 +187,7 @@ typedef struct {
 /* ------------------------------------------------------------------------------------ */
 
 int mtgv_abi_version(void);
+int mtgv_sizeof(int which); /* sizeof of 0 mtgv_tape_op, 1 mtgv_enc_tape, 2 mtgv_x_op, 3 mtgv_enc_params, 4 mtgv_enc_config */
 mtgv_ctx* mtgv_create(int device);
 void mtgv_destroy(mtgv_ctx* ctx);
 const char* mtgv_last_error(const mtgv_ctx* ctx);
@@ -212,6 +217,26 @@ int mtgv_set_encoder_config(mtgv_ctx* ctx, const mtgv_enc_config* cfg_host);
  * (encoder_train.py:149-156,189-230) from Philox4x32-10 keyed by (seed, index). */
 int mtgv_sample_encoder_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n_pairs, mtgv_enc_tape* tape,
                              void* stream);
+
+/* Same, for explicit cards (RanMtgEncDecDataset.image_batch_by_ids, encoder_train.py:122-139):
+ * cards [n_pairs] device int32 pool indices (NULL = draw them); the two probabilities
+ * override the configured ones when >= 0 (force_target_input / force_similar_neg). */
+int mtgv_sample_encoder_tape_ex(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n_pairs, const int32_t* cards,
+                                const int32_t* bgs, double target_is_input_prob, double similar_neg_prob,
+                                mtgv_enc_tape* tape, void* stream);
+
+/* Streaming ingest (the per-batch `_load_card_image` / `ilsvrc.ran()` of _make_image_batch,
+ * encoder_train.py:149-156,196): overwrite pool entries [first, first+n) in place with new
+ * HWC uint8 images (device) of the entries' existing size; asynchronous on `stream`.
+ * With explicit `bgs` in mtgv_sample_encoder_tape_ex, x uses bgs[i] and x2 uses bgs[slot]
+ * for a uniformly drawn slot (bg1 = random.choice(bg_imgs), :224). */
+int mtgv_update_card_images(mtgv_ctx* ctx, const uint8_t* cards, int first, int n, void* stream);
+int mtgv_update_bg_images(mtgv_ctx* ctx, const uint8_t* bgs, int first, int n, void* stream);
+
+/* Static rounded-rectangle mask of the card pool (round_rect_mask, util/image.py:406-425):
+ * which = 0 encoder (radius_ratio 0.05, encoder_datasets.py:763), 1 detection (0.046,
+ * od_datasets.py:223).  out: [card_h, card_w] float32 (device). */
+int mtgv_get_mask(mtgv_ctx* ctx, int which, float* out, void* stream);
 
 /* Subsystem (1): tape -> params.  Replaces cv2.getPerspectiveTransform / getRotationMatrix2D /
  * the matrix inversions inside cv2.warp* / crop_to_size geometry for every sample

@@ -19,7 +19,7 @@ MTGV_TAPE_MAX_OPS = 18
 MTGV_X_MAX_OPS = 16
 
 OUT_F16, OUT_U8, OUT_F32 = 0, 1, 2
-KIND_VIRTUAL, KIND_CROPPED = 0, 1
+KIND_VIRTUAL, KIND_CROPPED, KIND_BG_ONLY = 0, 1, 2
 
 # tape opcodes (mtgv_tape_opcode)
 (OP_NONE, OP_DOWNUP, OP_WARP, OP_AFFINE, OP_PERSPECTIVE, OP_TINT, OP_FADE_BLACK, OP_FADE_WHITE, OP_BC, OP_FLIP,
@@ -112,6 +112,10 @@ def load_library(path: str | None = None) -> C.CDLL:
         "mtgv_set_bg_pool": (i32, [vp, vp, vp, vp, i32]),
         "mtgv_set_encoder_config": (i32, [vp, vp]),
         "mtgv_sample_encoder_tape": (i32, [vp, u64, i64, i32, vp, vp]),
+        "mtgv_sample_encoder_tape_ex": (i32, [vp, u64, i64, i32, vp, vp, C.c_double, C.c_double, vp, vp]),
+        "mtgv_update_card_images": (i32, [vp, vp, i32, i32, vp]),
+        "mtgv_update_bg_images": (i32, [vp, vp, i32, i32, vp]),
+        "mtgv_get_mask": (i32, [vp, i32, vp, vp]),
         "mtgv_expand_params": (i32, [vp, vp, i32, vp, vp, vp]),
         "mtgv_encoder_batch": (i32, [vp, vp, i32, vp, i32, vp, vp]),
         "mtgv_encoder_targets": (i32, [vp, vp, i32, vp, i32, vp]),

@@ -99,22 +99,53 @@ class Context:
         self.cfg = cfg
 
     # ------------------------------------------------------------------ encoder path
-    def sample_encoder_tape(self, seed: int, first_index: int, n_pairs: int) -> torch.Tensor:
+    def update_card_images(self, images: torch.Tensor, first: int = 0):
+        """Overwrite pool cards [first, first+n) with (n,H,W,3) uint8 images already on the device."""
+        assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous()
+        assert tuple(images.shape[1:]) == (*self.card_hw, 3)
+        rc = self.lib.mtgv_update_card_images(self._h, _ptr(images), first, images.shape[0], self._stream())
+        self._check(rc, "mtgv_update_card_images")
+
+    def update_bg_images(self, images: torch.Tensor, first: int = 0):
+        assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous() and images.ndim == 4
+        rc = self.lib.mtgv_update_bg_images(self._h, _ptr(images), first, images.shape[0], self._stream())
+        self._check(rc, "mtgv_update_bg_images")
+
+    def sample_encoder_tape(self, seed: int, first_index: int, n_pairs: int, cards: torch.Tensor | None = None,
+                            bgs: torch.Tensor | None = None, target_is_input_prob: float | None = None, similar_neg_prob: float | None = None,
+                            out: torch.Tensor | None = None) -> torch.Tensor:
+        """Tapes of n_pairs x-samples followed (when paired) by n_pairs x2-samples."""
         n = n_pairs * (2 if self.cfg.paired else 1)
-        tape = torch.empty((n, abi.TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
-        rc = self.lib.mtgv_sample_encoder_tape(self._h, C.c_uint64(seed & (2**64 - 1)), C.c_int64(first_index), n_pairs,
-                                               _ptr(tape), self._stream())
-        self._check(rc, "mtgv_sample_encoder_tape")
+        tape = out if out is not None else torch.empty((n, abi.TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        if cards is not None:
+            cards = cards.to(self.device, dtype=torch.int32).contiguous()
+            assert cards.numel() == n_pairs
+        if bgs is not None:
+            bgs = bgs.to(self.device, dtype=torch.int32).contiguous()
+            assert bgs.numel() == n_pairs
+        rc = self.lib.mtgv_sample_encoder_tape_ex(
+            self._h, C.c_uint64(seed & (2**64 - 1)), C.c_int64(first_index), n_pairs, _ptr(cards), _ptr(bgs),
+            -1.0 if target_is_input_prob is None else float(target_is_input_prob),
+            -1.0 if similar_neg_prob is None else float(similar_neg_prob), _ptr(tape), self._stream())
+        self._check(rc, "mtgv_sample_encoder_tape_ex")
         return tape
+
+    def get_mask(self, which: str = "encoder") -> torch.Tensor:
+        out = torch.empty(self.card_hw, dtype=torch.float32, device=self.device)
+        self._check(self.lib.mtgv_get_mask(self._h, 0 if which == "encoder" else 1, _ptr(out), self._stream()), "mtgv_get_mask")
+        return out
 
     def upload_tape(self, tape_np: np.ndarray) -> torch.Tensor:
         assert tape_np.dtype == abi.TAPE_DTYPE
         return torch.from_numpy(tape_np.view(np.uint8).reshape(len(tape_np), -1).copy()).to(self.device)
 
-    def expand_params(self, tape: torch.Tensor, want_labels: bool = True):
+    def expand_params(self, tape: torch.Tensor, want_labels: bool = True, params: torch.Tensor | None = None,
+                      labels: torch.Tensor | None = None):
         n = tape.shape[0]
-        params = torch.empty((n, abi.PARAMS_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
-        labels = torch.empty((n, 3), dtype=torch.int64, device=self.device) if want_labels else None
+        if params is None:
+            params = torch.empty((n, abi.PARAMS_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        if labels is None and want_labels:
+            labels = torch.empty((n, 3), dtype=torch.int64, device=self.device)
         rc = self.lib.mtgv_expand_params(self._h, _ptr(tape), n, _ptr(params), _ptr(labels), self._stream())
         self._check(rc, "mtgv_expand_params")
         return params, labels

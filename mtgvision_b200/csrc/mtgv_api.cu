@@ -15,6 +15,17 @@ extern "C" {
 
 int mtgv_abi_version(void) { return MTGV_ABI_VERSION; }
 
+int mtgv_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(mtgv_tape_op);
+    case 1: return (int)sizeof(mtgv_enc_tape);
+    case 2: return (int)sizeof(mtgv_x_op);
+    case 3: return (int)sizeof(mtgv_enc_params);
+    case 4: return (int)sizeof(mtgv_enc_config);
+    default: return -1;
+  }
+}
+
 mtgv_ctx* mtgv_create(int device) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return nullptr;
@@ -111,6 +122,8 @@ int mtgv_set_bg_pool(mtgv_ctx* ctx, const uint8_t* bgs, const int64_t* offsets_h
   MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_planes, total));
   MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_off, (size_t)n * 8));
   MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_hw, (size_t)n * 2 * 4));
+  ctx->bg_off_host = off;
+  ctx->bg_hw_host.assign(hw_host, hw_host + 2 * (size_t)n);
   MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->bg_off, off.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
   MTGV_CUDA_OK(ctx, cudaMemcpy(ctx->bg_hw, hw_host, (size_t)n * 2 * 4, cudaMemcpyHostToDevice));
   // runs of equally-sized, contiguous images are ingested with one launch each
@@ -157,7 +170,51 @@ int mtgv_sample_encoder_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, 
   int rc = need_encoder(ctx, true);
   if (rc) return rc;
   if (!tape || n_pairs < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_sample_encoder_tape: bad arguments");
-  return enc_sample_tape(ctx, seed, first_index, n_pairs, tape, (cudaStream_t)stream);
+  return enc_sample_tape(ctx, seed, first_index, n_pairs, nullptr, nullptr, -1.0, -1.0, tape, (cudaStream_t)stream);
+}
+
+int mtgv_update_card_images(mtgv_ctx* ctx, const uint8_t* cards, int first, int n, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!ctx->n_cards) return fail(ctx, MTGV_ERR_STATE, "card pool not set (mtgv_set_card_pool)");
+  if (!cards || first < 0 || n < 0 || first + n > ctx->n_cards)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_update_card_images: range outside the pool");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return pool_planarize(ctx, cards, ctx->card_planes + (size_t)first * 3 * ctx->card_h * ctx->card_pitch, n, ctx->card_h,
+                        ctx->card_w, ctx->card_pitch, (cudaStream_t)stream);
+}
+
+int mtgv_update_bg_images(mtgv_ctx* ctx, const uint8_t* bgs, int first, int n, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!ctx->n_bgs) return fail(ctx, MTGV_ERR_STATE, "background pool not set (mtgv_set_bg_pool)");
+  if (!bgs || first < 0 || n < 0 || first + n > ctx->n_bgs)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_update_bg_images: range outside the pool");
+  if (n == 0) return MTGV_OK;
+  const int h = ctx->bg_hw_host[2 * first], w = ctx->bg_hw_host[2 * first + 1];
+  for (int j = first; j < first + n; j++)
+    if (ctx->bg_hw_host[2 * j] != h || ctx->bg_hw_host[2 * j + 1] != w)
+      return fail(ctx, MTGV_ERR_INVALID, "mtgv_update_bg_images: entries in the range differ in size");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return pool_planarize(ctx, bgs, ctx->bg_planes + ctx->bg_off_host[first], n, h, w, round_up(w, 16), (cudaStream_t)stream);
+}
+
+int mtgv_sample_encoder_tape_ex(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n_pairs, const int32_t* cards,
+                                const int32_t* bgs, double target_is_input_prob, double similar_neg_prob,
+                                mtgv_enc_tape* tape, void* stream) {
+  int rc = need_encoder(ctx, true);
+  if (rc) return rc;
+  if (!tape || n_pairs < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_sample_encoder_tape_ex: bad arguments");
+  return enc_sample_tape(ctx, seed, first_index, n_pairs, cards, bgs, target_is_input_prob, similar_neg_prob, tape,
+                         (cudaStream_t)stream);
+}
+
+int mtgv_get_mask(mtgv_ctx* ctx, int which, float* out, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!ctx->n_cards) return fail(ctx, MTGV_ERR_STATE, "card pool not set (mtgv_set_card_pool)");
+  if (!out || which < 0 || which > 1) return fail(ctx, MTGV_ERR_INVALID, "mtgv_get_mask: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  MTGV_CUDA_OK(ctx, cudaMemcpyAsync(out, which ? ctx->mask_det : ctx->mask_enc, (size_t)ctx->card_h * ctx->card_w * 4,
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return MTGV_OK;
 }
 
 int mtgv_expand_params(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels, void* stream) {

@@ -636,7 +636,7 @@ __device__ void stage_bg_composite(float* cur, float* scratch, const mtgv_enc_pa
         }
         const float bgv = clip01(sum);
         const int o = y * OW + x;
-        const float a = __ldcg(alpha + o);
+        const float a = alpha ? __ldcg(alpha + o) : 0.f;
         const float fgv = cur[o];
         cur[o] = clip01(__fadd_rn(__fmul_rn(bgv, __fsub_rn(1.f, a)), __fmul_rn(fgv, a)));
       }
@@ -787,18 +787,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
       __syncthreads();
       continue;
     }
-    const uint8_t* cplane = L.card_planes + ((size_t)sp.card * 3 + plane) * sp.card_h * L.card_pitch;
-    for (int b = tid; b < 256; b += nt) S.lut[b] = __fdiv_rn((float)b, 255.f);  // img_float32: u8/255
-    build_area_axis(S.tabs.xs, S.tabs.xn, S.tabs.xw, sp.src_w, sp.fg_rw, 0, sp.fg_rw);
-    build_area_axis(S.tabs.ys, S.tabs.yn, S.tabs.yw, sp.src_h, sp.fg_rh, 0, sp.fg_rh);
-    __syncthreads();
-    stage_card_area(S.P0, sp, cplane, L.card_pitch, S.lut, S.tabs);
+    const bool bg_only = sp.kind == MTGV_KIND_BG_ONLY;
+    if (bg_only) {
+      for (int i = tid; i < HW; i += nt) S.P0[i] = 0.f;
+    } else {
+      const uint8_t* cplane = L.card_planes + ((size_t)sp.card * 3 + plane) * sp.card_h * L.card_pitch;
+      for (int b = tid; b < 256; b += nt) S.lut[b] = __fdiv_rn((float)b, 255.f);  // img_float32: u8/255
+      build_area_axis(S.tabs.xs, S.tabs.xn, S.tabs.xw, sp.src_w, sp.fg_rw, 0, sp.fg_rw);
+      build_area_axis(S.tabs.ys, S.tabs.yn, S.tabs.yw, sp.src_h, sp.fg_rh, 0, sp.fg_rh);
+      __syncthreads();
+      stage_card_area(S.P0, sp, cplane, L.card_pitch, S.lut, S.tabs);
+    }
     __syncthreads();
     Vm vm{{S.P0, S.P1}, 0, OH, OW, plane, L.fields, sp.seed};
-    if (sp.kind == MTGV_KIND_VIRTUAL) {
+    if (sp.kind != MTGV_KIND_CROPPED) {
       for (int k = 0; k < sp.n_fg; k++) vm_run_op(vm, sp.ops[k], k);
-      const float* alpha = L.alpha0;
-      if (!alpha_static) {
+      const float* alpha = bg_only ? nullptr : L.alpha0;
+      if (!alpha_static && !bg_only) {
         alpha = L.alpha_scratch + (size_t)s * HW;
         if (tid == 0)
           while (ld_acquire(flags + s) == 0) __nanosleep(200);
@@ -1057,12 +1062,17 @@ __device__ void sample_virtual(Rng& r, mtgv_enc_tape* t, const mtgv_enc_config* 
 }
 
 __global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const mtgv_enc_config* cfg, PoolMeta pm,
-                              mtgv_enc_tape* tape) {
+                              const int32_t* cards, const int32_t* bgs, double p_tii, double p_neg, mtgv_enc_tape* tape) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pairs) return;
   const uint64_t g = (uint64_t)(first + i);
   Rng sel(seed, g, 1);  // card / background selection stream (re-derivable by other samples)
-  const int card = sel.below(pm.n_cards), bg = sel.below(pm.n_bgs);
+  int card = sel.below(pm.n_cards);
+  int bg = sel.below(pm.n_bgs);
+  if (cards) card = cards[i];
+  if (bgs) bg = bgs[i];
+  if (p_tii < 0.0) p_tii = cfg->target_is_input_prob;
+  if (p_neg < 0.0) p_neg = cfg->similar_neg_prob;
   const int n_x = cfg->paired ? 2 : 1;
   for (int which = 0; which < n_x; which++) {
     mtgv_enc_tape* t = &tape[which * n_pairs + i];
@@ -1072,16 +1082,20 @@ __global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const m
     t->seed = seed ^ (0x9E3779B97F4A7C15ull * (2 * g + which + 1));
     if (which == 1) {
       // hard negative (encoder_train.py:217-221) and bg1 = random.choice(bg_imgs) (:224)
-      if (r.uniform() < cfg->similar_neg_prob) {
+      if (r.uniform() < p_neg) {
         int m = pm.grp_off[card + 1] - pm.grp_off[card] - 1;
         if (m > 0) t->swap_choice = r.below(m);
       }
       int slot = r.below(n_pairs);
-      Rng other(seed, (uint64_t)(first + slot), 1);
-      other.below(pm.n_cards);
-      t->bg = other.below(pm.n_bgs);
+      if (bgs) {
+        t->bg = bgs[slot];
+      } else {
+        Rng other(seed, (uint64_t)(first + slot), 1);
+        other.below(pm.n_cards);
+        t->bg = other.below(pm.n_bgs);
+      }
     }
-    if (r.uniform() < cfg->target_is_input_prob) {
+    if (r.uniform() < p_tii) {
       t->kind = MTGV_KIND_CROPPED;
     } else {
       t->kind = MTGV_KIND_VIRTUAL;
@@ -1090,9 +1104,11 @@ __global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const m
   }
 }
 
-int enc_sample_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first, int n_pairs, mtgv_enc_tape* tape, cudaStream_t st) {
+int enc_sample_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first, int n_pairs, const int32_t* cards, const int32_t* bgs,
+                    double p_tii, double p_neg, mtgv_enc_tape* tape, cudaStream_t st) {
   if (n_pairs <= 0) return MTGV_OK;
-  k_sample_tape<<<(n_pairs + 63) / 64, 64, 0, st>>>(seed, first, n_pairs, ctx->cfg_dev, pool_meta(ctx), tape);
+  k_sample_tape<<<(n_pairs + 63) / 64, 64, 0, st>>>(seed, first, n_pairs, ctx->cfg_dev, pool_meta(ctx), cards, bgs, p_tii,
+                                                    p_neg, tape);
   ctx->launches++;
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   return MTGV_OK;
@@ -1102,14 +1118,13 @@ int enc_sample_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first, int n_pairs, mt
 // batch launch                                                                          //
 // ------------------------------------------------------------------------------------ //
 
-static int ensure_scratch(mtgv_ctx* ctx, int n) {
-  const size_t HW = (size_t)ctx->cfg.out_h * ctx->cfg.out_w;
-  if ((size_t)n > ctx->alpha_cap) {
+static int ensure_scratch(mtgv_ctx* ctx, int n, size_t HW) {
+  if ((size_t)n * HW > ctx->alpha_cap) {  // alpha_cap counts floats
     if (ctx->alpha_scratch) cudaFree(ctx->alpha_scratch);
     ctx->alpha_scratch = nullptr;
     ctx->alpha_cap = 0;
     MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->alpha_scratch, (size_t)n * HW * 4));
-    ctx->alpha_cap = n;
+    ctx->alpha_cap = (size_t)n * HW;
   }
   if ((size_t)n + 1 > ctx->sync_cap) {
     if (ctx->sync_words) cudaFree(ctx->sync_words);
@@ -1121,14 +1136,21 @@ static int ensure_scratch(mtgv_ctx* ctx, int n) {
   return MTGV_OK;
 }
 
+static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
+                           int OH, int OW, cudaStream_t st);
+
 int enc_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
               cudaStream_t st) {
+  return enc_batch_sized(ctx, params, n, out, out_dtype, fields, ctx->cfg.out_h, ctx->cfg.out_w, st);
+}
+
+static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
+                           int OH, int OW, cudaStream_t st) {
   if (n <= 0) return MTGV_OK;
-  const int OH = ctx->cfg.out_h, OW = ctx->cfg.out_w;
   const size_t smem = enc_smem_bytes(OH, OW);
   if ((int)smem > ctx->max_smem_optin)
     return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw too large: two float32 planes must fit in 227 KB of shared memory");
-  int rc = ensure_scratch(ctx, n);
+  int rc = ensure_scratch(ctx, n, (size_t)OH * OW);
   if (rc) return rc;
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->sync_words, 0, ((size_t)n + 1) * 4, st));
   static bool attr_set = false;
@@ -1160,8 +1182,6 @@ __global__ void k_target_params(const int32_t* cards, int n, const mtgv_enc_conf
 
 int enc_targets(mtgv_ctx* ctx, const int32_t* cards, int n, void* out, int out_dtype, cudaStream_t st) {
   if (n <= 0) return MTGV_OK;
-  if (ctx->cfg.y_h != ctx->cfg.out_h || ctx->cfg.y_w != ctx->cfg.out_w)
-    return fail(ctx, MTGV_ERR_LIMIT, "y_size_hw != x_size_hw is not supported yet");
   if ((size_t)n > ctx->tmp_params_cap) {
     if (ctx->tmp_params) cudaFree(ctx->tmp_params);
     ctx->tmp_params = nullptr; ctx->tmp_params_cap = 0;
@@ -1171,7 +1191,7 @@ int enc_targets(mtgv_ctx* ctx, const int32_t* cards, int n, void* out, int out_d
   k_target_params<<<(n + 63) / 64, 64, 0, st>>>(cards, n, ctx->cfg_dev, pool_meta(ctx), ctx->tmp_params);
   ctx->launches++;
   MTGV_CUDA_OK(ctx, cudaGetLastError());
-  return enc_batch(ctx, ctx->tmp_params, n, out, out_dtype, nullptr, st);
+  return enc_batch_sized(ctx, ctx->tmp_params, n, out, out_dtype, nullptr, ctx->cfg.y_h, ctx->cfg.y_w, st);
 }
 
 // ------------------------------------------------------------------------------------ //

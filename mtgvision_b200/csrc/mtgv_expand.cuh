@@ -259,7 +259,8 @@ MTGV_HD int expand_encoder_sample(const mtgv_enc_tape* t, const mtgv_enc_config*
     if (p->src_h > 6 * OH || p->src_w > 6 * OW) return p->status = MTGV_ERR_LIMIT;
     return 0;
   }
-  if (t->kind != MTGV_KIND_VIRTUAL) return p->status = MTGV_ERR_INVALID;
+  if (t->kind != MTGV_KIND_VIRTUAL && t->kind != MTGV_KIND_BG_ONLY) return p->status = MTGV_ERR_INVALID;
+  const bool bg_only = t->kind == MTGV_KIND_BG_ONLY;
   if (t->bg < 0 || t->bg >= pm.n_bgs) return p->status = MTGV_ERR_INVALID;
   if (t->n_fg + t->n_bg + t->n_vrtl > MTGV_TAPE_MAX_OPS) return p->status = MTGV_ERR_INVALID;
 
@@ -279,7 +280,7 @@ MTGV_HD int expand_encoder_sample(const mtgv_enc_tape* t, const mtgv_enc_config*
 
   int n = 0;
   const mtgv_tape_op* ops = t->ops;
-  for (int k = 0; k < t->n_fg; k++) {
+  for (int k = 0; k < (bg_only ? 0 : t->n_fg); k++) {
     if (n >= MTGV_X_MAX_OPS) return p->status = MTGV_ERR_LIMIT;
     int r = expand_plane_op(&ops[k], OH, OW, &p->ops[n]);
     if (r < 0) return p->status = r;
@@ -345,7 +346,7 @@ MTGV_HD int expand_encoder_sample(const mtgv_enc_tape* t, const mtgv_enc_config*
   // the rotate canvas' fixed-point tables share the free plane with the tile staging buffers
   if (2 * (p->rot_nh + p->rot_nw) + kWTileCap + 2048 > OH * OW) return p->status = MTGV_ERR_LIMIT;
 
-  for (int k = t->n_fg + t->n_bg; k < t->n_fg + t->n_bg + t->n_vrtl; k++) {
+  for (int k = t->n_fg + t->n_bg; k < t->n_fg + t->n_bg + (bg_only ? 0 : t->n_vrtl); k++) {
     if (n >= MTGV_X_MAX_OPS) return p->status = MTGV_ERR_LIMIT;
     int r = expand_plane_op(&ops[k], OH, OW, &p->ops[n]);
     if (r < 0) return p->status = r;

@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/mtgv.h"
 #include "mtgv_expand.cuh"
@@ -32,6 +33,8 @@ struct mtgv_ctx {
   int64_t* bg_off = nullptr;  // [n] byte offset of image j in bg_planes
   int32_t* bg_hw = nullptr;   // [n][2] (h, w)  (pitch = round_up(w,16))
   int n_bgs = 0;
+  std::vector<int64_t> bg_off_host;
+  std::vector<int32_t> bg_hw_host;
 
   // encoder
   mtgv_enc_config cfg{};
@@ -94,7 +97,8 @@ struct Philox {
 // entry points implemented in mtgv_enc.cu, called from mtgv_api.cu
 namespace mtgv {
 int enc_build_static_alpha(mtgv_ctx* ctx, cudaStream_t st);
-int enc_sample_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first, int n_pairs, mtgv_enc_tape* tape, cudaStream_t st);
+int enc_sample_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first, int n_pairs, const int32_t* cards, const int32_t* bgs, double p_tii,
+                    double p_neg, mtgv_enc_tape* tape, cudaStream_t st);
 int enc_expand(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels, cudaStream_t st);
 int enc_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
               cudaStream_t st);

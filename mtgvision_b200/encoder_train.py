@@ -1,0 +1,220 @@
+"""Drop-in for the batch former of `mtgvision/encoder_train.py` (reference :74-249).
+
+`RanMtgEncDecDataset` keeps the reference constructor, `__iter__`, `random_tensor_batch`,
+`random_image_batch`, `image_batch_by_ids`, `set_batch_size`, `from_hparams` and the batch
+dict keys (`x, x2, y, x_labels, x2_labels`).  Each batch is produced by three kernel
+launches on the caller's CUDA stream (tape sampler, parameter expansion, plane
+interpreter) and stays on the GPU: `x, x2[, y]` are contiguous NCHW tensors in `out_dtype`
+(fp16 default; uint8 / fp32 selectable), labels are `[B, 3] int64`.
+
+Use it with `DataLoader(ds, batch_size=None, num_workers=0)` - CUDA tensors cannot cross
+the worker fork the reference relies on (encoder_train.py:517-523), and none is needed.
+
+Multi-GPU: one process per GPU, `rank`/`world_size` select a disjoint slice of the global
+Philox sample-index space; nothing is exchanged between ranks.
+"""
+
+from __future__ import annotations
+
+import random
+import uuid
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch.utils.data import IterableDataset
+
+from . import abi, synth
+from .context import Context
+from .encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+
+_OUT = {"float16": abi.OUT_F16, "fp16": abi.OUT_F16, "uint8": abi.OUT_U8, "u8": abi.OUT_U8,
+        "float32": abi.OUT_F32, "fp32": abi.OUT_F32}
+
+
+class RanMtgEncDecDataset(IterableDataset):
+    def __init__(
+        self,
+        default_batch_size: int,
+        *,
+        predownload: bool = False,
+        paired: bool = False,
+        targets: bool = True,
+        x_size_hw: Tuple[int, int] = (192, 128),
+        y_size_hw: Tuple[int, int] = (192, 128),
+        half_upsidedown: bool = False,
+        target_is_input_prob: float = 0.05,
+        similar_neg_prob: float = 0.2,
+        check_data: bool = False,
+        # ---- B200 path ----
+        mtg: Optional[SyntheticBgFgMtgImages] = None,
+        ilsvrc: Optional[IlsvrcImages] = None,
+        device: Optional[int] = None,
+        out_dtype: str = "float16",
+        seed: Optional[int] = None,
+        rank: int = 0,
+        world_size: int = 1,
+    ):
+        assert default_batch_size > 0
+        self.default_batch_size = default_batch_size
+        self.paired = paired
+        self.targets = targets
+        self.x_size_hw = tuple(x_size_hw)
+        self.y_size_hw = tuple(y_size_hw)
+        self.mtg = mtg if mtg is not None else SyntheticBgFgMtgImages(img_type="small", predownload=predownload)
+        self.ilsvrc = ilsvrc if ilsvrc is not None else IlsvrcImages()
+        self.half_upsidedown = half_upsidedown
+        self.target_is_input_prob = target_is_input_prob
+        self.similar_neg_prob = similar_neg_prob
+        self.check_data = check_data
+        self.out_dtype = _OUT[out_dtype]
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.seed = random.getrandbits(63) if seed is None else int(seed)
+        self._batch_counter = 0
+        self.ctx = Context(device)
+        self.ctx.set_encoder_config(x_size_hw=self.x_size_hw, y_size_hw=self.y_size_hw,
+                                    target_is_input_prob=target_is_input_prob, similar_neg_prob=similar_neg_prob,
+                                    half_upsidedown=half_upsidedown, paired=paired, targets=targets)
+        pool = self.mtg.pool
+        self.ctx.set_card_pool(pool.images, pool.labels3, pool.grp_off, pool.grp_mem)
+        self.ctx.set_bg_pool(self.ilsvrc.images_u8)
+
+    # ------------------------------------------------------------------ reference surface
+    def __iter__(self):
+        while True:
+            yield self.random_tensor_batch()
+
+    def set_batch_size(self, batch_size):
+        self.default_batch_size = batch_size
+
+    @classmethod
+    def from_hparams(cls, hparams, **kw):
+        return cls(
+            default_batch_size=hparams.batch_size,
+            predownload=getattr(hparams, "force_download", False),
+            paired=hparams.loss_contrastive is not None or hparams.loss_set_contrastive is not None,
+            targets=hparams.loss_recon is not None,
+            x_size_hw=hparams.x_size_hw,
+            y_size_hw=hparams.y_size_hw,
+            half_upsidedown=hparams.half_upsidedown,
+            target_is_input_prob=hparams.target_is_input_prob,
+            similar_neg_prob=hparams.similar_neg_prob,
+            check_data=getattr(hparams, "check_data", False),
+            **kw,
+        )
+
+    def random_tensor_batch(self, n: int | None = None) -> dict:
+        """Device tensors: x, x2, y [n,3,H,W] out_dtype; x_labels, x2_labels [n,3] int64."""
+        if n is None:
+            n = self.default_batch_size
+        return self._generate(n, cards=None, t_prob=None, n_prob=None)
+
+    def random_image_batch(self, n: int | None = None) -> dict:
+        """numpy NHWC float32 + int labels, like the reference's BatchHintNumpy."""
+        return self._to_numpy(self.random_tensor_batch(n))
+
+    def image_batch_by_ids(self, ids, *, force_target_input: bool = False, force_similar_neg: bool = False) -> dict:
+        if isinstance(ids, (str, uuid.UUID)):
+            ids = [ids]
+        # reference: t = 1.0 if force else (None if force is None else 0.0), then `t or default`
+        # (encoder_train.py:133-134,178,217): False -> 0.0 -> falls back to the default probability
+        t = 1.0 if force_target_input else None
+        n = 1.0 if force_similar_neg else None
+        cards = torch.tensor([self.mtg.get_card_by_id(i).index for i in ids], dtype=torch.int32)
+        return self._to_numpy(self._generate(len(ids), cards=cards, t_prob=t, n_prob=n))
+
+    def host_tensor_batch(self, card_images: torch.Tensor, bg_images: torch.Tensor) -> dict:
+        """Host buffers in, host buffers out: the `_make_image_batch(cards, bg_imgs)` call of the
+        reference (encoder_train.py:189-230) for callers that keep their images on the host.
+
+        card_images (n,H,W,3) / bg_images (n,h,w,3): uint8 CPU tensors (pinned for full copy
+        speed) of the pools' image sizes.  They are copied into pool slots [0, n), sample i
+        uses card i and background i (x2: a random background of the batch, as in the
+        reference), and the finished batch is copied back into pinned host tensors.
+        Labels are those of pool slots [0, n)."""
+        n = card_images.shape[0]
+        assert bg_images.shape[0] == n
+        ctx = self.ctx
+        with torch.cuda.device(ctx.device):
+            if getattr(self, "_stage_n", 0) != n:
+                self._stage_cards = torch.empty(card_images.shape, dtype=torch.uint8, device=ctx.device)
+                self._stage_bgs = torch.empty(bg_images.shape, dtype=torch.uint8, device=ctx.device)
+                self._stage_idx = torch.arange(n, dtype=torch.int32, device=ctx.device)
+                self._stage_n = n
+                self._host_out = {}
+            self._stage_cards.copy_(card_images, non_blocking=True)
+            self._stage_bgs.copy_(bg_images, non_blocking=True)
+            ctx.update_card_images(self._stage_cards, 0)
+            ctx.update_bg_images(self._stage_bgs, 0)
+            batch = self._generate(n, cards=self._stage_idx, t_prob=None, n_prob=None, bgs=self._stage_idx)
+            out = {}
+            for k, v in batch.items():
+                h = self._host_out.get(k)
+                if h is None or h.shape != v.shape or h.dtype != v.dtype:
+                    h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                    self._host_out[k] = h
+                h.copy_(v, non_blocking=True)
+                out[k] = h
+            torch.cuda.current_stream(ctx.device).synchronize()
+        return out
+
+    # ------------------------------------------------------------------ internals
+    def _next_first_index(self, n: int) -> int:
+        """Disjoint global sample indices per (rank, batch): contiguous blocks of n."""
+        b = self._batch_counter
+        self._batch_counter += 1
+        return (b * self.world_size + self.rank) * n
+
+    def _generate(self, n: int, cards, t_prob, n_prob, bgs=None) -> dict:
+        ctx = self.ctx
+        with torch.cuda.device(ctx.device):
+            first = self._next_first_index(n)
+            tape = ctx.sample_encoder_tape(self.seed, first, n, cards=cards, bgs=bgs, target_is_input_prob=t_prob,
+                                           similar_neg_prob=n_prob)
+            params, labels = ctx.expand_params(tape)
+            imgs = ctx.encoder_batch(params, self.out_dtype)
+            out = {}
+            if self.targets:
+                # y = make_cropped of the x card (encoder_train.py:171-173, 199-201)
+                base = tape.view(torch.int32)[:n, 1]  # mtgv_enc_tape.card
+                out["y"] = ctx.encoder_targets(base, self.out_dtype)
+            out["x"] = imgs[:n]
+            out["x_labels"] = labels[:n]
+            if self.paired:
+                out["x2"] = imgs[n:]
+                out["x2_labels"] = labels[n:]
+            if self.check_data:
+                st = params.view(torch.int32)[:, abi.PARAMS_DTYPE.fields["status"][1] // 4]
+                if bool((st != 0).any()):
+                    raise abi.MtgvError("a sample failed parameter expansion (size limits: see DESIGN.md)")
+        return out
+
+    @staticmethod
+    def _to_numpy(batch: dict) -> dict:
+        out = {}
+        for k, v in batch.items():
+            if v.ndim == 4:
+                a = v.permute(0, 2, 3, 1).contiguous()
+                a = a.float() / 255.0 if a.dtype == torch.uint8 else a.float()
+                out[k] = a.cpu().numpy()
+            else:
+                out[k] = v.cpu().numpy()
+        return out
+
+
+class MtgDataModule:
+    """Shape of the reference's LightningDataModule (encoder_train.py:504-523) without the
+    pytorch_lightning dependency: `train_dataloader()` returns a DataLoader that yields the
+    dataset's pre-formed device batches."""
+
+    def __init__(self, train_dataset: RanMtgEncDecDataset, num_workers: int = 0, batch_size: int | None = None):
+        if num_workers != 0:
+            raise ValueError("the GPU generator runs in-process: num_workers must be 0")
+        self.train_dataset = train_dataset
+        if batch_size is not None:
+            train_dataset.set_batch_size(batch_size)
+
+    def train_dataloader(self):
+        from torch.utils.data import DataLoader
+
+        return DataLoader(self.train_dataset, batch_size=None, shuffle=False, num_workers=0)

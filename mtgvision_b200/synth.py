@@ -130,12 +130,45 @@ def synth_faces(n: int) -> list[CardFace]:
     return faces
 
 
-def make_card_pool(n: int, hw=CARD_HW) -> CardPool:
+def _card_chunk(args):
+    k0, k1, hw = args
+    return np.stack([synth_card(k, hw) for k in range(k0, k1)])
+
+
+def _bg_chunk(args):
+    j0, j1, hw = args
+    return [synth_bg(j, hw) for j in range(j0, j1)]
+
+
+def _chunks(n: int, workers: int):
+    step = max(1, (n + workers * 4 - 1) // (workers * 4))
+    return [(a, min(a + step, n)) for a in range(0, n, step)]
+
+
+def make_card_pool(n: int, hw=CARD_HW, workers: int = 1) -> CardPool:
+    """`workers > 1` generates the images in a process pool (bench setup only)."""
     images = np.empty((n, hw[0], hw[1], 3), dtype=np.uint8)
-    for k in range(n):
-        images[k] = synth_card(k, hw)
+    if workers > 1 and n >= 64:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(workers) as p:
+            spans = _chunks(n, workers)
+            for (a, b), part in zip(spans, p.imap(_card_chunk, [(a, b, hw) for a, b in spans])):
+                images[a:b] = part
+    else:
+        for k in range(n):
+            images[k] = synth_card(k, hw)
     return CardPool(images, synth_faces(n))
 
 
-def make_bg_pool(n: int, hw=BG_HW) -> list[np.ndarray]:
+def make_bg_pool(n: int, hw=BG_HW, workers: int = 1) -> list[np.ndarray]:
+    if workers > 1 and n >= 64:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(workers) as p:
+            spans = _chunks(n, workers)
+            out: list[np.ndarray] = []
+            for part in p.imap(_bg_chunk, [(a, b, hw) for a, b in spans]):
+                out.extend(part)
+            return out
     return [synth_bg(j, hw) for j in range(n)]

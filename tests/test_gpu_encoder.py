@@ -1,0 +1,264 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on
+identical sampled parameters and identical inputs.
+
+Bars (BASELINE.json north_star): labels / hard-negative indices bit-exact; warped pixels
+within +-1 LSB of uint8 of the reference (cv2.warpPerspective itself: bit-exact float32).
+"""
+import ctypes as C
+import os
+import random
+
+import cv2
+import numpy as np
+import pytest
+
+from mtgvision_b200 import abi, synth
+from oracle import cv2_restate as R
+from oracle import encoder_oracle as EO
+from oracle import tape_pack
+from tests import parity_util as PU
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+MAX_LSB = 1  # stated tolerance: |round(255*gpu) - round(255*ref)| <= 1 for every pixel
+
+
+@pytest.fixture(scope="module")
+def env():
+    pool, bgs = PU.small_pools(8, 8)
+    ctx = PU.make_context(pool, bgs, half_upsidedown=True)
+    yield pool, bgs, ctx
+    ctx.close()
+
+
+def _xops(n):
+    a = np.zeros(n, dtype=abi.XOP_DTYPE)
+    a["field"] = -1
+    a["field2"] = -1
+    return a
+
+
+def test_warp_perspective_bit_exact(env):
+    _, _, ctx = env
+    rng = np.random.default_rng(0)
+    for (sh, sw, c, dh, dw) in [(192, 128, 4, 192, 128), (680, 488, 3, 640, 640), (680, 488, 1, 1280, 1280), (37, 29, 3, 50, 40)]:
+        src = rng.random((3, sh, sw, c), dtype=np.float32)
+        Ms = []
+        for _ in range(3):
+            s = np.float32([[0, 0], [sw, 0], [0, sh], [sw, sh]])
+            d = (s * (dw / sw, dh / sh) + rng.uniform(-0.2, 0.2, (4, 2)) * [dw, dh]).astype(np.float32)
+            Ms.append(cv2.getPerspectiveTransform(s, d))
+        out = ctx.warp_perspective(torch.from_numpy(src), torch.from_numpy(np.stack(Ms)), (dh, dw)).cpu().numpy()
+        for k in range(3):
+            ref = cv2.warpPerspective(src[k], Ms[k], (dw, dh)).reshape(dh, dw, c)
+            assert np.array_equal(out[k], ref), (sh, sw, c, dh, dw)
+
+
+def test_plane_ops_against_cv2(env):
+    _, _, ctx = env
+    rng = np.random.default_rng(1)
+    img = rng.random((2, 192, 128, 4), dtype=np.float32)
+    run = lambda ops: ctx.run_plane_ops(torch.from_numpy(img.copy()), ops).cpu().numpy()  # noqa: E731
+    o = _xops(1); o[0]["code"] = abi.X_WARP_PERSP
+    s = np.float32([[0, 0], [128, 0], [0, 192], [128, 192]]); d = (s + rng.uniform(-12, 12, (4, 2))).astype(np.float32)
+    M = cv2.getPerspectiveTransform(s, d); o[0]["d"][:] = cv2.invert(M)[1].reshape(-1)
+    got = run(o)
+    for k in range(2):
+        assert np.array_equal(got[k], cv2.warpPerspective(img[k], M, (128, 192)))
+    o = _xops(1); o[0]["code"] = abi.X_WARP_AFFINE
+    A = cv2.getRotationMatrix2D((64, 96), 4.0, 1.05); A[:, 2] += (3.3, -7.1)
+    o[0]["d"][:6] = R.invert_affine(A).reshape(-1)
+    assert np.array_equal(run(o)[0], cv2.warpAffine(img[0], A, (128, 192)))
+    for n in (1, 2):
+        for dn in (0, 1, 2):
+            for up in (0, 1, 2):
+                o = _xops(1); o[0]["code"] = abi.X_DOWNUP; o[0]["i"][:3] = (n, dn, up)
+                ref = cv2.resize(cv2.resize(img[0], (128 >> n, 192 >> n), interpolation=dn), (128, 192), interpolation=up)
+                assert np.abs(run(o)[0] - ref).max() <= 1e-6
+    o = _xops(1); o[0]["code"] = abi.X_BLUR3
+    assert np.abs(run(o)[0] - cv2.GaussianBlur(img[0], (3, 3), 0)).max() <= 1e-6
+    o = _xops(1); o[0]["code"] = abi.X_SHARPEN
+    k = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]])
+    assert np.abs(run(o)[0] - np.clip(cv2.filter2D(img[0], -1, k), 0, 1)).max() <= 2e-6
+    o = _xops(1); o[0]["code"] = abi.X_ELEM; o[0]["f"][:] = (1.1, 0.9, 1.05, 1.0, 0.01, 0.0, -0.02, 0.0); o[0]["i"][:2] = (7, 1)
+    ref = img[0].copy()
+    for c in range(3):
+        ref[:, :, c] = np.clip(np.float32(o[0]["f"][c]) * ref[:, :, c] + np.float32(o[0]["f"][4 + c]), 0, 1)
+    assert np.array_equal(run(o)[0], ref)
+
+
+def test_expand_params_device_equals_host_and_cv2(env):
+    pool, bgs, ctx = env
+    tapes = [PU.oracle_virtual(pool, bgs, s, s % 8, (s // 8) % 8)[1] for s in range(300, 364)]
+    arr, _ = tape_pack.pack_tapes(tapes)
+    params, labels = ctx.expand_params(ctx.upload_tape(arr))
+    p = params.cpu().numpy().view(abi.PARAMS_DTYPE).reshape(-1)
+    assert np.all(p["status"] == 0)
+    hh = C.CDLL(os.path.join(os.path.dirname(__file__), "host_harness", "libmtgv_hostharness.so"))
+    hp = np.zeros(len(tapes), dtype=abi.PARAMS_DTYPE)
+    bg_hw = np.asarray([b.shape[:2] for b in bgs], dtype=np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    hh.hh_expand_encoder(vp(arr), len(tapes), C.byref(ctx.cfg), 680, 488, len(pool), vp(pool.labels3), vp(pool.grp_off),
+                         vp(pool.grp_mem), len(bgs), vp(bg_hw), vp(hp))
+    assert p.tobytes() == hp.tobytes()  # fp64 expansion identical on device and host, bit for bit
+    for t, q in zip(tapes, p):
+        for rec in t["bg_ops"]:
+            if rec["op"] == "warp_inv":
+                assert np.array_equal(cv2.invert(rec["M"])[1].reshape(-1), q["winv"])
+            if rec["op"] == "rotate":
+                assert (rec["nh"], rec["nw"]) == (q["rot_nh"], q["rot_nw"])
+
+
+def test_virtual_samples_within_one_lsb(env):
+    """make_virtual: 160 seeded samples covering every op, fp32 / fp16 / uint8 outputs."""
+    pool, bgs, ctx = env
+    refs, tapes = [], []
+    for seed in range(160):
+        img, t = PU.oracle_virtual(pool, bgs, seed, seed % 8, (seed // 8) % 8)
+        refs.append(img); tapes.append(t)
+    seen = set()
+    for t in tapes:
+        for rec in t["fg_ops"] + t["bg_ops"] + t["vrtl_ops"]:
+            seen.add(rec["op"] + (str(rec["kind"]) if rec["op"] == "noise" else ""))
+    for need in ["downup", "warp", "affine", "perspective", "tint", "fade_black", "fade_white", "bc", "blur", "sharpen",
+                 "noise0", "noise1", "noise2", "noise3", "gaussian_noise", "salt_pepper", "erase", "cutout"]:
+        assert need in seen, f"seed set does not exercise {need}"
+    for dt in (abi.OUT_F32, abi.OUT_F16, abi.OUT_U8):
+        out, labels, p = PU.gpu_run_tapes(ctx, tapes, dt)
+        assert np.all(p["status"] == 0)
+        worst = [PU.lsb_diff(o, r)[0] for o, r in zip(out, refs)]
+        assert max(worst) <= MAX_LSB, f"dtype {dt}: max uint8 LSB error {max(worst)} at sample {int(np.argmax(worst))}"
+        want = np.asarray([pool.labels3[t["card"]] for t in tapes], dtype=np.int64)
+        assert np.array_equal(labels, want)
+    out32, _, _ = PU.gpu_run_tapes(ctx, tapes, abi.OUT_F32)
+    err = max(float(np.abs(o - r).max()) for o, r in zip(out32, refs))
+    assert err * 255 < 1.0  # float32 outputs: max abs error stated in uint8 LSB
+
+
+def test_device_transcendentals_mode_still_within_one_lsb(env):
+    """Production mode computes cos/sin on the device (CUDA libm) instead of taking the host's."""
+    pool, bgs, ctx = env
+    refs, tapes = zip(*[PU.oracle_virtual(pool, bgs, s, s % 8, s % 5) for s in range(500, 532)])
+    out, _, _ = PU.gpu_run_tapes(ctx, list(tapes), abi.OUT_F32, host_transcendentals=False)
+    assert max(PU.lsb_diff(o, r)[0] for o, r in zip(out, refs)) <= MAX_LSB
+
+
+def test_cropped_samples_and_targets(env):
+    pool, bgs, ctx = env
+    tapes, refs = [], []
+    for k in range(8):
+        t = {"card": k, "bg": 0}
+        refs.append(EO.make_cropped(EO.u8_to_f32(pool.images[k]), (192, 128), tape=t))
+        tapes.append(t)
+    out, labels, _ = PU.gpu_run_tapes(ctx, tapes, abi.OUT_F32)
+    assert max(PU.lsb_diff(o, r)[0] for o, r in zip(out, refs)) == 0
+    assert max(float(np.abs(o - r).max()) for o, r in zip(out, refs)) < 1e-6
+    y = ctx.encoder_targets(torch.arange(8, dtype=torch.int32), abi.OUT_F32).permute(0, 2, 3, 1).cpu().numpy()
+    assert np.array_equal(y, out)
+    # rot180 of the crop (make_cropped(half_upsidedown=True) drawing upsidedown)
+    t = dict(tapes[3]); t["upsidedown"] = True
+    ud, _, _ = PU.gpu_run_tapes(ctx, [t], abi.OUT_F32)
+    assert np.array_equal(ud[0], out[3][::-1, ::-1])
+
+
+def test_batch_labels_and_hard_negative_indices_bit_exact():
+    """A whole oracle batch (x and x2 with same-name swaps resolved ON DEVICE from the recorded
+    random.choice index) - labels and swapped card indices must match exactly."""
+    pool = synth.make_card_pool(24)
+    bgs = synth.make_bg_pool(6)
+    ctx = PU.make_context(pool, bgs, half_upsidedown=False, similar_neg_prob=0.6)
+    random.seed(11); np.random.seed(11); EO.reset_shuffle_state()
+    bo = EO.BatchOracle(pool, bgs, paired=True, targets=False, similar_neg_prob=0.6)
+    imgs, lbls, tapes = bo.random_image_batch(24)
+    all_tapes = tapes["x"] + tapes["x2"]
+    assert any(t.get("swapped") for t in tapes["x2"])
+    out, labels, p = PU.gpu_run_tapes(ctx, all_tapes, abi.OUT_F16)
+    assert np.array_equal(labels[:24], lbls["x_labels"]) and np.array_equal(labels[24:], lbls["x2_labels"])
+    assert np.array_equal(p["card"], np.asarray([t["card"] for t in all_tapes]))  # hard-negative indices
+    ref = np.concatenate([imgs["x"], imgs["x2"]])
+    assert max(PU.lsb_diff(o, r)[0] for o, r in zip(out, ref)) <= MAX_LSB
+    ctx.close()
+
+
+def test_sampler_is_deterministic_sharded_and_distributed_like_the_reference(env):
+    pool, bgs, ctx = env
+    a = ctx.sample_encoder_tape(77, 0, 256).cpu().numpy().view(abi.TAPE_DTYPE).reshape(-1)
+    b = ctx.sample_encoder_tape(77, 0, 256).cpu().numpy().view(abi.TAPE_DTYPE).reshape(-1)
+    assert a.tobytes() == b.tobytes()
+    # shard [128, 256) of the same stream reproduces the x-tapes of the second half
+    c = ctx.sample_encoder_tape(77, 128, 128).cpu().numpy().view(abi.TAPE_DTYPE).reshape(-1)
+    for f in ("kind", "card", "upsidedown", "n_fg", "n_bg", "n_vrtl", "seed"):
+        assert np.array_equal(a[f][128:256], c[f][:128]), f
+    big = ctx.sample_encoder_tape(5, 0, 4096).cpu().numpy().view(abi.TAPE_DTYPE).reshape(-1)
+    x = big[:4096]
+    frac_cropped = (x["kind"] == abi.KIND_CROPPED).mean()
+    assert 0.03 < frac_cropped < 0.07  # target_is_input_prob = 0.05
+    v = x[x["kind"] == abi.KIND_VIRTUAL]
+    assert 0.45 < v["upsidedown"].mean() < 0.55
+    assert np.all(v["n_bg"] >= 3) and np.all(v["n_bg"] <= 5) and np.all(v["n_fg"] <= 4) and np.all(v["n_vrtl"] <= 7)
+    codes = v["ops"]["code"][:, 0]
+    assert 0.2 < (codes == abi.OP_DOWNUP).mean() < 0.3  # ApplyChoice(downscale_upscale, None, None, None)
+    x2 = big[4096:]
+    swapped = (x2["swap_choice"] >= 0).mean()
+    groups = np.diff(pool.grp_off)
+    expect = 0.2 * (groups[x2["card"]] > 1).mean()
+    assert abs(swapped - expect) < 0.03
+    assert set(np.unique(x["card"])) <= set(range(len(pool))) and len(np.unique(x["bg"])) == len(bgs)
+
+
+def test_production_batch_properties_at_full_size(env):
+    """BASELINE config 2 shape: 512 pairs, fp16 NCHW; size-independent properties."""
+    pool, bgs, ctx = env
+    tape = ctx.sample_encoder_tape(2026, 0, 512)
+    params, labels = ctx.expand_params(tape)
+    x = ctx.encoder_batch(params, abi.OUT_F16)
+    x_again = ctx.encoder_batch(params, abi.OUT_F16)
+    torch.cuda.synchronize()
+    assert x.shape == (1024, 3, 192, 128) and x.dtype == torch.float16 and x.is_contiguous()
+    assert torch.equal(x, x_again)  # idempotent: same params -> same bytes (Philox fields, no atomics)
+    assert bool(torch.isfinite(x.float()).all())
+    assert float(x.float().min()) > -1.0 and float(x.float().max()) < 2.0  # cubic overshoot only
+    p = params.cpu().numpy().view(abi.PARAMS_DTYPE).reshape(-1)
+    assert np.all(p["status"] == 0)
+    lab = labels.cpu().numpy()
+    assert np.array_equal(lab, pool.labels3[p["card"]].astype(np.int64))
+    same_name = lab[:512, 1] == lab[512:, 1]
+    assert same_name.all()  # x2 is the same card or a same-name hard negative
+    u8 = ctx.encoder_batch(params, abi.OUT_U8)
+    d = (u8.float() - (x.float().clamp(0, 1) * 255)).abs().max()
+    assert float(d) <= 0.75  # uint8 output is the rounding of the same float32 planes
+
+
+def test_dataset_dropin_surface():
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from mtgvision_b200.encoder_train import RanMtgEncDecDataset
+
+    pool, bgs = PU.small_pools(8, 8)
+    ds = RanMtgEncDecDataset(16, paired=True, targets=True, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=IlsvrcImages(images=bgs),
+                             seed=3, check_data=True)
+    b = next(iter(ds))
+    assert set(b) == {"x", "x2", "y", "x_labels", "x2_labels"}
+    assert b["x"].shape == b["x2"].shape == b["y"].shape == (16, 3, 192, 128) and b["x"].is_cuda
+    assert b["x_labels"].shape == (16, 3) and b["x_labels"].dtype == torch.int64
+    nb = ds.random_image_batch(4)
+    assert nb["x"].shape == (4, 192, 128, 3) and nb["x"].dtype == np.float32
+    ids = [pool.faces[2].id, pool.faces[5].id]
+    ib = ds.image_batch_by_ids(ids, force_target_input=True)
+    for k, i in enumerate((2, 5)):
+        ref = EO.make_cropped(EO.u8_to_f32(pool.images[i]), (192, 128))
+        assert PU.lsb_diff(ib["x"][k], ref)[0] <= 1 and np.array_equal(ib["x_labels"][k], pool.labels3[i])
+        assert np.allclose(ib["y"][k], ib["x"][k], atol=2e-3)
+    hb = ds.host_tensor_batch(torch.from_numpy(pool.images[:8]).pin_memory(), torch.from_numpy(np.stack(bgs[:8])).pin_memory())
+    assert hb["x"].shape == (8, 3, 192, 128) and not hb["x"].is_cuda
+    # static helpers with numpy in/out
+    y = SyntheticBgFgMtgImages.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128))
+    assert PU.lsb_diff(y, EO.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128)))[0] == 0
+    v = SyntheticBgFgMtgImages.make_virtual(pool.images[0], bgs[0], (192, 128), True)
+    assert v.shape == (192, 128, 3) and v.dtype == np.float32 and np.isfinite(v).all()
+    g = SyntheticBgFgMtgImages.make_bg(bgs[1], (192, 128))
+    assert g.shape == (192, 128, 3) and 0 <= g.min() and g.max() <= 1
+    m = SyntheticBgFgMtgImages.make_masked(pool.images[0])
+    assert m.shape == (680, 488, 4) and np.array_equal(m[:, :, 3], EO.round_rect_mask((680, 488), 0.05))
+    xp, yp = SyntheticBgFgMtgImages.make_virtual_pair(pool.images[0], bgs[0], (192, 128), (192, 128))
+    assert xp.shape == yp.shape == (192, 128, 3)
