@@ -61,7 +61,7 @@ void mtgv_destroy(mtgv_ctx* ctx) {
   free_cards(ctx);
   free_bgs(ctx);
   cudaFree(ctx->cfg_dev); cudaFree(ctx->alpha0); cudaFree(ctx->alpha_scratch); cudaFree(ctx->sync_words);
-  cudaFree(ctx->tmp_params);
+  cudaFree(ctx->tmp_params); cudaFree(ctx->bg_scratch);
   delete ctx;
 }
 
@@ -218,7 +218,7 @@ int mtgv_get_mask(mtgv_ctx* ctx, int which, float* out, void* stream) {
 }
 
 int mtgv_expand_params(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels, void* stream) {
-  int rc = need_encoder(ctx, true);
+  int rc = need_encoder(ctx, false);
   if (rc) return rc;
   if (!tape || !params || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_expand_params: bad arguments");
   return enc_expand(ctx, tape, n, params, labels, (cudaStream_t)stream);
@@ -226,7 +226,7 @@ int mtgv_expand_params(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc
 
 int mtgv_encoder_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
                        void* stream) {
-  int rc = need_encoder(ctx, true);
+  int rc = need_encoder(ctx, false);
   if (rc) return rc;
   if (!params || !out || n < 0 || out_dtype < 0 || out_dtype > 2)
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_encoder_batch: bad arguments");

@@ -15,6 +15,7 @@
 // oracle/cv2_restate.py.  Compiled with -fmad=false: every float multiply/add below is a
 // separate rounding, as in the reference's numpy / OpenCV scalar code.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "mtgv_internal.cuh"
 
@@ -408,11 +409,9 @@ __device__ void build_area_axis(int* s, int* n, float* w, int ssize, int dsize, 
 struct EncLaunch {
   const mtgv_enc_params* params;
   int n;
-  const uint8_t* card_planes;
-  int card_pitch;
-  const uint8_t* bg_planes;
-  const int64_t* bg_off;
   const float* alpha0;
+  const float* bg_scratch;  // [n,3,H,W] float32 from k_background
+  const float* fg_scratch;  // [n,3,H,W] float32 from k_foreground
   float* alpha_scratch;
   int* sync_words;
   void* out;
@@ -420,228 +419,556 @@ struct EncLaunch {
   const uint32_t* fields;
 };
 
-__device__ void stage_card_area(float* dst, const mtgv_enc_params& sp, const uint8_t* __restrict__ plane, int pitch,
-                                const float* lut, const AreaTabs& t) {
-  const int OH = sp.out_h, OW = sp.out_w;
-  const bool flip_src = sp.upsidedown && sp.kind == MTGV_KIND_VIRTUAL;   // rot180 of the card before masking
-  const bool flip_dst = sp.upsidedown && sp.kind == MTGV_KIND_CROPPED;   // rot180 of the resized crop
-  for (int i = threadIdx.x; i < OH * OW; i += blockDim.x) {
-    int y = i / OW, x = i % OW;
-    int ry = y - sp.fg_y0, rx = x - sp.fg_x0;
-    float v = 0.f;
-    if ((unsigned)ry < (unsigned)sp.fg_rh && (unsigned)rx < (unsigned)sp.fg_rw) {
-      const int y0 = t.ys[ry], ny = t.yn[ry], x0 = t.xs[rx], nx = t.xn[rx];
-      const float* wx = t.xw + rx * kAreaMaxTaps;
-      const float* wy = t.yw + ry * kAreaMaxTaps;
-      float sum = 0.f;
-      for (int j = 0; j < ny; j++) {
-        int sy = sp.src_y0 + y0 + j;
-        if (flip_src) sy = sp.card_h - 1 - sy;
-        const uint8_t* row = plane + (size_t)sy * pitch;
-        float h = 0.f;
-        for (int k = 0; k < nx; k++) {
-          int sx = sp.src_x0 + x0 + k;
-          if (flip_src) sx = sp.card_w - 1 - sx;
-          h = __fadd_rn(h, __fmul_rn(lut[__ldg(row + sx)], wx[k]));
-        }
-        sum = j == 0 ? __fmul_rn(wy[0], h) : __fadd_rn(sum, __fmul_rn(wy[j], h));
-      }
-      v = clip01(sum);
-    }
-    int o = flip_dst ? (OH - 1 - y) * OW + (OW - 1 - x) : i;
-    dst[o] = v;
-  }
+// k_foreground: INTER_AREA resize of one card plane (crop_to_size(pad=True) of make_virtual,
+// util/image.py:349-377, or remove_border_resized of make_cropped, :337-346) as a streaming
+// pass: every source row is read once with 16-byte loads, converted uint8 -> float32/255
+// through a LUT into a per-warp row buffer, reduced horizontally by the lanes (4 destination
+// columns each) and accumulated vertically in registers - cv2's ResizeArea_ order
+// (horizontal sums in tap order, then beta-weighted rows in source-row order).
+// One warp owns one (sample, plane, destination-row range) item; no block-level barriers.
+constexpr int kFgThreads = 256;
+constexpr int kFgWarps = kFgThreads / 32;
+constexpr int kFgRows = 32;   // max destination rows per item
+constexpr int kFgMaxQ = 8;    // destination columns per lane (out_w <= 256)
+
+__device__ __forceinline__ int fg_pos(int x) { return x + ((x >> 5) << 2); }  // skew: conflict-free 16-byte row stores
+
+// float32(b / 255.0) exactly as np.divide(u8, 255.0, dtype=float32) (util/image.py:233): one Newton
+// correction of b * fl(1/255) is correctly rounded for all 256 inputs (tests/test_host_expand.py).
+__device__ __forceinline__ float u8_over_255(uint32_t b) {
+  const float f = __uint_as_float(0x4B000000u | b) - 8388608.f;  // exact integer -> float
+  const float r = 0.003921568859368563f;                           // fl(1/255)
+  const float q = __fmul_rn(f, r);
+  const float e = __fmaf_rn(-255.f, q, f);
+  return __fmaf_rn(e, r, q);
 }
 
-// ------------------------------------------------------------------------------------ //
-// background chain + composite (make_bg + rgba_over_rgb)                                //
-// ------------------------------------------------------------------------------------ //
-
-struct BgCtx {
-  const uint8_t* src;
-  int h, w, pitch, fh, fv, nh, nw, bw0;
-  const double* rinv;
-  const double* winv;
-  const int *adelta, *bdelta, *rowX, *rowY;
-  const float* lut;
-  const float* rtile;
-  int rx0, ry0, rtw, rth;
+struct FgGeom {  // the two INTER_AREA geometries of a batch: [0] virtual (whole card, padded), [1] cropped
+  int src_h, src_w, rh, rw;
 };
 
-__device__ __forceinline__ float bg_src(const BgCtx& b, int y, int x) {
-  if ((unsigned)y >= (unsigned)b.h || (unsigned)x >= (unsigned)b.w) return 0.f;  // BORDER_CONSTANT
-  int yy = b.fv ? b.h - 1 - y : y, xx = b.fh ? b.w - 1 - x : x;                   // cv2.flip folded in
-  return b.lut[__ldg(b.src + (size_t)yy * b.pitch + xx)];
-}
-
-// one pixel of uimg.rotate_bounded's warpAffine output (canvas nh x nw)
-__device__ __forceinline__ float bg_rot(const BgCtx& b, int ry, int rx) {
-  int X = (b.rowX[ry] + b.adelta[rx]) >> 5, Y = (b.rowY[ry] + b.bdelta[rx]) >> 5;
-  int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-  float v0 = bg_src(b, sy, sx), v1 = bg_src(b, sy, sx + 1), v2 = bg_src(b, sy + 1, sx), v3 = bg_src(b, sy + 1, sx + 1);
-  return bilinear_weights_sum(v0, v1, v2, v3, X & 31, Y & 31);
-}
-
-__device__ __forceinline__ float bg_rot_cached(const BgCtx& b, int ry, int rx) {
-  if ((unsigned)ry >= (unsigned)b.nh || (unsigned)rx >= (unsigned)b.nw) return 0.f;
-  int ty = ry - b.ry0, tx = rx - b.rx0;
-  if ((unsigned)ty < (unsigned)b.rth && (unsigned)tx < (unsigned)b.rtw) return b.rtile[ty * b.rtw + tx];
-  return bg_rot(b, ry, rx);  // outside the staged tile: recompute (keeps tiling a pure optimisation)
-}
-
-// one pixel of Mutate.warp_inv's warpPerspective output
-__device__ __forceinline__ float bg_warp(const BgCtx& b, int wy, int wx) {
-  int X, Y;
-  persp_coord(b.winv, wx, wy, b.bw0, &X, &Y);
-  int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-  float v0 = bg_rot_cached(b, sy, sx), v1 = bg_rot_cached(b, sy, sx + 1);
-  float v2 = bg_rot_cached(b, sy + 1, sx), v3 = bg_rot_cached(b, sy + 1, sx + 1);
-  return bilinear_weights_sum(v0, v1, v2, v3, X & 31, Y & 31);
-}
-
-struct TileInfo {
-  int rx0, ry0, rtw, rth;
-};
-
-// cur holds the finished foreground plane; on return cur = clip(bg*(1-a) + fg*a).
-// `scratch` is the other plane (HW floats): int tables | warp tile | rotate tile.
-__device__ void stage_bg_composite(float* cur, float* scratch, const mtgv_enc_params& sp, int chan,
-                                   const uint8_t* __restrict__ bgplane, int pitch, float* lut, const AreaTabs& t,
-                                   const float* __restrict__ alpha, TileInfo* s_tile) {
-  const int OH = sp.out_h, OW = sp.out_w, HW = OH * OW;
-  const int nh = sp.rot_nh, nw = sp.rot_nw;
-  const int tid = threadIdx.x, nt = blockDim.x;
-
-  // LUT: uint8 -> float32/255 -> elementwise ops scheduled before the geometric group
-  for (int b = tid; b < 256; b += nt) {
-    float v = __fdiv_rn((float)b, 255.f);
-    for (int k = 0; k < sp.n_pre; k++) {
-      const mtgv_x_op& op = sp.ops[sp.n_fg + k];
-      if ((op.i[0] >> chan) & 1) {
-        v = __fadd_rn(__fmul_rn(op.f[chan], v), op.f[4 + chan]);
-        if (op.i[1]) v = clip01(v);
-      }
-    }
-    lut[b] = v;
+// REGW: horizontal tap weights held in registers (TAPS <= 5 taps, NQ <= 4 columns per lane: scales < 4,
+// out_w <= 128); otherwise they are read from the shared tables.
+template <bool REGW, int TAPS, int NQ>
+__device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, int c, int part, int split, int gi,
+                                        const int* __restrict__ gxs, const int* __restrict__ gxn,
+                                        const float* __restrict__ gxw, int* ys, int* yn, float* yw, float* rowbuf,
+                                        const uint8_t* __restrict__ card_planes, int pitch, float* __restrict__ fg_out,
+                                        int s, int lane) {
+  const int kind = sp->kind;
+  const int src_h = sp->src_h, rh = sp->fg_rh, rw = sp->fg_rw;
+  const int OH = sp->out_h, OW = sp->out_w, card_h = sp->card_h, card_w = sp->card_w;
+  const int src_y0 = sp->src_y0, src_x0 = sp->src_x0, fy0 = sp->fg_y0, fx0 = sp->fg_x0;
+  const bool flip_src = sp->upsidedown && kind == MTGV_KIND_VIRTUAL;  // rot180 of the card before masking
+  const bool flip_dst = sp->upsidedown && kind == MTGV_KIND_CROPPED;  // rot180 of the resized crop
+  const int rows_per = (rh + split - 1) / split;
+  const int r0 = part * rows_per, r1 = min(rh, r0 + rows_per);
+  if (r0 >= r1) return;
+  __syncwarp();
+  if (lane < r1 - r0) {
+    int st;
+    float ww[kAreaMaxTaps];
+    int nn = area_taps(src_h, rh, r0 + lane, &st, ww);
+    ys[lane] = st;
+    yn[lane] = nn;
+    for (int k = 0; k < kAreaMaxTaps; k++) yw[lane * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
   }
-  int* adelta = (int*)scratch;
-  int* bdelta = adelta + nw;
-  int* rowX = bdelta + nw;
-  int* rowY = rowX + nh;
-  float* wtile = (float*)(rowY + nh);
-  float* rtile = wtile + kWTileCap;
-  const int rcap = HW - 2 * (nw + nh) - kWTileCap;
-  for (int x = tid; x < nw; x += nt) {
-    adelta[x] = affine_col_delta(sp.rot_inv[0], x);
-    bdelta[x] = affine_col_delta(sp.rot_inv[3], x);
-  }
-  for (int y = tid; y < nh; y += nt) {
-    rowX[y] = affine_row_origin(sp.rot_inv[1], sp.rot_inv[2], y);
-    rowY[y] = affine_row_origin(sp.rot_inv[4], sp.rot_inv[5], y);
-  }
-  // crop_to_size: INTER_AREA (nh,nw)->(bg_rh,bg_rw), centre crop at (bg_y0,bg_x0)
-  build_area_axis(t.xs, t.xn, t.xw, nw, sp.bg_rw, sp.bg_x0, OW);
-  build_area_axis(t.ys, t.yn, t.yw, nh, sp.bg_rh, sp.bg_y0, OH);
-
-  BgCtx b;
-  b.src = bgplane; b.h = sp.bg_h; b.w = sp.bg_w; b.pitch = pitch; b.fh = sp.flip_h; b.fv = sp.flip_v;
-  b.nh = nh; b.nw = nw; b.bw0 = persp_block_w(nh, nw);
-  b.rinv = sp.rot_inv; b.winv = sp.winv;
-  b.adelta = adelta; b.bdelta = bdelta; b.rowX = rowX; b.rowY = rowY; b.lut = lut; b.rtile = rtile;
-
-  // tile shape: shrink until the warp_inv window of a tile fits the staging buffer
-  int TR = 16, TC = 32;
-  {
-    double sy = (double)nh / sp.bg_rh, sx = (double)nw / sp.bg_rw;
-    while (TR * TC > 1) {
-      int wh = (int)(TR * sy) + 3, ww = (int)(TC * sx) + 3;
-      if (wh * ww <= kWTileCap) break;
-      if (TC * sx >= TR * sy && TC > 1) TC >>= 1; else if (TR > 1) TR >>= 1; else TC >>= 1;
+  __syncwarp();
+  // this lane's destination columns: first source column, tap count and weights in registers
+  int x0r[REGW ? NQ : 1], nxr[REGW ? NQ : 1];
+  float wxr[REGW ? NQ : 1][REGW ? TAPS : 1];
+  if (REGW) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const int d = lane + 32 * q;
+      const bool on = d < rw;
+      x0r[q] = src_x0 + (on ? gxs[d] : 0);
+      nxr[q] = on ? gxn[d] : 0;
+#pragma unroll
+      for (int k = 0; k < TAPS; k++) wxr[q][k] = on ? gxw[d * kAreaMaxTaps + k] : 0.f;
     }
   }
-  const int n_post = sp.n_post;
-  const mtgv_x_op* post = sp.ops + sp.n_fg + sp.n_pre;
-  __syncthreads();
-
-  for (int ty0 = 0; ty0 < OH; ty0 += TR) {
-    for (int tx0 = 0; tx0 < OW; tx0 += TC) {
-      const int ty1 = min(ty0 + TR, OH), tx1 = min(tx0 + TC, OW);
-      const int wy0 = t.ys[ty0], wy1 = t.ys[ty1 - 1] + t.yn[ty1 - 1];
-      const int wx0 = t.xs[tx0], wx1 = t.xs[tx1 - 1] + t.xn[tx1 - 1];
-      const int WH = wy1 - wy0, WW = wx1 - wx0;
-      if (tid == 0) {
-        // bounding box, in rotate-canvas pixels, of the window's image under the inverse homography
-        int minx = 1 << 30, maxx = -(1 << 30), miny = 1 << 30, maxy = -(1 << 30);
-        for (int k = 0; k < 4; k++) {
-          int X, Y;
-          persp_coord(b.winv, (k & 1) ? wx1 - 1 : wx0, (k & 2) ? wy1 - 1 : wy0, b.bw0, &X, &Y);
-          int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-          minx = min(minx, sx); maxx = max(maxx, sx); miny = min(miny, sy); maxy = max(maxy, sy);
-        }
-        int x0 = max(minx - 1, 0), x1 = min(maxx + 3, nw), y0 = max(miny - 1, 0), y1 = min(maxy + 3, nh);
-        TileInfo ti;
-        ti.rx0 = x0; ti.ry0 = y0; ti.rtw = max(x1 - x0, 0); ti.rth = max(y1 - y0, 0);
-        if ((long long)ti.rtw * ti.rth > rcap || WH * WW > kWTileCap) { ti.rtw = 0; ti.rth = 0; }
-        *s_tile = ti;
-      }
-      __syncthreads();
-      b.rx0 = s_tile->rx0; b.ry0 = s_tile->ry0; b.rtw = s_tile->rtw; b.rth = s_tile->rth;
-      // rotate_bounded output for the tile's footprint
-      {
-        const int n = b.rtw * b.rth;
-        for (int k = tid; k < n; k += nt) rtile[k] = bg_rot(b, b.ry0 + k / b.rtw, b.rx0 + k % b.rtw);
-      }
-      __syncthreads();
-      const bool staged_w = WH * WW <= kWTileCap;
-      if (staged_w) {
-        // warp_inv output + elementwise ops scheduled after the geometric group
-        for (int k = tid; k < WH * WW; k += nt) {
-          float v = bg_warp(b, wy0 + k / WW, wx0 + k % WW);
-          for (int q = 0; q < n_post; q++) {
-            if ((post[q].i[0] >> chan) & 1) {
-              v = __fadd_rn(__fmul_rn(post[q].f[chan], v), post[q].f[4 + chan]);
-              if (post[q].i[1]) v = clip01(v);
-            }
-          }
-          wtile[k] = v;
-        }
-      }
-      __syncthreads();
-      // INTER_AREA reduction, clip, alpha composite (util/image.py:278-289)
-      const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
-      for (int k = tid; k < npx; k += nt) {
-        const int y = ty0 + k / tw, x = tx0 + k % tw;
-        const int y0 = t.ys[y], ny = t.yn[y], x0 = t.xs[x], nx = t.xn[x];
-        const float* wx = t.xw + x * kAreaMaxTaps;
-        const float* wy = t.yw + y * kAreaMaxTaps;
-        float sum = 0.f;
-        for (int j = 0; j < ny; j++) {
-          float h = 0.f;
-          for (int i = 0; i < nx; i++) {
-            float v;
-            if (staged_w) {
-              v = wtile[(y0 + j - wy0) * WW + (x0 + i - wx0)];
+  const uint8_t* plane = card_planes + ((size_t)sp->card * 3 + c) * card_h * pitch;
+  float* outp = fg_out + ((size_t)s * 3 + c) * OH * OW;
+  const int sy_first = ys[0], sy_last = ys[r1 - r0 - 1] + yn[r1 - r0 - 1] - 1;
+  auto row_ptr = [&](int sy) {
+    int row = src_y0 + sy;
+    if (flip_src) row = card_h - 1 - row;
+    return plane + (size_t)row * pitch;
+  };
+  const bool has16 = lane * 16 < pitch;  // fast path: pitch <= 512, one 16-byte load per lane and row
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if (has16) nxt = __ldg((const uint4*)(row_ptr(sy_first) + lane * 16));
+  int prev_sy = -1;
+  float h[NQ];
+  for (int r = r0; r < r1; r++) {
+    const int y0 = ys[r - r0], ny = yn[r - r0];
+    const float* wy = yw + (r - r0) * kAreaMaxTaps;
+    float acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) acc[q] = 0.f;
+    for (int j = 0; j < ny; j++) {
+      const int sy = y0 + j;
+      if (sy != prev_sy) {
+        prev_sy = sy;
+        const uint4 v = nxt;
+        if (has16 && sy < sy_last) nxt = __ldg((const uint4*)(row_ptr(sy + 1) + lane * 16));  // prefetch next source row
+        __syncwarp();
+        if (pitch <= 512) {
+          if (has16) {
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            if (!flip_src) {
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                float4 f;
+                f.x = u8_over_255(w4[t] & 255); f.y = u8_over_255((w4[t] >> 8) & 255);
+                f.z = u8_over_255((w4[t] >> 16) & 255); f.w = u8_over_255(w4[t] >> 24);
+                *(float4*)(rowbuf + fg_pos(lane * 16 + 4 * t)) = f;
+              }
             } else {
-              v = bg_warp(b, y0 + j, x0 + i);
-              for (int q = 0; q < n_post; q++) {
-                if ((post[q].i[0] >> chan) & 1) {
-                  v = __fadd_rn(__fmul_rn(post[q].f[chan], v), post[q].f[4 + chan]);
-                  if (post[q].i[1]) v = clip01(v);
-                }
+#pragma unroll
+              for (int t = 0; t < 16; t++) {
+                const int x = card_w - 1 - (lane * 16 + t);
+                if (x >= 0) rowbuf[fg_pos(x)] = u8_over_255((w4[t >> 2] >> (8 * (t & 3))) & 255);
               }
             }
-            h = __fadd_rn(h, __fmul_rn(v, wx[i]));
           }
-          sum = j == 0 ? __fmul_rn(wy[0], h) : __fadd_rn(sum, __fmul_rn(wy[j], h));
+        } else {  // wide cards: plain strided loop
+          const uint8_t* rp = row_ptr(sy);
+          for (int x = lane; x < card_w; x += 32) rowbuf[fg_pos(flip_src ? card_w - 1 - x : x)] = u8_over_255(__ldg(rp + x));
         }
-        const float bgv = clip01(sum);
-        const int o = y * OW + x;
-        const float a = alpha ? __ldcg(alpha + o) : 0.f;
-        const float fgv = cur[o];
-        cur[o] = clip01(__fadd_rn(__fmul_rn(bgv, __fsub_rn(1.f, a)), __fmul_rn(fgv, a)));
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          float hs = 0.f;
+          if (REGW) {
+#pragma unroll
+            for (int k = 0; k < TAPS; k++)
+              if (k < nxr[q]) hs = __fadd_rn(hs, __fmul_rn(rowbuf[fg_pos(x0r[q] + k)], wxr[q][k]));
+          } else {
+            const int d = lane + 32 * q;
+            if (d < rw) {
+              const int x0 = src_x0 + gxs[d], nx = gxn[d];
+              const float* wx = gxw + d * kAreaMaxTaps;
+              for (int k = 0; k < nx; k++) hs = __fadd_rn(hs, __fmul_rn(rowbuf[fg_pos(x0 + k)], wx[k]));
+            }
+          }
+          h[q] = hs;
+        }
       }
-      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < NQ; q++) acc[q] = j == 0 ? __fmul_rn(wy[0], h[q]) : __fadd_rn(acc[q], __fmul_rn(wy[j], h[q]));
     }
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const int d = lane + 32 * q;
+      if (d < rw) {
+        const int y = fy0 + r, x = fx0 + d;
+        const int o = flip_dst ? (OH - 1 - y) * OW + (OW - 1 - x) : y * OW + x;
+        outp[o] = clip01(acc[q]);  // img_clip after cv2.resize (util/image.py:334)
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kFgThreads, 3) k_foreground(const mtgv_enc_params* __restrict__ params, int n, int split,
+                                                           FgGeom g0, FgGeom g1, const uint8_t* __restrict__ card_planes,
+                                                           int pitch, float* __restrict__ fg_out) {
+  extern __shared__ __align__(16) unsigned char fg_smem_raw[];
+  // layout: per geometry: xs[256] xn[256] xw[256*8] | per warp: ys[32] yn[32] yw[32*8] | per warp: rowbuf
+  int* xs = (int*)fg_smem_raw;
+  int* xn = xs + 2 * 256;
+  float* xw = (float*)(xn + 2 * 256);
+  int* ytab = (int*)(xw + 2 * 256 * kAreaMaxTaps);
+  const int rowbuf_len = (pitch + (pitch >> 3) + 8 + 3) & ~3;  // keeps every warp's buffer 16-byte aligned
+  float* rowbufs = (float*)(ytab + kFgWarps * kFgRows * (2 + kAreaMaxTaps));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_maxtaps[2];
+  if (tid < 2) s_maxtaps[tid] = 0;
+  __syncthreads();
+  for (int q = tid; q < 2 * 256; q += blockDim.x) {
+    const FgGeom& g = q < 256 ? g0 : g1;
+    const int d = q & 255;
+    int st = 0, nn = 0;
+    float ww[kAreaMaxTaps];
+    if (d < g.rw && g.rw > 0) nn = area_taps(g.src_w, g.rw, d, &st, ww);
+    xs[q] = st;
+    xn[q] = nn;
+    for (int k = 0; k < kAreaMaxTaps; k++) xw[q * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
+    if (nn > 5) atomicMax(&s_maxtaps[q >> 8], nn);
+  }
+  __syncthreads();
+  int* ys = ytab + warp * kFgRows * (2 + kAreaMaxTaps);
+  int* yn = ys + kFgRows;
+  float* yw = (float*)(yn + kFgRows);
+  float* rowbuf = rowbufs + (size_t)warp * rowbuf_len;
+  const int n_items = n * 3 * split;
+  for (int item = blockIdx.x * kFgWarps + warp; item < n_items; item += gridDim.x * kFgWarps) {
+    const int s = item / (3 * split), rem = item - s * 3 * split, c = rem / split, part = rem - c * split;
+    const mtgv_enc_params* sp = params + s;
+    const int kind = sp->kind;
+    if (sp->status != 0 || kind == MTGV_KIND_BG_ONLY) continue;
+    const int gi = kind == MTGV_KIND_CROPPED ? 1 : 0;
+    const FgGeom& g = gi ? g1 : g0;
+    if (sp->src_h != g.src_h || sp->src_w != g.src_w || sp->fg_rh != g.rh || sp->fg_rw != g.rw) continue;  // host invariant
+    const int* gxs = xs + gi * 256;
+    const int* gxn = xn + gi * 256;
+    const float* gxw = xw + gi * 256 * kAreaMaxTaps;
+    const bool small = s_maxtaps[gi] == 0 && g.rw <= 128;
+    if (small)
+      fg_item<true, 5, 4>(sp, c, part, split, gi, gxs, gxn, gxw, ys, yn, yw, rowbuf, card_planes, pitch, fg_out, s, lane);
+    else
+      fg_item<false, kAreaMaxTaps, kFgMaxQ>(sp, c, part, split, gi, gxs, gxn, gxw, ys, yn, yw, rowbuf, card_planes, pitch, fg_out, s, lane);
+  }
+}
+
+__host__ __device__ inline size_t fg_smem_bytes(int pitch) {
+  size_t b = 2 * 256 * (8 + 4 * kAreaMaxTaps);
+  b += (size_t)kFgWarps * kFgRows * (8 + 4 * kAreaMaxTaps);
+  b += (size_t)kFgWarps * ((pitch + (pitch >> 3) + 8 + 3) & ~3) * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+// ------------------------------------------------------------------------------------ //
+// background chain (make_bg): k_background, all three channels per tile                  //
+// ------------------------------------------------------------------------------------ //
+//
+// make_bg (mtgvision/encoder_datasets.py:774-784) = flip -> rotate_bounded (warpAffine onto
+// an (nh,nw) canvas) -> warp_inv (warpPerspective, same canvas) -> crop_to_size (INTER_AREA to
+// (rh,rw), centre crop) with tint/fade before or after the geometric group.  Only the
+// out_h x out_w crop survives, so the chain is evaluated backwards per output tile:
+// the tile's INTER_AREA window of the warp_inv image, and under the inverse homography the
+// bounding box of that window in the rotate canvas.  Both are staged in shared memory as
+// float32 (every pixel of either stage is computed once per tile, with the reference's
+// arithmetic), coordinates are generated once and shared by the three colour channels.
+
+constexpr int kBgThreads = 256;
+constexpr int kBgTR = 8, kBgTC = 32;   // output pixels per tile
+constexpr int kBgWCap = 3200;          // warp_inv pixels staged per tile and channel
+constexpr int kBgRCap = 3328;          // rotate-canvas pixels staged per tile and channel
+constexpr int kBgAxis = 320;           // max bbox extent per axis covered by the fixed-point tables
+constexpr int kBgWRows = 64, kBgWBlk = 4;
+
+struct BgSmem {
+  float lut[3][256];
+  float wtile[3][kBgWCap];
+  float rtile[3][kBgRCap];
+  double org[kBgWRows * kBgWBlk * 3];  // X0,Y0,W0 of WarpPerspectiveInvoker per (row, column block)
+  int colA[kBgAxis], colB[kBgAxis], rowX[kBgAxis], rowY[kBgAxis];
+  int xs[kBgTC], xn[kBgTC], ys[kBgTR], yn[kBgTR];
+  float xw[kBgTC * kAreaMaxTaps], yw[kBgTR * kAreaMaxTaps];
+  float post_a[2][3], post_b[2][3];
+  int post_on[2][3], post_clip[2];
+  int tile[8];  // rx0, ry0, rtw, rth, staged flag
+  mtgv_enc_params sp;
+};
+
+struct BgView {
+  const uint8_t* src;
+  int h, w, pitch, fh, fv, nh, nw;
+  size_t plane;  // bytes per channel plane
+};
+
+// three channels of one flipped-source pixel (BORDER_CONSTANT 0 outside)
+__device__ __forceinline__ void bg_src3(const BgView& b, const BgSmem& S, int y, int x, float* v) {
+  if ((unsigned)y >= (unsigned)b.h || (unsigned)x >= (unsigned)b.w) {
+    v[0] = v[1] = v[2] = 0.f;
+    return;
+  }
+  int yy = b.fv ? b.h - 1 - y : y, xx = b.fh ? b.w - 1 - x : x;  // cv2.flip folded into the index
+  const uint8_t* p = b.src + (size_t)yy * b.pitch + xx;
+  v[0] = S.lut[0][__ldg(p)];
+  v[1] = S.lut[1][__ldg(p + b.plane)];
+  v[2] = S.lut[2][__ldg(p + 2 * b.plane)];
+}
+
+// one pixel of rotate_bounded's warpAffine output from fixed-point coordinates (X, Y in 1/32 px)
+__device__ __forceinline__ void bg_rot3(const BgView& b, const BgSmem& S, int X, int Y, float* out) {
+  int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+  float v0[3], v1[3], v2[3], v3[3];
+  bg_src3(b, S, sy, sx, v0);
+  bg_src3(b, S, sy, sx + 1, v1);
+  bg_src3(b, S, sy + 1, sx, v2);
+  bg_src3(b, S, sy + 1, sx + 1, v3);
+#pragma unroll
+  for (int c = 0; c < 3; c++) out[c] = bilinear_weights_sum(v0[c], v1[c], v2[c], v3[c], X & 31, Y & 31);
+}
+
+__device__ __forceinline__ void bg_rot3_at(const BgView& b, const BgSmem& S, int ry, int rx, float* out) {
+  if ((unsigned)ry >= (unsigned)b.nh || (unsigned)rx >= (unsigned)b.nw) {
+    out[0] = out[1] = out[2] = 0.f;
+    return;
+  }
+  int ty = ry - S.tile[1], tx = rx - S.tile[0];
+  if ((unsigned)ty < (unsigned)S.tile[3] && (unsigned)tx < (unsigned)S.tile[2]) {
+    int k = ty * S.tile[2] + tx;
+    out[0] = S.rtile[0][k]; out[1] = S.rtile[1][k]; out[2] = S.rtile[2][k];
+    return;
+  }
+  // outside the staged footprint: recompute (keeps the tiling a pure optimisation)
+  const double* m = S.sp.rot_inv;
+  int X = (affine_row_origin(m[1], m[2], ry) + affine_col_delta(m[0], rx)) >> 5;
+  int Y = (affine_row_origin(m[4], m[5], ry) + affine_col_delta(m[3], rx)) >> 5;
+  bg_rot3(b, S, X, Y, out);
+}
+
+__global__ void __launch_bounds__(kBgThreads) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
+                                                           const uint8_t* __restrict__ bg_planes,
+                                                           const int64_t* __restrict__ bg_off, float* __restrict__ bg_out) {
+  extern __shared__ __align__(16) unsigned char bg_smem_raw[];
+  BgSmem& S = *reinterpret_cast<BgSmem*>(bg_smem_raw);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int item = blockIdx.x; item < n * n_bands; item += gridDim.x) {
+    const int s = item / n_bands, band = item % n_bands;
+    __syncthreads();
+    {
+      const uint32_t* src = (const uint32_t*)(params + s);
+      uint32_t* dst = (uint32_t*)&S.sp;
+      for (int k = tid; k < (int)(sizeof(mtgv_enc_params) / 4); k += nt) dst[k] = src[k];
+    }
+    __syncthreads();
+    const mtgv_enc_params& sp = S.sp;
+    if (sp.status != 0 || sp.kind == MTGV_KIND_CROPPED) continue;
+    const int OH = sp.out_h, OW = sp.out_w, nh = sp.rot_nh, nw = sp.rot_nw;
+    // uint8 -> float32/255 -> elementwise ops scheduled before the geometric group, per channel
+    for (int q = tid; q < 768; q += nt) {
+      const int c = q >> 8;
+      float v = __fdiv_rn((float)(q & 255), 255.f);
+      for (int k = 0; k < sp.n_pre; k++) {
+        const mtgv_x_op& op = sp.ops[sp.n_fg + k];
+        if ((op.i[0] >> c) & 1) {
+          v = __fadd_rn(__fmul_rn(op.f[c], v), op.f[4 + c]);
+          if (op.i[1]) v = clip01(v);
+        }
+      }
+      S.lut[c][q & 255] = v;
+    }
+    if (tid < 6) {  // elementwise ops scheduled after the geometric group
+      const int q = tid / 3, c = tid % 3;
+      const bool on = q < sp.n_post;
+      const mtgv_x_op& op = sp.ops[sp.n_fg + sp.n_pre + (on ? q : 0)];
+      S.post_on[q][c] = on && ((op.i[0] >> c) & 1);
+      S.post_a[q][c] = op.f[c];
+      S.post_b[q][c] = op.f[4 + c];
+      if (c == 0) S.post_clip[q] = on && op.i[1];
+    }
+    BgView b;
+    b.h = sp.bg_h; b.w = sp.bg_w; b.pitch = (sp.bg_w + 15) & ~15; b.fh = sp.flip_h; b.fv = sp.flip_v;
+    b.nh = nh; b.nw = nw; b.plane = (size_t)b.h * b.pitch;
+    b.src = bg_planes + bg_off[sp.bg];
+    const int bw0 = persp_block_w(nh, nw);
+    // tile shape: shrink until a tile's warp_inv window fits the staging buffer
+    int TR = kBgTR, TC = kBgTC;
+    {
+      const double sy = (double)nh / sp.bg_rh, sx = (double)nw / sp.bg_rw;
+      while (TR * TC > 1) {
+        int wh = (int)(TR * sy) + 3, ww = (int)(TC * sx) + 3;
+        if (wh * ww <= kBgWCap && wh <= kBgWRows && (ww + bw0 - 1) / bw0 + 1 <= kBgWBlk) break;
+        if (TC * sx >= TR * sy && TC > 1) TC >>= 1; else if (TR > 1) TR >>= 1; else TC >>= 1;
+      }
+    }
+    const int band_rows = (OH + n_bands - 1) / n_bands;
+    const int by0 = band * band_rows, by1 = min(OH, by0 + band_rows);
+    float* outp = bg_out + (size_t)s * 3 * OH * OW;
+    for (int ty0 = by0; ty0 < by1; ty0 += TR) {
+      for (int tx0 = 0; tx0 < OW; tx0 += TC) {
+        const int ty1 = min(ty0 + TR, by1), tx1 = min(tx0 + TC, OW);
+        __syncthreads();
+        // crop_to_size: INTER_AREA (nh,nw)->(bg_rh,bg_rw) tables for this tile's rows / columns
+        if (tid < tx1 - tx0) {
+          int st; float ww[kAreaMaxTaps];
+          int nn = area_taps(nw, sp.bg_rw, sp.bg_x0 + tx0 + tid, &st, ww);
+          S.xs[tid] = st; S.xn[tid] = nn;
+          for (int k = 0; k < kAreaMaxTaps; k++) S.xw[tid * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
+        } else if (tid >= 64 && tid - 64 < ty1 - ty0) {
+          const int r = tid - 64;
+          int st; float ww[kAreaMaxTaps];
+          int nn = area_taps(nh, sp.bg_rh, sp.bg_y0 + ty0 + r, &st, ww);
+          S.ys[r] = st; S.yn[r] = nn;
+          for (int k = 0; k < kAreaMaxTaps; k++) S.yw[r * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
+        }
+        __syncthreads();
+        const int wy0 = S.ys[0], wy1 = S.ys[ty1 - ty0 - 1] + S.yn[ty1 - ty0 - 1];
+        const int wx0 = S.xs[0], wx1 = S.xs[tx1 - tx0 - 1] + S.xn[tx1 - tx0 - 1];
+        const int WH = wy1 - wy0, WW = wx1 - wx0;
+        const int blk0 = wx0 / bw0, nblk = (wx1 - 1) / bw0 - blk0 + 1;
+        const bool staged = WH * WW <= kBgWCap && WH <= kBgWRows && nblk <= kBgWBlk;
+        // per (row, column block) origins of the perspective coordinate generator
+        if (staged) {
+          for (int k = tid; k < WH * nblk; k += nt) {
+            const double bx = (double)((blk0 + k % nblk) * bw0), yy = (double)(wy0 + k / nblk);
+            const double* M = sp.winv;
+            S.org[3 * k + 0] = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
+            S.org[3 * k + 1] = __dadd_rn(__dadd_rn(__dmul_rn(M[3], bx), __dmul_rn(M[4], yy)), M[5]);
+            S.org[3 * k + 2] = __dadd_rn(__dadd_rn(__dmul_rn(M[6], bx), __dmul_rn(M[7], yy)), M[8]);
+          }
+        }
+        if (tid == 0) {
+          // bounding box, in rotate-canvas pixels, of the window's image under the inverse homography
+          int minx = 1 << 30, maxx = -(1 << 30), miny = 1 << 30, maxy = -(1 << 30);
+          for (int k = 0; k < 4; k++) {
+            int X, Y;
+            persp_coord(sp.winv, (k & 1) ? wx1 - 1 : wx0, (k & 2) ? wy1 - 1 : wy0, bw0, &X, &Y);
+            int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+            minx = min(minx, sx); maxx = max(maxx, sx); miny = min(miny, sy); maxy = max(maxy, sy);
+          }
+          int x0 = max(minx - 1, 0), x1 = min(maxx + 3, nw), y0 = max(miny - 1, 0), y1 = min(maxy + 3, nh);
+          int rtw = max(x1 - x0, 0), rth = max(y1 - y0, 0);
+          if (rtw * rth > kBgRCap || rtw > kBgAxis || rth > kBgAxis || !staged) rtw = rth = 0;
+          S.tile[0] = x0; S.tile[1] = y0; S.tile[2] = rtw; S.tile[3] = rth;
+        }
+        __syncthreads();
+        const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
+        // warpAffine fixed-point tables over the footprint
+        for (int k = tid; k < rtw; k += nt) {
+          S.colA[k] = affine_col_delta(sp.rot_inv[0], rx0 + k);
+          S.colB[k] = affine_col_delta(sp.rot_inv[3], rx0 + k);
+        }
+        for (int k = tid; k < rth; k += nt) {
+          S.rowX[k] = affine_row_origin(sp.rot_inv[1], sp.rot_inv[2], ry0 + k);
+          S.rowY[k] = affine_row_origin(sp.rot_inv[4], sp.rot_inv[5], ry0 + k);
+        }
+        __syncthreads();
+        // rotate_bounded output over the footprint: one warp per footprint row
+        {
+          const int nwarps = nt >> 5, lane = tid & 31;
+          const int rs = b.fv ? -b.pitch : b.pitch, cs = b.fh ? -1 : 1;
+          for (int ty = tid >> 5; ty < rth; ty += nwarps) {
+            const int oX = S.rowX[ty], oY = S.rowY[ty];
+            for (int tx = lane; tx < rtw; tx += 32) {
+              const int X = (oX + S.colA[tx]) >> 5, Y = (oY + S.colB[tx]) >> 5;
+              const int sx = X >> 5, sy = Y >> 5;  // canvases are far below the int16 saturation of cv2's remap
+              float v[3];
+              if ((unsigned)sx < (unsigned)(b.w - 1) && (unsigned)sy < (unsigned)(b.h - 1)) {
+                // all four taps inside the source: flips folded into the base address and strides
+                const uint8_t* p = b.src + (size_t)(b.fv ? b.h - 1 - sy : sy) * b.pitch + (b.fh ? b.w - 1 - sx : sx);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  const uint8_t* pc = p + c * b.plane;
+                  v[c] = bilinear_weights_sum(S.lut[c][__ldg(pc)], S.lut[c][__ldg(pc + cs)], S.lut[c][__ldg(pc + rs)],
+                                              S.lut[c][__ldg(pc + rs + cs)], X & 31, Y & 31);
+                }
+              } else {
+                bg_rot3(b, S, X, Y, v);
+              }
+              const int k = ty * rtw + tx;
+              S.rtile[0][k] = v[0]; S.rtile[1][k] = v[1]; S.rtile[2][k] = v[2];
+            }
+          }
+        }
+        __syncthreads();
+        if (staged) {
+          // warp_inv output over the window + elementwise ops scheduled after the geometric group
+          const double* M = sp.winv;
+          const double m0 = M[0], m3 = M[3], m6 = M[6];
+          float pa[2][3], pb[2][3];
+          int pon = 0;
+#pragma unroll
+          for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              pa[q][c] = S.post_a[q][c]; pb[q][c] = S.post_b[q][c];
+              pon |= (S.post_on[q][c] ? 1 : 0) << (q * 3 + c);
+            }
+          const int pclip = (S.post_clip[0] ? 1 : 0) | (S.post_clip[1] ? 2 : 0);
+          const int nwarps = nt >> 5, lane = tid & 31;
+          const int bw_shift = (bw0 & (bw0 - 1)) == 0 ? 31 - __clz(bw0) : -1;
+          const unsigned fast_w = rtw > 0 ? rtw - 1 : 0, fast_h = rth > 0 ? rth - 1 : 0;
+          for (int r = tid >> 5; r < WH; r += nwarps) {
+            for (int cx = lane; cx < WW; cx += 32) {
+              const int wx = wx0 + cx;
+              const int bi = bw_shift >= 0 ? wx >> bw_shift : wx / bw0;
+              const double* o = S.org + 3 * (r * nblk + (bi - blk0));
+              const double x1 = (double)(wx - bi * bw0);
+              double W = __dadd_rn(o[2], __dmul_rn(m6, x1));
+              W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+              const int X = __double2int_rn(__dmul_rn(__dadd_rn(o[0], __dmul_rn(m0, x1)), W));  // saturating, like cv2's clamp
+              const int Y = __double2int_rn(__dmul_rn(__dadd_rn(o[1], __dmul_rn(m3, x1)), W));
+              const int sx = X >> 5, sy = Y >> 5;
+              const int tx = sx - rx0, ty = sy - ry0;
+              float t0[3], t1[3], t2[3], t3[3];
+              if ((unsigned)tx < fast_w && (unsigned)ty < fast_h) {
+                const int q = ty * rtw + tx;  // 2x2 footprint inside the staged tile (hence inside the canvas)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  t0[c] = S.rtile[c][q]; t1[c] = S.rtile[c][q + 1]; t2[c] = S.rtile[c][q + rtw]; t3[c] = S.rtile[c][q + rtw + 1];
+                }
+              } else {
+                bg_rot3_at(b, S, sy, sx, t0);
+                bg_rot3_at(b, S, sy, sx + 1, t1);
+                bg_rot3_at(b, S, sy + 1, sx, t2);
+                bg_rot3_at(b, S, sy + 1, sx + 1, t3);
+              }
+              const int k = r * WW + cx;
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                float v = bilinear_weights_sum(t0[c], t1[c], t2[c], t3[c], X & 31, Y & 31);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                  if ((pon >> (q * 3 + c)) & 1) {
+                    v = __fadd_rn(__fmul_rn(pa[q][c], v), pb[q][c]);
+                    if ((pclip >> q) & 1) v = clip01(v);
+                  }
+                }
+                S.wtile[c][k] = v;
+              }
+            }
+          }
+        }
+        __syncthreads();
+        // INTER_AREA reduction + img_clip (util/image.py:334)
+        const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
+        for (int k = tid; k < npx; k += nt) {
+          const int r = k / tw, cidx = k - r * tw;
+          const int y0 = S.ys[r], ny = S.yn[r], x0 = S.xs[cidx], nx = S.xn[cidx];
+          const float* wx = S.xw + cidx * kAreaMaxTaps;
+          const float* wy = S.yw + r * kAreaMaxTaps;
+          float sum[3] = {0.f, 0.f, 0.f};
+          for (int j = 0; j < ny; j++) {
+            float h[3] = {0.f, 0.f, 0.f};
+            for (int i = 0; i < nx; i++) {
+              float v[3];
+              if (staged) {
+                const int q = (y0 + j - wy0) * WW + (x0 + i - wx0);
+                v[0] = S.wtile[0][q]; v[1] = S.wtile[1][q]; v[2] = S.wtile[2][q];
+              } else {  // window larger than the staging buffer (very large backgrounds): direct evaluation
+                int X, Y;
+                persp_coord(sp.winv, x0 + i, y0 + j, bw0, &X, &Y);
+                const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+                float v0[3], v1[3], v2[3], v3[3];
+                bg_rot3_at(b, S, sy, sx, v0); bg_rot3_at(b, S, sy, sx + 1, v1);
+                bg_rot3_at(b, S, sy + 1, sx, v2); bg_rot3_at(b, S, sy + 1, sx + 1, v3);
+                for (int c = 0; c < 3; c++) {
+                  float t = bilinear_weights_sum(v0[c], v1[c], v2[c], v3[c], X & 31, Y & 31);
+                  for (int q = 0; q < 2; q++)
+                    if (S.post_on[q][c]) {
+                      t = __fadd_rn(__fmul_rn(S.post_a[q][c], t), S.post_b[q][c]);
+                      if (S.post_clip[q]) t = clip01(t);
+                    }
+                  v[c] = t;
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < 3; c++) h[c] = __fadd_rn(h[c], __fmul_rn(v[c], wx[i]));
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) sum[c] = j == 0 ? __fmul_rn(wy[0], h[c]) : __fadd_rn(sum[c], __fmul_rn(wy[j], h[c]));
+          }
+          const int o = (ty0 + r) * OW + tx0 + cidx;
+#pragma unroll
+          for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = clip01(sum[c]);
+        }
+      }
+    }
+  }
+}
+
+// rgba_over_rgb (util/image.py:246-290): cur = clip(bg*(1-a) + fg*a); bg from k_background's output
+__device__ void stage_composite(float* cur, int HW, const float* __restrict__ bg, const float* __restrict__ alpha) {
+  for (int o = threadIdx.x; o < HW; o += blockDim.x) {
+    const float a = alpha ? __ldcg(alpha + o) : 0.f;
+    const float bgv = __ldcg(bg + o);
+    cur[o] = clip01(__fadd_rn(__fmul_rn(bgv, __fsub_rn(1.f, a)), __fmul_rn(cur[o], a)));
   }
 }
 
@@ -702,7 +1029,7 @@ __device__ __forceinline__ bool op_touches_alpha(const mtgv_x_op& op) {
 }
 
 struct SmemLayout {
-  float* P0; float* P1; float* lut; AreaTabs tabs; mtgv_enc_params* sp; TileInfo* tile; int* item;
+  float* P0; float* P1; float* lut; AreaTabs tabs; mtgv_enc_params* sp; int* item;
 };
 
 __host__ __device__ inline size_t enc_smem_bytes(int OH, int OW) {
@@ -732,7 +1059,6 @@ __device__ inline SmemLayout carve(unsigned char* raw, int OH, int OW) {
   size_t off = ((unsigned char*)f - raw + 15) & ~(size_t)15;
   s.sp = (mtgv_enc_params*)(raw + off);
   off = (off + sizeof(mtgv_enc_params) + 15) & ~(size_t)15;
-  s.tile = (TileInfo*)(raw + off);
   s.item = (int*)(raw + off + 32);
   return s;
 }
@@ -788,15 +1114,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
       continue;
     }
     const bool bg_only = sp.kind == MTGV_KIND_BG_ONLY;
-    if (bg_only) {
-      for (int i = tid; i < HW; i += nt) S.P0[i] = 0.f;
-    } else {
-      const uint8_t* cplane = L.card_planes + ((size_t)sp.card * 3 + plane) * sp.card_h * L.card_pitch;
-      for (int b = tid; b < 256; b += nt) S.lut[b] = __fdiv_rn((float)b, 255.f);  // img_float32: u8/255
-      build_area_axis(S.tabs.xs, S.tabs.xn, S.tabs.xw, sp.src_w, sp.fg_rw, 0, sp.fg_rw);
-      build_area_axis(S.tabs.ys, S.tabs.yn, S.tabs.yw, sp.src_h, sp.fg_rh, 0, sp.fg_rh);
-      __syncthreads();
-      stage_card_area(S.P0, sp, cplane, L.card_pitch, S.lut, S.tabs);
+    {
+      // foreground plane from k_foreground; zero padding around the resized card (crop_to_size pad=True)
+      const float* fg = L.fg_scratch + ((size_t)s * 3 + plane) * HW;
+      const int y0 = sp.fg_y0, y1 = sp.fg_y0 + sp.fg_rh, x0 = sp.fg_x0, x1 = sp.fg_x0 + sp.fg_rw;
+      for (int i = tid; i < HW; i += nt) {
+        const int y = i / OW, x = i - y * OW;
+        S.P0[i] = (!bg_only && y >= y0 && y < y1 && x >= x0 && x < x1) ? __ldcg(fg + i) : 0.f;
+      }
     }
     __syncthreads();
     Vm vm{{S.P0, S.P1}, 0, OH, OW, plane, L.fields, sp.seed};
@@ -809,9 +1134,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
           while (ld_acquire(flags + s) == 0) __nanosleep(200);
         __syncthreads();
       }
-      const int bpitch = (sp.bg_w + 15) & ~15;
-      const uint8_t* bplane = L.bg_planes + L.bg_off[sp.bg] + (size_t)plane * sp.bg_h * bpitch;
-      stage_bg_composite(vm.cur_p(), vm.oth_p(), sp, plane, bplane, bpitch, S.lut, S.tabs, alpha, S.tile);
+      stage_composite(vm.cur_p(), HW, L.bg_scratch + ((size_t)s * 3 + plane) * HW, alpha);
+      __syncthreads();
       const int base = sp.n_fg + sp.n_pre + sp.n_post;
       for (int k = 0; k < sp.n_vrtl; k++) vm_run_op(vm, sp.ops[base + k], base + k);
     }
@@ -1147,24 +1471,76 @@ int enc_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, in
 static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void* out, int out_dtype, const void* fields,
                            int OH, int OW, cudaStream_t st) {
   if (n <= 0) return MTGV_OK;
+  const size_t HW = (size_t)OH * OW;
   const size_t smem = enc_smem_bytes(OH, OW);
   if ((int)smem > ctx->max_smem_optin)
     return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw too large: two float32 planes must fit in 227 KB of shared memory");
-  int rc = ensure_scratch(ctx, n, (size_t)OH * OW);
+  // Samples are processed in chunks so that the background planes written by k_background
+  // (3*HW floats per sample) are still in the 126 MB L2 when k_encoder composites them.
+  int chunk = (int)((size_t)112 * 1024 * 1024 / (6 * HW * 4));
+  if (const char* e = getenv("MTGV_CHUNK")) chunk = atoi(e);
+  chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
+  int rc = ensure_scratch(ctx, chunk, HW);
   if (rc) return rc;
-  MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->sync_words, 0, ((size_t)n + 1) * 4, st));
+  if ((size_t)chunk * 6 * HW > ctx->bg_cap) {  // background planes followed by foreground planes
+    if (ctx->bg_scratch) cudaFree(ctx->bg_scratch);
+    ctx->bg_scratch = nullptr; ctx->bg_cap = 0;
+    MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_scratch, (size_t)chunk * 6 * HW * 4));
+    ctx->bg_cap = (size_t)chunk * 6 * HW;
+  }
+  float* fg_scratch = ctx->bg_scratch + (size_t)chunk * 3 * HW;
+  // the two INTER_AREA geometries a batch can contain (make_virtual / make_cropped)
+  FgGeom g0{0, 0, 0, 0}, g1{0, 0, 0, 0};
+  {
+    g0.src_h = ctx->card_h; g0.src_w = ctx->card_w;
+    if (ctx->card_h == OH && ctx->card_w == OW) { g0.rh = OH; g0.rw = OW; }
+    else { int y0, x0; crop_geometry(ctx->card_h, ctx->card_w, OH, OW, true, &g0.rh, &g0.rw, &y0, &x0); }
+    int border = (int)ceil(fmax(0.02 * ctx->card_h, 0.02 * ctx->card_w));
+    g1.src_h = ctx->card_h - 2 * border; g1.src_w = ctx->card_w - 2 * border; g1.rh = OH; g1.rw = OW;
+  }
+  if (OW > 256 || ctx->card_pitch > 4096) return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw width > 256 or card width > 4096");
+  const int fg_split = (OH + kFgRows - 1) / kFgRows > 8 ? (OH + kFgRows - 1) / kFgRows : 8;
+  const size_t fg_smem = fg_smem_bytes(ctx->card_pitch);
   static bool attr_set = false;
   if (!attr_set) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_background, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgSmem)));
+    MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->bg_blocks_per_sm, k_background, kBgThreads,
+                                                                     sizeof(BgSmem)));
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_foreground, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  EncLaunch L;
-  L.params = params; L.n = n; L.card_planes = ctx->card_planes; L.card_pitch = ctx->card_pitch;
-  L.bg_planes = ctx->bg_planes; L.bg_off = ctx->bg_off; L.alpha0 = ctx->alpha0; L.alpha_scratch = ctx->alpha_scratch;
-  L.sync_words = ctx->sync_words; L.out = out; L.out_dtype = out_dtype; L.fields = (const uint32_t*)fields;
-  int grid = 4 * n < ctx->sm_count ? 4 * n : ctx->sm_count;
-  k_encoder<<<grid, kThreads, smem, st>>>(L, OH, OW);
-  ctx->launches++;
+  const size_t elem = out_dtype == MTGV_OUT_F16 ? 2 : (out_dtype == MTGV_OUT_U8 ? 1 : 4);
+  const int n_bands = 4;
+  for (int base = 0; base < n; base += chunk) {
+    const int m = n - base < chunk ? n - base : chunk;
+    MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->sync_words, 0, ((size_t)m + 1) * 4, st));
+    if (ctx->n_bgs > 0) {
+      int grid_bg = ctx->sm_count * (ctx->bg_blocks_per_sm > 0 ? ctx->bg_blocks_per_sm : 1);
+      if (grid_bg > m * n_bands) grid_bg = m * n_bands;
+      k_background<<<grid_bg, kBgThreads, sizeof(BgSmem), st>>>(params + base, m, n_bands, ctx->bg_planes, ctx->bg_off,
+                                                                ctx->bg_scratch);
+      ctx->launches++;
+    }
+    {
+      int fg_blocks = 0;
+      MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fg_blocks, k_foreground, kFgThreads, fg_smem));
+      int grid_fg = ctx->sm_count * (fg_blocks > 0 ? fg_blocks : 1);
+      const int items = m * 3 * fg_split;
+      if (grid_fg > (items + kFgWarps - 1) / kFgWarps) grid_fg = (items + kFgWarps - 1) / kFgWarps;
+      k_foreground<<<grid_fg, kFgThreads, fg_smem, st>>>(params + base, m, fg_split, g0, g1, ctx->card_planes, ctx->card_pitch,
+                                                         fg_scratch);
+      ctx->launches++;
+    }
+    EncLaunch L;
+    L.params = params + base; L.n = m; L.fg_scratch = fg_scratch;
+    L.alpha0 = ctx->alpha0; L.bg_scratch = ctx->bg_scratch; L.alpha_scratch = ctx->alpha_scratch;
+    L.sync_words = ctx->sync_words; L.out = (char*)out + (size_t)base * 3 * HW * elem; L.out_dtype = out_dtype;
+    L.fields = (const uint32_t*)fields;
+    int grid = 4 * m < ctx->sm_count ? 4 * m : ctx->sm_count;
+    k_encoder<<<grid, kThreads, smem, st>>>(L, OH, OW);
+    ctx->launches++;
+  }
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   return MTGV_OK;
 }

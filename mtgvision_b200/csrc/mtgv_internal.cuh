@@ -42,6 +42,9 @@ struct mtgv_ctx {
   mtgv_enc_config* cfg_dev = nullptr;
   float* alpha0 = nullptr;  // static foreground alpha [out_h,out_w]: pad(area_resize(mask_enc))
   float* alpha_scratch = nullptr;
+  float* bg_scratch = nullptr;  // k_background output for one chunk: [chunk,3,H,W] float32
+  size_t bg_cap = 0;            // floats
+  int bg_blocks_per_sm = 0;
   size_t alpha_cap = 0;  // samples
   int32_t* sync_words = nullptr;  // [0] work counter, [1..] per-sample alpha-ready flags
   size_t sync_cap = 0;
