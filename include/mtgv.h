@@ -267,6 +267,112 @@ int mtgv_warp_perspective(mtgv_ctx* ctx, const float* src, int n, int sh, int sw
 int mtgv_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops,
                        const void* fields, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* Detection path (mtgvision/od_datasets.py)                                             */
+/* ------------------------------------------------------------------------------------ */
+
+#define MTGV_DET_MAX_CARDS 32    /* np.random.randint(num_cards_min, num_cards_max) - 1 <= 32 (BASELINE config 4) */
+#define MTGV_DET_MAX_ATTEMPTS 10 /* card_max_place_attempts (od_datasets.py:633)                                 */
+#define MTGV_DET_MAX_KP 8        /* points per keypoint polygon: 4 (obb) or 8 (seg)                              */
+#define MTGV_DET_MAX_KPOLY 3     /* polygons per card: 3 (obb: card, top, bottom) or 1 (seg)                     */
+#define MTGV_DET_MAX_PRE 4
+#define MTGV_DET_MAX_POST 8
+#define MTGV_DET_MAX_CARD_OPS 3
+
+/* Photometric ops: the subset of the albumentations graphs at od_datasets.py:420-512 named by the
+ * north star.  Parameters are the values after sampling (alpha/beta, shifts, sigma, rectangle). */
+typedef enum {
+  MTGV_PH_NONE = 0,
+  MTGV_PH_RBC = 1,         /* RandomBrightnessContrast: clip(x*d[0] + d[1])                          */
+  MTGV_PH_HSV = 2,         /* HueSaturationValue: d[0] hue shift (deg), d[1] sat shift, d[2] val shift (in 1/255) */
+  MTGV_PH_GAUSS_NOISE = 3, /* GaussNoise: clip(x + d[0]*N(0,1)); field = unit normals [H,W,3] f32 or PHILOX */
+  MTGV_PH_GAUSS_BLUR = 4,  /* GaussianBlur: d[0] sigma; ksize = max(3, int(6 sigma + 1) | 1), REFLECT_101    */
+  MTGV_PH_ERASE = 5        /* Erasing: i[0]=top i[1]=left i[2]=h i[3]=w i[4]=fill (0 random,1 random_uniform,
+                              2 ones,3 zeros), d[0..2]=uniform colour; field = random block [h,w,3] f32    */
+} mtgv_photo_code;
+
+typedef struct {
+  int32_t code;
+  int32_t i[5];
+  double d[3];
+  int64_t field; /* word offset into `fields` or MTGV_FIELD_PHILOX */
+} mtgv_photo_op; /* 56 bytes */
+
+typedef struct {
+  int32_t cx, cy;     /* random.randint centre (od_datasets.py:322-323)                              */
+  int32_t dst_given;  /* 1: dst[] holds the float32 corner targets computed by the host (numpy
+                         norm/arctan2/cos/sin + getRotationMatrix2D; the parity boundary)  */
+  int32_t _pad;
+  double deg;         /* np.random.uniform(0, 360)                        (:325)                    */
+  double area;        /* exp(np.random.uniform(log a_min, log a_max))     (:332)                    */
+  double jitter[4];   /* np.random.uniform(1-j, 1+j, size=4)              (:37)                     */
+  float dst[8];       /* dst_pts.astype(float32)                          (:348)                    */
+} mtgv_det_attempt;   /* 96 bytes */
+
+typedef struct {
+  int32_t card;       /* card pool index (mtg_ds.ran_path, :560) */
+  int32_t n_attempts; /* attempts available in att[] */
+  int32_t n_photo;
+  int32_t _pad;
+  mtgv_photo_op photo[MTGV_DET_MAX_CARD_OPS]; /* pre_transform_card, applied only if the card is placed (:581) */
+  mtgv_det_attempt att[MTGV_DET_MAX_ATTEMPTS];
+} mtgv_det_card;
+
+typedef struct {
+  int32_t bg_only; /* Gen.random took the ratio_bg branch (:686-687) */
+  int32_t bg;      /* background pool index */
+  int32_t bg_deg;  /* np.random.randint(0, 360) of make_background (:200) */
+  int32_t n_cards; /* np.random.randint(num_cards_min, num_cards_max) (:558) */
+  int32_t n_pre, n_post;
+  uint64_t seed;
+  int32_t bg_ab_given; /* 1: bg_ab holds the host-libm cos/sin of bg_deg (getRotationMatrix2D, :106) */
+  int32_t _pad;
+  double bg_ab[2];
+  mtgv_photo_op pre[MTGV_DET_MAX_PRE];    /* pre_transform_bg  (get_bg_transform_light) */
+  mtgv_photo_op post[MTGV_DET_MAX_POST];  /* post_transform_bg (get_bg_transform)       */
+  mtgv_det_card cards[MTGV_DET_MAX_CARDS];
+} mtgv_det_tape;
+
+typedef struct {
+  int32_t size_h, size_w;                 /* bg_size_hw (od_datasets.py:623)             */
+  int32_t num_cards_min, num_cards_max;   /* :624-625 (max exclusive, like np.random.randint) */
+  double min_visible;                     /* card_min_visible_ratio          :626 */
+  double min_visible_edges;               /* card_min_visible_ratio_edges    :627; < 0 = None */
+  double jitter_ratio;                    /* :628 */
+  double min_area_ratio, max_area_ratio;  /* :629-630 */
+  double ratio_bg;                        /* :634; 0 = None */
+  int32_t no_contains;                    /* :632 */
+  int32_t max_attempts;                   /* :633 */
+  int32_t kind;                           /* 0 obb, 1 seg  (:638) */
+  int32_t photometrics;                   /* 0 disables the albumentations stages (parity tests) */
+} mtgv_det_config;
+
+int mtgv_set_det_config(mtgv_ctx* ctx, const mtgv_det_config* cfg_host);
+
+/* Production sampler: draws what Gen.random / generate_synthetic_image draw for scenes
+ * [first_index, first_index+n) from Philox (od_datasets.py:520-611, 685-704). */
+int mtgv_sample_det_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n, mtgv_det_tape* tape, void* stream);
+
+/* Subsystem (4) + (1): placement rejection sampling and label warping on device.
+ * Replaces place_card_on_background_get_transform (:287-377, shapely tests restated with convex
+ * clipping), cv2.getPerspectiveTransform per attempt (:347), apply_transform_2d on keypoints
+ * (:352,597) and get_rotate_over_output_transform (:85-118).
+ *   params    [n] opaque scene programs for mtgv_det_batch (mtgv_det_params_size() bytes each)
+ *   accepted  [n, MAX_CARDS] int32: index of the accepted attempt per card, -1 = not placed
+ *   keypoints [n, MAX_CARDS*MAX_KPOLY, MAX_KP, 2] float64, in the reference's output order
+ *             (cards in reverse placement order, :594-601), pixel units
+ *   labels    [n, MAX_CARDS*MAX_KPOLY] int32 (keypoints_labels), -1 padding
+ *   counts    [n] int32 number of keypoint polygons */
+int mtgv_det_place(mtgv_ctx* ctx, const mtgv_det_tape* tape, int n, void* params, int32_t* accepted, double* keypoints,
+                   int32_t* labels, int32_t* counts, void* stream);
+int mtgv_det_params_size(void);
+
+/* Subsystems (2)(3)(5): background cover-warp, pre-augments, per-card warp of image + mask with
+ * alpha composite in reverse placement order, post-augments, cast.  Replaces make_background
+ * (:195-203), apply_transform_2d_img (:73-82), the composite loop (:594-601) and the
+ * albumentations calls (:552,581,604).  images: [n,3,S,S] NCHW of out_dtype. */
+int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int out_dtype, const void* fields, void* stream);
+
 /* Number of kernels launched by this context since creation (bench bookkeeping). */
 int64_t mtgv_launch_count(const mtgv_ctx* ctx);
 

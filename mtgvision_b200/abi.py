@@ -75,6 +75,42 @@ class EncConfig(C.Structure):
     ]
 
 
+# ---- detection path (mtgv_det_* in include/mtgv.h) ----
+DET_MAX_CARDS, DET_MAX_ATTEMPTS, DET_MAX_KP, DET_MAX_KPOLY = 32, 10, 8, 3
+DET_MAX_PRE, DET_MAX_POST, DET_MAX_CARD_OPS = 4, 8, 3
+PH_NONE, PH_RBC, PH_HSV, PH_GAUSS_NOISE, PH_GAUSS_BLUR, PH_ERASE = range(6)
+
+
+class PhotoOp(C.Structure):
+    _fields_ = [("code", C.c_int32), ("i", C.c_int32 * 5), ("d", C.c_double * 3), ("field", C.c_int64)]
+
+
+class DetAttempt(C.Structure):
+    _fields_ = [("cx", C.c_int32), ("cy", C.c_int32), ("dst_given", C.c_int32), ("_pad", C.c_int32),
+                ("deg", C.c_double), ("area", C.c_double), ("jitter", C.c_double * 4), ("dst", C.c_float * 8)]
+
+
+class DetCard(C.Structure):
+    _fields_ = [("card", C.c_int32), ("n_attempts", C.c_int32), ("n_photo", C.c_int32), ("_pad", C.c_int32),
+                ("photo", PhotoOp * DET_MAX_CARD_OPS), ("att", DetAttempt * DET_MAX_ATTEMPTS)]
+
+
+class DetTape(C.Structure):
+    _fields_ = [("bg_only", C.c_int32), ("bg", C.c_int32), ("bg_deg", C.c_int32), ("n_cards", C.c_int32),
+                ("n_pre", C.c_int32), ("n_post", C.c_int32), ("seed", C.c_uint64),
+                ("bg_ab_given", C.c_int32), ("_pad", C.c_int32), ("bg_ab", C.c_double * 2),
+                ("pre", PhotoOp * DET_MAX_PRE), ("post", PhotoOp * DET_MAX_POST), ("cards", DetCard * DET_MAX_CARDS)]
+
+
+class DetConfig(C.Structure):
+    _fields_ = [("size_h", C.c_int32), ("size_w", C.c_int32), ("num_cards_min", C.c_int32), ("num_cards_max", C.c_int32),
+                ("min_visible", C.c_double), ("min_visible_edges", C.c_double), ("jitter_ratio", C.c_double),
+                ("min_area_ratio", C.c_double), ("max_area_ratio", C.c_double), ("ratio_bg", C.c_double),
+                ("no_contains", C.c_int32), ("max_attempts", C.c_int32), ("kind", C.c_int32), ("photometrics", C.c_int32)]
+
+
+DET_TAPE_DTYPE = np.dtype(DetTape)
+
 assert C.sizeof(TapeOp) == 160, C.sizeof(TapeOp)
 assert C.sizeof(XOp) == 200, C.sizeof(XOp)
 
@@ -138,7 +174,14 @@ def load_library(path: str | None = None) -> C.CDLL:
     return lib
 
 
-_DET_PROTOS: dict = {}
+_vp, _i32 = C.c_void_p, C.c_int
+_DET_PROTOS: dict = {
+    "mtgv_set_det_config": (_i32, [_vp, _vp]),
+    "mtgv_sample_det_tape": (_i32, [_vp, C.c_uint64, C.c_int64, _i32, _vp, _vp]),
+    "mtgv_det_place": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mtgv_det_params_size": (_i32, []),
+    "mtgv_det_batch": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+}
 
 
 def declared_symbols() -> list[str]:

@@ -170,6 +170,55 @@ class Context:
         self._check(rc, "mtgv_encoder_targets")
         return out
 
+    # ------------------------------------------------------------------ detection path
+    def set_det_config(self, *, bg_size_hw=640, num_cards_min=1, num_cards_max=10, card_min_visible_ratio=0.5,
+                       card_min_visible_ratio_edges=1.0, card_jitter_ratio=0.3, card_min_area_ratio=0.02,
+                       card_max_area_ratio=0.9, card_no_contains=True, card_max_place_attempts=10, ratio_bg=None,
+                       kind="obb", photometrics=True):
+        hw = (bg_size_hw, bg_size_hw) if isinstance(bg_size_hw, int) else tuple(bg_size_hw)
+        cfg = abi.DetConfig(int(hw[0]), int(hw[1]), int(num_cards_min), int(num_cards_max), float(card_min_visible_ratio),
+                            -1.0 if card_min_visible_ratio_edges is None else float(card_min_visible_ratio_edges),
+                            float(card_jitter_ratio), float(card_min_area_ratio), float(card_max_area_ratio),
+                            float(ratio_bg or 0.0), int(card_no_contains), int(card_max_place_attempts),
+                            {"obb": 0, "seg": 1}[kind], int(photometrics))
+        self._check(self.lib.mtgv_set_det_config(self._h, C.byref(cfg)), "mtgv_set_det_config")
+        self.det_cfg = cfg
+
+    def sample_det_tape(self, seed: int, first_index: int, n: int) -> torch.Tensor:
+        tape = torch.empty((n, abi.DET_TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        rc = self.lib.mtgv_sample_det_tape(self._h, C.c_uint64(seed & (2**64 - 1)), C.c_int64(first_index), n, _ptr(tape),
+                                           self._stream())
+        self._check(rc, "mtgv_sample_det_tape")
+        return tape
+
+    def upload_det_tape(self, tape_np: np.ndarray) -> torch.Tensor:
+        assert tape_np.dtype == abi.DET_TAPE_DTYPE
+        return torch.from_numpy(tape_np.view(np.uint8).reshape(len(tape_np), -1).copy()).to(self.device)
+
+    def det_place(self, tape: torch.Tensor):
+        """-> (params, accepted [n,32], keypoints [n,96,8,2] f64, labels [n,96], counts [n])"""
+        n = tape.shape[0]
+        nk = abi.DET_MAX_CARDS * abi.DET_MAX_KPOLY
+        params = torch.empty((n, self.lib.mtgv_det_params_size()), dtype=torch.uint8, device=self.device)
+        accepted = torch.empty((n, abi.DET_MAX_CARDS), dtype=torch.int32, device=self.device)
+        keypoints = torch.zeros((n, nk, abi.DET_MAX_KP, 2), dtype=torch.float64, device=self.device)
+        labels = torch.empty((n, nk), dtype=torch.int32, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        rc = self.lib.mtgv_det_place(self._h, _ptr(tape), n, _ptr(params), _ptr(accepted), _ptr(keypoints), _ptr(labels),
+                                     _ptr(counts), self._stream())
+        self._check(rc, "mtgv_det_place")
+        return params, accepted, keypoints, labels, counts
+
+    def det_batch(self, params: torch.Tensor, out_dtype: int = abi.OUT_U8, fields: torch.Tensor | None = None,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+        n = params.shape[0]
+        shape = (n, 3, self.det_cfg.size_h, self.det_cfg.size_w)
+        if out is None:
+            out = torch.empty(shape, dtype=_TORCH_OUT[out_dtype], device=self.device)
+        rc = self.lib.mtgv_det_batch(self._h, _ptr(params), n, _ptr(out), out_dtype, _ptr(fields), self._stream())
+        self._check(rc, "mtgv_det_batch")
+        return out
+
     # ------------------------------------------------------------------ parity / debug entries
     def warp_perspective(self, src: torch.Tensor, M: torch.Tensor, dsize_hw) -> torch.Tensor:
         """src (n,h,w,c) float32, M (n,3,3) float64 -> (n,dh,dw,c) float32, cv2.warpPerspective semantics."""

@@ -22,6 +22,11 @@ int mtgv_sizeof(int which) {
     case 2: return (int)sizeof(mtgv_x_op);
     case 3: return (int)sizeof(mtgv_enc_params);
     case 4: return (int)sizeof(mtgv_enc_config);
+    case 5: return (int)sizeof(mtgv_photo_op);
+    case 6: return (int)sizeof(mtgv_det_attempt);
+    case 7: return (int)sizeof(mtgv_det_card);
+    case 8: return (int)sizeof(mtgv_det_tape);
+    case 9: return (int)sizeof(mtgv_det_config);
     default: return -1;
   }
 }

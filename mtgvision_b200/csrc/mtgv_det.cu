@@ -1,10 +1,741 @@
-// mtgv_det.cu - detection-scene generator kernels (placement rejection sampler, scene
-// compositor, photometrics).  Filled in after the encoder path; see DESIGN.md.
+// mtgv_det.cu - detection-scene generator for sm_100a (mtgvision/od_datasets.py).
+//
+//   k_det_sample  Philox tape of Gen.random / generate_synthetic_image draws        (production)
+//   k_det_place   subsystem (4): per scene, sequential rejection-sampled placement with the
+//                 shapely tests restated as fp64 convex clipping, homographies, warped keypoint
+//                 labels, composite list and the per-scene pixel program                (mtgv_det.cuh)
+//   k_det_pixels  subsystems (2)(3)(5): one thread per output pixel walks the scene program in
+//                 registers - background cover-warp, pre-augments, every placed card whose
+//                 footprint covers the pixel (warp of image + mask, alpha composite in reverse
+//                 placement order), post-augments, cast - and writes the pixel ONCE.  The
+//                 reference writes S*S pixels per card (od_datasets.py:594-599).  Only Gaussian
+//                 blurs need neighbours: the program is cut at each blur into passes that
+//                 ping-pong through a float32 scratch image.
+#include <cuda_fp16.h>
+
+#include "mtgv_det.cuh"
 #include "mtgv_internal.cuh"
 
 namespace mtgv {
+
+struct DetState {
+  mtgv_det_config cfg{};
+  bool set = false;
+  mtgv_det_config* cfg_dev = nullptr;
+  DetKeypoints kp{};
+  DetKeypoints* kp_dev = nullptr;
+  float* scratch[2] = {nullptr, nullptr};
+  size_t scratch_cap = 0;  // floats per buffer
+};
+
+static DetState* det_state(mtgv_ctx* ctx) {
+  if (!ctx->det) ctx->det = new DetState();
+  return (DetState*)ctx->det;
+}
+
 int det_destroy(mtgv_ctx* ctx) {
-  (void)ctx;
+  if (!ctx->det) return MTGV_OK;
+  DetState* d = (DetState*)ctx->det;
+  cudaFree(d->cfg_dev); cudaFree(d->kp_dev); cudaFree(d->scratch[0]); cudaFree(d->scratch[1]);
+  delete d;
+  ctx->det = nullptr;
   return MTGV_OK;
 }
+
+// ------------------------------------------------------------------------------------ //
+// placement kernel                                                                      //
+// ------------------------------------------------------------------------------------ //
+
+__global__ void k_det_place(const mtgv_det_tape* __restrict__ tape, int n, const mtgv_det_config* __restrict__ cfg,
+                            const DetKeypoints* __restrict__ kp, int card_h, int card_w, int n_cards, int n_bgs,
+                            const int32_t* __restrict__ bg_hw, DetParams* params, int32_t* accepted, double* keypoints,
+                            int32_t* labels, int32_t* counts) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const size_t nk = (size_t)MTGV_DET_MAX_CARDS * MTGV_DET_MAX_KPOLY;
+  det_place_scene(&tape[s], cfg, kp, card_h, card_w, n_cards, n_bgs, bg_hw, &params[s], accepted + (size_t)s * MTGV_DET_MAX_CARDS,
+                  keypoints + (size_t)s * nk * MTGV_DET_MAX_KP * 2, labels + (size_t)s * nk, counts + s);
+}
+
+// ------------------------------------------------------------------------------------ //
+// pixel helpers                                                                         //
+// ------------------------------------------------------------------------------------ //
+
+__device__ __forceinline__ float dclip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+__device__ __forceinline__ float d_u8_over_255(uint32_t b) {  // np.divide(u8, 255.0, dtype=float32), exact
+  const float f = __uint_as_float(0x4B000000u | b) - 8388608.f;
+  const float r = 0.003921568859368563f;
+  const float q = __fmul_rn(f, r);
+  return __fmaf_rn(__fmaf_rn(-255.f, q, f), r, q);
+}
+
+__device__ __forceinline__ float d_bilinear(float v0, float v1, float v2, float v3, int ax, int ay) {
+  const float fx = (float)ax * 0.03125f, fy = (float)ay * 0.03125f, gx = 1.f - fx, gy = 1.f - fy;
+  float s = __fmul_rn(v0, gy * gx);
+  s = __fadd_rn(s, __fmul_rn(v1, gy * fx));
+  s = __fadd_rn(s, __fmul_rn(v2, fy * gx));
+  return __fadd_rn(s, __fmul_rn(v3, fy * fx));
+}
+
+// cv2.cvtColor(float32 RGB -> HSV): H in degrees [0,360), S, V in [0,1] (RGB2HSV_f, color_hsv.simd.hpp)
+__device__ __forceinline__ void d_rgb2hsv(float r, float g, float b, float* h, float* s, float* v) {
+  float vmax = fmaxf(r, fmaxf(g, b)), vmin = fminf(r, fminf(g, b));
+  float diff = vmax - vmin;
+  *v = vmax;
+  *s = diff / (fabsf(vmax) + 1.1920929e-07f);
+  diff = 60.f / (diff + 1.1920929e-07f);
+  float hh;
+  if (vmax == r) hh = (g - b) * diff;
+  else if (vmax == g) hh = (b - r) * diff + 120.f;
+  else hh = (r - g) * diff + 240.f;
+  if (hh < 0.f) hh += 360.f;
+  *h = hh;
+}
+
+// cv2.cvtColor(float32 HSV -> RGB) (HSV2RGB_native)
+__device__ __forceinline__ void d_hsv2rgb(float h, float s, float v, float* r, float* g, float* b) {
+  if (s == 0.f) { *r = *g = *b = v; return; }
+  h *= (6.f / 360.f);
+  if (h < 0.f) do h += 6.f; while (h < 0.f);
+  else if (h >= 6.f) do h -= 6.f; while (h >= 6.f);
+  int sector = (int)floorf(h);
+  h -= (float)sector;
+  if ((unsigned)sector >= 6u) { sector = 0; h = 0.f; }
+  const float t0 = v, t1 = v * (1.f - s), t2 = v * (1.f - s * h), t3 = v * (1.f - s * (1.f - h));
+  switch (sector) {  // sector_data {b,g,r} = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
+    case 0: *b = t1; *g = t3; *r = t0; break;
+    case 1: *b = t1; *g = t0; *r = t2; break;
+    case 2: *b = t3; *g = t0; *r = t1; break;
+    case 3: *b = t0; *g = t2; *r = t1; break;
+    case 4: *b = t0; *g = t1; *r = t3; break;
+    default: *b = t2; *g = t1; *r = t0; break;
+  }
+}
+
+__device__ __forceinline__ void d_philox(uint64_t seed, int slot, uint32_t idx, uint32_t sub, uint32_t* r) {
+  Philox ph;
+  ph.key[0] = (uint32_t)seed ^ (0x85EBCA6Bu * (uint32_t)(slot + 1));
+  ph.key[1] = (uint32_t)(seed >> 32) ^ 0x64657421u;
+  ph(idx, sub, 0x6d746776u, 0, r);
+}
+__device__ __forceinline__ float d_unit(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float d_normal(uint32_t a, uint32_t b) {
+  return sqrtf(-2.f * logf(((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f))) * cospif(2.f * d_unit(b));
+}
+
+// pointwise photometric op on one RGB pixel at (y, x) of an image of width W (od_datasets.py:420-512)
+__device__ __forceinline__ void d_photo_point(const DetPhotoX& op, float* rgb, int y, int x, int W, uint64_t seed,
+                                              const uint32_t* __restrict__ fields) {
+  switch (op.code) {
+    case MTGV_PH_RBC:  // RandomBrightnessContrast on float32: clip(img*alpha + beta)
+#pragma unroll
+      for (int c = 0; c < 3; c++) rgb[c] = dclip01(__fadd_rn(__fmul_rn(rgb[c], op.f[0]), op.f[1]));
+      break;
+    case MTGV_PH_HSV: {  // HueSaturationValue through cv2's RGB<->HSV float conversion
+      float h, s, v;
+      d_rgb2hsv(rgb[0], rgb[1], rgb[2], &h, &s, &v);
+      h = h + op.f[0];
+      h = h - 360.f * floorf(h / 360.f);  // np.mod(h, 360)
+      s = dclip01(s + op.f[1]);
+      v = dclip01(v + op.f[2]);
+      d_hsv2rgb(h, s, v, &rgb[0], &rgb[1], &rgb[2]);
+      break;
+    }
+    case MTGV_PH_GAUSS_NOISE: {  // GaussNoise: clip(img + sigma * N(0,1))
+      const uint32_t p = (uint32_t)(y * W + x);
+      float g[3];
+      if (op.field != MTGV_FIELD_PHILOX) {
+        const float* f = (const float*)(fields + op.field) + (size_t)p * 3;
+        g[0] = f[0]; g[1] = f[1]; g[2] = f[2];
+      } else {
+        uint32_t r[4], q[4];
+        d_philox(seed, op.slot, p, 0, r);
+        d_philox(seed, op.slot, p, 1, q);
+        g[0] = d_normal(r[0], r[1]); g[1] = d_normal(r[2], r[3]); g[2] = d_normal(q[0], q[1]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) rgb[c] = dclip01(__fadd_rn(rgb[c], __fmul_rn(g[c], op.f[0])));
+      break;
+    }
+    case MTGV_PH_ERASE: {  // Erasing: rectangle fill
+      const int ty = y - op.i[0], tx = x - op.i[1];
+      if ((unsigned)ty < (unsigned)op.i[2] && (unsigned)tx < (unsigned)op.i[3]) {
+        if (op.i[4] == 0) {
+          const uint32_t p = (uint32_t)(ty * op.i[3] + tx);
+          if (op.field != MTGV_FIELD_PHILOX) {
+            const float* f = (const float*)(fields + op.field) + (size_t)p * 3;
+            rgb[0] = f[0]; rgb[1] = f[1]; rgb[2] = f[2];
+          } else {
+            uint32_t r[4];
+            d_philox(seed, op.slot, p, 2, r);
+            rgb[0] = d_unit(r[0]); rgb[1] = d_unit(r[1]); rgb[2] = d_unit(r[2]);
+          }
+        } else {
+          rgb[0] = op.f[0]; rgb[1] = op.f[1]; rgb[2] = op.f[2];
+        }
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// pixel kernel                                                                          //
+// ------------------------------------------------------------------------------------ //
+
+constexpr int kDetTW = 32, kDetTH = 8;  // pixels per CTA tile (one thread per pixel)
+
+struct DetLaunch {
+  const DetParams* params;
+  int n, pass;
+  const uint8_t* card_planes;
+  int card_h, card_w, card_pitch;
+  const float* mask;  // round_rect_mask(card_hw, 0.046)
+  const uint8_t* bg_planes;
+  const int64_t* bg_off;
+  const int32_t* bg_hw;
+  const float* src;   // scratch written by the previous pass  [n,S,S,3] float32
+  float* dst;         // scratch for the next pass
+  void* out;
+  int out_dtype;
+  const uint32_t* fields;
+};
+
+struct DetTileSmem {
+  int32_t status, bg, n_prog, n_blur, size_h, size_w, n_cull, first, last, blur_idx, is_final, _pad;
+  double bg_Minv[9];
+  uint64_t seed;
+  DetPhotoX prog[kDetProgMax];
+  DetCardX cards[MTGV_DET_MAX_CARDS];
+  float halo[(kDetTH + 2 * (kBlurHalfMax - 1)) * (kDetTW + 2 * (kBlurHalfMax - 1)) * 3];
+  float hrow[(kDetTH + 2 * (kBlurHalfMax - 1)) * kDetTW * 3];
+};
+
+__global__ void __launch_bounds__(kDetTW * kDetTH) k_det_pixels(DetLaunch L) {
+  extern __shared__ __align__(16) unsigned char det_smem_raw[];
+  DetTileSmem& T = *reinterpret_cast<DetTileSmem*>(det_smem_raw);
+  const int s = blockIdx.z, tid = threadIdx.y * kDetTW + threadIdx.x, nt = kDetTW * kDetTH;
+  const DetParams& P = L.params[s];
+  const int tx0 = blockIdx.x * kDetTW, ty0 = blockIdx.y * kDetTH;
+  if (tid == 0) {
+    T.status = P.status; T.bg = P.bg; T.n_prog = P.n_prog; T.n_blur = P.n_blur; T.size_h = P.size_h; T.size_w = P.size_w;
+    T.seed = P.seed;
+    // program segment of this pass: after the pass-th blur (or from the start) up to the next blur
+    int first = 0, seen = 0, blur_idx = -1;
+    if (L.pass > 0) {
+      first = P.n_prog;
+      for (int k = 0; k < P.n_prog; k++)
+        if (P.prog[k].code == MTGV_PH_GAUSS_BLUR && ++seen == L.pass) { first = k + 1; blur_idx = k; break; }
+    }
+    int last = P.n_prog;
+    for (int k = first; k < P.n_prog; k++)
+      if (P.prog[k].code == MTGV_PH_GAUSS_BLUR) { last = k; break; }
+    T.first = first; T.last = last; T.blur_idx = blur_idx; T.is_final = last == P.n_prog;
+  }
+  __syncthreads();
+  if (T.status != 0) {  // failed scenes produce zeros (the host raises from the status word)
+    if (L.pass == 0) {
+      const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
+      if (x < T.size_w && y < T.size_h) {
+        const size_t plane = (size_t)T.size_h * T.size_w, o = (size_t)y * T.size_w + x;
+        for (int c = 0; c < 3; c++) {
+          const size_t idx = ((size_t)s * 3 + c) * plane + o;
+          if (L.out_dtype == MTGV_OUT_F16) ((__half*)L.out)[idx] = __float2half_rn(0.f);
+          else if (L.out_dtype == MTGV_OUT_U8) ((uint8_t*)L.out)[idx] = 0;
+          else ((float*)L.out)[idx] = 0.f;
+        }
+      }
+    }
+    return;
+  }
+  if (L.pass > T.n_blur) return;  // this scene finished in an earlier pass
+  const int S_h = T.size_h, S_w = T.size_w;
+  for (int k = tid; k < (int)(sizeof(DetPhotoX) / 4) * T.n_prog; k += nt) ((uint32_t*)T.prog)[k] = ((const uint32_t*)P.prog)[k];
+  if (tid < 9) T.bg_Minv[tid] = P.bg_Minv[tid];
+  // does this segment composite the cards?  cull them against the tile
+  bool has_cards = false;
+  for (int k = T.first; k < T.last; k++) has_cards |= P.prog[k].code == kPhCards;
+  if (tid == 0) {
+    int nc = 0;
+    if (has_cards)
+      for (int k = 0; k < P.n_placed; k++) {
+        const DetCardX& c = P.cards[k];
+        if (c.x0 < tx0 + kDetTW && c.x1 > tx0 && c.y0 < ty0 + kDetTH && c.y1 > ty0) T.cards[nc++].card = k;  // index first
+      }
+    T.n_cull = nc;
+  }
+  __syncthreads();
+  for (int q = T.n_cull - 1; q >= 0; q--) {  // expand culled indices into full records (back to front: in place)
+    const int src_idx = T.cards[q].card;
+    __syncthreads();
+    for (int k = tid; k < (int)(sizeof(DetCardX) / 4); k += nt) ((uint32_t*)&T.cards[q])[k] = ((const uint32_t*)&P.cards[src_idx])[k];
+  }
+  __syncthreads();
+
+  const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
+  const bool live = x < S_w && y < S_h;
+  float rgb[3] = {0.f, 0.f, 0.f};
+
+  if (L.pass == 0) {
+    // make_background: cv2.warpPerspective(bg, M, (S,S)) with the cover transform (od_datasets.py:195-203)
+    if (live) {
+      const int bh = L.bg_hw[2 * T.bg], bw = L.bg_hw[2 * T.bg + 1], pitch = (bw + 15) & ~15;
+      const uint8_t* src = L.bg_planes + L.bg_off[T.bg];
+      const size_t plane = (size_t)bh * pitch;
+      int X, Y;
+      persp_coord(T.bg_Minv, x, y, persp_block_w(S_h, S_w), &X, &Y);
+      const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+      float v[4][3];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int yy = sy + (t >> 1), xx = sx + (t & 1);
+        const bool in = (unsigned)yy < (unsigned)bh && (unsigned)xx < (unsigned)bw;
+        const uint8_t* p = src + (size_t)(in ? yy : 0) * pitch + (in ? xx : 0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[t][c] = in ? d_u8_over_255(__ldg(p + c * plane)) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) rgb[c] = d_bilinear(v[0][c], v[1][c], v[2][c], v[3][c], X & 31, Y & 31);
+    }
+  } else {
+    // GaussianBlur that ended the previous segment: separable, BORDER_REFLECT_101, symmetric pairing
+    const DetPhotoX& bl = T.prog[T.blur_idx];
+    const int r = bl.i[0] / 2;
+    const int hw = kDetTW + 2 * r, hh = kDetTH + 2 * r;
+    const float* img = L.src + (size_t)s * S_h * S_w * 3;
+    for (int k = tid; k < hw * hh; k += nt) {
+      int yy = ty0 - r + k / hw, xx = tx0 - r + k % hw;
+      // reflect101 (possibly repeatedly for tiny images)
+      while (yy < 0 || yy >= S_h) yy = yy < 0 ? -yy : 2 * S_h - 2 - yy;
+      while (xx < 0 || xx >= S_w) xx = xx < 0 ? -xx : 2 * S_w - 2 - xx;
+      const float* p = img + ((size_t)yy * S_w + xx) * 3;
+      T.halo[3 * k] = p[0]; T.halo[3 * k + 1] = p[1]; T.halo[3 * k + 2] = p[2];
+    }
+    __syncthreads();
+    for (int k = tid; k < hh * kDetTW; k += nt) {
+      const int yy = k / kDetTW, xx = k % kDetTW;
+      const float* c0 = T.halo + (yy * hw + xx + r) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float acc = c0[c] * bl.k[0];
+        for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j] + c0[c + 3 * j]) * bl.k[j];
+        T.hrow[3 * k + c] = acc;
+      }
+    }
+    __syncthreads();
+    if (live) {
+      const float* c0 = T.hrow + ((threadIdx.y + r) * kDetTW + threadIdx.x) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float acc = c0[c] * bl.k[0];
+        for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j * kDetTW] + c0[c + 3 * j * kDetTW]) * bl.k[j];
+        rgb[c] = acc;
+      }
+    }
+  }
+
+  if (live) {
+    for (int k = T.first; k < T.last; k++) {
+      const DetPhotoX& op = T.prog[k];
+      if (op.code != kPhCards) {
+        d_photo_point(op, rgb, y, x, S_w, T.seed, L.fields);
+        continue;
+      }
+      // composite every card covering this pixel, reverse placement order (od_datasets.py:594-599)
+      const int bw0 = persp_block_w(S_h, S_w);
+      const int ch = L.card_h, cw = L.card_w, pitch = L.card_pitch;
+      for (int q = 0; q < T.n_cull; q++) {
+        const DetCardX& c = T.cards[q];
+        if (x < c.x0 || x >= c.x1 || y < c.y0 || y >= c.y1) continue;
+        int X, Y;
+        persp_coord(c.Minv, x, y, bw0, &X, &Y);
+        const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+        if (sx < -1 || sx >= cw || sy < -1 || sy >= ch) continue;  // all four taps outside: mask = 0
+        const bool x0 = sx >= 0, x1 = sx + 1 < cw, y0 = sy >= 0, y1 = sy + 1 < ch;
+        const float* mp = L.mask + (size_t)sy * cw + sx;
+        const float m = d_bilinear((y0 && x0) ? __ldg(mp) : 0.f, (y0 && x1) ? __ldg(mp + 1) : 0.f,
+                                   (y1 && x0) ? __ldg(mp + cw) : 0.f, (y1 && x1) ? __ldg(mp + cw + 1) : 0.f, X & 31, Y & 31);
+        if (m == 0.f) continue;  // mask*img + (1-mask)*bg == bg exactly
+        const uint8_t* base = L.card_planes + (size_t)c.card * 3 * ch * pitch;
+        float v[4][3];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int yy = sy + (t >> 1), xx = sx + (t & 1);
+          const bool in = (t >> 1 ? y1 : y0) && (t & 1 ? x1 : x0);
+          if (in) {
+            const uint8_t* p = base + (size_t)yy * pitch + xx;
+            float px[3];
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) px[cc] = d_u8_over_255(__ldg(p + (size_t)cc * ch * pitch));
+            for (int o = 0; o < c.n_ops; o++) d_photo_point(c.ops[o], px, yy, xx, cw, T.seed, L.fields);  // pre_transform_card (:581)
+            v[t][0] = px[0]; v[t][1] = px[1]; v[t][2] = px[2];
+          } else {
+            v[t][0] = v[t][1] = v[t][2] = 0.f;
+          }
+        }
+        const float im = __fsub_rn(1.f, m);
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) {
+          const float w = d_bilinear(v[0][cc], v[1][cc], v[2][cc], v[3][cc], X & 31, Y & 31);
+          rgb[cc] = __fadd_rn(__fmul_rn(m, w), __fmul_rn(im, rgb[cc]));
+        }
+      }
+    }
+    const size_t o = (size_t)y * S_w + x;
+    if (!T.is_final) {
+      float* d = L.dst + ((size_t)s * S_h * S_w + o) * 3;
+      d[0] = rgb[0]; d[1] = rgb[1]; d[2] = rgb[2];
+    } else {
+      const size_t plane = (size_t)S_h * S_w;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const size_t idx = ((size_t)s * 3 + c) * plane + o;
+        if (L.out_dtype == MTGV_OUT_F16) ((__half*)L.out)[idx] = __float2half_rn(rgb[c]);
+        else if (L.out_dtype == MTGV_OUT_U8) ((uint8_t*)L.out)[idx] = (uint8_t)(dclip01(rgb[c]) * 255.f);  // imwrite: (img*255).astype(uint8)
+        else ((float*)L.out)[idx] = rgb[c];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// production sampler                                                                    //
+// ------------------------------------------------------------------------------------ //
+
+struct DRng {
+  Philox ph;
+  uint32_t c0, c1, ctr, buf[4];
+  int have;
+  __device__ DRng(uint64_t seed, uint64_t index) {
+    ph.key[0] = (uint32_t)seed ^ 0x64657400u; ph.key[1] = (uint32_t)(seed >> 32);
+    c0 = (uint32_t)index; c1 = (uint32_t)(index >> 32); ctr = 0; have = 0;
+  }
+  __device__ uint32_t u32() { if (!have) { ph(c0, c1, 7u, ctr++, buf); have = 4; } return buf[--have]; }
+  __device__ double uniform() {
+    uint32_t a = u32() >> 5, b = u32() >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+  }
+  __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * uniform(); }
+  __device__ int below(int n) { return (int)(((uint64_t)u32() * (uint32_t)n) >> 32); }
+};
+
+__device__ void ph_init(mtgv_photo_op* o, int code) {
+  o->code = code;
+  for (int k = 0; k < 5; k++) o->i[k] = 0;
+  for (int k = 0; k < 3; k++) o->d[k] = 0.0;
+  o->field = MTGV_FIELD_PHILOX;
+}
+__device__ int ph_rbc(DRng& r, mtgv_photo_op* o, double p, double b, double c0, double c1) {
+  if (!(r.uniform() < p)) return 0;
+  ph_init(o, MTGV_PH_RBC);
+  o->d[0] = 1.0 + r.uniform(c0, c1);
+  o->d[1] = r.uniform(-b, b);
+  return 1;
+}
+__device__ int ph_hsv(DRng& r, mtgv_photo_op* o, double p, double val) {
+  if (!(r.uniform() < p)) return 0;
+  ph_init(o, MTGV_PH_HSV);
+  o->d[0] = r.uniform(-30, 30); o->d[1] = r.uniform(-40, 40); o->d[2] = r.uniform(-val, val);
+  return 1;
+}
+__device__ int ph_noise(DRng& r, mtgv_photo_op* o, double p, double smax) {
+  if (!(r.uniform() < p)) return 0;
+  ph_init(o, MTGV_PH_GAUSS_NOISE);
+  o->d[0] = r.uniform(0.0, smax);
+  return 1;
+}
+__device__ int ph_blur(DRng& r, mtgv_photo_op* o, double p, double smax) {
+  if (!(r.uniform() < p)) return 0;
+  ph_init(o, MTGV_PH_GAUSS_BLUR);
+  o->d[0] = r.uniform(0.0, smax);
+  return 1;
+}
+__device__ int ph_erase(DRng& r, mtgv_photo_op* o, double p, double s0, double s1, int fill, int h, int w) {
+  if (!(r.uniform() < p)) return 0;
+  const double area = r.uniform(s0, s1) * h * w, aspect = exp(r.uniform(log(0.3), log(3.3)));
+  const int eh = (int)rint(sqrt(area * aspect)), ew = (int)rint(sqrt(area / aspect));
+  if (eh < 1 || ew < 1 || eh >= h || ew >= w) return 0;
+  ph_init(o, MTGV_PH_ERASE);
+  o->i[0] = r.below(h - eh + 1); o->i[1] = r.below(w - ew + 1); o->i[2] = eh; o->i[3] = ew; o->i[4] = fill;
+  if (fill == 1) for (int k = 0; k < 3; k++) o->d[k] = r.uniform();
+  return 1;
+}
+__device__ int ph_fill(DRng& r, double p0, double p1, double p2) {  // np.random.choice(4, p)
+  const double u = r.uniform();
+  return u < p0 ? 0 : (u < p0 + p1 ? 1 : (u < p0 + p1 + p2 ? 2 : 3));
+}
+__device__ void ph_perm(DRng& r, int* idx, int n) {
+  for (int i = 0; i < n; i++) idx[i] = i;
+  for (int i = n - 1; i >= 1; i--) { int j = r.below(i + 1); int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
+}
+// one_of(noise family) / one_of(blur family): children outside the north-star subset are drawn and skipped
+__device__ int ph_noise_family(DRng& r, mtgv_photo_op* o, double p) {
+  const int c = r.below(3);
+  if (c == 0) return ph_noise(r, o, p, 0.2);
+  r.uniform();
+  return 0;
+}
+__device__ int ph_blur_family(DRng& r, mtgv_photo_op* o, double p) {
+  const int c = r.below(5);
+  if (c == 0) return ph_blur(r, o, p, 3.0);
+  r.uniform();
+  return 0;
+}
+
+__global__ void k_det_sample(uint64_t seed, int64_t first, int n, const mtgv_det_config* __restrict__ cfg, int n_cards_pool,
+                             int n_bgs, int card_h, int card_w, mtgv_det_tape* tape) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  mtgv_det_tape* t = &tape[i];
+  DRng r(seed, (uint64_t)(first + i));
+  const int S_h = cfg->size_h, S_w = cfg->size_w;
+  t->seed = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(first + i + 1));
+  t->bg_ab_given = 0; t->_pad = 0; t->bg_ab[0] = t->bg_ab[1] = 0.0;
+  t->n_pre = t->n_post = 0; t->n_cards = 0;
+  t->bg_only = cfg->ratio_bg > 0.0 && r.uniform() < cfg->ratio_bg;  // Gen.random (:686)
+  const bool ph = cfg->photometrics != 0;
+  int idx[8];
+  if (t->bg_only) {  // random_bg / make_aug_background (:206-210)
+    t->bg = r.below(n_bgs);
+    t->bg_deg = r.below(360);
+    const int fl = ph_fill(r, 0.1, 0.5, 0.2);
+    if (ph) {
+      ph_perm(r, idx, 4);
+      for (int q = 0; q < 3; q++) {
+        mtgv_photo_op* o = &t->pre[t->n_pre];
+        switch (idx[q]) {
+          case 0: t->n_pre += ph_rbc(r, o, 0.5, 0.4, -0.4, 0.4); break;
+          case 1: t->n_pre += ph_blur(r, o, 0.2, 2.0); break;
+          case 2: t->n_pre += ph_noise(r, o, 0.2, 0.1); break;
+          default: t->n_pre += ph_erase(r, o, 0.4, 0.02, 0.2, fl, S_h, S_w); break;
+        }
+      }
+    }
+    const int fe = ph_fill(r, 0.1, 0.1, 0.4);
+    if (ph) {
+      ph_perm(r, idx, 7);
+      for (int q = 0; q < 4; q++) {
+        mtgv_photo_op* o = &t->post[t->n_post];
+        switch (idx[q]) {
+          case 0: t->n_post += ph_rbc(r, o, 0.5, 0.7, -0.5, 0.5); break;
+          case 1: t->n_post += ph_hsv(r, o, 0.5, 30.0); break;
+          case 2: t->n_post += ph_noise_family(r, o, 0.5); break;
+          case 3: t->n_post += ph_blur_family(r, o, 0.5); break;
+          case 4: t->n_post += ph_noise_family(r, o, 0.1); break;
+          case 5: t->n_post += ph_blur_family(r, o, 0.1); break;
+          default: t->n_post += ph_erase(r, o, 0.4, 0.02, 0.4, fe, S_h, S_w); break;
+        }
+      }
+    }
+    return;
+  }
+  // generate_synthetic_image (:520-611)
+  const int fill_light = ph_fill(r, 0.1, 0.5, 0.2), fill_card = ph_fill(r, 0.1, 0.5, 0.2);
+  t->bg = r.below(n_bgs);
+  t->bg_deg = r.below(360);
+  if (ph) {
+    ph_perm(r, idx, 4);
+    for (int q = 0; q < 3; q++) {
+      mtgv_photo_op* o = &t->pre[t->n_pre];
+      switch (idx[q]) {
+        case 0: t->n_pre += ph_rbc(r, o, 0.5, 0.4, -0.4, 0.4); break;
+        case 1: t->n_pre += ph_blur(r, o, 0.2, 2.0); break;
+        case 2: t->n_pre += ph_noise(r, o, 0.2, 0.1); break;
+        default: t->n_pre += ph_erase(r, o, 0.4, 0.02, 0.2, fill_light, S_h, S_w); break;
+      }
+    }
+  }
+  const int span = cfg->num_cards_max - cfg->num_cards_min;
+  t->n_cards = cfg->num_cards_min + (span > 0 ? r.below(span) : 0);
+  if (t->n_cards > MTGV_DET_MAX_CARDS) t->n_cards = MTGV_DET_MAX_CARDS;
+  double edge = cfg->min_visible_edges < 0.0 ? cfg->min_visible : cfg->min_visible_edges;
+  if (edge < cfg->min_visible) edge = cfg->min_visible;
+  const int diag = (int)sqrt((double)card_h * card_h + (double)card_w * card_w);
+  const int pad = diag / 2, ovr = (int)(diag * (1.0 - edge));
+  const int lox = pad - ovr, hix = S_w - pad + ovr, loy = pad - ovr, hiy = S_h - pad + ovr;
+  const double la = log((double)S_h * S_w * cfg->min_area_ratio), lb = log((double)S_h * S_w * cfg->max_area_ratio);
+  for (int ci = 0; ci < t->n_cards; ci++) {
+    mtgv_det_card* c = &t->cards[ci];
+    c->card = r.below(n_cards_pool);
+    c->n_attempts = cfg->max_attempts < MTGV_DET_MAX_ATTEMPTS ? cfg->max_attempts : MTGV_DET_MAX_ATTEMPTS;
+    c->n_photo = 0; c->_pad = 0;
+    for (int ai = 0; ai < c->n_attempts; ai++) {
+      mtgv_det_attempt* a = &c->att[ai];
+      a->cx = lox + r.below(hix - lox + 1);  // random.randint is inclusive
+      a->cy = loy + r.below(hiy - loy + 1);
+      a->dst_given = 0; a->_pad = 0;
+      a->deg = r.uniform(0.0, 360.0);
+      a->area = exp(r.uniform(la, lb));
+      for (int k = 0; k < 4; k++) a->jitter[k] = r.uniform(1.0 - cfg->jitter_ratio, 1.0 + cfg->jitter_ratio);
+      for (int k = 0; k < 8; k++) a->dst[k] = 0.f;
+    }
+    if (ph) {  // get_card_transform (:490-512): 2 of 3
+      ph_perm(r, idx, 3);
+      for (int q = 0; q < 2; q++) {
+        mtgv_photo_op* o = &c->photo[c->n_photo];
+        switch (idx[q]) {
+          case 0: c->n_photo += ph_rbc(r, o, 0.8, 0.2, -0.4, -0.4); break;
+          case 1: c->n_photo += ph_hsv(r, o, 0.8, 0.0); break;
+          default: c->n_photo += ph_erase(r, o, 0.3, 0.02, 0.2, fill_card, card_h, card_w); break;
+        }
+      }
+    }
+  }
+  if (ph) {  // get_bg_transform (:441-487): 4 of 6
+    ph_perm(r, idx, 6);
+    for (int q = 0; q < 4; q++) {
+      mtgv_photo_op* o = &t->post[t->n_post];
+      switch (idx[q]) {
+        case 0: t->n_post += ph_rbc(r, o, 0.5, 0.4, -0.5, 0.5); break;
+        case 1: t->n_post += ph_hsv(r, o, 0.5, 0.0); break;
+        case 2: t->n_post += ph_noise_family(r, o, 0.5); break;
+        case 3: t->n_post += ph_blur_family(r, o, 0.5); break;
+        case 4: t->n_post += ph_noise_family(r, o, 0.1); break;
+        default: t->n_post += ph_blur_family(r, o, 0.1); break;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// host entry points                                                                     //
+// ------------------------------------------------------------------------------------ //
+
+static int det_ready(mtgv_ctx* ctx, DetState** out) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  DetState* d = det_state(ctx);
+  if (!d->set) return fail(ctx, MTGV_ERR_STATE, "detection config not set (mtgv_set_det_config)");
+  if (!ctx->n_cards) return fail(ctx, MTGV_ERR_STATE, "card pool not set (mtgv_set_card_pool)");
+  if (!ctx->n_bgs) return fail(ctx, MTGV_ERR_STATE, "background pool not set (mtgv_set_bg_pool)");
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return fail(ctx, MTGV_ERR_CUDA, cudaGetErrorString(e));
+  *out = d;
+  return MTGV_OK;
+}
+
+static int det_refresh_keypoints(mtgv_ctx* ctx, DetState* d) {
+  if (!d->set || !ctx->n_cards) return MTGV_OK;
+  det_keypoints(ctx->card_h, ctx->card_w, d->cfg.kind, &d->kp);
+  if (!d->kp_dev) MTGV_CUDA_OK(ctx, cudaMalloc(&d->kp_dev, sizeof(DetKeypoints)));
+  MTGV_CUDA_OK(ctx, cudaMemcpy(d->kp_dev, &d->kp, sizeof(DetKeypoints), cudaMemcpyHostToDevice));
+  return MTGV_OK;
+}
+
 }  // namespace mtgv
+
+using namespace mtgv;
+
+extern "C" {
+
+int mtgv_det_params_size(void) { return (int)sizeof(DetParams); }
+
+int mtgv_set_det_config(mtgv_ctx* ctx, const mtgv_det_config* cfg) {
+  if (!ctx || !cfg) return MTGV_ERR_INVALID;
+  if (cfg->size_h < 8 || cfg->size_w < 8 || cfg->size_h > 8192 || cfg->size_w > 8192)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_set_det_config: bg_size_hw out of range");
+  if (cfg->num_cards_min < 0 || cfg->num_cards_max - 1 > MTGV_DET_MAX_CARDS || cfg->num_cards_max < cfg->num_cards_min)
+    return fail(ctx, MTGV_ERR_LIMIT, "mtgv_set_det_config: at most 32 cards per scene");
+  if (cfg->max_attempts < 1 || cfg->max_attempts > MTGV_DET_MAX_ATTEMPTS)
+    return fail(ctx, MTGV_ERR_LIMIT, "mtgv_set_det_config: card_max_place_attempts must be 1..10");
+  if (cfg->kind != 0 && cfg->kind != 1) return fail(ctx, MTGV_ERR_INVALID, "mtgv_set_det_config: kind must be obb (0) or seg (1)");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DetState* d = det_state(ctx);
+  if (ctx->n_cards) {
+    // random.randint(pad - ovr, S - pad + ovr) raises "empty range" in the reference when the card
+    // diagonal does not fit (od_datasets.py:320-323)
+    double edge = cfg->min_visible_edges < 0.0 ? cfg->min_visible : cfg->min_visible_edges;
+    if (edge < cfg->min_visible) edge = cfg->min_visible;
+    const int diag = (int)sqrt((double)ctx->card_h * ctx->card_h + (double)ctx->card_w * ctx->card_w);
+    const int pad = diag / 2, ovr = (int)(diag * (1.0 - edge));
+    if (cfg->size_w - pad + ovr < pad - ovr || cfg->size_h - pad + ovr < pad - ovr)
+      return fail(ctx, MTGV_ERR_INVALID, "empty range in randrange: card diagonal does not fit bg_size_hw with this card_min_visible_ratio_edges");
+  }
+  d->cfg = *cfg;
+  d->set = true;
+  if (!d->cfg_dev) MTGV_CUDA_OK(ctx, cudaMalloc(&d->cfg_dev, sizeof(mtgv_det_config)));
+  MTGV_CUDA_OK(ctx, cudaMemcpy(d->cfg_dev, cfg, sizeof(*cfg), cudaMemcpyHostToDevice));
+  return det_refresh_keypoints(ctx, d);
+}
+
+int mtgv_sample_det_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n, mtgv_det_tape* tape, void* stream) {
+  DetState* d;
+  int rc = det_ready(ctx, &d);
+  if (rc) return rc;
+  if (!tape || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_sample_det_tape: bad arguments");
+  if (n == 0) return MTGV_OK;
+  k_det_sample<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(seed, first_index, n, d->cfg_dev, ctx->n_cards, ctx->n_bgs,
+                                                               ctx->card_h, ctx->card_w, tape);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+int mtgv_det_place(mtgv_ctx* ctx, const mtgv_det_tape* tape, int n, void* params, int32_t* accepted, double* keypoints,
+                   int32_t* labels, int32_t* counts, void* stream) {
+  DetState* d;
+  int rc = det_ready(ctx, &d);
+  if (rc) return rc;
+  if (!tape || !params || !accepted || !keypoints || !labels || !counts || n < 0)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_det_place: bad arguments");
+  if (n == 0) return MTGV_OK;
+  rc = det_refresh_keypoints(ctx, d);
+  if (rc) return rc;
+  k_det_place<<<(n + 31) / 32, 32, 0, (cudaStream_t)stream>>>(tape, n, d->cfg_dev, d->kp_dev, ctx->card_h, ctx->card_w, ctx->n_cards,
+                                                              ctx->n_bgs, ctx->bg_hw, (DetParams*)params, accepted, keypoints,
+                                                              labels, counts);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int out_dtype, const void* fields, void* stream) {
+  DetState* d;
+  int rc = det_ready(ctx, &d);
+  if (rc) return rc;
+  if (!params || !images || n < 0 || out_dtype < 0 || out_dtype > 2) return fail(ctx, MTGV_ERR_INVALID, "mtgv_det_batch: bad arguments");
+  if (n == 0) return MTGV_OK;
+  const int S_h = d->cfg.size_h, S_w = d->cfg.size_w;
+  const size_t per = (size_t)S_h * S_w * 3;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_det_pixels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetTileSmem)));
+    attr_set = true;
+  }
+  // scenes are processed in chunks so the blur scratch (2 float32 images per scene) stays bounded
+  size_t chunk = ((size_t)3 << 30) / (per * 4 * 2);
+  chunk = chunk < 1 ? 1 : (chunk > (size_t)n ? (size_t)n : chunk);
+  if (d->cfg.photometrics && chunk * per > d->scratch_cap) {
+    cudaFree(d->scratch[0]); cudaFree(d->scratch[1]);
+    d->scratch[0] = d->scratch[1] = nullptr; d->scratch_cap = 0;
+    MTGV_CUDA_OK(ctx, cudaMalloc(&d->scratch[0], chunk * per * 4));
+    MTGV_CUDA_OK(ctx, cudaMalloc(&d->scratch[1], chunk * per * 4));
+    d->scratch_cap = chunk * per;
+  }
+  const size_t elem = out_dtype == MTGV_OUT_F16 ? 2 : (out_dtype == MTGV_OUT_U8 ? 1 : 4);
+  for (size_t base = 0; base < (size_t)n; base += chunk) {
+    const int m = (int)((size_t)n - base < chunk ? (size_t)n - base : chunk);
+    // one pass per Gaussian blur in the scene program plus one; k_det_place rejects programs with more
+    // than kDetMaxBlur blurs (the reference graphs hold at most 3: one in bg_light, two blur families)
+    const int passes = d->cfg.photometrics ? 1 + kDetMaxBlur : 1;
+    for (int pass = 0; pass < passes; pass++) {
+      DetLaunch L;
+      L.params = (const DetParams*)params + base; L.n = m; L.pass = pass;
+      L.card_planes = ctx->card_planes; L.card_h = ctx->card_h; L.card_w = ctx->card_w; L.card_pitch = ctx->card_pitch;
+      L.mask = ctx->mask_det; L.bg_planes = ctx->bg_planes; L.bg_off = ctx->bg_off; L.bg_hw = ctx->bg_hw;
+      L.src = pass > 0 ? d->scratch[(pass - 1) & 1] : nullptr;
+      L.dst = d->scratch[pass & 1];
+      L.out = (char*)images + base * per * elem; L.out_dtype = out_dtype; L.fields = (const uint32_t*)fields;
+      dim3 grid((S_w + kDetTW - 1) / kDetTW, (S_h + kDetTH - 1) / kDetTH, m), block(kDetTW, kDetTH);
+      k_det_pixels<<<grid, block, sizeof(DetTileSmem), st>>>(L);
+      ctx->launches++;
+    }
+  }
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+}  // extern "C"

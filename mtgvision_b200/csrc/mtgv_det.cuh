@@ -1,0 +1,358 @@
+// mtgv_det.cuh - detection path, subsystem (4): placement rejection sampling, label warping and
+// scene-program expansion for one scene.  Host/device: unit-tested on the CPU through
+// tests/host_harness against oracle/det_oracle.py, runs in k_det_place on the GPU.
+//
+// Reference: mtgvision/od_datasets.py  place_card_on_background_get_transform (:287-377),
+// apply_transform_2d (:64-70), get_rotate_over_output_transform (:85-118),
+// make_card_with_mask keypoints (:244-279), generate_synthetic_image bookkeeping (:555-611).
+#pragma once
+
+#include "../../include/mtgv.h"
+#include "mtgv_geom.cuh"
+#include "mtgv_poly.cuh"
+
+namespace mtgv {
+
+constexpr int kDetProgMax = MTGV_DET_MAX_PRE + MTGV_DET_MAX_POST + 1;
+constexpr int kPhCards = 100;  // marker in the scene program: composite the placed cards here
+constexpr int kBlurHalfMax = 10;  // sigma <= 3 -> ksize <= 19
+constexpr int kDetMaxBlur = 3;    // Gaussian blurs per scene program (one pixel pass each)
+
+struct DetPhotoX {
+  int32_t code;
+  int32_t i[5];   // ERASE: top,left,h,w,fill   BLUR: i[0] = ksize
+  float f[4];     // RBC: alpha,beta   HSV: hue, sat/255, val/255   NOISE: sigma   ERASE: colour
+  float k[kBlurHalfMax];  // BLUR: k[0] centre weight, k[j] weight at +-j
+  int32_t slot, _pad;
+  int64_t field;
+};
+
+struct DetCardX {
+  double Minv[9];       // cv::invert(M): destination -> card coordinates (cv::warpPerspective)
+  int32_t x0, y0, x1, y1;  // destination pixels that can receive a non-zero mask tap
+  int32_t card, n_ops;
+  DetPhotoX ops[MTGV_DET_MAX_CARD_OPS];
+};
+
+struct DetParams {
+  int32_t status, bg, n_placed, n_prog;
+  int32_t size_h, size_w, n_blur, _pad;
+  double bg_Minv[9];
+  uint64_t seed;
+  DetPhotoX prog[kDetProgMax];
+  DetCardX cards[MTGV_DET_MAX_CARDS];  // composite order = reverse placement order (od_datasets.py:594)
+};
+
+struct DetKeypoints {  // make_card_with_mask keypoints for the pool's card size
+  int n_poly, n_pts;
+  double pts[MTGV_DET_MAX_KPOLY][MTGV_DET_MAX_KP][2];
+  double bbox[4][2];
+};
+
+MTGV_HD void det_box(double lft, double top, double rht, double bot, double margin, double mtr, double mbr, double out[4][2]) {
+  // _box (od_datasets.py:236-242) with mlr = mrr = 1
+  out[0][0] = MTGV_DADD(lft, MTGV_DMUL(margin, 1.0)); out[0][1] = MTGV_DADD(top, MTGV_DMUL(margin, mtr));
+  out[1][0] = MTGV_DSUB(rht, MTGV_DMUL(margin, 1.0)); out[1][1] = MTGV_DADD(top, MTGV_DMUL(margin, mtr));
+  out[2][0] = MTGV_DSUB(rht, MTGV_DMUL(margin, 1.0)); out[2][1] = MTGV_DSUB(bot, MTGV_DMUL(margin, mbr));
+  out[3][0] = MTGV_DADD(lft, MTGV_DMUL(margin, 1.0)); out[3][1] = MTGV_DSUB(bot, MTGV_DMUL(margin, mbr));
+}
+
+MTGV_HDN void det_keypoints(int h, int w, int kind, DetKeypoints* kp) {
+  const double W = (double)w, H = (double)h;
+  det_box(0.0, 0.0, W, H, 0.0, 1.0, 1.0, kp->bbox);
+  if (kind == 0) {  // obb: card, top, bottom boxes
+    kp->n_poly = 3;
+    kp->n_pts = 4;
+    const double r = 0.5, m = MTGV_DMUL(0.03, (double)(w > h ? w : h));
+    det_box(0.0, 0.0, W, H, 0.0, 1.0, 1.0, kp->pts[0]);
+    double t[4][2];
+    det_box(0.0, 0.0, W, MTGV_DMUL(r, H), m, 1.0, 0.5, t);
+    for (int k = 0; k < 4; k++) { kp->pts[1][k][0] = t[k][0]; kp->pts[1][k][1] = t[k][1]; }
+    det_box(0.0, MTGV_DMUL(MTGV_DSUB(1.0, r), H), W, H, m, 0.5, 1.0, t);
+    for (int k = 0; k < 4; k++) { kp->pts[2][k][0] = t[k][0]; kp->pts[2][k][1] = t[k][1]; }
+  } else {  // seg: card box minus the bottom indent [0.4w,0.6w] x [0.5h,1.1h]; vertex order: ours (unpinned)
+    kp->n_poly = 1;
+    kp->n_pts = 8;
+    const double x0 = MTGV_DMUL(W, 0.4), x1 = MTGV_DMUL(W, 0.6), y0 = MTGV_DMUL(H, 0.5);
+    const double v[8][2] = {{0, 0}, {W, 0}, {W, H}, {x1, H}, {x1, y0}, {x0, y0}, {x0, H}, {0, H}};
+    for (int k = 0; k < 8; k++) { kp->pts[0][k][0] = v[k][0]; kp->pts[0][k][1] = v[k][1]; }
+  }
+}
+
+// apply_transform_2d (od_datasets.py:64-70): [x,y,1] @ M.T then divide.  numpy's matmul is a
+// left-to-right FMA chain on x86 hosts with FMA.
+MTGV_HD void det_apply(const double* M, double x, double y, double* ox, double* oy) {
+  double a = MTGV_DADD(MTGV_DFMA(y, M[1], MTGV_DMUL(x, M[0])), M[2]);
+  double b = MTGV_DADD(MTGV_DFMA(y, M[4], MTGV_DMUL(x, M[3])), M[5]);
+  double c = MTGV_DADD(MTGV_DFMA(y, M[7], MTGV_DMUL(x, M[6])), M[8]);
+  *ox = MTGV_DDIV(a, c);
+  *oy = MTGV_DDIV(b, c);
+}
+
+MTGV_HD bool poly_inside_convex(double px, double py, const double* poly, int n) {
+  double orient = poly_signed2(poly, n) >= 0.0 ? 1.0 : -1.0;
+  for (int e = 0; e < n; e++) {
+    int e2 = e + 1 == n ? 0 : e + 1;
+    double ex = poly[2 * e], ey = poly[2 * e + 1];
+    double dx = MTGV_DSUB(poly[2 * e2], ex), dy = MTGV_DSUB(poly[2 * e2 + 1], ey);
+    if (MTGV_DMUL(orient, MTGV_DSUB(MTGV_DMUL(dx, MTGV_DSUB(py, ey)), MTGV_DMUL(dy, MTGV_DSUB(px, ex)))) < 0.0) return false;
+  }
+  return true;
+}
+
+// area(shape n conv): shape = quad (obb) or quad minus indent (seg); conv == nullptr: whole plane
+MTGV_HDN double det_shape_area(const double* quad, const double* indent, const double* conv, int nconv) {
+  double q[2 * kPolyMax];
+  int nq;
+  if (conv) nq = clip_convex(quad, 4, conv, nconv, q);
+  else { nq = 4; for (int k = 0; k < 8; k++) q[k] = quad[k]; }
+  double a = poly_area(q, nq);
+  if (indent && nq >= 3) {
+    double t[2 * kPolyMax];
+    int nt = clip_convex(q, nq, indent, 4, t);
+    a = MTGV_DSUB(a, poly_area(t, nt));
+  }
+  return a;
+}
+
+// The accept/reject tests of od_datasets.py:353-372 (shapely restated, see oracle/det_oracle.py).
+MTGV_HDN bool det_visible(const double* kp0, int kind, int size_h, int size_w, const double* existing, int n_existing,
+                         double min_visible, double min_visible_edge, bool no_contains) {
+  double quad[8], indent_buf[8];
+  const double* indent = nullptr;
+  if (kind == 0) {
+    for (int k = 0; k < 8; k++) quad[k] = kp0[k];
+  } else {
+    const int qi[4] = {0, 1, 2, 7}, ii[4] = {5, 4, 3, 6};
+    for (int k = 0; k < 4; k++) {
+      quad[2 * k] = kp0[2 * qi[k]]; quad[2 * k + 1] = kp0[2 * qi[k] + 1];
+      indent_buf[2 * k] = kp0[2 * ii[k]]; indent_buf[2 * k + 1] = kp0[2 * ii[k] + 1];
+    }
+    indent = indent_buf;
+  }
+  const double bw = (double)size_w, bh = (double)size_h;
+  const double img[8] = {0.0, 0.0, bw, 0.0, bw, bh, 0.0, bh};
+  const double card_area = det_shape_area(quad, indent, nullptr, 0);
+  const double vis_area = det_shape_area(quad, indent, img, 4);
+  if (MTGV_DDIV(vis_area, card_area) < min_visible_edge) return false;
+  bool visible = true;
+  for (int e = 0; e < n_existing; e++) {
+    const double* pq = existing + 8 * e;
+    double pc[2 * kPolyMax];
+    int npc = clip_convex(pq, 4, img, 4, pc);
+    double inter = npc >= 3 ? det_shape_area(quad, indent, pc, npc) : 0.0;
+    if (MTGV_DDIV(MTGV_DSUB(vis_area, inter), card_area) < min_visible) { visible = false; break; }
+    double p_area = poly_area(pq, 4);
+    if (MTGV_DDIV(MTGV_DSUB(p_area, inter), p_area) < min_visible) { visible = false; break; }
+    double vis_pts[2 * kPolyMax];
+    int nv = clip_convex(quad, 4, img, 4, vis_pts);
+    bool p_contains_vis = nv >= 3;
+    for (int k = 0; k < nv && p_contains_vis; k++) p_contains_vis = poly_inside_convex(vis_pts[2 * k], vis_pts[2 * k + 1], pq, 4);
+    bool vis_contains_p = true;
+    for (int k = 0; k < 4 && vis_contains_p; k++)
+      vis_contains_p = poly_inside_convex(pq[2 * k], pq[2 * k + 1], img, 4) && poly_inside_convex(pq[2 * k], pq[2 * k + 1], quad, 4);
+    if (vis_contains_p && indent) {
+      double t[2 * kPolyMax];
+      int nt = clip_convex(pq, 4, indent, 4, t);
+      vis_contains_p = poly_area(t, nt) == 0.0;
+    }
+    if ((no_contains && p_contains_vis) || vis_contains_p) visible = false;  // precedence as written (:369)
+  }
+  return visible;
+}
+
+// float32 corner targets of one placement attempt (od_datasets.py:336-349) when the host did not
+// supply them: corner_jitter_2d -> rotate_2d -> translate_2d with the platform's libm.
+MTGV_HDN void det_attempt_dst(const mtgv_det_attempt* a, int ch, int cw, float* dst) {
+  const double src[4][2] = {{0, 0}, {(double)cw, 0}, {(double)cw, (double)ch}, {0, (double)ch}};
+  const double scale = a->area / ((double)ch * (double)cw);
+  double cx = 0, cy = 0;
+  for (int k = 0; k < 4; k++) { cx += src[k][0]; cy += src[k][1]; }
+  cx /= 4.0; cy /= 4.0;
+  double M[6];
+  const double ang = a->deg * (3.141592653589793238462643383279502884 / 180.0);
+  rotation_from_ab((double)(float)(cw / 2.0), (double)(float)(ch / 2.0), cos(ang) * scale, sin(ang) * scale, M);
+  const double tx = (double)a->cx - (cw / 2.0) * scale, ty = (double)a->cy - (ch / 2.0) * scale;
+  for (int k = 0; k < 4; k++) {
+    const double dx = src[k][0] - cx, dy = src[k][1] - cy;
+    const double d = sqrt(dx * dx + dy * dy) * a->jitter[k], th = atan2(dy, dx);
+    const double jx = cx + d * cos(th), jy = cy + d * sin(th);
+    const double rx = MTGV_DADD(MTGV_DFMA(jy, M[1], MTGV_DMUL(jx, M[0])), M[2]);
+    const double ry = MTGV_DADD(MTGV_DFMA(jy, M[4], MTGV_DMUL(jx, M[3])), M[5]);
+    dst[2 * k] = (float)(rx + tx);
+    dst[2 * k + 1] = (float)(ry + ty);
+  }
+}
+
+MTGV_HD void det_photo_clear(DetPhotoX* o) {
+  o->code = MTGV_PH_NONE;
+  for (int k = 0; k < 5; k++) o->i[k] = 0;
+  for (int k = 0; k < 4; k++) o->f[k] = 0.f;
+  for (int k = 0; k < kBlurHalfMax; k++) o->k[k] = 0.f;
+  o->slot = 0; o->_pad = 0;
+  o->field = MTGV_FIELD_PHILOX;
+}
+
+// tape op -> kernel-ready op; returns false for ops that expand to nothing
+MTGV_HDN bool det_expand_photo(const mtgv_photo_op* t, int slot, DetPhotoX* o) {
+  det_photo_clear(o);
+  o->slot = slot;
+  o->field = t->field;
+  switch (t->code) {
+    case MTGV_PH_RBC:
+      o->code = MTGV_PH_RBC; o->f[0] = (float)t->d[0]; o->f[1] = (float)t->d[1];
+      return true;
+    case MTGV_PH_HSV:
+      if (t->d[0] == 0.0 && t->d[1] == 0.0 && t->d[2] == 0.0) return false;
+      o->code = MTGV_PH_HSV;
+      o->f[0] = (float)t->d[0]; o->f[1] = (float)MTGV_DDIV(t->d[1], 255.0); o->f[2] = (float)MTGV_DDIV(t->d[2], 255.0);
+      return true;
+    case MTGV_PH_GAUSS_NOISE:
+      o->code = MTGV_PH_GAUSS_NOISE; o->f[0] = (float)t->d[0];
+      return true;
+    case MTGV_PH_GAUSS_BLUR: {
+      const double sigma = t->d[0];
+      if (!(sigma > 0.0)) return false;
+      int ksize = (int)MTGV_DADD(MTGV_DMUL(sigma, 6.0), 1.0) | 1;
+      if (ksize < 3) ksize = 3;
+      if (ksize > 2 * kBlurHalfMax - 1) ksize = 2 * kBlurHalfMax - 1;
+      const int r = ksize / 2;
+      double w[kBlurHalfMax], sum = 0.0;
+      // numpy: k = exp(-(x*x) / (2 sigma^2)); k / k.sum() with x ascending from -r (pairwise-free: <= 19 terms)
+      const double den = MTGV_DMUL(MTGV_DMUL(2.0, sigma), sigma);
+      for (int j = 0; j <= r; j++) w[j] = exp(MTGV_DDIV(-(double)(j * j), den));
+      for (int x = -r; x <= r; x++) sum = MTGV_DADD(sum, w[x < 0 ? -x : x]);
+      o->code = MTGV_PH_GAUSS_BLUR;
+      o->i[0] = ksize;
+      for (int j = 0; j <= r; j++) o->k[j] = (float)MTGV_DDIV(w[j], sum);
+      return true;
+    }
+    case MTGV_PH_ERASE:
+      if (t->i[2] <= 0 || t->i[3] <= 0) return false;
+      o->code = MTGV_PH_ERASE;
+      for (int k = 0; k < 5; k++) o->i[k] = t->i[k];
+      for (int k = 0; k < 3; k++) o->f[k] = t->i[4] == 2 ? 1.f : (t->i[4] == 3 ? 0.f : (float)t->d[k]);
+      return true;
+    default:
+      return false;
+  }
+}
+
+// One scene: background transform, sequential placement, labels, composite list, scene program.
+MTGV_HD int det_place_scene(const mtgv_det_tape* t, const mtgv_det_config* cfg, const DetKeypoints* kp, int card_h, int card_w,
+                            int n_cards_pool, int n_bgs, const int32_t* bg_hw, DetParams* P, int32_t* accepted,
+                            double* keypoints, int32_t* labels, int32_t* count) {
+  const int S_h = cfg->size_h, S_w = cfg->size_w;
+  P->status = 0; P->bg = t->bg; P->n_placed = 0; P->n_prog = 0; P->size_h = S_h; P->size_w = S_w; P->n_blur = 0; P->_pad = 0;
+  P->seed = t->seed;
+  for (int k = 0; k < MTGV_DET_MAX_CARDS; k++) accepted[k] = -1;
+  for (int k = 0; k < MTGV_DET_MAX_CARDS * MTGV_DET_MAX_KPOLY; k++) labels[k] = -1;
+  *count = 0;
+  if (t->bg < 0 || t->bg >= n_bgs || t->n_cards < 0 || t->n_cards > MTGV_DET_MAX_CARDS) return P->status = MTGV_ERR_INVALID;
+  // ---- make_background: get_rotate_over_output_transform(mode="cover") (:85-118)
+  {
+    const int h = bg_hw[2 * t->bg], w = bg_hw[2 * t->bg + 1];
+    const double oh = (double)S_h, ow = (double)S_w, mx = oh > ow ? oh : ow;
+    const double a = MTGV_DDIV(oh, mx), b = MTGV_DDIV(ow, mx);
+    const double hyp = sqrt(MTGV_DADD(MTGV_DMUL(a, a), MTGV_DMUL(b, b)));  // math.hypot
+    const double scale = MTGV_DDIV(MTGV_DMUL(hyp, mx), (double)(h < w ? h : w));
+    double alpha, beta;
+    if (t->bg_ab_given) { alpha = t->bg_ab[0]; beta = t->bg_ab[1]; }
+    else {
+      const double ang = MTGV_DMUL((double)t->bg_deg, 3.141592653589793238462643383279502884 / 180.0);
+      alpha = MTGV_DMUL(cos(ang), scale); beta = MTGV_DMUL(sin(ang), scale);
+    }
+    double R[6], M[9];
+    rotation_from_ab((double)(w / 2), (double)(h / 2), alpha, beta, R);
+    const int tx = (S_w - w) >= 0 ? (S_w - w) / 2 : -((w - S_w + 1) / 2);  // python floor division
+    const int ty = (S_h - h) >= 0 ? (S_h - h) / 2 : -((h - S_h + 1) / 2);
+    M[0] = R[0]; M[1] = R[1]; M[2] = MTGV_DADD(R[2], (double)tx);
+    M[3] = R[3]; M[4] = R[4]; M[5] = MTGV_DADD(R[5], (double)ty);
+    M[6] = 0.0; M[7] = 0.0; M[8] = 1.0;
+    invert3x3(M, P->bg_Minv);
+  }
+  // ---- placement (:555-587)
+  double min_edge = cfg->min_visible_edges < 0.0 ? cfg->min_visible : cfg->min_visible_edges;
+  if (min_edge < cfg->min_visible) min_edge = cfg->min_visible;
+  double collide[MTGV_DET_MAX_CARDS * 8];
+  double placedM[MTGV_DET_MAX_CARDS][9];
+  int placed_card[MTGV_DET_MAX_CARDS], placed_src[MTGV_DET_MAX_CARDS];
+  int n_placed = 0;
+  const float src[8] = {0.f, 0.f, (float)card_w, 0.f, (float)card_w, (float)card_h, 0.f, (float)card_h};
+  if (!t->bg_only) {
+    for (int ci = 0; ci < t->n_cards; ci++) {
+      const mtgv_det_card* c = &t->cards[ci];
+      if (c->card < 0 || c->card >= n_cards_pool) return P->status = MTGV_ERR_INVALID;
+      const int na = c->n_attempts < cfg->max_attempts ? c->n_attempts : cfg->max_attempts;
+      for (int ai = 0; ai < na && ai < MTGV_DET_MAX_ATTEMPTS; ai++) {
+        const mtgv_det_attempt* a = &c->att[ai];
+        float dst[8];
+        if (a->dst_given) for (int k = 0; k < 8; k++) dst[k] = a->dst[k];
+        else det_attempt_dst(a, card_h, card_w, dst);
+        double M[9];
+        if (!get_perspective_transform(src, dst, M)) continue;
+        double kp0[2 * MTGV_DET_MAX_KP];
+        for (int k = 0; k < kp->n_pts; k++) det_apply(M, kp->pts[0][k][0], kp->pts[0][k][1], &kp0[2 * k], &kp0[2 * k + 1]);
+        if (!det_visible(kp0, cfg->kind, S_h, S_w, collide, n_placed, cfg->min_visible, min_edge, cfg->no_contains != 0)) continue;
+        accepted[ci] = ai;
+        for (int k = 0; k < 9; k++) placedM[n_placed][k] = M[k];
+        for (int k = 0; k < 4; k++) det_apply(M, kp->bbox[k][0], kp->bbox[k][1], &collide[8 * n_placed + 2 * k], &collide[8 * n_placed + 2 * k + 1]);
+        placed_card[n_placed] = c->card;
+        placed_src[n_placed] = ci;
+        n_placed++;
+        break;
+      }
+    }
+  }
+  // ---- labels and composite list in reverse placement order (:594-601)
+  P->n_placed = n_placed;
+  int out = 0;
+  for (int r = 0; r < n_placed; r++) {
+    const int pi = n_placed - 1 - r;
+    const double* M = placedM[pi];
+    for (int q = 0; q < kp->n_poly; q++) {
+      double* dstp = keypoints + ((size_t)out * MTGV_DET_MAX_KP) * 2;
+      for (int k = 0; k < kp->n_pts; k++) det_apply(M, kp->pts[q][k][0], kp->pts[q][k][1], &dstp[2 * k], &dstp[2 * k + 1]);
+      for (int k = kp->n_pts; k < MTGV_DET_MAX_KP; k++) { dstp[2 * k] = 0.0; dstp[2 * k + 1] = 0.0; }
+      labels[out] = q;
+      out++;
+    }
+    DetCardX* cx = &P->cards[r];
+    invert3x3(M, cx->Minv);
+    double minx = 1e300, maxx = -1e300, miny = 1e300, maxy = -1e300;
+    for (int k = 0; k < 4; k++) {
+      const double x = collide[8 * pi + 2 * k], y = collide[8 * pi + 2 * k + 1];
+      minx = fmin(minx, x); maxx = fmax(maxx, x); miny = fmin(miny, y); maxy = fmax(maxy, y);
+    }
+    // bilinear taps reach one source pixel beyond the card edge: 2 px of slack in destination space
+    minx = fmax(minx - 2.0, 0.0); miny = fmax(miny - 2.0, 0.0);
+    maxx = fmin(maxx + 3.0, (double)S_w); maxy = fmin(maxy + 3.0, (double)S_h);
+    cx->x0 = (int)floor(minx); cx->y0 = (int)floor(miny);
+    cx->x1 = maxx > minx ? (int)ceil(maxx) : cx->x0; cx->y1 = maxy > miny ? (int)ceil(maxy) : cx->y0;
+    cx->card = placed_card[pi];
+    cx->n_ops = 0;
+    const mtgv_det_card* c = &t->cards[placed_src[pi]];
+    for (int k = 0; k < c->n_photo && k < MTGV_DET_MAX_CARD_OPS; k++)
+      if (cfg->photometrics && det_expand_photo(&c->photo[k], 32 + 4 * placed_src[pi] + k, &cx->ops[cx->n_ops])) cx->n_ops++;
+  }
+  *count = out;
+  // ---- scene program: pre ops, cards, post ops
+  int n = 0;
+  if (cfg->photometrics)
+    for (int k = 0; k < t->n_pre && k < MTGV_DET_MAX_PRE; k++)
+      if (det_expand_photo(&t->pre[k], k, &P->prog[n])) n++;
+  det_photo_clear(&P->prog[n]);
+  P->prog[n].code = kPhCards;
+  n++;
+  if (cfg->photometrics)
+    for (int k = 0; k < t->n_post && k < MTGV_DET_MAX_POST; k++)
+      if (det_expand_photo(&t->post[k], 8 + k, &P->prog[n])) n++;
+  P->n_prog = n;
+  int nb = 0;
+  for (int k = 0; k < n; k++) nb += P->prog[k].code == MTGV_PH_GAUSS_BLUR;
+  P->n_blur = nb;
+  if (nb > kDetMaxBlur) return P->status = MTGV_ERR_LIMIT;
+  return 0;
+}
+
+}  // namespace mtgv

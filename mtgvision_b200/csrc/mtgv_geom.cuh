@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define MTGV_HD __host__ __device__ __forceinline__
+#define MTGV_HDN __host__ __device__ __noinline__  /* big, cold routines: keep one copy */
 #else
 #define MTGV_HD inline
+#define MTGV_HDN inline
 #endif
 
 #if defined(__CUDA_ARCH__)

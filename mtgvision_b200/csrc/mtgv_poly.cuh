@@ -30,7 +30,7 @@ MTGV_HD double poly_signed2(const double* p, int n) {
 
 // Sutherland-Hodgman: subject (any simple polygon) clipped by a CONVEX polygon.
 // out must hold 2*kPolyMax doubles; returns the vertex count (<= kPolyMax).
-MTGV_HD int clip_convex(const double* subj, int ns, const double* clip, int nc, double* out) {
+MTGV_HDN int clip_convex(const double* subj, int ns, const double* clip, int nc, double* out) {
   double a[2 * kPolyMax], b[2 * kPolyMax];
   int na = ns;
   for (int k = 0; k < 2 * ns; k++) a[k] = subj[k];

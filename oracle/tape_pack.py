@@ -132,3 +132,81 @@ def pack_tapes(tapes: list[dict], fields: FieldBuffer | None = None, host_transc
         for k, rec in enumerate(ops):
             _pack_op(rec, e["ops"][k], fields, host_transcendentals)
     return arr, fields
+
+
+# --------------------------------------------------------------------------- #
+# detection tapes (oracle/det_oracle.py records -> mtgv_det_tape)              #
+# --------------------------------------------------------------------------- #
+
+
+def _pack_photo(rec: dict, op, fields: FieldBuffer):
+    from oracle import det_oracle as DO
+
+    op["field"] = abi.MTGV_FIELD_PHILOX
+    ph = rec["ph"]
+    if ph == DO.PH_RBC:
+        op["code"] = abi.PH_RBC
+        op["d"][0], op["d"][1] = rec["alpha"], rec["beta"]
+    elif ph == DO.PH_HSV:
+        op["code"] = abi.PH_HSV
+        op["d"][0], op["d"][1], op["d"][2] = rec["hue"], rec["sat"], rec["val"]
+    elif ph == DO.PH_GAUSS_NOISE:
+        op["code"] = abi.PH_GAUSS_NOISE
+        op["d"][0] = rec["sigma"]
+        op["field"] = fields.add(rec["field"].astype(np.float32))
+    elif ph == DO.PH_GAUSS_BLUR:
+        op["code"] = abi.PH_GAUSS_BLUR
+        op["d"][0] = rec["sigma"]
+    elif ph == DO.PH_ERASE:
+        op["code"] = abi.PH_ERASE
+        if rec["active"]:
+            op["i"][0], op["i"][1], op["i"][2], op["i"][3] = rec["top"], rec["left"], rec["eh"], rec["ew"]
+        op["i"][4] = rec["fill"]
+        if "color" in rec:
+            op["d"][:3] = rec["color"]
+        if "field" in rec:
+            op["field"] = fields.add(rec["field"].astype(np.float32))
+    else:
+        raise KeyError(ph)
+
+
+def pack_det_tapes(tapes: list[dict], fields: FieldBuffer | None = None, host_transcendentals: bool = True, seed: int = 0):
+    """Scene tapes recorded by oracle.det_oracle.DetOracle -> (ndarray of mtgv_det_tape, FieldBuffer)."""
+    import math
+
+    fields = fields or FieldBuffer()
+    arr = np.zeros(len(tapes), dtype=abi.DET_TAPE_DTYPE)
+    for s, t in enumerate(tapes):
+        e = arr[s]
+        e["bg_only"] = int(t["bg_only"])
+        e["bg"], e["bg_deg"], e["n_cards"] = t["bg"], t["bg_deg"], t["n_cards"]
+        e["seed"] = seed + s
+        if host_transcendentals:
+            # getRotationMatrix2D's alpha/beta as cv2 computes them with the host libm (od_datasets.py:106)
+            h, w = t["bg_hw"]
+            S = t["size_hw"]
+            scale = math.hypot(S[0] / max(S), S[1] / max(S)) * max(S) / min(h, w)
+            a = t["bg_deg"] * (math.pi / 180.0)
+            e["bg_ab_given"] = 1
+            e["bg_ab"][0], e["bg_ab"][1] = math.cos(a) * scale, math.sin(a) * scale
+        for name, cap in (("pre", abi.DET_MAX_PRE), ("post", abi.DET_MAX_POST)):
+            assert len(t[name]) <= cap
+            e["n_" + name] = len(t[name])
+            for k, rec in enumerate(t[name]):
+                _pack_photo(rec, e[name][k], fields)
+        for ci, c in enumerate(t["cards"]):
+            cc = e["cards"][ci]
+            cc["card"] = c["card"]
+            cc["n_attempts"] = len(c["attempts"])
+            for ai, a in enumerate(c["attempts"]):
+                at = cc["att"][ai]
+                at["cx"], at["cy"], at["deg"], at["area"] = a["cx"], a["cy"], a["deg"], a["area"]
+                at["jitter"][:] = a["jitter"]
+                if host_transcendentals:
+                    at["dst_given"] = 1
+                    at["dst"][:] = np.asarray(a["dst"], dtype=np.float32).reshape(-1)
+            ops = c.get("photo", [])
+            cc["n_photo"] = len(ops)
+            for k, rec in enumerate(ops):
+                _pack_photo(rec, cc["photo"][k], fields)
+    return arr, fields

@@ -4,6 +4,7 @@
 #include "../../mtgvision_b200/csrc/mtgv_expand.cuh"
 #include "../../mtgvision_b200/csrc/mtgv_poly.cuh"
 #include "../../mtgvision_b200/csrc/mtgv_mask.h"
+#include "../../mtgvision_b200/csrc/mtgv_det.cuh"
 
 using namespace mtgv;
 
@@ -43,6 +44,35 @@ int hh_expand_encoder(const mtgv_enc_tape* tape, int n, const mtgv_enc_config* c
 }
 
 void hh_round_rect_mask(int h, int w, int radius, float* out) { host_round_rect_mask(h, w, radius, out); }
+
+int hh_det_params_size() { return (int)sizeof(DetParams); }
+
+// runs the placement / label warping of mtgv_det.cuh for n scenes on the host
+int hh_det_place(const mtgv_det_tape* tape, int n, const mtgv_det_config* cfg, int card_h, int card_w, int n_cards, int n_bgs,
+                 const int32_t* bg_hw, void* params, int32_t* accepted, double* keypoints, int32_t* labels, int32_t* counts) {
+  DetKeypoints kp;
+  det_keypoints(card_h, card_w, cfg->kind, &kp);
+  const size_t nk = (size_t)MTGV_DET_MAX_CARDS * MTGV_DET_MAX_KPOLY;
+  int bad = 0;
+  for (int s = 0; s < n; s++)
+    bad += det_place_scene(&tape[s], cfg, &kp, card_h, card_w, n_cards, n_bgs, bg_hw, (DetParams*)params + s,
+                           accepted + (size_t)s * MTGV_DET_MAX_CARDS, keypoints + (size_t)s * nk * MTGV_DET_MAX_KP * 2,
+                           labels + (size_t)s * nk, counts + s) != 0;
+  return bad;
+}
+
+void hh_det_keypoints(int h, int w, int kind, double* pts, double* bbox, int* n_poly, int* n_pts) {
+  DetKeypoints kp;
+  det_keypoints(h, w, kind, &kp);
+  *n_poly = kp.n_poly; *n_pts = kp.n_pts;
+  for (int q = 0; q < MTGV_DET_MAX_KPOLY; q++)
+    for (int k = 0; k < MTGV_DET_MAX_KP; k++) { pts[(q * MTGV_DET_MAX_KP + k) * 2] = kp.pts[q][k][0]; pts[(q * MTGV_DET_MAX_KP + k) * 2 + 1] = kp.pts[q][k][1]; }
+  for (int k = 0; k < 4; k++) { bbox[2 * k] = kp.bbox[k][0]; bbox[2 * k + 1] = kp.bbox[k][1]; }
+}
+
+void hh_det_apply(const double* M, const double* pts, int n, double* out) {
+  for (int k = 0; k < n; k++) det_apply(M, pts[2 * k], pts[2 * k + 1], &out[2 * k], &out[2 * k + 1]);
+}
 
 double hh_poly_area(const double* p, int n) { return poly_area(p, n); }
 int hh_clip_convex(const double* subj, int ns, const double* clip, int nc, double* out) {

@@ -21,7 +21,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_c():
     lib = abi.load_library()
     lib.mtgv_sizeof.restype = C.c_int
-    for which, t in enumerate([abi.TapeOp, abi.EncTape, abi.XOp, abi.EncParams, abi.EncConfig]):
+    for which, t in enumerate([abi.TapeOp, abi.EncTape, abi.XOp, abi.EncParams, abi.EncConfig, abi.PhotoOp,
+                               abi.DetAttempt, abi.DetCard, abi.DetTape, abi.DetConfig]):
         assert lib.mtgv_sizeof(which) == C.sizeof(t), t.__name__
     assert abi.TAPE_DTYPE.itemsize == C.sizeof(abi.EncTape)
     assert abi.PARAMS_DTYPE.itemsize == C.sizeof(abi.EncParams)
