@@ -116,7 +116,7 @@ class Context:
                             out: torch.Tensor | None = None) -> torch.Tensor:
         """Tapes of n_pairs x-samples followed (when paired) by n_pairs x2-samples."""
         n = n_pairs * (2 if self.cfg.paired else 1)
-        tape = out if out is not None else torch.empty((n, abi.TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        tape = out if out is not None else torch.zeros((n, abi.TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
         if cards is not None:
             cards = cards.to(self.device, dtype=torch.int32).contiguous()
             assert cards.numel() == n_pairs
@@ -185,7 +185,7 @@ class Context:
         self.det_cfg = cfg
 
     def sample_det_tape(self, seed: int, first_index: int, n: int) -> torch.Tensor:
-        tape = torch.empty((n, abi.DET_TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        tape = torch.zeros((n, abi.DET_TAPE_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
         rc = self.lib.mtgv_sample_det_tape(self._h, C.c_uint64(seed & (2**64 - 1)), C.c_int64(first_index), n, _ptr(tape),
                                            self._stream())
         self._check(rc, "mtgv_sample_det_tape")

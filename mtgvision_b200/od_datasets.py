@@ -1,0 +1,180 @@
+"""Drop-in for the detection-scene generator of `mtgvision/od_datasets.py` (reference).
+
+`Gen(**kwargs)` keeps the reference constructor arguments (od_datasets.py:620-639),
+`random()` / `random_bg()` and the sample dict keys (`image`, `keypoints`,
+`keypoints_labels`, :607-611); `save_sample` / `create_yolo_obb_dataset` keep the on-disk YOLO
+layout (:732-832).  Scenes are produced by libmtgv.so: a Philox tape sampler, the placement /
+label kernel (rejection sampling, overlap tests and keypoint warping on device) and the pixel
+kernel (background cover-warp, per-card warp of image + mask, alpha composite, photometrics).
+
+`random_batch(n)` is the GPU-native entry: device tensors `image [n,3,S,S]` (uint8 / fp16 /
+fp32 NCHW), padded `keypoints [n,Kmax,P,2] float64` in pixels, `labels [n,Kmax] int32`
+(-1 padding) and `counts [n]`.
+"""
+
+from __future__ import annotations
+
+import os
+import random
+import warnings
+from pathlib import Path
+from typing import Literal, Optional
+
+import numpy as np
+import torch
+
+from . import abi, synth
+from .context import Context
+from .encoder_datasets import CocoValImages, IlsvrcImages, SyntheticBgFgMtgImages
+
+_OUT = {"uint8": abi.OUT_U8, "u8": abi.OUT_U8, "float16": abi.OUT_F16, "fp16": abi.OUT_F16, "float32": abi.OUT_F32,
+        "fp32": abi.OUT_F32}
+
+
+class Gen:
+    def __init__(
+        self,
+        *,
+        bg_size_hw: tuple[int, int] | int = 640,
+        num_cards_min: int = 1,
+        num_cards_max: int = 10,
+        card_min_visible_ratio: float = 0.5,
+        card_min_visible_ratio_edges: Optional[float] = 1.0,
+        card_jitter_ratio: float = 0.3,
+        card_min_area_ratio: float = 0.02,
+        card_max_area_ratio: float = 0.9,
+        card_size_sample_mode: Literal["uniform", "log_uniform"] = "log_uniform",
+        card_no_contains: bool = True,
+        card_max_place_attempts: int = 10,
+        ratio_bg: Optional[float] = None,
+        ilsvrc_vs_coco_sample_weights: tuple[float, float] | None = (1.0, 1.0),
+        kind: Literal["obb", "seg"] = "obb",
+        # ---- B200 path ----
+        mtg_ds: Optional[SyntheticBgFgMtgImages] = None,
+        bg_ds: Optional[IlsvrcImages] = None,
+        bg2_ds: Optional[CocoValImages] = None,
+        device: Optional[int] = None,
+        seed: Optional[int] = None,
+        photometrics: bool = True,
+        rank: int = 0,
+        world_size: int = 1,
+    ):
+        if card_size_sample_mode != "log_uniform":
+            raise KeyError(card_size_sample_mode) if card_size_sample_mode != "uniform" else NotImplementedError(
+                "card_size_sample_mode='uniform' is not implemented on the B200 path")
+        self.mtg_ds = mtg_ds if mtg_ds is not None else SyntheticBgFgMtgImages(img_type="small")
+        self.bg_ds = bg_ds if bg_ds is not None else IlsvrcImages()
+        self.bg2_ds = bg2_ds
+        self.bg_size_hw = bg_size_hw
+        self.num_cards_min, self.num_cards_max = num_cards_min, num_cards_max
+        self.card_min_visible_ratio = card_min_visible_ratio
+        self.card_min_visible_ratio_edges = card_min_visible_ratio_edges
+        self.card_jitter_ratio = card_jitter_ratio
+        self.card_min_area_ratio, self.card_max_area_ratio = card_min_area_ratio, card_max_area_ratio
+        self.card_size_sample_mode = card_size_sample_mode
+        self.card_no_contains = card_no_contains
+        self.card_max_place_attempts = card_max_place_attempts
+        self.ratio_bg = ratio_bg
+        self.kind = kind
+        self.seed = random.getrandbits(63) if seed is None else int(seed)
+        self.rank, self.world_size = int(rank), int(world_size)
+        self._counter = 0
+        # both background datasets share one resident pool (the reference draws the dataset with
+        # ilsvrc_vs_coco_sample_weights and then an image uniformly, od_datasets.py:662-672)
+        bgs = list(self.bg_ds.images_u8) + (list(self.bg2_ds.images_u8) if self.bg2_ds is not None else [])
+        self.ctx = Context(device)
+        pool = self.mtg_ds.pool
+        self.ctx.set_card_pool(pool.images, pool.labels3, pool.grp_off, pool.grp_mem)
+        self.ctx.set_bg_pool(bgs)
+        # raises like the reference's random.randint when the card diagonal does not fit (od_datasets.py:322)
+        try:
+            self.ctx.set_det_config(bg_size_hw=bg_size_hw, num_cards_min=num_cards_min, num_cards_max=num_cards_max,
+                                    card_min_visible_ratio=card_min_visible_ratio,
+                                    card_min_visible_ratio_edges=card_min_visible_ratio_edges,
+                                    card_jitter_ratio=card_jitter_ratio, card_min_area_ratio=card_min_area_ratio,
+                                    card_max_area_ratio=card_max_area_ratio, card_no_contains=card_no_contains,
+                                    card_max_place_attempts=card_max_place_attempts, ratio_bg=ratio_bg, kind=kind,
+                                    photometrics=photometrics)
+        except abi.MtgvError as e:
+            if "empty range" in str(e):
+                raise ValueError(str(e)) from e
+            raise
+
+    # ------------------------------------------------------------------ GPU-native batch
+    def random_batch(self, n: int, out_dtype: str = "uint8") -> dict:
+        ctx = self.ctx
+        with torch.cuda.device(ctx.device):
+            first = (self._counter * self.world_size + self.rank) * n
+            self._counter += 1
+            tape = ctx.sample_det_tape(self.seed, first, n)
+            params, accepted, keypoints, labels, counts = ctx.det_place(tape)
+            image = ctx.det_batch(params, _OUT[out_dtype])
+        return {"image": image, "keypoints": keypoints, "labels": labels, "counts": counts, "accepted": accepted}
+
+    # ------------------------------------------------------------------ reference surface
+    def _one(self, force_bg: Optional[bool] = None) -> dict:
+        b = self.random_batch(1, "float32")
+        k = int(b["counts"][0])
+        P = 4 if self.kind == "obb" else 8
+        return {
+            "image": b["image"][0].permute(1, 2, 0).contiguous().cpu().numpy(),
+            "keypoints": b["keypoints"][0, :k, :P].cpu().numpy() if k else [],
+            "keypoints_labels": b["labels"][0, :k].cpu().numpy().astype(np.int64) if k else [],
+        }
+
+    def random(self) -> dict:
+        return self._one()
+
+    def random_bg(self) -> dict:
+        old = self.ctx.det_cfg.ratio_bg
+        try:
+            self.ctx.det_cfg.ratio_bg = 2.0  # every draw takes the background-only branch
+            self.ctx._check(self.ctx.lib.mtgv_set_det_config(self.ctx._h, abi.C.byref(self.ctx.det_cfg)), "mtgv_set_det_config")
+            return self._one()
+        finally:
+            self.ctx.det_cfg.ratio_bg = old
+            self.ctx._check(self.ctx.lib.mtgv_set_det_config(self.ctx._h, abi.C.byref(self.ctx.det_cfg)), "mtgv_set_det_config")
+
+
+# --------------------------------------------------------------------------------------- #
+# YOLO on-disk dataset (od_datasets.py:732-832): host-side writer, same layout               #
+# --------------------------------------------------------------------------------------- #
+
+
+def save_sample(sample: dict, i: int, label_dir, img_dir, ext: Literal["png", "jpg"] = "jpg"):
+    import cv2
+
+    img, kps, kps_labels = sample["image"], sample["keypoints"], sample["keypoints_labels"]
+    assert len(kps) == len(kps_labels)
+    assert img.ndim == 3
+    annotations = []
+    for pts, label in zip(kps, kps_labels):
+        pts = np.asarray(pts, dtype=np.float64) / img.shape[:2][::-1]  # points are (w, h)
+        if np.any(pts < 0) or np.any(pts > 1):
+            warnings.warn(f"points for image {i} are out of bounds, yolo will consider these invalid")
+        annotations.append(f"{label} {' '.join(map(str, pts.flatten()))}")
+    with open(os.path.join(label_dir, f"image_{i:04d}.txt"), "w") as f:
+        for ann in annotations:
+            f.write(ann + "\n")
+    u8 = (img * 255).astype(np.uint8) if img.dtype != np.uint8 else img  # imwrite semantics (util/image.py:101-104)
+    cv2.imwrite(os.path.join(img_dir, f"image_{i:04d}.{ext}"), cv2.cvtColor(u8, cv2.COLOR_RGB2BGR))
+
+
+def create_yolo_obb_dataset(generator: Gen, *, output_dir: str, num_train: int = 20000, num_val_ratio: float = 0.1,
+                            num_test_ratio: float = 0.1, ext: Literal["png", "jpg"] = "jpg"):
+    import yaml
+
+    output_dir = Path(output_dir)
+    if output_dir.exists() and len(list(output_dir.iterdir())) > 0:
+        raise FileExistsError(f"not clean... {output_dir}")
+    img_dir, label_dir = output_dir / "images", output_dir / "labels"
+    img_dir.mkdir(exist_ok=True, parents=True)
+    label_dir.mkdir(exist_ok=True, parents=True)
+    with open(output_dir / "mtg_obb.yaml", "w") as fp:
+        yaml.safe_dump({"path": ".", "train": str(img_dir / "train"), "val": str(img_dir / "val"),
+                        "test": str(img_dir / "test"), "names": {0: "card", 1: "card_top", 2: "card_bottom"}}, fp)
+    for name, num in [("train", num_train), ("val", int(num_val_ratio * num_train)), ("test", int(num_test_ratio * num_train))]:
+        (img_dir / name).mkdir(exist_ok=True, parents=True)
+        (label_dir / name).mkdir(exist_ok=True, parents=True)
+        for i in range(num):
+            save_sample(generator.random(), i=i, label_dir=label_dir / name, img_dir=img_dir / name, ext=ext)
