@@ -643,11 +643,15 @@ __host__ __device__ inline size_t fg_smem_bytes(int pitch) {
 // arithmetic), coordinates are generated once and shared by the three colour channels.
 
 constexpr int kBgThreads = 256;
-constexpr int kBgTR = 8, kBgTC = 32;   // output pixels per tile
-constexpr int kBgWCap = 3200;          // warp_inv pixels staged per tile and channel
-constexpr int kBgRCap = 3328;          // rotate-canvas pixels staged per tile and channel
-constexpr int kBgAxis = 320;           // max bbox extent per axis covered by the fixed-point tables
-constexpr int kBgWRows = 64, kBgWBlk = 4;
+#ifndef MTGV_BG_TC
+#define MTGV_BG_TC 32
+#endif
+constexpr int kBgTR = 8, kBgTC = MTGV_BG_TC;   // output pixels per tile
+constexpr int kBgWCap = MTGV_BG_TC == 16 ? 1792 : 3200;  // warp_inv pixels staged per tile and channel
+constexpr int kBgRCap = MTGV_BG_TC == 16 ? 2048 : 3328;  // rotate-canvas pixels staged per tile and channel
+constexpr int kBgAxis = MTGV_BG_TC == 16 ? 192 : 320;    // max bbox extent per axis covered by the fixed-point tables
+constexpr int kBgWRows = MTGV_BG_TC == 16 ? 32 : 64, kBgWBlk = MTGV_BG_TC == 16 ? 3 : 4;
+constexpr int kBgMinBlocks = MTGV_BG_TC == 16 ? 3 : 2;
 
 struct BgSmem {
   float lut[3][256];
@@ -712,7 +716,7 @@ __device__ __forceinline__ void bg_rot3_at(const BgView& b, const BgSmem& S, int
   bg_rot3(b, S, X, Y, out);
 }
 
-__global__ void __launch_bounds__(kBgThreads) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
+__global__ void __launch_bounds__(kBgThreads, kBgMinBlocks) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
                                                            const uint8_t* __restrict__ bg_planes,
                                                            const int64_t* __restrict__ bg_off, float* __restrict__ bg_out) {
   extern __shared__ __align__(16) unsigned char bg_smem_raw[];
@@ -1475,9 +1479,10 @@ static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, 
   const size_t smem = enc_smem_bytes(OH, OW);
   if ((int)smem > ctx->max_smem_optin)
     return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw too large: two float32 planes must fit in 227 KB of shared memory");
-  // Samples are processed in chunks so that the background planes written by k_background
-  // (3*HW floats per sample) are still in the 126 MB L2 when k_encoder composites them.
-  int chunk = (int)((size_t)112 * 1024 * 1024 / (6 * HW * 4));
+  // Chunk = as many samples as 1.5 GB of float32 scratch (background + foreground planes) holds: the
+  // persistent kernels lose more to per-launch tails than the pipeline gains from L2 residency of the
+  // scratch (measured: 6 chunks of 190 samples 79k x-samples/s, one chunk of 1024 92k).
+  int chunk = (int)((size_t)1536 * 1024 * 1024 / (6 * HW * 4));
   if (const char* e = getenv("MTGV_CHUNK")) chunk = atoi(e);
   chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
   int rc = ensure_scratch(ctx, chunk, HW);
