@@ -355,8 +355,84 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------- #
+# detection workloads (BASELINE configs[2], configs[3]) - own measurements for profiles/      #
+# --------------------------------------------------------------------------------------- #
+
+_DET_STATE = {}
+
+
+def _det_cpu_worker(args):
+    wid, n_scenes, S, max_cards = args
+    import random
+
+    import cv2
+    import numpy as np
+
+    from oracle import det_oracle as DO
+
+    cv2.setNumThreads(1)
+    random.seed(77 + wid)
+    np.random.seed(77 + wid)
+    o = DO.DetOracle(_DET_STATE["cards"], _DET_STATE["bgs"], bg_size_hw=S, num_cards_min=1, num_cards_max=max_cards,
+                     card_min_visible_ratio=0.5, card_min_visible_ratio_edges=0.0, card_jitter_ratio=0.7, ratio_bg=0.1, kind="seg")
+    for _ in range(n_scenes):
+        o.random()
+    return n_scenes
+
+
+def run_det(args):
+    import multiprocessing as mp
+
+    import numpy as np
+    import torch
+
+    from mtgvision_b200 import abi, synth
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from mtgvision_b200.od_datasets import Gen
+
+    S, max_cards, batch = (640, 9, 256) if args.workload == "det640" else (1280, 33, 256)
+    cards = synth.make_card_pool(args.pool_cards, workers=os.cpu_count() or 1)
+    bgs = synth.make_bg_pool(args.pool_bgs, workers=os.cpu_count() or 1)
+    gen = Gen(bg_size_hw=S, num_cards_min=1, num_cards_max=max_cards, card_min_visible_ratio=0.5,
+              card_min_visible_ratio_edges=0.0, card_jitter_ratio=0.7, ratio_bg=0.1, kind="seg",
+              mtg_ds=SyntheticBgFgMtgImages(pool=cards), bg_ds=IlsvrcImages(images=bgs), seed=7)
+    ctx = gen.ctx
+    for _ in range(args.warmup):
+        gen.random_batch(batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    placed = 0
+    l0 = ctx.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        b = gen.random_batch(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    placed = int((b["accepted"] >= 0).sum())
+    cpu = None
+    if not args.no_cpu_baseline:
+        _DET_STATE["cards"] = [cards.images[k] for k in range(32)]
+        _DET_STATE["bgs"] = bgs[:32]
+        w = os.cpu_count() or 1
+        per = 6 if S == 640 else 2
+        with mp.get_context("fork").Pool(w) as pool:
+            pool.map(_det_cpu_worker, [(i, 1, S, max_cards) for i in range(w)])
+            t0 = time.perf_counter()
+            n = sum(pool.map(_det_cpu_worker, [(i, per, S, max_cards) for i in range(w)]))
+            wall = time.perf_counter() - t0
+        cpu = {"value": n / wall, "unit": "scenes/s", "cores": w, "kind": "port", "sample": f"{n} scenes in {wall:.1f} s"}
+    print(json.dumps({"metric": f"detection scenes/sec {S}x{S}", "value": batch * args.steps / (ms * 1e-3), "unit": "scenes/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                      "config": {"workload": args.workload, "batch": batch, "max_cards": max_cards - 1, "kind": "seg",
+                                 "placed_cards_last_batch": placed, "out": "uint8 NCHW"},
+                      "gpu_launches": int(ctx.launch_count() - l0), "cpu_baseline": cpu}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "det640", "det1280"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -368,7 +444,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload != "encoder":
+        run_det(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         if args.warmup < 3:

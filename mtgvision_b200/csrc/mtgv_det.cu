@@ -26,6 +26,8 @@ struct DetState {
   DetKeypoints* kp_dev = nullptr;
   float* scratch[2] = {nullptr, nullptr};
   size_t scratch_cap = 0;  // floats per buffer
+  int32_t* lists = nullptr;  // pass_count[kDetMaxBlur+1] followed by pass_list[kDetMaxBlur+1][chunk]
+  size_t list_cap = 0;
 };
 
 static DetState* det_state(mtgv_ctx* ctx) {
@@ -36,7 +38,7 @@ static DetState* det_state(mtgv_ctx* ctx) {
 int det_destroy(mtgv_ctx* ctx) {
   if (!ctx->det) return MTGV_OK;
   DetState* d = (DetState*)ctx->det;
-  cudaFree(d->cfg_dev); cudaFree(d->kp_dev); cudaFree(d->scratch[0]); cudaFree(d->scratch[1]);
+  cudaFree(d->cfg_dev); cudaFree(d->kp_dev); cudaFree(d->scratch[0]); cudaFree(d->scratch[1]); cudaFree(d->lists);
   delete d;
   ctx->det = nullptr;
   return MTGV_OK;
@@ -46,15 +48,72 @@ int det_destroy(mtgv_ctx* ctx) {
 // placement kernel                                                                      //
 // ------------------------------------------------------------------------------------ //
 
-__global__ void k_det_place(const mtgv_det_tape* __restrict__ tape, int n, const mtgv_det_config* __restrict__ cfg,
-                            const DetKeypoints* __restrict__ kp, int card_h, int card_w, int n_cards, int n_bgs,
-                            const int32_t* __restrict__ bg_hw, DetParams* params, int32_t* accepted, double* keypoints,
-                            int32_t* labels, int32_t* counts) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per scene.  Cards are placed sequentially (card k is tested against cards 0..k-1,
+// od_datasets.py:558-587) but the <= 10 attempts of a card are independent given the accepted
+// set: lanes evaluate them in parallel and the lowest accepted attempt wins, which is exactly the
+// reference's "first attempt that passes".  Labels / composite records are emitted one card per lane.
+constexpr int kPlaceWarps = 4;
+
+__global__ void __launch_bounds__(kPlaceWarps * 32) k_det_place(const mtgv_det_tape* __restrict__ tape, int n,
+                                                                const mtgv_det_config* __restrict__ cfg,
+                                                                const DetKeypoints* __restrict__ kp, int card_h, int card_w,
+                                                                int n_cards, int n_bgs, const int32_t* __restrict__ bg_hw,
+                                                                DetParams* params, int32_t* accepted, double* keypoints,
+                                                                int32_t* labels, int32_t* counts) {
+  __shared__ DetPlaceState s_state[kPlaceWarps];
+  __shared__ double s_M[kPlaceWarps][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * kPlaceWarps + warp;
   if (s >= n) return;
+  const mtgv_det_tape* t = &tape[s];
+  DetParams* P = &params[s];
+  DetPlaceState* st = &s_state[warp];
   const size_t nk = (size_t)MTGV_DET_MAX_CARDS * MTGV_DET_MAX_KPOLY;
-  det_place_scene(&tape[s], cfg, kp, card_h, card_w, n_cards, n_bgs, bg_hw, &params[s], accepted + (size_t)s * MTGV_DET_MAX_CARDS,
-                  keypoints + (size_t)s * nk * MTGV_DET_MAX_KP * 2, labels + (size_t)s * nk, counts + s);
+  int32_t* acc = accepted + (size_t)s * MTGV_DET_MAX_CARDS;
+  int32_t* lab = labels + (size_t)s * nk;
+  double* kps = keypoints + (size_t)s * nk * MTGV_DET_MAX_KP * 2;
+  acc[lane] = -1;
+  for (int k = lane; k < (int)nk; k += 32) lab[k] = -1;
+  bool ok = true;
+  if (lane == 0) {
+    counts[s] = 0;
+    st->n_placed = 0;
+    ok = det_scene_header(t, cfg, n_bgs, P);
+    if (ok) det_bg_transform(t, cfg, bg_hw, P->bg_Minv);
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok) return;
+  __syncwarp();
+  const double min_edge = det_min_edge(cfg);
+  const int n_scene_cards = t->bg_only ? 0 : t->n_cards;
+  for (int ci = 0; ci < n_scene_cards; ci++) {
+    const mtgv_det_card* c = &t->cards[ci];
+    if (c->card < 0 || c->card >= n_cards) {
+      if (lane == 0) P->status = MTGV_ERR_INVALID;
+      return;
+    }
+    int na = c->n_attempts < cfg->max_attempts ? c->n_attempts : cfg->max_attempts;
+    na = na < MTGV_DET_MAX_ATTEMPTS ? na : MTGV_DET_MAX_ATTEMPTS;
+    double M[9];
+    const bool pass = lane < na && det_try_attempt(&c->att[lane], cfg, kp, card_h, card_w, st, min_edge, M);
+    const unsigned votes = __ballot_sync(0xffffffffu, pass);
+    if (votes) {
+      const int first = __ffs(votes) - 1;
+      if (lane == first) {
+        acc[ci] = first;
+        det_commit(st, kp, M, c->card, ci);
+      }
+    }
+    __syncwarp();
+  }
+  const int n_placed = st->n_placed;
+  if (lane < n_placed) det_emit_card(t, cfg, kp, st, lane, P, kps, lab);
+  if (lane == 0) {
+    P->n_placed = n_placed;
+    counts[s] = n_placed * kp->n_poly;
+    det_emit_program(t, cfg, P);
+  }
+  (void)s_M;
 }
 
 // ------------------------------------------------------------------------------------ //
@@ -186,11 +245,16 @@ __device__ __forceinline__ void d_photo_point(const DetPhotoX& op, float* rgb, i
 // pixel kernel                                                                          //
 // ------------------------------------------------------------------------------------ //
 
-constexpr int kDetTW = 32, kDetTH = 8;  // pixels per CTA tile (one thread per pixel)
+constexpr int kDetTW = 32, kDetTH = 32;   // pixels per tile
+constexpr int kDetBW = 32, kDetBH = 8;    // threads per CTA; each thread owns kDetTH / kDetBH rows of the tile
+constexpr int kDetRows = kDetTH / kDetBH;
+constexpr int kDetHalo = kBlurHalfMax - 1;
 
 struct DetLaunch {
   const DetParams* params;
   int n, pass;
+  const int32_t* pass_count;  // [kDetMaxBlur + 1] scenes that have a pass p (pass 0: all scenes, no list)
+  const int32_t* pass_list;   // [kDetMaxBlur + 1][n]
   const uint8_t* card_planes;
   int card_h, card_w, card_pitch;
   const float* mask;  // round_rect_mask(card_hw, 0.046)
@@ -205,198 +269,205 @@ struct DetLaunch {
 };
 
 struct DetTileSmem {
-  int32_t status, bg, n_prog, n_blur, size_h, size_w, n_cull, first, last, blur_idx, is_final, _pad;
+  int32_t status, bg, n_prog, n_blur, n_cull, first, last, blur_idx, is_final, has_cards, _p0, _p1;
   double bg_Minv[9];
   uint64_t seed;
+  int32_t cull[MTGV_DET_MAX_CARDS];
   DetPhotoX prog[kDetProgMax];
-  DetCardX cards[MTGV_DET_MAX_CARDS];
-  float halo[(kDetTH + 2 * (kBlurHalfMax - 1)) * (kDetTW + 2 * (kBlurHalfMax - 1)) * 3];
-  float hrow[(kDetTH + 2 * (kBlurHalfMax - 1)) * kDetTW * 3];
+  float halo[(kDetTH + 2 * kDetHalo) * (kDetTW + 2 * kDetHalo) * 3];
+  float hrow[(kDetTH + 2 * kDetHalo) * kDetTW * 3];
 };
 
-__global__ void __launch_bounds__(kDetTW * kDetTH) k_det_pixels(DetLaunch L) {
-  extern __shared__ __align__(16) unsigned char det_smem_raw[];
-  DetTileSmem& T = *reinterpret_cast<DetTileSmem*>(det_smem_raw);
-  const int s = blockIdx.z, tid = threadIdx.y * kDetTW + threadIdx.x, nt = kDetTW * kDetTH;
-  const DetParams& P = L.params[s];
-  const int tx0 = blockIdx.x * kDetTW, ty0 = blockIdx.y * kDetTH;
-  if (tid == 0) {
-    T.status = P.status; T.bg = P.bg; T.n_prog = P.n_prog; T.n_blur = P.n_blur; T.size_h = P.size_h; T.size_w = P.size_w;
-    T.seed = P.seed;
-    // program segment of this pass: after the pass-th blur (or from the start) up to the next blur
-    int first = 0, seen = 0, blur_idx = -1;
-    if (L.pass > 0) {
-      first = P.n_prog;
-      for (int k = 0; k < P.n_prog; k++)
-        if (P.prog[k].code == MTGV_PH_GAUSS_BLUR && ++seen == L.pass) { first = k + 1; blur_idx = k; break; }
-    }
-    int last = P.n_prog;
-    for (int k = first; k < P.n_prog; k++)
-      if (P.prog[k].code == MTGV_PH_GAUSS_BLUR) { last = k; break; }
-    T.first = first; T.last = last; T.blur_idx = blur_idx; T.is_final = last == P.n_prog;
-  }
-  __syncthreads();
-  if (T.status != 0) {  // failed scenes produce zeros (the host raises from the status word)
-    if (L.pass == 0) {
-      const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
-      if (x < T.size_w && y < T.size_h) {
-        const size_t plane = (size_t)T.size_h * T.size_w, o = (size_t)y * T.size_w + x;
-        for (int c = 0; c < 3; c++) {
-          const size_t idx = ((size_t)s * 3 + c) * plane + o;
-          if (L.out_dtype == MTGV_OUT_F16) ((__half*)L.out)[idx] = __float2half_rn(0.f);
-          else if (L.out_dtype == MTGV_OUT_U8) ((uint8_t*)L.out)[idx] = 0;
-          else ((float*)L.out)[idx] = 0.f;
-        }
-      }
-    }
+// scenes that still have work in pass p (one Gaussian blur per pass boundary)
+__global__ void k_det_lists(const DetParams* __restrict__ params, int n, int32_t* pass_count, int32_t* pass_list) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int nb = params[s].status == 0 ? params[s].n_blur : 0;
+  for (int p = 1; p <= nb && p <= kDetMaxBlur; p++) pass_list[(size_t)p * n + atomicAdd(&pass_count[p], 1)] = s;
+}
+
+__device__ __forceinline__ void det_store(const DetLaunch& L, int s, int S_h, int S_w, int y, int x, const float* rgb, bool final_) {
+  const size_t o = (size_t)y * S_w + x;
+  if (!final_) {
+    float* d = L.dst + ((size_t)s * S_h * S_w + o) * 3;
+    d[0] = rgb[0]; d[1] = rgb[1]; d[2] = rgb[2];
     return;
   }
-  if (L.pass > T.n_blur) return;  // this scene finished in an earlier pass
-  const int S_h = T.size_h, S_w = T.size_w;
-  for (int k = tid; k < (int)(sizeof(DetPhotoX) / 4) * T.n_prog; k += nt) ((uint32_t*)T.prog)[k] = ((const uint32_t*)P.prog)[k];
-  if (tid < 9) T.bg_Minv[tid] = P.bg_Minv[tid];
-  // does this segment composite the cards?  cull them against the tile
-  bool has_cards = false;
-  for (int k = T.first; k < T.last; k++) has_cards |= P.prog[k].code == kPhCards;
-  if (tid == 0) {
-    int nc = 0;
-    if (has_cards)
-      for (int k = 0; k < P.n_placed; k++) {
-        const DetCardX& c = P.cards[k];
-        if (c.x0 < tx0 + kDetTW && c.x1 > tx0 && c.y0 < ty0 + kDetTH && c.y1 > ty0) T.cards[nc++].card = k;  // index first
-      }
-    T.n_cull = nc;
+  const size_t plane = (size_t)S_h * S_w;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const size_t idx = ((size_t)s * 3 + c) * plane + o;
+    if (L.out_dtype == MTGV_OUT_F16) ((__half*)L.out)[idx] = __float2half_rn(rgb[c]);
+    else if (L.out_dtype == MTGV_OUT_U8) ((uint8_t*)L.out)[idx] = (uint8_t)(dclip01(rgb[c]) * 255.f);  // imwrite: (img*255).astype(uint8)
+    else ((float*)L.out)[idx] = rgb[c];
   }
-  __syncthreads();
-  for (int q = T.n_cull - 1; q >= 0; q--) {  // expand culled indices into full records (back to front: in place)
-    const int src_idx = T.cards[q].card;
+}
+
+__global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int S_h, int S_w) {
+  extern __shared__ __align__(16) unsigned char det_smem_raw[];
+  DetTileSmem& T = *reinterpret_cast<DetTileSmem*>(det_smem_raw);
+  const int tid = threadIdx.y * kDetBW + threadIdx.x, nt = kDetBW * kDetBH;
+  const int tiles_x = (S_w + kDetTW - 1) / kDetTW, tiles_y = (S_h + kDetTH - 1) / kDetTH, tiles = tiles_x * tiles_y;
+  const int n_scenes = L.pass == 0 ? L.n : L.pass_count[L.pass];
+  const int bw0 = persp_block_w(S_h, S_w);
+  for (long long work = blockIdx.x; work < (long long)n_scenes * tiles; work += gridDim.x) {
+    const int li = (int)(work / tiles), tile = (int)(work - (long long)li * tiles);
+    const int s = L.pass == 0 ? li : L.pass_list[(size_t)L.pass * L.n + li];
+    const DetParams& P = L.params[s];
+    const int tx0 = (tile % tiles_x) * kDetTW, ty0 = (tile / tiles_x) * kDetTH;
     __syncthreads();
-    for (int k = tid; k < (int)(sizeof(DetCardX) / 4); k += nt) ((uint32_t*)&T.cards[q])[k] = ((const uint32_t*)&P.cards[src_idx])[k];
-  }
-  __syncthreads();
+    if (tid == 0) {
+      T.status = P.status; T.bg = P.bg; T.n_prog = P.n_prog; T.n_blur = P.n_blur; T.seed = P.seed;
+      // program segment of this pass: after the pass-th blur (or from the start) up to the next blur
+      int first = 0, seen = 0, blur_idx = -1;
+      if (L.pass > 0) {
+        first = P.n_prog;
+        for (int k = 0; k < P.n_prog; k++)
+          if (P.prog[k].code == MTGV_PH_GAUSS_BLUR && ++seen == L.pass) { first = k + 1; blur_idx = k; break; }
+      }
+      int last = P.n_prog, has_cards = 0;
+      for (int k = first; k < P.n_prog; k++) {
+        if (P.prog[k].code == MTGV_PH_GAUSS_BLUR) { last = k; break; }
+        has_cards |= P.prog[k].code == kPhCards;
+      }
+      T.first = first; T.last = last; T.blur_idx = blur_idx; T.is_final = last == P.n_prog; T.has_cards = has_cards;
+    } else if (tid >= 32 && tid < 41) {
+      T.bg_Minv[tid - 32] = P.bg_Minv[tid - 32];
+    }
+    __syncthreads();
+    const bool live_scene = T.status == 0 && L.pass <= T.n_blur;
+    if (T.status != 0 && L.pass == 0) {  // failed scenes produce zeros (the host raises from the status word)
+      const float z[3] = {0.f, 0.f, 0.f};
+      for (int i = 0; i < kDetRows; i++) {
+        const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
+        if (x < S_w && y < S_h) det_store(L, s, S_h, S_w, y, x, z, true);
+      }
+    }
+    if (!live_scene) continue;
+    for (int k = tid; k < (int)(sizeof(DetPhotoX) / 4) * T.n_prog; k += nt) ((uint32_t*)T.prog)[k] = ((const uint32_t*)P.prog)[k];
+    if (tid < 32) {  // cull the placed cards against the tile (ballot compaction keeps composite order)
+      const bool hit = T.has_cards && tid < P.n_placed && P.cards[tid].x0 < tx0 + kDetTW && P.cards[tid].x1 > tx0 &&
+                       P.cards[tid].y0 < ty0 + kDetTH && P.cards[tid].y1 > ty0;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) T.cull[__popc(m & ((1u << tid) - 1))] = tid;
+      if (tid == 0) T.n_cull = __popc(m);
+    }
+    __syncthreads();
 
-  const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
-  const bool live = x < S_w && y < S_h;
-  float rgb[3] = {0.f, 0.f, 0.f};
-
-  if (L.pass == 0) {
-    // make_background: cv2.warpPerspective(bg, M, (S,S)) with the cover transform (od_datasets.py:195-203)
-    if (live) {
+    float rgb[kDetRows][3];
+    if (L.pass == 0) {
+      // make_background: cv2.warpPerspective(bg, M, (S,S)) with the cover transform (od_datasets.py:195-203)
       const int bh = L.bg_hw[2 * T.bg], bw = L.bg_hw[2 * T.bg + 1], pitch = (bw + 15) & ~15;
       const uint8_t* src = L.bg_planes + L.bg_off[T.bg];
       const size_t plane = (size_t)bh * pitch;
-      int X, Y;
-      persp_coord(T.bg_Minv, x, y, persp_block_w(S_h, S_w), &X, &Y);
-      const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-      float v[4][3];
 #pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const int yy = sy + (t >> 1), xx = sx + (t & 1);
-        const bool in = (unsigned)yy < (unsigned)bh && (unsigned)xx < (unsigned)bw;
-        const uint8_t* p = src + (size_t)(in ? yy : 0) * pitch + (in ? xx : 0);
-#pragma unroll
-        for (int c = 0; c < 3; c++) v[t][c] = in ? d_u8_over_255(__ldg(p + c * plane)) : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < 3; c++) rgb[c] = d_bilinear(v[0][c], v[1][c], v[2][c], v[3][c], X & 31, Y & 31);
-    }
-  } else {
-    // GaussianBlur that ended the previous segment: separable, BORDER_REFLECT_101, symmetric pairing
-    const DetPhotoX& bl = T.prog[T.blur_idx];
-    const int r = bl.i[0] / 2;
-    const int hw = kDetTW + 2 * r, hh = kDetTH + 2 * r;
-    const float* img = L.src + (size_t)s * S_h * S_w * 3;
-    for (int k = tid; k < hw * hh; k += nt) {
-      int yy = ty0 - r + k / hw, xx = tx0 - r + k % hw;
-      // reflect101 (possibly repeatedly for tiny images)
-      while (yy < 0 || yy >= S_h) yy = yy < 0 ? -yy : 2 * S_h - 2 - yy;
-      while (xx < 0 || xx >= S_w) xx = xx < 0 ? -xx : 2 * S_w - 2 - xx;
-      const float* p = img + ((size_t)yy * S_w + xx) * 3;
-      T.halo[3 * k] = p[0]; T.halo[3 * k + 1] = p[1]; T.halo[3 * k + 2] = p[2];
-    }
-    __syncthreads();
-    for (int k = tid; k < hh * kDetTW; k += nt) {
-      const int yy = k / kDetTW, xx = k % kDetTW;
-      const float* c0 = T.halo + (yy * hw + xx + r) * 3;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        float acc = c0[c] * bl.k[0];
-        for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j] + c0[c + 3 * j]) * bl.k[j];
-        T.hrow[3 * k + c] = acc;
-      }
-    }
-    __syncthreads();
-    if (live) {
-      const float* c0 = T.hrow + ((threadIdx.y + r) * kDetTW + threadIdx.x) * 3;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        float acc = c0[c] * bl.k[0];
-        for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j * kDetTW] + c0[c + 3 * j * kDetTW]) * bl.k[j];
-        rgb[c] = acc;
-      }
-    }
-  }
-
-  if (live) {
-    for (int k = T.first; k < T.last; k++) {
-      const DetPhotoX& op = T.prog[k];
-      if (op.code != kPhCards) {
-        d_photo_point(op, rgb, y, x, S_w, T.seed, L.fields);
-        continue;
-      }
-      // composite every card covering this pixel, reverse placement order (od_datasets.py:594-599)
-      const int bw0 = persp_block_w(S_h, S_w);
-      const int ch = L.card_h, cw = L.card_w, pitch = L.card_pitch;
-      for (int q = 0; q < T.n_cull; q++) {
-        const DetCardX& c = T.cards[q];
-        if (x < c.x0 || x >= c.x1 || y < c.y0 || y >= c.y1) continue;
+      for (int i = 0; i < kDetRows; i++) {
+        const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
+        rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
+        if (x >= S_w || y >= S_h) continue;
         int X, Y;
-        persp_coord(c.Minv, x, y, bw0, &X, &Y);
-        const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-        if (sx < -1 || sx >= cw || sy < -1 || sy >= ch) continue;  // all four taps outside: mask = 0
-        const bool x0 = sx >= 0, x1 = sx + 1 < cw, y0 = sy >= 0, y1 = sy + 1 < ch;
-        const float* mp = L.mask + (size_t)sy * cw + sx;
-        const float m = d_bilinear((y0 && x0) ? __ldg(mp) : 0.f, (y0 && x1) ? __ldg(mp + 1) : 0.f,
-                                   (y1 && x0) ? __ldg(mp + cw) : 0.f, (y1 && x1) ? __ldg(mp + cw + 1) : 0.f, X & 31, Y & 31);
-        if (m == 0.f) continue;  // mask*img + (1-mask)*bg == bg exactly
-        const uint8_t* base = L.card_planes + (size_t)c.card * 3 * ch * pitch;
+        persp_coord(T.bg_Minv, x, y, bw0, &X, &Y);
+        const int sx = X >> 5, sy = Y >> 5;
         float v[4][3];
 #pragma unroll
         for (int t = 0; t < 4; t++) {
           const int yy = sy + (t >> 1), xx = sx + (t & 1);
-          const bool in = (t >> 1 ? y1 : y0) && (t & 1 ? x1 : x0);
-          if (in) {
-            const uint8_t* p = base + (size_t)yy * pitch + xx;
-            float px[3];
+          const bool in = (unsigned)yy < (unsigned)bh && (unsigned)xx < (unsigned)bw;
+          const uint8_t* p = src + (size_t)(in ? yy : 0) * pitch + (in ? xx : 0);
 #pragma unroll
-            for (int cc = 0; cc < 3; cc++) px[cc] = d_u8_over_255(__ldg(p + (size_t)cc * ch * pitch));
-            for (int o = 0; o < c.n_ops; o++) d_photo_point(c.ops[o], px, yy, xx, cw, T.seed, L.fields);  // pre_transform_card (:581)
-            v[t][0] = px[0]; v[t][1] = px[1]; v[t][2] = px[2];
-          } else {
-            v[t][0] = v[t][1] = v[t][2] = 0.f;
-          }
+          for (int c = 0; c < 3; c++) v[t][c] = in ? d_u8_over_255(__ldg(p + c * plane)) : 0.f;
         }
-        const float im = __fsub_rn(1.f, m);
 #pragma unroll
-        for (int cc = 0; cc < 3; cc++) {
-          const float w = d_bilinear(v[0][cc], v[1][cc], v[2][cc], v[3][cc], X & 31, Y & 31);
-          rgb[cc] = __fadd_rn(__fmul_rn(m, w), __fmul_rn(im, rgb[cc]));
+        for (int c = 0; c < 3; c++) rgb[i][c] = d_bilinear(v[0][c], v[1][c], v[2][c], v[3][c], X & 31, Y & 31);
+      }
+    } else {
+      // GaussianBlur that ended the previous segment: separable, BORDER_REFLECT_101, symmetric pairing
+      const DetPhotoX& bl = T.prog[T.blur_idx];
+      const int r = bl.i[0] / 2;
+      const int hw = kDetTW + 2 * r, hh = kDetTH + 2 * r;
+      const float* img = L.src + (size_t)s * S_h * S_w * 3;
+      for (int k = tid; k < hw * hh; k += nt) {
+        int yy = ty0 - r + k / hw, xx = tx0 - r + k % hw;
+        while (yy < 0 || yy >= S_h) yy = yy < 0 ? -yy : 2 * S_h - 2 - yy;  // reflect101
+        while (xx < 0 || xx >= S_w) xx = xx < 0 ? -xx : 2 * S_w - 2 - xx;
+        const float* p = img + ((size_t)yy * S_w + xx) * 3;
+        T.halo[3 * k] = p[0]; T.halo[3 * k + 1] = p[1]; T.halo[3 * k + 2] = p[2];
+      }
+      __syncthreads();
+      for (int k = tid; k < hh * kDetTW; k += nt) {
+        const int yy = k / kDetTW, xx = k % kDetTW;
+        const float* c0 = T.halo + (yy * hw + xx + r) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float acc = c0[c] * bl.k[0];
+          for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j] + c0[c + 3 * j]) * bl.k[j];
+          T.hrow[3 * k + c] = acc;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kDetRows; i++) {
+        const float* c0 = T.hrow + ((threadIdx.y + i * kDetBH + r) * kDetTW + threadIdx.x) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float acc = c0[c] * bl.k[0];
+          for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j * kDetTW] + c0[c + 3 * j * kDetTW]) * bl.k[j];
+          rgb[i][c] = acc;
         }
       }
     }
-    const size_t o = (size_t)y * S_w + x;
-    if (!T.is_final) {
-      float* d = L.dst + ((size_t)s * S_h * S_w + o) * 3;
-      d[0] = rgb[0]; d[1] = rgb[1]; d[2] = rgb[2];
-    } else {
-      const size_t plane = (size_t)S_h * S_w;
+
+    const int ch = L.card_h, cw = L.card_w, pitch = L.card_pitch;
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const size_t idx = ((size_t)s * 3 + c) * plane + o;
-        if (L.out_dtype == MTGV_OUT_F16) ((__half*)L.out)[idx] = __float2half_rn(rgb[c]);
-        else if (L.out_dtype == MTGV_OUT_U8) ((uint8_t*)L.out)[idx] = (uint8_t)(dclip01(rgb[c]) * 255.f);  // imwrite: (img*255).astype(uint8)
-        else ((float*)L.out)[idx] = rgb[c];
+    for (int i = 0; i < kDetRows; i++) {
+      const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
+      if (x >= S_w || y >= S_h) continue;
+      float* px_rgb = rgb[i];
+      for (int k = T.first; k < T.last; k++) {
+        const DetPhotoX& op = T.prog[k];
+        if (op.code != kPhCards) {
+          d_photo_point(op, px_rgb, y, x, S_w, T.seed, L.fields);
+          continue;
+        }
+        // composite every card covering this pixel, reverse placement order (od_datasets.py:594-599)
+        for (int q = 0; q < T.n_cull; q++) {
+          const DetCardX& c = P.cards[T.cull[q]];
+          if (x < c.x0 || x >= c.x1 || y < c.y0 || y >= c.y1) continue;
+          int X, Y;
+          persp_coord(c.Minv, x, y, bw0, &X, &Y);
+          const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+          if (sx < -1 || sx >= cw || sy < -1 || sy >= ch) continue;  // all four taps outside: mask = 0
+          const bool x0 = sx >= 0, x1 = sx + 1 < cw, y0 = sy >= 0, y1 = sy + 1 < ch;
+          const float* mp = L.mask + (long long)sy * cw + sx;
+          const float m = d_bilinear((y0 && x0) ? __ldg(mp) : 0.f, (y0 && x1) ? __ldg(mp + 1) : 0.f,
+                                     (y1 && x0) ? __ldg(mp + cw) : 0.f, (y1 && x1) ? __ldg(mp + cw + 1) : 0.f, X & 31, Y & 31);
+          if (m == 0.f) continue;  // mask*img + (1-mask)*bg == bg exactly
+          const uint8_t* base = L.card_planes + (size_t)c.card * 3 * ch * pitch;
+          float v[4][3];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int yy = sy + (t >> 1), xx = sx + (t & 1);
+            const bool in = (t >> 1 ? y1 : y0) && (t & 1 ? x1 : x0);
+            if (in) {
+              const uint8_t* p = base + (size_t)yy * pitch + xx;
+              float px[3];
+#pragma unroll
+              for (int cc = 0; cc < 3; cc++) px[cc] = d_u8_over_255(__ldg(p + (size_t)cc * ch * pitch));
+              for (int o = 0; o < c.n_ops; o++) d_photo_point(c.ops[o], px, yy, xx, cw, T.seed, L.fields);  // pre_transform_card (:581)
+              v[t][0] = px[0]; v[t][1] = px[1]; v[t][2] = px[2];
+            } else {
+              v[t][0] = v[t][1] = v[t][2] = 0.f;
+            }
+          }
+          const float im = __fsub_rn(1.f, m);
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            const float w = d_bilinear(v[0][cc], v[1][cc], v[2][cc], v[3][cc], X & 31, Y & 31);
+            px_rgb[cc] = __fadd_rn(__fmul_rn(m, w), __fmul_rn(im, px_rgb[cc]));
+          }
+        }
       }
+      det_store(L, s, S_h, S_w, y, x, px_rgb, T.is_final != 0);
     }
   }
 }
@@ -683,7 +754,7 @@ int mtgv_det_place(mtgv_ctx* ctx, const mtgv_det_tape* tape, int n, void* params
   if (n == 0) return MTGV_OK;
   rc = det_refresh_keypoints(ctx, d);
   if (rc) return rc;
-  k_det_place<<<(n + 31) / 32, 32, 0, (cudaStream_t)stream>>>(tape, n, d->cfg_dev, d->kp_dev, ctx->card_h, ctx->card_w, ctx->n_cards,
+  k_det_place<<<(n + kPlaceWarps - 1) / kPlaceWarps, kPlaceWarps * 32, 0, (cudaStream_t)stream>>>(tape, n, d->cfg_dev, d->kp_dev, ctx->card_h, ctx->card_w, ctx->n_cards,
                                                               ctx->n_bgs, ctx->bg_hw, (DetParams*)params, accepted, keypoints,
                                                               labels, counts);
   ctx->launches++;
@@ -701,13 +772,17 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
   const size_t per = (size_t)S_h * S_w * 3;
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
+  static int blocks_per_sm = 1;
   if (!attr_set) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_det_pixels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetTileSmem)));
+    MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_det_pixels, kDetBW * kDetBH, sizeof(DetTileSmem)));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
     attr_set = true;
   }
   // scenes are processed in chunks so the blur scratch (2 float32 images per scene) stays bounded
   size_t chunk = ((size_t)3 << 30) / (per * 4 * 2);
   chunk = chunk < 1 ? 1 : (chunk > (size_t)n ? (size_t)n : chunk);
+  const int passes = d->cfg.photometrics ? 1 + kDetMaxBlur : 1;
   if (d->cfg.photometrics && chunk * per > d->scratch_cap) {
     cudaFree(d->scratch[0]); cudaFree(d->scratch[1]);
     d->scratch[0] = d->scratch[1] = nullptr; d->scratch_cap = 0;
@@ -715,22 +790,37 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
     MTGV_CUDA_OK(ctx, cudaMalloc(&d->scratch[1], chunk * per * 4));
     d->scratch_cap = chunk * per;
   }
+  if (chunk > d->list_cap) {
+    cudaFree(d->lists);
+    d->lists = nullptr; d->list_cap = 0;
+    MTGV_CUDA_OK(ctx, cudaMalloc(&d->lists, (size_t)(kDetMaxBlur + 1) * (chunk + 1) * 4));
+    d->list_cap = chunk;
+  }
   const size_t elem = out_dtype == MTGV_OUT_F16 ? 2 : (out_dtype == MTGV_OUT_U8 ? 1 : 4);
+  const int tiles = ((S_w + kDetTW - 1) / kDetTW) * ((S_h + kDetTH - 1) / kDetTH);
   for (size_t base = 0; base < (size_t)n; base += chunk) {
     const int m = (int)((size_t)n - base < chunk ? (size_t)n - base : chunk);
-    // one pass per Gaussian blur in the scene program plus one; k_det_place rejects programs with more
-    // than kDetMaxBlur blurs (the reference graphs hold at most 3: one in bg_light, two blur families)
-    const int passes = d->cfg.photometrics ? 1 + kDetMaxBlur : 1;
+    int32_t* pass_count = d->lists;
+    int32_t* pass_list = d->lists + (kDetMaxBlur + 1);
+    if (passes > 1) {
+      // one pass per Gaussian blur in a scene program plus one; k_det_place rejects programs with more
+      // than kDetMaxBlur blurs (the reference graphs hold at most 3: one in bg_light, two blur families)
+      MTGV_CUDA_OK(ctx, cudaMemsetAsync(pass_count, 0, (kDetMaxBlur + 1) * 4, st));
+      k_det_lists<<<(m + 127) / 128, 128, 0, st>>>((const DetParams*)params + base, m, pass_count, pass_list);
+      ctx->launches++;
+    }
     for (int pass = 0; pass < passes; pass++) {
       DetLaunch L;
-      L.params = (const DetParams*)params + base; L.n = m; L.pass = pass;
+      L.params = (const DetParams*)params + base; L.n = m; L.pass = pass; L.pass_count = pass_count; L.pass_list = pass_list;
       L.card_planes = ctx->card_planes; L.card_h = ctx->card_h; L.card_w = ctx->card_w; L.card_pitch = ctx->card_pitch;
       L.mask = ctx->mask_det; L.bg_planes = ctx->bg_planes; L.bg_off = ctx->bg_off; L.bg_hw = ctx->bg_hw;
       L.src = pass > 0 ? d->scratch[(pass - 1) & 1] : nullptr;
       L.dst = d->scratch[pass & 1];
       L.out = (char*)images + base * per * elem; L.out_dtype = out_dtype; L.fields = (const uint32_t*)fields;
-      dim3 grid((S_w + kDetTW - 1) / kDetTW, (S_h + kDetTH - 1) / kDetTH, m), block(kDetTW, kDetTH);
-      k_det_pixels<<<grid, block, sizeof(DetTileSmem), st>>>(L);
+      long long want = (long long)m * tiles;
+      long long cap = (long long)ctx->sm_count * blocks_per_sm * 4;
+      int grid = (int)(want < cap ? want : cap);
+      k_det_pixels<<<grid, dim3(kDetBW, kDetBH), sizeof(DetTileSmem), st>>>(L, S_h, S_w);
       ctx->launches++;
     }
   }

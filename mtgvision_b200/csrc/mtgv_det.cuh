@@ -238,105 +238,98 @@ MTGV_HDN bool det_expand_photo(const mtgv_photo_op* t, int slot, DetPhotoX* o) {
   }
 }
 
-// One scene: background transform, sequential placement, labels, composite list, scene program.
-MTGV_HD int det_place_scene(const mtgv_det_tape* t, const mtgv_det_config* cfg, const DetKeypoints* kp, int card_h, int card_w,
-                            int n_cards_pool, int n_bgs, const int32_t* bg_hw, DetParams* P, int32_t* accepted,
-                            double* keypoints, int32_t* labels, int32_t* count) {
-  const int S_h = cfg->size_h, S_w = cfg->size_w;
-  P->status = 0; P->bg = t->bg; P->n_placed = 0; P->n_prog = 0; P->size_h = S_h; P->size_w = S_w; P->n_blur = 0; P->_pad = 0;
-  P->seed = t->seed;
-  for (int k = 0; k < MTGV_DET_MAX_CARDS; k++) accepted[k] = -1;
-  for (int k = 0; k < MTGV_DET_MAX_CARDS * MTGV_DET_MAX_KPOLY; k++) labels[k] = -1;
-  *count = 0;
-  if (t->bg < 0 || t->bg >= n_bgs || t->n_cards < 0 || t->n_cards > MTGV_DET_MAX_CARDS) return P->status = MTGV_ERR_INVALID;
-  // ---- make_background: get_rotate_over_output_transform(mode="cover") (:85-118)
-  {
-    const int h = bg_hw[2 * t->bg], w = bg_hw[2 * t->bg + 1];
-    const double oh = (double)S_h, ow = (double)S_w, mx = oh > ow ? oh : ow;
-    const double a = MTGV_DDIV(oh, mx), b = MTGV_DDIV(ow, mx);
-    const double hyp = sqrt(MTGV_DADD(MTGV_DMUL(a, a), MTGV_DMUL(b, b)));  // math.hypot
-    const double scale = MTGV_DDIV(MTGV_DMUL(hyp, mx), (double)(h < w ? h : w));
-    double alpha, beta;
-    if (t->bg_ab_given) { alpha = t->bg_ab[0]; beta = t->bg_ab[1]; }
-    else {
-      const double ang = MTGV_DMUL((double)t->bg_deg, 3.141592653589793238462643383279502884 / 180.0);
-      alpha = MTGV_DMUL(cos(ang), scale); beta = MTGV_DMUL(sin(ang), scale);
-    }
-    double R[6], M[9];
-    rotation_from_ab((double)(w / 2), (double)(h / 2), alpha, beta, R);
-    const int tx = (S_w - w) >= 0 ? (S_w - w) / 2 : -((w - S_w + 1) / 2);  // python floor division
-    const int ty = (S_h - h) >= 0 ? (S_h - h) / 2 : -((h - S_h + 1) / 2);
-    M[0] = R[0]; M[1] = R[1]; M[2] = MTGV_DADD(R[2], (double)tx);
-    M[3] = R[3]; M[4] = R[4]; M[5] = MTGV_DADD(R[5], (double)ty);
-    M[6] = 0.0; M[7] = 0.0; M[8] = 1.0;
-    invert3x3(M, P->bg_Minv);
-  }
-  // ---- placement (:555-587)
-  double min_edge = cfg->min_visible_edges < 0.0 ? cfg->min_visible : cfg->min_visible_edges;
-  if (min_edge < cfg->min_visible) min_edge = cfg->min_visible;
-  double collide[MTGV_DET_MAX_CARDS * 8];
+struct DetPlaceState {  // accepted cards so far (shared memory per warp on the device, stack on the host)
+  double collide[MTGV_DET_MAX_CARDS * 8];   // apply_transform_2d(bbox, M) of every accepted card (:585)
   double placedM[MTGV_DET_MAX_CARDS][9];
   int placed_card[MTGV_DET_MAX_CARDS], placed_src[MTGV_DET_MAX_CARDS];
-  int n_placed = 0;
+  int n_placed;
+};
+
+MTGV_HD double det_min_edge(const mtgv_det_config* cfg) {
+  double e = cfg->min_visible_edges < 0.0 ? cfg->min_visible : cfg->min_visible_edges;  // None -> min_visible (:312-314)
+  return e < cfg->min_visible ? cfg->min_visible : e;
+}
+
+// make_background: get_rotate_over_output_transform(mode="cover") (:85-118), inverted like cv::warpPerspective does
+MTGV_HDN void det_bg_transform(const mtgv_det_tape* t, const mtgv_det_config* cfg, const int32_t* bg_hw, double* Minv) {
+  const int S_h = cfg->size_h, S_w = cfg->size_w;
+  const int h = bg_hw[2 * t->bg], w = bg_hw[2 * t->bg + 1];
+  const double oh = (double)S_h, ow = (double)S_w, mx = oh > ow ? oh : ow;
+  const double a = MTGV_DDIV(oh, mx), b = MTGV_DDIV(ow, mx);
+  const double hyp = sqrt(MTGV_DADD(MTGV_DMUL(a, a), MTGV_DMUL(b, b)));  // math.hypot
+  const double scale = MTGV_DDIV(MTGV_DMUL(hyp, mx), (double)(h < w ? h : w));
+  double alpha, beta;
+  if (t->bg_ab_given) { alpha = t->bg_ab[0]; beta = t->bg_ab[1]; }
+  else {
+    const double ang = MTGV_DMUL((double)t->bg_deg, 3.141592653589793238462643383279502884 / 180.0);
+    alpha = MTGV_DMUL(cos(ang), scale); beta = MTGV_DMUL(sin(ang), scale);
+  }
+  double R[6], M[9];
+  rotation_from_ab((double)(w / 2), (double)(h / 2), alpha, beta, R);
+  const int tx = (S_w - w) >= 0 ? (S_w - w) / 2 : -((w - S_w + 1) / 2);  // python floor division
+  const int ty = (S_h - h) >= 0 ? (S_h - h) / 2 : -((h - S_h + 1) / 2);
+  M[0] = R[0]; M[1] = R[1]; M[2] = MTGV_DADD(R[2], (double)tx);
+  M[3] = R[3]; M[4] = R[4]; M[5] = MTGV_DADD(R[5], (double)ty);
+  M[6] = 0.0; M[7] = 0.0; M[8] = 1.0;
+  invert3x3(M, Minv);
+}
+
+// one placement attempt (:317-372): homography from the corner targets, warped test polygon, visibility tests
+MTGV_HDN bool det_try_attempt(const mtgv_det_attempt* a, const mtgv_det_config* cfg, const DetKeypoints* kp, int card_h, int card_w,
+                              const DetPlaceState* st, double min_edge, double* M) {
   const float src[8] = {0.f, 0.f, (float)card_w, 0.f, (float)card_w, (float)card_h, 0.f, (float)card_h};
-  if (!t->bg_only) {
-    for (int ci = 0; ci < t->n_cards; ci++) {
-      const mtgv_det_card* c = &t->cards[ci];
-      if (c->card < 0 || c->card >= n_cards_pool) return P->status = MTGV_ERR_INVALID;
-      const int na = c->n_attempts < cfg->max_attempts ? c->n_attempts : cfg->max_attempts;
-      for (int ai = 0; ai < na && ai < MTGV_DET_MAX_ATTEMPTS; ai++) {
-        const mtgv_det_attempt* a = &c->att[ai];
-        float dst[8];
-        if (a->dst_given) for (int k = 0; k < 8; k++) dst[k] = a->dst[k];
-        else det_attempt_dst(a, card_h, card_w, dst);
-        double M[9];
-        if (!get_perspective_transform(src, dst, M)) continue;
-        double kp0[2 * MTGV_DET_MAX_KP];
-        for (int k = 0; k < kp->n_pts; k++) det_apply(M, kp->pts[0][k][0], kp->pts[0][k][1], &kp0[2 * k], &kp0[2 * k + 1]);
-        if (!det_visible(kp0, cfg->kind, S_h, S_w, collide, n_placed, cfg->min_visible, min_edge, cfg->no_contains != 0)) continue;
-        accepted[ci] = ai;
-        for (int k = 0; k < 9; k++) placedM[n_placed][k] = M[k];
-        for (int k = 0; k < 4; k++) det_apply(M, kp->bbox[k][0], kp->bbox[k][1], &collide[8 * n_placed + 2 * k], &collide[8 * n_placed + 2 * k + 1]);
-        placed_card[n_placed] = c->card;
-        placed_src[n_placed] = ci;
-        n_placed++;
-        break;
-      }
-    }
+  float dst[8];
+  if (a->dst_given) for (int k = 0; k < 8; k++) dst[k] = a->dst[k];
+  else det_attempt_dst(a, card_h, card_w, dst);
+  if (!get_perspective_transform(src, dst, M)) return false;
+  double kp0[2 * MTGV_DET_MAX_KP];
+  for (int k = 0; k < kp->n_pts; k++) det_apply(M, kp->pts[0][k][0], kp->pts[0][k][1], &kp0[2 * k], &kp0[2 * k + 1]);
+  return det_visible(kp0, cfg->kind, cfg->size_h, cfg->size_w, st->collide, st->n_placed, cfg->min_visible, min_edge,
+                     cfg->no_contains != 0);
+}
+
+MTGV_HD void det_commit(DetPlaceState* st, const DetKeypoints* kp, const double* M, int card, int ci) {
+  const int n = st->n_placed;
+  for (int k = 0; k < 9; k++) st->placedM[n][k] = M[k];
+  for (int k = 0; k < 4; k++) det_apply(M, kp->bbox[k][0], kp->bbox[k][1], &st->collide[8 * n + 2 * k], &st->collide[8 * n + 2 * k + 1]);
+  st->placed_card[n] = card;
+  st->placed_src[n] = ci;
+  st->n_placed = n + 1;
+}
+
+// r-th card of the output / composite order = placement order reversed (:594-601): labels + composite record
+MTGV_HDN void det_emit_card(const mtgv_det_tape* t, const mtgv_det_config* cfg, const DetKeypoints* kp, const DetPlaceState* st, int r,
+                            DetParams* P, double* keypoints, int32_t* labels) {
+  const int pi = st->n_placed - 1 - r;
+  const double* M = st->placedM[pi];
+  for (int q = 0; q < kp->n_poly; q++) {
+    const int out = r * kp->n_poly + q;
+    double* dstp = keypoints + ((size_t)out * MTGV_DET_MAX_KP) * 2;
+    for (int k = 0; k < kp->n_pts; k++) det_apply(M, kp->pts[q][k][0], kp->pts[q][k][1], &dstp[2 * k], &dstp[2 * k + 1]);
+    for (int k = kp->n_pts; k < MTGV_DET_MAX_KP; k++) { dstp[2 * k] = 0.0; dstp[2 * k + 1] = 0.0; }
+    labels[out] = q;
   }
-  // ---- labels and composite list in reverse placement order (:594-601)
-  P->n_placed = n_placed;
-  int out = 0;
-  for (int r = 0; r < n_placed; r++) {
-    const int pi = n_placed - 1 - r;
-    const double* M = placedM[pi];
-    for (int q = 0; q < kp->n_poly; q++) {
-      double* dstp = keypoints + ((size_t)out * MTGV_DET_MAX_KP) * 2;
-      for (int k = 0; k < kp->n_pts; k++) det_apply(M, kp->pts[q][k][0], kp->pts[q][k][1], &dstp[2 * k], &dstp[2 * k + 1]);
-      for (int k = kp->n_pts; k < MTGV_DET_MAX_KP; k++) { dstp[2 * k] = 0.0; dstp[2 * k + 1] = 0.0; }
-      labels[out] = q;
-      out++;
-    }
-    DetCardX* cx = &P->cards[r];
-    invert3x3(M, cx->Minv);
-    double minx = 1e300, maxx = -1e300, miny = 1e300, maxy = -1e300;
-    for (int k = 0; k < 4; k++) {
-      const double x = collide[8 * pi + 2 * k], y = collide[8 * pi + 2 * k + 1];
-      minx = fmin(minx, x); maxx = fmax(maxx, x); miny = fmin(miny, y); maxy = fmax(maxy, y);
-    }
-    // bilinear taps reach one source pixel beyond the card edge: 2 px of slack in destination space
-    minx = fmax(minx - 2.0, 0.0); miny = fmax(miny - 2.0, 0.0);
-    maxx = fmin(maxx + 3.0, (double)S_w); maxy = fmin(maxy + 3.0, (double)S_h);
-    cx->x0 = (int)floor(minx); cx->y0 = (int)floor(miny);
-    cx->x1 = maxx > minx ? (int)ceil(maxx) : cx->x0; cx->y1 = maxy > miny ? (int)ceil(maxy) : cx->y0;
-    cx->card = placed_card[pi];
-    cx->n_ops = 0;
-    const mtgv_det_card* c = &t->cards[placed_src[pi]];
-    for (int k = 0; k < c->n_photo && k < MTGV_DET_MAX_CARD_OPS; k++)
-      if (cfg->photometrics && det_expand_photo(&c->photo[k], 32 + 4 * placed_src[pi] + k, &cx->ops[cx->n_ops])) cx->n_ops++;
+  DetCardX* cx = &P->cards[r];
+  invert3x3(M, cx->Minv);
+  double minx = 1e300, maxx = -1e300, miny = 1e300, maxy = -1e300;
+  for (int k = 0; k < 4; k++) {
+    const double x = st->collide[8 * pi + 2 * k], y = st->collide[8 * pi + 2 * k + 1];
+    minx = fmin(minx, x); maxx = fmax(maxx, x); miny = fmin(miny, y); maxy = fmax(maxy, y);
   }
-  *count = out;
-  // ---- scene program: pre ops, cards, post ops
+  // bilinear taps reach one source pixel beyond the card edge: 2 px of slack in destination space
+  minx = fmax(minx - 2.0, 0.0); miny = fmax(miny - 2.0, 0.0);
+  maxx = fmin(maxx + 3.0, (double)cfg->size_w); maxy = fmin(maxy + 3.0, (double)cfg->size_h);
+  cx->x0 = (int)floor(minx); cx->y0 = (int)floor(miny);
+  cx->x1 = maxx > minx ? (int)ceil(maxx) : cx->x0; cx->y1 = maxy > miny ? (int)ceil(maxy) : cx->y0;
+  cx->card = st->placed_card[pi];
+  cx->n_ops = 0;
+  const mtgv_det_card* c = &t->cards[st->placed_src[pi]];
+  for (int k = 0; k < c->n_photo && k < MTGV_DET_MAX_CARD_OPS; k++)
+    if (cfg->photometrics && det_expand_photo(&c->photo[k], 32 + 4 * st->placed_src[pi] + k, &cx->ops[cx->n_ops])) cx->n_ops++;
+}
+
+// scene program: pre ops, cards, post ops
+MTGV_HDN int det_emit_program(const mtgv_det_tape* t, const mtgv_det_config* cfg, DetParams* P) {
   int n = 0;
   if (cfg->photometrics)
     for (int k = 0; k < t->n_pre && k < MTGV_DET_MAX_PRE; k++)
@@ -353,6 +346,46 @@ MTGV_HD int det_place_scene(const mtgv_det_tape* t, const mtgv_det_config* cfg, 
   P->n_blur = nb;
   if (nb > kDetMaxBlur) return P->status = MTGV_ERR_LIMIT;
   return 0;
+}
+
+MTGV_HD bool det_scene_header(const mtgv_det_tape* t, const mtgv_det_config* cfg, int n_bgs, DetParams* P) {
+  P->status = 0; P->bg = t->bg; P->n_placed = 0; P->n_prog = 0; P->size_h = cfg->size_h; P->size_w = cfg->size_w; P->n_blur = 0;
+  P->_pad = 0; P->seed = t->seed;
+  if (t->bg < 0 || t->bg >= n_bgs || t->n_cards < 0 || t->n_cards > MTGV_DET_MAX_CARDS) { P->status = MTGV_ERR_INVALID; return false; }
+  return true;
+}
+
+// One scene, sequentially (the specification; the device kernel k_det_place evaluates the attempts of a
+// card in parallel with the same routines and picks the first accepted one).
+MTGV_HD int det_place_scene(const mtgv_det_tape* t, const mtgv_det_config* cfg, const DetKeypoints* kp, int card_h, int card_w,
+                            int n_cards_pool, int n_bgs, const int32_t* bg_hw, DetParams* P, int32_t* accepted,
+                            double* keypoints, int32_t* labels, int32_t* count) {
+  for (int k = 0; k < MTGV_DET_MAX_CARDS; k++) accepted[k] = -1;
+  for (int k = 0; k < MTGV_DET_MAX_CARDS * MTGV_DET_MAX_KPOLY; k++) labels[k] = -1;
+  *count = 0;
+  if (!det_scene_header(t, cfg, n_bgs, P)) return P->status;
+  det_bg_transform(t, cfg, bg_hw, P->bg_Minv);
+  const double min_edge = det_min_edge(cfg);
+  DetPlaceState st;
+  st.n_placed = 0;
+  if (!t->bg_only) {
+    for (int ci = 0; ci < t->n_cards; ci++) {
+      const mtgv_det_card* c = &t->cards[ci];
+      if (c->card < 0 || c->card >= n_cards_pool) return P->status = MTGV_ERR_INVALID;
+      const int na = c->n_attempts < cfg->max_attempts ? c->n_attempts : cfg->max_attempts;
+      for (int ai = 0; ai < na && ai < MTGV_DET_MAX_ATTEMPTS; ai++) {
+        double M[9];
+        if (!det_try_attempt(&c->att[ai], cfg, kp, card_h, card_w, &st, min_edge, M)) continue;
+        accepted[ci] = ai;
+        det_commit(&st, kp, M, c->card, ci);
+        break;
+      }
+    }
+  }
+  P->n_placed = st.n_placed;
+  for (int r = 0; r < st.n_placed; r++) det_emit_card(t, cfg, kp, &st, r, P, keypoints, labels);
+  *count = st.n_placed * kp->n_poly;
+  return det_emit_program(t, cfg, P);
 }
 
 }  // namespace mtgv
