@@ -66,7 +66,7 @@ void mtgv_destroy(mtgv_ctx* ctx) {
   free_cards(ctx);
   free_bgs(ctx);
   cudaFree(ctx->cfg_dev); cudaFree(ctx->alpha0); cudaFree(ctx->alpha_scratch); cudaFree(ctx->sync_words);
-  cudaFree(ctx->tmp_params); cudaFree(ctx->bg_scratch);
+  cudaFree(ctx->tmp_params); cudaFree(ctx->bg_scratch); cudaFree(ctx->bg_counter);
   delete ctx;
 }
 
@@ -122,7 +122,7 @@ int mtgv_set_bg_pool(mtgv_ctx* ctx, const uint8_t* bgs, const int64_t* offsets_h
     int h = hw_host[2 * j], w = hw_host[2 * j + 1];
     if (h < 2 || w < 2) return fail(ctx, MTGV_ERR_INVALID, "mtgv_set_bg_pool: image smaller than 2x2");
     off[j] = (int64_t)total;
-    total += (size_t)3 * h * round_up(w, 16);
+    total += bg_image_bytes(h, w);
   }
   MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_planes, total));
   MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_off, (size_t)n * 8));
@@ -138,7 +138,7 @@ int mtgv_set_bg_pool(mtgv_ctx* ctx, const uint8_t* bgs, const int64_t* offsets_h
     while (k < n && hw_host[2 * k] == h && hw_host[2 * k + 1] == w &&
            offsets_host[k] == offsets_host[k - 1] + (int64_t)h * w * 3)
       k++;
-    int rc = pool_planarize(ctx, bgs + offsets_host[j], ctx->bg_planes + off[j], k - j, h, w, round_up(w, 16), 0);
+    int rc = pool_interleave(ctx, bgs + offsets_host[j], ctx->bg_planes + off[j], k - j, h, w, 0);
     if (rc) return rc;
     j = k;
   }
@@ -199,7 +199,7 @@ int mtgv_update_bg_images(mtgv_ctx* ctx, const uint8_t* bgs, int first, int n, v
     if (ctx->bg_hw_host[2 * j] != h || ctx->bg_hw_host[2 * j + 1] != w)
       return fail(ctx, MTGV_ERR_INVALID, "mtgv_update_bg_images: entries in the range differ in size");
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  return pool_planarize(ctx, bgs, ctx->bg_planes + ctx->bg_off_host[first], n, h, w, round_up(w, 16), (cudaStream_t)stream);
+  return pool_interleave(ctx, bgs, ctx->bg_planes + ctx->bg_off_host[first], n, h, w, (cudaStream_t)stream);
 }
 
 int mtgv_sample_encoder_tape_ex(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n_pairs, const int32_t* cards,

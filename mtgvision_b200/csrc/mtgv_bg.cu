@@ -1,0 +1,505 @@
+// mtgv_bg.cu - k_background: the background chain of make_virtual for sm_100a.
+//
+// make_bg (mtgvision/encoder_datasets.py:774-784) = flip -> rotate_bounded (warpAffine onto
+// an (nh,nw) canvas, util/image.py:380-398) -> warp_inv (warpPerspective, same canvas,
+// encoder_datasets.py:113-116) -> crop_to_size (INTER_AREA to (rh,rw), centre crop,
+// util/image.py:349-377), with tint / fade / brightness_contrast (:165-193) scheduled before
+// or after the geometric group.  Only the out_h x out_w crop survives, so the chain is
+// evaluated backwards per output tile: the tile's INTER_AREA window of the warp_inv image and,
+// under the inverse homography, the bounding box of that window in the rotate canvas.  Both
+// are staged in shared memory as float32; every pixel of either stage is computed once per
+// tile.
+//
+// What is exact and what is toleranced.  Source COORDINATES decide which texels are read and
+// are reproduced bit for bit: warpAffine's 10-bit fixed point and
+// warpPerspective's fp64 X/W on the 1/32 grid (note 1; a guarded fast path below recomputes
+// with cv2's exact operation order whenever its own result is within 2^-14 of a rounding
+// tie).  Pixel VALUES are float32 with fused multiply-adds and the u8 -> [0,1] scaling folded
+// into the interpolation; they differ from cv2's separately rounded sums by ~1e-7, far inside
+// the +-1 uint8 LSB bar of BASELINE.json (tests/test_gpu_encoder.py states the bar).
+//
+// Layouts: background pool = RGBX uint8 words (one 4-byte load per bilinear tap fetches the
+// three channels), rotate-canvas tile = float4 per pixel (one 16-byte shared load per tap),
+// warp_inv tile = three float planes.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "mtgv_internal.cuh"
+
+namespace mtgv {
+
+constexpr int kBgThreads = 256;
+constexpr int kBgTR = 8, kBgTC = 32;   // output pixels per tile
+constexpr int kBgWCap = 3200;          // warp_inv pixels staged per tile
+constexpr int kBgRCap = 3072;          // rotate-canvas pixels staged per tile
+constexpr int kBgWRows = 48, kBgWBlk = 3;
+constexpr int kBgCanvas = 704;         // rotate canvases up to this extent use per-item fixed-point tables
+constexpr int kBgBandRows = 32;        // output rows per work item
+constexpr int kBgMaxOW = 256;
+
+struct AreaEnt {  // one destination index of computeResizeAreaTab, compact: taps = [left?] mid* [right?]
+  int start, n;   // n = taps | left partial << 8 | right partial << 9
+  float wl, wm, wr;
+};
+
+struct BgSmem {
+  float4 rtile[kBgRCap];
+  float wtile[3][kBgWCap];
+  double org[kBgWRows * kBgWBlk * 4];  // X0, Y0, W0 of WarpPerspectiveInvoker per (window row, column block)
+  int colA[kBgCanvas], colB[kBgCanvas], rowX[kBgCanvas], rowY[kBgCanvas];
+  AreaEnt ax[kBgMaxOW], ay[kBgBandRows];
+  // the sample
+  int status, kind, bg, out_h, out_w, bg_h, bg_w, flip_h, flip_v, nh, nw, bg_rh, bg_rw, bg_y0, bg_x0, n_fg, n_pre, n_post;
+  double rot_inv[6], winv[9];
+  // elementwise chains: value = step1(step0(byte)); step = fma(v, a, b) [+ saturate]
+  float pre_a[2][3], pre_b[2][3];
+  int pre_clip[2], pre_steps, pre_linear;
+  float lin_a[3], lin_b[3];
+  float post_a[2][3], post_b[2][3];
+  int post_clip[2], post_steps;
+  int tile[4];  // rx0, ry0, rtw, rth
+  int item;
+};
+
+__device__ __forceinline__ float sat01(float v) { return __saturatef(v); }
+
+// cvRound(fX), cvRound(fY) of WarpPerspectiveInvoker for x1 columns past a block origin (X0,Y0,W0).
+// Exact restatement.
+__device__ __noinline__ void persp_exact(double X0, double Y0, double W0, double m0, double m3, double m6, double x1, int* X, int* Y) {
+  double W = __dadd_rn(W0, __dmul_rn(m6, x1));
+  W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+  *X = __double2int_rn(__dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W));  // saturating, like cv2's clamp
+  *Y = __double2int_rn(__dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W));
+}
+
+// Guarded fast path: reciprocal by rcp.approx + two Newton steps (relative error ~2^-52), results scaled by
+// 2^16 so the distance to the nearest rounding tie is visible in the low bits.  Whenever either coordinate
+// is within 4/65536 of a tie, saturates, or the reciprocal is not finite, the exact routine decides.  The
+// approximate value differs from cv2's by < 1e-6 of those 1/65536 units, so the outputs are identical.
+__device__ __forceinline__ void persp_xy(double X0, double Y0, double W0, double m0, double m3, double m6, double x1, int* X, int* Y) {
+  const double W = __fma_rn(m6, x1, W0);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(W));
+  double e = __fma_rn(-W, r, 1.0);
+  r = __fma_rn(r, e, r);
+  e = __fma_rn(-W, r, 1.0);
+  r = __fma_rn(r, e, r);
+  const double s = __dmul_rn(r, 2097152.0);  // 32 * 2^16
+  const int xq = __double2int_rn(__dmul_rn(__fma_rn(m0, x1, X0), s));
+  const int yq = __double2int_rn(__dmul_rn(__fma_rn(m3, x1, Y0), s));
+  const unsigned tx = ((unsigned)xq + 32772u) & 0xFFFFu, ty = ((unsigned)yq + 32772u) & 0xFFFFu;
+  const bool finite = (__double2hiint(r) & 0x7FF00000) != 0x7FF00000;
+  const bool in_range = (unsigned)xq + 0x7FF00000u < 0xFFE00000u && (unsigned)yq + 0x7FF00000u < 0xFFE00000u;
+  if (finite && in_range && tx > 8u && ty > 8u) {
+    *X = (int)((unsigned)xq + 32768u) >> 16;
+    *Y = (int)((unsigned)yq + 32768u) >> 16;
+  } else {
+    persp_exact(X0, Y0, W0, m0, m3, m6, x1, X, Y);
+  }
+}
+
+__device__ __forceinline__ float byte_f(uint32_t w, int c) {  // exact u8 -> float without I2F
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + c)) - 8388608.f;
+}
+
+__device__ __forceinline__ void bilinear_w(int ax, int ay, float* w) {  // initInterTab2D(INTER_LINEAR) products, exact
+  const float fx = (float)ax * 0.03125f, fy = (float)ay * 0.03125f, gx = 1.f - fx, gy = 1.f - fy;
+  w[0] = gy * gx; w[1] = gy * fx; w[2] = fy * gx; w[3] = fy * fx;
+}
+
+struct BgSrc {
+  const uint32_t* px;  // RGBX words
+  int h, w, pitchw, fh, fv;
+};
+
+// elementwise ops scheduled before the geometric group, applied to one source byte of channel c
+__device__ __forceinline__ float pre_chain(const BgSmem& S, float b, int c) {
+  float v = __fmaf_rn(b, S.pre_a[0][c], S.pre_b[0][c]);
+  if (S.pre_clip[0]) v = sat01(v);
+  if (S.pre_steps > 1) {
+    v = __fmaf_rn(v, S.pre_a[1][c], S.pre_b[1][c]);
+    if (S.pre_clip[1]) v = sat01(v);
+  }
+  return v;
+}
+
+// General rotate_bounded output pixel from its fixed-point source coordinates: any tap may fall
+// outside the source (BORDER_CONSTANT 0), cv2.flip folded into the index.
+__device__ __noinline__ float4 rot_px_general(const BgSmem& S, const BgSrc& b, int X, int Y) {
+  const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+  float w[4];
+  bilinear_w(X & 31, Y & 31, w);
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int y = sy + (t >> 1), x = sx + (t & 1);
+    if ((unsigned)y < (unsigned)b.h && (unsigned)x < (unsigned)b.w) {
+      const int yy = b.fv ? b.h - 1 - y : y, xx = b.fh ? b.w - 1 - x : x;
+      const uint32_t word = __ldg(b.px + (size_t)yy * b.pitchw + xx);
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc[c] = __fmaf_rn(pre_chain(S, byte_f(word, c), c), w[t], acc[c]);
+    }
+  }
+  return make_float4(acc[0], acc[1], acc[2], 0.f);
+}
+
+__device__ __forceinline__ void rot_coords(const BgSmem& S, int ry, int rx, int* X, int* Y) {
+  int cA, cB, oX, oY;
+  if (rx < kBgCanvas) { cA = S.colA[rx]; cB = S.colB[rx]; }
+  else { cA = affine_col_delta(S.rot_inv[0], rx); cB = affine_col_delta(S.rot_inv[3], rx); }
+  if (ry < kBgCanvas) { oX = S.rowX[ry]; oY = S.rowY[ry]; }
+  else { oX = affine_row_origin(S.rot_inv[1], S.rot_inv[2], ry); oY = affine_row_origin(S.rot_inv[4], S.rot_inv[5], ry); }
+  *X = (oX + cA) >> 5;
+  *Y = (oY + cB) >> 5;
+}
+
+// rotate canvas pixel (ry, rx) for the warp_inv stage: zero outside the canvas, the staged tile when inside
+// it, else recomputed (keeps the tiling a pure optimisation)
+__device__ __noinline__ float4 rot_at(const BgSmem& S, const BgSrc& b, int ry, int rx) {
+  if ((unsigned)ry >= (unsigned)S.nh || (unsigned)rx >= (unsigned)S.nw) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ty = ry - S.tile[1], tx = rx - S.tile[0];
+  if ((unsigned)ty < (unsigned)S.tile[3] && (unsigned)tx < (unsigned)S.tile[2]) return S.rtile[ty * S.tile[2] + tx];
+  int X, Y;
+  rot_coords(S, ry, rx, &X, &Y);
+  return rot_px_general(S, b, X, Y);
+}
+
+__device__ __forceinline__ float area_w(const AreaEnt& e, int k) {
+  if (k == 0 && (e.n & 256)) return e.wl;
+  if (k == (e.n & 255) - 1 && (e.n & 512)) return e.wr;
+  return e.wm;
+}
+
+__global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
+                                                              const uint8_t* __restrict__ bg_pool, const int64_t* __restrict__ bg_off,
+                                                              float* __restrict__ bg_out, int* __restrict__ work_counter) {
+  extern __shared__ __align__(16) unsigned char bg_smem_raw[];
+  BgSmem& S = *reinterpret_cast<BgSmem*>(bg_smem_raw);
+  const int tid = threadIdx.x, nt = kBgThreads, lane = tid & 31;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.item = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int item = S.item;
+    if (item >= n * n_bands) break;
+    const int s = item / n_bands, band = item - s * n_bands;
+    const mtgv_enc_params* gp = params + s;
+    if (tid == 0) {
+      S.status = gp->status; S.kind = gp->kind; S.bg = gp->bg; S.out_h = gp->out_h; S.out_w = gp->out_w;
+      S.bg_h = gp->bg_h; S.bg_w = gp->bg_w; S.flip_h = gp->flip_h; S.flip_v = gp->flip_v;
+      S.nh = gp->rot_nh; S.nw = gp->rot_nw; S.bg_rh = gp->bg_rh; S.bg_rw = gp->bg_rw; S.bg_y0 = gp->bg_y0; S.bg_x0 = gp->bg_x0;
+      S.n_fg = gp->n_fg; S.n_pre = gp->n_pre; S.n_post = gp->n_post;
+    } else if (tid >= 32 && tid < 38) {
+      S.rot_inv[tid - 32] = gp->rot_inv[tid - 32];
+    } else if (tid >= 64 && tid < 73) {
+      S.winv[tid - 64] = gp->winv[tid - 64];
+    }
+    __syncthreads();
+    if (S.status != 0 || S.kind == MTGV_KIND_CROPPED) continue;
+    const int OH = S.out_h, OW = S.out_w, nh = S.nh, nw = S.nw;
+    const int by0 = band * kBgBandRows, by1 = min(OH, by0 + kBgBandRows);
+    if (by0 >= by1) continue;
+    // ---- per-item tables ----
+    if (tid < 3) {
+      // elementwise chains (expand_elementwise, mtgv_expand.cuh): pre ops act on source bytes, post ops on warp_inv output
+      const int c = tid;
+      const mtgv_x_op* ops = gp->ops + S.n_fg;
+      const int n_pre = S.n_pre, n_post = S.n_post;
+      float a0 = 1.f / 255.f, b0 = 0.f, a1 = 1.f, b1 = 0.f;
+      int c0 = 0, c1 = 0;
+      if (n_pre >= 1 && ((ops[0].i[0] >> c) & 1)) { a0 = ops[0].f[c] * (1.f / 255.f); b0 = ops[0].f[4 + c]; c0 = ops[0].i[1]; }
+      if (n_pre >= 2 && ((ops[1].i[0] >> c) & 1)) { a1 = ops[1].f[c]; b1 = ops[1].f[4 + c]; c1 = ops[1].i[1]; }
+      S.pre_a[0][c] = a0; S.pre_b[0][c] = b0; S.pre_a[1][c] = a1; S.pre_b[1][c] = b1;
+      // the chain is affine on [0,255] when no step can leave [0,1] at either end of the byte range
+      const float lo0 = b0, hi0 = __fmaf_rn(255.f, a0, b0);
+      bool lin = !c0 || (fminf(lo0, hi0) >= 0.f && fmaxf(lo0, hi0) <= 1.f);
+      const float lo1 = __fmaf_rn(lo0, a1, b1), hi1 = __fmaf_rn(hi0, a1, b1);
+      lin = lin && (!c1 || (fminf(lo1, hi1) >= 0.f && fmaxf(lo1, hi1) <= 1.f));
+      S.lin_a[c] = a0 * a1;
+      S.lin_b[c] = __fmaf_rn(b0, a1, b1);
+      const unsigned all = __ballot_sync(0x7u, lin);
+      if (c == 0) {
+        S.pre_clip[0] = (n_pre >= 1) ? ops[0].i[1] : 0;
+        S.pre_clip[1] = (n_pre >= 2) ? ops[1].i[1] : 0;
+        S.pre_steps = n_pre >= 2 ? 2 : 1;
+        S.pre_linear = all == 0x7u;
+        S.post_steps = n_post;
+        S.post_clip[0] = n_post >= 1 ? ops[n_pre].i[1] : 0;
+        S.post_clip[1] = n_post >= 2 ? ops[n_pre + 1].i[1] : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const bool on = q < n_post && ((ops[n_pre + (q < n_post ? q : 0)].i[0] >> c) & 1);
+        S.post_a[q][c] = on ? ops[n_pre + q].f[c] : 1.f;
+        S.post_b[q][c] = on ? ops[n_pre + q].f[4 + c] : 0.f;
+      }
+    }
+    for (int k = tid; k < kBgCanvas; k += nt) {  // warpAffine fixed-point tables (cv::warpAffine adelta/bdelta, X0/Y0)
+      if (k < nw) { S.colA[k] = affine_col_delta(S.rot_inv[0], k); S.colB[k] = affine_col_delta(S.rot_inv[3], k); }
+      if (k < nh) { S.rowX[k] = affine_row_origin(S.rot_inv[1], S.rot_inv[2], k); S.rowY[k] = affine_row_origin(S.rot_inv[4], S.rot_inv[5], k); }
+    }
+    // crop_to_size: INTER_AREA (nh,nw)->(bg_rh,bg_rw) tables for the band's rows and all columns
+    for (int k = tid; k < OW + (by1 - by0); k += nt) {
+      AreaEnt e;
+      if (k < OW) { area_compact(nw, S.bg_rw, S.bg_x0 + k, &e.start, &e.n, &e.wl, &e.wm, &e.wr); S.ax[k] = e; }
+      else { area_compact(nh, S.bg_rh, S.bg_y0 + by0 + (k - OW), &e.start, &e.n, &e.wl, &e.wm, &e.wr); S.ay[k - OW] = e; }
+    }
+    BgSrc b;
+    b.h = S.bg_h; b.w = S.bg_w; b.pitchw = (S.bg_w + 3) & ~3; b.fh = S.flip_h; b.fv = S.flip_v;
+    b.px = reinterpret_cast<const uint32_t*>(bg_pool + bg_off[S.bg]);
+    const int bw0 = persp_block_w(nh, nw);
+    const int bw_shift = (bw0 & (bw0 - 1)) == 0 ? 31 - __clz(bw0) : -1;
+    // tile shape: shrink until a tile's warp_inv window fits the staging buffer
+    int TR = kBgTR, TC = kBgTC;
+    {
+      const double sy = (double)nh / S.bg_rh, sx = (double)nw / S.bg_rw;
+      while (TR * TC > 1) {
+        const int wh = (int)(TR * sy) + 3, ww = (int)(TC * sx) + 3;
+        if (wh * ww <= kBgWCap && wh <= kBgWRows && (ww + bw0 - 1) / bw0 + 1 <= kBgWBlk) break;
+        if (TC * sx >= TR * sy && TC > 1) TC >>= 1; else if (TR > 1) TR >>= 1; else TC >>= 1;
+      }
+    }
+    float* outp = bg_out + (size_t)s * 3 * OH * OW;
+    const double m0 = S.winv[0], m3 = S.winv[3], m6 = S.winv[6];
+    __syncthreads();
+    const bool pre_linear = S.pre_linear != 0;
+    float la[3], lb[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { la[c] = S.lin_a[c]; lb[c] = S.lin_b[c]; }
+
+    for (int ty0 = by0; ty0 < by1; ty0 += TR) {
+      for (int tx0 = 0; tx0 < OW; tx0 += TC) {
+        const int ty1 = min(ty0 + TR, by1), tx1 = min(tx0 + TC, OW);
+        const AreaEnt eY0 = S.ay[ty0 - by0], eY1 = S.ay[ty1 - 1 - by0], eX0 = S.ax[tx0], eX1 = S.ax[tx1 - 1];
+        const int wy0 = eY0.start, wy1 = eY1.start + (eY1.n & 255), wx0 = eX0.start, wx1 = eX1.start + (eX1.n & 255);
+        const int WH = wy1 - wy0, WW = wx1 - wx0;
+        const int blk0 = wx0 / bw0, nblk = (wx1 - 1) / bw0 - blk0 + 1;
+        const bool staged = WH * WW <= kBgWCap && WH <= kBgWRows && nblk <= kBgWBlk;
+        __syncthreads();  // previous tile's readers of rtile / wtile / org / tile[] are done
+        if (tid < 32) {
+          // bounding box, in rotate-canvas pixels, of the window's image under the inverse homography
+          // (a projective map with W > 0 sends the window rectangle into the convex hull of its corners)
+          int X, Y;
+          persp_coord(S.winv, (lane & 1) ? wx1 - 1 : wx0, (lane & 2) ? wy1 - 1 : wy0, bw0, &X, &Y);
+          int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+          int minx = sx, maxx = sx, miny = sy, maxy = sy;
+#pragma unroll
+          for (int o = 1; o < 4; o <<= 1) {
+            minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+            miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+          }
+          if (lane == 0) {
+            const int x0 = max(minx - 1, 0), x1 = min(maxx + 3, nw), y0 = max(miny - 1, 0), y1 = min(maxy + 3, nh);
+            int rtw = max(x1 - x0, 0), rth = max(y1 - y0, 0);
+            if (rtw * rth > kBgRCap || !staged) rtw = rth = 0;
+            S.tile[0] = x0; S.tile[1] = y0; S.tile[2] = rtw; S.tile[3] = rth;
+          }
+        } else if (staged) {
+          // per (row, column block) origins of the perspective coordinate generator
+          for (int k = tid - 32; k < WH * nblk; k += nt - 32) {
+            const double bx = (double)((blk0 + k % nblk) * bw0), yy = (double)(wy0 + k / nblk);
+            const double* M = S.winv;
+            S.org[4 * k + 0] = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
+            S.org[4 * k + 1] = __dadd_rn(__dadd_rn(__dmul_rn(M[3], bx), __dmul_rn(M[4], yy)), M[5]);
+            S.org[4 * k + 2] = __dadd_rn(__dadd_rn(__dmul_rn(M[6], bx), __dmul_rn(M[7], yy)), M[8]);
+          }
+        }
+        __syncthreads();
+        const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
+        // ---- rotate_bounded output over the footprint ----
+        {
+          const int npx = rtw * rth;
+          const unsigned magic = rtw > 0 ? (unsigned)((0x100000000ull + rtw - 1) / rtw) : 0u;
+          const int rs = b.fv ? -b.pitchw : b.pitchw, cs = b.fh ? -1 : 1;
+          const unsigned in_w = (unsigned)(b.w - 1), in_h = (unsigned)(b.h - 1);
+          for (int k = tid; k < npx; k += nt) {
+            const int ty = (int)__umulhi((unsigned)k, magic), tx = k - ty * rtw;
+            int X, Y;
+            rot_coords(S, ry0 + ty, rx0 + tx, &X, &Y);
+            const int sx = X >> 5, sy = Y >> 5;  // canvases are far below the int16 saturation of cv2's remap
+            float4 v;
+            if ((unsigned)sx < in_w && (unsigned)sy < in_h) {
+              // all four taps inside the source: flips folded into the base index and strides
+              const uint32_t* p = b.px + ((b.fv ? b.h - 1 - sy : sy) * b.pitchw + (b.fh ? b.w - 1 - sx : sx));
+              const uint32_t t0 = __ldg(p), t1 = __ldg(p + cs), t2 = __ldg(p + rs), t3 = __ldg(p + rs + cs);
+              float w[4];
+              bilinear_w(X & 31, Y & 31, w);
+              float o[3];
+              if (pre_linear) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  float a = byte_f(t0, c) * w[0];
+                  a = __fmaf_rn(byte_f(t1, c), w[1], a);
+                  a = __fmaf_rn(byte_f(t2, c), w[2], a);
+                  a = __fmaf_rn(byte_f(t3, c), w[3], a);
+                  o[c] = __fmaf_rn(a, la[c], lb[c]);
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  float a = pre_chain(S, byte_f(t0, c), c) * w[0];
+                  a = __fmaf_rn(pre_chain(S, byte_f(t1, c), c), w[1], a);
+                  a = __fmaf_rn(pre_chain(S, byte_f(t2, c), c), w[2], a);
+                  a = __fmaf_rn(pre_chain(S, byte_f(t3, c), c), w[3], a);
+                  o[c] = a;
+                }
+              }
+              v = make_float4(o[0], o[1], o[2], 0.f);
+            } else {
+              v = rot_px_general(S, b, X, Y);
+            }
+            S.rtile[k] = v;
+          }
+        }
+        __syncthreads();
+        if (staged) {
+          // ---- warp_inv output over the window + elementwise ops scheduled after the geometric group ----
+          const int npx = WH * WW;
+          const unsigned magic = (unsigned)((0x100000000ull + WW - 1) / WW);
+          const unsigned fast_w = rtw > 0 ? rtw - 1 : 0, fast_h = rth > 0 ? rth - 1 : 0;
+          const int post_steps = S.post_steps, pc0 = S.post_clip[0], pc1 = S.post_clip[1];
+          for (int k = tid; k < npx; k += nt) {
+            const int r = (int)__umulhi((unsigned)k, magic), cx = k - r * WW;
+            const int wx = wx0 + cx;
+            const int bi = bw_shift >= 0 ? wx >> bw_shift : wx / bw0;
+            const double* o = S.org + 4 * (r * nblk + (bi - blk0));
+            const double2 o01 = *reinterpret_cast<const double2*>(o);
+            int X, Y;
+            persp_xy(o01.x, o01.y, o[2], m0, m3, m6, (double)(wx - bi * bw0), &X, &Y);
+            const int sx = X >> 5, sy = Y >> 5;
+            const int tx = sx - rx0, ty = sy - ry0;
+            float4 t0, t1, t2, t3;
+            if ((unsigned)tx < fast_w && (unsigned)ty < fast_h) {
+              const float4* q = S.rtile + ty * rtw + tx;  // 2x2 footprint inside the staged tile (hence inside the canvas)
+              t0 = q[0]; t1 = q[1]; t2 = q[rtw]; t3 = q[rtw + 1];
+            } else {
+              const int ssx = sat_short(sx), ssy = sat_short(sy);
+              t0 = rot_at(S, b, ssy, ssx); t1 = rot_at(S, b, ssy, ssx + 1);
+              t2 = rot_at(S, b, ssy + 1, ssx); t3 = rot_at(S, b, ssy + 1, ssx + 1);
+            }
+            float w[4];
+            bilinear_w(X & 31, Y & 31, w);
+            float v[3];
+            v[0] = __fmaf_rn(t3.x, w[3], __fmaf_rn(t2.x, w[2], __fmaf_rn(t1.x, w[1], t0.x * w[0])));
+            v[1] = __fmaf_rn(t3.y, w[3], __fmaf_rn(t2.y, w[2], __fmaf_rn(t1.y, w[1], t0.y * w[0])));
+            v[2] = __fmaf_rn(t3.z, w[3], __fmaf_rn(t2.z, w[2], __fmaf_rn(t1.z, w[1], t0.z * w[0])));
+            if (post_steps > 0) {
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                v[c] = __fmaf_rn(v[c], S.post_a[0][c], S.post_b[0][c]);
+                if (pc0) v[c] = sat01(v[c]);
+              }
+              if (post_steps > 1) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  v[c] = __fmaf_rn(v[c], S.post_a[1][c], S.post_b[1][c]);
+                  if (pc1) v[c] = sat01(v[c]);
+                }
+              }
+            }
+            S.wtile[0][k] = v[0]; S.wtile[1][k] = v[1]; S.wtile[2][k] = v[2];
+          }
+        }
+        __syncthreads();
+        // ---- INTER_AREA reduction (cv::ResizeArea_: horizontal taps, then weighted rows) + img_clip (util/image.py:334) ----
+        const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
+        for (int k = tid; k < npx; k += nt) {
+          const int r = k / tw, cidx = k - r * tw;
+          const AreaEnt ey = S.ay[ty0 - by0 + r], ex = S.ax[tx0 + cidx];
+          const int ny = ey.n & 255, nx = ex.n & 255;
+          float sum[3] = {0.f, 0.f, 0.f};
+          for (int j = 0; j < ny; j++) {
+            float h[3] = {0.f, 0.f, 0.f};
+            for (int i = 0; i < nx; i++) {
+              const float wxi = area_w(ex, i);
+              float v[3];
+              if (staged) {
+                const int q = (ey.start + j - wy0) * WW + (ex.start + i - wx0);
+                v[0] = S.wtile[0][q]; v[1] = S.wtile[1][q]; v[2] = S.wtile[2][q];
+              } else {  // window larger than the staging buffer (very large backgrounds): direct evaluation
+                int X, Y;
+                persp_coord(S.winv, ex.start + i, ey.start + j, bw0, &X, &Y);
+                const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+                const float4 t0 = rot_at(S, b, sy, sx), t1 = rot_at(S, b, sy, sx + 1), t2 = rot_at(S, b, sy + 1, sx),
+                             t3 = rot_at(S, b, sy + 1, sx + 1);
+                float w[4];
+                bilinear_w(X & 31, Y & 31, w);
+                v[0] = __fmaf_rn(t3.x, w[3], __fmaf_rn(t2.x, w[2], __fmaf_rn(t1.x, w[1], t0.x * w[0])));
+                v[1] = __fmaf_rn(t3.y, w[3], __fmaf_rn(t2.y, w[2], __fmaf_rn(t1.y, w[1], t0.y * w[0])));
+                v[2] = __fmaf_rn(t3.z, w[3], __fmaf_rn(t2.z, w[2], __fmaf_rn(t1.z, w[1], t0.z * w[0])));
+                for (int q = 0; q < S.post_steps; q++)
+                  for (int c = 0; c < 3; c++) {
+                    v[c] = __fmaf_rn(v[c], S.post_a[q][c], S.post_b[q][c]);
+                    if (S.post_clip[q]) v[c] = sat01(v[c]);
+                  }
+              }
+#pragma unroll
+              for (int c = 0; c < 3; c++) h[c] = __fmaf_rn(v[c], wxi, h[c]);
+            }
+            const float wyj = area_w(ey, j);
+#pragma unroll
+            for (int c = 0; c < 3; c++) sum[c] = __fmaf_rn(wyj, h[c], sum[c]);
+          }
+          const int o = (ty0 + r) * OW + tx0 + cidx;
+#pragma unroll
+          for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = sat01(sum[c]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ //
+// pool ingest: HWC uint8 RGB -> RGBX words, rows padded to 16 B                          //
+// ------------------------------------------------------------------------------------ //
+
+__global__ void k_interleave(const uint8_t* __restrict__ hwc, uint32_t* __restrict__ words, int h, int w, int pitchw) {
+  const size_t img = blockIdx.y;
+  const uint8_t* src = hwc + img * (size_t)h * w * 3;
+  uint32_t* dst = words + img * (size_t)h * pitchw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)h * pitchw; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / pitchw), x = (int)(i % pitchw);
+    uint32_t v = 0;
+    if (x < w) {
+      const uint8_t* p = src + ((size_t)y * w + x) * 3;
+      v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    }
+    dst[i] = v;
+  }
+}
+
+int pool_interleave(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* words, int n, int h, int w, cudaStream_t st) {
+  if (n <= 0) return MTGV_OK;
+  const int pitchw = (w + 3) & ~3;
+  for (int i0 = 0; i0 < n; i0 += 32768) {
+    const int cnt = n - i0 < 32768 ? n - i0 : 32768;
+    dim3 grid(64, cnt);
+    k_interleave<<<grid, 256, 0, st>>>(hwc + (size_t)i0 * h * w * 3, (uint32_t*)words + (size_t)i0 * h * pitchw, h, w, pitchw);
+    ctx->launches++;
+  }
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+size_t bg_image_bytes(int h, int w) { return (size_t)h * ((w + 3) & ~3) * 4; }
+
+int bg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* bg_out, cudaStream_t st) {
+  if (OW > kBgMaxOW) return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw width > 256");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_background, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgSmem)));
+    MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->bg_blocks_per_sm, k_background, kBgThreads, sizeof(BgSmem)));
+    attr_set = true;
+  }
+  if (!ctx->bg_counter) MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_counter, 4));
+  MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->bg_counter, 0, 4, st));
+  const int n_bands = (OH + kBgBandRows - 1) / kBgBandRows;
+  int grid = ctx->sm_count * (ctx->bg_blocks_per_sm > 0 ? ctx->bg_blocks_per_sm : 1);
+  if (grid > m * n_bands) grid = m * n_bands;
+  k_background<<<grid, kBgThreads, sizeof(BgSmem), st>>>(params, m, n_bands, ctx->bg_planes, ctx->bg_off, bg_out, ctx->bg_counter);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+}  // namespace mtgv

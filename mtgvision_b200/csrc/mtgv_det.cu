@@ -357,9 +357,8 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
     float rgb[kDetRows][3];
     if (L.pass == 0) {
       // make_background: cv2.warpPerspective(bg, M, (S,S)) with the cover transform (od_datasets.py:195-203)
-      const int bh = L.bg_hw[2 * T.bg], bw = L.bg_hw[2 * T.bg + 1], pitch = (bw + 15) & ~15;
-      const uint8_t* src = L.bg_planes + L.bg_off[T.bg];
-      const size_t plane = (size_t)bh * pitch;
+      const int bh = L.bg_hw[2 * T.bg], bw = L.bg_hw[2 * T.bg + 1], pitchw = (bw + 3) & ~3;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(L.bg_planes + L.bg_off[T.bg]);  // RGBX words
 #pragma unroll
       for (int i = 0; i < kDetRows; i++) {
         const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
@@ -373,9 +372,9 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
         for (int t = 0; t < 4; t++) {
           const int yy = sy + (t >> 1), xx = sx + (t & 1);
           const bool in = (unsigned)yy < (unsigned)bh && (unsigned)xx < (unsigned)bw;
-          const uint8_t* p = src + (size_t)(in ? yy : 0) * pitch + (in ? xx : 0);
+          const uint32_t word = in ? __ldg(src + (size_t)yy * pitchw + xx) : 0u;
 #pragma unroll
-          for (int c = 0; c < 3; c++) v[t][c] = in ? d_u8_over_255(__ldg(p + c * plane)) : 0.f;
+          for (int c = 0; c < 3; c++) v[t][c] = in ? d_u8_over_255((word >> (8 * c)) & 255u) : 0.f;
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) rgb[i][c] = d_bilinear(v[0][c], v[1][c], v[2][c], v[3][c], X & 31, Y & 31);

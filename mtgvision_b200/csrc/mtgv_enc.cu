@@ -629,344 +629,6 @@ __host__ __device__ inline size_t fg_smem_bytes(int pitch) {
   return (b + 15) & ~(size_t)15;
 }
 
-// ------------------------------------------------------------------------------------ //
-// background chain (make_bg): k_background, all three channels per tile                  //
-// ------------------------------------------------------------------------------------ //
-//
-// make_bg (mtgvision/encoder_datasets.py:774-784) = flip -> rotate_bounded (warpAffine onto
-// an (nh,nw) canvas) -> warp_inv (warpPerspective, same canvas) -> crop_to_size (INTER_AREA to
-// (rh,rw), centre crop) with tint/fade before or after the geometric group.  Only the
-// out_h x out_w crop survives, so the chain is evaluated backwards per output tile:
-// the tile's INTER_AREA window of the warp_inv image, and under the inverse homography the
-// bounding box of that window in the rotate canvas.  Both are staged in shared memory as
-// float32 (every pixel of either stage is computed once per tile, with the reference's
-// arithmetic), coordinates are generated once and shared by the three colour channels.
-
-constexpr int kBgThreads = 256;
-#ifndef MTGV_BG_TC
-#define MTGV_BG_TC 32
-#endif
-constexpr int kBgTR = 8, kBgTC = MTGV_BG_TC;   // output pixels per tile
-constexpr int kBgWCap = MTGV_BG_TC == 16 ? 1792 : 3200;  // warp_inv pixels staged per tile and channel
-constexpr int kBgRCap = MTGV_BG_TC == 16 ? 2048 : 3328;  // rotate-canvas pixels staged per tile and channel
-constexpr int kBgAxis = MTGV_BG_TC == 16 ? 192 : 320;    // max bbox extent per axis covered by the fixed-point tables
-constexpr int kBgWRows = MTGV_BG_TC == 16 ? 32 : 64, kBgWBlk = MTGV_BG_TC == 16 ? 3 : 4;
-constexpr int kBgMinBlocks = MTGV_BG_TC == 16 ? 3 : 2;
-
-struct BgSmem {
-  float lut[3][256];
-  float wtile[3][kBgWCap];
-  float rtile[3][kBgRCap];
-  double org[kBgWRows * kBgWBlk * 3];  // X0,Y0,W0 of WarpPerspectiveInvoker per (row, column block)
-  int colA[kBgAxis], colB[kBgAxis], rowX[kBgAxis], rowY[kBgAxis];
-  int xs[kBgTC], xn[kBgTC], ys[kBgTR], yn[kBgTR];
-  float xw[kBgTC * kAreaMaxTaps], yw[kBgTR * kAreaMaxTaps];
-  float post_a[2][3], post_b[2][3];
-  int post_on[2][3], post_clip[2];
-  int tile[8];  // rx0, ry0, rtw, rth, staged flag
-  mtgv_enc_params sp;
-};
-
-struct BgView {
-  const uint8_t* src;
-  int h, w, pitch, fh, fv, nh, nw;
-  size_t plane;  // bytes per channel plane
-};
-
-// three channels of one flipped-source pixel (BORDER_CONSTANT 0 outside)
-__device__ __forceinline__ void bg_src3(const BgView& b, const BgSmem& S, int y, int x, float* v) {
-  if ((unsigned)y >= (unsigned)b.h || (unsigned)x >= (unsigned)b.w) {
-    v[0] = v[1] = v[2] = 0.f;
-    return;
-  }
-  int yy = b.fv ? b.h - 1 - y : y, xx = b.fh ? b.w - 1 - x : x;  // cv2.flip folded into the index
-  const uint8_t* p = b.src + (size_t)yy * b.pitch + xx;
-  v[0] = S.lut[0][__ldg(p)];
-  v[1] = S.lut[1][__ldg(p + b.plane)];
-  v[2] = S.lut[2][__ldg(p + 2 * b.plane)];
-}
-
-// one pixel of rotate_bounded's warpAffine output from fixed-point coordinates (X, Y in 1/32 px)
-__device__ __forceinline__ void bg_rot3(const BgView& b, const BgSmem& S, int X, int Y, float* out) {
-  int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-  float v0[3], v1[3], v2[3], v3[3];
-  bg_src3(b, S, sy, sx, v0);
-  bg_src3(b, S, sy, sx + 1, v1);
-  bg_src3(b, S, sy + 1, sx, v2);
-  bg_src3(b, S, sy + 1, sx + 1, v3);
-#pragma unroll
-  for (int c = 0; c < 3; c++) out[c] = bilinear_weights_sum(v0[c], v1[c], v2[c], v3[c], X & 31, Y & 31);
-}
-
-__device__ __forceinline__ void bg_rot3_at(const BgView& b, const BgSmem& S, int ry, int rx, float* out) {
-  if ((unsigned)ry >= (unsigned)b.nh || (unsigned)rx >= (unsigned)b.nw) {
-    out[0] = out[1] = out[2] = 0.f;
-    return;
-  }
-  int ty = ry - S.tile[1], tx = rx - S.tile[0];
-  if ((unsigned)ty < (unsigned)S.tile[3] && (unsigned)tx < (unsigned)S.tile[2]) {
-    int k = ty * S.tile[2] + tx;
-    out[0] = S.rtile[0][k]; out[1] = S.rtile[1][k]; out[2] = S.rtile[2][k];
-    return;
-  }
-  // outside the staged footprint: recompute (keeps the tiling a pure optimisation)
-  const double* m = S.sp.rot_inv;
-  int X = (affine_row_origin(m[1], m[2], ry) + affine_col_delta(m[0], rx)) >> 5;
-  int Y = (affine_row_origin(m[4], m[5], ry) + affine_col_delta(m[3], rx)) >> 5;
-  bg_rot3(b, S, X, Y, out);
-}
-
-__global__ void __launch_bounds__(kBgThreads, kBgMinBlocks) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
-                                                           const uint8_t* __restrict__ bg_planes,
-                                                           const int64_t* __restrict__ bg_off, float* __restrict__ bg_out) {
-  extern __shared__ __align__(16) unsigned char bg_smem_raw[];
-  BgSmem& S = *reinterpret_cast<BgSmem*>(bg_smem_raw);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int item = blockIdx.x; item < n * n_bands; item += gridDim.x) {
-    const int s = item / n_bands, band = item % n_bands;
-    __syncthreads();
-    {
-      const uint32_t* src = (const uint32_t*)(params + s);
-      uint32_t* dst = (uint32_t*)&S.sp;
-      for (int k = tid; k < (int)(sizeof(mtgv_enc_params) / 4); k += nt) dst[k] = src[k];
-    }
-    __syncthreads();
-    const mtgv_enc_params& sp = S.sp;
-    if (sp.status != 0 || sp.kind == MTGV_KIND_CROPPED) continue;
-    const int OH = sp.out_h, OW = sp.out_w, nh = sp.rot_nh, nw = sp.rot_nw;
-    // uint8 -> float32/255 -> elementwise ops scheduled before the geometric group, per channel
-    for (int q = tid; q < 768; q += nt) {
-      const int c = q >> 8;
-      float v = __fdiv_rn((float)(q & 255), 255.f);
-      for (int k = 0; k < sp.n_pre; k++) {
-        const mtgv_x_op& op = sp.ops[sp.n_fg + k];
-        if ((op.i[0] >> c) & 1) {
-          v = __fadd_rn(__fmul_rn(op.f[c], v), op.f[4 + c]);
-          if (op.i[1]) v = clip01(v);
-        }
-      }
-      S.lut[c][q & 255] = v;
-    }
-    if (tid < 6) {  // elementwise ops scheduled after the geometric group
-      const int q = tid / 3, c = tid % 3;
-      const bool on = q < sp.n_post;
-      const mtgv_x_op& op = sp.ops[sp.n_fg + sp.n_pre + (on ? q : 0)];
-      S.post_on[q][c] = on && ((op.i[0] >> c) & 1);
-      S.post_a[q][c] = op.f[c];
-      S.post_b[q][c] = op.f[4 + c];
-      if (c == 0) S.post_clip[q] = on && op.i[1];
-    }
-    BgView b;
-    b.h = sp.bg_h; b.w = sp.bg_w; b.pitch = (sp.bg_w + 15) & ~15; b.fh = sp.flip_h; b.fv = sp.flip_v;
-    b.nh = nh; b.nw = nw; b.plane = (size_t)b.h * b.pitch;
-    b.src = bg_planes + bg_off[sp.bg];
-    const int bw0 = persp_block_w(nh, nw);
-    // tile shape: shrink until a tile's warp_inv window fits the staging buffer
-    int TR = kBgTR, TC = kBgTC;
-    {
-      const double sy = (double)nh / sp.bg_rh, sx = (double)nw / sp.bg_rw;
-      while (TR * TC > 1) {
-        int wh = (int)(TR * sy) + 3, ww = (int)(TC * sx) + 3;
-        if (wh * ww <= kBgWCap && wh <= kBgWRows && (ww + bw0 - 1) / bw0 + 1 <= kBgWBlk) break;
-        if (TC * sx >= TR * sy && TC > 1) TC >>= 1; else if (TR > 1) TR >>= 1; else TC >>= 1;
-      }
-    }
-    const int band_rows = (OH + n_bands - 1) / n_bands;
-    const int by0 = band * band_rows, by1 = min(OH, by0 + band_rows);
-    float* outp = bg_out + (size_t)s * 3 * OH * OW;
-    for (int ty0 = by0; ty0 < by1; ty0 += TR) {
-      for (int tx0 = 0; tx0 < OW; tx0 += TC) {
-        const int ty1 = min(ty0 + TR, by1), tx1 = min(tx0 + TC, OW);
-        __syncthreads();
-        // crop_to_size: INTER_AREA (nh,nw)->(bg_rh,bg_rw) tables for this tile's rows / columns
-        if (tid < tx1 - tx0) {
-          int st; float ww[kAreaMaxTaps];
-          int nn = area_taps(nw, sp.bg_rw, sp.bg_x0 + tx0 + tid, &st, ww);
-          S.xs[tid] = st; S.xn[tid] = nn;
-          for (int k = 0; k < kAreaMaxTaps; k++) S.xw[tid * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
-        } else if (tid >= 64 && tid - 64 < ty1 - ty0) {
-          const int r = tid - 64;
-          int st; float ww[kAreaMaxTaps];
-          int nn = area_taps(nh, sp.bg_rh, sp.bg_y0 + ty0 + r, &st, ww);
-          S.ys[r] = st; S.yn[r] = nn;
-          for (int k = 0; k < kAreaMaxTaps; k++) S.yw[r * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
-        }
-        __syncthreads();
-        const int wy0 = S.ys[0], wy1 = S.ys[ty1 - ty0 - 1] + S.yn[ty1 - ty0 - 1];
-        const int wx0 = S.xs[0], wx1 = S.xs[tx1 - tx0 - 1] + S.xn[tx1 - tx0 - 1];
-        const int WH = wy1 - wy0, WW = wx1 - wx0;
-        const int blk0 = wx0 / bw0, nblk = (wx1 - 1) / bw0 - blk0 + 1;
-        const bool staged = WH * WW <= kBgWCap && WH <= kBgWRows && nblk <= kBgWBlk;
-        // per (row, column block) origins of the perspective coordinate generator
-        if (staged) {
-          for (int k = tid; k < WH * nblk; k += nt) {
-            const double bx = (double)((blk0 + k % nblk) * bw0), yy = (double)(wy0 + k / nblk);
-            const double* M = sp.winv;
-            S.org[3 * k + 0] = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
-            S.org[3 * k + 1] = __dadd_rn(__dadd_rn(__dmul_rn(M[3], bx), __dmul_rn(M[4], yy)), M[5]);
-            S.org[3 * k + 2] = __dadd_rn(__dadd_rn(__dmul_rn(M[6], bx), __dmul_rn(M[7], yy)), M[8]);
-          }
-        }
-        if (tid == 0) {
-          // bounding box, in rotate-canvas pixels, of the window's image under the inverse homography
-          int minx = 1 << 30, maxx = -(1 << 30), miny = 1 << 30, maxy = -(1 << 30);
-          for (int k = 0; k < 4; k++) {
-            int X, Y;
-            persp_coord(sp.winv, (k & 1) ? wx1 - 1 : wx0, (k & 2) ? wy1 - 1 : wy0, bw0, &X, &Y);
-            int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-            minx = min(minx, sx); maxx = max(maxx, sx); miny = min(miny, sy); maxy = max(maxy, sy);
-          }
-          int x0 = max(minx - 1, 0), x1 = min(maxx + 3, nw), y0 = max(miny - 1, 0), y1 = min(maxy + 3, nh);
-          int rtw = max(x1 - x0, 0), rth = max(y1 - y0, 0);
-          if (rtw * rth > kBgRCap || rtw > kBgAxis || rth > kBgAxis || !staged) rtw = rth = 0;
-          S.tile[0] = x0; S.tile[1] = y0; S.tile[2] = rtw; S.tile[3] = rth;
-        }
-        __syncthreads();
-        const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
-        // warpAffine fixed-point tables over the footprint
-        for (int k = tid; k < rtw; k += nt) {
-          S.colA[k] = affine_col_delta(sp.rot_inv[0], rx0 + k);
-          S.colB[k] = affine_col_delta(sp.rot_inv[3], rx0 + k);
-        }
-        for (int k = tid; k < rth; k += nt) {
-          S.rowX[k] = affine_row_origin(sp.rot_inv[1], sp.rot_inv[2], ry0 + k);
-          S.rowY[k] = affine_row_origin(sp.rot_inv[4], sp.rot_inv[5], ry0 + k);
-        }
-        __syncthreads();
-        // rotate_bounded output over the footprint: one warp per footprint row
-        {
-          const int nwarps = nt >> 5, lane = tid & 31;
-          const int rs = b.fv ? -b.pitch : b.pitch, cs = b.fh ? -1 : 1;
-          for (int ty = tid >> 5; ty < rth; ty += nwarps) {
-            const int oX = S.rowX[ty], oY = S.rowY[ty];
-            for (int tx = lane; tx < rtw; tx += 32) {
-              const int X = (oX + S.colA[tx]) >> 5, Y = (oY + S.colB[tx]) >> 5;
-              const int sx = X >> 5, sy = Y >> 5;  // canvases are far below the int16 saturation of cv2's remap
-              float v[3];
-              if ((unsigned)sx < (unsigned)(b.w - 1) && (unsigned)sy < (unsigned)(b.h - 1)) {
-                // all four taps inside the source: flips folded into the base address and strides
-                const uint8_t* p = b.src + (size_t)(b.fv ? b.h - 1 - sy : sy) * b.pitch + (b.fh ? b.w - 1 - sx : sx);
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                  const uint8_t* pc = p + c * b.plane;
-                  v[c] = bilinear_weights_sum(S.lut[c][__ldg(pc)], S.lut[c][__ldg(pc + cs)], S.lut[c][__ldg(pc + rs)],
-                                              S.lut[c][__ldg(pc + rs + cs)], X & 31, Y & 31);
-                }
-              } else {
-                bg_rot3(b, S, X, Y, v);
-              }
-              const int k = ty * rtw + tx;
-              S.rtile[0][k] = v[0]; S.rtile[1][k] = v[1]; S.rtile[2][k] = v[2];
-            }
-          }
-        }
-        __syncthreads();
-        if (staged) {
-          // warp_inv output over the window + elementwise ops scheduled after the geometric group
-          const double* M = sp.winv;
-          const double m0 = M[0], m3 = M[3], m6 = M[6];
-          float pa[2][3], pb[2][3];
-          int pon = 0;
-#pragma unroll
-          for (int q = 0; q < 2; q++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-              pa[q][c] = S.post_a[q][c]; pb[q][c] = S.post_b[q][c];
-              pon |= (S.post_on[q][c] ? 1 : 0) << (q * 3 + c);
-            }
-          const int pclip = (S.post_clip[0] ? 1 : 0) | (S.post_clip[1] ? 2 : 0);
-          const int nwarps = nt >> 5, lane = tid & 31;
-          const int bw_shift = (bw0 & (bw0 - 1)) == 0 ? 31 - __clz(bw0) : -1;
-          const unsigned fast_w = rtw > 0 ? rtw - 1 : 0, fast_h = rth > 0 ? rth - 1 : 0;
-          for (int r = tid >> 5; r < WH; r += nwarps) {
-            for (int cx = lane; cx < WW; cx += 32) {
-              const int wx = wx0 + cx;
-              const int bi = bw_shift >= 0 ? wx >> bw_shift : wx / bw0;
-              const double* o = S.org + 3 * (r * nblk + (bi - blk0));
-              const double x1 = (double)(wx - bi * bw0);
-              double W = __dadd_rn(o[2], __dmul_rn(m6, x1));
-              W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
-              const int X = __double2int_rn(__dmul_rn(__dadd_rn(o[0], __dmul_rn(m0, x1)), W));  // saturating, like cv2's clamp
-              const int Y = __double2int_rn(__dmul_rn(__dadd_rn(o[1], __dmul_rn(m3, x1)), W));
-              const int sx = X >> 5, sy = Y >> 5;
-              const int tx = sx - rx0, ty = sy - ry0;
-              float t0[3], t1[3], t2[3], t3[3];
-              if ((unsigned)tx < fast_w && (unsigned)ty < fast_h) {
-                const int q = ty * rtw + tx;  // 2x2 footprint inside the staged tile (hence inside the canvas)
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                  t0[c] = S.rtile[c][q]; t1[c] = S.rtile[c][q + 1]; t2[c] = S.rtile[c][q + rtw]; t3[c] = S.rtile[c][q + rtw + 1];
-                }
-              } else {
-                bg_rot3_at(b, S, sy, sx, t0);
-                bg_rot3_at(b, S, sy, sx + 1, t1);
-                bg_rot3_at(b, S, sy + 1, sx, t2);
-                bg_rot3_at(b, S, sy + 1, sx + 1, t3);
-              }
-              const int k = r * WW + cx;
-#pragma unroll
-              for (int c = 0; c < 3; c++) {
-                float v = bilinear_weights_sum(t0[c], t1[c], t2[c], t3[c], X & 31, Y & 31);
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                  if ((pon >> (q * 3 + c)) & 1) {
-                    v = __fadd_rn(__fmul_rn(pa[q][c], v), pb[q][c]);
-                    if ((pclip >> q) & 1) v = clip01(v);
-                  }
-                }
-                S.wtile[c][k] = v;
-              }
-            }
-          }
-        }
-        __syncthreads();
-        // INTER_AREA reduction + img_clip (util/image.py:334)
-        const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
-        for (int k = tid; k < npx; k += nt) {
-          const int r = k / tw, cidx = k - r * tw;
-          const int y0 = S.ys[r], ny = S.yn[r], x0 = S.xs[cidx], nx = S.xn[cidx];
-          const float* wx = S.xw + cidx * kAreaMaxTaps;
-          const float* wy = S.yw + r * kAreaMaxTaps;
-          float sum[3] = {0.f, 0.f, 0.f};
-          for (int j = 0; j < ny; j++) {
-            float h[3] = {0.f, 0.f, 0.f};
-            for (int i = 0; i < nx; i++) {
-              float v[3];
-              if (staged) {
-                const int q = (y0 + j - wy0) * WW + (x0 + i - wx0);
-                v[0] = S.wtile[0][q]; v[1] = S.wtile[1][q]; v[2] = S.wtile[2][q];
-              } else {  // window larger than the staging buffer (very large backgrounds): direct evaluation
-                int X, Y;
-                persp_coord(sp.winv, x0 + i, y0 + j, bw0, &X, &Y);
-                const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-                float v0[3], v1[3], v2[3], v3[3];
-                bg_rot3_at(b, S, sy, sx, v0); bg_rot3_at(b, S, sy, sx + 1, v1);
-                bg_rot3_at(b, S, sy + 1, sx, v2); bg_rot3_at(b, S, sy + 1, sx + 1, v3);
-                for (int c = 0; c < 3; c++) {
-                  float t = bilinear_weights_sum(v0[c], v1[c], v2[c], v3[c], X & 31, Y & 31);
-                  for (int q = 0; q < 2; q++)
-                    if (S.post_on[q][c]) {
-                      t = __fadd_rn(__fmul_rn(S.post_a[q][c], t), S.post_b[q][c]);
-                      if (S.post_clip[q]) t = clip01(t);
-                    }
-                  v[c] = t;
-                }
-              }
-#pragma unroll
-              for (int c = 0; c < 3; c++) h[c] = __fadd_rn(h[c], __fmul_rn(v[c], wx[i]));
-            }
-#pragma unroll
-            for (int c = 0; c < 3; c++) sum[c] = j == 0 ? __fmul_rn(wy[0], h[c]) : __fadd_rn(sum[c], __fmul_rn(wy[j], h[c]));
-          }
-          const int o = (ty0 + r) * OW + tx0 + cidx;
-#pragma unroll
-          for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = clip01(sum[c]);
-        }
-      }
-    }
-  }
-}
-
 // rgba_over_rgb (util/image.py:246-290): cur = clip(bg*(1-a) + fg*a); bg from k_background's output
 __device__ void stage_composite(float* cur, int HW, const float* __restrict__ bg, const float* __restrict__ alpha) {
   for (int o = threadIdx.x; o < HW; o += blockDim.x) {
@@ -1509,23 +1171,16 @@ static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, 
   static bool attr_set = false;
   if (!attr_set) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_background, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgSmem)));
-    MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->bg_blocks_per_sm, k_background, kBgThreads,
-                                                                     sizeof(BgSmem)));
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_foreground, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const size_t elem = out_dtype == MTGV_OUT_F16 ? 2 : (out_dtype == MTGV_OUT_U8 ? 1 : 4);
-  const int n_bands = 4;
   for (int base = 0; base < n; base += chunk) {
     const int m = n - base < chunk ? n - base : chunk;
     MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->sync_words, 0, ((size_t)m + 1) * 4, st));
     if (ctx->n_bgs > 0) {
-      int grid_bg = ctx->sm_count * (ctx->bg_blocks_per_sm > 0 ? ctx->bg_blocks_per_sm : 1);
-      if (grid_bg > m * n_bands) grid_bg = m * n_bands;
-      k_background<<<grid_bg, kBgThreads, sizeof(BgSmem), st>>>(params + base, m, n_bands, ctx->bg_planes, ctx->bg_off,
-                                                                ctx->bg_scratch);
-      ctx->launches++;
+      int rc2 = bg_launch(ctx, params + base, m, OH, OW, ctx->bg_scratch, st);
+      if (rc2) return rc2;
     }
     {
       int fg_blocks = 0;

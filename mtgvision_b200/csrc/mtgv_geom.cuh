@@ -221,6 +221,38 @@ MTGV_HD int area_taps(int ssize, int dsize, int d, int* start, float* w) {
   return n;
 }
 
+// The same table entry in compact form: taps are [left partial?] full* [right partial?], every
+// full tap weighs 1/cell.  *n = taps | left << 8 | right << 9; weights as area_taps emits them.
+MTGV_HD void area_compact(int ssize, int dsize, int d, int* start, int* n, float* wl, float* wm, float* wr) {
+  double scale = MTGV_DDIV(1.0, MTGV_DDIV((double)dsize, (double)ssize));
+  double fsx1 = MTGV_DMUL((double)d, scale);
+  double fsx2 = MTGV_DADD(fsx1, scale);
+  double cell = fmin(scale, MTGV_DSUB((double)ssize, fsx1));
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
+  sx1 = sx1 < sx2 ? sx1 : sx2;
+  int cnt = 0, flags = 0;
+  *start = sx1;
+  *wl = *wr = 0.f;
+  if (MTGV_DSUB((double)sx1, fsx1) > 1e-3) {
+    *start = sx1 - 1;
+    *wl = (float)MTGV_DDIV(MTGV_DSUB((double)sx1, fsx1), cell);
+    flags |= 256;
+    cnt++;
+  }
+  *wm = (float)MTGV_DDIV(1.0, cell);
+  int mid = sx2 - sx1;
+  if (mid > kAreaMaxTaps - cnt) mid = kAreaMaxTaps - cnt;
+  if (mid > 0) cnt += mid;
+  if (MTGV_DSUB(fsx2, (double)sx2) > 1e-3 && cnt < kAreaMaxTaps) {
+    double t = fmin(fmin(MTGV_DSUB(fsx2, (double)sx2), 1.0), cell);
+    *wr = (float)MTGV_DDIV(t, cell);
+    flags |= 512;
+    cnt++;
+  }
+  *n = cnt | flags;
+}
+
 // crop_to_size integer geometry (mtgvision/util/image.py:359-376).
 MTGV_HD void crop_geometry(int ih, int iw, int sh, int sw, bool pad, int* rh, int* rw, int* y0, int* x0) {
   double fh = MTGV_DDIV((double)ih, (double)sh), fw = MTGV_DDIV((double)iw, (double)sw);

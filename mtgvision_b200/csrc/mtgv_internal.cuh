@@ -28,10 +28,10 @@ struct mtgv_ctx {
   float* mask_enc = nullptr;  // round_rect_mask(card_hw, 0.05) float32, encoder make_masked
   float* mask_det = nullptr;  // round_rect_mask(card_hw, 0.046) float32, detection make_card_with_mask
 
-  // background pool (planar: per image [3][h][pitch])
+  // background pool: per image [h][pitchw] RGBX uint8 words, pitchw = round_up(w,4) (rows are whole 16-byte vectors)
   uint8_t* bg_planes = nullptr;
   int64_t* bg_off = nullptr;  // [n] byte offset of image j in bg_planes
-  int32_t* bg_hw = nullptr;   // [n][2] (h, w)  (pitch = round_up(w,16))
+  int32_t* bg_hw = nullptr;   // [n][2] (h, w)
   int n_bgs = 0;
   std::vector<int64_t> bg_off_host;
   std::vector<int32_t> bg_hw_host;
@@ -45,6 +45,7 @@ struct mtgv_ctx {
   float* bg_scratch = nullptr;  // k_background output for one chunk: [chunk,3,H,W] float32
   size_t bg_cap = 0;            // floats
   int bg_blocks_per_sm = 0;
+  int* bg_counter = nullptr;    // work-queue word of k_background
   size_t alpha_cap = 0;  // samples
   int32_t* sync_words = nullptr;  // [0] work counter, [1..] per-sample alpha-ready flags
   size_t sync_cap = 0;
@@ -111,4 +112,8 @@ int enc_warp_perspective(mtgv_ctx* ctx, const float* src, int n, int sh, int sw,
 int enc_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops,
                       const void* fields, uint64_t seed, cudaStream_t st);
 int pool_planarize(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* planes, int n, int h, int w, int pitch, cudaStream_t st);
+// mtgv_bg.cu
+int pool_interleave(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* words, int n, int h, int w, cudaStream_t st);
+size_t bg_image_bytes(int h, int w);
+int bg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* bg_out, cudaStream_t st);
 }  // namespace mtgv
