@@ -56,7 +56,9 @@ struct BgSmem {
   int pre_clip[2], pre_steps, pre_linear;
   float lin_a[3], lin_b[3];
   float post_a[2][3], post_b[2][3];
-  int post_clip[2], post_steps;
+  int post_clip[2], post_steps, post_linear;
+  float plin_a[3], plin_b[3];
+  int max_nx;
   int tile[4];  // rx0, ry0, rtw, rth
   int item;
 };
@@ -65,18 +67,20 @@ __device__ __forceinline__ float sat01(float v) { return __saturatef(v); }
 
 // cvRound(fX), cvRound(fY) of WarpPerspectiveInvoker for x1 columns past a block origin (X0,Y0,W0).
 // Exact restatement.
-__device__ __noinline__ void persp_exact(double X0, double Y0, double W0, double m0, double m3, double m6, double x1, int* X, int* Y) {
+__device__ __noinline__ int2 persp_exact(double X0, double Y0, double W0, double m0, double m3, double m6, double x1) {
   double W = __dadd_rn(W0, __dmul_rn(m6, x1));
   W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
-  *X = __double2int_rn(__dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W));  // saturating, like cv2's clamp
-  *Y = __double2int_rn(__dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W));
+  int2 r;
+  r.x = __double2int_rn(__dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W));  // saturating, like cv2's clamp
+  r.y = __double2int_rn(__dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W));
+  return r;
 }
 
 // Guarded fast path: reciprocal by rcp.approx + two Newton steps (relative error ~2^-52), results scaled by
 // 2^16 so the distance to the nearest rounding tie is visible in the low bits.  Whenever either coordinate
 // is within 4/65536 of a tie, saturates, or the reciprocal is not finite, the exact routine decides.  The
 // approximate value differs from cv2's by < 1e-6 of those 1/65536 units, so the outputs are identical.
-__device__ __forceinline__ void persp_xy(double X0, double Y0, double W0, double m0, double m3, double m6, double x1, int* X, int* Y) {
+__device__ __forceinline__ int2 persp_xy(double X0, double Y0, double W0, double m0, double m3, double m6, double x1) {
   const double W = __fma_rn(m6, x1, W0);
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(W));
@@ -90,12 +94,8 @@ __device__ __forceinline__ void persp_xy(double X0, double Y0, double W0, double
   const unsigned tx = ((unsigned)xq + 32772u) & 0xFFFFu, ty = ((unsigned)yq + 32772u) & 0xFFFFu;
   const bool finite = (__double2hiint(r) & 0x7FF00000) != 0x7FF00000;
   const bool in_range = (unsigned)xq + 0x7FF00000u < 0xFFE00000u && (unsigned)yq + 0x7FF00000u < 0xFFE00000u;
-  if (finite && in_range && tx > 8u && ty > 8u) {
-    *X = (int)((unsigned)xq + 32768u) >> 16;
-    *Y = (int)((unsigned)yq + 32768u) >> 16;
-  } else {
-    persp_exact(X0, Y0, W0, m0, m3, m6, x1, X, Y);
-  }
+  if (finite && in_range && tx > 8u && ty > 8u) return make_int2((int)((unsigned)xq + 32768u) >> 16, (int)((unsigned)yq + 32768u) >> 16);
+  return persp_exact(X0, Y0, W0, m0, m3, m6, x1);
 }
 
 __device__ __forceinline__ float byte_f(uint32_t w, int c) {  // exact u8 -> float without I2F
@@ -143,7 +143,7 @@ __device__ __noinline__ float4 rot_px_general(const BgSmem& S, const BgSrc& b, i
   return make_float4(acc[0], acc[1], acc[2], 0.f);
 }
 
-__device__ __forceinline__ void rot_coords(const BgSmem& S, int ry, int rx, int* X, int* Y) {
+__device__ __forceinline__ void rot_coords_general(const BgSmem& S, int ry, int rx, int* X, int* Y) {
   int cA, cB, oX, oY;
   if (rx < kBgCanvas) { cA = S.colA[rx]; cB = S.colB[rx]; }
   else { cA = affine_col_delta(S.rot_inv[0], rx); cB = affine_col_delta(S.rot_inv[3], rx); }
@@ -160,7 +160,7 @@ __device__ __noinline__ float4 rot_at(const BgSmem& S, const BgSrc& b, int ry, i
   const int ty = ry - S.tile[1], tx = rx - S.tile[0];
   if ((unsigned)ty < (unsigned)S.tile[3] && (unsigned)tx < (unsigned)S.tile[2]) return S.rtile[ty * S.tile[2] + tx];
   int X, Y;
-  rot_coords(S, ry, rx, &X, &Y);
+  rot_coords_general(S, ry, rx, &X, &Y);
   return rot_px_general(S, b, X, Y);
 }
 
@@ -168,6 +168,138 @@ __device__ __forceinline__ float area_w(const AreaEnt& e, int k) {
   if (k == 0 && (e.n & 256)) return e.wl;
   if (k == (e.n & 255) - 1 && (e.n & 512)) return e.wr;
   return e.wm;
+}
+
+__device__ __forceinline__ unsigned div_magic(int d) { return d > 0 ? (unsigned)((0x100000000ull + d - 1) / d) : 0u; }  // k/d = umulhi(k, magic) while k*d < 2^32
+
+// ---- stage R: rotate_bounded's warpAffine output over the staged footprint ----
+// LINEAR: the elementwise chain in front of the geometric group is affine on the byte range, so the four
+// taps are interpolated as integers (weights (32-ax)(32-ay).. sum to 1024, exact) and the chain is applied once.
+template <bool LINEAR, bool TABLES>
+__device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0, int ry0, int rtw, int rth, const float* la,
+                                             const float* lb, int tid) {
+  const int npx = rtw * rth;
+  const unsigned magic = div_magic(rtw);
+  const int rs = b.fv ? -b.pitchw : b.pitchw, cs = b.fh ? -1 : 1;
+  const unsigned in_w = (unsigned)(b.w - 1), in_h = (unsigned)(b.h - 1);
+  const int ybase = b.fv ? b.h - 1 : 0, ysign = b.fv ? -1 : 1, xbase = b.fh ? b.w - 1 : 0, xsign = b.fh ? -1 : 1;
+  for (int k = tid; k < npx; k += kBgThreads) {
+    const int ty = (int)__umulhi((unsigned)k, magic), tx = k - ty * rtw;
+    int X, Y;
+    if (TABLES) {
+      X = (S.rowX[ry0 + ty] + S.colA[rx0 + tx]) >> 5;
+      Y = (S.rowY[ry0 + ty] + S.colB[rx0 + tx]) >> 5;
+    } else {
+      rot_coords_general(S, ry0 + ty, rx0 + tx, &X, &Y);
+    }
+    const int sx = X >> 5, sy = Y >> 5;  // canvases are far below the int16 saturation of cv2's remap
+    float4 v;
+    if ((unsigned)sx < in_w && (unsigned)sy < in_h) {
+      // all four taps inside the source: cv2.flip folded into the base index and strides
+      const int i0 = (ybase + ysign * sy) * b.pitchw + (xbase + xsign * sx);
+      const uint32_t t0 = __ldg(b.px + i0), t1 = __ldg(b.px + (i0 + cs)), t2 = __ldg(b.px + (i0 + rs)), t3 = __ldg(b.px + (i0 + rs + cs));
+      const int ax = X & 31, ay = Y & 31;
+      if (LINEAR) {
+        const unsigned pxw = (unsigned)(32 - ax) + ((unsigned)ax << 16);
+        const unsigned wtop = pxw * (unsigned)(32 - ay), wbot = pxw * (unsigned)ay;  // (w00 | w01 << 16), (w10 | w11 << 16)
+        const unsigned rg_t = __byte_perm(t0, t1, 0x5140), rg_b = __byte_perm(t2, t3, 0x5140);  // [R0 R1 G0 G1]
+        const unsigned b_t = __byte_perm(t0, t1, 0x0062), b_b = __byte_perm(t2, t3, 0x0062);    // [B0 B1 . .]
+        const unsigned rw = __byte_perm(rg_t, rg_b, 0x5410), gw = __byte_perm(rg_t, rg_b, 0x7632), bw = __byte_perm(b_t, b_b, 0x5410);
+        const unsigned sr = __dp2a_hi(wbot, rw, __dp2a_lo(wtop, rw, 0u));
+        const unsigned sg = __dp2a_hi(wbot, gw, __dp2a_lo(wtop, gw, 0u));
+        const unsigned sb = __dp2a_hi(wbot, bw, __dp2a_lo(wtop, bw, 0u));
+        v = make_float4(__fmaf_rn((float)sr, la[0], lb[0]), __fmaf_rn((float)sg, la[1], lb[1]), __fmaf_rn((float)sb, la[2], lb[2]), 0.f);
+      } else {
+        float w[4];
+        bilinear_w(ax, ay, w);
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float a = pre_chain(S, byte_f(t0, c), c) * w[0];
+          a = __fmaf_rn(pre_chain(S, byte_f(t1, c), c), w[1], a);
+          a = __fmaf_rn(pre_chain(S, byte_f(t2, c), c), w[2], a);
+          a = __fmaf_rn(pre_chain(S, byte_f(t3, c), c), w[3], a);
+          o[c] = a;
+        }
+        v = make_float4(o[0], o[1], o[2], 0.f);
+      }
+    } else {
+      v = rot_px_general(S, b, X, Y);
+    }
+    S.rtile[k] = v;
+  }
+}
+
+// ---- stage A: INTER_AREA reduction (cv::ResizeArea_: horizontal taps, then weighted rows) + img_clip ----
+template <int NX>
+__device__ __forceinline__ void stage_area(const BgSmem& S, int ty0, int ty1, int tx0, int tx1, int by0, int wy0, int wx0, int WW,
+                                           float* __restrict__ outp, int OH, int OW, int tid) {
+  const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
+  const unsigned magic = div_magic(tw);
+  for (int k = tid; k < npx; k += kBgThreads) {
+    const int r = (int)__umulhi((unsigned)k, magic), cidx = k - r * tw;
+    const AreaEnt ey = S.ay[ty0 - by0 + r], ex = S.ax[tx0 + cidx];
+    const int ny = ey.n & 255, nx = ex.n & 255;
+    float wx[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) wx[i] = i < nx ? area_w(ex, i) : 0.f;
+    float sum[3] = {0.f, 0.f, 0.f};
+    int q = (ey.start - wy0) * WW + (ex.start - wx0);
+    for (int j = 0; j < ny; j++, q += WW) {
+      float h[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        if (i < nx) {
+          h[0] = __fmaf_rn(S.wtile[0][q + i], wx[i], h[0]);
+          h[1] = __fmaf_rn(S.wtile[1][q + i], wx[i], h[1]);
+          h[2] = __fmaf_rn(S.wtile[2][q + i], wx[i], h[2]);
+        }
+      }
+      const float wyj = area_w(ey, j);
+#pragma unroll
+      for (int c = 0; c < 3; c++) sum[c] = __fmaf_rn(wyj, h[c], sum[c]);
+    }
+    const int o = (ty0 + r) * OW + tx0 + cidx;
+#pragma unroll
+    for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = sat01(sum[c]);  // img_clip (util/image.py:334)
+  }
+}
+
+// window larger than the staging buffers (very large backgrounds): every tap evaluated directly
+__device__ __noinline__ void stage_area_direct(const BgSmem& S, const BgSrc& b, int ty0, int ty1, int tx0, int tx1, int by0, int bw0,
+                                               float* __restrict__ outp, int OH, int OW, int tid) {
+  const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
+  for (int k = tid; k < npx; k += kBgThreads) {
+    const int r = k / tw, cidx = k - r * tw;
+    const AreaEnt ey = S.ay[ty0 - by0 + r], ex = S.ax[tx0 + cidx];
+    const int ny = ey.n & 255, nx = ex.n & 255;
+    float sum[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < ny; j++) {
+      float h[3] = {0.f, 0.f, 0.f};
+      for (int i = 0; i < nx; i++) {
+        int X, Y;
+        persp_coord(S.winv, ex.start + i, ey.start + j, bw0, &X, &Y);
+        const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+        const float4 t0 = rot_at(S, b, sy, sx), t1 = rot_at(S, b, sy, sx + 1), t2 = rot_at(S, b, sy + 1, sx), t3 = rot_at(S, b, sy + 1, sx + 1);
+        float w[4], v[3];
+        bilinear_w(X & 31, Y & 31, w);
+        v[0] = __fmaf_rn(t3.x, w[3], __fmaf_rn(t2.x, w[2], __fmaf_rn(t1.x, w[1], t0.x * w[0])));
+        v[1] = __fmaf_rn(t3.y, w[3], __fmaf_rn(t2.y, w[2], __fmaf_rn(t1.y, w[1], t0.y * w[0])));
+        v[2] = __fmaf_rn(t3.z, w[3], __fmaf_rn(t2.z, w[2], __fmaf_rn(t1.z, w[1], t0.z * w[0])));
+        for (int q = 0; q < S.post_steps; q++)
+          for (int c = 0; c < 3; c++) {
+            v[c] = __fmaf_rn(v[c], S.post_a[q][c], S.post_b[q][c]);
+            if (S.post_clip[q]) v[c] = sat01(v[c]);
+          }
+        const float wxi = area_w(ex, i);
+        for (int c = 0; c < 3; c++) h[c] = __fmaf_rn(v[c], wxi, h[c]);
+      }
+      const float wyj = area_w(ey, j);
+      for (int c = 0; c < 3; c++) sum[c] = __fmaf_rn(wyj, h[c], sum[c]);
+    }
+    const int o = (ty0 + r) * OW + tx0 + cidx;
+    for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = sat01(sum[c]);
+  }
 }
 
 __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
@@ -178,7 +310,7 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
   const int tid = threadIdx.x, nt = kBgThreads, lane = tid & 31;
   for (;;) {
     __syncthreads();
-    if (tid == 0) S.item = atomicAdd(work_counter, 1);
+    if (tid == 0) { S.item = atomicAdd(work_counter, 1); S.max_nx = 0; }
     __syncthreads();
     const int item = S.item;
     if (item >= n * n_bands) break;
@@ -210,14 +342,27 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
       if (n_pre >= 1 && ((ops[0].i[0] >> c) & 1)) { a0 = ops[0].f[c] * (1.f / 255.f); b0 = ops[0].f[4 + c]; c0 = ops[0].i[1]; }
       if (n_pre >= 2 && ((ops[1].i[0] >> c) & 1)) { a1 = ops[1].f[c]; b1 = ops[1].f[4 + c]; c1 = ops[1].i[1]; }
       S.pre_a[0][c] = a0; S.pre_b[0][c] = b0; S.pre_a[1][c] = a1; S.pre_b[1][c] = b1;
-      // the chain is affine on [0,255] when no step can leave [0,1] at either end of the byte range
+      // a chain is affine on its input range when no clipped step can leave [0,1] at either end of the range
       const float lo0 = b0, hi0 = __fmaf_rn(255.f, a0, b0);
       bool lin = !c0 || (fminf(lo0, hi0) >= 0.f && fmaxf(lo0, hi0) <= 1.f);
       const float lo1 = __fmaf_rn(lo0, a1, b1), hi1 = __fmaf_rn(hi0, a1, b1);
       lin = lin && (!c1 || (fminf(lo1, hi1) >= 0.f && fmaxf(lo1, hi1) <= 1.f));
-      S.lin_a[c] = a0 * a1;
+      S.lin_a[c] = a0 * a1 * (1.f / 1024.f);  // applied to the integer tap sum (weights sum to 1024)
       S.lin_b[c] = __fmaf_rn(b0, a1, b1);
       const unsigned all = __ballot_sync(0x7u, lin);
+      // post chain on values in [0,1]
+      float pa0 = 1.f, pb0 = 0.f, pa1 = 1.f, pb1 = 0.f;
+      int pc0 = 0, pc1 = 0;
+      if (n_post >= 1 && ((ops[n_pre].i[0] >> c) & 1)) { pa0 = ops[n_pre].f[c]; pb0 = ops[n_pre].f[4 + c]; pc0 = ops[n_pre].i[1]; }
+      if (n_post >= 2 && ((ops[n_pre + 1].i[0] >> c) & 1)) { pa1 = ops[n_pre + 1].f[c]; pb1 = ops[n_pre + 1].f[4 + c]; pc1 = ops[n_pre + 1].i[1]; }
+      S.post_a[0][c] = pa0; S.post_b[0][c] = pb0; S.post_a[1][c] = pa1; S.post_b[1][c] = pb1;
+      const float ql0 = pb0, qh0 = pa0 + pb0;
+      bool plin = !pc0 || (fminf(ql0, qh0) >= 0.f && fmaxf(ql0, qh0) <= 1.f);
+      const float ql1 = __fmaf_rn(ql0, pa1, pb1), qh1 = __fmaf_rn(qh0, pa1, pb1);
+      plin = plin && (!pc1 || (fminf(ql1, qh1) >= 0.f && fmaxf(ql1, qh1) <= 1.f));
+      S.plin_a[c] = pa0 * pa1;
+      S.plin_b[c] = __fmaf_rn(pb0, pa1, pb1);
+      const unsigned pall = __ballot_sync(0x7u, plin);
       if (c == 0) {
         S.pre_clip[0] = (n_pre >= 1) ? ops[0].i[1] : 0;
         S.pre_clip[1] = (n_pre >= 2) ? ops[1].i[1] : 0;
@@ -226,12 +371,7 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
         S.post_steps = n_post;
         S.post_clip[0] = n_post >= 1 ? ops[n_pre].i[1] : 0;
         S.post_clip[1] = n_post >= 2 ? ops[n_pre + 1].i[1] : 0;
-      }
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const bool on = q < n_post && ((ops[n_pre + (q < n_post ? q : 0)].i[0] >> c) & 1);
-        S.post_a[q][c] = on ? ops[n_pre + q].f[c] : 1.f;
-        S.post_b[q][c] = on ? ops[n_pre + q].f[4 + c] : 0.f;
+        S.post_linear = pall == 0x7u;
       }
     }
     for (int k = tid; k < kBgCanvas; k += nt) {  // warpAffine fixed-point tables (cv::warpAffine adelta/bdelta, X0/Y0)
@@ -241,14 +381,21 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
     // crop_to_size: INTER_AREA (nh,nw)->(bg_rh,bg_rw) tables for the band's rows and all columns
     for (int k = tid; k < OW + (by1 - by0); k += nt) {
       AreaEnt e;
-      if (k < OW) { area_compact(nw, S.bg_rw, S.bg_x0 + k, &e.start, &e.n, &e.wl, &e.wm, &e.wr); S.ax[k] = e; }
-      else { area_compact(nh, S.bg_rh, S.bg_y0 + by0 + (k - OW), &e.start, &e.n, &e.wl, &e.wm, &e.wr); S.ay[k - OW] = e; }
+      if (k < OW) {
+        area_compact(nw, S.bg_rw, S.bg_x0 + k, &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+        S.ax[k] = e;
+        atomicMax(&S.max_nx, e.n & 255);
+      } else {
+        area_compact(nh, S.bg_rh, S.bg_y0 + by0 + (k - OW), &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+        S.ay[k - OW] = e;
+      }
     }
     BgSrc b;
     b.h = S.bg_h; b.w = S.bg_w; b.pitchw = (S.bg_w + 3) & ~3; b.fh = S.flip_h; b.fv = S.flip_v;
     b.px = reinterpret_cast<const uint32_t*>(bg_pool + bg_off[S.bg]);
     const int bw0 = persp_block_w(nh, nw);
-    const int bw_shift = (bw0 & (bw0 - 1)) == 0 ? 31 - __clz(bw0) : -1;
+    const unsigned bw_magic = div_magic(bw0);
+    const bool tables = nh <= kBgCanvas && nw <= kBgCanvas;
     // tile shape: shrink until a tile's warp_inv window fits the staging buffer
     int TR = kBgTR, TC = kBgTC;
     {
@@ -262,10 +409,11 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
     float* outp = bg_out + (size_t)s * 3 * OH * OW;
     const double m0 = S.winv[0], m3 = S.winv[3], m6 = S.winv[6];
     __syncthreads();
-    const bool pre_linear = S.pre_linear != 0;
-    float la[3], lb[3];
+    const bool pre_linear = S.pre_linear != 0, post_linear = S.post_linear != 0;
+    const int max_nx = S.max_nx;
+    float la[3], lb[3], pa[3], pb[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) { la[c] = S.lin_a[c]; lb[c] = S.lin_b[c]; }
+    for (int c = 0; c < 3; c++) { la[c] = S.lin_a[c]; lb[c] = S.lin_b[c]; pa[c] = S.plin_a[c]; pb[c] = S.plin_b[c]; }
 
     for (int ty0 = by0; ty0 < by1; ty0 += TR) {
       for (int tx0 = 0; tx0 < OW; tx0 += TC) {
@@ -273,7 +421,7 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
         const AreaEnt eY0 = S.ay[ty0 - by0], eY1 = S.ay[ty1 - 1 - by0], eX0 = S.ax[tx0], eX1 = S.ax[tx1 - 1];
         const int wy0 = eY0.start, wy1 = eY1.start + (eY1.n & 255), wx0 = eX0.start, wx1 = eX1.start + (eX1.n & 255);
         const int WH = wy1 - wy0, WW = wx1 - wx0;
-        const int blk0 = wx0 / bw0, nblk = (wx1 - 1) / bw0 - blk0 + 1;
+        const int blk0 = (int)__umulhi((unsigned)wx0, bw_magic), nblk = (int)__umulhi((unsigned)(wx1 - 1), bw_magic) - blk0 + 1;
         const bool staged = WH * WW <= kBgWCap && WH <= kBgWRows && nblk <= kBgWBlk;
         __syncthreads();  // previous tile's readers of rtile / wtile / org / tile[] are done
         if (tid < 32) {
@@ -296,8 +444,10 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
           }
         } else if (staged) {
           // per (row, column block) origins of the perspective coordinate generator
+          const unsigned nb_magic = div_magic(nblk);
           for (int k = tid - 32; k < WH * nblk; k += nt - 32) {
-            const double bx = (double)((blk0 + k % nblk) * bw0), yy = (double)(wy0 + k / nblk);
+            const int wr = (int)__umulhi((unsigned)k, nb_magic);
+            const double bx = (double)((blk0 + (k - wr * nblk)) * bw0), yy = (double)(wy0 + wr);
             const double* M = S.winv;
             S.org[4 * k + 0] = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
             S.org[4 * k + 1] = __dadd_rn(__dadd_rn(__dmul_rn(M[3], bx), __dmul_rn(M[4], yy)), M[5]);
@@ -306,67 +456,23 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
         }
         __syncthreads();
         const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
-        // ---- rotate_bounded output over the footprint ----
-        {
-          const int npx = rtw * rth;
-          const unsigned magic = rtw > 0 ? (unsigned)((0x100000000ull + rtw - 1) / rtw) : 0u;
-          const int rs = b.fv ? -b.pitchw : b.pitchw, cs = b.fh ? -1 : 1;
-          const unsigned in_w = (unsigned)(b.w - 1), in_h = (unsigned)(b.h - 1);
-          for (int k = tid; k < npx; k += nt) {
-            const int ty = (int)__umulhi((unsigned)k, magic), tx = k - ty * rtw;
-            int X, Y;
-            rot_coords(S, ry0 + ty, rx0 + tx, &X, &Y);
-            const int sx = X >> 5, sy = Y >> 5;  // canvases are far below the int16 saturation of cv2's remap
-            float4 v;
-            if ((unsigned)sx < in_w && (unsigned)sy < in_h) {
-              // all four taps inside the source: flips folded into the base index and strides
-              const uint32_t* p = b.px + ((b.fv ? b.h - 1 - sy : sy) * b.pitchw + (b.fh ? b.w - 1 - sx : sx));
-              const uint32_t t0 = __ldg(p), t1 = __ldg(p + cs), t2 = __ldg(p + rs), t3 = __ldg(p + rs + cs);
-              float w[4];
-              bilinear_w(X & 31, Y & 31, w);
-              float o[3];
-              if (pre_linear) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                  float a = byte_f(t0, c) * w[0];
-                  a = __fmaf_rn(byte_f(t1, c), w[1], a);
-                  a = __fmaf_rn(byte_f(t2, c), w[2], a);
-                  a = __fmaf_rn(byte_f(t3, c), w[3], a);
-                  o[c] = __fmaf_rn(a, la[c], lb[c]);
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                  float a = pre_chain(S, byte_f(t0, c), c) * w[0];
-                  a = __fmaf_rn(pre_chain(S, byte_f(t1, c), c), w[1], a);
-                  a = __fmaf_rn(pre_chain(S, byte_f(t2, c), c), w[2], a);
-                  a = __fmaf_rn(pre_chain(S, byte_f(t3, c), c), w[3], a);
-                  o[c] = a;
-                }
-              }
-              v = make_float4(o[0], o[1], o[2], 0.f);
-            } else {
-              v = rot_px_general(S, b, X, Y);
-            }
-            S.rtile[k] = v;
-          }
-        }
+        if (!tables) stage_rotate<false, false>(S, b, rx0, ry0, rtw, rth, la, lb, tid);
+        else if (pre_linear) stage_rotate<true, true>(S, b, rx0, ry0, rtw, rth, la, lb, tid);
+        else stage_rotate<false, true>(S, b, rx0, ry0, rtw, rth, la, lb, tid);
         __syncthreads();
         if (staged) {
-          // ---- warp_inv output over the window + elementwise ops scheduled after the geometric group ----
+          // ---- stage W: warp_inv output over the window + elementwise ops scheduled after the geometric group ----
           const int npx = WH * WW;
-          const unsigned magic = (unsigned)((0x100000000ull + WW - 1) / WW);
+          const unsigned magic = div_magic(WW);
           const unsigned fast_w = rtw > 0 ? rtw - 1 : 0, fast_h = rth > 0 ? rth - 1 : 0;
-          const int post_steps = S.post_steps, pc0 = S.post_clip[0], pc1 = S.post_clip[1];
           for (int k = tid; k < npx; k += nt) {
             const int r = (int)__umulhi((unsigned)k, magic), cx = k - r * WW;
             const int wx = wx0 + cx;
-            const int bi = bw_shift >= 0 ? wx >> bw_shift : wx / bw0;
+            const int bi = (int)__umulhi((unsigned)wx, bw_magic);
             const double* o = S.org + 4 * (r * nblk + (bi - blk0));
             const double2 o01 = *reinterpret_cast<const double2*>(o);
-            int X, Y;
-            persp_xy(o01.x, o01.y, o[2], m0, m3, m6, (double)(wx - bi * bw0), &X, &Y);
-            const int sx = X >> 5, sy = Y >> 5;
+            const int2 XY = persp_xy(o01.x, o01.y, o[2], m0, m3, m6, (double)(wx - bi * bw0));
+            const int sx = XY.x >> 5, sy = XY.y >> 5;
             const int tx = sx - rx0, ty = sy - ry0;
             float4 t0, t1, t2, t3;
             if ((unsigned)tx < fast_w && (unsigned)ty < fast_h) {
@@ -378,72 +484,31 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
               t2 = rot_at(S, b, ssy + 1, ssx); t3 = rot_at(S, b, ssy + 1, ssx + 1);
             }
             float w[4];
-            bilinear_w(X & 31, Y & 31, w);
+            bilinear_w(XY.x & 31, XY.y & 31, w);
             float v[3];
             v[0] = __fmaf_rn(t3.x, w[3], __fmaf_rn(t2.x, w[2], __fmaf_rn(t1.x, w[1], t0.x * w[0])));
             v[1] = __fmaf_rn(t3.y, w[3], __fmaf_rn(t2.y, w[2], __fmaf_rn(t1.y, w[1], t0.y * w[0])));
             v[2] = __fmaf_rn(t3.z, w[3], __fmaf_rn(t2.z, w[2], __fmaf_rn(t1.z, w[1], t0.z * w[0])));
-            if (post_steps > 0) {
+            if (post_linear) {
+#pragma unroll
+              for (int c = 0; c < 3; c++) v[c] = __fmaf_rn(v[c], pa[c], pb[c]);
+            } else {
 #pragma unroll
               for (int c = 0; c < 3; c++) {
                 v[c] = __fmaf_rn(v[c], S.post_a[0][c], S.post_b[0][c]);
-                if (pc0) v[c] = sat01(v[c]);
-              }
-              if (post_steps > 1) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                  v[c] = __fmaf_rn(v[c], S.post_a[1][c], S.post_b[1][c]);
-                  if (pc1) v[c] = sat01(v[c]);
-                }
+                if (S.post_clip[0]) v[c] = sat01(v[c]);
+                v[c] = __fmaf_rn(v[c], S.post_a[1][c], S.post_b[1][c]);
+                if (S.post_clip[1]) v[c] = sat01(v[c]);
               }
             }
             S.wtile[0][k] = v[0]; S.wtile[1][k] = v[1]; S.wtile[2][k] = v[2];
           }
         }
         __syncthreads();
-        // ---- INTER_AREA reduction (cv::ResizeArea_: horizontal taps, then weighted rows) + img_clip (util/image.py:334) ----
-        const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
-        for (int k = tid; k < npx; k += nt) {
-          const int r = k / tw, cidx = k - r * tw;
-          const AreaEnt ey = S.ay[ty0 - by0 + r], ex = S.ax[tx0 + cidx];
-          const int ny = ey.n & 255, nx = ex.n & 255;
-          float sum[3] = {0.f, 0.f, 0.f};
-          for (int j = 0; j < ny; j++) {
-            float h[3] = {0.f, 0.f, 0.f};
-            for (int i = 0; i < nx; i++) {
-              const float wxi = area_w(ex, i);
-              float v[3];
-              if (staged) {
-                const int q = (ey.start + j - wy0) * WW + (ex.start + i - wx0);
-                v[0] = S.wtile[0][q]; v[1] = S.wtile[1][q]; v[2] = S.wtile[2][q];
-              } else {  // window larger than the staging buffer (very large backgrounds): direct evaluation
-                int X, Y;
-                persp_coord(S.winv, ex.start + i, ey.start + j, bw0, &X, &Y);
-                const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-                const float4 t0 = rot_at(S, b, sy, sx), t1 = rot_at(S, b, sy, sx + 1), t2 = rot_at(S, b, sy + 1, sx),
-                             t3 = rot_at(S, b, sy + 1, sx + 1);
-                float w[4];
-                bilinear_w(X & 31, Y & 31, w);
-                v[0] = __fmaf_rn(t3.x, w[3], __fmaf_rn(t2.x, w[2], __fmaf_rn(t1.x, w[1], t0.x * w[0])));
-                v[1] = __fmaf_rn(t3.y, w[3], __fmaf_rn(t2.y, w[2], __fmaf_rn(t1.y, w[1], t0.y * w[0])));
-                v[2] = __fmaf_rn(t3.z, w[3], __fmaf_rn(t2.z, w[2], __fmaf_rn(t1.z, w[1], t0.z * w[0])));
-                for (int q = 0; q < S.post_steps; q++)
-                  for (int c = 0; c < 3; c++) {
-                    v[c] = __fmaf_rn(v[c], S.post_a[q][c], S.post_b[q][c]);
-                    if (S.post_clip[q]) v[c] = sat01(v[c]);
-                  }
-              }
-#pragma unroll
-              for (int c = 0; c < 3; c++) h[c] = __fmaf_rn(v[c], wxi, h[c]);
-            }
-            const float wyj = area_w(ey, j);
-#pragma unroll
-            for (int c = 0; c < 3; c++) sum[c] = __fmaf_rn(wyj, h[c], sum[c]);
-          }
-          const int o = (ty0 + r) * OW + tx0 + cidx;
-#pragma unroll
-          for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = sat01(sum[c]);
-        }
+        if (!staged) stage_area_direct(S, b, ty0, ty1, tx0, tx1, by0, bw0, outp, OH, OW, tid);
+        else if (max_nx <= 4) stage_area<4>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, outp, OH, OW, tid);
+        else if (max_nx <= 6) stage_area<6>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, outp, OH, OW, tid);
+        else stage_area<kAreaMaxTaps>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, outp, OH, OW, tid);
       }
     }
   }
