@@ -59,7 +59,7 @@ struct BgSmem {
   int post_clip[2], post_steps, post_linear;
   float plin_a[3], plin_b[3];
   int max_nx;
-  int tile[4];  // rx0, ry0, rtw, rth
+  int tile[8];  // rx0, ry0, rtw, rth, division magics of rtw, WW, tile width
   int item;
 };
 
@@ -170,40 +170,54 @@ __device__ __forceinline__ float area_w(const AreaEnt& e, int k) {
   return e.wm;
 }
 
-__device__ __forceinline__ unsigned div_magic(int d) { return d > 0 ? (unsigned)((0x100000000ull + d - 1) / d) : 0u; }  // k/d = umulhi(k, magic) while k*d < 2^32
+// k / d == (k * magic) >> 24 for k * d < 2^24 (tile-local indices and extents: k < 2^15, d < 2^9)
+__device__ __forceinline__ unsigned div_magic(int d) { return d > 0 ? ((1u << 24) + (unsigned)d - 1u) / (unsigned)d : 0u; }
+__device__ __forceinline__ int div_by(int k, unsigned magic) { return (int)(((unsigned)k * magic) >> 24); }
 
 // ---- stage R: rotate_bounded's warpAffine output over the staged footprint ----
 // LINEAR: the elementwise chain in front of the geometric group is affine on the byte range, so the four
 // taps are interpolated as integers (weights (32-ax)(32-ay).. sum to 1024, exact) and the chain is applied once.
+struct RTap {
+  int X, Y;
+  uint32_t t0, t1, t2, t3;
+  bool in;
+};
+
 template <bool LINEAR, bool TABLES>
-__device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0, int ry0, int rtw, int rth, const float* la,
-                                             const float* lb, int tid) {
+__device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0, int ry0, int rtw, int rth, unsigned magic,
+                                             const float* la, const float* lb, int tid) {
   const int npx = rtw * rth;
-  const unsigned magic = div_magic(rtw);
   const int rs = b.fv ? -b.pitchw : b.pitchw, cs = b.fh ? -1 : 1;
   const unsigned in_w = (unsigned)(b.w - 1), in_h = (unsigned)(b.h - 1);
   const int ybase = b.fv ? b.h - 1 : 0, ysign = b.fv ? -1 : 1, xbase = b.fh ? b.w - 1 : 0, xsign = b.fh ? -1 : 1;
-  for (int k = tid; k < npx; k += kBgThreads) {
-    const int ty = (int)__umulhi((unsigned)k, magic), tx = k - ty * rtw;
-    int X, Y;
+  auto fetch = [&](int k) {
+    RTap t;
+    const int ty = div_by(k, magic), tx = k - ty * rtw;
     if (TABLES) {
-      X = (S.rowX[ry0 + ty] + S.colA[rx0 + tx]) >> 5;
-      Y = (S.rowY[ry0 + ty] + S.colB[rx0 + tx]) >> 5;
+      t.X = (S.rowX[ry0 + ty] + S.colA[rx0 + tx]) >> 5;
+      t.Y = (S.rowY[ry0 + ty] + S.colB[rx0 + tx]) >> 5;
     } else {
-      rot_coords_general(S, ry0 + ty, rx0 + tx, &X, &Y);
+      rot_coords_general(S, ry0 + ty, rx0 + tx, &t.X, &t.Y);
     }
-    const int sx = X >> 5, sy = Y >> 5;  // canvases are far below the int16 saturation of cv2's remap
-    float4 v;
-    if ((unsigned)sx < in_w && (unsigned)sy < in_h) {
+    const int sx = t.X >> 5, sy = t.Y >> 5;  // canvases are far below the int16 saturation of cv2's remap
+    t.in = (unsigned)sx < in_w && (unsigned)sy < in_h;
+    t.t0 = t.t1 = t.t2 = t.t3 = 0u;
+    if (t.in) {
       // all four taps inside the source: cv2.flip folded into the base index and strides
       const int i0 = (ybase + ysign * sy) * b.pitchw + (xbase + xsign * sx);
-      const uint32_t t0 = __ldg(b.px + i0), t1 = __ldg(b.px + (i0 + cs)), t2 = __ldg(b.px + (i0 + rs)), t3 = __ldg(b.px + (i0 + rs + cs));
-      const int ax = X & 31, ay = Y & 31;
+      t.t0 = __ldg(b.px + i0); t.t1 = __ldg(b.px + (i0 + cs)); t.t2 = __ldg(b.px + (i0 + rs)); t.t3 = __ldg(b.px + (i0 + rs + cs));
+    }
+    return t;
+  };
+  auto finish = [&](int k, const RTap& t) {
+    float4 v;
+    if (t.in) {
+      const int ax = t.X & 31, ay = t.Y & 31;
       if (LINEAR) {
         const unsigned pxw = (unsigned)(32 - ax) + ((unsigned)ax << 16);
         const unsigned wtop = pxw * (unsigned)(32 - ay), wbot = pxw * (unsigned)ay;  // (w00 | w01 << 16), (w10 | w11 << 16)
-        const unsigned rg_t = __byte_perm(t0, t1, 0x5140), rg_b = __byte_perm(t2, t3, 0x5140);  // [R0 R1 G0 G1]
-        const unsigned b_t = __byte_perm(t0, t1, 0x0062), b_b = __byte_perm(t2, t3, 0x0062);    // [B0 B1 . .]
+        const unsigned rg_t = __byte_perm(t.t0, t.t1, 0x5140), rg_b = __byte_perm(t.t2, t.t3, 0x5140);  // [R0 R1 G0 G1]
+        const unsigned b_t = __byte_perm(t.t0, t.t1, 0x0062), b_b = __byte_perm(t.t2, t.t3, 0x0062);    // [B0 B1 . .]
         const unsigned rw = __byte_perm(rg_t, rg_b, 0x5410), gw = __byte_perm(rg_t, rg_b, 0x7632), bw = __byte_perm(b_t, b_b, 0x5410);
         const unsigned sr = __dp2a_hi(wbot, rw, __dp2a_lo(wtop, rw, 0u));
         const unsigned sg = __dp2a_hi(wbot, gw, __dp2a_lo(wtop, gw, 0u));
@@ -215,29 +229,35 @@ __device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0,
         float o[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          float a = pre_chain(S, byte_f(t0, c), c) * w[0];
-          a = __fmaf_rn(pre_chain(S, byte_f(t1, c), c), w[1], a);
-          a = __fmaf_rn(pre_chain(S, byte_f(t2, c), c), w[2], a);
-          a = __fmaf_rn(pre_chain(S, byte_f(t3, c), c), w[3], a);
+          float a = pre_chain(S, byte_f(t.t0, c), c) * w[0];
+          a = __fmaf_rn(pre_chain(S, byte_f(t.t1, c), c), w[1], a);
+          a = __fmaf_rn(pre_chain(S, byte_f(t.t2, c), c), w[2], a);
+          a = __fmaf_rn(pre_chain(S, byte_f(t.t3, c), c), w[3], a);
           o[c] = a;
         }
         v = make_float4(o[0], o[1], o[2], 0.f);
       }
     } else {
-      v = rot_px_general(S, b, X, Y);
+      v = rot_px_general(S, b, t.X, t.Y);
     }
     S.rtile[k] = v;
+  };
+  for (int k = tid; k < npx; k += 2 * kBgThreads) {
+    const int k2 = k + kBgThreads;
+    const bool two = k2 < npx;
+    const RTap a = fetch(k), c = fetch(two ? k2 : k);
+    finish(k, a);
+    if (two) finish(k2, c);
   }
 }
 
 // ---- stage A: INTER_AREA reduction (cv::ResizeArea_: horizontal taps, then weighted rows) + img_clip ----
 template <int NX>
 __device__ __forceinline__ void stage_area(const BgSmem& S, int ty0, int ty1, int tx0, int tx1, int by0, int wy0, int wx0, int WW,
-                                           float* __restrict__ outp, int OH, int OW, int tid) {
+                                           unsigned magic, float* __restrict__ outp, int OH, int OW, int tid) {
   const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
-  const unsigned magic = div_magic(tw);
   for (int k = tid; k < npx; k += kBgThreads) {
-    const int r = (int)__umulhi((unsigned)k, magic), cidx = k - r * tw;
+    const int r = div_by(k, magic), cidx = k - r * tw;
     const AreaEnt ey = S.ay[ty0 - by0 + r], ex = S.ax[tx0 + cidx];
     const int ny = ey.n & 255, nx = ex.n & 255;
     float wx[NX];
@@ -421,7 +441,7 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
         const AreaEnt eY0 = S.ay[ty0 - by0], eY1 = S.ay[ty1 - 1 - by0], eX0 = S.ax[tx0], eX1 = S.ax[tx1 - 1];
         const int wy0 = eY0.start, wy1 = eY1.start + (eY1.n & 255), wx0 = eX0.start, wx1 = eX1.start + (eX1.n & 255);
         const int WH = wy1 - wy0, WW = wx1 - wx0;
-        const int blk0 = (int)__umulhi((unsigned)wx0, bw_magic), nblk = (int)__umulhi((unsigned)(wx1 - 1), bw_magic) - blk0 + 1;
+        const int blk0 = div_by(wx0, bw_magic), nblk = div_by(wx1 - 1, bw_magic) - blk0 + 1;
         const bool staged = WH * WW <= kBgWCap && WH <= kBgWRows && nblk <= kBgWBlk;
         __syncthreads();  // previous tile's readers of rtile / wtile / org / tile[] are done
         if (tid < 32) {
@@ -441,12 +461,16 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
             int rtw = max(x1 - x0, 0), rth = max(y1 - y0, 0);
             if (rtw * rth > kBgRCap || !staged) rtw = rth = 0;
             S.tile[0] = x0; S.tile[1] = y0; S.tile[2] = rtw; S.tile[3] = rth;
+            S.tile[4] = (int)div_magic(rtw);
+          } else if (lane == 1) {
+            S.tile[5] = (int)div_magic(WW);
+          } else if (lane == 2) {
+            S.tile[6] = (int)div_magic(tx1 - tx0);
           }
         } else if (staged) {
           // per (row, column block) origins of the perspective coordinate generator
-          const unsigned nb_magic = div_magic(nblk);
           for (int k = tid - 32; k < WH * nblk; k += nt - 32) {
-            const int wr = (int)__umulhi((unsigned)k, nb_magic);
+            const int wr = nblk == 1 ? k : (nblk == 2 ? k >> 1 : k / 3);  // nblk <= kBgWBlk
             const double bx = (double)((blk0 + (k - wr * nblk)) * bw0), yy = (double)(wy0 + wr);
             const double* M = S.winv;
             S.org[4 * k + 0] = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
@@ -456,22 +480,24 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
         }
         __syncthreads();
         const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
-        if (!tables) stage_rotate<false, false>(S, b, rx0, ry0, rtw, rth, la, lb, tid);
-        else if (pre_linear) stage_rotate<true, true>(S, b, rx0, ry0, rtw, rth, la, lb, tid);
-        else stage_rotate<false, true>(S, b, rx0, ry0, rtw, rth, la, lb, tid);
+        const unsigned mg_r = (unsigned)S.tile[4], mg_w = (unsigned)S.tile[5], mg_a = (unsigned)S.tile[6];
+        if (!tables) stage_rotate<false, false>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
+        else if (pre_linear) stage_rotate<true, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
+        else stage_rotate<false, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
         __syncthreads();
         if (staged) {
           // ---- stage W: warp_inv output over the window + elementwise ops scheduled after the geometric group ----
           const int npx = WH * WW;
-          const unsigned magic = div_magic(WW);
           const unsigned fast_w = rtw > 0 ? rtw - 1 : 0, fast_h = rth > 0 ? rth - 1 : 0;
-          for (int k = tid; k < npx; k += nt) {
-            const int r = (int)__umulhi((unsigned)k, magic), cx = k - r * WW;
+          auto coords = [&](int k) {
+            const int r = div_by(k, mg_w), cx = k - r * WW;
             const int wx = wx0 + cx;
-            const int bi = (int)__umulhi((unsigned)wx, bw_magic);
+            const int bi = div_by(wx, bw_magic);
             const double* o = S.org + 4 * (r * nblk + (bi - blk0));
             const double2 o01 = *reinterpret_cast<const double2*>(o);
-            const int2 XY = persp_xy(o01.x, o01.y, o[2], m0, m3, m6, (double)(wx - bi * bw0));
+            return persp_xy(o01.x, o01.y, o[2], m0, m3, m6, (double)(wx - bi * bw0));
+          };
+          auto finish = [&](int k, int2 XY) {
             const int sx = XY.x >> 5, sy = XY.y >> 5;
             const int tx = sx - rx0, ty = sy - ry0;
             float4 t0, t1, t2, t3;
@@ -502,13 +528,20 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
               }
             }
             S.wtile[0][k] = v[0]; S.wtile[1][k] = v[1]; S.wtile[2][k] = v[2];
+          };
+          for (int k = tid; k < npx; k += 2 * nt) {
+            const int k2 = k + nt;
+            const bool two = k2 < npx;
+            const int2 xa = coords(k), xb = coords(two ? k2 : k);
+            finish(k, xa);
+            if (two) finish(k2, xb);
           }
         }
         __syncthreads();
         if (!staged) stage_area_direct(S, b, ty0, ty1, tx0, tx1, by0, bw0, outp, OH, OW, tid);
-        else if (max_nx <= 4) stage_area<4>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, outp, OH, OW, tid);
-        else if (max_nx <= 6) stage_area<6>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, outp, OH, OW, tid);
-        else stage_area<kAreaMaxTaps>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, outp, OH, OW, tid);
+        else if (max_nx <= 4) stage_area<4>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
+        else if (max_nx <= 6) stage_area<6>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
+        else stage_area<kAreaMaxTaps>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
       }
     }
   }

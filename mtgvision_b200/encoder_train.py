@@ -158,6 +158,78 @@ class RanMtgEncDecDataset(IterableDataset):
             torch.cuda.current_stream(ctx.device).synchronize()
         return out
 
+    def host_tensor_batches(self, source):
+        """Streaming form of `host_tensor_batch`: `source` yields `(card_images, bg_images)` pairs of
+        uint8 CPU tensors (pinned for full copy speed), one pair per batch, all of one batch size n;
+        the generator yields one dict of pinned host tensors per pair, in order.
+
+        Three CUDA streams overlap the upload of batch i+1, the kernels of batch i and the
+        download of batch i-1 (what the reference's DataLoader workers do with processes,
+        encoder_train.py:517-523).  Batches alternate between pool slots [0, n) and [n, 2n), so
+        both pools need at least 2n entries.  A yielded dict is valid until the generator is
+        advanced again (its buffers are the double-buffered download targets)."""
+        ctx = self.ctx
+        dev = ctx.device
+        with torch.cuda.device(dev):
+            s_in, s_k, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            main = torch.cuda.current_stream(dev)
+            for s in (s_in, s_k, s_out):
+                s.wait_stream(main)
+            slots = []
+            pending = []
+            i = 0
+            for card_images, bg_images in source:
+                n = card_images.shape[0]
+                assert bg_images.shape[0] == n
+                if not slots:
+                    if 2 * n > len(self.mtg.pool) or 2 * n > len(self.ilsvrc.images_u8):
+                        raise ValueError("host_tensor_batches needs pools of at least 2 * batch entries")
+                    for j in range(2):
+                        slots.append({
+                            "cards": torch.empty(card_images.shape, dtype=torch.uint8, device=dev),
+                            "bgs": torch.empty(bg_images.shape, dtype=torch.uint8, device=dev),
+                            "idx": torch.arange(j * n, (j + 1) * n, dtype=torch.int32, device=dev),
+                            "k_done": torch.cuda.Event(), "in_done": torch.cuda.Event(), "out_done": torch.cuda.Event(),
+                            "host": {}, "dev": None,
+                        })
+                sl = slots[i % 2]
+                # upload + pool ingest of this batch may start once the kernels that last read these slots are done
+                s_in.wait_event(sl["k_done"])
+                with torch.cuda.stream(s_in):
+                    sl["cards"].copy_(card_images, non_blocking=True)
+                    sl["bgs"].copy_(bg_images, non_blocking=True)
+                    ctx.update_card_images(sl["cards"], (i % 2) * n)
+                    ctx.update_bg_images(sl["bgs"], (i % 2) * n)
+                    sl["in_done"].record(s_in)
+                s_k.wait_event(sl["in_done"])
+                s_k.wait_event(sl["out_done"])  # the previous download from this slot's device batch is finished
+                with torch.cuda.stream(s_k):
+                    batch = self._generate(n, cards=sl["idx"], t_prob=None, n_prob=None, bgs=sl["idx"])
+                    sl["k_done"].record(s_k)
+                s_out.wait_event(sl["k_done"])
+                with torch.cuda.stream(s_out):
+                    out = {}
+                    for k, v in batch.items():
+                        v.record_stream(s_out)
+                        h = sl["host"].get(k)
+                        if h is None or h.shape != v.shape or h.dtype != v.dtype:
+                            h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                            sl["host"][k] = h
+                        h.copy_(v, non_blocking=True)
+                        out[k] = h
+                    sl["out_done"].record(s_out)
+                sl["dev"] = batch
+                pending.append((sl, out))
+                i += 1
+                if len(pending) == 2:
+                    done, res = pending.pop(0)
+                    done["out_done"].synchronize()
+                    yield res
+            for done, res in pending:
+                done["out_done"].synchronize()
+                yield res
+            main.wait_stream(s_out)
+
     # ------------------------------------------------------------------ internals
     def _next_first_index(self, n: int) -> int:
         """Disjoint global sample indices per (rank, batch): contiguous blocks of n."""

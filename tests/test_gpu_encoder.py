@@ -251,6 +251,15 @@ def test_dataset_dropin_surface():
         assert np.allclose(ib["y"][k], ib["x"][k], atol=2e-3)
     hb = ds.host_tensor_batch(torch.from_numpy(pool.images[:8]).pin_memory(), torch.from_numpy(np.stack(bgs[:8])).pin_memory())
     assert hb["x"].shape == (8, 3, 192, 128) and not hb["x"].is_cuda
+    # pipelined streaming form: three batches of 4 through the double-buffered pool slots
+    hc4 = torch.from_numpy(pool.images[:4]).pin_memory()
+    hb4 = torch.from_numpy(np.stack(bgs[:4])).pin_memory()
+    got = [{k: v.clone() for k, v in r.items()} for r in ds.host_tensor_batches((hc4, hb4) for _ in range(3))]
+    assert len(got) == 3
+    for r in got:
+        assert r["x"].shape == r["x2"].shape == (4, 3, 192, 128) and not r["x"].is_cuda
+        assert bool(torch.isfinite(r["x"].float()).all()) and float(r["x"].float().max()) > 0.1
+    assert not torch.equal(got[0]["x"], got[1]["x"])  # consecutive batches draw different augmentations
     # static helpers with numpy in/out
     y = SyntheticBgFgMtgImages.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128))
     assert PU.lsb_diff(y, EO.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128)))[0] == 0
