@@ -315,7 +315,7 @@ def run_cuda(args):
     if not args.no_e2e:
         hc = torch.from_numpy(cards.images[np.arange(PAIRS) % len(cards.images)]).pin_memory()
         hb = torch.from_numpy(np.stack([bgs[j % len(bgs)] for j in range(PAIRS)])).pin_memory()
-        e2e_steps = max(3, min(args.steps, 10))
+        e2e_steps = max(3, min(args.steps, 30))
 
         def feed(k):
             for _ in range(k):
@@ -452,7 +452,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--pool-cards", type=int, default=2048)
     ap.add_argument("--pool-bgs", type=int, default=1024)
-    ap.add_argument("--cpu-pairs-per-worker", type=int, default=48)
+    ap.add_argument("--cpu-pairs-per-worker", type=int, default=384)
     ap.add_argument("--ref-pairs-per-worker", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

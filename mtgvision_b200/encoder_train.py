@@ -175,13 +175,14 @@ class RanMtgEncDecDataset(IterableDataset):
             main = torch.cuda.current_stream(dev)
             for s in (s_in, s_k, s_out):
                 s.wait_stream(main)
-            slots = []
+            slots = getattr(self, "_pipe_slots", [])  # staging + pinned buffers persist across calls
             pending = []
             i = 0
             for card_images, bg_images in source:
                 n = card_images.shape[0]
                 assert bg_images.shape[0] == n
-                if not slots:
+                if not slots or slots[0]["cards"].shape != card_images.shape or slots[0]["bgs"].shape != bg_images.shape:
+                    slots = self._pipe_slots = []
                     if 2 * n > len(self.mtg.pool) or 2 * n > len(self.ilsvrc.images_u8):
                         raise ValueError("host_tensor_batches needs pools of at least 2 * batch entries")
                     for j in range(2):
