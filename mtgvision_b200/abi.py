@@ -131,7 +131,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("MTGV_LIB") or LIB_PATH  # MTGV_LIB: kernel-variant experiments (tests/build_variant.sh)
     if not os.path.isfile(p):
         raise MtgvError(
             f"libmtgv.so not found at {p}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

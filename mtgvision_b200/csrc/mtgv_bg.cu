@@ -28,7 +28,10 @@
 
 namespace mtgv {
 
-constexpr int kBgThreads = 256;
+#ifndef MTGV_BG_THREADS
+#define MTGV_BG_THREADS 256
+#endif
+constexpr int kBgThreads = MTGV_BG_THREADS;
 constexpr int kBgTR = 8, kBgTC = 32;   // output pixels per tile
 constexpr int kBgWCap = 3200;          // warp_inv pixels staged per tile
 constexpr int kBgRCap = 3072;          // rotate-canvas pixels staged per tile

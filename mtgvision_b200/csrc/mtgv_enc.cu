@@ -631,10 +631,84 @@ __host__ __device__ inline size_t fg_smem_bytes(int pitch) {
 
 // rgba_over_rgb (util/image.py:246-290): cur = clip(bg*(1-a) + fg*a); bg from k_background's output
 __device__ void stage_composite(float* cur, int HW, const float* __restrict__ bg, const float* __restrict__ alpha) {
-  for (int o = threadIdx.x; o < HW; o += blockDim.x) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if ((HW & 3) == 0) {
+    // 16-byte loads, four vectors (of each operand) in flight per thread before the first use
+    const float4* bg4 = reinterpret_cast<const float4*>(bg);
+    const float4* al4 = reinterpret_cast<const float4*>(alpha);
+    float4* cur4 = reinterpret_cast<float4*>(cur);
+    const int n4 = HW >> 2;
+    for (int j0 = tid; j0 < n4; j0 += 4 * nt) {
+      float4 b[4], a[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u * nt;
+        if (j < n4) {
+          b[u] = __ldcg(bg4 + j);
+          a[u] = alpha ? __ldcg(al4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u * nt;
+        if (j < n4) {
+          float4 c = cur4[j];
+          c.x = clip01(__fadd_rn(__fmul_rn(b[u].x, __fsub_rn(1.f, a[u].x)), __fmul_rn(c.x, a[u].x)));
+          c.y = clip01(__fadd_rn(__fmul_rn(b[u].y, __fsub_rn(1.f, a[u].y)), __fmul_rn(c.y, a[u].y)));
+          c.z = clip01(__fadd_rn(__fmul_rn(b[u].z, __fsub_rn(1.f, a[u].z)), __fmul_rn(c.z, a[u].z)));
+          c.w = clip01(__fadd_rn(__fmul_rn(b[u].w, __fsub_rn(1.f, a[u].w)), __fmul_rn(c.w, a[u].w)));
+          cur4[j] = c;
+        }
+      }
+    }
+    return;
+  }
+  for (int o = tid; o < HW; o += nt) {
     const float a = alpha ? __ldcg(alpha + o) : 0.f;
     const float bgv = __ldcg(bg + o);
     cur[o] = clip01(__fadd_rn(__fmul_rn(bgv, __fsub_rn(1.f, a)), __fmul_rn(cur[o], a)));
+  }
+}
+
+// foreground plane from k_foreground into shared memory, zero outside the pasted rectangle
+// (crop_to_size(pad=True), util/image.py:366-371)
+__device__ void stage_load_fg(float* P, int OH, int OW, const float* __restrict__ fg, bool none, int y0, int y1, int x0, int x1) {
+  const int tid = threadIdx.x, nt = blockDim.x, HW = OH * OW;
+  if ((OW & 3) == 0) {
+    const int W4 = OW >> 2, n4 = HW >> 2;
+    const unsigned magic = ((1u << 24) + (unsigned)W4 - 1u) / (unsigned)W4;  // j / W4 for j * W4 < 2^24
+    const float4* fg4 = reinterpret_cast<const float4*>(fg);
+    float4* P4 = reinterpret_cast<float4*>(P);
+    for (int j0 = tid; j0 < n4; j0 += 4 * nt) {
+      float4 v[4];
+      int yy[4], xx[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u * nt;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        yy[u] = (int)(((unsigned)j * magic) >> 24);
+        xx[u] = (j - yy[u] * W4) << 2;
+        if (j < n4 && !none && yy[u] >= y0 && yy[u] < y1 && xx[u] + 3 >= x0 && xx[u] < x1) v[u] = __ldcg(fg4 + j);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u * nt;
+        if (j < n4) {
+          const bool row = !none && yy[u] >= y0 && yy[u] < y1;
+          float4 c = v[u];
+          c.x = (row && xx[u] >= x0 && xx[u] < x1) ? c.x : 0.f;
+          c.y = (row && xx[u] + 1 >= x0 && xx[u] + 1 < x1) ? c.y : 0.f;
+          c.z = (row && xx[u] + 2 >= x0 && xx[u] + 2 < x1) ? c.z : 0.f;
+          c.w = (row && xx[u] + 3 >= x0 && xx[u] + 3 < x1) ? c.w : 0.f;
+          P4[j] = c;
+        }
+      }
+    }
+    return;
+  }
+  for (int i = tid; i < HW; i += nt) {
+    const int y = i / OW, x = i - y * OW;
+    P[i] = (!none && y >= y0 && y < y1 && x >= x0 && x < x1) ? __ldcg(fg + i) : 0.f;
   }
 }
 
@@ -780,15 +854,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
       continue;
     }
     const bool bg_only = sp.kind == MTGV_KIND_BG_ONLY;
-    {
-      // foreground plane from k_foreground; zero padding around the resized card (crop_to_size pad=True)
-      const float* fg = L.fg_scratch + ((size_t)s * 3 + plane) * HW;
-      const int y0 = sp.fg_y0, y1 = sp.fg_y0 + sp.fg_rh, x0 = sp.fg_x0, x1 = sp.fg_x0 + sp.fg_rw;
-      for (int i = tid; i < HW; i += nt) {
-        const int y = i / OW, x = i - y * OW;
-        S.P0[i] = (!bg_only && y >= y0 && y < y1 && x >= x0 && x < x1) ? __ldcg(fg + i) : 0.f;
-      }
-    }
+    stage_load_fg(S.P0, OH, OW, L.fg_scratch + ((size_t)s * 3 + plane) * HW, bg_only, sp.fg_y0, sp.fg_y0 + sp.fg_rh, sp.fg_x0,
+                  sp.fg_x0 + sp.fg_rw);
     __syncthreads();
     Vm vm{{S.P0, S.P1}, 0, OH, OW, plane, L.fields, sp.seed};
     if (sp.kind != MTGV_KIND_CROPPED) {
