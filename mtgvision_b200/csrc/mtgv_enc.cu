@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "mtgv_internal.cuh"
+#include "mtgv_persp.cuh"
 
 namespace mtgv {
 
@@ -77,6 +78,19 @@ __device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
   return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
+// four standard normals from one Philox call (two Box-Muller pairs)
+__device__ __forceinline__ void normals4(const uint32_t* r, float* g) {
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const float u1 = ((float)(r[2 * q] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.f * __logf(u1));
+    float sn, cs;
+    sincospif(2.f * u32_to_unit(r[2 * q + 1]), &sn, &cs);
+    g[2 * q] = rad * cs;
+    g[2 * q + 1] = rad * sn;
+  }
+}
+
 // ------------------------------------------------------------------------------------ //
 // plane interpreter                                                                     //
 // ------------------------------------------------------------------------------------ //
@@ -88,9 +102,21 @@ struct Vm {
   int chan;  // 0..2 colour, 3 alpha
   const uint32_t* fields;
   uint64_t seed;
+  double* aux;  // vm_aux_bytes(H, W) of scratch: per (row, column block) perspective origins
   __device__ float* cur_p() const { return P[cur]; }
   __device__ float* oth_p() const { return P[cur ^ 1]; }
 };
+
+__host__ __device__ inline size_t vm_aux_bytes(int H, int W) {
+  const int bw0 = persp_block_w(H, W);
+  return (size_t)H * ((W + bw0 - 1) / bw0) * 4 * sizeof(double);
+}
+
+// row-major walk of an h x w plane by the whole block without per-pixel divisions
+#define MTGV_FOR_PIXELS(i, x, y, h, w)                                                                       \
+  for (int i = threadIdx.x, x = threadIdx.x % (w), y = threadIdx.x / (w), dx__ = blockDim.x % (w),          \
+           dy__ = blockDim.x / (w);                                                                        \
+       i < (h) * (w); i += blockDim.x, x += dx__, y += dy__ + (x >= (w) ? 1 : 0), x -= (x >= (w) ? (w) : 0))
 
 // cv2.resize restated per destination pixel (oracle/cv2_restate.py resize_nearest/linear/cubic)
 __device__ __forceinline__ void cubic_coeffs(float x, float* c) {
@@ -178,24 +204,27 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
     }
     case MTGV_X_DOWNUP: {  // Mutate.downscale_upscale: two cv2.resize calls
       const int n = op.i[0], h2 = H >> n, w2 = W >> n;
-      for (int i = tid; i < h2 * w2; i += nt) oth[i] = resize_px(cur, H, W, h2, w2, op.i[1], i / w2, i % w2);
+      MTGV_FOR_PIXELS(i, x, y, h2, w2) oth[i] = resize_px(cur, H, W, h2, w2, op.i[1], y, x);
       __syncthreads();
-      for (int i = tid; i < HW; i += nt) cur[i] = resize_px(oth, h2, w2, H, W, op.i[2], i / W, i % W);
+      MTGV_FOR_PIXELS(i, x, y, H, W) cur[i] = resize_px(oth, h2, w2, H, W, op.i[2], y, x);
       break;
     }
     case MTGV_X_WARP_PERSP: {  // cv2.warpPerspective, same size
-      const int bw0 = persp_block_w(H, W);
-      for (int i = tid; i < HW; i += nt) {
-        int X, Y;
-        persp_coord(op.d, i % W, i / W, bw0, &X, &Y);
-        oth[i] = bilinear_plane(cur, H, W, X, Y);
+      const int bw0 = persp_block_w(H, W), nblk = (W + bw0 - 1) / bw0;
+      for (int k = tid; k < H * nblk; k += nt) persp_origin(op.d, (double)((k % nblk) * bw0), (double)(k / nblk), vm.aux + 4 * k);
+      __syncthreads();
+      const double m0 = op.d[0], m3 = op.d[3], m6 = op.d[6];
+      MTGV_FOR_PIXELS(i, x, y, H, W) {
+        const int bi = x / bw0;
+        const double* o = vm.aux + 4 * (y * nblk + bi);
+        const int2 XY = persp_xy(o[0], o[1], o[2], m0, m3, m6, (double)(x - bi * bw0));
+        oth[i] = bilinear_plane(cur, H, W, XY.x, XY.y);
       }
       vm.cur ^= 1;
       break;
     }
     case MTGV_X_WARP_AFFINE: {  // cv2.warpAffine, same size
-      for (int i = tid; i < HW; i += nt) {
-        int x = i % W, y = i / W;
+      MTGV_FOR_PIXELS(i, x, y, H, W) {
         int X = (affine_row_origin(op.d[1], op.d[2], y) + affine_col_delta(op.d[0], x)) >> 5;
         int Y = (affine_row_origin(op.d[4], op.d[5], y) + affine_col_delta(op.d[3], x)) >> 5;
         oth[i] = bilinear_plane(cur, H, W, X, Y);
@@ -204,8 +233,7 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
       break;
     }
     case MTGV_X_BLUR3: {  // cv2.GaussianBlur((3,3),0): [1/4,1/2,1/4] separable, REFLECT_101
-      for (int i = tid; i < HW; i += nt) {
-        int x = i % W, y = i / W;
+      MTGV_FOR_PIXELS(i, x, y, H, W) {
         int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
         float r[3];
 #pragma unroll
@@ -219,8 +247,7 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
       break;
     }
     case MTGV_X_SHARPEN: {  // filter2D [[0,-1,0],[-1,5,-1],[0,-1,0]] + clip (Mutate.sharpen)
-      for (int i = tid; i < HW; i += nt) {
-        int x = i % W, y = i / W;
+      MTGV_FOR_PIXELS(i, x, y, H, W) {
         float v = 5.f * cur[i] - cur[reflect101(y - 1, H) * W + x] - cur[y * W + reflect101(x - 1, W)] -
                   cur[y * W + reflect101(x + 1, W)] - cur[reflect101(y + 1, H) * W + x];
         oth[i] = clip01(v);
@@ -258,37 +285,44 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
         break;
       }
       const float* fld = inj ? (const float*)(vm.fields + op.field) : nullptr;
-      for (int i = tid; i < HW; i += nt) {
-        float x = cur[i], noisy;
-        float g = 0.f;
-        if (inj) {
-          g = fld[(size_t)i * 3 + c];
-        } else {
-          uint32_t r[4];
-          field_draw(vm.seed, slot, (uint32_t)i, (uint32_t)c, 0, r);
-          if (kind == 3) {  // Poisson(lam = clip(x)*0.8) by inversion
-            float lam = clip01(x) * 0.8f, p = expf(-lam), F = p, u = u32_to_unit(r[0]);
+      // device-generated fields: one Philox call per group of four consecutive pixels
+      for (int i0 = 4 * tid; i0 < HW; i0 += 4 * nt) {
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t r[4] = {0u, 0u, 0u, 0u};
+        if (!inj) {
+          field_draw(vm.seed, slot, (uint32_t)(i0 >> 2), (uint32_t)c, 0, r);
+          if (kind != 3) normals4(r, g4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          if (i >= HW) break;
+          float x = cur[i], noisy;
+          float g;
+          if (inj) {
+            g = fld[(size_t)i * 3 + c];
+          } else if (kind == 3) {  // Poisson(lam = clip(x)*0.8) by inversion
+            float lam = clip01(x) * 0.8f, p = __expf(-lam), F = p, uu = u32_to_unit(r[u]);
             int k = 0;
-            while (u > F && k < 32) {
+            while (uu > F && k < 32) {
               k++;
               p *= lam / (float)k;
               F += p;
             }
             g = (float)k;
           } else {
-            g = normal_from(r[0], r[1]);
-            if (kind == 1) g *= 0.22360679774997896f;  // sqrt(var=0.05)
+            g = kind == 1 ? g4[u] * 0.22360679774997896f : g4[u];  // sqrt(var=0.05)
           }
+          if (kind == 0)  // noise_speckle(strength 0.3): x * (1 + g*0.3)
+            noisy = clip01(__fmul_rn(x, __fadd_rn(1.f, __fmul_rn(g, 0.3f))));
+          else if (kind == 1)  // noise_gaussian(var 0.05)
+            noisy = clip01(__fadd_rn(x, g));
+          else {  // noise_poisson(peak .8, amount .5): clip(.5*clip(x) + .5*(counts/.8))
+            float xs = clip01(x);
+            noisy = clip01(__fadd_rn(__fmul_rn(0.5f, xs), __fmul_rn(0.5f, (float)((double)g / 0.8))));
+          }
+          cur[i] = __fadd_rn(__fmul_rn(ra, noisy), __fmul_rn(rb, x));
         }
-        if (kind == 0)  // noise_speckle(strength 0.3): x * (1 + g*0.3)
-          noisy = clip01(__fmul_rn(x, __fadd_rn(1.f, __fmul_rn(g, 0.3f))));
-        else if (kind == 1)  // noise_gaussian(var 0.05)
-          noisy = clip01(__fadd_rn(x, g));
-        else {  // noise_poisson(peak .8, amount .5): clip(.5*clip(x) + .5*(counts/.8))
-          float xs = clip01(x);
-          noisy = clip01(__fadd_rn(__fmul_rn(0.5f, xs), __fmul_rn(0.5f, (float)((double)g / 0.8))));
-        }
-        cur[i] = __fadd_rn(__fmul_rn(ra, noisy), __fmul_rn(rb, x));
       }
       break;
     }
@@ -297,16 +331,20 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
       const float* fld = inj ? (const float*)(vm.fields + op.field) : nullptr;
       const int nc = 3;
       if (c > 2) break;
-      for (int i = tid; i < HW; i += nt) {
-        float g;
-        if (inj) {
-          g = fld[(size_t)i * nc + c];
-        } else {
+      for (int i0 = 4 * tid; i0 < HW; i0 += 4 * nt) {
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!inj) {
           uint32_t r[4];
-          field_draw(vm.seed, slot, (uint32_t)i, (uint32_t)c, 0, r);
-          g = normal_from(r[0], r[1]) * 0.25f;
+          field_draw(vm.seed, slot, (uint32_t)(i0 >> 2), (uint32_t)c, 0, r);
+          normals4(r, g4);
         }
-        cur[i] = clip01(__fadd_rn(cur[i], g));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          if (i >= HW) break;
+          const float g = inj ? fld[(size_t)i * nc + c] : g4[u] * 0.25f;
+          cur[i] = clip01(__fadd_rn(cur[i], g));
+        }
       }
       break;
     }
@@ -379,27 +417,6 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
       break;
   }
   __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------ //
-// INTER_AREA tables in shared memory                                                    //
-// ------------------------------------------------------------------------------------ //
-
-struct AreaTabs {
-  int* xs; int* xn; float* xw;  // per destination column: first source index, tap count, weights[8]
-  int* ys; int* yn; float* yw;
-};
-
-// tables for destination indices [d0, d0+count) of a ssize -> dsize INTER_AREA resize
-__device__ void build_area_axis(int* s, int* n, float* w, int ssize, int dsize, int d0, int count) {
-  for (int k = threadIdx.x; k < count; k += blockDim.x) {
-    int st;
-    float ww[kAreaMaxTaps];
-    int nn = area_taps(ssize, dsize, d0 + k, &st, ww);
-    s[k] = st;
-    n[k] = nn;
-    for (int j = 0; j < kAreaMaxTaps; j++) w[k * kAreaMaxTaps + j] = j < nn ? ww[j] : 0.f;
-  }
 }
 
 // ------------------------------------------------------------------------------------ //
@@ -769,13 +786,14 @@ __device__ __forceinline__ bool op_touches_alpha(const mtgv_x_op& op) {
 }
 
 struct SmemLayout {
-  float* P0; float* P1; float* lut; AreaTabs tabs; mtgv_enc_params* sp; int* item;
+  float* P0; float* P1; double* aux; mtgv_enc_params* sp; int* item;
 };
 
 __host__ __device__ inline size_t enc_smem_bytes(int OH, int OW) {
   size_t HW = (size_t)OH * OW;
-  size_t b = 2 * HW * 4 + 256 * 4;
-  b += (size_t)OW * (8 + 4 * kAreaMaxTaps) + (size_t)OH * (8 + 4 * kAreaMaxTaps);
+  size_t b = 2 * HW * 4;
+  b = (b + 15) & ~(size_t)15;
+  b += vm_aux_bytes(OH, OW);
   b = (b + 15) & ~(size_t)15;
   b += sizeof(mtgv_enc_params);
   b = (b + 15) & ~(size_t)15;
@@ -786,17 +804,11 @@ __host__ __device__ inline size_t enc_smem_bytes(int OH, int OW) {
 __device__ inline SmemLayout carve(unsigned char* raw, int OH, int OW) {
   SmemLayout s;
   size_t HW = (size_t)OH * OW;
-  float* f = (float*)raw;
-  s.P0 = f; f += HW;
-  s.P1 = f; f += HW;
-  s.lut = f; f += 256;
-  s.tabs.xs = (int*)f; f += OW;
-  s.tabs.xn = (int*)f; f += OW;
-  s.tabs.xw = f; f += (size_t)OW * kAreaMaxTaps;
-  s.tabs.ys = (int*)f; f += OH;
-  s.tabs.yn = (int*)f; f += OH;
-  s.tabs.yw = f; f += (size_t)OH * kAreaMaxTaps;
-  size_t off = ((unsigned char*)f - raw + 15) & ~(size_t)15;
+  s.P0 = (float*)raw;
+  s.P1 = s.P0 + HW;
+  size_t off = (2 * HW * 4 + 15) & ~(size_t)15;
+  s.aux = (double*)(raw + off);
+  off = (off + vm_aux_bytes(OH, OW) + 15) & ~(size_t)15;
   s.sp = (mtgv_enc_params*)(raw + off);
   off = (off + sizeof(mtgv_enc_params) + 15) & ~(size_t)15;
   s.item = (int*)(raw + off + 32);
@@ -832,7 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
       if (!bad && sp.kind == MTGV_KIND_VIRTUAL && !alpha_static) {
         for (int i = tid; i < HW; i += nt) S.P0[i] = L.alpha0[i];
         __syncthreads();
-        Vm vm{{S.P0, S.P1}, 0, OH, OW, 3, L.fields, sp.seed};
+        Vm vm{{S.P0, S.P1}, 0, OH, OW, 3, L.fields, sp.seed, S.aux};
         for (int k = 0; k < sp.n_fg; k++) vm_run_op(vm, sp.ops[k], k);
         float* dst = L.alpha_scratch + (size_t)s * HW;
         const float* srcp = vm.cur_p();
@@ -857,7 +869,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
     stage_load_fg(S.P0, OH, OW, L.fg_scratch + ((size_t)s * 3 + plane) * HW, bg_only, sp.fg_y0, sp.fg_y0 + sp.fg_rh, sp.fg_x0,
                   sp.fg_x0 + sp.fg_rw);
     __syncthreads();
-    Vm vm{{S.P0, S.P1}, 0, OH, OW, plane, L.fields, sp.seed};
+    Vm vm{{S.P0, S.P1}, 0, OH, OW, plane, L.fields, sp.seed, S.aux};
     if (sp.kind != MTGV_KIND_CROPPED) {
       for (int k = 0; k < sp.n_fg; k++) vm_run_op(vm, sp.ops[k], k);
       const float* alpha = bg_only ? nullptr : L.alpha0;
@@ -1341,11 +1353,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_run_plane_ops(float* img, int h
   const int HW = h * w;
   float* P0 = (float*)smem_raw;
   float* P1 = P0 + HW;
-  mtgv_x_op* sop = (mtgv_x_op*)(P1 + HW);
+  double* aux = (double*)(smem_raw + (((size_t)2 * HW * 4 + 15) & ~(size_t)15));
+  mtgv_x_op* sop = (mtgv_x_op*)((unsigned char*)aux + ((vm_aux_bytes(h, w) + 15) & ~(size_t)15));
   const int im = blockIdx.x / c, ch = blockIdx.x % c;
   float* base = img + (size_t)im * HW * c;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) P0[i] = base[(size_t)i * c + ch];
-  Vm vm{{P0, P1}, 0, h, w, ch, fields, seed + (uint64_t)im};
+  Vm vm{{P0, P1}, 0, h, w, ch, fields, seed + (uint64_t)im, aux};
   __syncthreads();
   for (int k = 0; k < n_ops; k++) {
     for (int q = threadIdx.x; q < (int)(sizeof(mtgv_x_op) / 4); q += blockDim.x) ((uint32_t*)sop)[q] = ((const uint32_t*)(ops + k))[q];
@@ -1359,7 +1372,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_run_plane_ops(float* img, int h
 int enc_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops,
                       const void* fields, uint64_t seed, cudaStream_t st) {
   if (n <= 0) return MTGV_OK;
-  size_t smem = (size_t)2 * h * w * 4 + sizeof(mtgv_x_op) + 16;
+  size_t smem = (((size_t)2 * h * w * 4 + 15) & ~(size_t)15) + ((vm_aux_bytes(h, w) + 15) & ~(size_t)15) + sizeof(mtgv_x_op) + 16;
   if ((int)smem > ctx->max_smem_optin) return fail(ctx, MTGV_ERR_LIMIT, "image too large for the plane interpreter");
   if (c < 1 || c > 4) return fail(ctx, MTGV_ERR_INVALID, "channels must be 1..4");
   static bool attr_set = false;
