@@ -419,10 +419,6 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
   __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------ //
-// stage F0: card -> area-resized plane (crop_to_size(pad=True) / remove_border_resized)  //
-// ------------------------------------------------------------------------------------ //
-
 struct EncLaunch {
   const mtgv_enc_params* params;
   int n;
@@ -435,216 +431,6 @@ struct EncLaunch {
   int out_dtype;
   const uint32_t* fields;
 };
-
-// k_foreground: INTER_AREA resize of one card plane (crop_to_size(pad=True) of make_virtual,
-// util/image.py:349-377, or remove_border_resized of make_cropped, :337-346) as a streaming
-// pass: every source row is read once with 16-byte loads, converted uint8 -> float32/255
-// through a LUT into a per-warp row buffer, reduced horizontally by the lanes (4 destination
-// columns each) and accumulated vertically in registers - cv2's ResizeArea_ order
-// (horizontal sums in tap order, then beta-weighted rows in source-row order).
-// One warp owns one (sample, plane, destination-row range) item; no block-level barriers.
-constexpr int kFgThreads = 256;
-constexpr int kFgWarps = kFgThreads / 32;
-constexpr int kFgRows = 32;   // max destination rows per item
-constexpr int kFgMaxQ = 8;    // destination columns per lane (out_w <= 256)
-
-__device__ __forceinline__ int fg_pos(int x) { return x + ((x >> 5) << 2); }  // skew: conflict-free 16-byte row stores
-
-// float32(b / 255.0) exactly as np.divide(u8, 255.0, dtype=float32) (util/image.py:233): one Newton
-// correction of b * fl(1/255) is correctly rounded for all 256 inputs (tests/test_host_expand.py).
-__device__ __forceinline__ float u8_over_255(uint32_t b) {
-  const float f = __uint_as_float(0x4B000000u | b) - 8388608.f;  // exact integer -> float
-  const float r = 0.003921568859368563f;                           // fl(1/255)
-  const float q = __fmul_rn(f, r);
-  const float e = __fmaf_rn(-255.f, q, f);
-  return __fmaf_rn(e, r, q);
-}
-
-struct FgGeom {  // the two INTER_AREA geometries of a batch: [0] virtual (whole card, padded), [1] cropped
-  int src_h, src_w, rh, rw;
-};
-
-// REGW: horizontal tap weights held in registers (TAPS <= 5 taps, NQ <= 4 columns per lane: scales < 4,
-// out_w <= 128); otherwise they are read from the shared tables.
-template <bool REGW, int TAPS, int NQ>
-__device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, int c, int part, int split, int gi,
-                                        const int* __restrict__ gxs, const int* __restrict__ gxn,
-                                        const float* __restrict__ gxw, int* ys, int* yn, float* yw, float* rowbuf,
-                                        const uint8_t* __restrict__ card_planes, int pitch, float* __restrict__ fg_out,
-                                        int s, int lane) {
-  const int kind = sp->kind;
-  const int src_h = sp->src_h, rh = sp->fg_rh, rw = sp->fg_rw;
-  const int OH = sp->out_h, OW = sp->out_w, card_h = sp->card_h, card_w = sp->card_w;
-  const int src_y0 = sp->src_y0, src_x0 = sp->src_x0, fy0 = sp->fg_y0, fx0 = sp->fg_x0;
-  const bool flip_src = sp->upsidedown && kind == MTGV_KIND_VIRTUAL;  // rot180 of the card before masking
-  const bool flip_dst = sp->upsidedown && kind == MTGV_KIND_CROPPED;  // rot180 of the resized crop
-  const int rows_per = (rh + split - 1) / split;
-  const int r0 = part * rows_per, r1 = min(rh, r0 + rows_per);
-  if (r0 >= r1) return;
-  __syncwarp();
-  if (lane < r1 - r0) {
-    int st;
-    float ww[kAreaMaxTaps];
-    int nn = area_taps(src_h, rh, r0 + lane, &st, ww);
-    ys[lane] = st;
-    yn[lane] = nn;
-    for (int k = 0; k < kAreaMaxTaps; k++) yw[lane * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
-  }
-  __syncwarp();
-  // this lane's destination columns: first source column, tap count and weights in registers
-  int x0r[REGW ? NQ : 1], nxr[REGW ? NQ : 1];
-  float wxr[REGW ? NQ : 1][REGW ? TAPS : 1];
-  if (REGW) {
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      const int d = lane + 32 * q;
-      const bool on = d < rw;
-      x0r[q] = src_x0 + (on ? gxs[d] : 0);
-      nxr[q] = on ? gxn[d] : 0;
-#pragma unroll
-      for (int k = 0; k < TAPS; k++) wxr[q][k] = on ? gxw[d * kAreaMaxTaps + k] : 0.f;
-    }
-  }
-  const uint8_t* plane = card_planes + ((size_t)sp->card * 3 + c) * card_h * pitch;
-  float* outp = fg_out + ((size_t)s * 3 + c) * OH * OW;
-  const int sy_first = ys[0], sy_last = ys[r1 - r0 - 1] + yn[r1 - r0 - 1] - 1;
-  auto row_ptr = [&](int sy) {
-    int row = src_y0 + sy;
-    if (flip_src) row = card_h - 1 - row;
-    return plane + (size_t)row * pitch;
-  };
-  const bool has16 = lane * 16 < pitch;  // fast path: pitch <= 512, one 16-byte load per lane and row
-  uint4 nxt = make_uint4(0, 0, 0, 0);
-  if (has16) nxt = __ldg((const uint4*)(row_ptr(sy_first) + lane * 16));
-  int prev_sy = -1;
-  float h[NQ];
-  for (int r = r0; r < r1; r++) {
-    const int y0 = ys[r - r0], ny = yn[r - r0];
-    const float* wy = yw + (r - r0) * kAreaMaxTaps;
-    float acc[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; q++) acc[q] = 0.f;
-    for (int j = 0; j < ny; j++) {
-      const int sy = y0 + j;
-      if (sy != prev_sy) {
-        prev_sy = sy;
-        const uint4 v = nxt;
-        if (has16 && sy < sy_last) nxt = __ldg((const uint4*)(row_ptr(sy + 1) + lane * 16));  // prefetch next source row
-        __syncwarp();
-        if (pitch <= 512) {
-          if (has16) {
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            if (!flip_src) {
-#pragma unroll
-              for (int t = 0; t < 4; t++) {
-                float4 f;
-                f.x = u8_over_255(w4[t] & 255); f.y = u8_over_255((w4[t] >> 8) & 255);
-                f.z = u8_over_255((w4[t] >> 16) & 255); f.w = u8_over_255(w4[t] >> 24);
-                *(float4*)(rowbuf + fg_pos(lane * 16 + 4 * t)) = f;
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 16; t++) {
-                const int x = card_w - 1 - (lane * 16 + t);
-                if (x >= 0) rowbuf[fg_pos(x)] = u8_over_255((w4[t >> 2] >> (8 * (t & 3))) & 255);
-              }
-            }
-          }
-        } else {  // wide cards: plain strided loop
-          const uint8_t* rp = row_ptr(sy);
-          for (int x = lane; x < card_w; x += 32) rowbuf[fg_pos(flip_src ? card_w - 1 - x : x)] = u8_over_255(__ldg(rp + x));
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-          float hs = 0.f;
-          if (REGW) {
-#pragma unroll
-            for (int k = 0; k < TAPS; k++)
-              if (k < nxr[q]) hs = __fadd_rn(hs, __fmul_rn(rowbuf[fg_pos(x0r[q] + k)], wxr[q][k]));
-          } else {
-            const int d = lane + 32 * q;
-            if (d < rw) {
-              const int x0 = src_x0 + gxs[d], nx = gxn[d];
-              const float* wx = gxw + d * kAreaMaxTaps;
-              for (int k = 0; k < nx; k++) hs = __fadd_rn(hs, __fmul_rn(rowbuf[fg_pos(x0 + k)], wx[k]));
-            }
-          }
-          h[q] = hs;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < NQ; q++) acc[q] = j == 0 ? __fmul_rn(wy[0], h[q]) : __fadd_rn(acc[q], __fmul_rn(wy[j], h[q]));
-    }
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      const int d = lane + 32 * q;
-      if (d < rw) {
-        const int y = fy0 + r, x = fx0 + d;
-        const int o = flip_dst ? (OH - 1 - y) * OW + (OW - 1 - x) : y * OW + x;
-        outp[o] = clip01(acc[q]);  // img_clip after cv2.resize (util/image.py:334)
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kFgThreads, 3) k_foreground(const mtgv_enc_params* __restrict__ params, int n, int split,
-                                                           FgGeom g0, FgGeom g1, const uint8_t* __restrict__ card_planes,
-                                                           int pitch, float* __restrict__ fg_out) {
-  extern __shared__ __align__(16) unsigned char fg_smem_raw[];
-  // layout: per geometry: xs[256] xn[256] xw[256*8] | per warp: ys[32] yn[32] yw[32*8] | per warp: rowbuf
-  int* xs = (int*)fg_smem_raw;
-  int* xn = xs + 2 * 256;
-  float* xw = (float*)(xn + 2 * 256);
-  int* ytab = (int*)(xw + 2 * 256 * kAreaMaxTaps);
-  const int rowbuf_len = (pitch + (pitch >> 3) + 8 + 3) & ~3;  // keeps every warp's buffer 16-byte aligned
-  float* rowbufs = (float*)(ytab + kFgWarps * kFgRows * (2 + kAreaMaxTaps));
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int s_maxtaps[2];
-  if (tid < 2) s_maxtaps[tid] = 0;
-  __syncthreads();
-  for (int q = tid; q < 2 * 256; q += blockDim.x) {
-    const FgGeom& g = q < 256 ? g0 : g1;
-    const int d = q & 255;
-    int st = 0, nn = 0;
-    float ww[kAreaMaxTaps];
-    if (d < g.rw && g.rw > 0) nn = area_taps(g.src_w, g.rw, d, &st, ww);
-    xs[q] = st;
-    xn[q] = nn;
-    for (int k = 0; k < kAreaMaxTaps; k++) xw[q * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
-    if (nn > 5) atomicMax(&s_maxtaps[q >> 8], nn);
-  }
-  __syncthreads();
-  int* ys = ytab + warp * kFgRows * (2 + kAreaMaxTaps);
-  int* yn = ys + kFgRows;
-  float* yw = (float*)(yn + kFgRows);
-  float* rowbuf = rowbufs + (size_t)warp * rowbuf_len;
-  const int n_items = n * 3 * split;
-  for (int item = blockIdx.x * kFgWarps + warp; item < n_items; item += gridDim.x * kFgWarps) {
-    const int s = item / (3 * split), rem = item - s * 3 * split, c = rem / split, part = rem - c * split;
-    const mtgv_enc_params* sp = params + s;
-    const int kind = sp->kind;
-    if (sp->status != 0 || kind == MTGV_KIND_BG_ONLY) continue;
-    const int gi = kind == MTGV_KIND_CROPPED ? 1 : 0;
-    const FgGeom& g = gi ? g1 : g0;
-    if (sp->src_h != g.src_h || sp->src_w != g.src_w || sp->fg_rh != g.rh || sp->fg_rw != g.rw) continue;  // host invariant
-    const int* gxs = xs + gi * 256;
-    const int* gxn = xn + gi * 256;
-    const float* gxw = xw + gi * 256 * kAreaMaxTaps;
-    const bool small = s_maxtaps[gi] == 0 && g.rw <= 128;
-    if (small)
-      fg_item<true, 5, 4>(sp, c, part, split, gi, gxs, gxn, gxw, ys, yn, yw, rowbuf, card_planes, pitch, fg_out, s, lane);
-    else
-      fg_item<false, kAreaMaxTaps, kFgMaxQ>(sp, c, part, split, gi, gxs, gxn, gxw, ys, yn, yw, rowbuf, card_planes, pitch, fg_out, s, lane);
-  }
-}
-
-__host__ __device__ inline size_t fg_smem_bytes(int pitch) {
-  size_t b = 2 * 256 * (8 + 4 * kAreaMaxTaps);
-  b += (size_t)kFgWarps * kFgRows * (8 + 4 * kAreaMaxTaps);
-  b += (size_t)kFgWarps * ((pitch + (pitch >> 3) + 8 + 3) & ~3) * 4;
-  return (b + 15) & ~(size_t)15;
-}
 
 // rgba_over_rgb (util/image.py:246-290): cur = clip(bg*(1-a) + fg*a); bg from k_background's output
 __device__ void stage_composite(float* cur, int HW, const float* __restrict__ bg, const float* __restrict__ alpha) {
@@ -1235,22 +1021,9 @@ static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, 
     ctx->bg_cap = (size_t)chunk * 6 * HW;
   }
   float* fg_scratch = ctx->bg_scratch + (size_t)chunk * 3 * HW;
-  // the two INTER_AREA geometries a batch can contain (make_virtual / make_cropped)
-  FgGeom g0{0, 0, 0, 0}, g1{0, 0, 0, 0};
-  {
-    g0.src_h = ctx->card_h; g0.src_w = ctx->card_w;
-    if (ctx->card_h == OH && ctx->card_w == OW) { g0.rh = OH; g0.rw = OW; }
-    else { int y0, x0; crop_geometry(ctx->card_h, ctx->card_w, OH, OW, true, &g0.rh, &g0.rw, &y0, &x0); }
-    int border = (int)ceil(fmax(0.02 * ctx->card_h, 0.02 * ctx->card_w));
-    g1.src_h = ctx->card_h - 2 * border; g1.src_w = ctx->card_w - 2 * border; g1.rh = OH; g1.rw = OW;
-  }
-  if (OW > 256 || ctx->card_pitch > 4096) return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw width > 256 or card width > 4096");
-  const int fg_split = (OH + kFgRows - 1) / kFgRows > 8 ? (OH + kFgRows - 1) / kFgRows : 8;
-  const size_t fg_smem = fg_smem_bytes(ctx->card_pitch);
   static bool attr_set = false;
   if (!attr_set) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_foreground, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const size_t elem = out_dtype == MTGV_OUT_F16 ? 2 : (out_dtype == MTGV_OUT_U8 ? 1 : 4);
@@ -1262,14 +1035,8 @@ static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, 
       if (rc2) return rc2;
     }
     {
-      int fg_blocks = 0;
-      MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fg_blocks, k_foreground, kFgThreads, fg_smem));
-      int grid_fg = ctx->sm_count * (fg_blocks > 0 ? fg_blocks : 1);
-      const int items = m * 3 * fg_split;
-      if (grid_fg > (items + kFgWarps - 1) / kFgWarps) grid_fg = (items + kFgWarps - 1) / kFgWarps;
-      k_foreground<<<grid_fg, kFgThreads, fg_smem, st>>>(params + base, m, fg_split, g0, g1, ctx->card_planes, ctx->card_pitch,
-                                                         fg_scratch);
-      ctx->launches++;
+      int rc3 = fg_launch(ctx, params + base, m, OH, OW, fg_scratch, st);
+      if (rc3) return rc3;
     }
     EncLaunch L;
     L.params = params + base; L.n = m; L.fg_scratch = fg_scratch;

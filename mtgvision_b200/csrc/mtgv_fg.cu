@@ -1,0 +1,286 @@
+// mtgv_fg.cu - k_foreground: INTER_AREA resize of one card plane for sm_100a.
+//
+// crop_to_size(pad=True) of make_virtual (mtgvision/util/image.py:349-377 -> resize :321-334) and
+// remove_border_resized of make_cropped (:337-346) are cv2.resize(INTER_AREA) down-scales of the
+// 680x488 card to (178,128) / (192,128).  This is the path's HBM-bound kernel: every source byte
+// is read exactly once with 16-byte loads.
+//
+// The separable area filter is evaluated vertical-first.  A destination row's taps are
+// [partial row?] full rows* [partial row?] (computeResizeAreaTab); full rows
+// all weigh 1/cell, so they are summed as packed 16-bit integers (two byte columns per 32-bit add,
+// exact), and only the partial rows are converted to float32.  The weighted column sums of one
+// destination row go through a per-warp row buffer and the lanes reduce them horizontally with the
+// column taps held in registers.  cv2 filters horizontally first; the real-arithmetic result is the
+// same and the float32 roundings differ by ~1e-7, inside the +-1 uint8 LSB bar (the u8 -> [0,1]
+// scaling 1/255 is folded into the row weights for the same reason).  Coordinates (tap windows,
+// partial-tap thresholds) follow cv2's double arithmetic exactly (mtgv_geom.cuh: area_compact).
+//
+// One warp owns one (sample, plane, destination-row range) item; there are no block-level barriers
+// after the column tables are built.
+#include "mtgv_internal.cuh"
+
+namespace mtgv {
+
+constexpr int kFgThreads = 256;
+constexpr int kFgWarps = kFgThreads / 32;
+constexpr int kFgRows = 32;  // max destination rows per item
+constexpr int kFgMaxOW = 256;
+
+struct FgGeom {  // the two INTER_AREA geometries of a batch: [0] virtual (whole card, padded), [1] cropped
+  int src_h, src_w, rh, rw;
+};
+
+struct FgRow {  // vertical taps of one destination row: start row, n | left << 8 | right << 9, weights / 255
+  int start, n;
+  float wl, wm, wr;
+};
+
+__device__ __forceinline__ int fg_pos(int x) { return x + ((x >> 5) << 2); }  // skew: conflict-free 16-byte row stores
+__device__ __forceinline__ float fg_clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+__device__ __forceinline__ float fg_byte(uint32_t w, int k) {  // exact u8 -> float
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + k)) - 8388608.f;
+}
+
+// NCH: 16-byte chunks per lane and row (pitch <= 512 * NCH).  REGW: horizontal tap weights held in
+// registers (<= 5 taps, <= 4 destination columns per lane: scales < 4, out_w <= 128); otherwise they are
+// read from the shared tables.
+template <int NCH, bool REGW>
+__device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, int c, int part, int split,
+                                        const int* __restrict__ gxs, const int* __restrict__ gxn, const float* __restrict__ gxw,
+                                        FgRow* rows, float* rowbuf, const uint8_t* __restrict__ card_planes, int pitch,
+                                        float* __restrict__ fg_out, int s, int lane) {
+  const int kind = sp->kind;
+  const int src_h = sp->src_h, rh = sp->fg_rh, rw = sp->fg_rw;
+  const int OH = sp->out_h, OW = sp->out_w, card_h = sp->card_h, card_w = sp->card_w;
+  const int src_y0 = sp->src_y0, src_x0 = sp->src_x0, fy0 = sp->fg_y0, fx0 = sp->fg_x0;
+  const bool flip_src = sp->upsidedown && kind == MTGV_KIND_VIRTUAL;  // rot180 of the card before masking
+  const bool flip_dst = sp->upsidedown && kind == MTGV_KIND_CROPPED;  // rot180 of the resized crop
+  const int rows_per = (rh + split - 1) / split;
+  const int r0 = part * rows_per, r1 = min(rh, r0 + rows_per);
+  if (r0 >= r1) return;
+  __syncwarp();
+  if (lane < r1 - r0) {
+    FgRow e;
+    area_compact(src_h, rh, r0 + lane, &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+    const float k255 = 1.f / 255.f;
+    e.wl *= k255; e.wm *= k255; e.wr *= k255;
+    rows[lane] = e;
+  }
+  __syncwarp();
+  // this lane's destination columns: first source column, tap count and weights in registers
+  constexpr int TAPS = 5, NQ = REGW ? 4 : kFgMaxOW / 32;
+  int x0r[REGW ? NQ : 1], nxr[REGW ? NQ : 1];
+  float wxr[REGW ? NQ : 1][REGW ? TAPS : 1];
+  if (REGW) {
+#pragma unroll
+    for (int q = 0; q < (REGW ? NQ : 1); q++) {
+      const int d = lane + 32 * q;
+      const bool on = d < rw;
+      x0r[q] = src_x0 + (on ? gxs[d] : 0);
+      nxr[q] = on ? gxn[d] : 0;
+#pragma unroll
+      for (int k = 0; k < TAPS; k++) wxr[q][k] = on ? gxw[d * kAreaMaxTaps + k] : 0.f;
+    }
+  }
+  const uint8_t* plane = card_planes + ((size_t)sp->card * 3 + c) * card_h * pitch;
+  float* outp = fg_out + ((size_t)s * 3 + c) * OH * OW;
+  const int sy_last = rows[r1 - r0 - 1].start + (rows[r1 - r0 - 1].n & 255) - 1;
+  auto load_row = [&](int sy, uint4* v) {
+    int row = src_y0 + sy;
+    if (flip_src) row = card_h - 1 - row;
+    const uint8_t* p = plane + (size_t)row * pitch;
+#pragma unroll
+    for (int h = 0; h < NCH; h++) {
+      const int off = (lane + 32 * h) * 16;
+      v[h] = off < pitch ? __ldg((const uint4*)(p + off)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  uint4 cur[NCH], nxt[NCH];
+  int cur_sy = -1;
+  load_row(rows[0].start, nxt);
+  int nxt_sy = rows[0].start;
+  for (int r = r0; r < r1; r++) {
+    const FgRow e = rows[r - r0];
+    const int ny = e.n & 255;
+    float fa[NCH][16];
+    uint32_t ia[NCH][8];
+#pragma unroll
+    for (int h = 0; h < NCH; h++) {
+#pragma unroll
+      for (int t = 0; t < 16; t++) fa[h][t] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; t++) ia[h][t] = 0u;
+    }
+    bool any_mid = false;
+    for (int j = 0; j < ny; j++) {
+      const int sy = e.start + j;
+      if (sy != cur_sy) {  // rows shared by two destination rows (a partial tap of each) stay in registers
+        if (sy != nxt_sy) { load_row(sy, nxt); nxt_sy = sy; }  // not the prefetched row (never for contiguous taps)
+#pragma unroll
+        for (int h = 0; h < NCH; h++) cur[h] = nxt[h];
+        cur_sy = nxt_sy;
+        if (sy < sy_last) { load_row(sy + 1, nxt); nxt_sy = sy + 1; }  // prefetch the next source row
+      }
+      const bool left = j == 0 && (e.n & 256), right = j == ny - 1 && (e.n & 512);
+      if (left || right) {
+        const float w = left ? e.wl : e.wr;
+#pragma unroll
+        for (int h = 0; h < NCH; h++) {
+          const uint32_t w4[4] = {cur[h].x, cur[h].y, cur[h].z, cur[h].w};
+#pragma unroll
+          for (int t = 0; t < 16; t++) fa[h][t] = __fmaf_rn(fg_byte(w4[t >> 2], t & 3), w, fa[h][t]);
+        }
+      } else {
+        any_mid = true;
+#pragma unroll
+        for (int h = 0; h < NCH; h++) {
+          const uint32_t w4[4] = {cur[h].x, cur[h].y, cur[h].z, cur[h].w};
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            ia[h][2 * t] += __byte_perm(w4[t], 0u, 0x4140);      // bytes 0,1 as two 16-bit lanes
+            ia[h][2 * t + 1] += __byte_perm(w4[t], 0u, 0x4342);  // bytes 2,3
+          }
+        }
+      }
+    }
+    if (any_mid) {
+#pragma unroll
+      for (int h = 0; h < NCH; h++)
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          fa[h][2 * t] = __fmaf_rn((float)(ia[h][t] & 0xFFFFu), e.wm, fa[h][2 * t]);
+          fa[h][2 * t + 1] = __fmaf_rn((float)(ia[h][t] >> 16), e.wm, fa[h][2 * t + 1]);
+        }
+    }
+    __syncwarp();  // the previous row's horizontal readers are done
+#pragma unroll
+    for (int h = 0; h < NCH; h++) {
+      const int xb = (lane + 32 * h) * 16;
+      if (xb < pitch) {
+        if (!flip_src) {
+#pragma unroll
+          for (int t = 0; t < 4; t++)
+            *(float4*)(rowbuf + fg_pos(xb + 4 * t)) = make_float4(fa[h][4 * t], fa[h][4 * t + 1], fa[h][4 * t + 2], fa[h][4 * t + 3]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 16; t++) {
+            const int x = card_w - 1 - (xb + t);
+            if (x >= 0) rowbuf[fg_pos(x)] = fa[h][t];
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const int d = lane + 32 * q;
+      if (d < rw) {
+        float hs = 0.f;
+        if (REGW) {
+#pragma unroll
+          for (int k = 0; k < TAPS; k++)
+            if (k < nxr[REGW ? q : 0]) hs = __fmaf_rn(rowbuf[fg_pos(x0r[REGW ? q : 0] + k)], wxr[REGW ? q : 0][k], hs);
+        } else {
+          const int x0 = src_x0 + gxs[d], nx = gxn[d];
+          for (int k = 0; k < nx; k++) hs = __fmaf_rn(rowbuf[fg_pos(x0 + k)], gxw[d * kAreaMaxTaps + k], hs);
+        }
+        const int y = fy0 + r, x = fx0 + d;
+        const int o = flip_dst ? (OH - 1 - y) * OW + (OW - 1 - x) : y * OW + x;
+        outp[o] = fg_clip01(hs);  // img_clip after cv2.resize (util/image.py:334)
+      }
+    }
+  }
+}
+
+#ifndef MTGV_FG_BLOCKS
+#define MTGV_FG_BLOCKS 2
+#endif
+template <int NCH>
+__global__ void __launch_bounds__(kFgThreads, NCH == 1 ? MTGV_FG_BLOCKS : 2)
+    k_foreground(const mtgv_enc_params* __restrict__ params, int n, int split, FgGeom g0, FgGeom g1,
+                 const uint8_t* __restrict__ card_planes, int pitch, float* __restrict__ fg_out) {
+  extern __shared__ __align__(16) unsigned char fg_smem_raw[];
+  // layout: per geometry: xs[256] xn[256] xw[256*8] | per warp: rows[32] | per warp: rowbuf
+  int* xs = (int*)fg_smem_raw;
+  int* xn = xs + 2 * kFgMaxOW;
+  float* xw = (float*)(xn + 2 * kFgMaxOW);
+  FgRow* rtab = (FgRow*)(xw + 2 * kFgMaxOW * kAreaMaxTaps);
+  const int rowbuf_len = (pitch + (pitch >> 3) + 8 + 3) & ~3;  // keeps every warp's buffer 16-byte aligned
+  float* rowbufs = (float*)(rtab + kFgWarps * kFgRows);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_maxtaps[2];
+  if (tid < 2) s_maxtaps[tid] = 0;
+  __syncthreads();
+  for (int q = tid; q < 2 * kFgMaxOW; q += blockDim.x) {
+    const FgGeom& g = q < kFgMaxOW ? g0 : g1;
+    const int d = q & (kFgMaxOW - 1);
+    int st = 0, nn = 0;
+    float ww[kAreaMaxTaps];
+    if (d < g.rw && g.rw > 0) nn = area_taps(g.src_w, g.rw, d, &st, ww);
+    xs[q] = st;
+    xn[q] = nn;
+    for (int k = 0; k < kAreaMaxTaps; k++) xw[q * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
+    atomicMax(&s_maxtaps[q / kFgMaxOW], nn);
+  }
+  __syncthreads();
+  FgRow* rows = rtab + warp * kFgRows;
+  float* rowbuf = rowbufs + (size_t)warp * rowbuf_len;
+  const int n_items = n * 3 * split;
+  for (int item = blockIdx.x * kFgWarps + warp; item < n_items; item += gridDim.x * kFgWarps) {
+    const int s = item / (3 * split), rem = item - s * 3 * split, c = rem / split, part = rem - c * split;
+    const mtgv_enc_params* sp = params + s;
+    const int kind = sp->kind;
+    if (sp->status != 0 || kind == MTGV_KIND_BG_ONLY) continue;
+    const int gi = kind == MTGV_KIND_CROPPED ? 1 : 0;
+    const FgGeom& g = gi ? g1 : g0;
+    if (sp->src_h != g.src_h || sp->src_w != g.src_w || sp->fg_rh != g.rh || sp->fg_rw != g.rw) continue;  // host invariant
+    const int* gxs = xs + gi * kFgMaxOW;
+    const int* gxn = xn + gi * kFgMaxOW;
+    const float* gxw = xw + gi * kFgMaxOW * kAreaMaxTaps;
+    if (s_maxtaps[gi] <= 5 && g.rw <= 128)
+      fg_item<NCH, true>(sp, c, part, split, gxs, gxn, gxw, rows, rowbuf, card_planes, pitch, fg_out, s, lane);
+    else
+      fg_item<NCH, false>(sp, c, part, split, gxs, gxn, gxw, rows, rowbuf, card_planes, pitch, fg_out, s, lane);
+  }
+}
+
+static size_t fg_smem_bytes(int pitch) {
+  size_t b = 2 * kFgMaxOW * (8 + 4 * kAreaMaxTaps);
+  b += (size_t)kFgWarps * kFgRows * sizeof(FgRow);
+  b += (size_t)kFgWarps * ((pitch + (pitch >> 3) + 8 + 3) & ~3) * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* fg_out, cudaStream_t st) {
+  if (OW > kFgMaxOW) return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw width > 256");
+  if (ctx->card_pitch > 1024) return fail(ctx, MTGV_ERR_LIMIT, "card width > 1024");
+  // the two INTER_AREA geometries a batch can contain (make_virtual / make_cropped)
+  FgGeom g0{0, 0, 0, 0}, g1{0, 0, 0, 0};
+  g0.src_h = ctx->card_h; g0.src_w = ctx->card_w;
+  if (ctx->card_h == OH && ctx->card_w == OW) { g0.rh = OH; g0.rw = OW; }
+  else { int y0, x0; crop_geometry(ctx->card_h, ctx->card_w, OH, OW, true, &g0.rh, &g0.rw, &y0, &x0); }
+  const int border = (int)ceil(fmax(0.02 * ctx->card_h, 0.02 * ctx->card_w));
+  g1.src_h = ctx->card_h - 2 * border; g1.src_w = ctx->card_w - 2 * border; g1.rh = OH; g1.rw = OW;
+  const int split = (OH + kFgRows - 1) / kFgRows > 8 ? (OH + kFgRows - 1) / kFgRows : 8;
+  const size_t smem = fg_smem_bytes(ctx->card_pitch);
+  const bool wide = ctx->card_pitch > 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_foreground<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_foreground<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int blocks = 0;
+  if (wide) MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_foreground<2>, kFgThreads, smem));
+  else MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_foreground<1>, kFgThreads, smem));
+  int grid = ctx->sm_count * (blocks > 0 ? blocks : 1);
+  const int items = m * 3 * split;
+  if (grid > (items + kFgWarps - 1) / kFgWarps) grid = (items + kFgWarps - 1) / kFgWarps;
+  if (wide) k_foreground<2><<<grid, kFgThreads, smem, st>>>(params, m, split, g0, g1, ctx->card_planes, ctx->card_pitch, fg_out);
+  else k_foreground<1><<<grid, kFgThreads, smem, st>>>(params, m, split, g0, g1, ctx->card_planes, ctx->card_pitch, fg_out);
+  ctx->launches++;
+  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  return MTGV_OK;
+}
+
+}  // namespace mtgv

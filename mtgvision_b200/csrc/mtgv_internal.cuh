@@ -115,5 +115,7 @@ int pool_planarize(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* planes, int n, in
 // mtgv_bg.cu
 int pool_interleave(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* words, int n, int h, int w, cudaStream_t st);
 size_t bg_image_bytes(int h, int w);
+// mtgv_fg.cu
+int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* fg_out, cudaStream_t st);
 int bg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* bg_out, cudaStream_t st);
 }  // namespace mtgv

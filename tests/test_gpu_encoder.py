@@ -152,8 +152,13 @@ def test_cropped_samples_and_targets(env):
         refs.append(EO.make_cropped(EO.u8_to_f32(pool.images[k]), (192, 128), tape=t))
         tapes.append(t)
     out, labels, _ = PU.gpu_run_tapes(ctx, tapes, abi.OUT_F32)
-    assert max(PU.lsb_diff(o, r)[0] for o, r in zip(out, refs)) == 0
-    assert max(float(np.abs(o - r).max()) for o, r in zip(out, refs)) < 1e-6
+    # INTER_AREA taps are exact, the float32 sums are reordered (vertical first): ~1e-7 per value, so a
+    # uint8 rounding can flip on isolated pixels - never by more than the stated 1 LSB
+    assert max(PU.lsb_diff(o, r)[0] for o, r in zip(out, refs)) <= MAX_LSB
+    assert max(float(np.abs(o - r).max()) for o, r in zip(out, refs)) < 2e-6
+    g8 = np.rint(np.clip(np.stack(out), 0, 1) * 255).astype(np.int32)
+    r8 = np.rint(np.clip(np.stack(refs), 0, 1) * 255).astype(np.int32)
+    assert (g8 != r8).mean() < 1e-3
     y = ctx.encoder_targets(torch.arange(8, dtype=torch.int32), abi.OUT_F32).permute(0, 2, 3, 1).cpu().numpy()
     assert np.array_equal(y, out)
     # rot180 of the crop (make_cropped(half_upsidedown=True) drawing upsidedown)
@@ -262,7 +267,7 @@ def test_dataset_dropin_surface():
     assert not torch.equal(got[0]["x"], got[1]["x"])  # consecutive batches draw different augmentations
     # static helpers with numpy in/out
     y = SyntheticBgFgMtgImages.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128))
-    assert PU.lsb_diff(y, EO.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128)))[0] == 0
+    assert PU.lsb_diff(y, EO.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128)))[0] <= 1
     v = SyntheticBgFgMtgImages.make_virtual(pool.images[0], bgs[0], (192, 128), True)
     assert v.shape == (192, 128, 3) and v.dtype == np.float32 and np.isfinite(v).all()
     g = SyntheticBgFgMtgImages.make_bg(bgs[1], (192, 128))
