@@ -25,6 +25,7 @@ constexpr int kFgThreads = 256;
 constexpr int kFgWarps = kFgThreads / 32;
 constexpr int kFgRows = 32;  // max destination rows per item
 constexpr int kFgMaxOW = 256;
+constexpr int kFgPf = 4;     // source rows in flight per warp
 
 struct FgGeom {  // the two INTER_AREA geometries of a batch: [0] virtual (whole card, padded), [1] cropped
   int src_h, src_w, rh, rw;
@@ -45,9 +46,8 @@ __device__ __forceinline__ float fg_byte(uint32_t w, int k) {  // exact u8 -> fl
 // registers (<= 5 taps, <= 4 destination columns per lane: scales < 4, out_w <= 128); otherwise they are
 // read from the shared tables.
 template <int NCH, bool REGW>
-__device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, int c, int part, int split,
-                                        const int* __restrict__ gxs, const int* __restrict__ gxn, const float* __restrict__ gxw,
-                                        FgRow* rows, float* rowbuf, const uint8_t* __restrict__ card_planes, int pitch,
+__device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, int c, int part, int split, const FgRow* __restrict__ cols,
+                                        FgRow* rows, float* rowbuf, uint8_t* ring, const uint8_t* __restrict__ card_planes, int pitch,
                                         float* __restrict__ fg_out, int s, int lane) {
   const int kind = sp->kind;
   const int src_h = sp->src_h, rh = sp->fg_rh, rw = sp->fg_rw;
@@ -67,38 +67,34 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
     rows[lane] = e;
   }
   __syncwarp();
-  // this lane's destination columns: first source column, tap count and weights in registers
-  constexpr int TAPS = 5, NQ = REGW ? 4 : kFgMaxOW / 32;
-  int x0r[REGW ? NQ : 1], nxr[REGW ? NQ : 1];
-  float wxr[REGW ? NQ : 1][REGW ? TAPS : 1];
-  if (REGW) {
-#pragma unroll
-    for (int q = 0; q < (REGW ? NQ : 1); q++) {
-      const int d = lane + 32 * q;
-      const bool on = d < rw;
-      x0r[q] = src_x0 + (on ? gxs[d] : 0);
-      nxr[q] = on ? gxn[d] : 0;
-#pragma unroll
-      for (int k = 0; k < TAPS; k++) wxr[q][k] = on ? gxw[d * kAreaMaxTaps + k] : 0.f;
-    }
-  }
   const uint8_t* plane = card_planes + ((size_t)sp->card * 3 + c) * card_h * pitch;
   float* outp = fg_out + ((size_t)s * 3 + c) * OH * OW;
   const int sy_last = rows[r1 - r0 - 1].start + (rows[r1 - r0 - 1].n & 255) - 1;
-  auto load_row = [&](int sy, uint4* v) {
-    int row = src_y0 + sy;
-    if (flip_src) row = card_h - 1 - row;
-    const uint8_t* p = plane + (size_t)row * pitch;
+  // Source rows are consumed in increasing order.  kFgPf rows are kept in flight ahead of the one in use as
+  // 16-byte cp.async copies into a per-warp ring in shared memory (each lane later reads back only the bytes
+  // it copied itself, so no warp barrier is involved); exactly one group is committed per row.
+  auto prefetch_row = [&](int sy) {
+    if (sy <= sy_last) {
+      int row = src_y0 + sy;
+      if (flip_src) row = card_h - 1 - row;
+      const uint8_t* p = plane + (size_t)row * pitch;
+      uint8_t* dst = ring + (size_t)(sy % kFgPf) * (NCH * 512);
 #pragma unroll
-    for (int h = 0; h < NCH; h++) {
-      const int off = (lane + 32 * h) * 16;
-      v[h] = off < pitch ? __ldg((const uint4*)(p + off)) : make_uint4(0u, 0u, 0u, 0u);
+      for (int h = 0; h < NCH; h++) {
+        const int off = (lane + 32 * h) * 16;
+        if (off < pitch) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + off);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(p + off) : "memory");
+        }
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  uint4 cur[NCH], nxt[NCH];
-  int cur_sy = -1;
-  load_row(rows[0].start, nxt);
-  int nxt_sy = rows[0].start;
+  uint4 cur[NCH];
+  const int sy_first = rows[0].start;
+  int cur_sy = sy_first - 1;
+#pragma unroll
+  for (int u = 0; u < kFgPf; u++) prefetch_row(sy_first + u);
   for (int r = r0; r < r1; r++) {
     const FgRow e = rows[r - r0];
     const int ny = e.n & 255;
@@ -114,12 +110,16 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
     bool any_mid = false;
     for (int j = 0; j < ny; j++) {
       const int sy = e.start + j;
-      if (sy != cur_sy) {  // rows shared by two destination rows (a partial tap of each) stay in registers
-        if (sy != nxt_sy) { load_row(sy, nxt); nxt_sy = sy; }  // not the prefetched row (never for contiguous taps)
+      while (sy > cur_sy) {  // rows shared by two destination rows (a partial tap of each) stay in registers
+        cur_sy++;
+        asm volatile("cp.async.wait_group %0;" ::"n"(kFgPf - 1) : "memory");
+        const uint8_t* src = ring + (size_t)(cur_sy % kFgPf) * (NCH * 512);
 #pragma unroll
-        for (int h = 0; h < NCH; h++) cur[h] = nxt[h];
-        cur_sy = nxt_sy;
-        if (sy < sy_last) { load_row(sy + 1, nxt); nxt_sy = sy + 1; }  // prefetch the next source row
+        for (int h = 0; h < NCH; h++) {
+          const int off = (lane + 32 * h) * 16;
+          cur[h] = off < pitch ? *(const uint4*)(src + off) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        prefetch_row(cur_sy + kFgPf);
       }
       const bool left = j == 0 && (e.n & 256), right = j == ny - 1 && (e.n & 512);
       if (left || right) {
@@ -172,17 +172,27 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
     }
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
+    for (int q = 0; q < (REGW ? 4 : kFgMaxOW / 32); q++) {
       const int d = lane + 32 * q;
       if (d < rw) {
-        float hs = 0.f;
+        // column taps: first * wl + (sum of the inner taps) * wm + last * wr; the table stores wl = wm / wr = wm
+        // for taps that are not partial (REGW: <= 5 taps, unrolled)
+        const FgRow ce = cols[d];
+        const int nx = ce.n & 255;
+        const float* v = rowbuf + fg_pos(src_x0 + ce.start);
+        const int wrap = 32 - ((src_x0 + ce.start) & 31);  // taps from this index on sit behind the next skew step
+        float hs = v[0] * ce.wl, mid = 0.f;
         if (REGW) {
 #pragma unroll
-          for (int k = 0; k < TAPS; k++)
-            if (k < nxr[REGW ? q : 0]) hs = __fmaf_rn(rowbuf[fg_pos(x0r[REGW ? q : 0] + k)], wxr[REGW ? q : 0][k], hs);
+          for (int k = 1; k < 4; k++)
+            if (k < nx - 1) mid += v[k + (k >= wrap ? 4 : 0)];
         } else {
-          const int x0 = src_x0 + gxs[d], nx = gxn[d];
-          for (int k = 0; k < nx; k++) hs = __fmaf_rn(rowbuf[fg_pos(x0 + k)], gxw[d * kAreaMaxTaps + k], hs);
+          for (int k = 1; k < nx - 1; k++) mid += v[k + (((src_x0 + ce.start + k) >> 5) - ((src_x0 + ce.start) >> 5)) * 4];
+        }
+        hs = __fmaf_rn(mid, ce.wm, hs);
+        if (nx > 1) {
+          const int k = nx - 1;
+          hs = __fmaf_rn(v[k + (((src_x0 + ce.start + k) >> 5) - ((src_x0 + ce.start) >> 5)) * 4], ce.wr, hs);
         }
         const int y = fy0 + r, x = fx0 + d;
         const int o = flip_dst ? (OH - 1 - y) * OW + (OW - 1 - x) : y * OW + x;
@@ -195,36 +205,33 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
 #ifndef MTGV_FG_BLOCKS
 #define MTGV_FG_BLOCKS 2
 #endif
-template <int NCH>
+template <int NCH, bool REGW>
 __global__ void __launch_bounds__(kFgThreads, NCH == 1 ? MTGV_FG_BLOCKS : 2)
     k_foreground(const mtgv_enc_params* __restrict__ params, int n, int split, FgGeom g0, FgGeom g1,
                  const uint8_t* __restrict__ card_planes, int pitch, float* __restrict__ fg_out) {
   extern __shared__ __align__(16) unsigned char fg_smem_raw[];
-  // layout: per geometry: xs[256] xn[256] xw[256*8] | per warp: rows[32] | per warp: rowbuf
-  int* xs = (int*)fg_smem_raw;
-  int* xn = xs + 2 * kFgMaxOW;
-  float* xw = (float*)(xn + 2 * kFgMaxOW);
-  FgRow* rtab = (FgRow*)(xw + 2 * kFgMaxOW * kAreaMaxTaps);
+  // layout: per geometry: cols[256] | per warp: rows[32] | per warp: rowbuf
+  FgRow* ctab = (FgRow*)fg_smem_raw;
+  FgRow* rtab = ctab + 2 * kFgMaxOW;
   const int rowbuf_len = (pitch + (pitch >> 3) + 8 + 3) & ~3;  // keeps every warp's buffer 16-byte aligned
-  float* rowbufs = (float*)(rtab + kFgWarps * kFgRows);
+  float* rowbufs = (float*)(((uintptr_t)(rtab + kFgWarps * kFgRows) + 15) & ~(uintptr_t)15);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int s_maxtaps[2];
-  if (tid < 2) s_maxtaps[tid] = 0;
-  __syncthreads();
   for (int q = tid; q < 2 * kFgMaxOW; q += blockDim.x) {
     const FgGeom& g = q < kFgMaxOW ? g0 : g1;
     const int d = q & (kFgMaxOW - 1);
-    int st = 0, nn = 0;
-    float ww[kAreaMaxTaps];
-    if (d < g.rw && g.rw > 0) nn = area_taps(g.src_w, g.rw, d, &st, ww);
-    xs[q] = st;
-    xn[q] = nn;
-    for (int k = 0; k < kAreaMaxTaps; k++) xw[q * kAreaMaxTaps + k] = k < nn ? ww[k] : 0.f;
-    atomicMax(&s_maxtaps[q / kFgMaxOW], nn);
+    FgRow e{0, 0, 0.f, 0.f, 0.f};
+    if (d < g.rw && g.rw > 0) {
+      area_compact(g.src_w, g.rw, d, &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+      if ((e.n & 255) == 1 && (e.n & 512) && !(e.n & 256)) e.wl = e.wr;  // single right-partial tap
+      else if (!(e.n & 256)) e.wl = e.wm;
+      if (!(e.n & 512)) e.wr = e.wm;
+    }
+    ctab[q] = e;
   }
   __syncthreads();
   FgRow* rows = rtab + warp * kFgRows;
   float* rowbuf = rowbufs + (size_t)warp * rowbuf_len;
+  uint8_t* ring = (uint8_t*)(rowbufs + (size_t)kFgWarps * rowbuf_len) + (size_t)warp * kFgPf * NCH * 512;
   const int n_items = n * 3 * split;
   for (int item = blockIdx.x * kFgWarps + warp; item < n_items; item += gridDim.x * kFgWarps) {
     const int s = item / (3 * split), rem = item - s * 3 * split, c = rem / split, part = rem - c * split;
@@ -234,20 +241,15 @@ __global__ void __launch_bounds__(kFgThreads, NCH == 1 ? MTGV_FG_BLOCKS : 2)
     const int gi = kind == MTGV_KIND_CROPPED ? 1 : 0;
     const FgGeom& g = gi ? g1 : g0;
     if (sp->src_h != g.src_h || sp->src_w != g.src_w || sp->fg_rh != g.rh || sp->fg_rw != g.rw) continue;  // host invariant
-    const int* gxs = xs + gi * kFgMaxOW;
-    const int* gxn = xn + gi * kFgMaxOW;
-    const float* gxw = xw + gi * kFgMaxOW * kAreaMaxTaps;
-    if (s_maxtaps[gi] <= 5 && g.rw <= 128)
-      fg_item<NCH, true>(sp, c, part, split, gxs, gxn, gxw, rows, rowbuf, card_planes, pitch, fg_out, s, lane);
-    else
-      fg_item<NCH, false>(sp, c, part, split, gxs, gxn, gxw, rows, rowbuf, card_planes, pitch, fg_out, s, lane);
+    fg_item<NCH, REGW>(sp, c, part, split, ctab + gi * kFgMaxOW, rows, rowbuf, ring, card_planes, pitch, fg_out, s, lane);
   }
 }
 
 static size_t fg_smem_bytes(int pitch) {
-  size_t b = 2 * kFgMaxOW * (8 + 4 * kAreaMaxTaps);
-  b += (size_t)kFgWarps * kFgRows * sizeof(FgRow);
+  size_t b = 2 * kFgMaxOW * sizeof(FgRow);
+  b += (size_t)kFgWarps * kFgRows * sizeof(FgRow) + 16;
   b += (size_t)kFgWarps * ((pitch + (pitch >> 3) + 8 + 3) & ~3) * 4;
+  b += (size_t)kFgWarps * kFgPf * (pitch > 512 ? 2 : 1) * 512;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -264,20 +266,27 @@ int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int O
   const int split = (OH + kFgRows - 1) / kFgRows > 8 ? (OH + kFgRows - 1) / kFgRows : 8;
   const size_t smem = fg_smem_bytes(ctx->card_pitch);
   const bool wide = ctx->card_pitch > 512;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_foreground<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_foreground<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  // register-resident column taps need <= 5 taps (scale < 4) and <= 4 destination columns per lane
+  int max_taps = 0;
+  for (int gi = 0; gi < 2; gi++) {
+    const FgGeom& g = gi ? g1 : g0;
+    for (int d = 0; d < g.rw; d++) {
+      int st;
+      float ww[kAreaMaxTaps];
+      const int nn = area_taps(g.src_w, g.rw, d, &st, ww);
+      if (nn > max_taps) max_taps = nn;
+    }
   }
+  const bool regw = max_taps <= 5 && OW <= 128;
+  void (*kern)(const mtgv_enc_params*, int, int, FgGeom, FgGeom, const uint8_t*, int, float*) =
+      wide ? (regw ? k_foreground<2, true> : k_foreground<2, false>) : (regw ? k_foreground<1, true> : k_foreground<1, false>);
+  MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int blocks = 0;
-  if (wide) MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_foreground<2>, kFgThreads, smem));
-  else MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_foreground<1>, kFgThreads, smem));
+  MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kFgThreads, smem));
   int grid = ctx->sm_count * (blocks > 0 ? blocks : 1);
   const int items = m * 3 * split;
   if (grid > (items + kFgWarps - 1) / kFgWarps) grid = (items + kFgWarps - 1) / kFgWarps;
-  if (wide) k_foreground<2><<<grid, kFgThreads, smem, st>>>(params, m, split, g0, g1, ctx->card_planes, ctx->card_pitch, fg_out);
-  else k_foreground<1><<<grid, kFgThreads, smem, st>>>(params, m, split, g0, g1, ctx->card_planes, ctx->card_pitch, fg_out);
+  kern<<<grid, kFgThreads, smem, st>>>(params, m, split, g0, g1, ctx->card_planes, ctx->card_pitch, fg_out);
   ctx->launches++;
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   return MTGV_OK;
