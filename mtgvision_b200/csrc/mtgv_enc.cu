@@ -746,8 +746,11 @@ int pool_planarize(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* planes, int n, in
 
 __global__ void k_expand(const mtgv_enc_tape* tape, int n, const mtgv_enc_config* cfg, PoolMeta pm, mtgv_enc_params* params,
                          int64_t* labels) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
+  // one warp per sample, lane 0 working: every sample takes its own path through the op expansions, so 32
+  // samples in one warp serialise (measured 4.6 active lanes per instruction); one sample per warp spreads
+  // the same serial chains over all SMs instead
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= n || (threadIdx.x & 31) != 0) return;
   expand_encoder_sample(&tape[s], cfg, pm, &params[s]);
   if (labels) {
     int card = params[s].card;
@@ -765,7 +768,7 @@ static PoolMeta pool_meta(const mtgv_ctx* ctx) {
 
 int enc_expand(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels, cudaStream_t st) {
   if (n <= 0) return MTGV_OK;
-  k_expand<<<(n + 63) / 64, 64, 0, st>>>(tape, n, ctx->cfg_dev, pool_meta(ctx), params, labels);
+  k_expand<<<(n + 3) / 4, 128, 0, st>>>(tape, n, ctx->cfg_dev, pool_meta(ctx), params, labels);
   ctx->launches++;
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   return MTGV_OK;
@@ -918,8 +921,11 @@ __device__ void sample_virtual(Rng& r, mtgv_enc_tape* t, const mtgv_enc_config* 
 
 __global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const mtgv_enc_config* cfg, PoolMeta pm,
                               const int32_t* cards, const int32_t* bgs, double p_tii, double p_neg, mtgv_enc_tape* tape) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pairs) return;
+  // one warp per x-sample (lane 0 working), see k_expand; `which` selects x or x2 of pair i
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_xs = cfg->paired ? 2 : 1;
+  const int i = w / n_xs, only = w - i * n_xs;
+  if (i >= n_pairs || (threadIdx.x & 31) != 0) return;
   const uint64_t g = (uint64_t)(first + i);
   Rng sel(seed, g, 1);  // card / background selection stream (re-derivable by other samples)
   int card = sel.below(pm.n_cards);
@@ -929,7 +935,7 @@ __global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const m
   if (p_tii < 0.0) p_tii = cfg->target_is_input_prob;
   if (p_neg < 0.0) p_neg = cfg->similar_neg_prob;
   const int n_x = cfg->paired ? 2 : 1;
-  for (int which = 0; which < n_x; which++) {
+  for (int which = only; which <= only; which++) {
     mtgv_enc_tape* t = &tape[which * n_pairs + i];
     Rng r(seed, g, 2 + which);
     t->card = card; t->bg = bg; t->swap_choice = -1; t->upsidedown = 0;
@@ -962,7 +968,8 @@ __global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const m
 int enc_sample_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first, int n_pairs, const int32_t* cards, const int32_t* bgs,
                     double p_tii, double p_neg, mtgv_enc_tape* tape, cudaStream_t st) {
   if (n_pairs <= 0) return MTGV_OK;
-  k_sample_tape<<<(n_pairs + 63) / 64, 64, 0, st>>>(seed, first, n_pairs, ctx->cfg_dev, pool_meta(ctx), cards, bgs, p_tii,
+  const int n_warps = n_pairs * (ctx->cfg.paired ? 2 : 1);
+  k_sample_tape<<<(n_warps + 3) / 4, 128, 0, st>>>(seed, first, n_pairs, ctx->cfg_dev, pool_meta(ctx), cards, bgs, p_tii,
                                                     p_neg, tape);
   ctx->launches++;
   MTGV_CUDA_OK(ctx, cudaGetLastError());
