@@ -315,7 +315,7 @@ def run_cuda(args):
     if not args.no_e2e:
         hc = torch.from_numpy(cards.images[np.arange(PAIRS) % len(cards.images)]).pin_memory()
         hb = torch.from_numpy(np.stack([bgs[j % len(bgs)] for j in range(PAIRS)])).pin_memory()
-        e2e_steps = max(3, min(args.steps, 30))
+        e2e_steps = max(3, min(args.steps, 30))  # pipeline fill and drain are inside the timed region
 
         def feed(k):
             for _ in range(k):

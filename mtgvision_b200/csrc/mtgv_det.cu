@@ -557,8 +557,9 @@ __device__ int ph_blur_family(DRng& r, mtgv_photo_op* o, double p) {
 
 __global__ void k_det_sample(uint64_t seed, int64_t first, int n, const mtgv_det_config* __restrict__ cfg, int n_cards_pool,
                              int n_bgs, int card_h, int card_w, mtgv_det_tape* tape) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  // one warp per scene, lane 0 working: scenes take divergent paths through the augmentation graphs
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n || (threadIdx.x & 31) != 0) return;
   mtgv_det_tape* t = &tape[i];
   DRng r(seed, (uint64_t)(first + i));
   const int S_h = cfg->size_h, S_w = cfg->size_w;
@@ -736,7 +737,7 @@ int mtgv_sample_det_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int 
   if (rc) return rc;
   if (!tape || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_sample_det_tape: bad arguments");
   if (n == 0) return MTGV_OK;
-  k_det_sample<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(seed, first_index, n, d->cfg_dev, ctx->n_cards, ctx->n_bgs,
+  k_det_sample<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(seed, first_index, n, d->cfg_dev, ctx->n_cards, ctx->n_bgs,
                                                                ctx->card_h, ctx->card_w, tape);
   ctx->launches++;
   MTGV_CUDA_OK(ctx, cudaGetLastError());

@@ -171,7 +171,10 @@ class RanMtgEncDecDataset(IterableDataset):
         ctx = self.ctx
         dev = ctx.device
         with torch.cuda.device(dev):
-            s_in, s_k, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            if getattr(self, "_pipe_streams", None) is None:
+                # persistent: the caching allocator keeps one block pool per stream, new streams would cudaMalloc again
+                self._pipe_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_in, s_k, s_out = self._pipe_streams
             main = torch.cuda.current_stream(dev)
             for s in (s_in, s_k, s_out):
                 s.wait_stream(main)
