@@ -35,8 +35,8 @@ namespace mtgv {
 constexpr int kBgThreads = MTGV_BG_THREADS;
 constexpr int kBgTR = 8, kBgTC = 32;   // output pixels per tile
 constexpr int kBgWCap = 3200;          // warp_inv pixels staged per tile
-constexpr int kBgRCap = 3072;          // rotate-canvas pixels staged per tile
-constexpr int kBgWRows = 48, kBgWBlk = 3;
+constexpr int kBgRCap = 2816;          // rotate-canvas pixels staged per tile
+constexpr int kBgWRows = 32, kBgWSegs = 8;  // window rows / 16-column coordinate segments per tile
 constexpr int kBgCanvas = 704;         // rotate canvases up to this extent use per-item fixed-point tables
 constexpr int kBgBandRows = 32;        // output rows per work item
 constexpr int kBgMaxOW = 256;
@@ -49,7 +49,7 @@ struct AreaEnt {  // one destination index of computeResizeAreaTab, compact: tap
 struct BgSmem {
   float4 rtile[kBgRCap];
   float wtile[3][kBgWCap];
-  double org[kBgWRows * kBgWBlk * 4];  // X0, Y0, W0 of WarpPerspectiveInvoker per (window row, column block)
+  PerspSeg seg[kBgWRows * kBgWSegs];   // reference coordinates of the warp_inv stage per (window row, 16-column segment)
   int colA[kBgCanvas], colB[kBgCanvas], rowX[kBgCanvas], rowY[kBgCanvas];
   AreaEnt ax[kBgMaxOW], ay[kBgBandRows];
   // the sample
@@ -68,6 +68,12 @@ struct BgSmem {
 };
 
 __device__ __forceinline__ float sat01(float v) { return __saturatef(v); }
+
+__device__ __noinline__ int2 persp_coord_nl(const double* M, int x, int y, int bw0) {
+  int2 r;
+  persp_coord(M, x, y, bw0, &r.x, &r.y);
+  return r;
+}
 
 __device__ __forceinline__ float byte_f(uint32_t w, int c) {  // exact u8 -> float without I2F
   return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + c)) - 8388608.f;
@@ -213,12 +219,18 @@ __device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0,
     }
     S.rtile[k] = v;
   };
+  // software-pipelined: the four tap words of the next two pixels are in flight while the current two are blended
+  if (tid >= npx) return;
+  RTap na = fetch(tid), nc = fetch(tid + kBgThreads < npx ? tid + kBgThreads : tid);
   for (int k = tid; k < npx; k += 2 * kBgThreads) {
-    const int k2 = k + kBgThreads;
-    const bool two = k2 < npx;
-    const RTap a = fetch(k), c = fetch(two ? k2 : k);
+    const int k2 = k + kBgThreads, k3 = k + 2 * kBgThreads, k4 = k + 3 * kBgThreads;
+    const RTap a = na, c = nc;
+    if (k3 < npx) {
+      na = fetch(k3);
+      nc = fetch(k4 < npx ? k4 : k3);
+    }
     finish(k, a);
-    if (two) finish(k2, c);
+    if (k2 < npx) finish(k2, c);
   }
 }
 
@@ -385,7 +397,6 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
     b.h = S.bg_h; b.w = S.bg_w; b.pitchw = (S.bg_w + 3) & ~3; b.fh = S.flip_h; b.fv = S.flip_v;
     b.px = reinterpret_cast<const uint32_t*>(bg_pool + bg_off[S.bg]);
     const int bw0 = persp_block_w(nh, nw);
-    const unsigned bw_magic = div_magic(bw0);
     const bool tables = nh <= kBgCanvas && nw <= kBgCanvas;
     // tile shape: shrink until a tile's warp_inv window fits the staging buffer
     int TR = kBgTR, TC = kBgTC;
@@ -393,12 +404,11 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
       const double sy = (double)nh / S.bg_rh, sx = (double)nw / S.bg_rw;
       while (TR * TC > 1) {
         const int wh = (int)(TR * sy) + 3, ww = (int)(TC * sx) + 3;
-        if (wh * ww <= kBgWCap && wh <= kBgWRows && (ww + bw0 - 1) / bw0 + 1 <= kBgWBlk) break;
+        if (wh * ww <= kBgWCap && wh <= kBgWRows && (ww >> kPerspSegShift) + 2 <= kBgWSegs) break;
         if (TC * sx >= TR * sy && TC > 1) TC >>= 1; else if (TR > 1) TR >>= 1; else TC >>= 1;
       }
     }
     float* outp = bg_out + (size_t)s * 3 * OH * OW;
-    const double m0 = S.winv[0], m3 = S.winv[3], m6 = S.winv[6];
     __syncthreads();
     const bool pre_linear = S.pre_linear != 0, post_linear = S.post_linear != 0;
     const int max_nx = S.max_nx;
@@ -406,50 +416,62 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
 #pragma unroll
     for (int c = 0; c < 3; c++) { la[c] = S.lin_a[c]; lb[c] = S.lin_b[c]; pa[c] = S.plin_a[c]; pb[c] = S.plin_b[c]; }
 
-    for (int ty0 = by0; ty0 < by1; ty0 += TR) {
-      for (int tx0 = 0; tx0 < OW; tx0 += TC) {
-        const int ty1 = min(ty0 + TR, by1), tx1 = min(tx0 + TC, OW);
-        const AreaEnt eY0 = S.ay[ty0 - by0], eY1 = S.ay[ty1 - 1 - by0], eX0 = S.ax[tx0], eX1 = S.ax[tx1 - 1];
-        const int wy0 = eY0.start, wy1 = eY1.start + (eY1.n & 255), wx0 = eX0.start, wx1 = eX1.start + (eX1.n & 255);
-        const int WH = wy1 - wy0, WW = wx1 - wx0;
-        const int blk0 = div_by(wx0, bw_magic), nblk = div_by(wx1 - 1, bw_magic) - blk0 + 1;
-        const bool staged = WH * WW <= kBgWCap && WH <= kBgWRows && nblk <= kBgWBlk;
-        __syncthreads();  // previous tile's readers of rtile / wtile / org / tile[] are done
-        if (tid < 32) {
-          // bounding box, in rotate-canvas pixels, of the window's image under the inverse homography
-          // (a projective map with W > 0 sends the window rectangle into the convex hull of its corners)
-          int X, Y;
-          persp_coord(S.winv, (lane & 1) ? wx1 - 1 : wx0, (lane & 2) ? wy1 - 1 : wy0, bw0, &X, &Y);
-          int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-          int minx = sx, maxx = sx, miny = sy, maxy = sy;
+    // Tiles of the band are software-pipelined: the set-up of tile t+1 (bounding box, coordinate segments) shares
+    // a barrier interval with the INTER_AREA reduction of tile t, which reads none of what the set-up writes.
+    struct TileGeom { int ty0, ty1, tx0, tx1, wy0, wy1, wx0, wx1, WH, WW, seg0, nseg; bool staged; };
+    const int tiles_x = (OW + TC - 1) / TC, n_tiles = tiles_x * ((by1 - by0 + TR - 1) / TR);
+    auto geom = [&](int t) {
+      TileGeom g;
+      const int tyi = t / tiles_x;
+      g.ty0 = by0 + tyi * TR; g.tx0 = (t - tyi * tiles_x) * TC;
+      g.ty1 = min(g.ty0 + TR, by1); g.tx1 = min(g.tx0 + TC, OW);
+      const AreaEnt eY0 = S.ay[g.ty0 - by0], eY1 = S.ay[g.ty1 - 1 - by0], eX0 = S.ax[g.tx0], eX1 = S.ax[g.tx1 - 1];
+      g.wy0 = eY0.start; g.wy1 = eY1.start + (eY1.n & 255); g.wx0 = eX0.start; g.wx1 = eX1.start + (eX1.n & 255);
+      g.WH = g.wy1 - g.wy0; g.WW = g.wx1 - g.wx0;
+      g.seg0 = g.wx0 >> kPerspSegShift; g.nseg = ((g.wx1 - 1) >> kPerspSegShift) - g.seg0 + 1;
+      g.staged = g.WH * g.WW <= kBgWCap && g.WH <= kBgWRows && g.nseg <= kBgWSegs;
+      return g;
+    };
+    auto setup = [&](const TileGeom& g) {
+      if (tid < 32) {
+        // bounding box, in rotate-canvas pixels, of the window's image under the inverse homography
+        // (a projective map with W > 0 sends the window rectangle into the convex hull of its corners)
+        int X, Y;
+        persp_coord(S.winv, (lane & 1) ? g.wx1 - 1 : g.wx0, (lane & 2) ? g.wy1 - 1 : g.wy0, bw0, &X, &Y);
+        int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+        int minx = sx, maxx = sx, miny = sy, maxy = sy;
 #pragma unroll
-          for (int o = 1; o < 4; o <<= 1) {
-            minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
-            miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
-          }
-          if (lane == 0) {
-            const int x0 = max(minx - 1, 0), x1 = min(maxx + 3, nw), y0 = max(miny - 1, 0), y1 = min(maxy + 3, nh);
-            int rtw = max(x1 - x0, 0), rth = max(y1 - y0, 0);
-            if (rtw * rth > kBgRCap || !staged) rtw = rth = 0;
-            S.tile[0] = x0; S.tile[1] = y0; S.tile[2] = rtw; S.tile[3] = rth;
-            S.tile[4] = (int)div_magic(rtw);
-          } else if (lane == 1) {
-            S.tile[5] = (int)div_magic(WW);
-          } else if (lane == 2) {
-            S.tile[6] = (int)div_magic(tx1 - tx0);
-          }
-        } else if (staged) {
-          // per (row, column block) origins of the perspective coordinate generator
-          for (int k = tid - 32; k < WH * nblk; k += nt - 32) {
-            const int wr = nblk == 1 ? k : (nblk == 2 ? k >> 1 : k / 3);  // nblk <= kBgWBlk
-            const double bx = (double)((blk0 + (k - wr * nblk)) * bw0), yy = (double)(wy0 + wr);
-            const double* M = S.winv;
-            S.org[4 * k + 0] = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
-            S.org[4 * k + 1] = __dadd_rn(__dadd_rn(__dmul_rn(M[3], bx), __dmul_rn(M[4], yy)), M[5]);
-            S.org[4 * k + 2] = __dadd_rn(__dadd_rn(__dmul_rn(M[6], bx), __dmul_rn(M[7], yy)), M[8]);
-          }
+        for (int o = 1; o < 4; o <<= 1) {
+          minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+          miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
         }
-        __syncthreads();
+        if (lane == 0) {
+          const int x0 = max(minx - 1, 0), x1 = min(maxx + 3, nw), y0 = max(miny - 1, 0), y1 = min(maxy + 3, nh);
+          int rtw = max(x1 - x0, 0), rth = max(y1 - y0, 0);
+          if (rtw * rth > kBgRCap || !g.staged) rtw = rth = 0;
+          S.tile[0] = x0; S.tile[1] = y0; S.tile[2] = rtw; S.tile[3] = rth;
+          S.tile[4] = (int)div_magic(rtw);
+        } else if (lane == 1) {
+          S.tile[5] = (int)div_magic(g.WW);
+        } else if (lane == 2) {
+          S.tile[6] = (int)div_magic(g.tx1 - g.tx0);
+        }
+      } else if (g.staged) {
+        // exact cv2 coordinates at the reference column of every (window row, segment)
+        for (int k = tid - 32; k < g.WH * g.nseg; k += nt - 32) {
+          const int wr = k / g.nseg;
+          persp_seg_build(S.winv, g.seg0 + (k - wr * g.nseg), g.wy0 + wr, bw0, &S.seg[k]);
+        }
+      }
+    };
+    TileGeom g = geom(0);
+    setup(g);
+    __syncthreads();
+    for (int t = 0; t < n_tiles; t++) {
+      {
+        const int ty0 = g.ty0, ty1 = g.ty1, tx0 = g.tx0, tx1 = g.tx1, wy0 = g.wy0, wx0 = g.wx0, WH = g.WH, WW = g.WW;
+        const int seg0 = g.seg0, nseg = g.nseg;
+        const bool staged = g.staged;
         const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
         const unsigned mg_r = (unsigned)S.tile[4], mg_w = (unsigned)S.tile[5], mg_a = (unsigned)S.tile[6];
         if (!tables) stage_rotate<false, false>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
@@ -463,10 +485,11 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
           auto coords = [&](int k) {
             const int r = div_by(k, mg_w), cx = k - r * WW;
             const int wx = wx0 + cx;
-            const int bi = div_by(wx, bw_magic);
-            const double* o = S.org + 4 * (r * nblk + (bi - blk0));
-            const double2 o01 = *reinterpret_cast<const double2*>(o);
-            return persp_xy(o01.x, o01.y, o[2], m0, m3, m6, (double)(wx - bi * bw0));
+            const PerspSeg sg = S.seg[r * nseg + ((wx >> kPerspSegShift) - seg0)];
+            int2 XY;
+            if (!persp_seg_eval(sg, (float)((wx & ((1 << kPerspSegShift) - 1)) - (1 << (kPerspSegShift - 1))), &XY.x, &XY.y))
+              XY = persp_coord_nl(S.winv, wx, wy0 + r, bw0);
+            return XY;
           };
           auto finish = [&](int k, int2 XY) {
             const int sx = XY.x >> 5, sy = XY.y >> 5;
@@ -514,6 +537,11 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
         else if (max_nx <= 6) stage_area<6>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
         else stage_area<kAreaMaxTaps>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
       }
+      if (t + 1 < n_tiles) {
+        g = geom(t + 1);
+        setup(g);
+      }
+      __syncthreads();
     }
   }
 }

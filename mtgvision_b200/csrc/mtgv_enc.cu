@@ -1097,8 +1097,16 @@ __global__ void k_warp_perspective(const float* __restrict__ src, int sh, int sw
   const float* S = src + (size_t)img * sh * sw * c;
   float* D = dst + (size_t)img * dh * dw * c;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dh * dw; i += gridDim.x * blockDim.x) {
+    // the segment-relative fast path of the production kernels (mtgv_persp.cuh), with the exact routine as its
+    // fallback: this entry is the one compared bit for bit against cv2.warpPerspective
     int X, Y;
-    persp_coord(Mi, i % dw, i / dw, bw0, &X, &Y);
+    {
+      const int x = i % dw, y = i / dw;
+      PerspSeg sg;
+      persp_seg_build(Mi, x >> kPerspSegShift, y, bw0, &sg);
+      if (!persp_seg_eval(sg, (float)((x & ((1 << kPerspSegShift) - 1)) - (1 << (kPerspSegShift - 1))), &X, &Y))
+        persp_coord(Mi, x, y, bw0, &X, &Y);
+    }
     int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
     bool x0 = (unsigned)sx < (unsigned)sw, x1 = (unsigned)(sx + 1) < (unsigned)sw;
     bool y0 = (unsigned)sy < (unsigned)sh, y1 = (unsigned)(sy + 1) < (unsigned)sh;

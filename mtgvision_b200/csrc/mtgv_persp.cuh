@@ -47,3 +47,58 @@ static __device__ __forceinline__ void persp_origin(const double* M, double bx, 
 }
 
 }  // namespace mtgv
+
+namespace mtgv {
+
+// ---- segment-relative coordinates ------------------------------------------------------------
+// Along a destination row, fX(x) = 32 * NX(x) / W(x) with NX, W linear in x.  Around a reference
+// column c:  fX(c + u) - fX(c) = u * D / (1 + e * u),  D = (32 * m0 - m6 * fX(c)) / W(c),  e = m6 / W(c)
+// (exact algebra).  A segment stores cv2's own fX(c), fY(c) (exact fp64 evaluation, split into
+// integer and float32 fraction) and D, e in float32; the other columns of the segment (|u| <= 8) are
+// evaluated in float32.  With |u * D| <= 300 the float32 error of the sum is below 1.4e-4 (2.5 ulp on the
+// product, 1 ulp on the quotient, 1/2 ulp of 512 on the sum), so whenever the result is further than kPerspGuard from a
+// rounding tie it rounds to the same integer as cv2's double; otherwise (or for degenerate
+// segments, which carry NaN) the caller evaluates the exact routine.
+constexpr int kPerspSegShift = 4;           // 16 columns per segment, reference at +8
+constexpr float kPerspGuard = 4.0e-4f;
+
+struct PerspSeg {
+  int xc, yc;
+  float fx, fy, dx, dy, e, _pad;
+};
+
+static __device__ __forceinline__ void persp_seg_build(const double* M, int seg, int y, int bw0, PerspSeg* s) {
+  const int xc = (seg << kPerspSegShift) + (1 << (kPerspSegShift - 1));
+  const int bxi = (bw0 & (bw0 - 1)) == 0 ? (xc & ~(bw0 - 1)) : (xc / bw0) * bw0;
+  double o[3];
+  persp_origin(M, (double)bxi, (double)y, o);
+  const double x1 = (double)(xc - bxi);
+  const double W = __dadd_rn(o[2], __dmul_rn(M[6], x1));
+  const double Wi = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+  const double fX = __dmul_rn(__dadd_rn(o[0], __dmul_rn(M[0], x1)), Wi);
+  const double fY = __dmul_rn(__dadd_rn(o[1], __dmul_rn(M[3], x1)), Wi);
+  const int Xc = __double2int_rn(fX), Yc = __double2int_rn(fY);
+  s->xc = Xc; s->yc = Yc;
+  s->fx = (float)(fX - (double)Xc);
+  s->fy = (float)(fY - (double)Yc);
+  const double iw = Wi * 0.03125;  // 1 / W up to one rounding; D and e only need float32 accuracy
+  float dx = (float)((32.0 * M[0] - M[6] * fX) * iw), dy = (float)((32.0 * M[3] - M[6] * fY) * iw);
+  const float e = (float)(M[6] * iw);
+  const float half = (float)(1 << (kPerspSegShift - 1));
+  const bool ok = W != 0.0 && fabs(fX) < 1.0e9 && fabs(fY) < 1.0e9 && fabsf(dx) * half <= 300.f && fabsf(dy) * half <= 300.f &&
+                  fabsf(e) * half <= 0.25f;
+  if (!ok) dx = dy = __int_as_float(0x7fc00000);  // NaN: every evaluation falls back to the exact routine
+  s->dx = dx; s->dy = dy; s->e = e; s->_pad = 0.f;
+}
+
+// u = column - reference column of the segment.  Returns false when the exact routine must decide.
+static __device__ __forceinline__ bool persp_seg_eval(const PerspSeg& s, float u, int* X, int* Y) {
+  const float q = __fdividef(u, __fmaf_rn(s.e, u, 1.f));
+  const float sx = __fmaf_rn(q, s.dx, s.fx), sy = __fmaf_rn(q, s.dy, s.fy);
+  const float rx = rintf(sx), ry = rintf(sy);
+  *X = s.xc + (int)rx;
+  *Y = s.yc + (int)ry;
+  return fabsf(sx - rx) < 0.5f - kPerspGuard && fabsf(sy - ry) < 0.5f - kPerspGuard;  // false for NaN
+}
+
+}  // namespace mtgv
