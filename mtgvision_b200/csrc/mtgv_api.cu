@@ -66,7 +66,7 @@ void mtgv_destroy(mtgv_ctx* ctx) {
   free_cards(ctx);
   free_bgs(ctx);
   cudaFree(ctx->cfg_dev); cudaFree(ctx->alpha0); cudaFree(ctx->alpha_scratch); cudaFree(ctx->sync_words);
-  cudaFree(ctx->tmp_params); cudaFree(ctx->bg_scratch); cudaFree(ctx->bg_counter);
+  cudaFree(ctx->tmp_params); cudaFree(ctx->bg_scratch); cudaFree(ctx->bg_counter); cudaFree(ctx->fg_counter);
   delete ctx;
 }
 

@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
       continue;
     }
     const bool bg_only = sp.kind == MTGV_KIND_BG_ONLY;
-    stage_load_fg(S.P0, OH, OW, L.fg_scratch + ((size_t)s * 3 + plane) * HW, bg_only, sp.fg_y0, sp.fg_y0 + sp.fg_rh, sp.fg_x0,
+    stage_load_fg(S.P0, OH, OW, L.fg_scratch + ((size_t)fg_plane_owner(L.params, L.n, s) * 3 + plane) * HW, bg_only, sp.fg_y0, sp.fg_y0 + sp.fg_rh, sp.fg_x0,
                   sp.fg_x0 + sp.fg_rw);
     __syncthreads();
     Vm vm{{S.P0, S.P1}, 0, OH, OW, plane, L.fields, sp.seed, S.aux};

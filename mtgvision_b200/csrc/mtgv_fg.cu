@@ -208,7 +208,7 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
 template <int NCH, bool REGW>
 __global__ void __launch_bounds__(kFgThreads, NCH == 1 ? MTGV_FG_BLOCKS : 2)
     k_foreground(const mtgv_enc_params* __restrict__ params, int n, int split, FgGeom g0, FgGeom g1,
-                 const uint8_t* __restrict__ card_planes, int pitch, float* __restrict__ fg_out) {
+                 const uint8_t* __restrict__ card_planes, int pitch, float* __restrict__ fg_out, int* __restrict__ work_counter) {
   extern __shared__ __align__(16) unsigned char fg_smem_raw[];
   // layout: per geometry: cols[256] | per warp: rows[32] | per warp: rowbuf
   FgRow* ctab = (FgRow*)fg_smem_raw;
@@ -233,11 +233,16 @@ __global__ void __launch_bounds__(kFgThreads, NCH == 1 ? MTGV_FG_BLOCKS : 2)
   float* rowbuf = rowbufs + (size_t)warp * rowbuf_len;
   uint8_t* ring = (uint8_t*)(rowbufs + (size_t)kFgWarps * rowbuf_len) + (size_t)warp * kFgPf * NCH * 512;
   const int n_items = n * 3 * split;
-  for (int item = blockIdx.x * kFgWarps + warp; item < n_items; item += gridDim.x * kFgWarps) {
+  for (;;) {  // warps pull items from a global queue: skipped (aliased, cropped-geometry) items cost nothing
+    int item = 0;
+    if (lane == 0) item = atomicAdd(work_counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
     const int s = item / (3 * split), rem = item - s * 3 * split, c = rem / split, part = rem - c * split;
     const mtgv_enc_params* sp = params + s;
     const int kind = sp->kind;
     if (sp->status != 0 || kind == MTGV_KIND_BG_ONLY) continue;
+    if (fg_plane_owner(params, n, s) != s) continue;  // the pair partner's planes are identical and are reused
     const int gi = kind == MTGV_KIND_CROPPED ? 1 : 0;
     const FgGeom& g = gi ? g1 : g0;
     if (sp->src_h != g.src_h || sp->src_w != g.src_w || sp->fg_rh != g.rh || sp->fg_rw != g.rw) continue;  // host invariant
@@ -278,7 +283,7 @@ int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int O
     }
   }
   const bool regw = max_taps <= 5 && OW <= 128;
-  void (*kern)(const mtgv_enc_params*, int, int, FgGeom, FgGeom, const uint8_t*, int, float*) =
+  void (*kern)(const mtgv_enc_params*, int, int, FgGeom, FgGeom, const uint8_t*, int, float*, int*) =
       wide ? (regw ? k_foreground<2, true> : k_foreground<2, false>) : (regw ? k_foreground<1, true> : k_foreground<1, false>);
   MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int blocks = 0;
@@ -286,7 +291,9 @@ int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int O
   int grid = ctx->sm_count * (blocks > 0 ? blocks : 1);
   const int items = m * 3 * split;
   if (grid > (items + kFgWarps - 1) / kFgWarps) grid = (items + kFgWarps - 1) / kFgWarps;
-  kern<<<grid, kFgThreads, smem, st>>>(params, m, split, g0, g1, ctx->card_planes, ctx->card_pitch, fg_out);
+  if (!ctx->fg_counter) MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->fg_counter, 4));
+  MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->fg_counter, 0, 4, st));
+  kern<<<grid, kFgThreads, smem, st>>>(params, m, split, g0, g1, ctx->card_planes, ctx->card_pitch, fg_out, ctx->fg_counter);
   ctx->launches++;
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   return MTGV_OK;

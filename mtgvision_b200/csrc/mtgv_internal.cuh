@@ -46,6 +46,7 @@ struct mtgv_ctx {
   size_t bg_cap = 0;            // floats
   int bg_blocks_per_sm = 0;
   int* bg_counter = nullptr;    // work-queue word of k_background
+  int* fg_counter = nullptr;    // work-queue word of k_foreground
   size_t alpha_cap = 0;  // samples
   int32_t* sync_words = nullptr;  // [0] work counter, [1..] per-sample alpha-ready flags
   size_t sync_cap = 0;
@@ -97,6 +98,25 @@ struct Philox {
 };
 
 }  // namespace mtgv
+
+#if defined(__CUDACC__)
+namespace mtgv {
+// x and x2 of a positive pair usually resize the SAME card with the same geometry (make_virtual of the same
+// card, no hard-negative swap): the area-resized foreground planes are identical, so sample s of the second half
+// of a launch reuses the planes of sample s - n/2 when every input of the resize matches.  Evaluated
+// identically by k_foreground (skip) and k_encoder (read the partner's planes).
+__device__ __forceinline__ int fg_plane_owner(const mtgv_enc_params* __restrict__ p, int n, int s) {
+  if ((n & 1) || s < (n >> 1)) return s;
+  const mtgv_enc_params& a = p[s];
+  const mtgv_enc_params& b = p[s - (n >> 1)];
+  const bool same = a.status == 0 && b.status == 0 && a.kind == b.kind && a.kind != MTGV_KIND_BG_ONLY && a.card == b.card &&
+                    a.upsidedown == b.upsidedown && a.out_h == b.out_h && a.out_w == b.out_w && a.src_y0 == b.src_y0 &&
+                    a.src_x0 == b.src_x0 && a.src_h == b.src_h && a.src_w == b.src_w && a.fg_rh == b.fg_rh && a.fg_rw == b.fg_rw &&
+                    a.fg_y0 == b.fg_y0 && a.fg_x0 == b.fg_x0;
+  return same ? s - (n >> 1) : s;
+}
+}  // namespace mtgv
+#endif
 
 // entry points implemented in mtgv_enc.cu, called from mtgv_api.cu
 namespace mtgv {
