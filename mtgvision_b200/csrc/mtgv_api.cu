@@ -174,6 +174,7 @@ static int need_encoder(mtgv_ctx* ctx, bool need_bg) {
 int mtgv_sample_encoder_tape(mtgv_ctx* ctx, uint64_t seed, int64_t first_index, int n_pairs, mtgv_enc_tape* tape, void* stream) {
   int rc = need_encoder(ctx, true);
   if (rc) return rc;
+  if (n_pairs == 0) return MTGV_OK;  // empty batch: nothing to write (the caller's buffer may be a null pointer)
   if (!tape || n_pairs < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_sample_encoder_tape: bad arguments");
   return enc_sample_tape(ctx, seed, first_index, n_pairs, nullptr, nullptr, -1.0, -1.0, tape, (cudaStream_t)stream);
 }
@@ -207,6 +208,7 @@ int mtgv_sample_encoder_tape_ex(mtgv_ctx* ctx, uint64_t seed, int64_t first_inde
                                 mtgv_enc_tape* tape, void* stream) {
   int rc = need_encoder(ctx, true);
   if (rc) return rc;
+  if (n_pairs == 0) return MTGV_OK;
   if (!tape || n_pairs < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_sample_encoder_tape_ex: bad arguments");
   return enc_sample_tape(ctx, seed, first_index, n_pairs, cards, bgs, target_is_input_prob, similar_neg_prob, tape,
                          (cudaStream_t)stream);
@@ -225,6 +227,7 @@ int mtgv_get_mask(mtgv_ctx* ctx, int which, float* out, void* stream) {
 int mtgv_expand_params(mtgv_ctx* ctx, const mtgv_enc_tape* tape, int n, mtgv_enc_params* params, int64_t* labels, void* stream) {
   int rc = need_encoder(ctx, false);
   if (rc) return rc;
+  if (n == 0) return MTGV_OK;
   if (!tape || !params || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_expand_params: bad arguments");
   return enc_expand(ctx, tape, n, params, labels, (cudaStream_t)stream);
 }
@@ -233,6 +236,7 @@ int mtgv_encoder_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void
                        void* stream) {
   int rc = need_encoder(ctx, false);
   if (rc) return rc;
+  if (n == 0) return MTGV_OK;
   if (!params || !out || n < 0 || out_dtype < 0 || out_dtype > 2)
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_encoder_batch: bad arguments");
   return enc_batch(ctx, params, n, out, out_dtype, fields, (cudaStream_t)stream);
@@ -241,6 +245,7 @@ int mtgv_encoder_batch(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, void
 int mtgv_encoder_targets(mtgv_ctx* ctx, const int32_t* cards, int n, void* out, int out_dtype, void* stream) {
   int rc = need_encoder(ctx, false);
   if (rc) return rc;
+  if (n == 0) return MTGV_OK;
   if (!cards || !out || n < 0 || out_dtype < 0 || out_dtype > 2)
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_encoder_targets: bad arguments");
   return enc_targets(ctx, cards, n, out, out_dtype, (cudaStream_t)stream);

@@ -29,14 +29,21 @@
 
 namespace mtgv {
 
+#ifndef MTGV_BG_SKIP
+#define MTGV_BG_SKIP 0  // timing experiments only: 1 skip stage R, 2 skip stage W, 4 skip stage A, 8 skip tile set-up
+#endif
 #ifndef MTGV_BG_THREADS
 #define MTGV_BG_THREADS 256
 #endif
 constexpr int kBgThreads = MTGV_BG_THREADS;
-constexpr int kBgTR = 8, kBgTC = 32;   // output pixels per tile
-constexpr int kBgWCap = 3200;          // warp_inv pixels staged per tile
-constexpr int kBgRCap = 2816;          // rotate-canvas pixels staged per tile
-constexpr int kBgWRows = 32, kBgWSegs = 8;  // window rows / 16-column coordinate segments per tile
+#ifndef MTGV_BG_BIG
+#define MTGV_BG_BIG 0  // 1: one 512-thread CTA per SM working on 16x32 tiles (experiment)
+#endif
+constexpr int kBgCtas = MTGV_BG_BIG ? 1 : 2;
+constexpr int kBgTR = MTGV_BG_BIG ? 16 : 8, kBgTC = 32;   // output pixels per tile
+constexpr int kBgWCap = MTGV_BG_BIG ? 6400 : 3200;          // warp_inv pixels staged per tile
+constexpr int kBgRCap = MTGV_BG_BIG ? 5632 : 2816;          // rotate-canvas pixels staged per tile
+constexpr int kBgWRows = MTGV_BG_BIG ? 64 : 32, kBgWSegs = 8;  // window rows / 16-column coordinate segments per tile
 constexpr int kBgCanvas = 704;         // rotate canvases up to this extent use per-item fixed-point tables
 constexpr int kBgBandRows = 32;        // output rows per work item
 constexpr int kBgMaxOW = 256;
@@ -215,7 +222,10 @@ __device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0,
         v = make_float4(o[0], o[1], o[2], 0.f);
       }
     } else {
-      v = rot_px_general(S, b, t.X, t.Y);
+      // BORDER_CONSTANT: all four taps outside the source (the empty corners of the rotate canvas) -> 0
+      const int sx = t.X >> 5, sy = t.Y >> 5;
+      if (sx < -1 || sy < -1 || sx >= b.w || sy >= b.h) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      else v = rot_px_general(S, b, t.X, t.Y);
     }
     S.rtile[k] = v;
   };
@@ -305,7 +315,7 @@ __device__ __noinline__ void stage_area_direct(const BgSmem& S, const BgSrc& b, 
   }
 }
 
-__global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
+__global__ void __launch_bounds__(kBgThreads, kBgCtas) k_background(const mtgv_enc_params* __restrict__ params, int n, int n_bands,
                                                               const uint8_t* __restrict__ bg_pool, const int64_t* __restrict__ bg_off,
                                                               float* __restrict__ bg_out, int* __restrict__ work_counter) {
   extern __shared__ __align__(16) unsigned char bg_smem_raw[];
@@ -474,11 +484,12 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
         const bool staged = g.staged;
         const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
         const unsigned mg_r = (unsigned)S.tile[4], mg_w = (unsigned)S.tile[5], mg_a = (unsigned)S.tile[6];
-        if (!tables) stage_rotate<false, false>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
+        if (MTGV_BG_SKIP & 1) {}
+        else if (!tables) stage_rotate<false, false>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
         else if (pre_linear) stage_rotate<true, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
         else stage_rotate<false, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
         __syncthreads();
-        if (staged) {
+        if (staged && !(MTGV_BG_SKIP & 2)) {
           // ---- stage W: warp_inv output over the window + elementwise ops scheduled after the geometric group ----
           const int npx = WH * WW;
           const unsigned fast_w = rtw > 0 ? rtw - 1 : 0, fast_h = rth > 0 ? rth - 1 : 0;
@@ -532,14 +543,15 @@ __global__ void __launch_bounds__(kBgThreads, 2) k_background(const mtgv_enc_par
           }
         }
         __syncthreads();
-        if (!staged) stage_area_direct(S, b, ty0, ty1, tx0, tx1, by0, bw0, outp, OH, OW, tid);
+        if (MTGV_BG_SKIP & 4) {}
+        else if (!staged) stage_area_direct(S, b, ty0, ty1, tx0, tx1, by0, bw0, outp, OH, OW, tid);
         else if (max_nx <= 4) stage_area<4>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
         else if (max_nx <= 6) stage_area<6>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
         else stage_area<kAreaMaxTaps>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
       }
       if (t + 1 < n_tiles) {
         g = geom(t + 1);
-        setup(g);
+        if (!(MTGV_BG_SKIP & 8)) setup(g);
       }
       __syncthreads();
     }

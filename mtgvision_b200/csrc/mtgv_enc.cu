@@ -214,8 +214,9 @@ __device__ void vm_run_op(Vm& vm, const mtgv_x_op& op, int slot) {
       for (int k = tid; k < H * nblk; k += nt) persp_origin(op.d, (double)((k % nblk) * bw0), (double)(k / nblk), vm.aux + 4 * k);
       __syncthreads();
       const double m0 = op.d[0], m3 = op.d[3], m6 = op.d[6];
+      const int bw_shift = (bw0 & (bw0 - 1)) == 0 ? 31 - __clz(bw0) : -1;
       MTGV_FOR_PIXELS(i, x, y, H, W) {
-        const int bi = x / bw0;
+        const int bi = bw_shift >= 0 ? x >> bw_shift : x / bw0;
         const double* o = vm.aux + 4 * (y * nblk + bi);
         const int2 XY = persp_xy(o[0], o[1], o[2], m0, m3, m6, (double)(x - bi * bw0));
         oth[i] = bilinear_plane(cur, H, W, XY.x, XY.y);

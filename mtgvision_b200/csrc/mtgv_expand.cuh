@@ -343,8 +343,6 @@ MTGV_HD int expand_encoder_sample(const mtgv_enc_tape* t, const mtgv_enc_config*
   // INTER_AREA down-scale only (cv2 switches to a different kernel when enlarging); taps <= 8
   if (p->bg_rh < OH || p->bg_rw < OW || p->bg_rh > p->rot_nh || p->bg_rw > p->rot_nw) return p->status = MTGV_ERR_LIMIT;
   if (p->rot_nh > 6 * p->bg_rh || p->rot_nw > 6 * p->bg_rw) return p->status = MTGV_ERR_LIMIT;
-  // the rotate canvas' fixed-point tables share the free plane with the tile staging buffers
-  if (2 * (p->rot_nh + p->rot_nw) + kWTileCap + 2048 > OH * OW) return p->status = MTGV_ERR_LIMIT;
 
   for (int k = t->n_fg + t->n_bg; k < t->n_fg + t->n_bg + (bg_only ? 0 : t->n_vrtl); k++) {
     if (n >= MTGV_X_MAX_OPS) return p->status = MTGV_ERR_LIMIT;

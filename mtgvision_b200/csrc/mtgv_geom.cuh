@@ -48,7 +48,6 @@ constexpr int kInterTab = 32;
 constexpr int kAbBits = 10;
 constexpr int kAbScale = 1024;
 constexpr int kAreaMaxTaps = 8;  // supports INTER_AREA scale factors up to 6
-constexpr int kWTileCap = 6144;  // floats of warp_inv output staged per background tile (mtgv_enc.cu)
 
 // ---------------------------------------------------------------------------------------
 // cv::hal::LU64f + back substitution, n = 8, one right-hand side
