@@ -15,6 +15,7 @@
 
 #include "mtgv_det.cuh"
 #include "mtgv_internal.cuh"
+#include "mtgv_persp.cuh"
 
 namespace mtgv {
 
@@ -137,6 +138,22 @@ __device__ __forceinline__ float d_bilinear(float v0, float v1, float v2, float 
   return __fadd_rn(s, __fmul_rn(v3, fy * fx));
 }
 
+// cv2.warpPerspective coordinates of destination (x, y): block origin + guarded fast path (mtgv_persp.cuh)
+__device__ __forceinline__ int2 d_persp(const double* M, int x, int y, int bw0, int bw_shift) {
+  const int bxi = bw_shift >= 0 ? (x >> bw_shift) << bw_shift : (x / bw0) * bw0;
+  double o[3];
+  persp_origin(M, (double)bxi, (double)y, o);
+  return persp_xy(o[0], o[1], o[2], M[0], M[3], M[6], (double)(x - bxi));
+}
+
+// bilinear blend of four uint8 taps [b00 b01 b10 b11] with the 1/32-px weights, exact in integers
+// ((32-ax)(32-ay) ... sum to 1024), scaled to [0,1] once
+__device__ __forceinline__ float d_bilinear_u8(uint32_t taps, int ax, int ay) {
+  const unsigned pxw = (unsigned)(32 - ax) + ((unsigned)ax << 16);
+  const unsigned s = __dp2a_hi(pxw * (unsigned)ay, taps, __dp2a_lo(pxw * (unsigned)(32 - ay), taps, 0u));
+  return (float)s * (1.0f / (1024.0f * 255.0f));
+}
+
 // cv2.cvtColor(float32 RGB -> HSV): H in degrees [0,360), S, V in [0,1] (RGB2HSV_f, color_hsv.simd.hpp)
 __device__ __forceinline__ void d_rgb2hsv(float r, float g, float b, float* h, float* s, float* v) {
   float vmax = fmaxf(r, fmaxf(g, b)), vmin = fminf(r, fminf(g, b));
@@ -208,10 +225,13 @@ __device__ __forceinline__ void d_photo_point(const DetPhotoX& op, float* rgb, i
         const float* f = (const float*)(fields + op.field) + (size_t)p * 3;
         g[0] = f[0]; g[1] = f[1]; g[2] = f[2];
       } else {
-        uint32_t r[4], q[4];
-        d_philox(seed, op.slot, p, 0, r);
-        d_philox(seed, op.slot, p, 1, q);
-        g[0] = d_normal(r[0], r[1]); g[1] = d_normal(r[2], r[3]); g[2] = d_normal(q[0], q[1]);
+        uint32_t r[4];
+        d_philox(seed, op.slot, p, 0, r);  // one call: two Box-Muller pairs, three of the four normals used
+        const float rad0 = sqrtf(-2.f * __logf(((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f)));
+        const float rad1 = sqrtf(-2.f * __logf(((float)(r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f)));
+        float sn, cs;
+        sincospif(2.f * d_unit(r[1]), &sn, &cs);
+        g[0] = rad0 * cs; g[1] = rad0 * sn; g[2] = rad1 * cospif(2.f * d_unit(r[3]));
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) rgb[c] = dclip01(__fadd_rn(rgb[c], __fmul_rn(g[c], op.f[0])));
@@ -310,6 +330,7 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
   const int tiles_x = (S_w + kDetTW - 1) / kDetTW, tiles_y = (S_h + kDetTH - 1) / kDetTH, tiles = tiles_x * tiles_y;
   const int n_scenes = L.pass == 0 ? L.n : L.pass_count[L.pass];
   const int bw0 = persp_block_w(S_h, S_w);
+  const int bw_shift = (bw0 & (bw0 - 1)) == 0 ? 31 - __clz(bw0) : -1;
   for (long long work = blockIdx.x; work < (long long)n_scenes * tiles; work += gridDim.x) {
     const int li = (int)(work / tiles), tile = (int)(work - (long long)li * tiles);
     const int s = L.pass == 0 ? li : L.pass_list[(size_t)L.pass * L.n + li];
@@ -364,9 +385,20 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
         const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
         rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
         if (x >= S_w || y >= S_h) continue;
-        int X, Y;
-        persp_coord(T.bg_Minv, x, y, bw0, &X, &Y);
+        const int2 XY = d_persp(T.bg_Minv, x, y, bw0, bw_shift);
+        const int X = XY.x, Y = XY.y;
         const int sx = X >> 5, sy = Y >> 5;
+        if ((unsigned)sx < (unsigned)(bw - 1) && (unsigned)sy < (unsigned)(bh - 1)) {
+          // all four taps inside: RGBX words, channels blended exactly in integers
+          const uint32_t* p = src + (size_t)sy * pitchw + sx;
+          const uint32_t t0 = __ldg(p), t1 = __ldg(p + 1), t2 = __ldg(p + pitchw), t3 = __ldg(p + pitchw + 1);
+          const unsigned rg_t = __byte_perm(t0, t1, 0x5140), rg_b = __byte_perm(t2, t3, 0x5140);
+          const unsigned b_t = __byte_perm(t0, t1, 0x0062), b_b = __byte_perm(t2, t3, 0x0062);
+          rgb[i][0] = d_bilinear_u8(__byte_perm(rg_t, rg_b, 0x5410), X & 31, Y & 31);
+          rgb[i][1] = d_bilinear_u8(__byte_perm(rg_t, rg_b, 0x7632), X & 31, Y & 31);
+          rgb[i][2] = d_bilinear_u8(__byte_perm(b_t, b_b, 0x5410), X & 31, Y & 31);
+          continue;
+        }
         float v[4][3];
 #pragma unroll
         for (int t = 0; t < 4; t++) {
@@ -432,8 +464,8 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
         for (int q = 0; q < T.n_cull; q++) {
           const DetCardX& c = P.cards[T.cull[q]];
           if (x < c.x0 || x >= c.x1 || y < c.y0 || y >= c.y1) continue;
-          int X, Y;
-          persp_coord(c.Minv, x, y, bw0, &X, &Y);
+          const int2 XY = d_persp(c.Minv, x, y, bw0, bw_shift);
+          const int X = XY.x, Y = XY.y;
           const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
           if (sx < -1 || sx >= cw || sy < -1 || sy >= ch) continue;  // all four taps outside: mask = 0
           const bool x0 = sx >= 0, x1 = sx + 1 < cw, y0 = sy >= 0, y1 = sy + 1 < ch;
@@ -442,6 +474,20 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
                                      (y1 && x0) ? __ldg(mp + cw) : 0.f, (y1 && x1) ? __ldg(mp + cw + 1) : 0.f, X & 31, Y & 31);
           if (m == 0.f) continue;  // mask*img + (1-mask)*bg == bg exactly
           const uint8_t* base = L.card_planes + (size_t)c.card * 3 * ch * pitch;
+          const float im = __fsub_rn(1.f, m);
+          if (c.n_ops == 0 && x0 && x1 && y0 && y1) {
+            // no per-texel card augmentation and all four taps inside: integer bilinear per channel plane
+            const uint8_t* p = base + (size_t)sy * pitch + sx;
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) {
+              const uint8_t* q = p + (size_t)cc * ch * pitch;
+              const uint32_t taps = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + pitch) << 16) |
+                                    ((uint32_t)__ldg(q + pitch + 1) << 24);
+              const float w = d_bilinear_u8(taps, X & 31, Y & 31);
+              px_rgb[cc] = __fadd_rn(__fmul_rn(m, w), __fmul_rn(im, px_rgb[cc]));
+            }
+            continue;
+          }
           float v[4][3];
 #pragma unroll
           for (int t = 0; t < 4; t++) {
@@ -458,7 +504,6 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
               v[t][0] = v[t][1] = v[t][2] = 0.f;
             }
           }
-          const float im = __fsub_rn(1.f, m);
 #pragma unroll
           for (int cc = 0; cc < 3; cc++) {
             const float w = d_bilinear(v[0][cc], v[1][cc], v[2][cc], v[3][cc], X & 31, Y & 31);

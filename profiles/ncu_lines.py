@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """Per-source-line instruction and stall-sample shares of one kernel in an ncu report.
 
-    python profiles/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX [top_n]
+    python profiles/ncu_lines.py REPORT.ncu-rep KERNEL_REGEX [top_n] [launch_skip]
 """
 import csv, io, subprocess, sys
 
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 50
+skip = sys.argv[4] if len(sys.argv) > 4 else "0"  # launches of the kernel to skip inside the report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name",
-                      f"regex:{kern}", "--launch-count", "1"], capture_output=True, text=True).stdout
+                      f"regex:{kern}", "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = None
 items = []
