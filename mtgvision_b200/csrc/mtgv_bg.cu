@@ -594,11 +594,10 @@ size_t bg_image_bytes(int h, int w) { return (size_t)h * ((w + 3) & ~3) * 4; }
 
 int bg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* bg_out, cudaStream_t st) {
   if (OW > kBgMaxOW) return fail(ctx, MTGV_ERR_LIMIT, "x_size_hw width > 256");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attrs_set & 1u)) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_background, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgSmem)));
     MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->bg_blocks_per_sm, k_background, kBgThreads, sizeof(BgSmem)));
-    attr_set = true;
+    ctx->attrs_set |= 1u;
   }
   if (!ctx->bg_counter) MTGV_CUDA_OK(ctx, cudaMalloc(&ctx->bg_counter, 4));
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(ctx->bg_counter, 0, 4, st));

@@ -816,13 +816,12 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
   const int S_h = d->cfg.size_h, S_w = d->cfg.size_w;
   const size_t per = (size_t)S_h * S_w * 3;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
   static int blocks_per_sm = 1;
-  if (!attr_set) {
+  if (!(ctx->attrs_set & 2u)) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_det_pixels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetTileSmem)));
     MTGV_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_det_pixels, kDetBW * kDetBH, sizeof(DetTileSmem)));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    attr_set = true;
+    ctx->attrs_set |= 2u;
   }
   // scenes are processed in chunks so the blur scratch (2 float32 images per scene) stays bounded
   size_t chunk = ((size_t)3 << 30) / (per * 4 * 2);

@@ -1029,10 +1029,9 @@ static int enc_batch_sized(mtgv_ctx* ctx, const mtgv_enc_params* params, int n, 
     ctx->bg_cap = (size_t)chunk * 6 * HW;
   }
   float* fg_scratch = ctx->bg_scratch + (size_t)chunk * 3 * HW;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attrs_set & 4u)) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_encoder, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-    attr_set = true;
+    ctx->attrs_set |= 4u;
   }
   const size_t elem = out_dtype == MTGV_OUT_F16 ? 2 : (out_dtype == MTGV_OUT_U8 ? 1 : 4);
   for (int base = 0; base < n; base += chunk) {
@@ -1158,10 +1157,9 @@ int enc_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, con
   size_t smem = (((size_t)2 * h * w * 4 + 15) & ~(size_t)15) + ((vm_aux_bytes(h, w) + 15) & ~(size_t)15) + sizeof(mtgv_x_op) + 16;
   if ((int)smem > ctx->max_smem_optin) return fail(ctx, MTGV_ERR_LIMIT, "image too large for the plane interpreter");
   if (c < 1 || c > 4) return fail(ctx, MTGV_ERR_INVALID, "channels must be 1..4");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attrs_set & 8u)) {
     MTGV_CUDA_OK(ctx, cudaFuncSetAttribute(k_run_plane_ops, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin));
-    attr_set = true;
+    ctx->attrs_set |= 8u;
   }
   k_run_plane_ops<<<n * c, kThreads, smem, st>>>(img, h, w, c, ops, n_ops, (const uint32_t*)fields, seed);
   ctx->launches++;
