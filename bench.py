@@ -443,9 +443,65 @@ def run_det(args):
                       "gpu_launches": int(ctx.launch_count() - l0), "cpu_baseline": cpu}), flush=True)
 
 
+def run_dewarp(args):
+    """Serving-side dewarp (od_export.py:95-111): 32 detected cards of one 1080p uint8 frame per step."""
+    import cv2
+    import numpy as np
+    import torch
+
+    from mtgvision_b200.od_export import Dewarper
+
+    rng = np.random.default_rng(3)
+    H, W, n = 1080, 1920, 32
+    frame = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    quads = []
+    for _ in range(n):
+        cx, cy, s, a = rng.uniform(0.2, 0.8) * W, rng.uniform(0.2, 0.8) * H, rng.uniform(60, 200), rng.uniform(0, 6.283)
+        rot = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        quads.append((np.array([[-0.7, -1.0], [0.7, -1.0], [0.7, 1.0], [-0.7, 1.0]]) * s) @ rot.T + (cx, cy))
+    quads = np.stack(quads)
+    dw = Dewarper(device=0)
+    fd = torch.from_numpy(frame).cuda()
+    qd = torch.from_numpy(quads).cuda()
+    for _ in range(args.warmup):
+        dw.extract_dewarped(fd, qd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = dw.extract_dewarped(fd, qd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    # end to end: pinned frame in, pinned crops out
+    hf = torch.from_numpy(frame).pin_memory()
+    ho = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fd.copy_(hf, non_blocking=True)
+        ho.copy_(dw.extract_dewarped(fd, qd), non_blocking=True)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    cv2.setNumThreads(1)
+    dst = ((1 + 0.05) * np.asarray([[0, 0], [128, 0], [128, 192], [0, 192]]) - 0.025 * np.asarray([128, 192])).astype(np.float32)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        for q in quads:
+            cv2.warpPerspective(frame, cv2.getPerspectiveTransform(q.astype(np.float32), dst), (128, 192))
+    cpu = reps * n / (time.perf_counter() - t0)
+    out_bytes = n * 192 * 128 * 3
+    print(json.dumps({"metric": "dewarped cards/sec (1080p uint8 frame, 32 cards, 192x128 out)", "value": n / (ms * 1e-3), "unit": "cards/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "dtype": "u8",
+                      "config": {"workload": "dewarp", "frame": [H, W, 3], "cards": n},
+                      "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "cards/s", "h2d_bytes_per_step": int(frame.nbytes), "d2h_bytes_per_step": out_bytes},
+                      "cpu_baseline": {"value": cpu, "unit": "cards/s", "cores": 1, "kind": "reference",
+                                       "sample": f"cv2.getPerspectiveTransform + cv2.warpPerspective, {reps * n} cards, 1 thread"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="encoder", choices=["encoder", "det640", "det1280"])
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "det640", "det1280", "dewarp"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -457,7 +513,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.workload != "encoder":
+    if args.workload == "dewarp":
+        run_dewarp(args)
+    elif args.workload != "encoder":
         run_det(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -373,6 +373,18 @@ int mtgv_det_params_size(void);
  * albumentations calls (:552,581,604).  images: [n,3,S,S] NCHW of out_dtype. */
 int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int out_dtype, const void* fields, void* stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* Serving-side dewarp (mtgvision/od_export.py), SURVEY 8f.4                              */
+/* ------------------------------------------------------------------------------------ */
+
+/* InstanceSeg.extract_dewarped (od_export.py:95-111) for n detected cards of one frame:
+ * M_k = cv2.getPerspectiveTransform(quads[k] float32 (4 corners x,y), dst_rect float32 (4 corners of
+ * the expanded output rectangle, computed by the caller like :102-104)), then
+ * cv2.warpPerspective(frame uint8 HWC with c = 1..4 channels, M_k, (ow, oh)) - INTER_LINEAR, constant 0 border,
+ * uint8 fixed-point blend.  out: [n, oh, ow, c] uint8.  Needs no pool or config.  Bit-exact. */
+int mtgv_extract_dewarped(mtgv_ctx* ctx, const uint8_t* frame, int frame_h, int frame_w, int channels, const float* quads,
+                          int n, const float* dst_rect, uint8_t* out, int out_h, int out_w, void* stream);
+
 /* Number of kernels launched by this context since creation (bench bookkeeping). */
 int64_t mtgv_launch_count(const mtgv_ctx* ctx);
 

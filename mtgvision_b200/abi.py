@@ -157,6 +157,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "mtgv_encoder_targets": (i32, [vp, vp, i32, vp, i32, vp]),
         "mtgv_warp_perspective": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
         "mtgv_run_plane_ops": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, vp, u64, vp]),
+        "mtgv_extract_dewarped": (i32, [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]),
         "mtgv_launch_count": (i64, [vp]),
     }
     for name, (res, args) in protos.items():

@@ -219,6 +219,24 @@ class Context:
         self._check(rc, "mtgv_det_batch")
         return out
 
+    # ------------------------------------------------------------------ serving-side dewarp
+    def extract_dewarped(self, frame: torch.Tensor, quads: torch.Tensor, out_size_hw=(192, 128), expand_ratio: float = 0.05) -> torch.Tensor:
+        """InstanceSeg.extract_dewarped (mtgvision/od_export.py:95-111) for every detected card of a frame.
+        frame (H,W,C) uint8; quads (n,4,2) corner points ordered like `xyxyxyxy`; returns (n,h,w,C) uint8 on the device."""
+        frame = frame.to(self.device, dtype=torch.uint8).contiguous()
+        assert frame.ndim == 3 and 1 <= frame.shape[2] <= 4
+        quads = torch.as_tensor(quads).to(torch.float32).reshape(-1, 8).to(self.device).contiguous()  # .astype(np.float32) (:106)
+        h, w = int(out_size_hw[0]), int(out_size_hw[1])
+        # dst_pts = (1 + r) * [[0,0],[w,0],[w,h],[0,h]] - 0.5 * r * [w,h] in float64, then float32 (:101-107)
+        dst = (1.0 + expand_ratio) * np.asarray([[0, 0], [w, 0], [w, h], [0, h]]) - (0.5 * expand_ratio) * np.asarray([w, h])
+        dst_t = torch.from_numpy(dst.astype(np.float32).reshape(8)).to(self.device)
+        n = quads.shape[0]
+        out = torch.empty((n, h, w, frame.shape[2]), dtype=torch.uint8, device=self.device)
+        rc = self.lib.mtgv_extract_dewarped(self._h, _ptr(frame), frame.shape[0], frame.shape[1], frame.shape[2], _ptr(quads), n,
+                                            _ptr(dst_t), _ptr(out), h, w, self._stream())
+        self._check(rc, "mtgv_extract_dewarped")
+        return out
+
     # ------------------------------------------------------------------ parity / debug entries
     def warp_perspective(self, src: torch.Tensor, M: torch.Tensor, dsize_hw) -> torch.Tensor:
         """src (n,h,w,c) float32, M (n,3,3) float64 -> (n,dh,dw,c) float32, cv2.warpPerspective semantics."""

@@ -260,6 +260,17 @@ int mtgv_warp_perspective(mtgv_ctx* ctx, const float* src, int n, int sh, int sw
   return enc_warp_perspective(ctx, src, n, sh, sw, c, M, dst, dh, dw, (cudaStream_t)stream);
 }
 
+int mtgv_extract_dewarped(mtgv_ctx* ctx, const uint8_t* frame, int frame_h, int frame_w, int channels, const float* quads, int n,
+                          const float* dst_rect, uint8_t* out, int out_h, int out_w, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (n == 0) return MTGV_OK;
+  if (!frame || !quads || !dst_rect || !out || n < 0 || frame_h < 1 || frame_w < 1 || out_h < 1 || out_w < 1 || channels < 1 ||
+      channels > 4)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_extract_dewarped: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return dewarp_u8(ctx, frame, frame_h, frame_w, channels, quads, n, dst_rect, out, out_h, out_w, (cudaStream_t)stream);
+}
+
 int mtgv_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops, const void* fields,
                        uint64_t seed, void* stream) {
   if (!ctx) return MTGV_ERR_INVALID;

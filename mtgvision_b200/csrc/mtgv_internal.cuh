@@ -136,6 +136,9 @@ int pool_planarize(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* planes, int n, in
 // mtgv_bg.cu
 int pool_interleave(mtgv_ctx* ctx, const uint8_t* hwc, uint8_t* words, int n, int h, int w, cudaStream_t st);
 size_t bg_image_bytes(int h, int w);
+// mtgv_dewarp.cu
+int dewarp_u8(mtgv_ctx* ctx, const uint8_t* frame, int fh, int fw, int fc, const float* quads, int n, const float* dst_rect,
+              uint8_t* out, int oh, int ow, cudaStream_t st);
 // mtgv_fg.cu
 int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* fg_out, cudaStream_t st);
 int bg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* bg_out, cudaStream_t st);

@@ -262,6 +262,27 @@ def warp_perspective(src: np.ndarray, M: np.ndarray, dsize_wh) -> np.ndarray:
     return remap_bilinear_fixed(src, X, Y)
 
 
+def warp_perspective_u8(src: np.ndarray, M: np.ndarray, dsize_wh) -> np.ndarray:
+    """cv2.warpPerspective on uint8 images (od_export.py:108, the serving-side dewarp): same
+    coordinates as the float path, but remapBilinear's fixed-point blend: the four weights are
+    saturate_cast<short>(w * 32768) = 32*(32-ax|ax)*(32-ay|ay) (exact, they sum to 32768) and the
+    pixel is (sum(tap * weight) + 2^14) >> 15; taps outside the source are 0."""
+    assert src.dtype == np.uint8 and src.ndim == 3
+    X, Y = warp_perspective_coords(invert3x3(M), dsize_wh)
+    sh, sw = src.shape[:2]
+    sx = np.clip(X >> INTER_BITS, -32768, 32767)
+    sy = np.clip(Y >> INTER_BITS, -32768, 32767)
+    ax, ay = X & (INTER_TAB_SIZE - 1), Y & (INTER_TAB_SIZE - 1)
+    acc = np.zeros((*X.shape, src.shape[2]), dtype=np.int64)
+    weights = (32 * (32 - ax) * (32 - ay), 32 * ax * (32 - ay), 32 * (32 - ax) * ay, 32 * ax * ay)
+    for wgt, (dy, dx) in zip(weights, ((0, 0), (0, 1), (1, 0), (1, 1))):
+        yy, xx = sy + dy, sx + dx
+        ok = (yy >= 0) & (yy < sh) & (xx >= 0) & (xx < sw)
+        tap = np.where(ok[..., None], src[np.clip(yy, 0, sh - 1), np.clip(xx, 0, sw - 1)].astype(np.int64), 0)
+        acc += tap * wgt[..., None]
+    return ((acc + (1 << 14)) >> 15).astype(np.uint8)
+
+
 def warp_affine_coords(Ainv: np.ndarray, dsize_wh) -> tuple[np.ndarray, np.ndarray]:
     """WarpAffineInvoker coordinate generation: 10-bit fixed point per row/column
     tables, result in 1/32 px.  saturate_cast<int>(double) is round-half-even."""

@@ -83,3 +83,18 @@ def test_resize_small_kernels_within_tolerance(rng):
     k = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]])
     assert np.abs(cv2.filter2D(img, -1, k) - R.sharpen3(img)).max() <= 2e-6
     assert np.array_equal(cv2.getGaussianKernel(3, 0).ravel(), [0.25, 0.5, 0.25])
+
+
+def test_warp_perspective_u8_fixed_point_bit_exact():
+    """uint8 warpPerspective (serving-side dewarp, od_export.py:108): remapBilinear's 15-bit fixed point."""
+    rng = np.random.default_rng(5)
+    for t in range(12):
+        H, W = int(rng.integers(200, 700)), int(rng.integers(200, 800))
+        src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        quad = np.float32([[W * .2, H * .2], [W * .8, H * .25], [W * .75, H * .8], [W * .15, H * .7]]) + rng.uniform(-40, 40, (4, 2)).astype(np.float32)
+        if t % 4 == 0:
+            quad[0] = (-30, -20)
+        h, w = 192, 128
+        dst = ((1 + 0.05) * np.asarray([[0, 0], [w, 0], [w, h], [0, h]]) - 0.025 * np.asarray([w, h])).astype(np.float32)
+        M = cv2.getPerspectiveTransform(quad, dst)
+        assert np.array_equal(R.warp_perspective_u8(src, M, (w, h)), cv2.warpPerspective(src, M, (w, h)))
