@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(kPlaceWarps * 32) k_det_place(const mtgv_det_t
                                                                 DetParams* params, int32_t* accepted, double* keypoints,
                                                                 int32_t* labels, int32_t* counts) {
   __shared__ DetPlaceState s_state[kPlaceWarps];
-  __shared__ double s_M[kPlaceWarps][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * kPlaceWarps + warp;
   if (s >= n) return;
@@ -114,7 +113,6 @@ __global__ void __launch_bounds__(kPlaceWarps * 32) k_det_place(const mtgv_det_t
     counts[s] = n_placed * kp->n_poly;
     det_emit_program(t, cfg, P);
   }
-  (void)s_M;
 }
 
 // ------------------------------------------------------------------------------------ //
@@ -196,9 +194,6 @@ __device__ __forceinline__ void d_philox(uint64_t seed, int slot, uint32_t idx, 
   ph(idx, sub, 0x6d746776u, 0, r);
 }
 __device__ __forceinline__ float d_unit(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
-__device__ __forceinline__ float d_normal(uint32_t a, uint32_t b) {
-  return sqrtf(-2.f * logf(((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f))) * cospif(2.f * d_unit(b));
-}
 
 // pointwise photometric op on one RGB pixel at (y, x) of an image of width W (od_datasets.py:420-512)
 __device__ __forceinline__ void d_photo_point(const DetPhotoX& op, float* rgb, int y, int x, int W, uint64_t seed,

@@ -72,11 +72,6 @@ __device__ __forceinline__ void field_draw(uint64_t seed, int slot, uint32_t pix
   ph.key[1] = (uint32_t)(seed >> 32);
   ph(pixel, chan, sub, 0x6d746776u, r);
 }
-__device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
-  float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  float u2 = u32_to_unit(b);
-  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
-}
 
 // four standard normals from one Philox call (two Box-Muller pairs)
 __device__ __forceinline__ void normals4(const uint32_t* r, float* g) {
@@ -935,7 +930,6 @@ __global__ void k_sample_tape(uint64_t seed, int64_t first, int n_pairs, const m
   if (bgs) bg = bgs[i];
   if (p_tii < 0.0) p_tii = cfg->target_is_input_prob;
   if (p_neg < 0.0) p_neg = cfg->similar_neg_prob;
-  const int n_x = cfg->paired ? 2 : 1;
   for (int which = only; which <= only; which++) {
     mtgv_enc_tape* t = &tape[which * n_pairs + i];
     Rng r(seed, g, 2 + which);
