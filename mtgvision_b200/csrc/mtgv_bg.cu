@@ -493,14 +493,15 @@ __global__ void __launch_bounds__(kBgThreads, kBgCtas) k_background(const mtgv_e
           // ---- stage W: warp_inv output over the window + elementwise ops scheduled after the geometric group ----
           const int npx = WH * WW;
           const unsigned fast_w = rtw > 0 ? rtw - 1 : 0, fast_h = rth > 0 ? rth - 1 : 0;
-          auto coords = [&](int k) {
+          auto coords = [&](int k, int2* XY) {  // returns false when the exact routine has to decide
             const int r = div_by(k, mg_w), cx = k - r * WW;
             const int wx = wx0 + cx;
             const PerspSeg sg = S.seg[r * nseg + ((wx >> kPerspSegShift) - seg0)];
-            int2 XY;
-            if (!persp_seg_eval(sg, (float)((wx & ((1 << kPerspSegShift) - 1)) - (1 << (kPerspSegShift - 1))), &XY.x, &XY.y))
-              XY = persp_coord_nl(S.winv, wx, wy0 + r, bw0);
-            return XY;
+            return persp_seg_eval(sg, (float)((wx & ((1 << kPerspSegShift) - 1)) - (1 << (kPerspSegShift - 1))), &XY->x, &XY->y);
+          };
+          auto coords_exact = [&](int k) {
+            const int r = div_by(k, mg_w);
+            return persp_coord_nl(S.winv, wx0 + (k - r * WW), wy0 + r, bw0);
           };
           auto finish = [&](int k, int2 XY) {
             const int sx = XY.x >> 5, sy = XY.y >> 5;
@@ -534,11 +535,18 @@ __global__ void __launch_bounds__(kBgThreads, kBgCtas) k_background(const mtgv_e
             }
             S.wtile[0][k] = v[0]; S.wtile[1][k] = v[1]; S.wtile[2][k] = v[2];
           };
-          for (int k = tid; k < npx; k += 2 * nt) {
-            const int k2 = k + nt;
-            const bool two = k2 < npx;
-            const int2 xa = coords(k), xb = coords(two ? k2 : k);
-            finish(k, xa);
+          // the trip count is uniform over the warp (inactive lanes recompute pixel 0 and store nothing), so the rare
+          // exact-coordinate fallback sits behind one warp vote instead of per-lane divergence bookkeeping
+          for (int kb = 0; kb < npx; kb += 2 * nt) {
+            const int k = kb + tid, k2 = k + nt;
+            const bool one = k < npx, two = k2 < npx;
+            int2 xa, xb;
+            const bool oka = coords(one ? k : 0, &xa), okb = coords(two ? k2 : 0, &xb);
+            if (__any_sync(0xffffffffu, !(oka && okb))) {
+              if (!oka) xa = coords_exact(one ? k : 0);
+              if (!okb) xb = coords_exact(two ? k2 : 0);
+            }
+            if (one) finish(k, xa);
             if (two) finish(k2, xb);
           }
         }

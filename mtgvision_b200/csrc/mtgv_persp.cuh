@@ -92,13 +92,19 @@ static __device__ __forceinline__ void persp_seg_build(const double* M, int seg,
 }
 
 // u = column - reference column of the segment.  Returns false when the exact routine must decide.
+// Rounding by the 1.5 * 2^23 trick: (s + K) - K is rint(s) for |s| < 2^22, and the low mantissa bits of
+// s + K are that integer.
 static __device__ __forceinline__ bool persp_seg_eval(const PerspSeg& s, float u, int* X, int* Y) {
-  const float q = __fdividef(u, __fmaf_rn(s.e, u, 1.f));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmaf_rn(s.e, u, 1.f)));  // |e * u| <= 1/4: no denormals, 1 ulp
+  const float q = u * r;
   const float sx = __fmaf_rn(q, s.dx, s.fx), sy = __fmaf_rn(q, s.dy, s.fy);
-  const float rx = rintf(sx), ry = rintf(sy);
-  *X = s.xc + (int)rx;
-  *Y = s.yc + (int)ry;
-  return fabsf(sx - rx) < 0.5f - kPerspGuard && fabsf(sy - ry) < 0.5f - kPerspGuard;  // false for NaN
+  const float K = 12582912.f;
+  const float kx = sx + K, ky = sy + K;
+  *X = s.xc + (__float_as_int(kx) - 0x4B400000);
+  *Y = s.yc + (__float_as_int(ky) - 0x4B400000);
+  const float ex = fabsf(sx - (kx - K)), ey = fabsf(sy - (ky - K));
+  return ex < 0.5f - kPerspGuard && ey < 0.5f - kPerspGuard;  // false for NaN (degenerate segments carry NaN slopes)
 }
 
 }  // namespace mtgv
