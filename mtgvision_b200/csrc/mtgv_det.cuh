@@ -136,16 +136,32 @@ MTGV_HDN bool det_visible(const double* kp0, int kind, int size_h, int size_w, c
   const double vis_area = det_shape_area(quad, indent, img, 4);
   if (MTGV_DDIV(vis_area, card_area) < min_visible_edge) return false;
   bool visible = true;
+  // loop invariants: the candidate clipped to the frame, and its bounding box
+  double vis_pts[2 * kPolyMax];
+  const int nv = clip_convex(quad, 4, img, 4, vis_pts);
+  double qx0 = quad[0], qx1 = quad[0], qy0 = quad[1], qy1 = quad[1];
+  for (int k = 1; k < 4; k++) {
+    qx0 = fmin(qx0, quad[2 * k]); qx1 = fmax(qx1, quad[2 * k]);
+    qy0 = fmin(qy0, quad[2 * k + 1]); qy1 = fmax(qy1, quad[2 * k + 1]);
+  }
   for (int e = 0; e < n_existing; e++) {
     const double* pq = existing + 8 * e;
+    {
+      // Strictly separated bounding boxes: the polygons are disjoint, so the intersection is empty (inter = 0: both
+      // area tests reduce to ones that already passed) and neither contains the other - nothing can reject here.
+      double px0 = pq[0], px1 = pq[0], py0 = pq[1], py1 = pq[1];
+      for (int k = 1; k < 4; k++) {
+        px0 = fmin(px0, pq[2 * k]); px1 = fmax(px1, pq[2 * k]);
+        py0 = fmin(py0, pq[2 * k + 1]); py1 = fmax(py1, pq[2 * k + 1]);
+      }
+      if (px1 < qx0 || qx1 < px0 || py1 < qy0 || qy1 < py0) continue;
+    }
     double pc[2 * kPolyMax];
     int npc = clip_convex(pq, 4, img, 4, pc);
     double inter = npc >= 3 ? det_shape_area(quad, indent, pc, npc) : 0.0;
     if (MTGV_DDIV(MTGV_DSUB(vis_area, inter), card_area) < min_visible) { visible = false; break; }
     double p_area = poly_area(pq, 4);
     if (MTGV_DDIV(MTGV_DSUB(p_area, inter), p_area) < min_visible) { visible = false; break; }
-    double vis_pts[2 * kPolyMax];
-    int nv = clip_convex(quad, 4, img, 4, vis_pts);
     bool p_contains_vis = nv >= 3;
     for (int k = 0; k < nv && p_contains_vis; k++) p_contains_vis = poly_inside_convex(vis_pts[2 * k], vis_pts[2 * k + 1], pq, 4);
     bool vis_contains_p = true;
