@@ -202,7 +202,8 @@ int mtgv_set_card_pool(mtgv_ctx* ctx, const uint8_t* cards, int n, int h, int w,
                        const int32_t* grp_off, const int32_t* grp_mem, int n_mem);
 
 /* Background pool: replaces IlsvrcImages._load_image (encoder_datasets.py:457-474).
- * bgs: concatenated HWC uint8 images (device); offsets[n] byte offsets; hw[n][2]. */
+ * bgs: concatenated HWC uint8 images (device); offsets[n] byte offsets; hw[n][2].  The library keeps
+ * its own copy as RGBX words (one 4-byte load per bilinear tap). */
 int mtgv_set_bg_pool(mtgv_ctx* ctx, const uint8_t* bgs, const int64_t* offsets_host, const int32_t* hw_host, int n);
 
 int mtgv_set_encoder_config(mtgv_ctx* ctx, const mtgv_enc_config* cfg_host);

@@ -1,19 +1,20 @@
-// mtgv_enc.cu - encoder-pair generator kernels for sm_100a.
+// mtgv_enc.cu - k_encoder (the plane interpreter of the encoder-pair generator), the tape sampler,
+// the parameter expansion launch and the batch driver for sm_100a.
 //
-// One persistent CTA per SM walks a work queue of (sample, plane) items.  A plane is one
-// channel of one augmented sample held entirely in shared memory as float32
-// (2 ping-pong planes of out_h*out_w*4 B = 2*96 KiB for 192x128): every stage of the
-// reference pipeline (area resize -> downscale/upscale -> warp -> photometrics ->
-// background chain -> composite -> shuffled post-augments) runs on-chip and the only HBM
-// traffic is the uint8 card/background source read and the NCHW fp16/u8 plane write.
-// The three colour planes and the alpha plane of a sample are independent except at the
-// composite, where colour CTAs consume the alpha plane published by the alpha CTA
-// (L2 scratch + release/acquire flag; the queue order guarantees the producer is running).
+// One encoder batch = k_sample_tape -> k_expand -> [k_background (mtgv_bg.cu) | k_foreground
+// (mtgv_fg.cu)] -> k_encoder.  The first two pixel kernels write float32 planes to scratch; k_encoder
+// runs one persistent CTA per SM over a work queue of (sample, plane) items.  A plane is one channel
+// of one augmented sample held entirely in shared memory as float32 (2 ping-pong planes of
+// out_h*out_w*4 B = 2*96 KiB for 192x128): the foreground ops (downscale/upscale, warp, photometrics),
+// the composite over the background plane and the shuffled post-augments all run on-chip, and the
+// plane leaves as NCHW fp16/u8.  The three colour planes and the alpha plane of a sample are
+// independent except at the composite, where colour CTAs consume the alpha plane published by the alpha
+// CTA (L2 scratch + release/acquire flag; the queue order guarantees the producer is running).
 //
-// Reference semantics (mtgvision/encoder_datasets.py, mtgvision/util/image.py) are cited
-// at each stage; the cv2 arithmetic follows SURVEY.md section 8a-notes and is restated in
-// oracle/cv2_restate.py.  Compiled with -fmad=false: every float multiply/add below is a
-// separate rounding, as in the reference's numpy / OpenCV scalar code.
+// Reference semantics (mtgvision/encoder_datasets.py, mtgvision/util/image.py) are cited at each
+// stage; the cv2 arithmetic follows SURVEY.md section 8a-notes and is restated in
+// oracle/cv2_restate.py.  Compiled with -fmad=false; fused multiply-adds appear only where written
+// explicitly (value paths, see DESIGN.md "What is exact and what is toleranced").
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
