@@ -649,6 +649,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_encoder(EncLaunch L, int OH, in
       continue;
     }
     const bool bg_only = sp.kind == MTGV_KIND_BG_ONLY;
+    if (sp.kind != MTGV_KIND_CROPPED) {
+      // the composite reads this sample's background plane (and the static alpha) some microseconds from now:
+      // pull the lines into L2 while the foreground ops run
+      const char* bgp = (const char*)(L.bg_scratch + ((size_t)s * 3 + plane) * HW);
+      for (int o = tid * 128; o < HW * 4; o += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(bgp + o));
+    }
     stage_load_fg(S.P0, OH, OW, L.fg_scratch + ((size_t)fg_plane_owner(L.params, L.n, s) * 3 + plane) * HW, bg_only, sp.fg_y0, sp.fg_y0 + sp.fg_rh, sp.fg_x0,
                   sp.fg_x0 + sp.fg_rw);
     __syncthreads();
