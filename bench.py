@@ -343,7 +343,7 @@ def run_cuda(args):
                "ms_per_step": float(e_ms.item()) / e2e_steps,
                "h2d_gbs_needed_at_this_rate": h2d * e2e_steps / (float(e_ms.item()) * 1e-3) / 1e9,
                "api": "RanMtgEncDecDataset.host_tensor_batches (pinned uint8 cards+backgrounds in, pinned fp16 x/x2 + int64 labels out; "
-                      "upload of batch i+1 / kernels of batch i / download of batch i-1 overlap on three streams; "
+                      "upload + pool ingest of batch i+1 / kernels of batch i / download of batch i-1 overlap on four streams; "
                       "timed = max(CUDA events, host wall clock) over all steps including pipeline fill and drain)"}
 
     # ---- context only: the training-loop call (pool resident, nothing uploaded), batch read back to pinned host ----

@@ -163,8 +163,8 @@ class RanMtgEncDecDataset(IterableDataset):
         uint8 CPU tensors (pinned for full copy speed), one pair per batch, all of one batch size n;
         the generator yields one dict of pinned host tensors per pair, in order.
 
-        Three CUDA streams overlap the upload of batch i+1, the kernels of batch i and the
-        download of batch i-1 (what the reference's DataLoader workers do with processes,
+        Four CUDA streams overlap the upload of batch i+1 (and its conversion into the pool
+        layout), the kernels of batch i and the download of batch i-1 (what the reference's DataLoader workers do with processes,
         encoder_train.py:517-523).  Batches alternate between pool slots [0, n) and [n, 2n), so
         both pools need at least 2n entries.  A yielded dict is valid until the generator is
         advanced again (its buffers are the double-buffered download targets)."""
@@ -173,10 +173,10 @@ class RanMtgEncDecDataset(IterableDataset):
         with torch.cuda.device(dev):
             if getattr(self, "_pipe_streams", None) is None:
                 # persistent: the caching allocator keeps one block pool per stream, new streams would cudaMalloc again
-                self._pipe_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-            s_in, s_k, s_out = self._pipe_streams
+                self._pipe_streams = tuple(torch.cuda.Stream(dev) for _ in range(4))
+            s_in, s_pl, s_k, s_out = self._pipe_streams  # upload | pool ingest | kernels | download
             main = torch.cuda.current_stream(dev)
-            for s in (s_in, s_k, s_out):
+            for s in (s_in, s_pl, s_k, s_out):
                 s.wait_stream(main)
             slots = getattr(self, "_pipe_slots", [])  # staging + pinned buffers persist across calls
             pending = []
@@ -193,7 +193,8 @@ class RanMtgEncDecDataset(IterableDataset):
                             "cards": torch.empty(card_images.shape, dtype=torch.uint8, device=dev),
                             "bgs": torch.empty(bg_images.shape, dtype=torch.uint8, device=dev),
                             "idx": torch.arange(j * n, (j + 1) * n, dtype=torch.int32, device=dev),
-                            "k_done": torch.cuda.Event(), "in_done": torch.cuda.Event(), "out_done": torch.cuda.Event(),
+                            "k_done": torch.cuda.Event(), "copy_done": torch.cuda.Event(), "in_done": torch.cuda.Event(),
+                            "out_done": torch.cuda.Event(),
                             "host": {}, "dev": None,
                         })
                 sl = slots[i % 2]
@@ -202,9 +203,13 @@ class RanMtgEncDecDataset(IterableDataset):
                 with torch.cuda.stream(s_in):
                     sl["cards"].copy_(card_images, non_blocking=True)
                     sl["bgs"].copy_(bg_images, non_blocking=True)
+                    sl["copy_done"].record(s_in)
+                # the layout conversion into the pools runs on its own stream so the next upload starts right away
+                s_pl.wait_event(sl["copy_done"])
+                with torch.cuda.stream(s_pl):
                     ctx.update_card_images(sl["cards"], (i % 2) * n)
                     ctx.update_bg_images(sl["bgs"], (i % 2) * n)
-                    sl["in_done"].record(s_in)
+                    sl["in_done"].record(s_pl)
                 s_k.wait_event(sl["in_done"])
                 s_k.wait_event(sl["out_done"])  # the previous download from this slot's device batch is finished
                 with torch.cuda.stream(s_k):
