@@ -105,6 +105,7 @@ int mtgv_set_card_pool(mtgv_ctx* ctx, const uint8_t* cards, int n, int h, int w,
     MTGV_CUDA_OK(ctx, cudaMemcpy(*dst[k], m.data(), (size_t)h * w * 4, cudaMemcpyHostToDevice));
   }
   ctx->n_cards = n;
+  ctx->card_epoch++;
   rc = enc_build_static_alpha(ctx, 0);
   if (rc) return rc;
   MTGV_CUDA_OK(ctx, cudaDeviceSynchronize());
@@ -185,6 +186,7 @@ int mtgv_update_card_images(mtgv_ctx* ctx, const uint8_t* cards, int first, int 
   if (!cards || first < 0 || n < 0 || first + n > ctx->n_cards)
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_update_card_images: range outside the pool");
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  ctx->card_epoch++;
   return pool_planarize(ctx, cards, ctx->card_planes + (size_t)first * 3 * ctx->card_h * ctx->card_pitch, n, ctx->card_h,
                         ctx->card_w, ctx->card_pitch, (cudaStream_t)stream);
 }

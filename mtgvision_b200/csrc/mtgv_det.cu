@@ -29,6 +29,11 @@ struct DetState {
   size_t scratch_cap = 0;  // floats per buffer
   int32_t* lists = nullptr;  // pass_count[kDetMaxBlur+1] followed by pass_list[kDetMaxBlur+1][chunk]
   size_t list_cap = 0;
+  // detection's own card copy: RGBA words [n][h][w], A = round_rect_mask(card_hw, 0.046) * 255 - image and mask
+  // of make_card_with_mask (od_datasets.py:218-235) are warped by the same matrix, one 4-byte load per tap serves both
+  uint32_t* card_rgba = nullptr;
+  size_t rgba_cap = 0;
+  uint64_t rgba_epoch = 0;
 };
 
 static DetState* det_state(mtgv_ctx* ctx) {
@@ -39,7 +44,7 @@ static DetState* det_state(mtgv_ctx* ctx) {
 int det_destroy(mtgv_ctx* ctx) {
   if (!ctx->det) return MTGV_OK;
   DetState* d = (DetState*)ctx->det;
-  cudaFree(d->cfg_dev); cudaFree(d->kp_dev); cudaFree(d->scratch[0]); cudaFree(d->scratch[1]); cudaFree(d->lists);
+  cudaFree(d->cfg_dev); cudaFree(d->kp_dev); cudaFree(d->scratch[0]); cudaFree(d->scratch[1]); cudaFree(d->lists); cudaFree(d->card_rgba);
   delete d;
   ctx->det = nullptr;
   return MTGV_OK;
@@ -256,6 +261,19 @@ __device__ __forceinline__ void d_photo_point(const DetPhotoX& op, float* rgb, i
   }
 }
 
+__global__ void k_det_rgba(const uint8_t* __restrict__ planes, int pitch, const float* __restrict__ mask, uint32_t* __restrict__ rgba,
+                           int h, int w) {
+  const size_t card = blockIdx.y;
+  const uint8_t* src = planes + card * 3 * (size_t)h * pitch;
+  uint32_t* dst = rgba + card * (size_t)h * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h * w; i += gridDim.x * blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    const uint8_t* p = src + (size_t)y * pitch + x;
+    const uint32_t a = mask[i] != 0.f ? 255u : 0u;  // the mask is {0,1}-valued (cv::circle fill)
+    dst[i] = (uint32_t)p[0] | ((uint32_t)p[(size_t)h * pitch] << 8) | ((uint32_t)p[2 * (size_t)h * pitch] << 16) | (a << 24);
+  }
+}
+
 // ------------------------------------------------------------------------------------ //
 // pixel kernel                                                                          //
 // ------------------------------------------------------------------------------------ //
@@ -270,9 +288,8 @@ struct DetLaunch {
   int n, pass;
   const int32_t* pass_count;  // [kDetMaxBlur + 1] scenes that have a pass p (pass 0: all scenes, no list)
   const int32_t* pass_list;   // [kDetMaxBlur + 1][n]
-  const uint8_t* card_planes;
-  int card_h, card_w, card_pitch;
-  const float* mask;  // round_rect_mask(card_hw, 0.046)
+  const uint32_t* card_rgba;  // [n][h][w] RGBA words, A = mask * 255
+  int card_h, card_w;
   const uint8_t* bg_planes;
   const int64_t* bg_off;
   const int32_t* bg_hw;
@@ -443,7 +460,7 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
       }
     }
 
-    const int ch = L.card_h, cw = L.card_w, pitch = L.card_pitch;
+    const int ch = L.card_h, cw = L.card_w;
 #pragma unroll
     for (int i = 0; i < kDetRows; i++) {
       const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
@@ -464,35 +481,38 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
           const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
           if (sx < -1 || sx >= cw || sy < -1 || sy >= ch) continue;  // all four taps outside: mask = 0
           const bool x0 = sx >= 0, x1 = sx + 1 < cw, y0 = sy >= 0, y1 = sy + 1 < ch;
-          const float* mp = L.mask + (long long)sy * cw + sx;
-          const float m = d_bilinear((y0 && x0) ? __ldg(mp) : 0.f, (y0 && x1) ? __ldg(mp + 1) : 0.f,
-                                     (y1 && x0) ? __ldg(mp + cw) : 0.f, (y1 && x1) ? __ldg(mp + cw + 1) : 0.f, X & 31, Y & 31);
+          const uint32_t* tp = L.card_rgba + (size_t)c.card * ch * cw + (long long)sy * cw + sx;
+          const uint32_t t0 = (y0 && x0) ? __ldg(tp) : 0u, t1 = (y0 && x1) ? __ldg(tp + 1) : 0u;
+          const uint32_t t2 = (y1 && x0) ? __ldg(tp + cw) : 0u, t3 = (y1 && x1) ? __ldg(tp + cw + 1) : 0u;
+          const int ax = X & 31, ay = Y & 31;
+          // mask: {0,255} bytes blended exactly; taps outside the card are 0 like the warp's constant border
+          const unsigned mtaps = (__byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410) >> 7) & 0x01010101u;
+          const unsigned pxw = (unsigned)(32 - ax) + ((unsigned)ax << 16);
+          const float m = (float)__dp2a_hi(pxw * (unsigned)ay, mtaps, __dp2a_lo(pxw * (unsigned)(32 - ay), mtaps, 0u)) * (1.0f / 1024.0f);  // exact
           if (m == 0.f) continue;  // mask*img + (1-mask)*bg == bg exactly
-          const uint8_t* base = L.card_planes + (size_t)c.card * 3 * ch * pitch;
           const float im = __fsub_rn(1.f, m);
-          if (c.n_ops == 0 && x0 && x1 && y0 && y1) {
-            // no per-texel card augmentation and all four taps inside: integer bilinear per channel plane
-            const uint8_t* p = base + (size_t)sy * pitch + sx;
-#pragma unroll
-            for (int cc = 0; cc < 3; cc++) {
-              const uint8_t* q = p + (size_t)cc * ch * pitch;
-              const uint32_t taps = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + pitch) << 16) |
-                                    ((uint32_t)__ldg(q + pitch + 1) << 24);
-              const float w = d_bilinear_u8(taps, X & 31, Y & 31);
-              px_rgb[cc] = __fadd_rn(__fmul_rn(m, w), __fmul_rn(im, px_rgb[cc]));
-            }
+          if (c.n_ops == 0) {
+            // no per-texel card augmentation: integer bilinear per channel (outside taps are 0, as in the float path)
+            const unsigned rg_t = __byte_perm(t0, t1, 0x5140), rg_b = __byte_perm(t2, t3, 0x5140);
+            const unsigned b_t = __byte_perm(t0, t1, 0x0062), b_b = __byte_perm(t2, t3, 0x0062);
+            const float wr = d_bilinear_u8(__byte_perm(rg_t, rg_b, 0x5410), ax, ay);
+            const float wg = d_bilinear_u8(__byte_perm(rg_t, rg_b, 0x7632), ax, ay);
+            const float wb = d_bilinear_u8(__byte_perm(b_t, b_b, 0x5410), ax, ay);
+            px_rgb[0] = __fadd_rn(__fmul_rn(m, wr), __fmul_rn(im, px_rgb[0]));
+            px_rgb[1] = __fadd_rn(__fmul_rn(m, wg), __fmul_rn(im, px_rgb[1]));
+            px_rgb[2] = __fadd_rn(__fmul_rn(m, wb), __fmul_rn(im, px_rgb[2]));
             continue;
           }
           float v[4][3];
+          const uint32_t tw[4] = {t0, t1, t2, t3};
 #pragma unroll
           for (int t = 0; t < 4; t++) {
             const int yy = sy + (t >> 1), xx = sx + (t & 1);
             const bool in = (t >> 1 ? y1 : y0) && (t & 1 ? x1 : x0);
             if (in) {
-              const uint8_t* p = base + (size_t)yy * pitch + xx;
               float px[3];
 #pragma unroll
-              for (int cc = 0; cc < 3; cc++) px[cc] = d_u8_over_255(__ldg(p + (size_t)cc * ch * pitch));
+              for (int cc = 0; cc < 3; cc++) px[cc] = d_u8_over_255((tw[t] >> (8 * cc)) & 255u);
               for (int o = 0; o < c.n_ops; o++) d_photo_point(c.ops[o], px, yy, xx, cw, T.seed, L.fields);  // pre_transform_card (:581)
               v[t][0] = px[0]; v[t][1] = px[1]; v[t][2] = px[2];
             } else {
@@ -501,7 +521,7 @@ __global__ void __launch_bounds__(kDetBW * kDetBH) k_det_pixels(DetLaunch L, int
           }
 #pragma unroll
           for (int cc = 0; cc < 3; cc++) {
-            const float w = d_bilinear(v[0][cc], v[1][cc], v[2][cc], v[3][cc], X & 31, Y & 31);
+            const float w = d_bilinear(v[0][cc], v[1][cc], v[2][cc], v[3][cc], ax, ay);
             px_rgb[cc] = __fadd_rn(__fmul_rn(m, w), __fmul_rn(im, px_rgb[cc]));
           }
         }
@@ -835,6 +855,27 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
     MTGV_CUDA_OK(ctx, cudaMalloc(&d->lists, (size_t)(kDetMaxBlur + 1) * (chunk + 1) * 4));
     d->list_cap = chunk;
   }
+  // (re)build detection's RGBA card copy when the pool changed since the last batch
+  {
+    const size_t words = (size_t)ctx->n_cards * ctx->card_h * ctx->card_w;
+    if (words > d->rgba_cap) {
+      cudaFree(d->card_rgba);
+      d->card_rgba = nullptr; d->rgba_cap = 0;
+      MTGV_CUDA_OK(ctx, cudaMalloc(&d->card_rgba, words * 4));
+      d->rgba_cap = words;
+      d->rgba_epoch = 0;
+    }
+    if (d->rgba_epoch != ctx->card_epoch) {
+      for (int c0 = 0; c0 < ctx->n_cards; c0 += 32768) {
+        const int cnt = ctx->n_cards - c0 < 32768 ? ctx->n_cards - c0 : 32768;
+        k_det_rgba<<<dim3(64, cnt), 256, 0, st>>>(ctx->card_planes + (size_t)c0 * 3 * ctx->card_h * ctx->card_pitch, ctx->card_pitch,
+                                                   ctx->mask_det, d->card_rgba + (size_t)c0 * ctx->card_h * ctx->card_w, ctx->card_h,
+                                                   ctx->card_w);
+        ctx->launches++;
+      }
+      d->rgba_epoch = ctx->card_epoch;
+    }
+  }
   const size_t elem = out_dtype == MTGV_OUT_F16 ? 2 : (out_dtype == MTGV_OUT_U8 ? 1 : 4);
   const int tiles = ((S_w + kDetTW - 1) / kDetTW) * ((S_h + kDetTH - 1) / kDetTH);
   for (size_t base = 0; base < (size_t)n; base += chunk) {
@@ -851,8 +892,8 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
     for (int pass = 0; pass < passes; pass++) {
       DetLaunch L;
       L.params = (const DetParams*)params + base; L.n = m; L.pass = pass; L.pass_count = pass_count; L.pass_list = pass_list;
-      L.card_planes = ctx->card_planes; L.card_h = ctx->card_h; L.card_w = ctx->card_w; L.card_pitch = ctx->card_pitch;
-      L.mask = ctx->mask_det; L.bg_planes = ctx->bg_planes; L.bg_off = ctx->bg_off; L.bg_hw = ctx->bg_hw;
+      L.card_rgba = d->card_rgba; L.card_h = ctx->card_h; L.card_w = ctx->card_w;
+      L.bg_planes = ctx->bg_planes; L.bg_off = ctx->bg_off; L.bg_hw = ctx->bg_hw;
       L.src = pass > 0 ? d->scratch[(pass - 1) & 1] : nullptr;
       L.dst = d->scratch[pass & 1];
       L.out = (char*)images + base * per * elem; L.out_dtype = out_dtype; L.fields = (const uint32_t*)fields;

@@ -18,7 +18,8 @@ struct mtgv_ctx {
   int max_smem_optin = 0;
   std::string err;
   int64_t launches = 0;
-  unsigned attrs_set = 0;  // per-context (= per-device) bits: which kernels had their function attributes set
+  unsigned attrs_set = 0;
+  uint64_t card_epoch = 0;  // bumped whenever card pixels change (set / update): derived copies rebuild lazily  // per-context (= per-device) bits: which kernels had their function attributes set
 
   // card pool (planar copy: [n][3][h][pitch] uint8, pitch multiple of 16)
   uint8_t* card_planes = nullptr;
