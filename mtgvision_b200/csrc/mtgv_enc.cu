@@ -23,7 +23,10 @@
 
 namespace mtgv {
 
-constexpr int kThreads = 512;
+#ifndef MTGV_ENC_THREADS
+#define MTGV_ENC_THREADS 512
+#endif
+constexpr int kThreads = MTGV_ENC_THREADS;
 
 // ------------------------------------------------------------------------------------ //
 // small device helpers                                                                  //
