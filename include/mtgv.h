@@ -386,6 +386,27 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
 int mtgv_extract_dewarped(mtgv_ctx* ctx, const uint8_t* frame, int frame_h, int frame_w, int channels, const float* quads,
                           int n, const float* dst_rect, uint8_t* out, int out_h, int out_w, void* stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* Image decode into the pools (mtgvision/util/image.py:107-114), SURVEY 8f.1             */
+/* ------------------------------------------------------------------------------------ */
+
+/* Frame size of one JPEG file (host memory): hw[0] = height, hw[1] = width.  Host-only marker walk; fails with
+ * MTGV_ERR_INVALID and a message for files the decoder does not support (progressive, arithmetic coding,
+ * CMYK, 12-bit, chroma subsampled by more than 2). */
+int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw);
+
+/* imread_float's cv2.imread(path, IMREAD_COLOR_RGB) (util/image.py:107-114; IlsvrcImages._load_image
+ * encoder_datasets.py:457-474) for n baseline JPEG files at once, on the device.
+ * files: HOST bytes, file i = files[file_off[i] .. file_off[i+1]) (file_off: host, n+1 entries).
+ * out: DEVICE uint8; image i is written as [h,w,3] RGB at out + out_off[i] (out_off: host, n entries) - with
+ *      out_off = cumulative 3*h*w this is exactly the buffer mtgv_set_bg_pool takes, with equal-size files and
+ *      out_off = i*H*W*3 the tensor mtgv_set_card_pool / mtgv_update_*_images take.
+ * hw: host [n][2] as returned by mtgv_jpeg_info (what the caller sized `out` with); a file whose frame header
+ *     disagrees fails the call.  Bit-exact with cv2.imdecode (libjpeg-turbo: ISLOW IDCT, fancy upsampling).
+ * Work is queued on `stream`; the host arrays may be reused when the call returns. */
+int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out,
+                           const int64_t* out_off, const int32_t* hw, void* stream);
+
 /* Number of kernels launched by this context since creation (bench bookkeeping). */
 int64_t mtgv_launch_count(const mtgv_ctx* ctx);
 

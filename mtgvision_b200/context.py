@@ -237,6 +237,41 @@ class Context:
         self._check(rc, "mtgv_extract_dewarped")
         return out
 
+    # ------------------------------------------------------------------ image decode into the pools
+    def jpeg_info(self, data: bytes) -> tuple[int, int]:
+        """(h, w) of a baseline JPEG file; raises MtgvError for files the device decoder does not support."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        hw = np.zeros(2, dtype=np.int32)
+        rc = self.lib.mtgv_jpeg_info(self._h, buf.ctypes.data_as(C.c_void_p), len(buf), hw.ctypes.data_as(C.c_void_p))
+        self._check(rc, "mtgv_jpeg_info")
+        return int(hw[0]), int(hw[1])
+
+    def decode_jpegs(self, files: list[bytes]):
+        """cv2.imread(path, IMREAD_COLOR_RGB) (mtgvision/util/image.py:107-114) for a list of JPEG files, on the device.
+        Returns (flat uint8 device tensor, byte offsets int64 [n], hw int32 [n,2]); image i is
+        flat[off[i] : off[i] + 3*h*w].view(h, w, 3) - the arguments of mtgv_set_bg_pool."""
+        n = len(files)
+        hw = np.zeros((n, 2), dtype=np.int32)
+        for i, f in enumerate(files):
+            hw[i] = self.jpeg_info(f)
+        sizes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
+        out_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        file_off = np.concatenate([[0], np.cumsum([len(f) for f in files])]).astype(np.int64)
+        blob = np.frombuffer(b"".join(files), dtype=np.uint8)
+        out = torch.empty(int(out_off[-1]), dtype=torch.uint8, device=self.device)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.mtgv_decode_jpeg_batch(self._h, vp(blob), vp(file_off), n, _ptr(out), vp(out_off), vp(hw), self._stream())
+        self._check(rc, "mtgv_decode_jpeg_batch")
+        return out, out_off[:-1].copy(), hw
+
+    def set_bg_pool_from_jpegs(self, files: list[bytes]):
+        """Background pool straight from JPEG file bytes: decoded on the device, never materialised on the host."""
+        flat, off, hw = self.decode_jpegs(files)
+        torch.cuda.current_stream(self.device).synchronize()  # mtgv_set_bg_pool ingests on its own stream
+        rc = self.lib.mtgv_set_bg_pool(self._h, _ptr(flat), off.ctypes.data_as(C.c_void_p), hw.ctypes.data_as(C.c_void_p), len(files))
+        self._check(rc, "mtgv_set_bg_pool")
+        self.n_bgs = len(files)
+
     # ------------------------------------------------------------------ parity / debug entries
     def warp_perspective(self, src: torch.Tensor, M: torch.Tensor, dsize_hw) -> torch.Tensor:
         """src (n,h,w,c) float32, M (n,3,3) float64 -> (n,dh,dw,c) float32, cv2.warpPerspective semantics."""

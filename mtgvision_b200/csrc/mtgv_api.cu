@@ -63,6 +63,7 @@ void mtgv_destroy(mtgv_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   det_destroy(ctx);
+  jpeg_destroy(ctx);
   free_cards(ctx);
   free_bgs(ctx);
   cudaFree(ctx->cfg_dev); cudaFree(ctx->alpha0); cudaFree(ctx->alpha_scratch); cudaFree(ctx->sync_words);
@@ -271,6 +272,21 @@ int mtgv_extract_dewarped(mtgv_ctx* ctx, const uint8_t* frame, int frame_h, int 
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_extract_dewarped: bad arguments");
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   return dewarp_u8(ctx, frame, frame_h, frame_w, channels, quads, n, dst_rect, out, out_h, out_w, (cudaStream_t)stream);
+}
+
+int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!file || !hw || len < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_jpeg_info: bad arguments");
+  return jpeg_info(ctx, file, len, hw);
+}
+
+int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
+                           const int32_t* hw, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (n == 0) return MTGV_OK;
+  if (!files || !file_off || !out || !out_off || !hw || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return jpeg_decode_batch(ctx, files, file_off, n, out, out_off, hw, (cudaStream_t)stream);
 }
 
 int mtgv_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops, const void* fields,

@@ -57,6 +57,8 @@ struct mtgv_ctx {
 
   // detection state lives in mtgv_det.cu
   void* det = nullptr;
+  // JPEG decode scratch lives in mtgv_jpeg.cu
+  void* jpeg = nullptr;
 };
 
 namespace mtgv {
@@ -140,6 +142,11 @@ size_t bg_image_bytes(int h, int w);
 // mtgv_dewarp.cu
 int dewarp_u8(mtgv_ctx* ctx, const uint8_t* frame, int fh, int fw, int fc, const float* quads, int n, const float* dst_rect,
               uint8_t* out, int oh, int ow, cudaStream_t st);
+// mtgv_jpeg.cu
+int jpeg_destroy(mtgv_ctx* ctx);
+int jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw);
+int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
+                      const int32_t* hw, cudaStream_t st);
 // mtgv_fg.cu
 int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* fg_out, cudaStream_t st);
 int bg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* bg_out, cudaStream_t st);

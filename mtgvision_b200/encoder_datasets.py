@@ -14,6 +14,7 @@ pixels come from libmtgv.so.  What differs, by design:
 
 from __future__ import annotations
 
+import os
 import random
 import uuid
 from math import ceil
@@ -52,25 +53,50 @@ def _u8_to_f32(img_u8: np.ndarray) -> np.ndarray:
 
 class IlsvrcImages:
     """Background image source with the reference's interface (encoder_datasets.py:421-478)
-    over a resident pool of uint8 images."""
+    over a resident pool of uint8 images, or - like the reference - over a directory of JPEG files
+    (`root`, `subdir`), which are decoded on the device straight into the pool."""
 
-    def __init__(self, images: Optional[list[np.ndarray]] = None, n: int = 64):
+    _EXTS = (".jpeg", ".jpg")
+
+    def __init__(self, images: Optional[list[np.ndarray]] = None, n: int = 64, *, root=None, subdir="val",
+                 files: Optional[list[bytes]] = None):
+        self._images = self.jpeg_files = None
+        if root is not None or files is not None:
+            if files is None:
+                root = os.path.join(str(root), str(subdir)) if subdir is not None else str(root)
+                if subdir is not None and os.path.isabs(str(subdir)):
+                    raise ValueError("subdir must be a relative path")
+                paths = sorted(os.path.join(d, f) for d, _, fs in os.walk(root) for f in fs if f.lower().endswith(self._EXTS))
+                assert len(paths) > 0, f"Dataset is empty. Please download the dataset. {root}"
+                self._paths = paths
+                files = [open(p, "rb").read() for p in paths]
+            else:
+                self._paths = [f"bg://{j:06d}" for j in range(len(files))]
+            assert len(files) > 0, "Dataset is empty."
+            self.jpeg_files = list(files)
+            return
         self._images = images if images is not None else synth.make_bg_pool(n)
         assert len(self._images) > 0, "Dataset is empty."
         self._paths = [f"bg://{j:06d}" for j in range(len(self._images))]
 
     def __len__(self):
-        return len(self._images)
+        return len(self._paths)
+
+    def _image_u8(self, item) -> np.ndarray:
+        if self._images is not None:
+            return self._images[item]
+        flat, _, hw = _StaticEngine.get().decode_jpegs([self.jpeg_files[item]])  # imread_float's cv2.imread, on the device
+        return flat.cpu().numpy().reshape(int(hw[0, 0]), int(hw[0, 1]), 3)
 
     def __getitem__(self, item):
-        return _u8_to_f32(self._images[item])
+        return _u8_to_f32(self._image_u8(item))
 
     def __iter__(self):
-        for im in self._images:
-            yield _u8_to_f32(im)
+        for j in range(len(self)):
+            yield self[j]
 
     def ran_index(self) -> int:
-        return random.randrange(len(self._images))
+        return random.randrange(len(self))
 
     def ran_path(self) -> str:
         return random.choice(self._paths)
@@ -83,7 +109,14 @@ class IlsvrcImages:
 
     @property
     def images_u8(self) -> list[np.ndarray]:
-        return self._images
+        return self._images if self._images is not None else [self._image_u8(j) for j in range(len(self))]
+
+    def fill_pool(self, ctx: Context) -> None:
+        """Make this source the background pool of `ctx` (file-backed sources never touch a host pixel)."""
+        if self.jpeg_files is not None:
+            ctx.set_bg_pool_from_jpegs(self.jpeg_files)
+        else:
+            ctx.set_bg_pool(self._images)
 
 
 class CocoValImages(IlsvrcImages):

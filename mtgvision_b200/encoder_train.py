@@ -77,7 +77,7 @@ class RanMtgEncDecDataset(IterableDataset):
                                     half_upsidedown=half_upsidedown, paired=paired, targets=targets)
         pool = self.mtg.pool
         self.ctx.set_card_pool(pool.images, pool.labels3, pool.grp_off, pool.grp_mem)
-        self.ctx.set_bg_pool(self.ilsvrc.images_u8)
+        self.ilsvrc.fill_pool(self.ctx)
 
     # ------------------------------------------------------------------ reference surface
     def __iter__(self):

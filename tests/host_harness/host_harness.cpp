@@ -5,6 +5,7 @@
 #include "../../mtgvision_b200/csrc/mtgv_poly.cuh"
 #include "../../mtgvision_b200/csrc/mtgv_mask.h"
 #include "../../mtgvision_b200/csrc/mtgv_det.cuh"
+#include "../../mtgvision_b200/csrc/mtgv_jpeg.cuh"
 
 using namespace mtgv;
 
@@ -77,5 +78,50 @@ void hh_det_apply(const double* M, const double* pts, int n, double* out) {
 double hh_poly_area(const double* p, int n) { return poly_area(p, n); }
 int hh_clip_convex(const double* subj, int ns, const double* clip, int nc, double* out) {
   return clip_convex(subj, ns, clip, nc, out);
+}
+
+// Host run of the JPEG decode arithmetic of mtgv_jpeg.cuh (the device kernels call the same functions per
+// segment / block / pixel).  hw: out [2]; out: [h,w,3] RGB or NULL to only parse.  Returns 0, or -1 with msg set.
+int hh_jpeg_decode(const uint8_t* file, int64_t len, int32_t* hw, uint8_t* out, char* msg, int msg_cap) {
+  JpegImg im;
+  JpegTables tb;
+  std::vector<JpegSeg> segs;
+  std::string err;
+  if (jpeg_parse(file, len, 0, &im, &tb, &segs, &err) != 0) {
+    snprintf(msg, msg_cap, "%s", err.c_str());
+    return -1;
+  }
+  hw[0] = im.h; hw[1] = im.w;
+  if (!out) return 0;
+  std::vector<int16_t> coef((size_t)im.nblk * 64, 0);
+  int64_t plane_total = 0;
+  for (int c = 0; c < im.ncomp; c++) { im.plane_off[c] = plane_total; plane_total += (int64_t)im.bw[c] * im.bh[c] * 64; }
+  std::vector<uint8_t> planes((size_t)plane_total);
+  for (const JpegSeg& sg : segs) jpeg_decode_segment(file, im, &tb, sg, coef.data(), kJpegZigzag);
+  for (int c = 0; c < im.ncomp; c++)
+    for (int b = 0; b < im.bw[c] * im.bh[c]; b++) {
+      const int16_t* blk = coef.data() + (size_t)(im.blk0[c] + b) * 64;
+      int ws[8][8];
+      for (int t = 0; t < 8; t++) {
+        int x[8], o[8];
+        for (int r = 0; r < 8; r++) x[r] = (int)blk[r * 8 + t] * (int)tb.qt[im.tq[c]][r * 8 + t];
+        jpeg_idct8(x, o, kJpegPass1Shift);
+        for (int r = 0; r < 8; r++) ws[r][t] = o[r];
+      }
+      const int by = b / im.bw[c], bx = b % im.bw[c];
+      for (int t = 0; t < 8; t++) {
+        int o[8];
+        jpeg_idct8(ws[t], o, kJpegPass2Shift);
+        for (int k = 0; k < 8; k++)
+          planes[(size_t)im.plane_off[c] + (size_t)(by * 8 + t) * (im.bw[c] * 8) + bx * 8 + k] = (uint8_t)jpeg_clamp255(o[k] + 128);
+      }
+    }
+  for (int y = 0; y < im.h; y++)
+    for (int x = 0; x < im.w; x++) {
+      int rgb[3];
+      jpeg_pixel(im, planes.data(), y, x, rgb);
+      for (int k = 0; k < 3; k++) out[((size_t)y * im.w + x) * 3 + k] = (uint8_t)rgb[k];
+    }
+  return 0;
 }
 }

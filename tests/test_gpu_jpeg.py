@@ -1,0 +1,86 @@
+"""Device JPEG decode through the C ABI against cv2.imdecode itself: bit-exact."""
+import cv2
+import numpy as np
+import pytest
+
+from tests import jpeg_cases
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _ref(data):
+    return cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR_RGB)
+
+
+def _check(ctx, files, names=None):
+    flat, off, hw = ctx.decode_jpegs(files)
+    flat = flat.cpu().numpy()
+    for i, data in enumerate(files):
+        ref = _ref(data)
+        h, w = hw[i]
+        assert (h, w) == ref.shape[:2]
+        got = flat[off[i]: off[i] + 3 * h * w].reshape(h, w, 3)
+        assert np.array_equal(got, ref), (names[i] if names else i, int(np.abs(got.astype(int) - ref).max()))
+
+
+def test_small_suite_bit_exact():
+    from mtgvision_b200.context import Context
+
+    ctx = Context(0)
+    cases = jpeg_cases.small_suite()
+    _check(ctx, [d for _, d in cases], [n for n, _ in cases])
+    ctx.close()
+
+
+def test_pool_sized_batches_bit_exact():
+    """375x500 backgrounds and 680x488 cards, with and without restart intervals, all lanes-per-warp regimes."""
+    from mtgvision_b200.context import Context
+
+    ctx = Context(0)
+    rng = np.random.default_rng(5)
+    files = []
+    for k in range(24):
+        hw = (375, 500) if k % 3 else (680, 488)
+        files.append(jpeg_cases.encode(jpeg_cases.image(rng, *hw, ["mixed", "smooth", "noise"][k % 3]), [85, 92, 75][k % 3],
+                                       ["420", "444", "422", "440"][k % 4], rst=[0, 0, 4, 1][k % 4], optimize=k % 2))
+    _check(ctx, files)
+    _check(ctx, files[:1])
+    # many restart intervals: decoders share warps
+    many = [jpeg_cases.encode(jpeg_cases.image(rng, 375, 500, "mixed"), 80, "420", rst=1) for _ in range(64)]
+    _check(ctx, many)
+    assert ctx.decode_jpegs([])[0].numel() == 0
+    ctx.close()
+
+
+def test_decoded_files_feed_the_background_pool():
+    """IlsvrcImages over JPEG files (decoded on the device into the pool) == over the cv2-decoded arrays."""
+    from mtgvision_b200 import synth
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from mtgvision_b200.encoder_train import RanMtgEncDecDataset
+    from tests import parity_util as PU
+
+    pool, _ = PU.small_pools(8, 1)
+    files = [jpeg_cases.encode(synth.synth_bg(j), 90, "420") for j in range(8)]
+    outs = []
+    for src in (IlsvrcImages(images=[_ref(f) for f in files]), IlsvrcImages(files=files)):
+        ds = RanMtgEncDecDataset(8, paired=True, targets=False, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=src, seed=3)
+        b = next(iter(ds))
+        outs.append((b["x"].cpu().numpy(), b["x2"].cpu().numpy()))
+        ds.ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(IlsvrcImages(files=files)[2], _ref(files[2]).astype(np.float32) / 255.0)
+
+
+def test_rejects_unsupported_and_mismatched():
+    from mtgvision_b200.abi import MtgvError
+    from mtgvision_b200.context import Context
+
+    ctx = Context(0)
+    rng = np.random.default_rng(3)
+    img = jpeg_cases.image(rng, 24, 24, "mixed")
+    with pytest.raises(MtgvError, match="progressive"):
+        ctx.decode_jpegs([jpeg_cases.encode(img, progressive=1)])
+    with pytest.raises(MtgvError, match="SOI"):
+        ctx.jpeg_info(b"\x89PNG....")
+    ctx.close()

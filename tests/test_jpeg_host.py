@@ -1,0 +1,60 @@
+"""The JPEG decode arithmetic shared by the device kernels (mtgvision_b200/csrc/mtgv_jpeg.cuh), compiled for the host
+by tests/host_harness and compared bit for bit with cv2.imdecode - the call behind the reference's imread_float
+(mtgvision/util/image.py:107-114) - and with the oracle restatement."""
+import ctypes as C
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import jpeg_oracle
+from tests import jpeg_cases
+
+HARNESS = os.path.join(os.path.dirname(__file__), "host_harness", "libmtgv_hostharness.so")
+
+
+@pytest.fixture(scope="module")
+def hh():
+    return C.CDLL(HARNESS)
+
+
+def host_decode(hh, data: bytes):
+    buf = np.frombuffer(data, np.uint8)
+    hw = np.zeros(2, np.int32)
+    msg = C.create_string_buffer(256)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    if hh.hh_jpeg_decode(vp(buf), C.c_int64(len(buf)), vp(hw), None, msg, 256) != 0:
+        raise ValueError(msg.value.decode())
+    out = np.zeros((hw[0], hw[1], 3), np.uint8)
+    assert hh.hh_jpeg_decode(vp(buf), C.c_int64(len(buf)), vp(hw), vp(out), msg, 256) == 0
+    return out
+
+
+def test_shared_arithmetic_equals_cv2(hh):
+    for name, data in jpeg_cases.small_suite():
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR_RGB)
+        got = host_decode(hh, data)
+        assert got.shape == ref.shape and np.array_equal(got, ref), name
+
+
+def test_background_sized_files(hh):
+    rng = np.random.default_rng(11)
+    for s, rst in [("420", 0), ("422", 8), ("444", 0), ("440", 5)]:
+        data = jpeg_cases.encode(jpeg_cases.image(rng, 375, 500, "mixed"), 90, s, rst)
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR_RGB)
+        assert np.array_equal(host_decode(hh, data), ref), (s, rst)
+    data = jpeg_cases.encode(jpeg_cases.image(rng, 75, 100, "noise"), 97, "420")
+    assert np.array_equal(host_decode(hh, data), jpeg_oracle.decode(data))
+
+
+def test_unsupported_files_are_rejected_with_a_message(hh):
+    rng = np.random.default_rng(3)
+    img = jpeg_cases.image(rng, 24, 24, "mixed")
+    with pytest.raises(ValueError, match="progressive"):
+        host_decode(hh, jpeg_cases.encode(img, progressive=1))
+    with pytest.raises(ValueError, match="SOI"):
+        host_decode(hh, b"\x89PNG....")
+    good = jpeg_cases.encode(img)
+    with pytest.raises(ValueError, match="truncated"):
+        host_decode(hh, good[:100])
