@@ -407,6 +407,10 @@ int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw)
 int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out,
                            const int64_t* out_off, const int32_t* hw, void* stream);
 
+/* Device time of the three kernels (entropy decode, inverse DCT, upsample + colour) of the last
+ * mtgv_decode_jpeg_batch call, measured with CUDA events on its stream; waits for that batch (bench bookkeeping). */
+int mtgv_jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms3);
+
 /* Number of kernels launched by this context since creation (bench bookkeeping). */
 int64_t mtgv_launch_count(const mtgv_ctx* ctx);
 

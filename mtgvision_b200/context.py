@@ -246,10 +246,8 @@ class Context:
         self._check(rc, "mtgv_jpeg_info")
         return int(hw[0]), int(hw[1])
 
-    def decode_jpegs(self, files: list[bytes]):
-        """cv2.imread(path, IMREAD_COLOR_RGB) (mtgvision/util/image.py:107-114) for a list of JPEG files, on the device.
-        Returns (flat uint8 device tensor, byte offsets int64 [n], hw int32 [n,2]); image i is
-        flat[off[i] : off[i] + 3*h*w].view(h, w, 3) - the arguments of mtgv_set_bg_pool."""
+    def prepare_jpegs(self, files: list[bytes]) -> dict:
+        """Host-side batch of JPEG files for `decode_prepared`: pinned concatenated bytes, offsets and frame sizes."""
         n = len(files)
         hw = np.zeros((n, 2), dtype=np.int32)
         for i, f in enumerate(files):
@@ -257,12 +255,33 @@ class Context:
         sizes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
         out_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         file_off = np.concatenate([[0], np.cumsum([len(f) for f in files])]).astype(np.int64)
-        blob = np.frombuffer(b"".join(files), dtype=np.uint8)
-        out = torch.empty(int(out_off[-1]), dtype=torch.uint8, device=self.device)
+        blob = torch.empty(max(int(file_off[-1]), 1), dtype=torch.uint8).pin_memory()
+        blob.numpy()[: int(file_off[-1])] = np.frombuffer(b"".join(files), dtype=np.uint8)
+        return {"n": n, "blob": blob, "file_off": file_off, "out_off": out_off, "hw": hw}
+
+    def decode_prepared(self, batch: dict, out: torch.Tensor | None = None) -> torch.Tensor:
+        """mtgv_decode_jpeg_batch on a prepared batch; returns the flat uint8 device tensor of all images."""
+        total = int(batch["out_off"][-1])
+        if out is None:
+            out = torch.empty(total, dtype=torch.uint8, device=self.device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.numel() >= total
         vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        rc = self.lib.mtgv_decode_jpeg_batch(self._h, vp(blob), vp(file_off), n, _ptr(out), vp(out_off), vp(hw), self._stream())
+        rc = self.lib.mtgv_decode_jpeg_batch(self._h, C.c_void_p(batch["blob"].data_ptr()), vp(batch["file_off"]), batch["n"], _ptr(out),
+                                             vp(batch["out_off"]), vp(batch["hw"]), self._stream())
         self._check(rc, "mtgv_decode_jpeg_batch")
-        return out, out_off[:-1].copy(), hw
+        return out
+
+    def jpeg_last_kernel_ms(self) -> tuple[float, float, float]:
+        ms = (C.c_float * 3)()
+        self._check(self.lib.mtgv_jpeg_last_kernel_ms(self._h, ms), "mtgv_jpeg_last_kernel_ms")
+        return ms[0], ms[1], ms[2]
+
+    def decode_jpegs(self, files: list[bytes]):
+        """cv2.imread(path, IMREAD_COLOR_RGB) (mtgvision/util/image.py:107-114) for a list of JPEG files, on the device.
+        Returns (flat uint8 device tensor, byte offsets int64 [n], hw int32 [n,2]); image i is
+        flat[off[i] : off[i] + 3*h*w].view(h, w, 3) - the arguments of mtgv_set_bg_pool."""
+        batch = self.prepare_jpegs(files)
+        return self.decode_prepared(batch), batch["out_off"][:-1].copy(), batch["hw"]
 
     def set_bg_pool_from_jpegs(self, files: list[bytes]):
         """Background pool straight from JPEG file bytes: decoded on the device, never materialised on the host."""

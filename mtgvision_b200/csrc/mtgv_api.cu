@@ -280,6 +280,12 @@ int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw)
   return jpeg_info(ctx, file, len, hw);
 }
 
+int mtgv_jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms3) {
+  if (!ctx || !ms3) return MTGV_ERR_INVALID;
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return jpeg_last_kernel_ms(ctx, ms3);
+}
+
 int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
                            const int32_t* hw, void* stream) {
   if (!ctx) return MTGV_ERR_INVALID;

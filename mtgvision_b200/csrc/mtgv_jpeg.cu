@@ -2,10 +2,10 @@
 // Replaces the cv2.imread behind imread_float (mtgvision/util/image.py:107-114) for the images that feed
 // mtgv_set_bg_pool / mtgv_set_card_pool; arithmetic in mtgv_jpeg.cuh, bit-exact with cv2 (libjpeg-turbo ISLOW +
 // fancy upsampling).  Three kernels per batch, all images of the batch in each launch:
-//   k_jpeg_entropy  one decoder thread per restart interval (a file without DRI is one interval).  Huffman decode
-//                   is a serial bit walk, so the parallelism is files x intervals; when there are fewer intervals
-//                   than warps the machine can hold, every decoder gets a warp to itself (lane 0 walks, no
-//                   divergence partners), else `lanes` decoders share a warp.
+//   k_jpeg_entropy  one warp per run of restart intervals (a file without DRI is one interval).  Huffman decode is
+//                   a serial bit walk, so the parallelism is files x intervals: lane 0 walks the bits out of a
+//                   shared-memory ring that the whole warp keeps filled with byte-unstuffed stream data; tables in
+//                   shared memory.  Throughput comes from many files in flight (<= 32 warps per SM).
 //   k_jpeg_idct     8 threads per 8x8 block: dequantise, column pass, row pass through shared memory, one 8-byte
 //                   store per thread into the component sample plane.
 //   k_jpeg_color    one thread per output pixel: triangle-filter chroma upsampling + fixed-point YCbCr->RGB,
@@ -15,14 +15,18 @@
 #include "mtgv_internal.cuh"
 #include "mtgv_jpeg.cuh"
 
+#include <thread>
+
 namespace mtgv {
 
 struct JpegState {
   uint8_t* files = nullptr;   size_t files_cap = 0;
   int16_t* coef = nullptr;    size_t coef_cap = 0;    // int16 elements
   uint8_t* planes = nullptr;  size_t planes_cap = 0;
-  uint8_t* desc = nullptr;    size_t desc_cap = 0;    // JpegImg[n] | JpegTables[n] | JpegSeg[nseg]
+  uint8_t* desc = nullptr;    size_t desc_cap = 0;    // JpegImg[n] | JpegTables[n] | JpegSeg[nseg] | JpegWork[nwork]
   uint8_t* desc_host = nullptr; size_t desc_host_cap = 0;  // pinned
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around the three kernels of the last batch
+  bool timed = false;
 };
 
 static int grow(mtgv_ctx* ctx, void** p, size_t* cap, size_t need) {
@@ -37,18 +41,211 @@ static int grow(mtgv_ctx* ctx, void** p, size_t* cap, size_t need) {
 
 __constant__ uint8_t c_zigzag[64];
 
-__global__ void k_jpeg_entropy(const uint8_t* __restrict__ files, const JpegImg* __restrict__ imgs, const JpegTables* __restrict__ tbs,
-                               const JpegSeg* __restrict__ segs, int nseg, int stride, int16_t* __restrict__ coef) {
+// ---- entropy decode: one warp per work item (a run of restart intervals of one file) ----
+// Lane 0 walks the bit stream; the whole warp feeds it: 128 raw bytes per round are loaded coalesced, the stuffed
+// zero after every 0xFF is squeezed out with ballots, and the clean bytes go to a shared-memory ring that lane 0
+// reads a 32-bit word at a time.  The first marker (RSTn / EOI) ends the stream: zero bits follow, like jdhuff.c.
+// Huffman tables, the zigzag order and the block layout of one MCU sit in shared memory next to the ring.
+constexpr int kRing = 1024;  // bytes, power of two
+constexpr int kEntWarps = 2;
+
+struct JpegWork {
+  int32_t img, seg0, nseg, _pad;
+};
+
+struct EntWarp {
+  uint32_t ring[kRing / 4];
+  uint16_t fast[4][1 << kJpegFastBits];
+  int32_t maxcode[4][18];
+  int32_t valoff[4][18];
+  uint8_t vals[4][256];
+  uint8_t blk_c[16], blk_y[16], blk_x[16];
+};
+
+// win: the next 32 unread bits, first bit in bit 31; used: bits of win already consumed by this symbol
+__device__ __forceinline__ int ent_symbol(const EntWarp& S, int ti, uint32_t win, int& used) {
+  const unsigned e = S.fast[ti][win >> (32 - kJpegFastBits)];
+  if (e) {
+    used = (int)(e >> 8);
+    return (int)(e & 255u);
+  }
+  const int top16 = (int)(win >> 16);
+  int l = kJpegFastBits + 1;
+  while (l <= 16 && (top16 >> (16 - l)) > S.maxcode[ti][l]) l++;
+  if (l > 16) {  // corrupt data: libjpeg warns and returns a zero symbol
+    used = 16;
+    return 0;
+  }
+  used = l;
+  return S.vals[ti][((top16 >> (16 - l)) + S.valoff[ti][l]) & 255];
+}
+
+// the s (1..15) bits after the code, sign-extended like HUFF_EXTEND; used + s <= 31
+__device__ __forceinline__ int ent_extend(uint32_t win, int used, int s) {
+  const int v = (int)((win << used) >> (32 - s));
+  return v < (1 << (s - 1)) ? v - ((1 << s) - 1) : v;
+}
+
+__global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* __restrict__ files, const JpegImg* __restrict__ imgs,
+                                                               const JpegTables* __restrict__ tbs, const JpegSeg* __restrict__ segs,
+                                                               const JpegWork* __restrict__ work, int nwork, int16_t* __restrict__ coef) {
+  __shared__ EntWarp smem[kEntWarps];
   __shared__ uint8_t zz[64];
   if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t % stride) return;
-  const int s = t / stride;
-  if (s >= nseg) return;
-  const JpegSeg sg = segs[s];
-  const JpegImg im = imgs[sg.img];
-  jpeg_decode_segment(files + im.file_off, im, tbs + sg.img, sg, coef, zz);
+  const int lane = threadIdx.x & 31, wi = blockIdx.x * kEntWarps + (threadIdx.x >> 5);
+  if (wi >= nwork) return;
+  EntWarp& S = smem[threadIdx.x >> 5];
+  const JpegWork wk = work[wi];
+  const JpegImg& im = imgs[wk.img];
+  {  // tables of this file
+    const JpegTables* T = tbs + wk.img;
+    const uint32_t* src = (const uint32_t*)T->fast;
+    uint32_t* dst = (uint32_t*)S.fast;
+    for (int i = lane; i < (int)(sizeof(S.fast) / 4); i += 32) dst[i] = src[i];
+    for (int i = lane; i < 4 * 18; i += 32) {
+      ((int32_t*)S.maxcode)[i] = ((const int32_t*)T->maxcode)[i];
+      ((int32_t*)S.valoff)[i] = ((const int32_t*)T->valoff)[i];
+    }
+    for (int i = lane; i < 4 * 256 / 4; i += 32) ((uint32_t*)S.vals)[i] = ((const uint32_t*)T->vals)[i];
+    if (lane == 0) {
+      int j = 0;
+      for (int c = 0; c < im.ncomp; c++)
+        for (int by = 0; by < im.cv[c]; by++)
+          for (int bx = 0; bx < im.ch[c]; bx++, j++) { S.blk_c[j] = (uint8_t)c; S.blk_y[j] = (uint8_t)by; S.blk_x[j] = (uint8_t)bx; }
+    }
+  }
+  int nb_mcu = 0;
+  for (int c = 0; c < im.ncomp; c++) nb_mcu += im.ch[c] * im.cv[c];
+  const int mcux = im.mcux, ncomp = im.ncomp;
+  // per-component constants in registers (ncomp <= 3)
+  int c_h[3], c_v[3], c_bw[3], c_td[3], c_ta[3];
+  int64_t c_base[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const bool on = c < ncomp;
+    c_h[c] = on ? im.ch[c] : 1; c_v[c] = on ? im.cv[c] : 1; c_bw[c] = on ? im.bw[c] : 0;
+    c_td[c] = on ? im.td[c] : 0; c_ta[c] = on ? 2 + im.ta[c] : 2;
+    c_base[c] = on ? im.coef_blk + im.blk0[c] : 0;
+  }
+  const uint8_t* file = files + im.file_off;
+  const int file_len = im.file_len;
+  __syncwarp();
+
+  for (int sgi = 0; sgi < wk.nseg; sgi++) {
+    const JpegSeg sg = segs[wk.seg0 + sgi];
+    // ---- stream state (uniform across the warp) ----
+    int src = sg.byte_off;
+    unsigned wp = 0, rp = 0, carry = 0;
+    bool ended = false;
+    // ---- decoder state (lane 0) ----
+    unsigned bp = 0;  // bits consumed
+    int k = 0, j = 0, m = 0, done = 0, ta = 2;
+    int my = sg.mcu0 / mcux, mx = sg.mcu0 - my * mcux;
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    int16_t* blk = nullptr;
+    int cc = 0;
+    for (;;) {
+      // ---- refill: 128 raw bytes per round while they fit ----
+      while (!ended && wp - rp <= (unsigned)(kRing - 132)) {
+        unsigned b[5];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int idx = src + 32 * q + lane;
+          b[q] = idx < file_len ? (unsigned)__ldg(file + idx) : 0x1FFu;  // past the end: reads as a marker
+        }
+        {
+          const int idx = src + 128;
+          b[4] = idx < file_len ? (unsigned)__ldg(file + idx) : 0x1FFu;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          unsigned prev = __shfl_up_sync(0xffffffffu, b[q], 1);
+          if (lane == 0) prev = carry;
+          unsigned next = __shfl_down_sync(0xffffffffu, b[q], 1);
+          const unsigned first_next = q < 3 ? __shfl_sync(0xffffffffu, b[q + 1], 0) : b[4];
+          if (lane == 31) next = first_next;
+          carry = __shfl_sync(0xffffffffu, b[q], 31);
+          const bool marker = b[q] > 0xFFu || (b[q] == 0xFFu && next != 0u);
+          const bool drop = prev == 0xFFu && b[q] == 0u;
+          const unsigned mm = __ballot_sync(0xffffffffu, marker);
+          const int fm = mm ? __ffs(mm) - 1 : 32;
+          const bool keep = !drop && lane < fm;
+          const unsigned km = __ballot_sync(0xffffffffu, keep);
+          if (keep) ((uint8_t*)S.ring)[((wp + __popc(km & ((1u << lane) - 1u))) & (kRing - 1)) ^ 3u] = (uint8_t)b[q];
+          wp += __popc(km);
+          if (mm) {
+            ended = true;
+            break;
+          }
+        }
+        src += 128;
+        if (ended) {  // zero-pad to a whole word; lane 0 feeds zero words from there on
+          const unsigned pad = (4u - (wp & 3u)) & 3u;
+          if (lane < (int)pad) ((uint8_t*)S.ring)[((wp + lane) & (kRing - 1)) ^ 3u] = 0;
+          wp += pad;
+        }
+      }
+      __syncwarp();
+      // ---- decode (lane 0) until the ring runs dry or the segment is complete ----
+      if (lane == 0) {
+        const unsigned avail = wp >> 2;  // whole words in the ring (wp is word aligned once the stream has ended)
+        for (;;) {
+          const unsigned idx = bp >> 5;
+          if (idx + 2u > avail && !ended) break;
+          const uint32_t w0 = idx < avail ? S.ring[idx & (kRing / 4 - 1)] : 0u;
+          const uint32_t w1 = idx + 1u < avail ? S.ring[(idx + 1u) & (kRing / 4 - 1)] : 0u;
+          const uint32_t win = __funnelshift_l(w1, w0, bp & 31u);
+          int used;
+          if (k == 0) {
+            cc = S.blk_c[j];
+            const int by = S.blk_y[j], bx = S.blk_x[j];
+            const int ch = cc == 0 ? c_h[0] : (cc == 1 ? c_h[1] : c_h[2]);
+            const int cv = cc == 0 ? c_v[0] : (cc == 1 ? c_v[1] : c_v[2]);
+            const int bw = cc == 0 ? c_bw[0] : (cc == 1 ? c_bw[1] : c_bw[2]);
+            const int64_t base = cc == 0 ? c_base[0] : (cc == 1 ? c_base[1] : c_base[2]);
+            blk = coef + (base + (int64_t)(my * cv + by) * bw + mx * ch + bx) * 64;
+            ta = cc == 0 ? c_ta[0] : (cc == 1 ? c_ta[1] : c_ta[2]);
+            const int td = cc == 0 ? c_td[0] : (cc == 1 ? c_td[1] : c_td[2]);
+            const int s = ent_symbol(S, td, win, used) & 15;
+            int diff = 0;
+            if (s) { diff = ent_extend(win, used, s); used += s; }
+            int p;
+            if (cc == 0) p = (pred0 += diff);
+            else if (cc == 1) p = (pred1 += diff);
+            else p = (pred2 += diff);
+            blk[0] = (int16_t)p;
+            k = 1;
+          } else {
+            const int rs = ent_symbol(S, ta, win, used);
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0) {
+              k = r == 15 ? k + 16 : 64;
+            } else {
+              k += r;
+              const int v = ent_extend(win, used, s);
+              used += s;
+              if (k <= 63) blk[zz[k]] = (int16_t)v;
+              k++;
+            }
+          }
+          bp += (unsigned)used;
+          if (k >= 64) {
+            k = 0;
+            if (++j == nb_mcu) {
+              j = 0;
+              if (++mx == mcux) { mx = 0; my++; }
+              if (++m == sg.nmcu) { done = 1; break; }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      done = __shfl_sync(0xffffffffu, done, 0);
+      rp = (__shfl_sync(0xffffffffu, bp, 0) >> 5) << 2;
+      if (done) break;
+    }
+  }
 }
 
 // grid (ceil(max blocks / 32), n images), 256 threads = 32 blocks of 8 threads
@@ -90,19 +287,35 @@ __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ i
   }
 }
 
-// grid (ceil(max pixels / 256), n images)
+// grid (ceil(max pixels / 1024), n images): a thread converts 4 consecutive pixels (linear index, rows may wrap) and
+// stores their 12 bytes as three words when the image's output address is word aligned
 __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ imgs, const uint8_t* __restrict__ planes,
                                                     uint8_t* __restrict__ out) {
-  const JpegImg& im = imgs[blockIdx.y];
+  __shared__ JpegImg im;
+  for (int i = threadIdx.x; i < (int)(sizeof(JpegImg) / 4); i += 256) ((uint32_t*)&im)[i] = ((const uint32_t*)&imgs[blockIdx.y])[i];
+  __syncthreads();
   const int npix = im.h * im.w;
   uint8_t* dst = out + im.out_off;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
-    const int y = i / im.w, x = i - y * im.w;
-    int rgb[3];
-    jpeg_pixel(im, planes, y, x, rgb);
-    dst[(int64_t)i * 3 + 0] = (uint8_t)rgb[0];
-    dst[(int64_t)i * 3 + 1] = (uint8_t)rgb[1];
-    dst[(int64_t)i * 3 + 2] = (uint8_t)rgb[2];
+  const bool aligned = (((uintptr_t)dst) & 3) == 0;
+  for (int i = (blockIdx.x * 256 + threadIdx.x) * 4; i < npix; i += gridDim.x * 1024) {
+    int y = i / im.w, x = i - y * im.w;
+    uint8_t px[12];
+    const int cnt = npix - i < 4 ? npix - i : 4;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int rgb[3] = {0, 0, 0};
+      if (q < cnt) jpeg_pixel(im, planes, y, x, rgb);
+      px[3 * q] = (uint8_t)rgb[0]; px[3 * q + 1] = (uint8_t)rgb[1]; px[3 * q + 2] = (uint8_t)rgb[2];
+      if (++x == im.w) { x = 0; y++; }
+    }
+    if (aligned && cnt == 4) {
+      uint32_t* d = (uint32_t*)(dst + (int64_t)i * 3);
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        d[q] = (uint32_t)px[4 * q] | ((uint32_t)px[4 * q + 1] << 8) | ((uint32_t)px[4 * q + 2] << 16) | ((uint32_t)px[4 * q + 3] << 24);
+    } else {
+      for (int q = 0; q < 3 * cnt; q++) dst[(int64_t)i * 3 + q] = px[q];
+    }
   }
 }
 
@@ -111,8 +324,17 @@ int jpeg_destroy(mtgv_ctx* ctx) {
   if (!st) return MTGV_OK;
   cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc);
   if (st->desc_host) cudaFreeHost(st->desc_host);
+  for (auto& e : st->ev) if (e) cudaEventDestroy(e);
   delete st;
   ctx->jpeg = nullptr;
+  return MTGV_OK;
+}
+
+int jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms) {
+  JpegState* st = (JpegState*)ctx->jpeg;
+  if (!st || !st->timed) return fail(ctx, MTGV_ERR_INVALID, "mtgv_jpeg_last_kernel_ms: no batch was decoded yet");
+  MTGV_CUDA_OK(ctx, cudaEventSynchronize(st->ev[3]));
+  for (int k = 0; k < 3; k++) MTGV_CUDA_OK(ctx, cudaEventElapsedTime(&ms[k], st->ev[k], st->ev[k + 1]));
   return MTGV_OK;
 }
 
@@ -132,18 +354,42 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   if (!ctx->jpeg) {
     ctx->jpeg = new JpegState();
     MTGV_CUDA_OK(ctx, cudaMemcpyToSymbol(c_zigzag, kJpegZigzag, 64));
+    for (auto& e : ((JpegState*)ctx->jpeg)->ev) MTGV_CUDA_OK(ctx, cudaEventCreate(&e));
   }
   JpegState* st = (JpegState*)ctx->jpeg;
   std::vector<JpegImg> imgs(n);
   std::vector<JpegTables> tbs(n);
   std::vector<JpegSeg> segs;
+  {  // marker walk + table build, a few host threads over contiguous file ranges
+    unsigned hc = std::thread::hardware_concurrency();
+    const int nt = n < 64 ? 1 : (int)(hc < 2 ? 1 : (hc > 8 ? 8 : hc));
+    std::vector<std::vector<JpegSeg>> tsegs(nt);
+    std::vector<std::string> terr(nt);
+    std::vector<int> tbad(nt, -1);
+    auto run = [&](int t) {
+      const int i0 = (int)((int64_t)n * t / nt), i1 = (int)((int64_t)n * (t + 1) / nt);
+      for (int i = i0; i < i1; i++) {
+        const int64_t len = file_off[i + 1] - file_off[i];
+        if (len < 0) { terr[t] = "bad offsets"; tbad[t] = i; return; }
+        if (jpeg_parse(files + file_off[i], len, i, &imgs[i], &tbs[i], &tsegs[t], &terr[t]) != 0) { tbad[t] = i; return; }
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(run, t);
+    run(0);
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nt; t++)
+      if (tbad[t] >= 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: file " + std::to_string(tbad[t]) + ": " + terr[t]);
+    for (int t = 0; t < nt; t++) {
+      const int base = (int)segs.size();
+      const int i0 = (int)((int64_t)n * t / nt), i1 = (int)((int64_t)n * (t + 1) / nt);
+      for (int i = i0; i < i1; i++) imgs[i].seg0 += base;
+      segs.insert(segs.end(), tsegs[t].begin(), tsegs[t].end());
+    }
+  }
   int64_t nblk_total = 0, plane_total = 0;
   int max_blk = 0, max_pix = 0;
   for (int i = 0; i < n; i++) {
-    std::string err;
-    const int64_t len = file_off[i + 1] - file_off[i];
-    if (len < 0 || jpeg_parse(files + file_off[i], len, i, &imgs[i], &tbs[i], &segs, &err) != 0)
-      return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: file " + std::to_string(i) + ": " + (len < 0 ? "bad offsets" : err));
     JpegImg& im = imgs[i];
     if (im.h != hw[2 * i] || im.w != hw[2 * i + 1])
       return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: file " + std::to_string(i) + " is " + std::to_string(im.h) + "x" +
@@ -161,7 +407,18 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   }
   const size_t file_bytes = (size_t)(file_off[n] - file_off[0]);
   const size_t nseg = segs.size();
-  const size_t o_tb = sizeof(JpegImg) * n, o_sg = o_tb + sizeof(JpegTables) * n, desc_bytes = o_sg + sizeof(JpegSeg) * nseg;
+  // work items: one warp each; runs of restart intervals of one file, cut so that about 32 warps per SM exist
+  std::vector<JpegWork> work;
+  {
+    const size_t target = (size_t)ctx->sm_count * 32;
+    const int group = (int)((nseg + target - 1) / target);
+    for (int i = 0; i < n; i++)
+      for (int s0 = 0; s0 < imgs[i].nseg; s0 += group)
+        work.push_back(JpegWork{i, imgs[i].seg0 + s0, imgs[i].nseg - s0 < group ? imgs[i].nseg - s0 : group, 0});
+  }
+  const size_t nwork = work.size();
+  const size_t o_tb = sizeof(JpegImg) * n, o_sg = o_tb + sizeof(JpegTables) * n, o_wk = o_sg + sizeof(JpegSeg) * nseg,
+               desc_bytes = o_wk + sizeof(JpegWork) * nwork;
   int rc;
   if ((rc = grow(ctx, (void**)&st->files, &st->files_cap, file_bytes + 16))) return rc;
   if ((rc = grow(ctx, (void**)&st->coef, &st->coef_cap, (size_t)nblk_total * 64 * sizeof(int16_t)))) return rc;
@@ -177,24 +434,27 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   memcpy(st->desc_host, imgs.data(), o_tb);
   memcpy(st->desc_host + o_tb, tbs.data(), sizeof(JpegTables) * n);
   memcpy(st->desc_host + o_sg, segs.data(), sizeof(JpegSeg) * nseg);
+  memcpy(st->desc_host + o_wk, work.data(), sizeof(JpegWork) * nwork);
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->desc, st->desc_host, desc_bytes, cudaMemcpyHostToDevice, stream));
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->files, files + file_off[0], file_bytes, cudaMemcpyHostToDevice, stream));
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->coef, 0, (size_t)nblk_total * 64 * sizeof(int16_t), stream));
   const JpegImg* d_img = (const JpegImg*)st->desc;
   const JpegTables* d_tb = (const JpegTables*)(st->desc + o_tb);
   const JpegSeg* d_sg = (const JpegSeg*)(st->desc + o_sg);
-  // decoders per warp: alone while the intervals fit the machine as whole warps (16 warps per SM), else shared
-  int lanes = 1;
-  while (lanes < 32 && (nseg + lanes - 1) / lanes > (size_t)ctx->sm_count * 16) lanes *= 2;
-  const int stride = 32 / lanes;
-  const long long threads = (long long)nseg * stride;
-  k_jpeg_entropy<<<(unsigned)((threads + 63) / 64), 64, 0, stream>>>(st->files, d_img, d_tb, d_sg, (int)nseg, stride, st->coef);
+  const JpegWork* d_wk = (const JpegWork*)(st->desc + o_wk);
+  MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[0], stream));
+  k_jpeg_entropy<<<(unsigned)((nwork + kEntWarps - 1) / kEntWarps), 32 * kEntWarps, 0, stream>>>(st->files, d_img, d_tb, d_sg, d_wk, (int)nwork,
+                                                                                                  st->coef);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
+  MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));
   k_jpeg_idct<<<dim3((max_blk + 31) / 32, n), 256, 0, stream>>>(d_img, d_tb, st->coef, st->planes);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
-  const int gx = (max_pix + 255) / 256;
+  MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[2], stream));
+  const int gx = (max_pix + 1023) / 1024;
   k_jpeg_color<<<dim3(gx < 1024 ? gx : 1024, n), 256, 0, stream>>>(d_img, st->planes, out);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
+  MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[3], stream));
+  st->timed = true;
   ctx->launches += 3;
   return MTGV_OK;
 }

@@ -43,6 +43,8 @@ struct JpegImg {
   int32_t ch[3], cv[3], tq[3], td[3], ta[3];
   int32_t bw[3], bh[3];  // component extent in blocks (whole MCUs)
   int32_t blk0[3];       // first block of component c relative to coef_blk
+  int32_t hf[3], vf[3];  // upsampling factors hmax / ch, vmax / cv
+  int32_t dh[3], dw[3];  // downsampled component size ceil(h * cv / vmax), ceil(w * ch / hmax)
   int32_t seg0, nseg;
   int32_t nblk, _pad;
 };
@@ -191,6 +193,10 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
     im->bh[c] = im->mcuy * im->cv[c];
     im->blk0[c] = im->nblk;
     im->nblk += im->bw[c] * im->bh[c];
+    im->hf[c] = im->hmax / im->ch[c];
+    im->vf[c] = im->vmax / im->cv[c];
+    im->dh[c] = (im->h * im->cv[c] + im->vmax - 1) / im->vmax;
+    im->dw[c] = (im->w * im->ch[c] + im->hmax - 1) / im->hmax;
   }
   im->scan_off = (int32_t)pos;
   im->file_len = (int32_t)len;
@@ -373,9 +379,9 @@ MTGV_HD int jpeg_clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 MTGV_HD int jpeg_chroma(const JpegImg& im, const uint8_t* planes, int c, int y, int x) {
   const uint8_t* P = planes + im.plane_off[c];
   const int pitch = im.bw[c] * 8;
-  const int hf = im.hmax / im.ch[c], vf = im.vmax / im.cv[c];
+  const int hf = im.hf[c], vf = im.vf[c];
   if (hf == 1 && vf == 1) return P[y * pitch + x];
-  const int dh = (im.h * im.cv[c] + im.vmax - 1) / im.vmax, dw = (im.w * im.ch[c] + im.hmax - 1) / im.hmax;
+  const int dh = im.dh[c], dw = im.dw[c];
   int inrow = y, other = y;
   if (vf == 2) {  // the neighbouring row of the triangle filter; edge rows replicated (jdmainct.c context rows)
     inrow = y >> 1;
