@@ -23,7 +23,9 @@ struct JpegState {
   uint8_t* files = nullptr;   size_t files_cap = 0;
   int16_t* coef = nullptr;    size_t coef_cap = 0;    // int16 elements
   uint8_t* planes = nullptr;  size_t planes_cap = 0;
-  uint8_t* desc = nullptr;    size_t desc_cap = 0;    // JpegImg[n] | JpegTables[n] | JpegSeg[nseg] | JpegWork[nwork]
+  uint8_t* clean = nullptr;   size_t clean_cap = 0;   // byte-unstuffed scans of the single-interval files
+  uint64_t* sync = nullptr;   size_t sync_cap = 0;    // subsequence checkpoints (bytes)
+  uint8_t* desc = nullptr;    size_t desc_cap = 0;    // JpegImg[n] | JpegTables[n] | JpegSeg[nseg] | JpegWork[nwork] | int32 par_list[npar]
   uint8_t* desc_host = nullptr; size_t desc_host_cap = 0;  // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around the three kernels of the last batch
   bool timed = false;
@@ -63,7 +65,8 @@ struct EntWarp {
 };
 
 // win: the next 32 unread bits, first bit in bit 31; used: bits of win already consumed by this symbol
-__device__ __forceinline__ int ent_symbol(const EntWarp& S, int ti, uint32_t win, int& used) {
+template <class Tables>
+__device__ __forceinline__ int ent_symbol(const Tables& S, int ti, uint32_t win, int& used) {
   const unsigned e = S.fast[ti][win >> (32 - kJpegFastBits)];
   if (e) {
     used = (int)(e >> 8);
@@ -248,6 +251,282 @@ __global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* 
   }
 }
 
+// ---- entropy decode of single-interval files: one CTA per file, every thread a stretch of the bit stream ----
+// Huffman streams resynchronise by themselves: a decoder started at an arbitrary bit in an arbitrary state falls into
+// step with the true symbol boundaries after a few dozen symbols (Klein & Wiseman 2003; Weissenberger & Schmidt 2018 for
+// GPUs).  The CTA first squeezes the stuffed zeros out of the scan into a clean big-endian copy, then cuts it into
+// 1024-bit subsequences; thread t owns a contiguous run of them.
+//   round 0   every thread decodes its run from a cold state (bit = start of the run, block start), keeping the state
+//             (bit position, zigzag index, block-in-MCU) and the number of completed blocks at every subsequence end;
+//   round r   a thread whose predecessor's final state differs from the state it started from decodes again from there,
+//             overwriting its checkpoints until one repeats (from there on its earlier decode was already right);
+//             repeated until no thread starts over - then every checkpoint follows from the true start of the scan by
+//             induction, whatever the data (worst case: as many rounds as threads);
+//   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
+// DC terms are stored as differences and integrated by k_jpeg_dc.
+constexpr int kSubBits = 1024;
+constexpr int kParThreads = 256;
+constexpr uint64_t kStateMask = (1ull << 48) - 1;
+
+struct ParSmem {
+  uint16_t fast[4][1 << kJpegFastBits];
+  int32_t maxcode[4][18];
+  int32_t valoff[4][18];
+  uint8_t vals[4][256];
+  uint8_t blk_c[16], blk_y[16], blk_x[16], blk_td[16], blk_ta[16];
+  int32_t c_h[3], c_v[3], c_bw[3];
+  int64_t c_base[3];
+  unsigned wsum[kParThreads / 32];
+  int marker, changed;
+  uint8_t zz[64];
+};
+
+struct ParState {
+  unsigned p;  // bits consumed
+  int k, j;    // next zigzag index (0: a DC term follows), block within the MCU
+};
+
+__device__ __forceinline__ uint64_t par_pack(const ParState& s, int nb) {
+  return (uint64_t)s.p | ((uint64_t)s.k << 32) | ((uint64_t)s.j << 40) | ((uint64_t)(nb & 0xffff) << 48);
+}
+__device__ __forceinline__ ParState par_unpack(uint64_t v) {
+  ParState s;
+  s.p = (unsigned)v; s.k = (int)(v >> 32) & 63; s.j = (int)(v >> 40) & 15;
+  return s;
+}
+
+struct ParGeom {
+  int nb_mcu, mcux, nblk_scan;
+};
+
+__device__ __forceinline__ int16_t* par_blk(const ParSmem& S, const ParGeom& G, int16_t* coef, int b) {
+  const int mcu = b / G.nb_mcu, j = b - mcu * G.nb_mcu;
+  const int my = mcu / G.mcux, mx = mcu - my * G.mcux;
+  const int c = S.blk_c[j];
+  return coef + (S.c_base[c] + (int64_t)(my * S.c_v[c] + S.blk_y[j]) * S.c_bw[c] + mx * S.c_h[c] + S.blk_x[j]) * 64;
+}
+
+// decodes from st up to the bit `boundary`; returns the number of blocks completed.  WRITE: b = index (scan order) of
+// the block st lies in; coefficients of blocks >= nblk_scan (garbage after the last MCU) are dropped.
+template <bool WRITE>
+__device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, const uint32_t* __restrict__ cl, unsigned Lw, ParState& st,
+                                          unsigned boundary, int16_t* coef, int& b) {
+  unsigned p = st.p;
+  int k = st.k, j = st.j, nb = 0;
+  int16_t* blk = nullptr;
+  if (WRITE) blk = par_blk(S, G, coef, b < G.nblk_scan ? b : 0);
+  while (p < boundary) {
+    const unsigned idx = p >> 5;
+    const uint32_t w0 = idx < Lw ? cl[idx] : 0u;
+    const uint32_t w1 = idx + 1u < Lw ? cl[idx + 1u] : 0u;
+    const uint32_t win = __funnelshift_l(w1, w0, p & 31u);
+    const bool dc = k == 0;
+    const int ti = dc ? S.blk_td[j] : S.blk_ta[j];
+    int used;
+    const int sym = ent_symbol(S, ti, win, used);
+    const int s = sym & 15, r = dc ? 0 : sym >> 4;
+    if (s) {
+      if (WRITE) {
+        const int pos = dc ? 0 : k + r;
+        if (pos < 64 && b < G.nblk_scan) blk[S.zz[pos]] = (int16_t)ent_extend(win, used, s);
+      }
+      used += s;
+    }
+    k = dc ? 1 : (s ? k + r + 1 : (r == 15 ? k + 16 : 64));
+    p += (unsigned)used;
+    if (k >= 64) {
+      k = 0;
+      nb++;
+      if (++j == G.nb_mcu) j = 0;
+      if (WRITE) {
+        b++;
+        blk = par_blk(S, G, coef, b < G.nblk_scan ? b : 0);
+      }
+    }
+  }
+  st.p = p; st.k = k; st.j = j;
+  return nb;
+}
+
+__global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t* __restrict__ files, const JpegImg* __restrict__ imgs,
+                                                                 const JpegTables* __restrict__ tbs, const int32_t* __restrict__ par_list,
+                                                                 uint8_t* __restrict__ clean, uint64_t* __restrict__ sync,
+                                                                 int16_t* __restrict__ coef) {
+  __shared__ ParSmem S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = par_list[blockIdx.x];
+  const JpegImg& im = imgs[img];
+  {
+    const JpegTables* T = tbs + img;
+    for (int i = tid; i < (int)(sizeof(S.fast) / 4); i += kParThreads) ((uint32_t*)S.fast)[i] = ((const uint32_t*)T->fast)[i];
+    for (int i = tid; i < 4 * 18; i += kParThreads) {
+      ((int32_t*)S.maxcode)[i] = ((const int32_t*)T->maxcode)[i];
+      ((int32_t*)S.valoff)[i] = ((const int32_t*)T->valoff)[i];
+    }
+    for (int i = tid; i < 4 * 256 / 4; i += kParThreads) ((uint32_t*)S.vals)[i] = ((const uint32_t*)T->vals)[i];
+    if (tid < 64) S.zz[tid] = c_zigzag[tid];
+    if (tid == 0) {
+      int j = 0;
+      for (int c = 0; c < im.ncomp; c++) {
+        S.c_h[c] = im.ch[c]; S.c_v[c] = im.cv[c]; S.c_bw[c] = im.bw[c]; S.c_base[c] = im.coef_blk + im.blk0[c];
+        for (int by = 0; by < im.cv[c]; by++)
+          for (int bx = 0; bx < im.ch[c]; bx++, j++) {
+            S.blk_c[j] = (uint8_t)c; S.blk_y[j] = (uint8_t)by; S.blk_x[j] = (uint8_t)bx;
+            S.blk_td[j] = (uint8_t)im.td[c]; S.blk_ta[j] = (uint8_t)(2 + im.ta[c]);
+          }
+      }
+    }
+  }
+  ParGeom G;
+  G.nb_mcu = 0;
+  for (int c = 0; c < im.ncomp; c++) G.nb_mcu += im.ch[c] * im.cv[c];
+  G.mcux = im.mcux;
+  G.nblk_scan = im.mcux * im.mcuy * G.nb_mcu;
+  const uint8_t* file = files + im.file_off;
+  const int file_len = im.file_len, scan_off = im.scan_off;
+  uint8_t* cl8 = clean + im.clean_off;
+  __syncthreads();
+
+  // ---- squeeze out the stuffed zeros: 4 consecutive bytes per thread, 1 KiB per pass; the first marker ends the scan ----
+  unsigned wp = 0;
+  for (int base = scan_off;; base += 4 * kParThreads) {
+    const int i0 = base + tid * 4;
+    unsigned b[6];  // previous byte, four own bytes, next byte
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      const int idx = i0 - 1 + q;
+      b[q] = idx < scan_off ? 0u : (idx < file_len ? (unsigned)__ldg(file + idx) : 0x1FFu);  // past the end reads as a marker
+    }
+    int mk = 0x7fffffff;
+    unsigned keep = 0;
+#pragma unroll
+    for (int q = 1; q <= 4; q++) {
+      const bool marker = b[q] > 0xFFu || (b[q] == 0xFFu && b[q + 1] != 0u);
+      if (marker && mk == 0x7fffffff) mk = i0 + q - 1;
+      if (!(b[q - 1] == 0xFFu && b[q] == 0u)) keep |= 1u << (q - 1);
+    }
+    if (tid == 0) S.marker = 0x7fffffff;
+    __syncthreads();
+    if (mk != 0x7fffffff) atomicMin(&S.marker, mk);
+    __syncthreads();
+    const int first_marker = S.marker;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (i0 + q >= first_marker) keep &= ~(1u << q);
+    const int cnt = __popc(keep);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) S.wsum[warp] = (unsigned)incl;
+    __syncthreads();
+    unsigned woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kParThreads / 32; w++) {
+      if (w < warp) woff += S.wsum[w];
+      tot += S.wsum[w];
+    }
+    unsigned pos = wp + woff + (unsigned)(incl - cnt);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if ((keep >> q) & 1u) cl8[(pos++) ^ 3u] = (uint8_t)b[q + 1];
+    wp += tot;
+    __syncthreads();
+    if (first_marker != 0x7fffffff) break;
+  }
+  if (tid < 8) cl8[(wp + tid) ^ 3u] = 0;  // whole last word (+1) reads as zero bits
+  __syncthreads();
+  const unsigned Lw = (wp + 3u) >> 2;
+  const uint32_t* cl = (const uint32_t*)cl8;
+
+  // ---- subsequence runs ----
+  const int nsub = (int)((wp * 8u + kSubBits - 1) / kSubBits) > 0 ? (int)((wp * 8u + kSubBits - 1) / kSubBits) : 1;
+  const int per = (nsub + kParThreads - 1) / kParThreads;
+  const int s0 = tid * per, s1 = s0 + per < nsub ? s0 + per : nsub;
+  uint64_t* out = sync + im.sync_off;
+  int dummy_b = 0;
+  ParState cold;
+  cold.p = (unsigned)s0 * kSubBits; cold.k = 0; cold.j = 0;
+  uint64_t my_in = par_pack(cold, 0);
+  if (s0 < nsub) {
+    ParState st = cold;
+    for (int i = s0; i < s1; i++) {
+      const int nb = par_decode<false>(S, G, cl, Lw, st, (unsigned)(i + 1) * kSubBits, nullptr, dummy_b);
+      out[i] = par_pack(st, nb);
+    }
+  }
+  __syncthreads();
+  for (;;) {
+    uint64_t in = my_in;
+    if (s0 > 0 && s0 < nsub) in = out[s0 - 1] & kStateMask;
+    if (tid == 0) S.changed = 0;
+    __syncthreads();
+    if (in != my_in) {
+      my_in = in;
+      S.changed = 1;
+      ParState st = par_unpack(in);
+      for (int i = s0; i < s1; i++) {
+        const int nb = par_decode<false>(S, G, cl, Lw, st, (unsigned)(i + 1) * kSubBits, nullptr, dummy_b);
+        const uint64_t nw = par_pack(st, nb), old = out[i];
+        out[i] = nw;
+        if (((nw ^ old) & kStateMask) == 0) break;
+      }
+    }
+    __syncthreads();
+    const int ch = S.changed;
+    __syncthreads();
+    if (!ch) break;
+  }
+
+  // ---- block index at the start of every run, then the writing pass ----
+  int mine = 0;
+  for (int i = s0; i < s1; i++) mine += (int)(out[i] >> 48);
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) S.wsum[warp] = (unsigned)incl;
+  __syncthreads();
+  int b = incl - mine;
+  for (int w = 0; w < warp; w++) b += (int)S.wsum[w];
+  if (s0 < nsub) {
+    ParState st = par_unpack(my_in);
+    par_decode<true>(S, G, cl, Lw, st, (unsigned)s1 * kSubBits, coef, b);
+  }
+}
+
+// one warp per (file, component): DC differences -> DC terms, in scan order (a single restart interval)
+__global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs, const int32_t* __restrict__ par_list, int16_t* __restrict__ coef) {
+  const JpegImg& im = imgs[par_list[blockIdx.x]];
+  const int c = blockIdx.y, lane = threadIdx.x;
+  if (c >= im.ncomp) return;
+  const int ch = im.ch[c], cv = im.cv[c], bw = im.bw[c], nbc = ch * cv, mcux = im.mcux, total = im.mcux * im.mcuy * nbc;
+  int16_t* base = coef + (im.coef_blk + im.blk0[c]) * 64;
+  int carry = 0;
+  for (int q0 = 0; q0 < total; q0 += 32) {
+    const int q = q0 + lane;
+    int16_t* ptr = nullptr;
+    int v = 0;
+    if (q < total) {
+      const int m = q / nbc, wi = q - m * nbc, by = wi / ch, bx = wi - by * ch, my = m / mcux, mx = m - my * mcux;
+      ptr = base + ((int64_t)(my * cv + by) * bw + mx * ch + bx) * 64;
+      v = *ptr;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    v += carry;
+    if (ptr) *ptr = (int16_t)v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+
 // grid (ceil(max blocks / 32), n images), 256 threads = 32 blocks of 8 threads
 __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ imgs, const JpegTables* __restrict__ tbs,
                                                    const int16_t* __restrict__ coef, uint8_t* __restrict__ planes) {
@@ -322,7 +601,7 @@ __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ 
 int jpeg_destroy(mtgv_ctx* ctx) {
   JpegState* st = (JpegState*)ctx->jpeg;
   if (!st) return MTGV_OK;
-  cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc);
+  cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc); cudaFree(st->clean); cudaFree(st->sync);
   if (st->desc_host) cudaFreeHost(st->desc_host);
   for (auto& e : st->ev) if (e) cudaEventDestroy(e);
   delete st;
@@ -407,23 +686,44 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   }
   const size_t file_bytes = (size_t)(file_off[n] - file_off[0]);
   const size_t nseg = segs.size();
-  // work items: one warp each; runs of restart intervals of one file, cut so that about 32 warps per SM exist
+  // single-interval files go to the subsequence-parallel kernel (one CTA each); files with restart intervals to the
+  // interval-parallel kernel: one warp per run of intervals, cut so that about 32 warps per SM exist
   std::vector<JpegWork> work;
+  std::vector<int32_t> par_list;
+  int64_t clean_total = 0, sync_total = 0;
   {
+    size_t nseg_multi = 0;
+    for (int i = 0; i < n; i++) {
+      JpegImg& im = imgs[i];
+      im.par = im.nseg == 1 ? 1 : 0;
+      if (im.par) {
+        const int64_t scan_bytes = (int64_t)im.file_len - im.scan_off;
+        im.clean_off = clean_total;
+        im.sync_off = sync_total;
+        clean_total += (scan_bytes + 32 + 15) / 16 * 16;
+        sync_total += scan_bytes * 8 / kSubBits + 2;
+        par_list.push_back(i);
+      } else {
+        nseg_multi += (size_t)im.nseg;
+      }
+    }
     const size_t target = (size_t)ctx->sm_count * 32;
-    const int group = (int)((nseg + target - 1) / target);
+    const int group = (int)((nseg_multi + target - 1) / target);
     for (int i = 0; i < n; i++)
-      for (int s0 = 0; s0 < imgs[i].nseg; s0 += group)
-        work.push_back(JpegWork{i, imgs[i].seg0 + s0, imgs[i].nseg - s0 < group ? imgs[i].nseg - s0 : group, 0});
+      if (!imgs[i].par)
+        for (int s0 = 0; s0 < imgs[i].nseg; s0 += group)
+          work.push_back(JpegWork{i, imgs[i].seg0 + s0, imgs[i].nseg - s0 < group ? imgs[i].nseg - s0 : group, 0});
   }
-  const size_t nwork = work.size();
+  const size_t nwork = work.size(), npar = par_list.size();
   const size_t o_tb = sizeof(JpegImg) * n, o_sg = o_tb + sizeof(JpegTables) * n, o_wk = o_sg + sizeof(JpegSeg) * nseg,
-               desc_bytes = o_wk + sizeof(JpegWork) * nwork;
+               o_pl = o_wk + sizeof(JpegWork) * nwork, desc_bytes = o_pl + sizeof(int32_t) * npar;
   int rc;
   if ((rc = grow(ctx, (void**)&st->files, &st->files_cap, file_bytes + 16))) return rc;
   if ((rc = grow(ctx, (void**)&st->coef, &st->coef_cap, (size_t)nblk_total * 64 * sizeof(int16_t)))) return rc;
   if ((rc = grow(ctx, (void**)&st->planes, &st->planes_cap, (size_t)plane_total))) return rc;
   if ((rc = grow(ctx, (void**)&st->desc, &st->desc_cap, desc_bytes))) return rc;
+  if ((rc = grow(ctx, (void**)&st->clean, &st->clean_cap, (size_t)clean_total + 16))) return rc;
+  if ((rc = grow(ctx, (void**)&st->sync, &st->sync_cap, ((size_t)sync_total + 1) * sizeof(uint64_t)))) return rc;
   MTGV_CUDA_OK(ctx, cudaStreamSynchronize(stream));  // an earlier batch may still be reading the staging buffer
   if (desc_bytes > st->desc_host_cap) {
     if (st->desc_host) MTGV_CUDA_OK(ctx, cudaFreeHost(st->desc_host));
@@ -435,6 +735,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   memcpy(st->desc_host + o_tb, tbs.data(), sizeof(JpegTables) * n);
   memcpy(st->desc_host + o_sg, segs.data(), sizeof(JpegSeg) * nseg);
   memcpy(st->desc_host + o_wk, work.data(), sizeof(JpegWork) * nwork);
+  memcpy(st->desc_host + o_pl, par_list.data(), sizeof(int32_t) * npar);
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->desc, st->desc_host, desc_bytes, cudaMemcpyHostToDevice, stream));
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->files, files + file_off[0], file_bytes, cudaMemcpyHostToDevice, stream));
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->coef, 0, (size_t)nblk_total * 64 * sizeof(int16_t), stream));
@@ -443,9 +744,20 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   const JpegSeg* d_sg = (const JpegSeg*)(st->desc + o_sg);
   const JpegWork* d_wk = (const JpegWork*)(st->desc + o_wk);
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[0], stream));
-  k_jpeg_entropy<<<(unsigned)((nwork + kEntWarps - 1) / kEntWarps), 32 * kEntWarps, 0, stream>>>(st->files, d_img, d_tb, d_sg, d_wk, (int)nwork,
-                                                                                                  st->coef);
-  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  const int32_t* d_pl = (const int32_t*)(st->desc + o_pl);
+  if (npar) {
+    k_jpeg_entropy_par<<<(unsigned)npar, kParThreads, 0, stream>>>(st->files, d_img, d_tb, d_pl, st->clean, st->sync, st->coef);
+    MTGV_CUDA_OK(ctx, cudaGetLastError());
+    k_jpeg_dc<<<dim3((unsigned)npar, 3), 32, 0, stream>>>(d_img, d_pl, st->coef);
+    MTGV_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+  }
+  if (nwork) {
+    k_jpeg_entropy<<<(unsigned)((nwork + kEntWarps - 1) / kEntWarps), 32 * kEntWarps, 0, stream>>>(st->files, d_img, d_tb, d_sg, d_wk,
+                                                                                                    (int)nwork, st->coef);
+    MTGV_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+  }
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));
   k_jpeg_idct<<<dim3((max_blk + 31) / 32, n), 256, 0, stream>>>(d_img, d_tb, st->coef, st->planes);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
@@ -455,7 +767,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[3], stream));
   st->timed = true;
-  ctx->launches += 3;
+  ctx->launches += 2;
   return MTGV_OK;
 }
 

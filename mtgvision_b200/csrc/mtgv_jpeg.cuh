@@ -46,7 +46,9 @@ struct JpegImg {
   int32_t hf[3], vf[3];  // upsampling factors hmax / ch, vmax / cv
   int32_t dh[3], dw[3];  // downsampled component size ceil(h * cv / vmax), ceil(w * ch / hmax)
   int32_t seg0, nseg;
-  int32_t nblk, _pad;
+  int32_t nblk, par;     // par: decoded by the subsequence-parallel kernel (single interval); DC terms are written as differences
+  int64_t clean_off;     // byte-unstuffed copy of the scan in the clean scratch (bytes, multiple of 16)
+  int64_t sync_off;      // checkpoint states of the subsequences (uint64 units)
 };
 
 struct JpegSeg {  // one restart interval (or the whole scan): decoded by one thread

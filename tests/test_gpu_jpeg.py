@@ -46,6 +46,11 @@ def test_pool_sized_batches_bit_exact():
                                        ["420", "444", "422", "440"][k % 4], rst=[0, 0, 4, 1][k % 4], optimize=k % 2))
     _check(ctx, files)
     _check(ctx, files[:1])
+    # long scans: many subsequences per thread of the parallel entropy decoder; flat image: very short scan
+    big = [jpeg_cases.encode(jpeg_cases.image(rng, 680, 488, "noise"), 100, "444", optimize=1),
+           jpeg_cases.encode(jpeg_cases.image(rng, 1080, 1920, "mixed"), 95, "420"),
+           jpeg_cases.encode(np.full((375, 500, 3), 128, np.uint8), 90, "420")]
+    _check(ctx, big)
     # many restart intervals: decoders share warps
     many = [jpeg_cases.encode(jpeg_cases.image(rng, 375, 500, "mixed"), 80, "420", rst=1) for _ in range(64)]
     _check(ctx, many)
