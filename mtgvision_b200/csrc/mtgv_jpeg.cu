@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* 
 // Huffman streams resynchronise by themselves: a decoder started at an arbitrary bit in an arbitrary state falls into
 // step with the true symbol boundaries after a few dozen symbols (Klein & Wiseman 2003; Weissenberger & Schmidt 2018 for
 // GPUs).  The CTA first squeezes the stuffed zeros out of the scan into a clean big-endian copy, then cuts it into
-// 1024-bit subsequences; thread t owns a contiguous run of them.
+// runs, one per thread, with a checkpoint every 512 bits.
 //   round 0   every thread decodes its run from a cold state (bit = start of the run, block start), keeping the state
 //             (bit position, zigzag index, block-in-MCU) and the number of completed blocks at every subsequence end;
 //   round r   a thread whose predecessor's final state differs from the state it started from decodes again from there,
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* 
 //             induction, whatever the data (worst case: as many rounds as threads);
 //   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
 // DC terms are stored as differences and integrated by k_jpeg_dc.
-constexpr int kSubBits = 1024;
+constexpr int kSubBits = 512;
 constexpr int kParThreads = 256;
 constexpr uint64_t kStateMask = (1ull << 48) - 1;
 
@@ -315,10 +315,14 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
   int k = st.k, j = st.j, nb = 0;
   int16_t* blk = nullptr;
   if (WRITE) blk = par_blk(S, G, coef, b < G.nblk_scan ? b : 0);
+  unsigned cur = p >> 5;  // two stream words stay in registers; a symbol is at most 31 bits, so the window moves by 0 or 1 words
+  uint32_t w0 = cur < Lw ? cl[cur] : 0u, w1 = cur + 1u < Lw ? cl[cur + 1u] : 0u;
   while (p < boundary) {
-    const unsigned idx = p >> 5;
-    const uint32_t w0 = idx < Lw ? cl[idx] : 0u;
-    const uint32_t w1 = idx + 1u < Lw ? cl[idx + 1u] : 0u;
+    if ((p >> 5) != cur) {
+      cur = p >> 5;
+      w0 = w1;
+      w1 = cur + 1u < Lw ? cl[cur + 1u] : 0u;
+    }
     const uint32_t win = __funnelshift_l(w1, w0, p & 31u);
     const bool dc = k == 0;
     const int ti = dc ? S.blk_td[j] : S.blk_ta[j];
@@ -441,36 +445,43 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
   const unsigned Lw = (wp + 3u) >> 2;
   const uint32_t* cl = (const uint32_t*)cl8;
 
-  // ---- subsequence runs ----
-  const int nsub = (int)((wp * 8u + kSubBits - 1) / kSubBits) > 0 ? (int)((wp * 8u + kSubBits - 1) / kSubBits) : 1;
-  const int per = (nsub + kParThreads - 1) / kParThreads;
-  const int s0 = tid * per, s1 = s0 + per < nsub ? s0 + per : nsub;
-  uint64_t* out = sync + im.sync_off;
+  // ---- runs: thread t owns bits [t * run_bits, (t + 1) * run_bits) of the clean scan, a checkpoint every kSubBits ----
+  const unsigned total_bits = wp * 8u;
+  unsigned run_bits = ((total_bits + kParThreads - 1) / kParThreads + 31u) & ~31u;
+  if (run_bits < (unsigned)kSubBits) run_bits = kSubBits;
+  const int cps = (int)((run_bits + kSubBits - 1) / kSubBits);
+  const unsigned run0 = (unsigned)tid * run_bits;
+  const bool active = run0 < total_bits || tid == 0;
+  const unsigned run1 = run0 + run_bits < total_bits ? run0 + run_bits : total_bits;
+  const int ncp = active ? (int)((run1 - run0 + kSubBits - 1) / kSubBits) : 0;
+  uint64_t* out = sync + im.sync_off + (size_t)tid * cps;
   int dummy_b = 0;
   ParState cold;
-  cold.p = (unsigned)s0 * kSubBits; cold.k = 0; cold.j = 0;
+  cold.p = run0; cold.k = 0; cold.j = 0;
   uint64_t my_in = par_pack(cold, 0);
-  if (s0 < nsub) {
+  {
     ParState st = cold;
-    for (int i = s0; i < s1; i++) {
-      const int nb = par_decode<false>(S, G, cl, Lw, st, (unsigned)(i + 1) * kSubBits, nullptr, dummy_b);
-      out[i] = par_pack(st, nb);
+    for (int c = 0; c < ncp; c++) {
+      const unsigned bnd = run0 + (unsigned)(c + 1) * kSubBits;
+      const int nb = par_decode<false>(S, G, cl, Lw, st, bnd < run1 ? bnd : run1, nullptr, dummy_b);
+      out[c] = par_pack(st, nb);
     }
   }
   __syncthreads();
   for (;;) {
     uint64_t in = my_in;
-    if (s0 > 0 && s0 < nsub) in = out[s0 - 1] & kStateMask;
+    if (tid > 0 && active) in = out[-1] & kStateMask;  // the predecessor's run is full: its last checkpoint is its run end
     if (tid == 0) S.changed = 0;
     __syncthreads();
     if (in != my_in) {
       my_in = in;
       S.changed = 1;
       ParState st = par_unpack(in);
-      for (int i = s0; i < s1; i++) {
-        const int nb = par_decode<false>(S, G, cl, Lw, st, (unsigned)(i + 1) * kSubBits, nullptr, dummy_b);
-        const uint64_t nw = par_pack(st, nb), old = out[i];
-        out[i] = nw;
+      for (int c = 0; c < ncp; c++) {
+        const unsigned bnd = run0 + (unsigned)(c + 1) * kSubBits;
+        const int nb = par_decode<false>(S, G, cl, Lw, st, bnd < run1 ? bnd : run1, nullptr, dummy_b);
+        const uint64_t nw = par_pack(st, nb), old = out[c];
+        out[c] = nw;
         if (((nw ^ old) & kStateMask) == 0) break;
       }
     }
@@ -482,7 +493,7 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
 
   // ---- block index at the start of every run, then the writing pass ----
   int mine = 0;
-  for (int i = s0; i < s1; i++) mine += (int)(out[i] >> 48);
+  for (int c = 0; c < ncp; c++) mine += (int)(out[c] >> 48);
   int incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -493,9 +504,9 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
   __syncthreads();
   int b = incl - mine;
   for (int w = 0; w < warp; w++) b += (int)S.wsum[w];
-  if (s0 < nsub) {
+  if (ncp > 0) {
     ParState st = par_unpack(my_in);
-    par_decode<true>(S, G, cl, Lw, st, (unsigned)s1 * kSubBits, coef, b);
+    par_decode<true>(S, G, cl, Lw, st, run1, coef, b);
   }
 }
 
@@ -566,34 +577,81 @@ __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ i
   }
 }
 
-// grid (ceil(max pixels / 1024), n images): a thread converts 4 consecutive pixels (linear index, rows may wrap) and
-// stores their 12 bytes as three words when the image's output address is word aligned
+// grid (row bands, n images): a CTA walks the rows of its band; a thread converts 4 consecutive pixels of a row and
+// stores their 12 bytes as three words when the row start is word aligned.  4:2:0 (h2v2) and 4:4:4 interior groups
+// take a straight-line path (one aligned 4-byte luma load, the vertical chroma blend shared by the four pixels);
+// row ends, narrow images and the other sampling modes go through the generic jpeg_pixel.
+constexpr int kColorRows = 8;
+
+__device__ __forceinline__ void ycc_store(int Y, int cb, int cr, uint8_t* px) {
+  cb -= 128; cr -= 128;
+  px[0] = (uint8_t)jpeg_clamp255(Y + ((91881 * cr + 32768) >> 16));
+  px[1] = (uint8_t)jpeg_clamp255(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
+  px[2] = (uint8_t)jpeg_clamp255(Y + ((116130 * cb + 32768) >> 16));
+}
+
 __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ imgs, const uint8_t* __restrict__ planes,
                                                     uint8_t* __restrict__ out) {
   __shared__ JpegImg im;
   for (int i = threadIdx.x; i < (int)(sizeof(JpegImg) / 4); i += 256) ((uint32_t*)&im)[i] = ((const uint32_t*)&imgs[blockIdx.y])[i];
   __syncthreads();
-  const int npix = im.h * im.w;
-  uint8_t* dst = out + im.out_off;
-  const bool aligned = (((uintptr_t)dst) & 3) == 0;
-  for (int i = (blockIdx.x * 256 + threadIdx.x) * 4; i < npix; i += gridDim.x * 1024) {
-    int y = i / im.w, x = i - y * im.w;
-    uint8_t px[12];
-    const int cnt = npix - i < 4 ? npix - i : 4;
+  const int W = im.w, H = im.h, groups = (W + 3) >> 2;
+  const bool h2v2 = im.ncomp == 3 && im.hf[1] == 2 && im.vf[1] == 2 && im.hf[2] == 2 && im.vf[2] == 2 && im.dw[1] > 2;
+  const bool h1v1 = im.ncomp == 3 && im.hf[1] == 1 && im.vf[1] == 1 && im.hf[2] == 1 && im.vf[2] == 1;
+  const uint8_t* PY = planes + im.plane_off[0];
+  const uint8_t* PB = planes + im.plane_off[1];
+  const uint8_t* PR = planes + im.plane_off[2];
+  const int pitchY = im.bw[0] * 8, pitchC = im.ncomp == 3 ? im.bw[1] * 8 : 0;
+  for (int y = blockIdx.x * kColorRows; y < H; y += gridDim.x * kColorRows) {
+    const int yend = y + kColorRows < H ? y + kColorRows : H;
+    for (int yy = y; yy < yend; yy++) {
+      uint8_t* drow = out + im.out_off + (int64_t)yy * W * 3;
+      const bool aligned = (((uintptr_t)drow) & 3) == 0;
+      // vertical neighbours of the chroma triangle filter (edge rows replicated)
+      const int inrow = yy >> 1, dh = im.dh[1];
+      const int other = (yy & 1) ? (inrow + 1 < dh ? inrow + 1 : dh - 1) : (inrow > 0 ? inrow - 1 : 0);
+      const int bias_e = 8, bias_o = 7;
+      for (int g = threadIdx.x; g < groups; g += 256) {
+        const int x0 = g * 4;
+        uint8_t px[12];
+        const int cnt = W - x0 < 4 ? W - x0 : 4;
+        if (h2v2 && x0 > 0 && x0 + 5 < W && cnt == 4) {
+          const uint32_t y4 = *(const uint32_t*)(PY + (int64_t)yy * pitchY + x0);
+          const int j = x0 >> 1;
+          const uint8_t* b0 = PB + (int64_t)inrow * pitchC + j - 1;
+          const uint8_t* b1 = PB + (int64_t)other * pitchC + j - 1;
+          const uint8_t* r0 = PR + (int64_t)inrow * pitchC + j - 1;
+          const uint8_t* r1 = PR + (int64_t)other * pitchC + j - 1;
+          int cb[4], cr[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      int rgb[3] = {0, 0, 0};
-      if (q < cnt) jpeg_pixel(im, planes, y, x, rgb);
-      px[3 * q] = (uint8_t)rgb[0]; px[3 * q + 1] = (uint8_t)rgb[1]; px[3 * q + 2] = (uint8_t)rgb[2];
-      if (++x == im.w) { x = 0; y++; }
-    }
-    if (aligned && cnt == 4) {
-      uint32_t* d = (uint32_t*)(dst + (int64_t)i * 3);
+          for (int q = 0; q < 4; q++) { cb[q] = 3 * b0[q] + b1[q]; cr[q] = 3 * r0[q] + r1[q]; }
+          ycc_store(y4 & 255, (3 * cb[1] + cb[0] + bias_e) >> 4, (3 * cr[1] + cr[0] + bias_e) >> 4, px);
+          ycc_store((y4 >> 8) & 255, (3 * cb[1] + cb[2] + bias_o) >> 4, (3 * cr[1] + cr[2] + bias_o) >> 4, px + 3);
+          ycc_store((y4 >> 16) & 255, (3 * cb[2] + cb[1] + bias_e) >> 4, (3 * cr[2] + cr[1] + bias_e) >> 4, px + 6);
+          ycc_store(y4 >> 24, (3 * cb[2] + cb[3] + bias_o) >> 4, (3 * cr[2] + cr[3] + bias_o) >> 4, px + 9);
+        } else if (h1v1 && cnt == 4) {
+          const uint32_t y4 = *(const uint32_t*)(PY + (int64_t)yy * pitchY + x0);
+          const uint32_t b4 = *(const uint32_t*)(PB + (int64_t)yy * pitchC + x0);
+          const uint32_t r4 = *(const uint32_t*)(PR + (int64_t)yy * pitchC + x0);
 #pragma unroll
-      for (int q = 0; q < 3; q++)
-        d[q] = (uint32_t)px[4 * q] | ((uint32_t)px[4 * q + 1] << 8) | ((uint32_t)px[4 * q + 2] << 16) | ((uint32_t)px[4 * q + 3] << 24);
-    } else {
-      for (int q = 0; q < 3 * cnt; q++) dst[(int64_t)i * 3 + q] = px[q];
+          for (int q = 0; q < 4; q++) ycc_store((y4 >> (8 * q)) & 255, (b4 >> (8 * q)) & 255, (r4 >> (8 * q)) & 255, px + 3 * q);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            int rgb[3] = {0, 0, 0};
+            if (q < cnt) jpeg_pixel(im, planes, yy, x0 + q, rgb);
+            px[3 * q] = (uint8_t)rgb[0]; px[3 * q + 1] = (uint8_t)rgb[1]; px[3 * q + 2] = (uint8_t)rgb[2];
+          }
+        }
+        if (aligned && cnt == 4) {
+          uint32_t* d = (uint32_t*)(drow + x0 * 3);
+#pragma unroll
+          for (int q = 0; q < 3; q++)
+            d[q] = (uint32_t)px[4 * q] | ((uint32_t)px[4 * q + 1] << 8) | ((uint32_t)px[4 * q + 2] << 16) | ((uint32_t)px[4 * q + 3] << 24);
+        } else {
+          for (int q = 0; q < 3 * cnt; q++) drow[x0 * 3 + q] = px[q];
+        }
+      }
     }
   }
 }
@@ -667,7 +725,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
     }
   }
   int64_t nblk_total = 0, plane_total = 0;
-  int max_blk = 0, max_pix = 0;
+  int max_blk = 0, max_h = 0;
   for (int i = 0; i < n; i++) {
     JpegImg& im = imgs[i];
     if (im.h != hw[2 * i] || im.w != hw[2 * i + 1])
@@ -682,7 +740,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
     }
     nblk_total += im.nblk;
     if (im.nblk > max_blk) max_blk = im.nblk;
-    if (im.h * im.w > max_pix) max_pix = im.h * im.w;
+    if (im.h > max_h) max_h = im.h;
   }
   const size_t file_bytes = (size_t)(file_off[n] - file_off[0]);
   const size_t nseg = segs.size();
@@ -701,7 +759,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
         im.clean_off = clean_total;
         im.sync_off = sync_total;
         clean_total += (scan_bytes + 32 + 15) / 16 * 16;
-        sync_total += scan_bytes * 8 / kSubBits + 2;
+        sync_total += scan_bytes * 8 / kSubBits + 2 * kParThreads + 8;
         par_list.push_back(i);
       } else {
         nseg_multi += (size_t)im.nseg;
@@ -738,12 +796,12 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   memcpy(st->desc_host + o_pl, par_list.data(), sizeof(int32_t) * npar);
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->desc, st->desc_host, desc_bytes, cudaMemcpyHostToDevice, stream));
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->files, files + file_off[0], file_bytes, cudaMemcpyHostToDevice, stream));
-  MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->coef, 0, (size_t)nblk_total * 64 * sizeof(int16_t), stream));
   const JpegImg* d_img = (const JpegImg*)st->desc;
   const JpegTables* d_tb = (const JpegTables*)(st->desc + o_tb);
   const JpegSeg* d_sg = (const JpegSeg*)(st->desc + o_sg);
   const JpegWork* d_wk = (const JpegWork*)(st->desc + o_wk);
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[0], stream));
+  MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->coef, 0, (size_t)nblk_total * 64 * sizeof(int16_t), stream));
   const int32_t* d_pl = (const int32_t*)(st->desc + o_pl);
   if (npar) {
     k_jpeg_entropy_par<<<(unsigned)npar, kParThreads, 0, stream>>>(st->files, d_img, d_tb, d_pl, st->clean, st->sync, st->coef);
@@ -762,7 +820,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   k_jpeg_idct<<<dim3((max_blk + 31) / 32, n), 256, 0, stream>>>(d_img, d_tb, st->coef, st->planes);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[2], stream));
-  const int gx = (max_pix + 1023) / 1024;
+  const int gx = (max_h + kColorRows - 1) / kColorRows;
   k_jpeg_color<<<dim3(gx < 1024 ? gx : 1024, n), 256, 0, stream>>>(d_img, st->planes, out);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[3], stream));
