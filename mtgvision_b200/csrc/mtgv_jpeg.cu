@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* 
 //             induction, whatever the data (worst case: as many rounds as threads);
 //   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
 // DC terms are stored as differences and integrated by k_jpeg_dc.
-constexpr int kSubBits = 512;
+constexpr int kSubBits = 512;  // measured: 128 -> 25 % slower (per-checkpoint overhead in the cold pass), 1024 -> later break-off in the rounds
 constexpr int kParThreads = 256;
 constexpr uint64_t kStateMask = (1ull << 48) - 1;
 
@@ -274,8 +274,8 @@ struct ParSmem {
   int32_t valoff[4][18];
   uint8_t vals[4][256];
   uint8_t blk_c[16], blk_y[16], blk_x[16], blk_td[16], blk_ta[16];
-  int32_t c_h[3], c_v[3], c_bw[3];
-  int64_t c_base[3];
+  int64_t j_off[16];           // coefficient index of block j of MCU (0,0)
+  int32_t j_rs[16], j_cs[16];  // ... plus my * j_rs + mx * j_cs for MCU (mx, my)
   unsigned wsum[kParThreads / 32];
   int marker, changed;
   uint8_t zz[64];
@@ -299,11 +299,8 @@ struct ParGeom {
   int nb_mcu, mcux, nblk_scan;
 };
 
-__device__ __forceinline__ int16_t* par_blk(const ParSmem& S, const ParGeom& G, int16_t* coef, int b) {
-  const int mcu = b / G.nb_mcu, j = b - mcu * G.nb_mcu;
-  const int my = mcu / G.mcux, mx = mcu - my * G.mcux;
-  const int c = S.blk_c[j];
-  return coef + (S.c_base[c] + (int64_t)(my * S.c_v[c] + S.blk_y[j]) * S.c_bw[c] + mx * S.c_h[c] + S.blk_x[j]) * 64;
+__device__ __forceinline__ int16_t* par_blk(const ParSmem& S, int16_t* coef, int j, int mx, int my) {
+  return coef + S.j_off[j] + (int64_t)my * S.j_rs[j] + mx * S.j_cs[j];
 }
 
 // decodes from st up to the bit `boundary`; returns the number of blocks completed.  WRITE: b = index (scan order) of
@@ -314,7 +311,13 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
   unsigned p = st.p;
   int k = st.k, j = st.j, nb = 0;
   int16_t* blk = nullptr;
-  if (WRITE) blk = par_blk(S, G, coef, b < G.nblk_scan ? b : 0);
+  int mx = 0, my = 0;
+  if (WRITE) {  // MCU coordinates follow the block counter from here on without divisions
+    const int mcu = b / G.nb_mcu;
+    my = mcu / G.mcux;
+    mx = mcu - my * G.mcux;
+    blk = par_blk(S, coef, j, mx, my);
+  }
   unsigned cur = p >> 5;  // two stream words stay in registers; a symbol is at most 31 bits, so the window moves by 0 or 1 words
   uint32_t w0 = cur < Lw ? cl[cur] : 0u, w1 = cur + 1u < Lw ? cl[cur + 1u] : 0u;
   while (p < boundary) {
@@ -341,10 +344,13 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
     if (k >= 64) {
       k = 0;
       nb++;
-      if (++j == G.nb_mcu) j = 0;
+      if (++j == G.nb_mcu) {
+        j = 0;
+        if (WRITE && ++mx == G.mcux) { mx = 0; my++; }
+      }
       if (WRITE) {
         b++;
-        blk = par_blk(S, G, coef, b < G.nblk_scan ? b : 0);
+        blk = par_blk(S, coef, j, mx, my);
       }
     }
   }
@@ -371,14 +377,15 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
     if (tid < 64) S.zz[tid] = c_zigzag[tid];
     if (tid == 0) {
       int j = 0;
-      for (int c = 0; c < im.ncomp; c++) {
-        S.c_h[c] = im.ch[c]; S.c_v[c] = im.cv[c]; S.c_bw[c] = im.bw[c]; S.c_base[c] = im.coef_blk + im.blk0[c];
+      for (int c = 0; c < im.ncomp; c++)
         for (int by = 0; by < im.cv[c]; by++)
           for (int bx = 0; bx < im.ch[c]; bx++, j++) {
             S.blk_c[j] = (uint8_t)c; S.blk_y[j] = (uint8_t)by; S.blk_x[j] = (uint8_t)bx;
             S.blk_td[j] = (uint8_t)im.td[c]; S.blk_ta[j] = (uint8_t)(2 + im.ta[c]);
+            S.j_off[j] = (im.coef_blk + im.blk0[c] + (int64_t)by * im.bw[c] + bx) * 64;
+            S.j_rs[j] = im.cv[c] * im.bw[c] * 64;
+            S.j_cs[j] = im.ch[c] * 64;
           }
-      }
     }
   }
   ParGeom G;
