@@ -392,14 +392,17 @@ __global__ void __launch_bounds__(kBgThreads, kBgCtas) k_background(const mtgv_e
       if (k < nh) { S.rowX[k] = affine_row_origin(S.rot_inv[1], S.rot_inv[2], k); S.rowY[k] = affine_row_origin(S.rot_inv[4], S.rot_inv[5], k); }
     }
     // crop_to_size: INTER_AREA (nh,nw)->(bg_rh,bg_rw) tables for the band's rows and all columns
+    const bool enlarge = S.bg_rh > nh || S.bg_rw > nw;  // cv::resize: INTER_AREA enlarging = 2-tap area-linear on both axes
     for (int k = tid; k < OW + (by1 - by0); k += nt) {
       AreaEnt e;
       if (k < OW) {
-        area_compact(nw, S.bg_rw, S.bg_x0 + k, &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+        if (enlarge) area_linear_compact(nw, S.bg_rw, S.bg_x0 + k, &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+        else area_compact(nw, S.bg_rw, S.bg_x0 + k, &e.start, &e.n, &e.wl, &e.wm, &e.wr);
         S.ax[k] = e;
         atomicMax(&S.max_nx, e.n & 255);
       } else {
-        area_compact(nh, S.bg_rh, S.bg_y0 + by0 + (k - OW), &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+        if (enlarge) area_linear_compact(nh, S.bg_rh, S.bg_y0 + by0 + (k - OW), &e.start, &e.n, &e.wl, &e.wm, &e.wr);
+        else area_compact(nh, S.bg_rh, S.bg_y0 + by0 + (k - OW), &e.start, &e.n, &e.wl, &e.wm, &e.wr);
         S.ay[k - OW] = e;
       }
     }

@@ -252,6 +252,30 @@ MTGV_HD void area_compact(int ssize, int dsize, int d, int* start, int* n, float
   *n = cnt | flags;
 }
 
+// cv::resize(INTER_AREA) when either axis is enlarged: BOTH axes fall back to the 2-tap linear kernel with the
+// "area" coefficient rule (resize.cpp: area_mode): sx = floor(dx*scale), fx = (dx+1) - (sx+1)*inv_scale, clamped to
+// [0,1) by "fx <= 0 ? 0 : fx - floor(fx)"; at the last source sample the single tap S[ssize-1] is used.
+// Same compact form as area_compact: taps S[start] * wl (+ S[start+1] * wr).
+MTGV_HD void area_linear_compact(int ssize, int dsize, int d, int* start, int* n, float* wl, float* wm, float* wr) {
+  double inv_scale = MTGV_DDIV((double)dsize, (double)ssize);
+  double scale = MTGV_DDIV(1.0, inv_scale);
+  int sx = (int)floor(MTGV_DMUL((double)d, scale));
+  float fx = (float)MTGV_DSUB((double)(d + 1), MTGV_DMUL((double)(sx + 1), inv_scale));
+  fx = fx <= 0.f ? 0.f : fx - floorf(fx);
+  if (sx < 0) { sx = 0; fx = 0.f; }
+  *wm = 0.f;
+  if (sx >= ssize - 1) {
+    *start = ssize - 1;
+    *wl = 1.f; *wr = 0.f;
+    *n = 1 | 256;
+    return;
+  }
+  *start = sx;
+  *wl = 1.f - fx;
+  *wr = fx;
+  *n = 2 | 256 | 512;
+}
+
 // crop_to_size integer geometry (mtgvision/util/image.py:359-376).
 MTGV_HD void crop_geometry(int ih, int iw, int sh, int sw, bool pad, int* rh, int* rw, int* y0, int* x0) {
   double fh = MTGV_DDIV((double)ih, (double)sh), fw = MTGV_DDIV((double)iw, (double)sw);

@@ -35,6 +35,15 @@ void hh_affine_coords(const double* Ainv, int dh, int dw, int32_t* X, int32_t* Y
 
 int hh_area_taps(int ssize, int dsize, int d, int* start, float* w) { return area_taps(ssize, dsize, d, start, w); }
 
+// the 2-tap table cv::resize(INTER_AREA) uses when enlarging: returns the tap count, weights in w[0..1]
+int hh_area_linear_taps(int ssize, int dsize, int d, int* start, float* w) {
+  int n;
+  float wl, wm, wr;
+  area_linear_compact(ssize, dsize, d, start, &n, &wl, &wm, &wr);
+  w[0] = wl; w[1] = wr;
+  return n & 255;
+}
+
 int hh_expand_encoder(const mtgv_enc_tape* tape, int n, const mtgv_enc_config* cfg, int card_h, int card_w, int n_cards,
                       const int32_t* labels3, const int32_t* grp_off, const int32_t* grp_mem, int n_bgs,
                       const int32_t* bg_hw, mtgv_enc_params* out) {

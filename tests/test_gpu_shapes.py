@@ -27,6 +27,8 @@ CASES = {
     "small_output_many_taps": ((680, 488), [(375, 500), (300, 400)], (128, 96)),  # INTER_AREA scales up to 5.3 (limit 6)
     "wide_cards_two_chunks": ((936, 672), [(375, 500), (500, 375)], (192, 128)),
     "square_output": ((680, 488), [(375, 500), (400, 400)], (160, 160)),
+    # backgrounds smaller than the output: crop_to_size enlarges with cv2's 2-tap "area-linear" INTER_AREA kernel
+    "tiny_backgrounds_enlarged": ((680, 488), [(90, 120), (60, 50), (128, 100), (150, 127), (40, 333)], (192, 128)),
 }
 
 

@@ -115,6 +115,29 @@ def test_area_taps_match_restatement(hh):
             assert [np.float32(w[k]) for k in range(n)] == [a for _, a in ref[d]]
 
 
+def test_area_linear_taps_reproduce_cv2_enlarging_inter_area(hh):
+    """cv2.resize(INTER_AREA) with either axis enlarged (crop_to_size of a small background, util/image.py:321-334)
+    is a separable 2-tap filter with the 'area' coefficient rule: rebuilt from the harness tables it must equal cv2."""
+    rng = np.random.default_rng(0)
+    for (sh, sw), (dh, dw) in [((90, 120), (192, 256)), ((60, 50), (230, 192)), ((128, 100), (192, 150)), ((191, 127), (192, 128)),
+                               ((100, 300), (192, 576)), ((7, 5), (192, 137))]:
+        src = rng.random((sh, sw, 3), dtype=np.float32)
+        ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)
+
+        def table(ssize, dsize):
+            T = np.zeros((dsize, ssize), np.float64)
+            for d in range(dsize):
+                start = C.c_int(0)
+                w = (C.c_float * 2)()
+                n = hh.hh_area_linear_taps(ssize, dsize, d, C.byref(start), w)
+                for k in range(n):
+                    T[d, start.value + k] += w[k]
+            return T
+
+        got = np.einsum("ys,sxc->yxc", table(sh, dh), np.einsum("xs,ysc->yxc", table(sw, dw), src.astype(np.float64)))
+        assert np.abs(got - ref).max() < 1e-6, ((sh, sw), (dh, dw), np.abs(got - ref).max())
+
+
 def test_host_mask_matches_reference_kat(hh):
     import hashlib
     for hw, rad, sha in [((680, 488), 34, "75fac4e48730e3c0"), ((680, 488), 32, "d7923dd2973e78fe")]:
