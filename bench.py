@@ -584,11 +584,64 @@ def run_jpeg(args):
                                        "sample": f"cv2.imdecode of {min(n, 256)} of the same files, 1 thread"}}), flush=True)
 
 
+def run_jpegenc(args):
+    """Dataset-writer image encode (save_sample -> imwrite, od_datasets.py:829-831): 256 scenes of 640x640 per step."""
+    import cv2
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mtgvision_b200 import synth
+    from mtgvision_b200.context import Context
+
+    n, S = 256, 640
+    rng = np.random.default_rng(0)
+    scenes = np.empty((n, S, S, 3), np.uint8)
+    for k in range(n):  # low-pass background with sharp-edged patches: scene-like statistics
+        bg = cv2.resize(synth.synth_bg(k % 64), (S, S), interpolation=cv2.INTER_LINEAR)
+        for _ in range(4):
+            y, x, h, w = rng.integers(0, S - 200), rng.integers(0, S - 200), rng.integers(60, 200), rng.integers(60, 200)
+            bg[y:y + h, x:x + w] = synth.synth_card(int(rng.integers(0, 16)))[:h, :w]
+        scenes[k] = bg
+    ctx = Context(0)
+    dev = torch.from_numpy(scenes).cuda().permute(0, 3, 1, 2).contiguous()  # mtgv_det_batch's layout
+    for _ in range(args.warmup):
+        out, lens = ctx.encode_jpegs_device(dev)
+    torch.cuda.synchronize()
+    kms = np.zeros(2)
+    for _ in range(args.steps):
+        out, lens = ctx.encode_jpegs_device(dev)
+        kms += ctx.jpeg_encode_last_kernel_ms()
+    kms /= args.steps
+    ms = float(kms.sum())
+    ctx.encode_jpegs_host(dev)  # untimed: allocates the compact and pinned buffers the context keeps
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        files = ctx.encode_jpegs_host(dev)
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    cv2.setNumThreads(1)
+    t0 = time.perf_counter()
+    ref = [cv2.imencode(".jpg", cv2.cvtColor(scenes[k], cv2.COLOR_RGB2BGR))[1].tobytes() for k in range(64)]
+    cpu = 64 / (time.perf_counter() - t0)
+    same = all(files[k].tobytes() == ref[k] for k in range(64))
+    out_bytes = sum(len(f) for f in files)
+    print(json.dumps({"metric": "scenes JPEG-encoded per second (640x640, quality 95, 4:2:0)", "value": n / (ms * 1e-3), "unit": "images/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "dtype": "i32",
+                      "config": {"workload": "jpegenc", "scenes": n, "size": [S, S], "mean_file_bytes": out_bytes // n,
+                                 "kernel_ms": {"k_jpegenc_dct": kms[0], "k_jpegenc_huff": kms[1]},
+                                 "timing": "value: CUDA events around the two kernels inside the library; e2e: host wall clock of "
+                                           "Context.encode_jpegs_host (device uint8 NCHW scenes in, the files in pinned host memory out)"},
+                      "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": out_bytes},
+                      "bytes_equal_cv2": same,
+                      "cpu_baseline": {"value": cpu, "unit": "images/s", "cores": 1, "kind": "reference",
+                                       "sample": "cv2.imencode of 64 of the same scenes, 1 thread"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jpeg-rst", type=int, default=0)
     ap.add_argument("--jpeg-files", type=int, default=2048)
-    ap.add_argument("--workload", default="encoder", choices=["encoder", "det640", "det1280", "dewarp", "jpeg"])
+    ap.add_argument("--workload", default="encoder", choices=["encoder", "det640", "det1280", "dewarp", "jpeg", "jpegenc"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -604,6 +657,8 @@ def main():
         run_dewarp(args)
     elif args.workload == "jpeg":
         run_jpeg(args)
+    elif args.workload == "jpegenc":
+        run_jpegenc(args)
     elif args.workload != "encoder":
         run_det(args)
     elif args.impl == "reference":

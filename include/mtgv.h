@@ -411,6 +411,32 @@ int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* f
  * mtgv_decode_jpeg_batch call, measured with CUDA events on its stream; waits for that batch (bench bookkeeping). */
 int mtgv_jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms3);
 
+/* ------------------------------------------------------------------------------------ */
+/* Image encode for the on-disk dataset writer (mtgvision/od_datasets.py:794-832), 8f.2   */
+/* ------------------------------------------------------------------------------------ */
+
+#define MTGV_LAYOUT_NHWC 0 /* [n,h,w,3] */
+#define MTGV_LAYOUT_NCHW 1 /* [n,3,h,w] (mtgv_det_batch's output) */
+
+/* save_sample's imwrite (od_datasets.py:829-831; util/image.py:95-104: cv2.imwrite of the uint8 RGB image) for n
+ * images at once, on the device: baseline JPEG, 4:2:0, standard Huffman tables, JFIF header - the FILE BYTES of
+ * cv2.imencode(".jpg", bgr, [IMWRITE_JPEG_QUALITY, quality]) (cv2.imwrite's default quality is 95).
+ * images: device uint8 RGB in `layout`; h and w multiples of 16 (save_sample asserts 640x640), else MTGV_ERR_LIMIT.
+ * out: device, image i's file at out + i*cap (cap: bytes per image, multiple of 4); out_len: device int32 [n], the
+ * file length, or -1 when the file does not fit in cap (nothing usable is written for that image). */
+int mtgv_encode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int layout, int quality, uint8_t* out,
+                           int64_t cap, int32_t* out_len, void* stream);
+
+/* Packs the files of mtgv_encode_jpeg_batch back to back so that one transfer brings them to the host: offsets (device
+ * int64 [n+1]) receives the exclusive prefix sum of the file lengths (files that did not fit count as empty), compact
+ * (device, at least the sum of the lengths; n*cap always suffices) file i at compact + offsets[i]. */
+int mtgv_compact_jpeg_files(mtgv_ctx* ctx, const uint8_t* slots, int64_t cap, const int32_t* out_len, int n, uint8_t* compact,
+                            int64_t* offsets, void* stream);
+
+/* Device time of the two kernels (colour + DCT + quantisation, Huffman coding + stuffing) of the last
+ * mtgv_encode_jpeg_batch call, CUDA events on its stream; waits for that batch (bench bookkeeping). */
+int mtgv_jpeg_encode_last_kernel_ms(mtgv_ctx* ctx, float* ms2);
+
 /* Number of kernels launched by this context since creation (bench bookkeeping). */
 int64_t mtgv_launch_count(const mtgv_ctx* ctx);
 

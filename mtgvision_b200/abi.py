@@ -119,6 +119,9 @@ PARAMS_DTYPE = np.dtype(EncParams)
 XOP_DTYPE = np.dtype(XOp)
 
 
+LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
+
+
 class MtgvError(RuntimeError):
     pass
 
@@ -160,6 +163,9 @@ def load_library(path: str | None = None) -> C.CDLL:
         "mtgv_extract_dewarped": (i32, [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]),
         "mtgv_jpeg_info": (i32, [vp, vp, i64, vp]),
         "mtgv_jpeg_last_kernel_ms": (i32, [vp, vp]),
+        "mtgv_encode_jpeg_batch": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i64, vp, vp]),
+        "mtgv_jpeg_encode_last_kernel_ms": (i32, [vp, vp]),
+        "mtgv_compact_jpeg_files": (i32, [vp, vp, i64, vp, i32, vp, vp, vp]),
         "mtgv_decode_jpeg_batch": (i32, [vp, vp, vp, i32, vp, vp, vp, vp]),
         "mtgv_launch_count": (i64, [vp]),
     }

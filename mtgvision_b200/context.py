@@ -291,6 +291,55 @@ class Context:
         self._check(rc, "mtgv_set_bg_pool")
         self.n_bgs = len(files)
 
+    # ------------------------------------------------------------------ image encode for the dataset writer
+    def encode_jpegs(self, images: torch.Tensor, quality: int = 95, layout: str | None = None, cap: int | None = None) -> list[bytes]:
+        """cv2.imwrite's JPEG bytes (save_sample -> imwrite, od_datasets.py:829-831) for a batch of uint8 RGB images on the
+        device: (n,3,H,W) or (n,H,W,3), H and W multiples of 16.  Returns one `bytes` per image."""
+        return [v.tobytes() for v in self.encode_jpegs_host(images, quality, layout, cap)]
+
+    def encode_jpegs_host(self, images: torch.Tensor, quality: int = 95, layout: str | None = None, cap: int | None = None) -> list[np.ndarray]:
+        """Like `encode_jpegs`, without the per-file copy: the files are compacted on the device, brought over in ONE
+        transfer into a pinned buffer the context keeps, and returned as uint8 views of it (valid until the next call)."""
+        out, lens = self.encode_jpegs_device(images, quality, layout, cap)
+        n, capb = out.shape
+        if n == 0:
+            return []
+        if getattr(self, "_jpeg_compact", None) is None or self._jpeg_compact.numel() < n * capb:
+            self._jpeg_compact = torch.empty(n * capb, dtype=torch.uint8, device=self.device)
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=self.device)
+        rc = self.lib.mtgv_compact_jpeg_files(self._h, _ptr(out), C.c_int64(capb), _ptr(lens), n, _ptr(self._jpeg_compact), _ptr(offsets),
+                                              self._stream())
+        self._check(rc, "mtgv_compact_jpeg_files")
+        meta = torch.cat([offsets, lens.to(torch.int64)]).cpu().numpy()  # one small transfer, synchronises
+        off_h, lens_h = meta[: n + 1], meta[n + 1:]
+        if (lens_h < 0).any():
+            raise abi.MtgvError(f"mtgv_encode_jpeg_batch: {int((lens_h < 0).sum())} image(s) do not fit in cap={capb} bytes")
+        total = int(off_h[n])
+        if getattr(self, "_jpeg_pinned", None) is None or self._jpeg_pinned.numel() < total:
+            self._jpeg_pinned = torch.empty(max(total + total // 4, 1 << 20), dtype=torch.uint8).pin_memory()
+        self._jpeg_pinned[:total].copy_(self._jpeg_compact[:total])
+        host = self._jpeg_pinned.numpy()
+        return [host[off_h[i]: off_h[i] + lens_h[i]] for i in range(n)]
+
+    def encode_jpegs_device(self, images: torch.Tensor, quality: int = 95, layout: str | None = None, cap: int | None = None):
+        assert images.is_cuda and images.dtype == torch.uint8 and images.ndim == 4 and images.is_contiguous()
+        if layout is None:
+            layout = "nchw" if images.shape[1] == 3 and images.shape[3] != 3 else "nhwc"
+        n = images.shape[0]
+        h, w = (images.shape[2], images.shape[3]) if layout == "nchw" else (images.shape[1], images.shape[2])
+        cap = int(cap) if cap is not None else (h * w * 3 // 2 + 4096) // 4 * 4
+        out = torch.empty((n, cap), dtype=torch.uint8, device=self.device)
+        lens = torch.empty(n, dtype=torch.int32, device=self.device)
+        rc = self.lib.mtgv_encode_jpeg_batch(self._h, _ptr(images), n, h, w, abi.LAYOUT_NCHW if layout == "nchw" else abi.LAYOUT_NHWC,
+                                             int(quality), _ptr(out), C.c_int64(cap), _ptr(lens), self._stream())
+        self._check(rc, "mtgv_encode_jpeg_batch")
+        return out, lens
+
+    def jpeg_encode_last_kernel_ms(self) -> tuple[float, float]:
+        ms = (C.c_float * 2)()
+        self._check(self.lib.mtgv_jpeg_encode_last_kernel_ms(self._h, ms), "mtgv_jpeg_encode_last_kernel_ms")
+        return ms[0], ms[1]
+
     # ------------------------------------------------------------------ parity / debug entries
     def warp_perspective(self, src: torch.Tensor, M: torch.Tensor, dsize_hw) -> torch.Tensor:
         """src (n,h,w,c) float32, M (n,3,3) float64 -> (n,dh,dw,c) float32, cv2.warpPerspective semantics."""

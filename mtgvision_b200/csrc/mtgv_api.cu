@@ -64,6 +64,7 @@ void mtgv_destroy(mtgv_ctx* ctx) {
   cudaDeviceSynchronize();
   det_destroy(ctx);
   jpeg_destroy(ctx);
+  jpegenc_destroy(ctx);
   free_cards(ctx);
   free_bgs(ctx);
   cudaFree(ctx->cfg_dev); cudaFree(ctx->alpha0); cudaFree(ctx->alpha_scratch); cudaFree(ctx->sync_words);
@@ -293,6 +294,34 @@ int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* f
   if (!files || !file_off || !out || !out_off || !hw || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: bad arguments");
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   return jpeg_decode_batch(ctx, files, file_off, n, out, out_off, hw, (cudaStream_t)stream);
+}
+
+int mtgv_encode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int layout, int quality, uint8_t* out,
+                           int64_t cap, int32_t* out_len, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (n == 0) return MTGV_OK;
+  if (!images || !out || !out_len || n < 0 || h < 16 || w < 16 || (layout != MTGV_LAYOUT_NHWC && layout != MTGV_LAYOUT_NCHW) ||
+      quality < 1 || quality > 100 || cap < 1024 || (cap & 3))
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_encode_jpeg_batch: bad arguments");
+  if ((h & 15) || (w & 15) || h > 65520 || w > 65520)
+    return fail(ctx, MTGV_ERR_LIMIT, "mtgv_encode_jpeg_batch: image sides must be multiples of 16 (whole 4:2:0 MCUs)");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return jpegenc_batch(ctx, images, n, h, w, layout, quality, out, cap, out_len, (cudaStream_t)stream);
+}
+
+int mtgv_compact_jpeg_files(mtgv_ctx* ctx, const uint8_t* slots, int64_t cap, const int32_t* out_len, int n, uint8_t* compact,
+                            int64_t* offsets, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!offsets || n < 0 || (n > 0 && (!slots || !out_len || !compact || cap < 4 || (cap & 3))))
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_compact_jpeg_files: bad arguments");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return jpegenc_compact(ctx, slots, cap, out_len, n, compact, offsets, (cudaStream_t)stream);
+}
+
+int mtgv_jpeg_encode_last_kernel_ms(mtgv_ctx* ctx, float* ms2) {
+  if (!ctx || !ms2) return MTGV_ERR_INVALID;
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  return jpegenc_last_kernel_ms(ctx, ms2);
 }
 
 int mtgv_run_plane_ops(mtgv_ctx* ctx, float* img, int n, int h, int w, int c, const mtgv_x_op* ops, int n_ops, const void* fields,

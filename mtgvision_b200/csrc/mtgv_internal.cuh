@@ -59,6 +59,8 @@ struct mtgv_ctx {
   void* det = nullptr;
   // JPEG decode scratch lives in mtgv_jpeg.cu
   void* jpeg = nullptr;
+  // JPEG encode scratch lives in mtgv_jpegenc.cu
+  void* jpegenc = nullptr;
 };
 
 namespace mtgv {
@@ -148,6 +150,13 @@ int jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms);
 int jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw);
 int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
                       const int32_t* hw, cudaStream_t st);
+// mtgv_jpegenc.cu
+int jpegenc_destroy(mtgv_ctx* ctx);
+int jpegenc_last_kernel_ms(mtgv_ctx* ctx, float* ms);
+int jpegenc_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int layout, int quality, uint8_t* out, int64_t cap,
+                  int32_t* out_len, cudaStream_t st);
+int jpegenc_compact(mtgv_ctx* ctx, const uint8_t* slots, int64_t cap, const int32_t* out_len, int n, uint8_t* compact, int64_t* offsets,
+                    cudaStream_t st);
 // mtgv_fg.cu
 int fg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* fg_out, cudaStream_t st);
 int bg_launch(mtgv_ctx* ctx, const mtgv_enc_params* params, int m, int OH, int OW, float* bg_out, cudaStream_t st);

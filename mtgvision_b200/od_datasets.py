@@ -160,8 +160,38 @@ def save_sample(sample: dict, i: int, label_dir, img_dir, ext: Literal["png", "j
     cv2.imwrite(os.path.join(img_dir, f"image_{i:04d}.{ext}"), cv2.cvtColor(u8, cv2.COLOR_RGB2BGR))
 
 
+def save_batch(generator: Gen, batch: dict, first_i: int, label_dir, img_dir, quality: int = 95) -> int:
+    """`save_sample` for a whole `Gen.random_batch(n, "uint8")`: the label text is formatted on the host exactly like
+    `save_sample`, the images are JPEG-encoded on the device (`mtgv_encode_jpeg_batch`: the bytes cv2.imwrite would write)
+    and only the compressed files cross PCIe.  Returns the number of samples written."""
+    image = batch["image"]
+    n, _, H, W = image.shape
+    files = generator.ctx.encode_jpegs_host(image, quality)  # views of one pinned buffer, written out below
+    counts = batch["counts"].cpu().numpy()
+    kps = batch["keypoints"].cpu().numpy()
+    labels = batch["labels"].cpu().numpy()
+    P = 4 if generator.kind == "obb" else 8
+    for k in range(n):
+        i = first_i + k
+        lines = []
+        for pts, label in zip(kps[k, : counts[k], :P], labels[k, : counts[k]].astype(np.int64)):
+            pts = np.asarray(pts, dtype=np.float64) / (W, H)  # points are (w, h)
+            if np.any(pts < 0) or np.any(pts > 1):
+                warnings.warn(f"points for image {i} are out of bounds, yolo will consider these invalid")
+            lines.append(f"{label} {' '.join(map(str, pts.flatten()))}")
+        with open(os.path.join(label_dir, f"image_{i:04d}.txt"), "w") as f:
+            for ann in lines:
+                f.write(ann + "\n")
+        with open(os.path.join(img_dir, f"image_{i:04d}.jpg"), "wb") as f:
+            f.write(files[k])
+    return n
+
+
 def create_yolo_obb_dataset(generator: Gen, *, output_dir: str, num_train: int = 20000, num_val_ratio: float = 0.1,
-                            num_test_ratio: float = 0.1, ext: Literal["png", "jpg"] = "jpg"):
+                            num_test_ratio: float = 0.1, ext: Literal["png", "jpg"] = "jpg", batch: int = 256):
+    """od_datasets.py:732-791.  ext="jpg" with scene sides that are multiples of 16 (the reference asserts 640x640) takes
+    the batched path: scenes are generated AND JPEG-encoded on the GPU, `batch` at a time; otherwise one `save_sample`
+    per scene like the reference."""
     import yaml
 
     output_dir = Path(output_dir)
@@ -173,8 +203,16 @@ def create_yolo_obb_dataset(generator: Gen, *, output_dir: str, num_train: int =
     with open(output_dir / "mtg_obb.yaml", "w") as fp:
         yaml.safe_dump({"path": ".", "train": str(img_dir / "train"), "val": str(img_dir / "val"),
                         "test": str(img_dir / "test"), "names": {0: "card", 1: "card_top", 2: "card_bottom"}}, fp)
+    S = generator.bg_size_hw if isinstance(generator.bg_size_hw, (tuple, list)) else (generator.bg_size_hw, generator.bg_size_hw)
+    batched = ext == "jpg" and batch > 1 and S[0] % 16 == 0 and S[1] % 16 == 0
     for name, num in [("train", num_train), ("val", int(num_val_ratio * num_train)), ("test", int(num_test_ratio * num_train))]:
         (img_dir / name).mkdir(exist_ok=True, parents=True)
         (label_dir / name).mkdir(exist_ok=True, parents=True)
+        if batched:
+            i = 0
+            while i < num:
+                b = generator.random_batch(min(batch, num - i), "uint8")
+                i += save_batch(generator, b, i, label_dir / name, img_dir / name)
+            continue
         for i in range(num):
             save_sample(generator.random(), i=i, label_dir=label_dir / name, img_dir=img_dir / name, ext=ext)

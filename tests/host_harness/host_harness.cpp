@@ -6,6 +6,7 @@
 #include "../../mtgvision_b200/csrc/mtgv_mask.h"
 #include "../../mtgvision_b200/csrc/mtgv_det.cuh"
 #include "../../mtgvision_b200/csrc/mtgv_jpeg.cuh"
+#include "../../mtgvision_b200/csrc/mtgv_jpegenc.cuh"
 
 using namespace mtgv;
 
@@ -132,5 +133,67 @@ int hh_jpeg_decode(const uint8_t* file, int64_t len, int32_t* hw, uint8_t* out, 
       for (int k = 0; k < 3; k++) out[((size_t)y * im.w + x) * 3 + k] = (uint8_t)rgb[k];
     }
   return 0;
+}
+
+// Host run of the JPEG encode arithmetic of mtgv_jpegenc.cuh (the device kernels call the same functions per pixel /
+// block).  rgb: [h,w,3] uint8, h and w multiples of 16.  Returns the file length (<= cap) or -1.
+int64_t hh_jpeg_encode(const uint8_t* rgb, int h, int w, int quality, uint8_t* out, int64_t cap) {
+  if (h % 16 || w % 16) return -1;
+  JpegEncTables T;
+  jpegenc_tables(quality, &T);
+  std::vector<uint8_t> o = jpegenc_header(h, w, T);
+  const int mx = w / 16, my = h / 16, nmcu = mx * my;
+  std::vector<int16_t> coef((size_t)nmcu * 6 * 64);
+  for (int m = 0; m < nmcu; m++) {
+    const int y0 = (m / mx) * 16, x0 = (m % mx) * 16;
+    int Y[16][16], Cb[8][8], Cr[8][8];
+    for (int qy = 0; qy < 8; qy++)
+      for (int qx = 0; qx < 8; qx++) {
+        int sb = 0, sr = 0;
+        for (int dy = 0; dy < 2; dy++)
+          for (int dx = 0; dx < 2; dx++) {
+            const uint8_t* p = rgb + ((size_t)(y0 + 2 * qy + dy) * w + x0 + 2 * qx + dx) * 3;
+            int y, cb, cr;
+            jpegenc_ycc(p[0], p[1], p[2], &y, &cb, &cr);
+            Y[2 * qy + dy][2 * qx + dx] = y; sb += cb; sr += cr;
+          }
+        const int bias = ((x0 / 2 + qx) & 1) ? 2 : 1;
+        Cb[qy][qx] = (sb + bias) >> 2; Cr[qy][qx] = (sr + bias) >> 2;
+      }
+    for (int j = 0; j < 6; j++) {
+      int ws[8][8], d[8], r[8];
+      for (int row = 0; row < 8; row++) {
+        for (int k = 0; k < 8; k++) d[k] = (j < 4 ? Y[(j >> 1) * 8 + row][(j & 1) * 8 + k] : (j == 4 ? Cb[row][k] : Cr[row][k])) - 128;
+        jpegenc_fdct8(d, r, true);
+        for (int k = 0; k < 8; k++) ws[row][k] = r[k];
+      }
+      int nat[64];
+      for (int col = 0; col < 8; col++) {
+        for (int k = 0; k < 8; k++) d[k] = ws[k][col];
+        jpegenc_fdct8(d, r, false);
+        for (int k = 0; k < 8; k++) nat[k * 8 + col] = jpegenc_quant(r[k], T.q[j < 4 ? 0 : 1][k * 8 + col]);
+      }
+      for (int k = 0; k < 64; k++) coef[((size_t)m * 6 + j) * 64 + k] = (int16_t)nat[kJpegZigzag[k]];
+    }
+  }
+  struct Bits {
+    std::vector<uint8_t>* o; uint64_t acc = 0; int n = 0;
+    void operator()(unsigned code, int size) {
+      acc = (acc << size) | code; n += size;
+      while (n >= 8) { uint8_t b = (uint8_t)(acc >> (n - 8)); o->push_back(b); if (b == 0xFF) o->push_back(0); n -= 8; }
+    }
+  } put;
+  put.o = &o;
+  for (int m = 0; m < nmcu; m++)
+    for (int j = 0; j < 6; j++) {
+      const int pb = jpegenc_pred_block(m, j);
+      const int t = j < 4 ? 0 : 1;
+      jpegenc_block(&coef[((size_t)m * 6 + j) * 64], pb < 0 ? 0 : coef[(size_t)pb * 64], T.dc[t], T.ac[t], put);
+    }
+  if (put.n) put((1u << (8 - put.n)) - 1u, 8 - put.n);
+  o.push_back(0xFF); o.push_back(0xD9);
+  if ((int64_t)o.size() > cap) return -1;
+  memcpy(out, o.data(), o.size());
+  return (int64_t)o.size();
 }
 }
