@@ -456,6 +456,15 @@ def run_det(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     placed = int((b["accepted"] >= 0).sum())
+    # the dataset writer's path (create_yolo_obb_dataset): scenes generated AND JPEG-encoded on the device, files to pinned host memory
+    ctx.encode_jpegs_host(gen.random_batch(batch)["image"])  # untimed: allocates the encoder's buffers
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    file_bytes = 0
+    for _ in range(args.steps):
+        files = ctx.encode_jpegs_host(gen.random_batch(batch)["image"])
+        file_bytes += sum(len(f) for f in files)
+    writer_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     cpu = None
     if not args.no_cpu_baseline:
         _DET_STATE["cards"] = [cards.images[k] for k in range(32)]
@@ -472,6 +481,10 @@ def run_det(args):
                       "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                       "config": {"workload": args.workload, "batch": batch, "max_cards": max_cards - 1, "kind": "seg",
                                  "placed_cards_last_batch": placed, "out": "uint8 NCHW"},
+                      "writer": {"value": batch / (writer_ms * 1e-3), "unit": "scenes/s", "ms_per_batch": writer_ms,
+                                 "d2h_bytes_per_step": file_bytes // args.steps,
+                                 "api": "Gen.random_batch + Context.encode_jpegs_host: scene generation and JPEG encode on the device, "
+                                        "files (cv2.imwrite's bytes) in pinned host memory; host wall clock"},
                       "gpu_launches": int(ctx.launch_count() - l0), "cpu_baseline": cpu}), flush=True)
 
 
