@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* 
 //   round r   a thread whose predecessor's final state differs from the state it started from decodes again from there,
 //             overwriting its checkpoints until one repeats (from there on its earlier decode was already right);
 //             repeated until no thread starts over - then every checkpoint follows from the true start of the scan by
-//             induction, whatever the data (worst case: as many rounds as threads);
+//             induction, whatever the data (worst case: as many rounds as threads).  (Measured and dropped: queueing the
+//             runs that start over and decoding them one checkpoint per step with packed warps - 10 % slower, the extra
+//             barriers and window reloads cost more than the idle lanes);
 //   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
 // DC terms are stored as differences and integrated by k_jpeg_dc.
 constexpr int kSubBits = 512;  // measured: 128 -> 25 % slower (per-checkpoint overhead in the cold pass), 1024 -> later break-off in the rounds
