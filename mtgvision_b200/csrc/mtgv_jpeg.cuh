@@ -139,6 +139,7 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
       im->ncomp = s[5];
       if (im->ncomp != 1 && im->ncomp != 3) return jpeg_fail(err, "only grayscale or YCbCr files are supported");
       if (n < 6 + 3 * im->ncomp || im->h <= 0 || im->w <= 0) return jpeg_fail(err, "bad frame header");
+      if (im->h > 16384 || im->w > 16384) return jpeg_fail(err, "image larger than 16384 pixels per side");
       for (int c = 0; c < im->ncomp; c++) {
         comp_id[c] = s[6 + 3 * c];
         im->ch[c] = s[7 + 3 * c] >> 4;

@@ -17,6 +17,7 @@ from __future__ import annotations
 import os
 import random
 import uuid
+import warnings
 from math import ceil
 from typing import Iterator, Literal, Optional
 
@@ -54,12 +55,14 @@ def _u8_to_f32(img_u8: np.ndarray) -> np.ndarray:
 class IlsvrcImages:
     """Background image source with the reference's interface (encoder_datasets.py:421-478)
     over a resident pool of uint8 images, or - like the reference - over a directory of JPEG files
-    (`root`, `subdir`), which are decoded on the device straight into the pool."""
+    (`root`, `subdir`), which are decoded on the device straight into the pool.  Files the
+    baseline decoder rejects (progressive, CMYK, ...) raise `MtgvError`, or are left out with a warning
+    when `skip_unsupported=True`."""
 
     _EXTS = (".jpeg", ".jpg")
 
     def __init__(self, images: Optional[list[np.ndarray]] = None, n: int = 64, *, root=None, subdir="val",
-                 files: Optional[list[bytes]] = None):
+                 files: Optional[list[bytes]] = None, skip_unsupported: bool = False):
         self._images = self.jpeg_files = None
         if root is not None or files is not None:
             if files is None:
@@ -72,6 +75,18 @@ class IlsvrcImages:
                 files = [open(p, "rb").read() for p in paths]
             else:
                 self._paths = [f"bg://{j:06d}" for j in range(len(files))]
+            if skip_unsupported:
+                # ILSVRC holds a few progressive / CMYK files; the device decoder is baseline-only and has no fallback:
+                # leave them out of the background pool (with a warning) instead of failing the whole ingest
+                keep = []
+                for j, f in enumerate(files):
+                    try:
+                        _StaticEngine.get().jpeg_info(f)
+                        keep.append(j)
+                    except abi.MtgvError as e:
+                        warnings.warn(f"background {self._paths[j]} skipped: {e}")
+                files = [files[j] for j in keep]
+                self._paths = [self._paths[j] for j in keep]
             assert len(files) > 0, "Dataset is empty."
             self.jpeg_files = list(files)
             return

@@ -89,3 +89,10 @@ def test_rejects_unsupported_and_mismatched():
     with pytest.raises(MtgvError, match="SOI"):
         ctx.jpeg_info(b"\x89PNG....")
     ctx.close()
+    # a file-backed background source can leave such files out instead of failing
+    from mtgvision_b200.encoder_datasets import IlsvrcImages
+
+    files = [jpeg_cases.encode(img), jpeg_cases.encode(img, progressive=1), jpeg_cases.encode(img, 80, "444")]
+    with pytest.warns(UserWarning, match="progressive"):
+        src = IlsvrcImages(files=files, skip_unsupported=True)
+    assert len(src) == 2 and np.array_equal(src.images_u8[1], _ref(files[2]))
