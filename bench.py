@@ -353,6 +353,40 @@ def run_cuda(args):
                       "upload + pool ingest of batch i+1 / kernels of batch i / download of batch i-1 overlap on four streams; "
                       "timed = max(CUDA events, host wall clock) over all steps including pipeline fill and drain)"}
 
+    # ---- the same end-to-end call with the inputs as the JPEG FILES the reference's loaders read ----
+    if e2e is not None and not args.no_e2e_jpeg:
+        import cv2
+
+        q = [cv2.IMWRITE_JPEG_QUALITY, 90]
+        card_files = [cv2.imencode(".jpg", cards.images[k % len(cards.images)][:, :, ::-1], q)[1].tobytes() for k in range(PAIRS)]
+        bg_files = [cv2.imencode(".jpg", bgs[j % len(bgs)][:, :, ::-1], q)[1].tobytes() for j in range(PAIRS)]
+        item = ds.prepare_jpeg_batch(card_files, bg_files)
+
+        def feed_jpeg(k):
+            for _ in range(k):
+                yield item
+
+        for _ in ds.host_tensor_batches(feed_jpeg(3)):
+            pass
+        barrier()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_w0 = time.perf_counter()
+        es.record()
+        for res in ds.host_tensor_batches(feed_jpeg(e2e_steps)):
+            checksum += float(res["x_labels"][0, 0])
+        ee.record()
+        torch.cuda.synchronize()
+        t_w1 = time.perf_counter()
+        j_ms = torch.tensor([max(es.elapsed_time(ee), 1e3 * (t_w1 - t_w0))], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(j_ms, op=dist.ReduceOp.MAX)
+        e2e["from_jpeg_files"] = {
+            "value": world * n_x * e2e_steps / (float(j_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(item["file_off"][-1]),
+            "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": float(j_ms.item()) / e2e_steps,
+            "api": "RanMtgEncDecDataset.host_tensor_batches fed with prepare_jpeg_batch items: the batch's 512 cards and 512 backgrounds as "
+                   "quality-90 JPEG files in pinned host memory (what the reference's loaders read from disk), decoded on the device "
+                   "(bit-exact with cv2.imread) into the pools; not the e2e number: the reference CPU arm is timed on decoded arrays"}
+
     # ---- context only: the training-loop call (pool resident, nothing uploaded), batch read back to pinned host ----
     if e2e is not None:
         it = iter(ds)
@@ -664,6 +698,7 @@ def main():
     ap.add_argument("--cpu-pairs-per-worker", type=int, default=384)
     ap.add_argument("--ref-pairs-per-worker", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-jpeg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload == "dewarp":

@@ -158,10 +158,27 @@ class RanMtgEncDecDataset(IterableDataset):
             torch.cuda.current_stream(ctx.device).synchronize()
         return out
 
+    def prepare_jpeg_batch(self, card_files: list[bytes], bg_files: list[bytes]) -> dict:
+        """One batch's inputs as JPEG files (n cards of the pool's card size, n backgrounds of one size) for
+        `host_tensor_batches`: parsed once, bytes concatenated in pinned memory."""
+        n = len(card_files)
+        assert len(bg_files) == n and n > 0
+        b = self.ctx.prepare_jpegs(list(card_files) + list(bg_files))
+        ch, cw = (int(v) for v in b["hw"][0])
+        bh, bw = (int(v) for v in b["hw"][n])
+        if not (b["hw"][:n] == (ch, cw)).all() or not (b["hw"][n:] == (bh, bw)).all() or (ch, cw) != tuple(self.ctx.card_hw):
+            raise ValueError("prepare_jpeg_batch: cards must have the pool's card size and backgrounds one common size")
+        b.update(n_pairs=n, card_shape=(n, ch, cw, 3), bg_shape=(n, bh, bw, 3))
+        return b
+
     def host_tensor_batches(self, source):
         """Streaming form of `host_tensor_batch`: `source` yields `(card_images, bg_images)` pairs of
         uint8 CPU tensors (pinned for full copy speed), one pair per batch, all of one batch size n;
         the generator yields one dict of pinned host tensors per pair, in order.
+
+        An item may also be a dict from `prepare_jpeg_batch(card_files, bg_files)`: the batch's inputs as the JPEG
+        FILES the reference's loaders read (`_load_card_image`, `IlsvrcImages._load_image` -> imread_float); only the
+        compressed bytes cross PCIe and the files are decoded on the device into the staging buffers.
 
         Four CUDA streams overlap the upload of batch i+1 (and its conversion into the pool
         layout), the kernels of batch i and the download of batch i-1 (what the reference's DataLoader workers do with processes,
@@ -181,17 +198,24 @@ class RanMtgEncDecDataset(IterableDataset):
             slots = getattr(self, "_pipe_slots", [])  # staging + pinned buffers persist across calls
             pending = []
             i = 0
-            for card_images, bg_images in source:
-                n = card_images.shape[0]
-                assert bg_images.shape[0] == n
-                if not slots or slots[0]["cards"].shape != card_images.shape or slots[0]["bgs"].shape != bg_images.shape:
+            for item in source:
+                if isinstance(item, dict):
+                    jpeg = item
+                    n, card_shape, bg_shape = item["n_pairs"], item["card_shape"], item["bg_shape"]
+                else:
+                    jpeg = None
+                    card_images, bg_images = item
+                    n, card_shape, bg_shape = card_images.shape[0], tuple(card_images.shape), tuple(bg_images.shape)
+                    assert bg_images.shape[0] == n
+                if not slots or tuple(slots[0]["cards"].shape) != card_shape or tuple(slots[0]["bgs"].shape) != bg_shape:
                     slots = self._pipe_slots = []
-                    if 2 * n > len(self.mtg.pool) or 2 * n > len(self.ilsvrc.images_u8):
+                    if 2 * n > len(self.mtg.pool) or 2 * n > len(self.ilsvrc):
                         raise ValueError("host_tensor_batches needs pools of at least 2 * batch entries")
+                    nc, nb = int(np.prod(card_shape)), int(np.prod(bg_shape))
                     for j in range(2):
+                        flat = torch.empty(nc + nb, dtype=torch.uint8, device=dev)  # cards then backgrounds: one decode target
                         slots.append({
-                            "cards": torch.empty(card_images.shape, dtype=torch.uint8, device=dev),
-                            "bgs": torch.empty(bg_images.shape, dtype=torch.uint8, device=dev),
+                            "flat": flat, "cards": flat[:nc].view(card_shape), "bgs": flat[nc:].view(bg_shape),
                             "idx": torch.arange(j * n, (j + 1) * n, dtype=torch.int32, device=dev),
                             "k_done": torch.cuda.Event(), "copy_done": torch.cuda.Event(), "in_done": torch.cuda.Event(),
                             "out_done": torch.cuda.Event(),
@@ -201,8 +225,11 @@ class RanMtgEncDecDataset(IterableDataset):
                 # upload + pool ingest of this batch may start once the kernels that last read these slots are done
                 s_in.wait_event(sl["k_done"])
                 with torch.cuda.stream(s_in):
-                    sl["cards"].copy_(card_images, non_blocking=True)
-                    sl["bgs"].copy_(bg_images, non_blocking=True)
+                    if jpeg is not None:
+                        ctx.decode_prepared(jpeg, sl["flat"])  # file bytes up, Huffman / IDCT / colour kernels on this stream
+                    else:
+                        sl["cards"].copy_(card_images, non_blocking=True)
+                        sl["bgs"].copy_(bg_images, non_blocking=True)
                     sl["copy_done"].record(s_in)
                 # the layout conversion into the pools runs on its own stream so the next upload starts right away
                 s_pl.wait_event(sl["copy_done"])

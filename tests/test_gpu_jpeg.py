@@ -77,6 +77,31 @@ def test_decoded_files_feed_the_background_pool():
     assert np.array_equal(IlsvrcImages(files=files)[2], _ref(files[2]).astype(np.float32) / 255.0)
 
 
+def test_host_pipeline_fed_with_jpeg_files_equals_decoded_arrays():
+    """host_tensor_batches with prepare_jpeg_batch items == the same call with the cv2-decoded images as tensors."""
+    from mtgvision_b200 import synth
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from mtgvision_b200.encoder_train import RanMtgEncDecDataset
+    from tests import parity_util as PU
+
+    pool, bgs = PU.small_pools(8, 8)
+    n = 4
+    card_files = [jpeg_cases.encode(pool.images[k], 90, "420") for k in range(n)]
+    bg_files = [jpeg_cases.encode(bgs[j], 90, "420") for j in range(n)]
+    hc = torch.from_numpy(np.stack([_ref(f) for f in card_files]))
+    hb = torch.from_numpy(np.stack([_ref(f) for f in bg_files]))
+    outs = []
+    for mode in ("arrays", "files"):
+        ds = RanMtgEncDecDataset(n, paired=True, targets=False, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=IlsvrcImages(images=bgs), seed=5)
+        item = (hc, hb) if mode == "arrays" else ds.prepare_jpeg_batch(card_files, bg_files)
+        got = [{k: v.clone() for k, v in res.items()} for res in ds.host_tensor_batches(item for _ in range(3))]
+        outs.append(got)
+        ds.ctx.close()
+    for a, b in zip(*outs):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+
+
 def test_rejects_unsupported_and_mismatched():
     from mtgvision_b200.abi import MtgvError
     from mtgvision_b200.context import Context
