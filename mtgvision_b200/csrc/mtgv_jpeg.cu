@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* 
 //             repeated until no thread starts over - then every checkpoint follows from the true start of the scan by
 //             induction, whatever the data (worst case: as many rounds as threads).  (Measured and dropped: queueing the
 //             runs that start over and decoding them one checkpoint per step with packed warps - 10 % slower, the extra
-//             barriers and window reloads cost more than the idle lanes);
+//             barriers and window reloads cost more than the idle lanes; 12-bit look-up tables built by the CTA
+//             - 6 % slower: long codes are not the problem, the 34 KB of tables cost occupancy);
 //   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
 // DC terms are stored as differences and integrated by k_jpeg_dc.
 constexpr int kSubBits = 512;  // measured: 128 -> 25 % slower (per-checkpoint overhead in the cold pass), 1024 -> later break-off in the rounds
