@@ -214,6 +214,10 @@ def run_cuda(args):
         import torch.distributed as dist
 
         torch.cuda.set_device(local_rank)
+        # rank 0's stdout must hold ONE JSON line: NCCL prints its version banner to stdout when the first communicator comes up
+        sys.stdout.flush()
+        _stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -429,6 +433,9 @@ def run_cuda(args):
                                              "failed_samples": int((status != 0).sum())}),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if dist is not None:
+            sys.stdout.flush()
+            os.dup2(_stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

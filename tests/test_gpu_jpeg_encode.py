@@ -75,3 +75,28 @@ def test_batched_dataset_writer_equals_cv2_imwrite(tmp_path):
         OD.save_sample(sample, k, one, one, ext="jpg")
         assert (one / f"image_{k:04d}.txt").read_text() == (tmp_path / f"image_{k:04d}.txt").read_text()
         assert (one / f"image_{k:04d}.jpg").read_bytes() == (tmp_path / f"image_{k:04d}.jpg").read_bytes()
+
+
+def test_create_yolo_obb_dataset_batched_layout(tmp_path):
+    """od_datasets.py:732-791 through the batched GPU path: same directory layout, yaml and file naming as the reference."""
+    import yaml
+
+    from mtgvision_b200 import od_datasets as OD
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from tests import parity_util as PU
+
+    pool, bgs = PU.small_pools(8, 8)
+    gen = OD.Gen(card_min_visible_ratio=0.5, card_min_visible_ratio_edges=0.0, card_jitter_ratio=0.7, ratio_bg=0.1, kind="seg",
+                 mtg_ds=SyntheticBgFgMtgImages(pool=pool), bg_ds=IlsvrcImages(images=bgs), seed=3)
+    out = tmp_path / "ds"
+    OD.create_yolo_obb_dataset(gen, output_dir=str(out), num_train=5, num_val_ratio=0.4, num_test_ratio=0.2, batch=4)
+    cfg = yaml.safe_load((out / "mtg_obb.yaml").read_text())
+    assert cfg["names"] == {0: "card", 1: "card_top", 2: "card_bottom"}
+    for name, num in (("train", 5), ("val", 2), ("test", 1)):
+        imgs = sorted(os.listdir(out / "images" / name))
+        assert imgs == [f"image_{i:04d}.jpg" for i in range(num)]
+        assert sorted(os.listdir(out / "labels" / name)) == [f"image_{i:04d}.txt" for i in range(num)]
+        im = cv2.imread(str(out / "images" / name / imgs[0]))
+        assert im is not None and im.shape == (640, 640, 3)
+    with pytest.raises(FileExistsError):
+        OD.create_yolo_obb_dataset(gen, output_dir=str(out), num_train=1)
