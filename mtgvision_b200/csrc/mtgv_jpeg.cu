@@ -268,7 +268,10 @@ __global__ void __launch_bounds__(32 * kEntWarps) k_jpeg_entropy(const uint8_t* 
 //   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
 // DC terms are stored as differences and integrated by k_jpeg_dc.
 constexpr int kSubBits = 512;  // measured: 128 -> 25 % slower (per-checkpoint overhead in the cold pass), 1024 -> later break-off in the rounds
-constexpr int kParThreads = 256;
+#ifndef MTGV_JPEG_PAR_THREADS
+#define MTGV_JPEG_PAR_THREADS 256
+#endif
+constexpr int kParThreads = MTGV_JPEG_PAR_THREADS;  // runs per file
 constexpr uint64_t kStateMask = (1ull << 48) - 1;
 
 struct ParSmem {
