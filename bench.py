@@ -157,6 +157,24 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        # NVML in-process (a sample every 5 ms) when the bindings load; else nvidia-smi's own 20 ms loop
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                import torch
+
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(self.gpu).uuid)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml, self.handle, self.stop_flag = pynvml, h, False
+            self.samples = []
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
@@ -165,11 +183,42 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), sm, mx, r))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def _stop_nvml(self, t0, t1):
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        sm, mx, reasons = [], [], set()
+        for t, c, m, r in self.samples:
+            if t < t0 or t > t1:
+                continue
+            sm.append(float(c))
+            mx.append(float(m))
+            reasons.update(k for k, b in bits.items() if r & b)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
+
     def stop(self, t0, t1):
+        if getattr(self, "nvml", None) is not None:
+            return self._stop_nvml(t0, t1)
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

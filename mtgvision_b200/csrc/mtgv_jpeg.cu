@@ -25,6 +25,7 @@ struct JpegState {
   uint8_t* planes = nullptr;  size_t planes_cap = 0;
   uint8_t* clean = nullptr;   size_t clean_cap = 0;   // byte-unstuffed scans of the single-interval files
   uint64_t* sync = nullptr;   size_t sync_cap = 0;    // subsequence checkpoints (bytes)
+  int32_t* endblk = nullptr;  size_t endblk_cap = 0;  // per file: first block the entropy decoder never reached
   uint8_t* desc = nullptr;    size_t desc_cap = 0;    // JpegImg[n] | JpegTables[n] | JpegSeg[nseg] | JpegWork[nwork] | int32 par_list[npar]
   uint8_t* desc_host = nullptr; size_t desc_host_cap = 0;  // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around the three kernels of the last batch
@@ -367,7 +368,7 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
 __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t* __restrict__ files, const JpegImg* __restrict__ imgs,
                                                                  const JpegTables* __restrict__ tbs, const int32_t* __restrict__ par_list,
                                                                  uint8_t* __restrict__ clean, uint64_t* __restrict__ sync,
-                                                                 int16_t* __restrict__ coef) {
+                                                                 int16_t* __restrict__ coef, int32_t* __restrict__ end_blk) {
   __shared__ ParSmem S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = par_list[blockIdx.x];
@@ -517,17 +518,32 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
   __syncthreads();
   int b = incl - mine;
   for (int w = 0; w < warp; w++) b += (int)S.wsum[w];
-  if (ncp > 0) {
-    ParState st = par_unpack(my_in);
-    par_decode<true>(S, G, cl, Lw, st, run1, coef, b);
+  ParState st = par_unpack(my_in);
+  if (ncp > 0) par_decode<true>(S, G, cl, Lw, st, run1, coef, b);
+  if (active && run1 == total_bits) {
+    // The run that reaches the end of the data.  A complete scan has decoded every block by now.  After a premature end
+    // (truncated file, stray marker) libjpeg finishes the MCU in which a request for bits ran past the data from zero bits
+    // and skips every later MCU, whose coefficients stay zero - grey (jdhuff.c decode_mcu, insufficient_data).
+    if (b < G.nblk_scan) {
+      if (st.p <= total_bits) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, b);  // the request that finds no data
+      while (!(st.k == 0 && st.j == 0) && b < G.nblk_scan) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, b);
+    }
+    end_blk[img] = b;  // first block that was never decoded
   }
 }
 
 // one warp per (file, component): DC differences -> DC terms, in scan order (a single restart interval)
-__global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs, const int32_t* __restrict__ par_list, int16_t* __restrict__ coef) {
+__global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs, const int32_t* __restrict__ par_list, int16_t* __restrict__ coef,
+                                                const int32_t* __restrict__ end_blk) {
   const JpegImg& im = imgs[par_list[blockIdx.x]];
   const int c = blockIdx.y, lane = threadIdx.x;
   if (c >= im.ncomp) return;
+  int nb_mcu = 0, joff = 0;  // blocks per MCU, first block of this component within the MCU
+  for (int k = 0; k < im.ncomp; k++) {
+    if (k < c) joff += im.ch[k] * im.cv[k];
+    nb_mcu += im.ch[k] * im.cv[k];
+  }
+  const int eb = end_blk[par_list[blockIdx.x]];  // blocks from here on were skipped (premature end of data): they stay zero
   const int ch = im.ch[c], cv = im.cv[c], bw = im.bw[c], nbc = ch * cv, mcux = im.mcux, total = im.mcux * im.mcuy * nbc;
   int16_t* base = coef + (im.coef_blk + im.blk0[c]) * 64;
   int carry = 0;
@@ -546,7 +562,7 @@ __global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs
       if (lane >= d) v += t;
     }
     v += carry;
-    if (ptr) *ptr = (int16_t)v;
+    if (ptr && (q / nbc) * nb_mcu + joff + (q % nbc) < eb) *ptr = (int16_t)v;
     carry = __shfl_sync(0xffffffffu, v, 31);
   }
 }
@@ -672,7 +688,7 @@ __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ 
 int jpeg_destroy(mtgv_ctx* ctx) {
   JpegState* st = (JpegState*)ctx->jpeg;
   if (!st) return MTGV_OK;
-  cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc); cudaFree(st->clean); cudaFree(st->sync);
+  cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc); cudaFree(st->clean); cudaFree(st->sync); cudaFree(st->endblk);
   if (st->desc_host) cudaFreeHost(st->desc_host);
   for (auto& e : st->ev) if (e) cudaEventDestroy(e);
   delete st;
@@ -795,6 +811,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   if ((rc = grow(ctx, (void**)&st->desc, &st->desc_cap, desc_bytes))) return rc;
   if ((rc = grow(ctx, (void**)&st->clean, &st->clean_cap, (size_t)clean_total + 16))) return rc;
   if ((rc = grow(ctx, (void**)&st->sync, &st->sync_cap, ((size_t)sync_total + 1) * sizeof(uint64_t)))) return rc;
+  if ((rc = grow(ctx, (void**)&st->endblk, &st->endblk_cap, (size_t)n * sizeof(int32_t)))) return rc;
   MTGV_CUDA_OK(ctx, cudaStreamSynchronize(stream));  // an earlier batch may still be reading the staging buffer
   if (desc_bytes > st->desc_host_cap) {
     if (st->desc_host) MTGV_CUDA_OK(ctx, cudaFreeHost(st->desc_host));
@@ -817,9 +834,9 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->coef, 0, (size_t)nblk_total * 64 * sizeof(int16_t), stream));
   const int32_t* d_pl = (const int32_t*)(st->desc + o_pl);
   if (npar) {
-    k_jpeg_entropy_par<<<(unsigned)npar, kParThreads, 0, stream>>>(st->files, d_img, d_tb, d_pl, st->clean, st->sync, st->coef);
+    k_jpeg_entropy_par<<<(unsigned)npar, kParThreads, 0, stream>>>(st->files, d_img, d_tb, d_pl, st->clean, st->sync, st->coef, st->endblk);
     MTGV_CUDA_OK(ctx, cudaGetLastError());
-    k_jpeg_dc<<<dim3((unsigned)npar, 3), 32, 0, stream>>>(d_img, d_pl, st->coef);
+    k_jpeg_dc<<<dim3((unsigned)npar, 3), 32, 0, stream>>>(d_img, d_pl, st->coef, st->endblk);
     MTGV_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 2;
   }

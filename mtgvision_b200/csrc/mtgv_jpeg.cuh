@@ -241,6 +241,7 @@ struct JpegBits {
   uint64_t buf;  // the low n bits are unread
   int n;
   int marker;    // a marker was reached: the rest of the segment reads as zero bits (jdhuff.c)
+  int fake;      // zero bits at the tail of buf that are not file data
 };
 
 MTGV_HD unsigned jpeg_ldb(const uint8_t* p) {
@@ -259,10 +260,12 @@ MTGV_HD void jpeg_fill(JpegBits& b) {
       if (c == 0xFF) {
         const unsigned nx = b.p + 1 < b.end ? jpeg_ldb(b.p + 1) : 0xD9u;
         if (nx == 0) b.p += 2;  // stuffed zero byte
-        else { b.marker = 1; c = 0; }
+        else { b.marker = 1; c = 0; b.fake += 8; }
       } else {
         b.p++;
       }
+    } else {
+      b.fake += 8;
     }
     b.buf = (b.buf << 8) | c;
     b.n += 8;
@@ -305,10 +308,13 @@ MTGV_HD void jpeg_decode_segment(const uint8_t* file, const JpegImg& im, const J
   JpegBits b;
   b.p = file + sg.byte_off;
   b.end = file + im.file_len;
-  b.buf = 0; b.n = 0; b.marker = 0;
+  b.buf = 0; b.n = 0; b.marker = 0; b.fake = 0;
   int pred[3] = {0, 0, 0};
   int my = sg.mcu0 / im.mcux, mx = sg.mcu0 - my * im.mcux;
   for (int m = 0; m < sg.nmcu; m++) {
+    // jdhuff.c decode_mcu: once a request for bits ran past the data (premature end of the file) the MCU in progress is
+    // finished from zero bits and the later MCUs of the interval are skipped: their coefficients stay zero (grey)
+    if (b.n < b.fake) break;
     for (int c = 0; c < im.ncomp; c++) {
       const int tdc = im.td[c], tac = 2 + im.ta[c];
       for (int by = 0; by < im.cv[c]; by++) {

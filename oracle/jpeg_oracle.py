@@ -128,11 +128,14 @@ class _Bits:
     def __init__(self, data: bytes, pos: int):
         self.d, self.p, self.buf, self.n = data, pos, 0, 0
         self.hit_marker = False
+        self.fake = 0  # zero bits at the tail of the buffer that are not file data (fed after a marker / the end of the file)
 
     def _fill(self):
         while self.n <= 24:
             b = 0
+            self.fake += 8
             if not self.hit_marker and self.p < len(self.d):
+                self.fake -= 8
                 b = self.d[self.p]
                 if b == 0xFF:
                     nx = self.d[self.p + 1] if self.p + 1 < len(self.d) else 0xD9
@@ -141,6 +144,7 @@ class _Bits:
                     else:
                         self.hit_marker = True  # jdhuff.c feeds zero bits once a marker is reached
                         b = 0
+                        self.fake += 8
                 else:
                     self.p += 1
             self.buf = ((self.buf << 8) | b) & 0xFFFFFFFFFFFF
@@ -155,7 +159,7 @@ class _Bits:
 
     def restart(self):
         """Discard the partial byte and step over the RSTn marker."""
-        self.buf = self.n = 0
+        self.buf = self.n = self.fake = 0
         self.hit_marker = False
         while self.p + 1 < len(self.d) and not (self.d[self.p] == 0xFF and 0xD0 <= self.d[self.p + 1] <= 0xD7):
             self.p += 1
@@ -213,6 +217,10 @@ def entropy_decode(data: bytes, info: dict):
                 bits.restart()
                 pred = [0] * len(comps)
             n += 1
+            # jdhuff.c decode_mcu: once a request for bits ran past the data (premature end of the file) the MCU in progress
+            # is finished from zero bits and every later MCU is skipped - its coefficients stay zero (grey) - until a restart
+            if bits.n < bits.fake:
+                continue
             for ci, c in enumerate(comps):
                 dc_lut, ac_lut = luts[(0, c["td"])], luts[(1, c["ta"])]
                 for by in range(c["v"]):

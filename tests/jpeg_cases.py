@@ -41,3 +41,28 @@ def small_suite(seed=0):
     for h, w in [(17, 23), (32, 32)]:
         out.append((f"{h}x{w}_gray", encode(image(rng, h, w, "mixed")[:, :, 0], 80)))
     return out
+
+
+def truncated_suite(seed=1):
+    """Files cut short inside the scan ("Premature end of JPEG file"): cv2.imread decodes what is there and leaves the rest
+    grey; cv2.imdecode refuses them, so the reference for these is `imread_ref`."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for (h, w), s, q in [((64, 80), "420", 90), ((48, 48), "444", 75), ((100, 37), "422", 95), ((33, 70), "440", 60), ((120, 160), "420", 85)]:
+        data = encode(image(rng, h, w, "mixed"), q, s)
+        scan = data.index(b"\xff\xda")
+        for frac in (0.05, 0.31, 0.5, 0.77, 0.98):
+            cut = scan + 14 + int((len(data) - scan - 16) * frac)
+            out.append((f"{h}x{w}_{s}_q{q}_cut{frac}", data[:cut]))
+        out.append((f"{h}x{w}_{s}_q{q}_noEOI", data[:-2]))
+    return out
+
+
+def imread_ref(data: bytes, tmpdir) -> np.ndarray:
+    """cv2.imread(path, IMREAD_COLOR_RGB) - the reference's own call (imread_float, util/image.py:107-114)."""
+    import os
+
+    p = os.path.join(str(tmpdir), "case.jpg")
+    with open(p, "wb") as f:
+        f.write(data)
+    return cv2.imread(p, cv2.IMREAD_COLOR_RGB)

@@ -77,6 +77,25 @@ def test_decoded_files_feed_the_background_pool():
     assert np.array_equal(IlsvrcImages(files=files)[2], _ref(files[2]).astype(np.float32) / 255.0)
 
 
+def test_truncated_files_decode_like_cv2_imread(tmp_path):
+    """Premature end of the data (ILSVRC has such files): finished MCU from zero bits, the rest grey - cv2.imread's result."""
+    from mtgvision_b200.context import Context
+
+    ctx = Context(0)
+    cases = jpeg_cases.truncated_suite()
+    rng = np.random.default_rng(8)
+    big = jpeg_cases.encode(jpeg_cases.image(rng, 375, 500, "mixed"), 90, "420")
+    cases += [(f"375x500_cut{c}", big[:c]) for c in (len(big) // 3, len(big) - 1000, 700)]
+    flat, off, hw = ctx.decode_jpegs([d for _, d in cases])
+    flat = flat.cpu().numpy()
+    for i, (name, data) in enumerate(cases):
+        ref = jpeg_cases.imread_ref(data, tmp_path)
+        h, w = hw[i]
+        got = flat[off[i]: off[i] + 3 * h * w].reshape(h, w, 3)
+        assert np.array_equal(got, ref), (name, int((got != ref).any(axis=2).sum()))
+    ctx.close()
+
+
 def test_host_pipeline_fed_with_jpeg_files_equals_decoded_arrays():
     """host_tensor_batches with prepare_jpeg_batch items == the same call with the cv2-decoded images as tensors."""
     from mtgvision_b200 import synth

@@ -58,3 +58,8 @@ def test_unsupported_files_are_rejected_with_a_message(hh):
     good = jpeg_cases.encode(img)
     with pytest.raises(ValueError, match="truncated"):
         host_decode(hh, good[:100])
+
+
+def test_truncated_files_decode_like_cv2_imread(hh, tmp_path):
+    for name, data in jpeg_cases.truncated_suite():
+        assert np.array_equal(host_decode(hh, data), jpeg_cases.imread_ref(data, tmp_path)), name

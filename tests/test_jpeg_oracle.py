@@ -30,3 +30,11 @@ def test_unsupported_files_are_rejected():
         jpeg_oracle.decode(jpeg_cases.encode(img, progressive=1))
     with pytest.raises(jpeg_oracle.JpegUnsupported):
         jpeg_oracle.decode(b"\x89PNG....")
+
+
+def test_truncated_files_decode_like_cv2_imread(tmp_path):
+    """A premature end of the data: the MCU in progress is finished from zero bits, later MCUs stay grey (jdhuff.c)."""
+    for name, data in jpeg_cases.truncated_suite():
+        ref = jpeg_cases.imread_ref(data, tmp_path)
+        assert ref is not None, name
+        assert np.array_equal(jpeg_oracle.decode(data), ref), name
