@@ -2,15 +2,17 @@
 // Replaces the cv2.imwrite behind save_sample / imwrite (mtgvision/od_datasets.py:794-832, util/image.py:95-104)
 // for uint8 images whose sides are multiples of 16; arithmetic in mtgv_jpegenc.cuh, FILE BYTES identical to cv2's
 // (libjpeg-turbo: quality-scaled Annex K tables, 4:2:0, ISLOW forward DCT, standard Huffman tables, JFIF header).
-// Two kernels per batch, every image of the batch in each launch:
+// Five kernels per batch, every image of the batch in each launch:
 //   k_jpegenc_dct   a CTA takes four MCUs: RGB -> YCbCr with the 2x2 chroma box filter (one pixel quad per thread),
 //                   then 8 threads per 8x8 block run the row and column passes of the forward DCT through shared
 //                   memory, quantise and store the block in zigzag order (coalesced 3 KiB per CTA).
-//   k_jpegenc_huff  one CTA per image.  Huffman coding is a serial bit stream, made parallel in four steps:
-//                   (A) every thread sizes one block's code (DC difference against its predecessor block, read
-//                   straight from the coefficient array), a CTA scan turns sizes into bit offsets; (B) every thread
-//                   writes its block's bits at its offset into a zeroed word buffer (atomicOr on the two words it
-//                   shares with its neighbours, plain stores between); (C) the last byte is padded with one bits;
+//   k_jpegenc_size / _scan / _emit / _stuff.  Huffman coding is a serial bit stream, made parallel in four steps:
+//                   (A) a warp per block sizes its code - lanes own two coefficients each, the zero run in front of a
+//                   nonzero coefficient comes from the block's nonzero mask (ballot), the DC difference from the
+//                   predecessor block in the coefficient array - and a CTA scan turns sizes into bit offsets; (B) the
+//                   warps assemble each block's bits in shared memory (a warp prefix sum places every lane's symbols)
+//                   and copy them to a zeroed word buffer (atomicOr on the two words shared with the neighbouring
+//                   blocks, plain stores between); (C) the last byte is padded with one bits;
 //                   (D) 0xFF bytes are counted per word, scanned, and the stream is copied behind the header with the
 //                   stuffed zero bytes inserted; EOI and the file length close the image.
 #include "mtgv_internal.cuh"
@@ -102,42 +104,81 @@ __global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__
   for (int i = tid; i < live; i += 256) dst[i] = ((const uint4*)outb)[i];
 }
 
-struct CountPut {
-  int n = 0;
-  __device__ __forceinline__ void operator()(unsigned, int size) { n += size; }
+// encode_one_block (jchuff.c) by one warp: lane l owns zigzag coefficients l and l + 32.  The run in front of a nonzero
+// coefficient is the distance to the previous set bit of the block's nonzero mask, so every lane knows its own symbols
+// (ZRLs, run/size code, value bits) and their length without walking the block; warp prefix sums give the bit positions.
+struct WarpBlock {
+  uint32_t zrl, code0, code1;   // ZRL code; this lane's run/size (or DC) codes, length << 16 | code; 0 = nothing to emit
+  int nz0, nz1;                 // ZRLs in front of the two symbols
+  uint32_t val0, val1;          // value bits
+  int nb0, nb1;                 // number of value bits
+  int len0, len1;               // bits this lane emits for coefficient l / l + 32
+  int eob;                      // lane 0: length << 16 | code of the EOB symbol, 0 if the block ends on coefficient 63
 };
 
-struct WordPut {  // writes bits at an arbitrary bit offset of a zeroed big-endian word stream
-  uint32_t* words;
-  uint32_t cap_words;
-  uint32_t w;       // next word to write
-  uint64_t acc = 0;
-  int n;            // pending bits in acc (the first n0 are the neighbour's: zeros here)
-  bool first = true;
-  __device__ __forceinline__ WordPut(uint32_t* base, uint32_t cap, uint32_t bit_off) : words(base), cap_words(cap), w(bit_off >> 5), n((int)(bit_off & 31u)) {}
-  __device__ __forceinline__ void emit(uint32_t v, bool shared_word) {
-    if (w < cap_words) {
-      const uint32_t be = __byte_perm(v, 0, 0x0123);  // stream order = byte order in memory
-      if (shared_word) atomicOr(words + w, be);
-      else words[w] = be;
+__device__ __forceinline__ WarpBlock warp_block(const int16_t* __restrict__ zz, int last_dc, const uint32_t* dc_tab, const uint32_t* ac_tab,
+                                                int lane) {
+  WarpBlock B;
+  int v0 = zz[lane], v1 = zz[lane + 32];
+  if (lane == 0) v0 -= last_dc;
+  // bit l of m_lo / m_hi: AC coefficient l / l + 32 (zigzag order) is nonzero
+  const unsigned m_lo = __ballot_sync(0xffffffffu, v0 != 0 && lane != 0), m_hi = __ballot_sync(0xffffffffu, v1 != 0);
+  B.zrl = ac_tab[0xF0];
+  const int zl = (int)(B.zrl >> 16);
+  const unsigned lt = (1u << lane) - 1u;
+  const int last_lo = m_lo ? 31 - __clz(m_lo) : 0;
+  auto one = [&](bool dc, int v, int prev, int k, uint32_t& code, int& nz, uint32_t& val, int& nb, int& len) {
+    code = 0; nz = 0; val = 0; nb = 0; len = 0;
+    if (dc) {  // DC difference
+      nb = 32 - __clz(v < 0 ? -v : v);
+      code = dc_tab[nb];
+    } else if (v != 0) {
+      const int run = k - prev - 1;  // prev: the previous nonzero coefficient (0 = the DC term)
+      nz = run >> 4;
+      nb = 32 - __clz(v < 0 ? -v : v);
+      code = ac_tab[((run & 15) << 4) + nb];
+    } else {
+      return;
     }
-    w++;
-  }
-  __device__ __forceinline__ void operator()(unsigned code, int size) {
-    acc = (acc << size) | code;
-    n += size;
-    if (n >= 32) {
-      emit((uint32_t)(acc >> (n - 32)), first);
-      first = false;
-      n -= 32;
-    }
-  }
-  __device__ __forceinline__ void flush() {
-    if (n > 0) emit((uint32_t)(acc << (32 - n)), true);
-  }
-};
+    val = (unsigned)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u);
+    len = nz * zl + (int)(code >> 16) + nb;
+  };
+  const unsigned b0 = m_lo & lt, b1 = m_hi & lt;
+  one(lane == 0, v0, b0 ? 31 - __clz(b0) : 0, lane, B.code0, B.nz0, B.val0, B.nb0, B.len0);
+  one(false, v1, b1 ? 63 - __clz(b1) : last_lo, lane + 32, B.code1, B.nz1, B.val1, B.nb1, B.len1);
+  const int last = m_hi ? 63 - __clz(m_hi) : last_lo;
+  B.eob = last < 63 ? (int)ac_tab[0] : 0;
+  return B;
+}
 
-__device__ __forceinline__ int block_scan_excl(int v, int* warp_sums, int* total) {  // 1024 threads
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+__device__ __forceinline__ int warp_excl(int v, int lane) {
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  return incl - v;
+}
+
+// ORs the low nbits (1..32) of val into an MSB-first bit stream held as 32-bit words (word 0 bit 31 = first bit)
+__device__ __forceinline__ void smem_put(uint32_t* buf, unsigned bitpos, uint32_t val, int nbits) {
+  const unsigned w = bitpos >> 5, sh = bitpos & 31u;
+  const uint64_t v64 = (uint64_t)val << (64 - nbits - (int)sh);
+  atomicOr(&buf[w], (uint32_t)(v64 >> 32));
+  if ((uint32_t)v64) atomicOr(&buf[w + 1], (uint32_t)v64);
+}
+
+constexpr int kHuffThreads = 512, kHuffWarps = kHuffThreads / 32;
+constexpr int kEncBufWords = 56;  // a block's code: at most 20 + 63 * 26 bits, plus the 31 bits in front of it in its first word
+
+__device__ __forceinline__ int block_scan_excl(int v, int* warp_sums, int* total) {  // kHuffThreads threads
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = v;
 #pragma unroll
@@ -150,7 +191,7 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_sums, int* total
   __syncthreads();
   int woff = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < 32; w++) {
+  for (int w = 0; w < kHuffWarps; w++) {
     const int s = warp_sums[w];
     if (w < warp) woff += s;
     tot += s;
@@ -159,61 +200,112 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_sums, int* total
   return woff + incl - v;
 }
 
-__global__ void __launch_bounds__(1024) k_jpegenc_huff(const int16_t* __restrict__ coef, int nmcu, const JpegEncTables* __restrict__ T,
-                                                       const uint8_t* __restrict__ header, int header_len, uint32_t* __restrict__ bits,
-                                                       uint32_t* __restrict__ boff, uint8_t* __restrict__ out, int64_t cap,
-                                                       int32_t* __restrict__ out_len) {
+// (A) code size of every block of every image: a warp per block
+__global__ void __launch_bounds__(256) k_jpegenc_size(const int16_t* __restrict__ coef, int nblk, const JpegEncTables* __restrict__ T,
+                                                      uint32_t* __restrict__ boff) {
   __shared__ uint32_t dc[2][16], ac[2][256];
-  __shared__ int warp_sums[32];
-  const int tid = threadIdx.x, img = blockIdx.x, nblk = nmcu * 6;
-  for (int i = tid; i < 32; i += 1024) ((uint32_t*)dc)[i] = ((const uint32_t*)T->dc)[i];
-  for (int i = tid; i < 512; i += 1024) ((uint32_t*)ac)[i] = ((const uint32_t*)T->ac)[i];
-  const int16_t* C = coef + (int64_t)img * nblk * 64;
-  uint32_t* W = bits + (int64_t)img * (cap >> 2);
-  uint32_t* O = boff + (int64_t)img * nblk;
-  uint8_t* dst = out + (int64_t)img * cap;
-  const uint32_t cap_words = (uint32_t)(cap >> 2);
+  for (int i = threadIdx.x; i < 32; i += 256) ((uint32_t*)dc)[i] = ((const uint32_t*)T->dc)[i];
+  for (int i = threadIdx.x; i < 512; i += 256) ((uint32_t*)ac)[i] = ((const uint32_t*)T->ac)[i];
   __syncthreads();
-  // (A) code size of every block -> bit offsets
+  const int lane = threadIdx.x & 31;
+  const int img = blockIdx.y;
+  const int16_t* C = coef + (int64_t)img * nblk * 64;
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < nblk; b += gridDim.x * 8) {
+    const int m = b / 6, j = b - m * 6, pb = jpegenc_pred_block(m, j), t = j < 4 ? 0 : 1;
+    const WarpBlock B = warp_block(C + (int64_t)b * 64, pb < 0 ? 0 : (int)C[(int64_t)pb * 64], dc[t], ac[t], lane);
+    const int len = warp_sum(B.len0 + B.len1) + (B.eob >> 16);
+    if (lane == 0) boff[(int64_t)img * nblk + b] = (unsigned)len;
+  }
+}
+
+// sizes -> bit offsets, one CTA per image; total_bits[img] = length of the image's code
+__global__ void __launch_bounds__(kHuffThreads) k_jpegenc_scan(int nblk, uint32_t* __restrict__ boff, uint32_t* __restrict__ total_bits) {
+  __shared__ int warp_sums[kHuffWarps];
+  uint32_t* O = boff + (int64_t)blockIdx.x * nblk;
   unsigned run = 0;
-  for (int base = 0; base < nblk; base += 1024) {
-    const int b = base + tid;
-    int len = 0;
-    if (b < nblk) {
-      const int m = b / 6, j = b - m * 6, pb = jpegenc_pred_block(m, j), t = j < 4 ? 0 : 1;
-      CountPut cp;
-      jpegenc_block(C + (int64_t)b * 64, pb < 0 ? 0 : (int)C[(int64_t)pb * 64], dc[t], ac[t], cp);
-      len = cp.n;
-    }
+  for (int base = 0; base < nblk; base += kHuffThreads) {
+    const int b = base + threadIdx.x;
+    const int len = b < nblk ? (int)O[b] : 0;
     int tot;
     const int ex = block_scan_excl(len, warp_sums, &tot);
     if (b < nblk) O[b] = run + (unsigned)ex;
     run += (unsigned)tot;
   }
-  const unsigned total_bits = run;
+  if (threadIdx.x == 0) total_bits[blockIdx.x] = run;
+}
+
+// (B) the bits: every lane ORs its symbols into the warp's shared-memory image of the block, which is then copied to the
+// image's zeroed word buffer (the first and last word are shared with the neighbouring blocks: atomicOr; stores between)
+__global__ void __launch_bounds__(256) k_jpegenc_emit(const int16_t* __restrict__ coef, int nblk,
+                                                      const JpegEncTables* __restrict__ T, const uint32_t* __restrict__ boff,
+                                                      const uint32_t* __restrict__ total_bits, uint32_t* __restrict__ bits, int64_t cap) {
+  __shared__ uint32_t dc[2][16], ac[2][256];
+  __shared__ uint32_t ebuf[8][kEncBufWords];
+  for (int i = threadIdx.x; i < 32; i += 256) ((uint32_t*)dc)[i] = ((const uint32_t*)T->dc)[i];
+  for (int i = threadIdx.x; i < 512; i += 256) ((uint32_t*)ac)[i] = ((const uint32_t*)T->ac)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  uint32_t* buf = ebuf[threadIdx.x >> 5];
+  const uint32_t cap_words = (uint32_t)(cap >> 2);
+  const int img = blockIdx.y;
+  if ((int64_t)((total_bits[img] + 7u) >> 3) + 4 > cap) return;  // the image does not fit: k_jpegenc_stuff reports it
+  const int16_t* C = coef + (int64_t)img * nblk * 64;
+  uint32_t* W = bits + (int64_t)img * (cap >> 2);
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < nblk; b += gridDim.x * 8) {
+    const int m = b / 6, j = b - m * 6, pb = jpegenc_pred_block(m, j), t = j < 4 ? 0 : 1;
+    const WarpBlock B = warp_block(C + (int64_t)b * 64, pb < 0 ? 0 : (int)C[(int64_t)pb * 64], dc[t], ac[t], lane);
+    const unsigned off = boff[(int64_t)img * nblk + b], s0 = off & 31u;
+    const int tot0 = warp_sum(B.len0);
+    const int len = tot0 + warp_sum(B.len1) + (B.eob >> 16);
+    buf[lane] = 0;
+    if (lane + 32 < kEncBufWords) buf[lane + 32] = 0;
+    __syncwarp();
+    unsigned p0 = s0 + (unsigned)warp_excl(B.len0, lane), p1 = s0 + (unsigned)tot0 + (unsigned)warp_excl(B.len1, lane);
+    if (B.len0) {
+      for (int z = 0; z < B.nz0; z++, p0 += B.zrl >> 16) smem_put(buf, p0, B.zrl & 0xffffu, (int)(B.zrl >> 16));
+      smem_put(buf, p0, B.code0 & 0xffffu, (int)(B.code0 >> 16));
+      if (B.nb0) smem_put(buf, p0 + (B.code0 >> 16), B.val0, B.nb0);
+    }
+    if (B.len1) {
+      for (int z = 0; z < B.nz1; z++, p1 += B.zrl >> 16) smem_put(buf, p1, B.zrl & 0xffffu, (int)(B.zrl >> 16));
+      smem_put(buf, p1, B.code1 & 0xffffu, (int)(B.code1 >> 16));
+      if (B.nb1) smem_put(buf, p1 + (B.code1 >> 16), B.val1, B.nb1);
+    }
+    if (lane == 0 && B.eob) smem_put(buf, s0 + (unsigned)len - ((unsigned)B.eob >> 16), (unsigned)B.eob & 0xffffu, B.eob >> 16);
+    __syncwarp();
+    const int nw = (int)((s0 + (unsigned)len + 31u) >> 5);
+    const uint32_t w0 = off >> 5;
+    for (int i = lane; i < nw; i += 32) {
+      if (w0 + i < cap_words) {
+        const uint32_t be = __byte_perm(buf[i], 0, 0x0123);  // stream order = byte order in memory
+        if (i == 0 || i == nw - 1) atomicOr(W + w0 + i, be);
+        else W[w0 + i] = be;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// (C) one bits up to the byte boundary, (D) byte stuffing behind the header, EOI, file length: one CTA per image
+__global__ void __launch_bounds__(kHuffThreads) k_jpegenc_stuff(const uint32_t* __restrict__ total_bits_all, const uint8_t* __restrict__ header,
+                                                                int header_len, uint32_t* __restrict__ bits, uint8_t* __restrict__ out, int64_t cap,
+                                                                int32_t* __restrict__ out_len) {
+  __shared__ int warp_sums[kHuffWarps];
+  const int tid = threadIdx.x, img = blockIdx.x;
+  uint32_t* W = bits + (int64_t)img * (cap >> 2);
+  uint8_t* dst = out + (int64_t)img * cap;
+  const unsigned total_bits = total_bits_all[img];
   const unsigned nbytes = (total_bits + 7u) >> 3;
   const bool fits = (int64_t)nbytes + 4 <= cap;  // the word buffer holds the whole stream
-  __syncthreads();
-  // (B) the bits
-  if (fits) {
-    for (int b = tid; b < nblk; b += 1024) {
-      const int m = b / 6, j = b - m * 6, pb = jpegenc_pred_block(m, j), t = j < 4 ? 0 : 1;
-      WordPut wp(W, cap_words, O[b]);
-      jpegenc_block(C + (int64_t)b * 64, pb < 0 ? 0 : (int)C[(int64_t)pb * 64], dc[t], ac[t], wp);
-      wp.flush();
-    }
-    // (C) one bits up to the byte boundary (jchuff.c flush_bits)
-    if (tid == 0 && (total_bits & 7u)) {
-      const unsigned pad = 8u - (total_bits & 7u), sh = 32u - (total_bits & 31u) - pad;
-      atomicOr(W + (total_bits >> 5), __byte_perm(((1u << pad) - 1u) << sh, 0, 0x0123));
-    }
+  if (fits && tid == 0 && (total_bits & 7u)) {  // jchuff.c flush_bits
+    const unsigned pad = 8u - (total_bits & 7u), sh = 32u - (total_bits & 31u) - pad;
+    W[total_bits >> 5] |= __byte_perm(((1u << pad) - 1u) << sh, 0, 0x0123);
   }
   __syncthreads();
-  // (D) byte stuffing behind the header
   unsigned pos = (unsigned)header_len;
   if (fits) {
     const unsigned nwords = (nbytes + 3u) >> 2;
-    for (unsigned base = 0; base < nwords; base += 1024) {
+    for (unsigned base = 0; base < nwords; base += kHuffThreads) {
       const unsigned wi = base + tid;
       uint32_t v = 0;
       int cnt = 0, nb = 0;
@@ -239,19 +331,19 @@ __global__ void __launch_bounds__(1024) k_jpegenc_huff(const int16_t* __restrict
   }
   const bool ok = fits && (int64_t)pos + 2 <= cap;
   if (ok) {
-    for (int i = tid; i < header_len; i += 1024) dst[i] = header[i];
+    for (int i = tid; i < header_len; i += kHuffThreads) dst[i] = header[i];
     if (tid == 0) { dst[pos] = 0xFF; dst[pos + 1] = 0xD9; }
   }
   if (tid == 0) out_len[img] = ok ? (int32_t)(pos + 2) : -1;
 }
 
 // file lengths -> byte offsets of the compact layout (one CTA; files that did not fit count as empty)
-__global__ void __launch_bounds__(1024) k_jpegenc_offsets(const int32_t* __restrict__ out_len, int n, int64_t* __restrict__ offsets) {
-  __shared__ int warp_sums[32];
+__global__ void __launch_bounds__(kHuffThreads) k_jpegenc_offsets(const int32_t* __restrict__ out_len, int n, int64_t* __restrict__ offsets) {
+  __shared__ int warp_sums[kHuffWarps];
   __shared__ long long carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
+  for (int base = 0; base < n; base += kHuffThreads) {
     const int i = base + threadIdx.x;
     const int v = i < n && out_len[i] > 0 ? out_len[i] : 0;
     int tot;
@@ -284,7 +376,7 @@ __global__ void __launch_bounds__(256) k_jpegenc_compact(const uint8_t* __restri
 
 int jpegenc_compact(mtgv_ctx* ctx, const uint8_t* slots, int64_t cap, const int32_t* out_len, int n, uint8_t* compact, int64_t* offsets,
                     cudaStream_t stream) {
-  k_jpegenc_offsets<<<1, 1024, 0, stream>>>(out_len, n, offsets);
+  k_jpegenc_offsets<<<1, kHuffThreads, 0, stream>>>(out_len, n, offsets);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   k_jpegenc_compact<<<dim3(32, n), 256, 0, stream>>>(slots, cap, out_len, offsets, compact);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
@@ -338,7 +430,7 @@ int jpegenc_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int
   int rc;
   if ((rc = enc_grow(ctx, (void**)&st->coef, &st->coef_cap, (size_t)n * nblk * 64 * sizeof(int16_t)))) return rc;
   if ((rc = enc_grow(ctx, (void**)&st->bits, &st->bits_cap, (size_t)n * (size_t)cap))) return rc;
-  if ((rc = enc_grow(ctx, (void**)&st->boff, &st->boff_cap, (size_t)n * nblk * sizeof(uint32_t)))) return rc;
+  if ((rc = enc_grow(ctx, (void**)&st->boff, &st->boff_cap, ((size_t)n * nblk + (size_t)n) * sizeof(uint32_t)))) return rc;
   ImgLayout L;
   if (layout == MTGV_LAYOUT_NCHW) { L.img_stride = (int64_t)3 * h * w; L.row_stride = w; L.px_stride = 1; L.ch_stride = h * w; }
   else { L.img_stride = (int64_t)3 * h * w; L.row_stride = 3 * w; L.px_stride = 3; L.ch_stride = 1; }
@@ -347,11 +439,25 @@ int jpegenc_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->bits, 0, (size_t)n * (size_t)cap, stream));
-  k_jpegenc_huff<<<n, 1024, 0, stream>>>(st->coef, nmcu, st->tables, st->header, st->header_len, st->bits, st->boff, out, cap, out_len);
-  MTGV_CUDA_OK(ctx, cudaGetLastError());
+  {
+    // per image as many 8-warp CTAs as its blocks need, capped so that the grid stays around 32 CTAs per SM
+    int gx = (nblk + 7) / 8;
+    const int cap_gx = (ctx->sm_count * 32 + n - 1) / n;
+    if (gx > cap_gx) gx = cap_gx < 1 ? 1 : cap_gx;
+    const dim3 grid((unsigned)gx, (unsigned)n);
+    uint32_t* tbits = st->boff + (size_t)n * nblk;  // [n] behind the block offsets
+    k_jpegenc_size<<<grid, 256, 0, stream>>>(st->coef, nblk, st->tables, st->boff);
+    MTGV_CUDA_OK(ctx, cudaGetLastError());
+    k_jpegenc_scan<<<n, kHuffThreads, 0, stream>>>(nblk, st->boff, tbits);
+    MTGV_CUDA_OK(ctx, cudaGetLastError());
+    k_jpegenc_emit<<<grid, 256, 0, stream>>>(st->coef, nblk, st->tables, st->boff, tbits, st->bits, cap);
+    MTGV_CUDA_OK(ctx, cudaGetLastError());
+    k_jpegenc_stuff<<<n, kHuffThreads, 0, stream>>>(tbits, st->header, st->header_len, st->bits, out, cap, out_len);
+    MTGV_CUDA_OK(ctx, cudaGetLastError());
+  }
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[2], stream));
   st->timed = true;
-  ctx->launches += 2;
+  ctx->launches += 5;
   return MTGV_OK;
 }
 
