@@ -633,14 +633,17 @@ __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ 
   const int pitchY = im.bw[0] * 8, pitchC = im.ncomp == 3 ? im.bw[1] * 8 : 0;
   for (int y = blockIdx.x * kColorRows; y < H; y += gridDim.x * kColorRows) {
     const int yend = y + kColorRows < H ? y + kColorRows : H;
-    for (int yy = y; yy < yend; yy++) {
-      uint8_t* drow = out + im.out_off + (int64_t)yy * W * 3;
-      const bool aligned = (((uintptr_t)drow) & 3) == 0;
-      // vertical neighbours of the chroma triangle filter (edge rows replicated)
-      const int inrow = yy >> 1, dh = im.dh[1];
-      const int other = (yy & 1) ? (inrow + 1 < dh ? inrow + 1 : dh - 1) : (inrow > 0 ? inrow - 1 : 0);
-      const int bias_e = 8, bias_o = 7;
-      for (int g = threadIdx.x; g < groups; g += 256) {
+    {
+      // the band's (row, 4-pixel group) pairs are dealt to the threads as one list: rows narrower than 1024 pixels
+      // would otherwise leave most of the CTA idle
+      for (int idx = threadIdx.x; idx < (yend - y) * groups; idx += 256) {
+        const int yy = y + idx / groups, g = idx - (yy - y) * groups;
+        uint8_t* drow = out + im.out_off + (int64_t)yy * W * 3;
+        const bool aligned = (((uintptr_t)drow) & 3) == 0;
+        // vertical neighbours of the chroma triangle filter (edge rows replicated)
+        const int inrow = yy >> 1, dh = im.dh[1];
+        const int other = (yy & 1) ? (inrow + 1 < dh ? inrow + 1 : dh - 1) : (inrow > 0 ? inrow - 1 : 0);
+        const int bias_e = 8, bias_o = 7;
         const int x0 = g * 4;
         uint8_t px[12];
         const int cnt = W - x0 < 4 ? W - x0 : 4;
