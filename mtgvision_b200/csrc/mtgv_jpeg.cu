@@ -25,6 +25,7 @@ struct JpegState {
   uint8_t* planes = nullptr;  size_t planes_cap = 0;
   uint8_t* clean = nullptr;   size_t clean_cap = 0;   // byte-unstuffed scans of the single-interval files
   uint64_t* sync = nullptr;   size_t sync_cap = 0;    // subsequence checkpoints (bytes)
+  int16_t* dcs = nullptr;     size_t dcs_cap = 0;     // DC term of every block of the single-interval files
   int32_t* endblk = nullptr;  size_t endblk_cap = 0;  // per file: first block the entropy decoder never reached
   uint8_t* desc = nullptr;    size_t desc_cap = 0;    // JpegImg[n] | JpegTables[n] | JpegSeg[nseg] | JpegWork[nwork] | int32 par_list[npar]
   uint8_t* desc_host = nullptr; size_t desc_host_cap = 0;  // pinned
@@ -314,7 +315,7 @@ __device__ __forceinline__ int16_t* par_blk(const ParSmem& S, int16_t* coef, int
 // the block st lies in; coefficients of blocks >= nblk_scan (garbage after the last MCU) are dropped.
 template <bool WRITE>
 __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, const uint32_t* __restrict__ cl, unsigned Lw, ParState& st,
-                                          unsigned boundary, int16_t* coef, int& b) {
+                                          unsigned boundary, int16_t* coef, int16_t* dcs, int& b) {
   unsigned p = st.p;
   int k = st.k, j = st.j, nb = 0;
   int16_t* blk = nullptr;
@@ -342,7 +343,11 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
     if (s) {
       if (WRITE) {
         const int pos = dc ? 0 : k + r;
-        if (pos < 64 && b < G.nblk_scan) blk[S.zz[pos]] = (int16_t)ent_extend(win, used, s);
+        if (pos < 64 && b < G.nblk_scan) {
+          const int16_t v = (int16_t)ent_extend(win, used, s);
+          if (dc) dcs[(blk - coef) >> 6] = v;  // DC differences go to the compact per-block array k_jpeg_dc integrates
+          else blk[S.zz[pos]] = v;
+        }
       }
       used += s;
     }
@@ -368,7 +373,7 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
 __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t* __restrict__ files, const JpegImg* __restrict__ imgs,
                                                                  const JpegTables* __restrict__ tbs, const int32_t* __restrict__ par_list,
                                                                  uint8_t* __restrict__ clean, uint64_t* __restrict__ sync,
-                                                                 int16_t* __restrict__ coef, int32_t* __restrict__ end_blk) {
+                                                                 int16_t* __restrict__ coef, int16_t* __restrict__ dcs, int32_t* __restrict__ end_blk) {
   __shared__ ParSmem S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = par_list[blockIdx.x];
@@ -477,7 +482,7 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
     ParState st = cold;
     for (int c = 0; c < ncp; c++) {
       const unsigned bnd = run0 + (unsigned)(c + 1) * kSubBits;
-      const int nb = par_decode<false>(S, G, cl, Lw, st, bnd < run1 ? bnd : run1, nullptr, dummy_b);
+      const int nb = par_decode<false>(S, G, cl, Lw, st, bnd < run1 ? bnd : run1, nullptr, nullptr, dummy_b);
       out[c] = par_pack(st, nb);
     }
   }
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
       ParState st = par_unpack(in);
       for (int c = 0; c < ncp; c++) {
         const unsigned bnd = run0 + (unsigned)(c + 1) * kSubBits;
-        const int nb = par_decode<false>(S, G, cl, Lw, st, bnd < run1 ? bnd : run1, nullptr, dummy_b);
+        const int nb = par_decode<false>(S, G, cl, Lw, st, bnd < run1 ? bnd : run1, nullptr, nullptr, dummy_b);
         const uint64_t nw = par_pack(st, nb), old = out[c];
         out[c] = nw;
         if (((nw ^ old) & kStateMask) == 0) break;
@@ -519,21 +524,21 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
   int b = incl - mine;
   for (int w = 0; w < warp; w++) b += (int)S.wsum[w];
   ParState st = par_unpack(my_in);
-  if (ncp > 0) par_decode<true>(S, G, cl, Lw, st, run1, coef, b);
+  if (ncp > 0) par_decode<true>(S, G, cl, Lw, st, run1, coef, dcs, b);
   if (active && run1 == total_bits) {
     // The run that reaches the end of the data.  A complete scan has decoded every block by now.  After a premature end
     // (truncated file, stray marker) libjpeg finishes the MCU in which a request for bits ran past the data from zero bits
     // and skips every later MCU, whose coefficients stay zero - grey (jdhuff.c decode_mcu, insufficient_data).
     if (b < G.nblk_scan) {
-      if (st.p <= total_bits) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, b);  // the request that finds no data
-      while (!(st.k == 0 && st.j == 0) && b < G.nblk_scan) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, b);
+      if (st.p <= total_bits) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, dcs, b);  // the request that finds no data
+      while (!(st.k == 0 && st.j == 0) && b < G.nblk_scan) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, dcs, b);
     }
     end_blk[img] = b;  // first block that was never decoded
   }
 }
 
 // one warp per (file, component): DC differences -> DC terms, in scan order (a single restart interval)
-__global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs, const int32_t* __restrict__ par_list, int16_t* __restrict__ coef,
+__global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs, const int32_t* __restrict__ par_list, int16_t* __restrict__ dcs,
                                                 const int32_t* __restrict__ end_blk) {
   const JpegImg& im = imgs[par_list[blockIdx.x]];
   const int c = blockIdx.y, lane = threadIdx.x;
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs
   }
   const int eb = end_blk[par_list[blockIdx.x]];  // blocks from here on were skipped (premature end of data): they stay zero
   const int ch = im.ch[c], cv = im.cv[c], bw = im.bw[c], nbc = ch * cv, mcux = im.mcux, total = im.mcux * im.mcuy * nbc;
-  int16_t* base = coef + (im.coef_blk + im.blk0[c]) * 64;
+  int16_t* base = dcs + (im.coef_blk + im.blk0[c]);  // one entry per block, same block order as the coefficient array
   int carry = 0;
   for (int q0 = 0; q0 < total; q0 += 32) {
     const int q = q0 + lane;
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs
     int v = 0;
     if (q < total) {
       const int m = q / nbc, wi = q - m * nbc, by = wi / ch, bx = wi - by * ch, my = m / mcux, mx = m - my * mcux;
-      ptr = base + ((int64_t)(my * cv + by) * bw + mx * ch + bx) * 64;
+      ptr = base + ((int64_t)(my * cv + by) * bw + mx * ch + bx);
       v = *ptr;
     }
 #pragma unroll
@@ -569,7 +574,8 @@ __global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs
 
 // grid (ceil(max blocks / 32), n images), 256 threads = 32 blocks of 8 threads
 __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ imgs, const JpegTables* __restrict__ tbs,
-                                                   const int16_t* __restrict__ coef, uint8_t* __restrict__ planes) {
+                                                   const int16_t* __restrict__ coef, const int16_t* __restrict__ dcs,
+                                                   uint8_t* __restrict__ planes) {
   __shared__ int ws[32][8][9];
   const JpegImg& im = imgs[blockIdx.y];
   const int g = threadIdx.x >> 3, t = threadIdx.x & 7;
@@ -583,6 +589,7 @@ __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ i
     int x[8], o[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) x[r] = (int)blk[r * 8 + t] * (int)q[r * 8 + t];
+    if (im.par && t == 0) x[0] = (int)dcs[im.coef_blk + b] * (int)q[0];  // DC term from the integrated per-block array
     jpeg_idct8(x, o, kJpegPass1Shift);  // column t
 #pragma unroll
     for (int r = 0; r < 8; r++) ws[g][r][t] = o[r];
@@ -691,7 +698,7 @@ __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ 
 int jpeg_destroy(mtgv_ctx* ctx) {
   JpegState* st = (JpegState*)ctx->jpeg;
   if (!st) return MTGV_OK;
-  cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc); cudaFree(st->clean); cudaFree(st->sync); cudaFree(st->endblk);
+  cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc); cudaFree(st->clean); cudaFree(st->sync); cudaFree(st->endblk); cudaFree(st->dcs);
   if (st->desc_host) cudaFreeHost(st->desc_host);
   for (auto& e : st->ev) if (e) cudaEventDestroy(e);
   delete st;
@@ -815,6 +822,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   if ((rc = grow(ctx, (void**)&st->clean, &st->clean_cap, (size_t)clean_total + 16))) return rc;
   if ((rc = grow(ctx, (void**)&st->sync, &st->sync_cap, ((size_t)sync_total + 1) * sizeof(uint64_t)))) return rc;
   if ((rc = grow(ctx, (void**)&st->endblk, &st->endblk_cap, (size_t)n * sizeof(int32_t)))) return rc;
+  if ((rc = grow(ctx, (void**)&st->dcs, &st->dcs_cap, ((size_t)nblk_total + 1) * sizeof(int16_t)))) return rc;
   MTGV_CUDA_OK(ctx, cudaStreamSynchronize(stream));  // an earlier batch may still be reading the staging buffer
   if (desc_bytes > st->desc_host_cap) {
     if (st->desc_host) MTGV_CUDA_OK(ctx, cudaFreeHost(st->desc_host));
@@ -835,11 +843,12 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   const JpegWork* d_wk = (const JpegWork*)(st->desc + o_wk);
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[0], stream));
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->coef, 0, (size_t)nblk_total * 64 * sizeof(int16_t), stream));
+  MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->dcs, 0, (size_t)nblk_total * sizeof(int16_t), stream));
   const int32_t* d_pl = (const int32_t*)(st->desc + o_pl);
   if (npar) {
-    k_jpeg_entropy_par<<<(unsigned)npar, kParThreads, 0, stream>>>(st->files, d_img, d_tb, d_pl, st->clean, st->sync, st->coef, st->endblk);
+    k_jpeg_entropy_par<<<(unsigned)npar, kParThreads, 0, stream>>>(st->files, d_img, d_tb, d_pl, st->clean, st->sync, st->coef, st->dcs, st->endblk);
     MTGV_CUDA_OK(ctx, cudaGetLastError());
-    k_jpeg_dc<<<dim3((unsigned)npar, 3), 32, 0, stream>>>(d_img, d_pl, st->coef, st->endblk);
+    k_jpeg_dc<<<dim3((unsigned)npar, 3), 32, 0, stream>>>(d_img, d_pl, st->dcs, st->endblk);
     MTGV_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 2;
   }
@@ -850,7 +859,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
     ctx->launches += 1;
   }
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));
-  k_jpeg_idct<<<dim3((max_blk + 31) / 32, n), 256, 0, stream>>>(d_img, d_tb, st->coef, st->planes);
+  k_jpeg_idct<<<dim3((max_blk + 31) / 32, n), 256, 0, stream>>>(d_img, d_tb, st->coef, st->dcs, st->planes);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[2], stream));
   const int gx = (max_h + kColorRows - 1) / kColorRows;
