@@ -81,11 +81,15 @@ class Gen:
         self._counter = 0
         # both background datasets share one resident pool (the reference draws the dataset with
         # ilsvrc_vs_coco_sample_weights and then an image uniformly, od_datasets.py:662-672)
-        bgs = list(self.bg_ds.images_u8) + (list(self.bg2_ds.images_u8) if self.bg2_ds is not None else [])
+        sources = [self.bg_ds] + ([self.bg2_ds] if self.bg2_ds is not None else [])
         self.ctx = Context(device)
         pool = self.mtg_ds.pool
         self.ctx.set_card_pool(pool.images, pool.labels3, pool.grp_off, pool.grp_mem)
-        self.ctx.set_bg_pool(bgs)
+        if all(getattr(d, "jpeg_files", None) is not None for d in sources):
+            # file-backed sources (IlsvrcImages(root=...)): decoded on the device straight into the pool
+            self.ctx.set_bg_pool_from_jpegs([f for d in sources for f in d.jpeg_files])
+        else:
+            self.ctx.set_bg_pool([im for d in sources for im in d.images_u8])
         # raises like the reference's random.randint when the card diagonal does not fit (od_datasets.py:322)
         try:
             self.ctx.set_det_config(bg_size_hw=bg_size_hw, num_cards_min=num_cards_min, num_cards_max=num_cards_max,
