@@ -421,7 +421,8 @@ int mtgv_jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms3);
 /* save_sample's imwrite (od_datasets.py:829-831; util/image.py:95-104: cv2.imwrite of the uint8 RGB image) for n
  * images at once, on the device: baseline JPEG, 4:2:0, standard Huffman tables, JFIF header - the FILE BYTES of
  * cv2.imencode(".jpg", bgr, [IMWRITE_JPEG_QUALITY, quality]) (cv2.imwrite's default quality is 95).
- * images: device uint8 RGB in `layout`; h and w multiples of 16 (save_sample asserts 640x640), else MTGV_ERR_LIMIT.
+ * images: device uint8 RGB in `layout`, any size up to 16384 per side (sizes that are not whole 16x16 MCUs follow libjpeg's
+ * edge-replication and dummy-block rules; save_sample itself asserts 640x640).
  * out: device, image i's file at out + i*cap (cap: bytes per image, multiple of 4); out_len: device int32 [n], the
  * file length, or -1 when the file does not fit in cap (nothing usable is written for that image). */
 int mtgv_encode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int layout, int quality, uint8_t* out,

@@ -294,7 +294,7 @@ class Context:
     # ------------------------------------------------------------------ image encode for the dataset writer
     def encode_jpegs(self, images: torch.Tensor, quality: int = 95, layout: str | None = None, cap: int | None = None) -> list[bytes]:
         """cv2.imwrite's JPEG bytes (save_sample -> imwrite, od_datasets.py:829-831) for a batch of uint8 RGB images on the
-        device: (n,3,H,W) or (n,H,W,3), H and W multiples of 16.  Returns one `bytes` per image."""
+        device: (n,3,H,W) or (n,H,W,3), any size.  Returns one `bytes` per image."""
         return [v.tobytes() for v in self.encode_jpegs_host(images, quality, layout, cap)]
 
     def encode_jpegs_host(self, images: torch.Tensor, quality: int = 95, layout: str | None = None, cap: int | None = None) -> list[np.ndarray]:
@@ -327,7 +327,7 @@ class Context:
             layout = "nchw" if images.shape[1] == 3 and images.shape[3] != 3 else "nhwc"
         n = images.shape[0]
         h, w = (images.shape[2], images.shape[3]) if layout == "nchw" else (images.shape[1], images.shape[2])
-        cap = int(cap) if cap is not None else (h * w * 3 // 2 + 4096) // 4 * 4
+        cap = int(cap) if cap is not None else (((h + 15) // 16) * ((w + 15) // 16) * 384 + 4096) // 4 * 4
         out = torch.empty((n, cap), dtype=torch.uint8, device=self.device)
         lens = torch.empty(n, dtype=torch.int32, device=self.device)
         rc = self.lib.mtgv_encode_jpeg_batch(self._h, _ptr(images), n, h, w, abi.LAYOUT_NCHW if layout == "nchw" else abi.LAYOUT_NHWC,

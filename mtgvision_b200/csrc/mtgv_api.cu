@@ -300,11 +300,10 @@ int mtgv_encode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, i
                            int64_t cap, int32_t* out_len, void* stream) {
   if (!ctx) return MTGV_ERR_INVALID;
   if (n == 0) return MTGV_OK;
-  if (!images || !out || !out_len || n < 0 || h < 16 || w < 16 || (layout != MTGV_LAYOUT_NHWC && layout != MTGV_LAYOUT_NCHW) ||
+  if (!images || !out || !out_len || n < 0 || h < 1 || w < 1 || (layout != MTGV_LAYOUT_NHWC && layout != MTGV_LAYOUT_NCHW) ||
       quality < 1 || quality > 100 || cap < 1024 || (cap & 3))
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_encode_jpeg_batch: bad arguments");
-  if ((h & 15) || (w & 15) || h > 65520 || w > 65520)
-    return fail(ctx, MTGV_ERR_LIMIT, "mtgv_encode_jpeg_batch: image sides must be multiples of 16 (whole 4:2:0 MCUs)");
+  if (h > 16384 || w > 16384) return fail(ctx, MTGV_ERR_LIMIT, "mtgv_encode_jpeg_batch: image larger than 16384 pixels per side");
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   return jpegenc_batch(ctx, images, n, h, w, layout, quality, out, cap, out_len, (cudaStream_t)stream);
 }

@@ -1,6 +1,6 @@
 // mtgv_jpegenc.cu - batched baseline JPEG encode of generated scenes.
 // Replaces the cv2.imwrite behind save_sample / imwrite (mtgvision/od_datasets.py:794-832, util/image.py:95-104)
-// for uint8 images whose sides are multiples of 16; arithmetic in mtgv_jpegenc.cuh, FILE BYTES identical to cv2's
+// for uint8 RGB images of any size; arithmetic in mtgv_jpegenc.cuh, FILE BYTES identical to cv2's
 // (libjpeg-turbo: quality-scaled Annex K tables, 4:2:0, ISLOW forward DCT, standard Huffman tables, JFIF header).
 // Five kernels per batch, every image of the batch in each launch:
 //   k_jpegenc_dct   a CTA takes four MCUs: RGB -> YCbCr with the 2x2 chroma box filter (one pixel quad per thread),
@@ -47,7 +47,7 @@ struct ImgLayout {
   int row_stride, px_stride, ch_stride;
 };
 
-__global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__ images, ImgLayout L, int mcux, int nmcu,
+__global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__ images, ImgLayout L, int H, int W, int mcux, int nmcu,
                                                      const JpegEncTables* __restrict__ T, int16_t* __restrict__ coef) {
   __shared__ int16_t samp[24][64];   // level-shifted samples, natural order; blocks = 4 MCUs x (Y00 Y01 Y10 Y11 Cb Cr)
   __shared__ int ws[24][8][9];
@@ -60,15 +60,23 @@ __global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__
     if (m < nmcu) {
       const int my = m / mcux, mx = m - my * mcux;
       const uint8_t* base = images + (int64_t)img * L.img_stride;
+      const bool edge = (my + 1) * 16 > H || (mx + 1) * 16 > W;  // an MCU that sticks out of the image
       int sb = 0, sr = 0;
 #pragma unroll
       for (int dy = 0; dy < 2; dy++)
 #pragma unroll
         for (int dx = 0; dx < 2; dx++) {
-          const int y = my * 16 + 2 * qy + dy, x = mx * 16 + 2 * qx + dx;
-          const uint8_t* p = base + (int64_t)y * L.row_stride + (int64_t)x * L.px_stride;
+          // edge rules (mtgv_jpegenc.cuh): inside the image both rows are the pixel's own
+          int y = my * 16 + 2 * qy + dy, x = mx * 16 + 2 * qx + dx, yl = y, yc = y;
+          if (edge) { x = jpegenc_col(x, W); yl = jpegenc_luma_row(y, H); yc = jpegenc_chroma_row(y, H); }
+          const uint8_t* p = base + (int64_t)yl * L.row_stride + (int64_t)x * L.px_stride;
           int Y, cb, cr;
           jpegenc_ycc(__ldg(p), __ldg(p + L.ch_stride), __ldg(p + 2 * (int64_t)L.ch_stride), &Y, &cb, &cr);
+          if (yc != yl) {
+            const uint8_t* pc = base + (int64_t)yc * L.row_stride + (int64_t)x * L.px_stride;
+            int Yc;
+            jpegenc_ycc(__ldg(pc), __ldg(pc + L.ch_stride), __ldg(pc + 2 * (int64_t)L.ch_stride), &Yc, &cb, &cr);
+          }
           const int yy = 2 * qy + dy, xx = 2 * qx + dx;
           samp[lm * 6 + (yy >> 3) * 2 + (xx >> 3)][(yy & 7) * 8 + (xx & 7)] = (int16_t)(Y - 128);
           sb += cb; sr += cr;
@@ -99,6 +107,13 @@ __global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__
     for (int k = 0; k < 8; k++) outb[b][c_zz_of_natural[k * 8 + t]] = (int16_t)jpegenc_quant(o[k], q[k * 8 + t]);
   }
   __syncthreads();
+  if ((((W + 7) >> 3) | ((H + 7) >> 3)) & 1) {  // an odd number of luma block columns / rows: the last MCUs hold dummy blocks
+    if (tid < 4 && m0 + tid < nmcu) {  // luma blocks wholly outside the image: zero AC, DC of the block before (jccoefct.c)
+      const int m = m0 + tid, my = m / mcux, mx = m - my * mcux;
+      jpegenc_dummy_blocks(&outb[tid * 6][0], mx == mcux - 1 && (((W + 7) >> 3) & 1), my == nmcu / mcux - 1 && (((H + 7) >> 3) & 1));
+    }
+    __syncthreads();
+  }
   const int live = (nmcu - m0 < 4 ? nmcu - m0 : 4) * 6 * 64 / 8;  // uint4 words of the live MCUs
   uint4* dst = (uint4*)(coef + ((int64_t)img * nmcu + m0) * 6 * 64);
   for (int i = tid; i < live; i += 256) dst[i] = ((const uint4*)outb)[i];
@@ -426,7 +441,7 @@ int jpegenc_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int
     st->header_len = (int)hdr.size();
     st->quality = quality; st->h = h; st->w = w;
   }
-  const int mcux = w / 16, nmcu = mcux * (h / 16), nblk = nmcu * 6;
+  const int mcux = (w + 15) / 16, nmcu = mcux * ((h + 15) / 16), nblk = nmcu * 6;
   int rc;
   if ((rc = enc_grow(ctx, (void**)&st->coef, &st->coef_cap, (size_t)n * nblk * 64 * sizeof(int16_t)))) return rc;
   if ((rc = enc_grow(ctx, (void**)&st->bits, &st->bits_cap, (size_t)n * (size_t)cap))) return rc;
@@ -435,7 +450,7 @@ int jpegenc_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int
   if (layout == MTGV_LAYOUT_NCHW) { L.img_stride = (int64_t)3 * h * w; L.row_stride = w; L.px_stride = 1; L.ch_stride = h * w; }
   else { L.img_stride = (int64_t)3 * h * w; L.row_stride = 3 * w; L.px_stride = 3; L.ch_stride = 1; }
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[0], stream));
-  k_jpegenc_dct<<<dim3((nmcu + 3) / 4, n), 256, 0, stream>>>(images, L, mcux, nmcu, st->tables, st->coef);
+  k_jpegenc_dct<<<dim3((nmcu + 3) / 4, n), 256, 0, stream>>>(images, L, h, w, mcux, nmcu, st->tables, st->coef);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->bits, 0, (size_t)n * (size_t)cap, stream));

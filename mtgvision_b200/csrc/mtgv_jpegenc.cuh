@@ -9,8 +9,8 @@
 //   quantisation     jcdctmgr.c  (round half away from zero by 8*Q; tables: jcparam.c jpeg_quality_scaling)
 //   entropy coding   jchuff.c    (encode_one_block with the tables of jstdhuff.c)
 //   markers          jcmarker.c  (SOI APP0 DQT DQT SOF0 DHT*4 SOS ... EOI)
-// Image sizes are multiples of 16 (whole 4:2:0 MCUs; save_sample asserts 640x640): edge replication and dummy blocks
-// are not needed and not restated.
+// Sizes that are not whole 16x16 MCUs (save_sample itself asserts 640x640) follow libjpeg's edge replication and
+// dummy-block rules (jcsample.c, jcprepct.c, jccoefct.c): jpegenc_col / _luma_row / _chroma_row / _dummy_blocks.
 #pragma once
 
 #include <stdint.h>
@@ -193,6 +193,35 @@ MTGV_HD void jpegenc_block(const int16_t* zz, int last_dc, const uint32_t* dc_ta
     r = 0;
   }
   if (r > 0) { e = ac_tab[0]; put(e & 0xffffu, (int)(e >> 16)); }
+}
+
+// Edge rules for sizes that are not whole MCUs.  Columns are replicated at full resolution before the chroma box filter
+// (jcsample.c expand_right_edge); luma rows are replicated; for chroma the rows are replicated to an even count, filtered,
+// and the DOWNSAMPLED rows replicated below that (jcprepct.c) - so a tap of a chroma row past the last one reads the rows
+// of the last one.
+MTGV_HD int jpegenc_col(int x, int W) { return x < W ? x : W - 1; }
+MTGV_HD int jpegenc_luma_row(int y, int H) { return y < H ? y : H - 1; }
+MTGV_HD int jpegenc_chroma_row(int y, int H) {
+  const int ch = (H + 1) >> 1;
+  int cr = y >> 1;
+  if (cr >= ch) cr = ch - 1;
+  const int r = 2 * cr + (y & 1);
+  return r < H ? r : H - 1;
+}
+
+// Luma blocks of an MCU that lie wholly outside the image are "dummy" blocks: zero AC terms, DC term of the block before
+// them in the MCU (jccoefct.c compress_data).  blk: the MCU's four luma blocks (scan order, 64 coefficients each, DC
+// first); right / bottom: the MCU's second block column / row is outside the image.
+MTGV_HD void jpegenc_dummy_blocks(int16_t* blk, bool right, bool bottom) {
+  if (!right && !bottom) return;
+  for (int j = 1; j < 4; j++) {
+    const bool dummy = (j >= 2 && bottom) || ((j & 1) && right);
+    if (!dummy) continue;
+    const int src = (j >= 2 && bottom) ? 1 : j - 1;  // a dummy row copies the last block of the row above
+    const int16_t dcv = blk[src * 64];
+    for (int k = 0; k < 64; k++) blk[j * 64 + k] = 0;
+    blk[j * 64] = dcv;
+  }
 }
 
 // index (within the 6 blocks of an MCU, scan order Y00 Y01 Y10 Y11 Cb Cr) of the block whose DC predicts block j of

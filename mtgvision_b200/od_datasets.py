@@ -193,9 +193,8 @@ def save_batch(generator: Gen, batch: dict, first_i: int, label_dir, img_dir, qu
 
 def create_yolo_obb_dataset(generator: Gen, *, output_dir: str, num_train: int = 20000, num_val_ratio: float = 0.1,
                             num_test_ratio: float = 0.1, ext: Literal["png", "jpg"] = "jpg", batch: int = 256):
-    """od_datasets.py:732-791.  ext="jpg" with scene sides that are multiples of 16 (the reference asserts 640x640) takes
-    the batched path: scenes are generated AND JPEG-encoded on the GPU, `batch` at a time; otherwise one `save_sample`
-    per scene like the reference."""
+    """od_datasets.py:732-791.  ext="jpg" takes the batched path: scenes are generated AND JPEG-encoded on the GPU,
+    `batch` at a time; ext="png" writes one `save_sample` per scene like the reference."""
     import yaml
 
     output_dir = Path(output_dir)
@@ -207,8 +206,7 @@ def create_yolo_obb_dataset(generator: Gen, *, output_dir: str, num_train: int =
     with open(output_dir / "mtg_obb.yaml", "w") as fp:
         yaml.safe_dump({"path": ".", "train": str(img_dir / "train"), "val": str(img_dir / "val"),
                         "test": str(img_dir / "test"), "names": {0: "card", 1: "card_top", 2: "card_bottom"}}, fp)
-    S = generator.bg_size_hw if isinstance(generator.bg_size_hw, (tuple, list)) else (generator.bg_size_hw, generator.bg_size_hw)
-    batched = ext == "jpg" and batch > 1 and S[0] % 16 == 0 and S[1] % 16 == 0
+    batched = ext == "jpg" and batch > 1
     for name, num in [("train", num_train), ("val", int(num_val_ratio * num_train)), ("test", int(num_test_ratio * num_train))]:
         (img_dir / name).mkdir(exist_ok=True, parents=True)
         (label_dir / name).mkdir(exist_ok=True, parents=True)

@@ -17,9 +17,8 @@ density 1:1.  This module restates its published algorithm:
                                              final byte padded with one bits)
   * markers                    jcmarker.c   (SOI, APP0, DQT x2, SOF0, DHT x4, SOS, EOI)
 
-Image sizes must be multiples of 16 (whole 4:2:0 MCUs): `save_sample` asserts 640x640 and the detection
-configurations are 640^2 and 1280^2, so the edge-replication and dummy-block rules of jcprepct.c /
-jccoefct.c are not restated.
+Image sizes that are not whole 16x16 MCUs (`save_sample` itself asserts 640x640) follow the edge-replication and
+dummy-block rules of jcsample.c / jcprepct.c / jccoefct.c, restated in `encode`.
 
 Pinned: `tests/test_jpeg_encode_oracle.py` compares `encode()` byte for byte with `cv2.imencode`.
 
@@ -231,25 +230,44 @@ def header(h: int, w: int, ql: np.ndarray, qc: np.ndarray) -> bytes:
     return out
 
 
+def _pad_edge(a: np.ndarray, h: int, w: int) -> np.ndarray:
+    return np.pad(a, ((0, h - a.shape[0]), (0, w - a.shape[1])), mode="edge")
+
+
 def encode(rgb: np.ndarray, quality: int = 95) -> bytes:
-    """== cv2.imencode('.jpg', rgb[:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, quality]).tobytes() for H, W multiples of 16."""
+    """== cv2.imencode('.jpg', rgb[:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, quality]).tobytes().
+
+    Sizes that are not whole 16x16 MCUs follow libjpeg's edge rules: columns are replicated at full resolution before
+    the chroma box filter (jcsample.c expand_right_edge), rows are replicated to an even count before it and the
+    DOWNSAMPLED rows are replicated below that (jcprepct.c), and luma blocks that lie wholly outside the image are
+    "dummy" blocks - zero AC terms, DC term copied from the block before them in the MCU (jccoefct.c compress_data)."""
     h, w, _ = rgb.shape
-    if h % 16 or w % 16:
-        raise ValueError("image size must be a multiple of 16 (whole 4:2:0 MCUs)")
+    mcuy, mcux = -(-h // 16), -(-w // 16)
     ql, qc = quant_table(STD_LUMA_Q, quality), quant_table(STD_CHROMA_Q, quality)
     y, cb, cr = rgb_to_ycc(rgb)
-    cy = fdct_quant(y, ql)
-    ccb = fdct_quant(downsample_h2v2(cb), qc)
-    ccr = fdct_quant(downsample_h2v2(cr), qc)
+    cy = fdct_quant(_pad_edge(y, mcuy * 16, mcux * 16), ql)
+    even_h = h + (h & 1)
+    ccb = fdct_quant(_pad_edge(downsample_h2v2(_pad_edge(cb, even_h, mcux * 16)), mcuy * 8, mcux * 8), qc)
+    ccr = fdct_quant(_pad_edge(downsample_h2v2(_pad_edge(cr, even_h, mcux * 16)), mcuy * 8, mcux * 8), qc)
+    hib, wib = -(-h // 8), -(-w // 8)  # luma blocks that hold image samples
     dcl, acl = huff_codes(DC_LUMA_BITS, DC_LUMA_VALS), huff_codes(AC_LUMA_BITS, AC_LUMA_VALS)
     dcc, acc = huff_codes(DC_CHROMA_BITS, DC_CHROMA_VALS), huff_codes(AC_CHROMA_BITS, AC_CHROMA_VALS)
     bw = _BitWriter()
     last = [0, 0, 0]
-    for my in range(h // 16):
-        for mx in range(w // 16):
+    for my in range(mcuy):
+        for mx in range(mcux):
+            blocks = []  # the MCU's luma blocks in scan order, dummy rules applied in that order
             for by in range(2):
+                row_real = 2 * my + by < hib
                 for bx in range(2):
-                    last[0] = _encode_block(bw, cy[2 * my + by, 2 * mx + bx], last[0], dcl, acl)
+                    if row_real and 2 * mx + bx < wib:
+                        blk = cy[2 * my + by, 2 * mx + bx]
+                    else:
+                        blk = np.zeros(64, dtype=cy.dtype)
+                        blk[0] = blocks[-1][0] if row_real else blocks[2 * by - 1][0]
+                    blocks.append(blk)
+            for blk in blocks:
+                last[0] = _encode_block(bw, blk, last[0], dcl, acl)
             last[1] = _encode_block(bw, ccb[my, mx], last[1], dcc, acc)
             last[2] = _encode_block(bw, ccr[my, mx], last[2], dcc, acc)
     bw.flush()

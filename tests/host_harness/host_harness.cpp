@@ -138,11 +138,11 @@ int hh_jpeg_decode(const uint8_t* file, int64_t len, int32_t* hw, uint8_t* out, 
 // Host run of the JPEG encode arithmetic of mtgv_jpegenc.cuh (the device kernels call the same functions per pixel /
 // block).  rgb: [h,w,3] uint8, h and w multiples of 16.  Returns the file length (<= cap) or -1.
 int64_t hh_jpeg_encode(const uint8_t* rgb, int h, int w, int quality, uint8_t* out, int64_t cap) {
-  if (h % 16 || w % 16) return -1;
+  if (h < 1 || w < 1) return -1;
   JpegEncTables T;
   jpegenc_tables(quality, &T);
   std::vector<uint8_t> o = jpegenc_header(h, w, T);
-  const int mx = w / 16, my = h / 16, nmcu = mx * my;
+  const int mx = (w + 15) / 16, my = (h + 15) / 16, nmcu = mx * my;
   std::vector<int16_t> coef((size_t)nmcu * 6 * 64);
   for (int m = 0; m < nmcu; m++) {
     const int y0 = (m / mx) * 16, x0 = (m % mx) * 16;
@@ -152,9 +152,12 @@ int64_t hh_jpeg_encode(const uint8_t* rgb, int h, int w, int quality, uint8_t* o
         int sb = 0, sr = 0;
         for (int dy = 0; dy < 2; dy++)
           for (int dx = 0; dx < 2; dx++) {
-            const uint8_t* p = rgb + ((size_t)(y0 + 2 * qy + dy) * w + x0 + 2 * qx + dx) * 3;
-            int y, cb, cr;
+            const int gy = y0 + 2 * qy + dy, gx = jpegenc_col(x0 + 2 * qx + dx, w);
+            const uint8_t* p = rgb + ((size_t)jpegenc_luma_row(gy, h) * w + gx) * 3;
+            const uint8_t* pc = rgb + ((size_t)jpegenc_chroma_row(gy, h) * w + gx) * 3;
+            int y, cb, cr, yc;
             jpegenc_ycc(p[0], p[1], p[2], &y, &cb, &cr);
+            jpegenc_ycc(pc[0], pc[1], pc[2], &yc, &cb, &cr);
             Y[2 * qy + dy][2 * qx + dx] = y; sb += cb; sr += cr;
           }
         const int bias = ((x0 / 2 + qx) & 1) ? 2 : 1;
@@ -175,6 +178,7 @@ int64_t hh_jpeg_encode(const uint8_t* rgb, int h, int w, int quality, uint8_t* o
       }
       for (int k = 0; k < 64; k++) coef[((size_t)m * 6 + j) * 64 + k] = (int16_t)nat[kJpegZigzag[k]];
     }
+    jpegenc_dummy_blocks(&coef[(size_t)m * 6 * 64], (m % mx) == mx - 1 && (((w + 7) / 8) & 1), (m / mx) == my - 1 && (((h + 7) / 8) & 1));
   }
   struct Bits {
     std::vector<uint8_t>* o; uint64_t acc = 0; int n = 0;

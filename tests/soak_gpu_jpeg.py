@@ -38,10 +38,10 @@ for b0 in range(0, n_dec, 250):
             bad_dec.append(meta[b0 + i])
 bad_enc, nbytes = [], 0
 for i in range(n_enc):
-    h, w = 16 * int(rng.integers(1, 50)), 16 * int(rng.integers(1, 50))
+    h, w = (16 * int(rng.integers(1, 50)), 16 * int(rng.integers(1, 50))) if i % 2 else (int(rng.integers(1, 500)), int(rng.integers(1, 500)))
     q = int(rng.integers(1, 101))
     imgs = np.stack([jpeg_cases.image(rng, h, w, kind) for kind in ("noise", "mixed", "smooth")])
-    out = ctx.encode_jpegs(torch.from_numpy(imgs).cuda(), q, cap=(h * w * 4 + 8192) // 4 * 4)
+    out = ctx.encode_jpegs(torch.from_numpy(imgs).cuda(), q, cap=((h + 16) * (w + 16) * 4 + 8192) // 4 * 4)
     for k in range(3):
         ref = cv2.imencode(".jpg", cv2.cvtColor(imgs[k], cv2.COLOR_RGB2BGR), [cv2.IMWRITE_JPEG_QUALITY, q])[1].tobytes()
         nbytes += len(ref)

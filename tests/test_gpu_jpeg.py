@@ -121,6 +121,26 @@ def test_host_pipeline_fed_with_jpeg_files_equals_decoded_arrays():
             assert torch.equal(a[k], b[k]), k
 
 
+def test_detection_generator_over_jpeg_backgrounds():
+    """Gen over a file-backed background source == Gen over the cv2-decoded arrays."""
+    from mtgvision_b200 import synth
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from mtgvision_b200.od_datasets import Gen
+    from tests import parity_util as PU
+
+    pool, _ = PU.small_pools(8, 1)
+    files = [jpeg_cases.encode(synth.synth_bg(j), 90, "420") for j in range(6)]
+    outs = []
+    for src in (IlsvrcImages(images=[_ref(f) for f in files]), IlsvrcImages(files=files)):
+        gen = Gen(card_min_visible_ratio=0.5, card_min_visible_ratio_edges=0.0, card_jitter_ratio=0.7, ratio_bg=0.1, kind="seg",
+                  mtg_ds=SyntheticBgFgMtgImages(pool=pool), bg_ds=src, seed=21)
+        b = gen.random_batch(6)
+        outs.append((b["image"].cpu().numpy(), b["keypoints"].cpu().numpy(), b["counts"].cpu().numpy()))
+        gen.ctx.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_rejects_unsupported_and_mismatched():
     from mtgvision_b200.abi import MtgvError
     from mtgvision_b200.context import Context

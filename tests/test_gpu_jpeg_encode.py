@@ -16,7 +16,9 @@ def cv2_bytes(rgb, quality=None):
     return cv2.imencode(".jpg", cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR), params)[1].tobytes()
 
 
-@pytest.mark.parametrize("hw,quality", [((640, 640), None), ((1280, 1280), None), ((64, 48), 75), ((16, 16), 100), ((128, 256), 30), ((320, 208), 1)])
+@pytest.mark.parametrize("hw,quality", [((640, 640), None), ((1280, 1280), None), ((64, 48), 75), ((16, 16), 100), ((128, 256), 30), ((320, 208), 1),
+                                        ((1, 1), None), ((7, 5), 90), ((9, 17), None), ((17, 16), 60), ((31, 33), None), ((100, 101), 80), ((375, 500), None),
+                                        ((49, 15), 100), ((15, 130), None)])
 def test_file_bytes_equal_cv2(hw, quality):
     from mtgvision_b200.context import Context
 
@@ -26,7 +28,7 @@ def test_file_bytes_equal_cv2(hw, quality):
     imgs += [np.zeros((*hw, 3), np.uint8), np.full((*hw, 3), 255, np.uint8)]
     batch = np.stack(imgs)
     q = 95 if quality is None else quality
-    cap = hw[0] * hw[1] * 3 + 4096  # noise at quality 100 expands
+    cap = (hw[0] + 16) * (hw[1] + 16) * 3 + 4096  # noise at quality 100 expands
     nhwc = ctx.encode_jpegs(torch.from_numpy(batch).cuda(), q, cap=cap // 4 * 4)
     nchw = ctx.encode_jpegs(torch.from_numpy(batch).cuda().permute(0, 3, 1, 2).contiguous(), q, layout="nchw", cap=cap // 4 * 4)
     for k, img in enumerate(imgs):
@@ -45,8 +47,8 @@ def test_capacity_and_size_errors():
     noise = torch.from_numpy(jpeg_cases.image(rng, 64, 64, "noise")[None]).cuda()
     with pytest.raises(MtgvError, match="do not fit"):
         ctx.encode_jpegs(noise, 100, cap=2048)
-    with pytest.raises(MtgvError, match="multiples of 16"):
-        ctx.encode_jpegs(torch.zeros((1, 40, 64, 3), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(MtgvError, match="16384"):
+        ctx.encode_jpegs(torch.zeros((1, 1, 16400, 3), dtype=torch.uint8, device="cuda"))
     assert ctx.encode_jpegs(torch.zeros((0, 64, 64, 3), dtype=torch.uint8, device="cuda")) == []
     ctx.close()
 
