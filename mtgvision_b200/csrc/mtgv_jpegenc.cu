@@ -47,6 +47,7 @@ struct ImgLayout {
   int row_stride, px_stride, ch_stride;
 };
 
+template <bool RAGGED>  // RAGGED: the image is not a whole number of 16x16 MCUs (edge replication, dummy blocks)
 __global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__ images, ImgLayout L, int H, int W, int mcux, int nmcu,
                                                      const JpegEncTables* __restrict__ T, int16_t* __restrict__ coef) {
   __shared__ int16_t samp[24][64];   // level-shifted samples, natural order; blocks = 4 MCUs x (Y00 Y01 Y10 Y11 Cb Cr)
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__
     if (m < nmcu) {
       const int my = m / mcux, mx = m - my * mcux;
       const uint8_t* base = images + (int64_t)img * L.img_stride;
-      const bool edge = (my + 1) * 16 > H || (mx + 1) * 16 > W;  // an MCU that sticks out of the image
+      const bool edge = RAGGED && ((my + 1) * 16 > H || (mx + 1) * 16 > W);  // an MCU that sticks out of the image
       int sb = 0, sr = 0;
 #pragma unroll
       for (int dy = 0; dy < 2; dy++)
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__
           const uint8_t* p = base + (int64_t)yl * L.row_stride + (int64_t)x * L.px_stride;
           int Y, cb, cr;
           jpegenc_ycc(__ldg(p), __ldg(p + L.ch_stride), __ldg(p + 2 * (int64_t)L.ch_stride), &Y, &cb, &cr);
-          if (yc != yl) {
+          if (RAGGED && yc != yl) {
             const uint8_t* pc = base + (int64_t)yc * L.row_stride + (int64_t)x * L.px_stride;
             int Yc;
             jpegenc_ycc(__ldg(pc), __ldg(pc + L.ch_stride), __ldg(pc + 2 * (int64_t)L.ch_stride), &Yc, &cb, &cr);
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) k_jpegenc_dct(const uint8_t* __restrict__
     for (int k = 0; k < 8; k++) outb[b][c_zz_of_natural[k * 8 + t]] = (int16_t)jpegenc_quant(o[k], q[k * 8 + t]);
   }
   __syncthreads();
-  if ((((W + 7) >> 3) | ((H + 7) >> 3)) & 1) {  // an odd number of luma block columns / rows: the last MCUs hold dummy blocks
+  if (RAGGED && ((((W + 7) >> 3) | ((H + 7) >> 3)) & 1)) {  // an odd number of luma block columns / rows: the last MCUs hold dummy blocks
     if (tid < 4 && m0 + tid < nmcu) {  // luma blocks wholly outside the image: zero AC, DC of the block before (jccoefct.c)
       const int m = m0 + tid, my = m / mcux, mx = m - my * mcux;
       jpegenc_dummy_blocks(&outb[tid * 6][0], mx == mcux - 1 && (((W + 7) >> 3) & 1), my == nmcu / mcux - 1 && (((H + 7) >> 3) & 1));
@@ -172,14 +173,14 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-__device__ __forceinline__ int warp_excl(int v, int lane) {
+__device__ __forceinline__ int warp_incl(int v, int lane) {
   int incl = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const int t = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += t;
   }
-  return incl - v;
+  return incl;
 }
 
 // ORs the low nbits (1..32) of val into an MSB-first bit stream held as 32-bit words (word 0 bit 31 = first bit)
@@ -270,25 +271,23 @@ __global__ void __launch_bounds__(256) k_jpegenc_emit(const int16_t* __restrict_
     const int m = b / 6, j = b - m * 6, pb = jpegenc_pred_block(m, j), t = j < 4 ? 0 : 1;
     const WarpBlock B = warp_block(C + (int64_t)b * 64, pb < 0 ? 0 : (int)C[(int64_t)pb * 64], dc[t], ac[t], lane);
     const unsigned off = boff[(int64_t)img * nblk + b], s0 = off & 31u;
-    const int tot0 = warp_sum(B.len0);
-    const int len = tot0 + warp_sum(B.len1) + (B.eob >> 16);
-    buf[lane] = 0;
-    if (lane + 32 < kEncBufWords) buf[lane + 32] = 0;
+    const int in0 = warp_incl(B.len0, lane), in1 = warp_incl(B.len1, lane);
+    const int tot0 = __shfl_sync(0xffffffffu, in0, 31);
+    const int len = tot0 + __shfl_sync(0xffffffffu, in1, 31) + (B.eob >> 16);
+    const int nw = (int)((s0 + (unsigned)len + 31u) >> 5);
+    for (int i = lane; i < nw; i += 32) buf[i] = 0;
     __syncwarp();
-    unsigned p0 = s0 + (unsigned)warp_excl(B.len0, lane), p1 = s0 + (unsigned)tot0 + (unsigned)warp_excl(B.len1, lane);
-    if (B.len0) {
+    unsigned p0 = s0 + (unsigned)(in0 - B.len0), p1 = s0 + (unsigned)(tot0 + in1 - B.len1);
+    if (B.len0) {  // run/size code and value bits go in as one field (at most 16 + 11 bits)
       for (int z = 0; z < B.nz0; z++, p0 += B.zrl >> 16) smem_put(buf, p0, B.zrl & 0xffffu, (int)(B.zrl >> 16));
-      smem_put(buf, p0, B.code0 & 0xffffu, (int)(B.code0 >> 16));
-      if (B.nb0) smem_put(buf, p0 + (B.code0 >> 16), B.val0, B.nb0);
+      smem_put(buf, p0, ((B.code0 & 0xffffu) << B.nb0) | B.val0, (int)(B.code0 >> 16) + B.nb0);
     }
     if (B.len1) {
       for (int z = 0; z < B.nz1; z++, p1 += B.zrl >> 16) smem_put(buf, p1, B.zrl & 0xffffu, (int)(B.zrl >> 16));
-      smem_put(buf, p1, B.code1 & 0xffffu, (int)(B.code1 >> 16));
-      if (B.nb1) smem_put(buf, p1 + (B.code1 >> 16), B.val1, B.nb1);
+      smem_put(buf, p1, ((B.code1 & 0xffffu) << B.nb1) | B.val1, (int)(B.code1 >> 16) + B.nb1);
     }
     if (lane == 0 && B.eob) smem_put(buf, s0 + (unsigned)len - ((unsigned)B.eob >> 16), (unsigned)B.eob & 0xffffu, B.eob >> 16);
     __syncwarp();
-    const int nw = (int)((s0 + (unsigned)len + 31u) >> 5);
     const uint32_t w0 = off >> 5;
     for (int i = lane; i < nw; i += 32) {
       if (w0 + i < cap_words) {
@@ -450,7 +449,8 @@ int jpegenc_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int
   if (layout == MTGV_LAYOUT_NCHW) { L.img_stride = (int64_t)3 * h * w; L.row_stride = w; L.px_stride = 1; L.ch_stride = h * w; }
   else { L.img_stride = (int64_t)3 * h * w; L.row_stride = 3 * w; L.px_stride = 3; L.ch_stride = 1; }
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[0], stream));
-  k_jpegenc_dct<<<dim3((nmcu + 3) / 4, n), 256, 0, stream>>>(images, L, h, w, mcux, nmcu, st->tables, st->coef);
+  if ((h | w) & 15) k_jpegenc_dct<true><<<dim3((nmcu + 3) / 4, n), 256, 0, stream>>>(images, L, h, w, mcux, nmcu, st->tables, st->coef);
+  else k_jpegenc_dct<false><<<dim3((nmcu + 3) / 4, n), 256, 0, stream>>>(images, L, h, w, mcux, nmcu, st->tables, st->coef);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->bits, 0, (size_t)n * (size_t)cap, stream));
