@@ -20,7 +20,7 @@ density 1:1.  This module restates its published algorithm:
 Image sizes that are not whole 16x16 MCUs (`save_sample` itself asserts 640x640) follow the edge-replication and
 dummy-block rules of jcsample.c / jcprepct.c / jccoefct.c, restated in `encode`.
 
-Pinned: `tests/test_jpeg_encode_oracle.py` compares `encode()` byte for byte with `cv2.imencode`.
+Pinned: `tests/test_jpeg_encode.py` compares `encode()` byte for byte with `cv2.imencode`.
 
 Nothing under `mtgvision_b200/` may import this module.
 """
