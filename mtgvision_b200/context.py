@@ -283,6 +283,14 @@ class Context:
         batch = self.prepare_jpegs(files)
         return self.decode_prepared(batch), batch["out_off"][:-1].copy(), batch["hw"]
 
+    def set_card_pool_from_jpegs(self, files: list[bytes], labels3, grp_off, grp_mem):
+        """Card pool straight from JPEG file bytes (all of one size): decoded on the device, never materialised on the host."""
+        flat, _, hw = self.decode_jpegs(files)
+        if len(files) == 0 or not (hw == hw[0]).all():
+            raise ValueError("card files must all have the same size")
+        torch.cuda.current_stream(self.device).synchronize()
+        self.set_card_pool(flat.view(len(files), int(hw[0, 0]), int(hw[0, 1]), 3), labels3, grp_off, grp_mem)
+
     def set_bg_pool_from_jpegs(self, files: list[bytes]):
         """Background pool straight from JPEG file bytes: decoded on the device, never materialised on the host."""
         flat, off, hw = self.decode_jpegs(files)

@@ -121,6 +121,26 @@ def test_host_pipeline_fed_with_jpeg_files_equals_decoded_arrays():
             assert torch.equal(a[k], b[k]), k
 
 
+def test_card_pool_from_jpeg_files():
+    """mtgv_set_card_pool fed from device-decoded files == fed from the cv2-decoded arrays (same generated batch)."""
+    from mtgvision_b200 import abi, synth
+    from tests import parity_util as PU
+
+    pool, bgs = PU.small_pools(4, 4)
+    files = [jpeg_cases.encode(pool.images[k], 92, "420") for k in range(4)]
+    decoded = synth.CardPool(np.stack([_ref(f) for f in files]), pool.faces)
+    outs = []
+    for mode in ("arrays", "files"):
+        ctx = PU.make_context(decoded, bgs)
+        if mode == "files":
+            ctx.set_card_pool_from_jpegs(files, decoded.labels3, decoded.grp_off, decoded.grp_mem)
+        tape = ctx.sample_encoder_tape(7, 0, 4)
+        params, labels = ctx.expand_params(tape)
+        outs.append((ctx.encoder_batch(params, abi.OUT_U8).cpu().numpy(), labels.cpu().numpy()))
+        ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_detection_generator_over_jpeg_backgrounds():
     """Gen over a file-backed background source == Gen over the cv2-decoded arrays."""
     from mtgvision_b200 import synth
