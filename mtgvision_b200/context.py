@@ -89,6 +89,7 @@ class Context:
                                        hw.ctypes.data_as(C.c_void_p), len(images))
         self._check(rc, "mtgv_set_bg_pool")
         self.n_bgs = len(images)
+        self.bg_hw = hw
 
     def set_encoder_config(self, *, x_size_hw=(192, 128), y_size_hw=(192, 128), target_is_input_prob=0.05,
                            similar_neg_prob=0.2, half_upsidedown=False, paired=True, targets=False):
@@ -238,6 +239,14 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ image decode into the pools
+    def oversized_backgrounds(self, x_size_hw) -> np.ndarray:
+        """Pool indices of backgrounds so large that some rotations need an INTER_AREA reduction beyond the kernels' limit
+        (factor 6: DESIGN.md, limits): `rotate_bounded` grows the canvas up to the image diagonal and `crop_to_size` then
+        shrinks it by min(canvas_h / out_h, canvas_w / out_w).  Samples that hit the limit are flagged in params.status."""
+        hw = np.asarray(getattr(self, "bg_hw", np.zeros((0, 2))), dtype=np.float64).reshape(-1, 2)
+        diag = np.hypot(hw[:, 0], hw[:, 1])
+        return np.nonzero(np.minimum(diag / x_size_hw[0], diag / x_size_hw[1]) > 6.0)[0]
+
     def jpeg_info(self, data: bytes) -> tuple[int, int]:
         """(h, w) of a baseline JPEG file; raises MtgvError for files the device decoder does not support."""
         buf = np.frombuffer(data, dtype=np.uint8)
@@ -298,6 +307,7 @@ class Context:
         rc = self.lib.mtgv_set_bg_pool(self._h, _ptr(flat), off.ctypes.data_as(C.c_void_p), hw.ctypes.data_as(C.c_void_p), len(files))
         self._check(rc, "mtgv_set_bg_pool")
         self.n_bgs = len(files)
+        self.bg_hw = hw
 
     # ------------------------------------------------------------------ image encode for the dataset writer
     def encode_jpegs(self, images: torch.Tensor, quality: int = 95, layout: str | None = None, cap: int | None = None) -> list[bytes]:

@@ -78,6 +78,13 @@ class RanMtgEncDecDataset(IterableDataset):
         pool = self.mtg.pool
         self.ctx.set_card_pool(pool.images, pool.labels3, pool.grp_off, pool.grp_mem)
         self.ilsvrc.fill_pool(self.ctx)
+        big = self.ctx.oversized_backgrounds(self.x_size_hw)
+        if len(big):
+            import warnings
+
+            warnings.warn(f"{len(big)} background(s) (first: pool index {int(big[0])}, {tuple(int(v) for v in self.ctx.bg_hw[big[0]])}) are large "
+                          f"enough that some rotations exceed the x6 INTER_AREA limit at x_size_hw={self.x_size_hw}; those samples are "
+                          "flagged in params.status (check_data=True raises on them)")
 
     # ------------------------------------------------------------------ reference surface
     def __iter__(self):

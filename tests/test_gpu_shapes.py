@@ -112,3 +112,16 @@ def test_pair_partner_plane_reuse_is_invisible():
         assert torch.equal(both[16:], second_alone)
     finally:
         ctx.close()
+
+
+def test_oversized_background_is_reported_at_ingest():
+    """A background whose rotated canvas can exceed the x6 INTER_AREA limit: warned about when the pool is filled."""
+    from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
+    from mtgvision_b200.encoder_train import RanMtgEncDecDataset
+
+    pool, bgs = PU.small_pools(4, 4)
+    huge = np.zeros((1500, 2000, 3), np.uint8)
+    with pytest.warns(UserWarning, match="INTER_AREA limit"):
+        ds = RanMtgEncDecDataset(2, paired=True, targets=False, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=IlsvrcImages(images=list(bgs) + [huge]), seed=1)
+    assert list(ds.ctx.oversized_backgrounds((192, 128))) == [4]
+    ds.ctx.close()
