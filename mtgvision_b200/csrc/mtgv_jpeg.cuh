@@ -46,9 +46,11 @@ struct JpegImg {
   int32_t hf[3], vf[3];  // upsampling factors hmax / ch, vmax / cv
   int32_t dh[3], dw[3];  // downsampled component size ceil(h * cv / vmax), ceil(w * ch / hmax)
   int32_t seg0, nseg;
-  int32_t nblk, par;     // par: decoded by the subsequence-parallel kernel (single interval); DC terms are written as differences
+  int32_t nblk, par;     // decoded by k_jpeg_entropy_par: 1 = one interval (self-synchronising runs, DC terms integrated by
+                         // k_jpeg_dc), 2 = restart intervals (a thread per interval, DC terms written directly)
   int64_t clean_off;     // byte-unstuffed copy of the scan in the clean scratch (bytes, multiple of 16)
   int64_t sync_off;      // checkpoint states of the subsequences (uint64 units)
+  int64_t rst_off;       // par == 2: clean byte position of every restart interval but the first (uint32 units)
 };
 
 struct JpegSeg {  // one restart interval (or the whole scan): decoded by one thread
@@ -69,7 +71,7 @@ inline int jpeg_fail(std::string* err, const char* msg) {
 }
 
 // Fills im (geometry, table selectors; offsets other than scan_off are the caller's), tb and appends the
-// image's segments.  Returns 0 or -1 with *err set.
+// image's segments (segs may be null: the interval count is then derived from DRI alone).  Returns 0 or -1 with *err set.
 inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im, JpegTables* tb, std::vector<JpegSeg>* segs,
                       std::string* err) {
   memset(im, 0, sizeof(*im));
@@ -203,8 +205,14 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
   }
   im->scan_off = (int32_t)pos;
   im->file_len = (int32_t)len;
-  // segments: the whole scan, or one per restart interval (the RSTn markers are byte aligned: B.1.1.5)
+  // segments: the whole scan, or one per restart interval (the RSTn markers are byte aligned: B.1.1.5).  The device
+  // decoder finds the markers itself while it unstuffs the scan (segs == nullptr): only the interval count is needed.
   const int total = im->mcux * im->mcuy;
+  if (!segs) {
+    im->seg0 = 0;
+    im->nseg = im->dri > 0 ? (total + im->dri - 1) / im->dri : 1;
+    return 0;
+  }
   im->seg0 = (int32_t)segs->size();
   if (im->dri <= 0) {
     segs->push_back(JpegSeg{img_index, 0, total, (int32_t)pos});
