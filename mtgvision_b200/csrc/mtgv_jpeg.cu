@@ -197,52 +197,14 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
   return nb;
 }
 
-__global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t* __restrict__ files, const JpegImg* __restrict__ imgs,
-                                                                 const JpegTables* __restrict__ tbs,
-                                                                 uint8_t* __restrict__ clean, uint64_t* __restrict__ sync,
-                                                                 int16_t* __restrict__ coef, int16_t* __restrict__ dcs, int32_t* __restrict__ end_blk,
-                                                                 uint32_t* __restrict__ rstpos) {
-  __shared__ ParSmem S;
+// ---- squeeze out the stuffed zeros: 4 consecutive bytes per thread, 1 KiB per pass; the first marker ends the scan ----
+// RST: restart markers (files with restart intervals) are squeezed out too and the clean position behind each is recorded
+// in rp: the intervals start there, byte aligned, with fresh DC predictions.  Returns the clean length in bytes.
+template <bool RST>
+__device__ __forceinline__ unsigned par_unstuff(ParSmem& S, const uint8_t* __restrict__ file, int scan_off, int file_len, uint8_t* __restrict__ cl8,
+                                                uint32_t* __restrict__ rp, int nseg, unsigned* nrst_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int img = blockIdx.x;
-  const JpegImg& im = imgs[img];
-  {
-    const JpegTables* T = tbs + img;
-    for (int i = tid; i < (int)(sizeof(S.fast) / 4); i += kParThreads) ((uint32_t*)S.fast)[i] = ((const uint32_t*)T->fast)[i];
-    for (int i = tid; i < 4 * 18; i += kParThreads) {
-      ((int32_t*)S.maxcode)[i] = ((const int32_t*)T->maxcode)[i];
-      ((int32_t*)S.valoff)[i] = ((const int32_t*)T->valoff)[i];
-    }
-    for (int i = tid; i < 4 * 256 / 4; i += kParThreads) ((uint32_t*)S.vals)[i] = ((const uint32_t*)T->vals)[i];
-    if (tid < 64) S.zz[tid] = c_zigzag[tid];
-    if (tid == 0) {
-      int j = 0;
-      for (int c = 0; c < im.ncomp; c++)
-        for (int by = 0; by < im.cv[c]; by++)
-          for (int bx = 0; bx < im.ch[c]; bx++, j++) {
-            S.blk_c[j] = (uint8_t)c; S.blk_y[j] = (uint8_t)by; S.blk_x[j] = (uint8_t)bx;
-            S.blk_td[j] = (uint8_t)im.td[c]; S.blk_ta[j] = (uint8_t)(2 + im.ta[c]);
-            S.j_off[j] = (im.coef_blk + im.blk0[c] + (int64_t)by * im.bw[c] + bx) * 64;
-            S.j_rs[j] = im.cv[c] * im.bw[c] * 64;
-            S.j_cs[j] = im.ch[c] * 64;
-          }
-    }
-  }
-  ParGeom G;
-  G.nb_mcu = 0;
-  for (int c = 0; c < im.ncomp; c++) G.nb_mcu += im.ch[c] * im.cv[c];
-  G.mcux = im.mcux;
-  G.nblk_scan = im.mcux * im.mcuy * G.nb_mcu;
-  const uint8_t* file = files + im.file_off;
-  const int file_len = im.file_len, scan_off = im.scan_off;
-  uint8_t* cl8 = clean + im.clean_off;
-  __syncthreads();
-
-  // ---- squeeze out the stuffed zeros: 4 consecutive bytes per thread, 1 KiB per pass; the first marker ends the scan ----
-  // Restart markers (files with restart intervals) are squeezed out too; the clean position behind each is recorded: the
-  // intervals start there, byte aligned, with fresh DC predictions.
-  const bool intervals = im.par == 2;
-  uint32_t* rp = rstpos + im.rst_off;
+  constexpr bool intervals = RST;
   unsigned wp = 0, nrst = 0;
   for (int base = scan_off;; base += 4 * kParThreads) {
     const int i0 = base + tid * 4;
@@ -292,7 +254,7 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
     for (int q = 0; q < 4; q++) {
       if ((keep >> q) & 1u) cl8[(pos++) ^ 3u] = (uint8_t)b[q + 1];
       if ((rst >> q) & 1u) {
-        if ((int)ri < im.nseg - 1) rp[ri] = pos;  // the next interval starts at this clean byte
+        if ((int)ri < nseg - 1) rp[ri] = pos;  // the next interval starts at this clean byte
         ri++;
       }
     }
@@ -301,6 +263,56 @@ __global__ void __launch_bounds__(kParThreads) k_jpeg_entropy_par(const uint8_t*
     __syncthreads();
     if (first_marker != 0x7fffffff) break;
   }
+  *nrst_out = nrst;
+  return wp;
+}
+
+__global__ void __launch_bounds__(kParThreads, 1536 / kParThreads) k_jpeg_entropy_par(const uint8_t* __restrict__ files, const JpegImg* __restrict__ imgs,
+                                                                 const JpegTables* __restrict__ tbs,
+                                                                 uint8_t* __restrict__ clean, uint64_t* __restrict__ sync,
+                                                                 int16_t* __restrict__ coef, int16_t* __restrict__ dcs, int32_t* __restrict__ end_blk,
+                                                                 uint32_t* __restrict__ rstpos) {
+  __shared__ ParSmem S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = blockIdx.x;
+  const JpegImg& im = imgs[img];
+  {
+    const JpegTables* T = tbs + img;
+    for (int i = tid; i < (int)(sizeof(S.fast) / 4); i += kParThreads) ((uint32_t*)S.fast)[i] = ((const uint32_t*)T->fast)[i];
+    for (int i = tid; i < 4 * 18; i += kParThreads) {
+      ((int32_t*)S.maxcode)[i] = ((const int32_t*)T->maxcode)[i];
+      ((int32_t*)S.valoff)[i] = ((const int32_t*)T->valoff)[i];
+    }
+    for (int i = tid; i < 4 * 256 / 4; i += kParThreads) ((uint32_t*)S.vals)[i] = ((const uint32_t*)T->vals)[i];
+    if (tid < 64) S.zz[tid] = c_zigzag[tid];
+    if (tid == 0) {
+      int j = 0;
+      for (int c = 0; c < im.ncomp; c++)
+        for (int by = 0; by < im.cv[c]; by++)
+          for (int bx = 0; bx < im.ch[c]; bx++, j++) {
+            S.blk_c[j] = (uint8_t)c; S.blk_y[j] = (uint8_t)by; S.blk_x[j] = (uint8_t)bx;
+            S.blk_td[j] = (uint8_t)im.td[c]; S.blk_ta[j] = (uint8_t)(2 + im.ta[c]);
+            S.j_off[j] = (im.coef_blk + im.blk0[c] + (int64_t)by * im.bw[c] + bx) * 64;
+            S.j_rs[j] = im.cv[c] * im.bw[c] * 64;
+            S.j_cs[j] = im.ch[c] * 64;
+          }
+    }
+  }
+  ParGeom G;
+  G.nb_mcu = 0;
+  for (int c = 0; c < im.ncomp; c++) G.nb_mcu += im.ch[c] * im.cv[c];
+  G.mcux = im.mcux;
+  G.nblk_scan = im.mcux * im.mcuy * G.nb_mcu;
+  const uint8_t* file = files + im.file_off;
+  const int file_len = im.file_len, scan_off = im.scan_off;
+  uint8_t* cl8 = clean + im.clean_off;
+  __syncthreads();
+
+  const bool intervals = im.par == 2;
+  uint32_t* rp = rstpos + im.rst_off;
+  unsigned nrst = 0;
+  const unsigned wp = intervals ? par_unstuff<true>(S, file, scan_off, file_len, cl8, rp, im.nseg, &nrst)
+                                : par_unstuff<false>(S, file, scan_off, file_len, cl8, rp, im.nseg, &nrst);
   if (tid < 8) cl8[(wp + tid) ^ 3u] = 0;  // whole last word (+1) reads as zero bits
   __syncthreads();
   const unsigned Lw = (wp + 3u) >> 2;
