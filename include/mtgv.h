@@ -403,7 +403,9 @@ int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw)
  *      out_off = i*H*W*3 the tensor mtgv_set_card_pool / mtgv_update_*_images take.
  * hw: host [n][2] as returned by mtgv_jpeg_info (what the caller sized `out` with); a file whose frame header
  *     disagrees fails the call.  Bit-exact with cv2.imdecode (libjpeg-turbo: ISLOW IDCT, fancy upsampling).
- * Work is queued on `stream`; the host arrays may be reused when the call returns. */
+ * Work is queued on `stream`.  file_off, out_off and hw may be reused when the call returns; `files` is read by an
+ * asynchronous copy when it is page-locked memory and must then stay valid until that work has run (pageable memory is
+ * staged before the call returns). */
 int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out,
                            const int64_t* out_off, const int32_t* hw, void* stream);
 

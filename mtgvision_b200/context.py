@@ -278,6 +278,9 @@ class Context:
         rc = self.lib.mtgv_decode_jpeg_batch(self._h, C.c_void_p(batch["blob"].data_ptr()), vp(batch["file_off"]), batch["n"], _ptr(out),
                                              vp(batch["out_off"]), vp(batch["hw"]), self._stream())
         self._check(rc, "mtgv_decode_jpeg_batch")
+        # the pinned file bytes are read by an asynchronous copy: keep them alive until the next call (which starts by
+        # waiting for the stream) instead of letting the caller's dict be the only reference
+        self._jpeg_inflight = batch
         return out
 
     def jpeg_last_kernel_ms(self) -> tuple[float, float, float]:
