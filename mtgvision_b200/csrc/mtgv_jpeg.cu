@@ -599,6 +599,7 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   if (!ctx->jpeg) {
     ctx->jpeg = new JpegState();
     MTGV_CUDA_OK(ctx, cudaMemcpyToSymbol(c_zigzag, kJpegZigzag, 64));
+    MTGV_CUDA_OK(ctx, cudaDeviceSynchronize());  // once: the table is in place before kernels on the caller's stream read it
     for (auto& e : ((JpegState*)ctx->jpeg)->ev) MTGV_CUDA_OK(ctx, cudaEventCreate(&e));
   }
   JpegState* st = (JpegState*)ctx->jpeg;
@@ -667,7 +668,8 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   if ((rc = grow(ctx, (void**)&st->endblk, &st->endblk_cap, (size_t)n * sizeof(int32_t)))) return rc;
   if ((rc = grow(ctx, (void**)&st->dcs, &st->dcs_cap, ((size_t)nblk_total + 1) * sizeof(int16_t)))) return rc;
   if ((rc = grow(ctx, (void**)&st->rstpos, &st->rstpos_cap, ((size_t)rst_total + 1) * sizeof(uint32_t)))) return rc;
-  MTGV_CUDA_OK(ctx, cudaStreamSynchronize(stream));  // an earlier batch may still be reading the staging buffer
+  // an earlier batch (on whatever stream) may still be reading the staging buffer and the scratch arrays
+  if (st->timed) MTGV_CUDA_OK(ctx, cudaEventSynchronize(st->ev[3]));
   if (desc_bytes > st->desc_host_cap) {
     if (st->desc_host) MTGV_CUDA_OK(ctx, cudaFreeHost(st->desc_host));
     st->desc_host = nullptr; st->desc_host_cap = 0;

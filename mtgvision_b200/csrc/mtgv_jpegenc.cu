@@ -424,19 +424,22 @@ int jpegenc_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int
     uint8_t inv[64];
     for (int k = 0; k < 64; k++) inv[kJpegZigzag[k]] = (uint8_t)k;
     MTGV_CUDA_OK(ctx, cudaMemcpyToSymbol(c_zz_of_natural, inv, 64));
+    MTGV_CUDA_OK(ctx, cudaDeviceSynchronize());  // once: the table is in place before kernels on the caller's stream read it
     MTGV_CUDA_OK(ctx, cudaMalloc((void**)&s->tables, sizeof(JpegEncTables)));
     MTGV_CUDA_OK(ctx, cudaMalloc((void**)&s->header, 1024));
     for (auto& e : s->ev) MTGV_CUDA_OK(ctx, cudaEventCreate(&e));
   }
   JpegEncState* st = (JpegEncState*)ctx->jpegenc;
+  if (st->timed) MTGV_CUDA_OK(ctx, cudaEventSynchronize(st->ev[2]));  // the previous batch (on whatever stream) still owns tables and scratch
   if (st->quality != quality || st->h != h || st->w != w) {
     JpegEncTables T;
     jpegenc_tables(quality, &T);
     const std::vector<uint8_t> hdr = jpegenc_header(h, w, T);
     if (hdr.size() > 1024) return fail(ctx, MTGV_ERR_LIMIT, "mtgv_encode_jpeg_batch: header too long");
-    MTGV_CUDA_OK(ctx, cudaStreamSynchronize(stream));
-    MTGV_CUDA_OK(ctx, cudaMemcpy(st->tables, &T, sizeof(T), cudaMemcpyHostToDevice));
-    MTGV_CUDA_OK(ctx, cudaMemcpy(st->header, hdr.data(), hdr.size(), cudaMemcpyHostToDevice));
+    // on the caller's stream, so that the kernels below are ordered behind the upload
+    MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->tables, &T, sizeof(T), cudaMemcpyHostToDevice, stream));
+    MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->header, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, stream));
+    MTGV_CUDA_OK(ctx, cudaStreamSynchronize(stream));  // T and hdr are locals
     st->header_len = (int)hdr.size();
     st->quality = quality; st->h = h; st->w = w;
   }
