@@ -37,8 +37,9 @@ BYTES_BG = BG_HW[0] * BG_HW[1] * 3
 BYTES_OUT_F16 = 3 * X_HW[0] * X_HW[1] * 2
 
 
-def workload_config(args, extra=None):
-    cfg = {
+def workload_config(args):
+    """The `config` of the JSON line - identical for the CUDA arm and the reference arm (run-dependent counts go to `stats`)."""
+    return {
         "workload": "encoder training batches: 512 positive pairs (x, x2) with hard-negative same-name swaps, "
                     "synthetic 680x488 cards + 375x500 backgrounds -> [512,3,192,128] fp16 NCHW + int64 labels",
         "pairs_per_step": PAIRS,
@@ -47,12 +48,10 @@ def workload_config(args, extra=None):
         "bg_pool": args.pool_bgs,
         "target_is_input_prob": 0.05,
         "similar_neg_prob": 0.2,
+        "inputs_e2e": "JPEG files (quality 90) of the batch's cards and backgrounds in host memory, as the reference's loaders read them",
         "parallelism": f"{args.gpus} independent shard(s), one process per GPU, no collective",
         "l2": "inputs larger than L2: each step reads ~1000 distinct cards (~1 GB) of a multi-GB resident pool; no flush",
     }
-    if extra:
-        cfg.update(extra)
-    return cfg
 
 
 # --------------------------------------------------------------------------------------- #
@@ -60,10 +59,55 @@ def workload_config(args, extra=None):
 # --------------------------------------------------------------------------------------- #
 
 _CPU_STATE = {}
+JPEG_Q = 90
+
+
+def _encode_chunk(args):
+    import cv2
+
+    kind, a, b = args
+    src = _CPU_STATE["cards"].images if kind == "c" else _CPU_STATE["bgs"]
+    cv2.setNumThreads(1)
+    return [cv2.imencode(".jpg", src[k][:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, JPEG_Q])[1].tobytes() for k in range(a, b)]
+
+
+def encode_pools_as_jpeg(cards, bgs, workers):
+    """The pools as the files a loader would find on disk (cv2.imwrite quality 90): (card_files, bg_files)."""
+    import multiprocessing as mp
+
+    _CPU_STATE["cards"], _CPU_STATE["bgs"] = cards, bgs
+    nc, nb = len(cards.images), len(bgs)
+    jobs = [("c", a, min(a + 32, nc)) for a in range(0, nc, 32)] + [("b", a, min(a + 32, nb)) for a in range(0, nb, 32)]
+    with mp.get_context("fork").Pool(max(1, workers)) as pool:
+        parts = pool.map(_encode_chunk, jobs)
+    files = [f for part in parts for f in part]
+    return files[:nc], files[nc:]
+
+
+class _DecodingImages:
+    """images[k] = cv2.imread of file k (imread_float, util/image.py:107-114: IMREAD_COLOR_RGB) - every access decodes,
+    like `ran_card` -> dl_and_open_im_resized and IlsvrcImages.ran -> _load_image do per drawn sample."""
+
+    def __init__(self, files):
+        self.files = files
+
+    def __len__(self):
+        return len(self.files)
+
+    def __getitem__(self, k):
+        import cv2
+        import numpy as np
+
+        return cv2.imdecode(np.frombuffer(self.files[k], np.uint8), cv2.IMREAD_COLOR_RGB)
+
+
+class _FileCards:
+    def __init__(self, pool, files):
+        self.images, self.labels3, self.group_of = _DecodingImages(files), pool.labels3, pool.group_of
 
 
 def _cpu_worker(args):
-    wid, n_pairs, batch = args
+    wid, step, n_pairs, from_files = args
     import random
 
     import cv2
@@ -72,71 +116,84 @@ def _cpu_worker(args):
     from oracle import encoder_oracle as EO
 
     cv2.setNumThreads(1)
-    random.seed(1000 + wid)
-    np.random.seed(1000 + wid)
+    random.seed(1000 + 7919 * (step + 1) + wid)
+    np.random.seed(1000 + 7919 * (step + 1) + wid)
     EO.reset_shuffle_state()
-    bo = EO.BatchOracle(_CPU_STATE["cards"], _CPU_STATE["bgs"], paired=True, targets=False, x_size_hw=X_HW,
-                        target_is_input_prob=0.05, similar_neg_prob=0.2)
-    done = 0
+    cards, bgs = _CPU_STATE["cards"], _CPU_STATE["bgs"]
+    if from_files:
+        cards, bgs = _FileCards(cards, _CPU_STATE["card_files"]), _DecodingImages(_CPU_STATE["bg_files"])
+    bo = EO.BatchOracle(cards, bgs, paired=True, targets=False, x_size_hw=X_HW, target_is_input_prob=0.05, similar_neg_prob=0.2)
     t0 = time.perf_counter()
-    while done < n_pairs:
-        b = min(batch, n_pairs - done)
-        imgs, _, _ = bo.random_image_batch(b)
-        done += b
-        assert imgs["x"].shape == (b, X_HW[0], X_HW[1], 3)
-    return 2 * done, time.perf_counter() - t0
+    imgs, _, _ = bo.random_image_batch(n_pairs)  # one batch former call per worker, like a DataLoader worker
+    assert imgs["x"].shape == (n_pairs, X_HW[0], X_HW[1], 3) and imgs["x2"].shape == imgs["x"].shape
+    return 2 * n_pairs, time.perf_counter() - t0
 
 
-def cpu_generator_throughput(pairs_per_worker: int, workers: int | None = None, pool_cards: int = 64, pool_bgs: int = 64):
-    """The reference generator (oracle port: same cv2/numpy calls in the same order as
-    mtgvision/encoder_datasets.py + encoder_train.py:189-230) with one process per host core,
-    like the reference's DataLoader workers (encoder_train.py:517-523).  Returns
-    (x_samples_per_s, workers, x_samples, wall_s)."""
-    import multiprocessing as mp
+class CpuGenerator:
+    """The reference generator (oracle port: the same cv2/numpy calls in the same order as mtgvision/encoder_datasets.py +
+    encoder_train.py:149-230) on all host cores: ONE persistent pool of worker processes, one per core, like the
+    reference's DataLoader workers (encoder_train.py:517-523), over pools of the size the config states."""
 
-    from mtgvision_b200 import synth
+    def __init__(self, pool_cards, pool_bgs, workers=None, cards=None, bgs=None, files=None):
+        import multiprocessing as mp
 
-    workers = workers or os.cpu_count() or 1
-    if "cards" not in _CPU_STATE:
-        _CPU_STATE["cards"] = synth.make_card_pool(pool_cards)
-        _CPU_STATE["bgs"] = synth.make_bg_pool(pool_bgs)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(workers) as pool:
-        pool.map(_cpu_worker, [(w, 2, 2) for w in range(workers)])  # warm-up: imports, page-in
+        from mtgvision_b200 import synth
+
+        self.workers = workers or os.cpu_count() or 1
+        if cards is None:
+            cards = synth.make_card_pool(pool_cards, workers=self.workers)
+            bgs = synth.make_bg_pool(pool_bgs, workers=self.workers)
+        _CPU_STATE["cards"], _CPU_STATE["bgs"] = cards, bgs
+        if files is None:
+            files = encode_pools_as_jpeg(cards, bgs, self.workers)
+        _CPU_STATE["card_files"], _CPU_STATE["bg_files"] = files
+        self.pool = mp.get_context("fork").Pool(self.workers)  # forked after the pools exist: workers share them copy-on-write
+        self.pool.map(_cpu_worker, [(w, -1, 2, True) for w in range(self.workers)])  # warm-up: imports, page-in
+        self._step = 0
+
+    def step(self, pairs_per_worker, from_files=True):
+        """-> (x_samples, wall seconds) of one map over all workers."""
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(w, pairs_per_worker, 16) for w in range(workers)])
-        wall = time.perf_counter() - t0
-    total = sum(r[0] for r in res)
-    return total / wall, workers, total, wall
+        res = self.pool.map(_cpu_worker, [(w, self._step, pairs_per_worker, from_files) for w in range(self.workers)])
+        self._step += 1
+        return sum(r[0] for r in res), time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    pairs = max(1, args.ref_pairs_per_worker)
+    gen = CpuGenerator(args.pool_cards, args.pool_bgs)
+    workers = gen.workers
     vals = []
-    workers = os.cpu_count() or 1
-    pairs = max(4, args.ref_pairs_per_worker)
-    total = 0
-    t_all = time.perf_counter()
     for step in range(args.warmup + args.steps):
-        v, workers, n, wall = cpu_generator_throughput(pairs, workers)
+        n, wall = gen.step(pairs, from_files=True)
         if step >= args.warmup:
             vals.append((n, wall))
-            total += n
+    n_arr, w_arr = gen.step(pairs, from_files=False)  # context: the same step on decoded arrays (no cv2.imdecode)
+    gen.close()
     n_sum = sum(n for n, _ in vals)
     w_sum = sum(w for _, w in vals)
     value = n_sum / w_sum
-    sample = (f"{pairs} pairs per worker per step x {workers} workers, batch 16, pools of 64 synthetic cards/backgrounds "
-              f"(same generator as the GPU arm's pools); {n_sum} x-samples in {w_sum:.1f} s")
+    sample = (f"each step: {workers} worker processes (one per host core, cv2 threads=1, one persistent pool) x one batch of {pairs} pairs = "
+              f"{2 * pairs * workers} x-samples, drawn from pools of {args.pool_cards} cards / {args.pool_bgs} backgrounds held as quality-{JPEG_Q} JPEG "
+              f"files in host memory; per drawn card/background cv2.imdecode (imread_float) + the generator; {n_sum} x-samples in {w_sum:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * w_sum / max(1, len(vals)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, {"note": "reference CPU generator (oracle port, cv2/numpy), all host cores"}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "from_decoded_arrays": n_arr / w_arr},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "reference CPU generator (oracle port of the reference's cv2/numpy code; the reference itself is Python and needs "
+                "mtgdata/kornia/lightning, absent here) on all host cores, files in host memory -> batches in host memory",
     }
     print(json.dumps(line), flush=True)
 
@@ -288,7 +345,8 @@ def run_cuda(args):
     # here the same three C-ABI calls are issued with explicit events around the plane kernel)
     total_steps = args.warmup + args.steps
     tape = torch.empty((n_x, abi.TAPE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    params = [torch.empty((n_x, abi.PARAMS_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in range(args.steps)]
+    n_keep = min(args.steps, 64)  # parameter blocks kept for the sample statistics; longer runs reuse them cyclically
+    params = [torch.empty((n_x, abi.PARAMS_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in range(n_keep)]
     labels = torch.empty((n_x, 3), dtype=torch.int64, device=dev)
     out = torch.empty((n_x, 3, X_HW[0], X_HW[1]), dtype=torch.float16, device=dev)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -297,7 +355,7 @@ def run_cuda(args):
     def step(i, timed_idx=None):
         first = (i * world + rank) * PAIRS
         ctx.sample_encoder_tape(ds.seed, first, PAIRS, out=tape)
-        p = params[timed_idx] if timed_idx is not None else params[0]
+        p = params[timed_idx % n_keep] if timed_idx is not None else params[0]
         ctx.expand_params(tape, params=p, labels=labels)
         if timed_idx is not None:
             ev[timed_idx][0].record()
@@ -325,6 +383,7 @@ def run_cuda(args):
     clocks.start()
     time.sleep(0.25)
     launches0 = ctx.launch_count()
+    free0 = torch.cuda.mem_get_info(dev)[0]
     t0 = time.perf_counter()
     e_start.record()
     for k in range(args.steps):
@@ -333,6 +392,7 @@ def run_cuda(args):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     launches = ctx.launch_count() - launches0
+    free1 = torch.cuda.mem_get_info(dev)[0]
     ms_total = e_start.elapsed_time(e_end)
     clk = clocks.stop(t0, t1)
     barrier()
@@ -349,8 +409,12 @@ def run_cuda(args):
     n_virtual = int((kinds == abi.KIND_VIRTUAL).sum())
     n_cropped = int((kinds == abi.KIND_CROPPED).sum())
     alg_bytes = n_virtual * (BYTES_CARD + BYTES_BG + BYTES_OUT_F16) + n_cropped * (BYTES_CARD + BYTES_OUT_F16)
-    alg_per_launch = alg_bytes / args.steps
+    alg_per_launch = alg_bytes / n_keep  # sample kinds of the last n_keep steps
     k_avg_ms = sum(k_ms) / len(k_ms)
+    tenth = max(1, len(k_ms) // 10)
+    drift = {"kernel_ms_first_tenth": sum(k_ms[:tenth]) / tenth, "kernel_ms_last_tenth": sum(k_ms[-tenth:]) / tenth,
+             "kernel_ms_min": min(k_ms), "kernel_ms_median": statistics.median(k_ms), "kernel_ms_max": max(k_ms),
+             "device_memory_growth_bytes": int(free0 - free1)}
     achieved = alg_per_launch / (k_avg_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
@@ -371,74 +435,91 @@ def run_cuda(args):
                 "kernel_share_of_step": k_avg_ms * args.steps / ms_total}
 
     # ---- e2e: host buffers in -> host buffers out through the public dataset API ----
+    # Headline pair (like for like with the reference arm): the batch's 512 cards and 512 backgrounds arrive as the JPEG
+    # FILES the reference's loaders read (encoder_train.py:149-156 -> dl_and_open_im_resized / imread_float,
+    # util/image.py:107-114), in pinned host memory; every step parses / validates its batch (prepare_jpeg_batch_pinned),
+    # uploads the compressed bytes, decodes on the device, ingests into the pools, generates, and downloads x, x2, labels.
     e2e = None
+    card_files = bg_files = None
     if not args.no_e2e:
-        hc = torch.from_numpy(cards.images[np.arange(PAIRS) % len(cards.images)]).pin_memory()
-        hb = torch.from_numpy(np.stack([bgs[j % len(bgs)] for j in range(PAIRS)])).pin_memory()
-        e2e_steps = max(3, min(args.steps, 30))  # pipeline fill and drain are inside the timed region
-
-        def feed(k):
-            for _ in range(k):
-                yield hc, hb
-
-        for _ in ds.host_tensor_batches(feed(3)):  # warm-up: staging buffers, pinned outputs
-            pass
-        barrier()
-        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_w0 = time.perf_counter()
-        es.record()
-        checksum = 0.0
-        for res in ds.host_tensor_batches(feed(e2e_steps)):
-            checksum += float(res["x_labels"][0, 0])  # the consumer touches every batch on the host
-        ee.record()
-        torch.cuda.synchronize()
-        t_w1 = time.perf_counter()
-        e_ms = torch.tensor([max(es.elapsed_time(ee), 1e3 * (t_w1 - t_w0))], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-        d2h = sum(v.numel() * v.element_size() for v in res.values())
-        h2d = int(hc.numel() + hb.numel())
-        e2e = {"value": world * n_x * e2e_steps / (float(e_ms.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "ms_per_step": float(e_ms.item()) / e2e_steps,
-               "h2d_gbs_needed_at_this_rate": h2d * e2e_steps / (float(e_ms.item()) * 1e-3) / 1e9,
-               "api": "RanMtgEncDecDataset.host_tensor_batches (pinned uint8 cards+backgrounds in, pinned fp16 x/x2 + int64 labels out; "
-                      "upload + pool ingest of batch i+1 / kernels of batch i / download of batch i-1 overlap on four streams; "
-                      "timed = max(CUDA events, host wall clock) over all steps including pipeline fill and drain)"}
-
-    # ---- the same end-to-end call with the inputs as the JPEG FILES the reference's loaders read ----
-    if e2e is not None and not args.no_e2e_jpeg:
-        import cv2
-
-        q = [cv2.IMWRITE_JPEG_QUALITY, 90]
-        card_files = [cv2.imencode(".jpg", cards.images[k % len(cards.images)][:, :, ::-1], q)[1].tobytes() for k in range(PAIRS)]
-        bg_files = [cv2.imencode(".jpg", bgs[j % len(bgs)][:, :, ::-1], q)[1].tobytes() for j in range(PAIRS)]
-        item = ds.prepare_jpeg_batch(card_files, bg_files)
+        e2e_steps = max(3, min(args.steps, args.e2e_max_steps))  # pipeline fill and drain are inside the timed region
+        card_files, bg_files = encode_pools_as_jpeg(cards, bgs, host_workers)
+        n_rot = 4  # distinct pinned batches rotated through, so consecutive steps upload and decode different files
+        rot = []
+        for r_ in range(n_rot):
+            sel_c = [card_files[(r_ * PAIRS + k) % len(card_files)] for k in range(PAIRS)]
+            sel_b = [bg_files[(r_ * PAIRS + k) % len(bg_files)] for k in range(PAIRS)]
+            lens = [len(f) for f in sel_c + sel_b]
+            off = np.zeros(2 * PAIRS + 1, dtype=np.int64)
+            np.cumsum(lens, out=off[1:])
+            blob = torch.empty(int(off[-1]), dtype=torch.uint8).pin_memory()
+            blob.numpy()[:] = np.frombuffer(b"".join(sel_c + sel_b), dtype=np.uint8)
+            rot.append((blob, off))
+        h2d_files = sum(int(o[-1]) for _, o in rot) / n_rot
 
         def feed_jpeg(k):
-            for _ in range(k):
-                yield item
+            for i in range(k):
+                blob, off = rot[i % n_rot]
+                yield ds.prepare_jpeg_batch_pinned(blob, off, bg_hw=BG_HW)  # inside the timed loop
 
-        for _ in ds.host_tensor_batches(feed_jpeg(3)):
+        def timed(feed_fn, k):
+            barrier()
+            es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_w0 = time.perf_counter()
+            es.record()
+            chk, res = 0.0, None
+            for res in ds.host_tensor_batches(feed_fn(k)):
+                chk += float(res["x_labels"][0, 0])  # the consumer touches every batch on the host
+            ee.record()
+            torch.cuda.synchronize()
+            t_w1 = time.perf_counter()
+            ms = torch.tensor([max(es.elapsed_time(ee), 1e3 * (t_w1 - t_w0))], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item()), res
+
+        for _ in ds.host_tensor_batches(feed_jpeg(4)):  # warm-up: staging buffers, pinned outputs, decoder scratch
             pass
-        barrier()
-        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_w0 = time.perf_counter()
-        es.record()
-        for res in ds.host_tensor_batches(feed_jpeg(e2e_steps)):
-            checksum += float(res["x_labels"][0, 0])
-        ee.record()
-        torch.cuda.synchronize()
-        t_w1 = time.perf_counter()
-        j_ms = torch.tensor([max(es.elapsed_time(ee), 1e3 * (t_w1 - t_w0))], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(j_ms, op=dist.ReduceOp.MAX)
-        e2e["from_jpeg_files"] = {
-            "value": world * n_x * e2e_steps / (float(j_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(item["file_off"][-1]),
-            "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": float(j_ms.item()) / e2e_steps,
-            "api": "RanMtgEncDecDataset.host_tensor_batches fed with prepare_jpeg_batch items: the batch's 512 cards and 512 backgrounds as "
-                   "quality-90 JPEG files in pinned host memory (what the reference's loaders read from disk), decoded on the device "
-                   "(bit-exact with cv2.imread) into the pools; not the e2e number: the reference CPU arm is timed on decoded arrays"}
+        j_ms, res = timed(feed_jpeg, e2e_steps)
+        d2h = sum(v.numel() * v.element_size() for v in res.values())
+        e2e = {"value": world * n_x * e2e_steps / (j_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_files),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": j_ms / e2e_steps,
+               "api": "RanMtgEncDecDataset.host_tensor_batches fed with prepare_jpeg_batch_pinned items (called inside the timed loop): "
+                      "the batch's 512 cards + 512 backgrounds as quality-90 JPEG files in pinned host memory -> device decode "
+                      "(bit-exact with cv2.imread) -> pool ingest -> generation -> pinned fp16 x/x2 + int64 labels; upload+decode of "
+                      "batch i+1 / kernels of batch i / download of batch i-1 overlap on four streams; "
+                      "timed = max(CUDA events, host wall clock) over all steps including pipeline fill and drain"}
+
+        # ---- the same call fed with decoded uint8 arrays (798 MB per batch over PCIe: the link is the bound) ----
+        if not args.no_e2e_raw:
+            hc = torch.from_numpy(cards.images[np.arange(PAIRS) % len(cards.images)]).pin_memory()
+            hb = torch.from_numpy(np.stack([bgs[j % len(bgs)] for j in range(PAIRS)])).pin_memory()
+
+            def feed(k):
+                for _ in range(k):
+                    yield hc, hb
+
+            for _ in ds.host_tensor_batches(feed(3)):
+                pass
+            raw_steps = min(e2e_steps, 30)
+            r_ms, _ = timed(feed, raw_steps)
+            h2d = int(hc.numel() + hb.numel())
+            e2e["from_raw_arrays"] = {
+                "value": world * n_x * raw_steps / (r_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                "steps": raw_steps, "ms_per_step": r_ms / raw_steps, "h2d_gbs_needed_at_this_rate": h2d * raw_steps / (r_ms * 1e-3) / 1e9,
+                "api": "the same call fed with pinned uint8 card/background ARRAYS (decoded images): PCIe-bound, 798 MB per batch"}
+            del hc, hb
+
+        # ---- the same call fed with lists of `bytes` objects (prepare_jpeg_batch: one extra host copy into pinned staging) ----
+        def feed_bytes(k):
+            for i in range(k):
+                yield ds.prepare_jpeg_batch([card_files[(i * PAIRS + q) % len(card_files)] for q in range(PAIRS)],
+                                            [bg_files[(i * PAIRS + q) % len(bg_files)] for q in range(PAIRS)])
+
+        b_steps = min(e2e_steps, 10)
+        b_ms, _ = timed(feed_bytes, b_steps)
+        e2e["from_bytes_objects"] = {"value": world * n_x * b_steps / (b_ms * 1e-3), "unit": UNIT, "steps": b_steps,
+                                     "api": "prepare_jpeg_batch(list of bytes, list of bytes) inside the loop: join + copy into fresh pinned memory"}
 
     # ---- context only: the training-loop call (pool resident, nothing uploaded), batch read back to pinned host ----
     if e2e is not None:
@@ -451,7 +532,7 @@ def run_cuda(args):
         barrier()
         rs, re_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         rs.record()
-        for _ in range(e2e["steps"]):
+        for _ in range(min(e2e["steps"], 30)):
             b = next(it)
             for k2, v in b.items():
                 hosts[k2].copy_(v, non_blocking=True)
@@ -460,26 +541,32 @@ def run_cuda(args):
         r_ms = torch.tensor([rs.elapsed_time(re_)], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(r_ms, op=dist.ReduceOp.MAX)
-        e2e["resident_pool"] = {"value": world * n_x * e2e["steps"] / (float(r_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+        e2e["resident_pool"] = {"value": world * n_x * min(e2e["steps"], 30) / (float(r_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
                                 "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in b.values())),
                                 "api": "next(iter(RanMtgEncDecDataset)) + copy of the batch to pinned host memory (cards and backgrounds stay in HBM; "
                                        "not the e2e number: nothing is uploaded)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, w, n, wall = cpu_generator_throughput(args.cpu_pairs_per_worker)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": w, "kind": "port",
-                        "sample": f"{args.cpu_pairs_per_worker} pairs per worker x {w} worker processes (cv2 threads=1), batch 16, "
-                                  f"64-card/64-bg synthetic pools: {n} x-samples in {wall:.1f} s"}
+        gen = CpuGenerator(args.pool_cards, args.pool_bgs, cards=cards, bgs=bgs,
+                           files=(card_files, bg_files) if card_files is not None else None)
+        n, wall = gen.step(args.cpu_pairs_per_worker, from_files=True)
+        n2, wall2 = gen.step(max(1, args.cpu_pairs_per_worker // 4), from_files=False)
+        gen.close()
+        cpu_baseline = {"value": n / wall, "unit": UNIT, "cores": gen.workers, "kind": "port",
+                        "sample": f"one batch of {args.cpu_pairs_per_worker} pairs per worker x {gen.workers} worker processes (cv2 threads=1), pools of "
+                                  f"{args.pool_cards} cards / {args.pool_bgs} backgrounds as quality-{JPEG_Q} JPEG files in host memory, cv2.imdecode per drawn image "
+                                  f"+ generator: {n} x-samples in {wall:.1f} s",
+                        "from_decoded_arrays": n2 / wall2}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, {"out_dtype": "fp16 NCHW", "setup_s": round(t_setup, 1),
-                                             "virtual": n_virtual, "cropped": n_cropped,
-                                             "failed_samples": int((status != 0).sum())}),
+            "config": workload_config(args),
+            "stats": {"out_dtype": "fp16 NCHW", "setup_s": round(t_setup, 1), "virtual": n_virtual, "cropped": n_cropped,
+                      "failed_samples": int((status != 0).sum()), "sampled_steps": n_keep, **drift},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         if dist is not None:
@@ -752,9 +839,10 @@ def main():
     ap.add_argument("--pool-cards", type=int, default=2048)
     ap.add_argument("--pool-bgs", type=int, default=1024)
     ap.add_argument("--cpu-pairs-per-worker", type=int, default=384)
-    ap.add_argument("--ref-pairs-per-worker", type=int, default=16)
+    ap.add_argument("--ref-pairs-per-worker", type=int, default=128)
+    ap.add_argument("--e2e-max-steps", type=int, default=30)
+    ap.add_argument("--no-e2e-raw", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-e2e-jpeg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload == "dewarp":

@@ -395,6 +395,12 @@ int mtgv_extract_dewarped(mtgv_ctx* ctx, const uint8_t* frame, int frame_h, int 
  * CMYK, 12-bit, chroma subsampled by more than 2). */
 int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw);
 
+/* mtgv_jpeg_info for n files in ONE call: file i = files[file_off[i] .. file_off[i+1]) (host memory, file_off has n+1
+ * entries), hw: host [n][2].  The marker walks run on a few host threads; what a loader does before it sizes the
+ * output of mtgv_decode_jpeg_batch (the reference opens one file at a time: IlsvrcImages._load_image,
+ * encoder_datasets.py:457-474).  The first unsupported or damaged file fails the call, its index is in the message. */
+int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, int32_t* hw);
+
 /* imread_float's cv2.imread(path, IMREAD_COLOR_RGB) (util/image.py:107-114; IlsvrcImages._load_image
  * encoder_datasets.py:457-474) for n baseline JPEG files at once, on the device.
  * files: HOST bytes, file i = files[file_off[i] .. file_off[i+1]) (file_off: host, n+1 entries).

@@ -255,18 +255,44 @@ class Context:
         self._check(rc, "mtgv_jpeg_info")
         return int(hw[0]), int(hw[1])
 
-    def prepare_jpegs(self, files: list[bytes]) -> dict:
-        """Host-side batch of JPEG files for `decode_prepared`: pinned concatenated bytes, offsets and frame sizes."""
-        n = len(files)
-        hw = np.zeros((n, 2), dtype=np.int32)
-        for i, f in enumerate(files):
-            hw[i] = self.jpeg_info(f)
-        sizes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
-        out_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-        file_off = np.concatenate([[0], np.cumsum([len(f) for f in files])]).astype(np.int64)
-        blob = torch.empty(max(int(file_off[-1]), 1), dtype=torch.uint8).pin_memory()
-        blob.numpy()[: int(file_off[-1])] = np.frombuffer(b"".join(files), dtype=np.uint8)
+    def jpeg_info_batch(self, blob, file_off: np.ndarray) -> np.ndarray:
+        """(h, w) of every file of a concatenated host buffer in one C call (threaded marker walks): int32 [n, 2]."""
+        file_off = np.ascontiguousarray(file_off, dtype=np.int64)
+        n = len(file_off) - 1
+        hw = np.zeros((max(n, 0), 2), dtype=np.int32)
+        if n > 0:
+            base = blob.data_ptr() if isinstance(blob, torch.Tensor) else np.frombuffer(blob, dtype=np.uint8).ctypes.data
+            rc = self.lib.mtgv_jpeg_info_batch(self._h, C.c_void_p(base), file_off.ctypes.data_as(C.c_void_p), n,
+                                               hw.ctypes.data_as(C.c_void_p))
+            self._check(rc, "mtgv_jpeg_info_batch")
+        return hw
+
+    def prepare_jpeg_blob(self, blob: torch.Tensor, file_off, hw: np.ndarray | None = None) -> dict:
+        """Zero-copy batch for `decode_prepared`: `blob` is a uint8 CPU tensor (pinned for an asynchronous upload - e.g.
+        the arena a loader `readinto`s its files) that already holds the files back to back, file i =
+        blob[file_off[i]:file_off[i+1]].  `hw` (int32 [n,2]) skips the header pass when the caller knows the frame sizes;
+        mtgv_decode_jpeg_batch checks them against every file either way."""
+        assert blob.dtype == torch.uint8 and not blob.is_cuda and blob.is_contiguous()
+        file_off = np.ascontiguousarray(file_off, dtype=np.int64)
+        n = len(file_off) - 1
+        if hw is None:
+            hw = self.jpeg_info_batch(blob, file_off)
+        hw = np.ascontiguousarray(hw, dtype=np.int32).reshape(n, 2)
+        out_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(hw[:, 0].astype(np.int64) * hw[:, 1] * 3, out=out_off[1:])
         return {"n": n, "blob": blob, "file_off": file_off, "out_off": out_off, "hw": hw}
+
+    def prepare_jpegs(self, files: list[bytes]) -> dict:
+        """Host-side batch of JPEG files for `decode_prepared`: the files are concatenated into pinned memory (one copy,
+        the staging buffer is kept and grown on demand) and their headers parsed in one C call."""
+        n = len(files)
+        file_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(f) for f in files], out=file_off[1:])
+        total = int(file_off[-1])
+        blob = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        if total:
+            blob.numpy()[:total] = np.frombuffer(b"".join(files), dtype=np.uint8)
+        return self.prepare_jpeg_blob(blob, file_off)
 
     def decode_prepared(self, batch: dict, out: torch.Tensor | None = None) -> torch.Tensor:
         """mtgv_decode_jpeg_batch on a prepared batch; returns the flat uint8 device tensor of all images."""

@@ -281,6 +281,13 @@ int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw)
   return jpeg_info(ctx, file, len, hw);
 }
 
+int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, int32_t* hw) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (n == 0) return MTGV_OK;
+  if (!files || !file_off || !hw || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_jpeg_info_batch: bad arguments");
+  return jpeg_info_batch(ctx, files, file_off, n, hw);
+}
+
 int mtgv_jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms3) {
   if (!ctx || !ms3) return MTGV_ERR_INVALID;
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -304,6 +311,7 @@ int mtgv_encode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, i
       quality < 1 || quality > 100 || cap < 1024 || (cap & 3))
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_encode_jpeg_batch: bad arguments");
   if (h > 16384 || w > 16384) return fail(ctx, MTGV_ERR_LIMIT, "mtgv_encode_jpeg_batch: image larger than 16384 pixels per side");
+  if (n > 65535) return fail(ctx, MTGV_ERR_LIMIT, "mtgv_encode_jpeg_batch: more than 65535 images per call (one grid row per image); split the batch");
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   return jpegenc_batch(ctx, images, n, h, w, layout, quality, out, cap, out_len, (cudaStream_t)stream);
 }
@@ -313,6 +321,7 @@ int mtgv_compact_jpeg_files(mtgv_ctx* ctx, const uint8_t* slots, int64_t cap, co
   if (!ctx) return MTGV_ERR_INVALID;
   if (!offsets || n < 0 || (n > 0 && (!slots || !out_len || !compact || cap < 4 || (cap & 3))))
     return fail(ctx, MTGV_ERR_INVALID, "mtgv_compact_jpeg_files: bad arguments");
+  if (n > 65535) return fail(ctx, MTGV_ERR_LIMIT, "mtgv_compact_jpeg_files: more than 65535 files per call (one grid row per file); split the batch");
   MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   return jpegenc_compact(ctx, slots, cap, out_len, n, compact, offsets, (cudaStream_t)stream);
 }

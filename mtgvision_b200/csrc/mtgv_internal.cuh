@@ -148,6 +148,7 @@ int dewarp_u8(mtgv_ctx* ctx, const uint8_t* frame, int fh, int fw, int fc, const
 int jpeg_destroy(mtgv_ctx* ctx);
 int jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms);
 int jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw);
+int jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, int32_t* hw);
 int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
                       const int32_t* hw, cudaStream_t st);
 // mtgv_jpegenc.cu

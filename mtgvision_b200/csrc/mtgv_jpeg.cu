@@ -594,6 +594,41 @@ int jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw) {
   return MTGV_OK;
 }
 
+// marker walk of n files on a few host threads; fn(i, im, tb) receives every parsed file (called concurrently for
+// different i).  Returns the index of the first failing file (message in *err) or -1.
+template <class Fn>
+static int jpeg_parse_many(const uint8_t* files, const int64_t* file_off, int n, std::string* err, Fn fn) {
+  unsigned hc = std::thread::hardware_concurrency();
+  const int nt = n < 64 ? 1 : (int)(hc < 2 ? 1 : (hc > 8 ? 8 : hc));
+  std::vector<std::string> terr(nt);
+  std::vector<int> tbad(nt, -1);
+  auto run = [&](int t) {
+    const int i0 = (int)((int64_t)n * t / nt), i1 = (int)((int64_t)n * (t + 1) / nt);
+    JpegImg im;
+    JpegTables tb;
+    for (int i = i0; i < i1; i++) {
+      const int64_t len = file_off[i + 1] - file_off[i];
+      if (len < 0) { terr[t] = "bad offsets"; tbad[t] = i; return; }
+      if (jpeg_parse(files + file_off[i], len, i, &im, &tb, nullptr, &terr[t]) != 0) { tbad[t] = i; return; }
+      fn(i, im, tb);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(run, t);
+  run(0);
+  for (auto& x : th) x.join();
+  for (int t = 0; t < nt; t++)
+    if (tbad[t] >= 0) { *err = "file " + std::to_string(tbad[t]) + ": " + terr[t]; return tbad[t]; }
+  return -1;
+}
+
+int jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, int32_t* hw) {
+  std::string err;
+  if (jpeg_parse_many(files, file_off, n, &err, [&](int i, const JpegImg& im, const JpegTables&) { hw[2 * i] = im.h; hw[2 * i + 1] = im.w; }) >= 0)
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_jpeg_info_batch: " + err);
+  return MTGV_OK;
+}
+
 int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
                       const int32_t* hw, cudaStream_t stream) {
   if (!ctx->jpeg) {
@@ -606,24 +641,9 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   std::vector<JpegImg> imgs(n);
   std::vector<JpegTables> tbs(n);
   {  // marker walk + table build, a few host threads over contiguous file ranges
-    unsigned hc = std::thread::hardware_concurrency();
-    const int nt = n < 64 ? 1 : (int)(hc < 2 ? 1 : (hc > 8 ? 8 : hc));
-    std::vector<std::string> terr(nt);
-    std::vector<int> tbad(nt, -1);
-    auto run = [&](int t) {
-      const int i0 = (int)((int64_t)n * t / nt), i1 = (int)((int64_t)n * (t + 1) / nt);
-      for (int i = i0; i < i1; i++) {
-        const int64_t len = file_off[i + 1] - file_off[i];
-        if (len < 0) { terr[t] = "bad offsets"; tbad[t] = i; return; }
-        if (jpeg_parse(files + file_off[i], len, i, &imgs[i], &tbs[i], nullptr, &terr[t]) != 0) { tbad[t] = i; return; }
-      }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(run, t);
-    run(0);
-    for (auto& x : th) x.join();
-    for (int t = 0; t < nt; t++)
-      if (tbad[t] >= 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: file " + std::to_string(tbad[t]) + ": " + terr[t]);
+    std::string err;
+    if (jpeg_parse_many(files, file_off, n, &err, [&](int i, const JpegImg& im, const JpegTables& tb) { imgs[i] = im; tbs[i] = tb; }) >= 0)
+      return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: " + err);
   }
   int64_t nblk_total = 0, plane_total = 0;
   int max_blk = 0, max_h = 0;

@@ -85,6 +85,7 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
     if (pos + 4 > len) return jpeg_fail(err, "truncated before the scan");
     if (d[pos] != 0xFF) return jpeg_fail(err, "marker expected");
     while (pos + 1 < len && d[pos + 1] == 0xFF) pos++;
+    if (pos + 1 >= len) return jpeg_fail(err, "truncated before the scan");  // header ends in 0xFF fill bytes
     const int m = d[pos + 1];
     pos += 2;
     if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;

@@ -390,11 +390,13 @@ __global__ void __launch_bounds__(256) k_jpegenc_compact(const uint8_t* __restri
 
 int jpegenc_compact(mtgv_ctx* ctx, const uint8_t* slots, int64_t cap, const int32_t* out_len, int n, uint8_t* compact, int64_t* offsets,
                     cudaStream_t stream) {
-  k_jpegenc_offsets<<<1, kHuffThreads, 0, stream>>>(out_len, n, offsets);
+  k_jpegenc_offsets<<<1, kHuffThreads, 0, stream>>>(out_len, n, offsets);  // n == 0: writes offsets[0] = 0 and nothing else
   MTGV_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  if (n == 0) return MTGV_OK;
   k_jpegenc_compact<<<dim3(32, n), 256, 0, stream>>>(slots, cap, out_len, offsets, compact);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
-  ctx->launches += 2;
+  ctx->launches++;
   return MTGV_OK;
 }
 

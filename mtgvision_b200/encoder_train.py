@@ -26,6 +26,7 @@ from torch.utils.data import IterableDataset
 
 from . import abi, synth
 from .context import Context
+from .shards import ShardCursor
 from .encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
 
 _OUT = {"float16": abi.OUT_F16, "fp16": abi.OUT_F16, "uint8": abi.OUT_U8, "u8": abi.OUT_U8,
@@ -70,7 +71,7 @@ class RanMtgEncDecDataset(IterableDataset):
         self.out_dtype = _OUT[out_dtype]
         self.rank, self.world_size = int(rank), int(world_size)
         self.seed = random.getrandbits(63) if seed is None else int(seed)
-        self._batch_counter = 0
+        self._shards = ShardCursor(self.rank, self.world_size)
         self.ctx = Context(device)
         self.ctx.set_encoder_config(x_size_hw=self.x_size_hw, y_size_hw=self.y_size_hw,
                                     target_is_input_prob=target_is_input_prob, similar_neg_prob=similar_neg_prob,
@@ -138,7 +139,9 @@ class RanMtgEncDecDataset(IterableDataset):
         speed) of the pools' image sizes.  They are copied into pool slots [0, n), sample i
         uses card i and background i (x2: a random background of the batch, as in the
         reference), and the finished batch is copied back into pinned host tensors.
-        Labels are those of pool slots [0, n)."""
+        Labels are those of pool slots [0, n).  Hard-negative swaps are OFF on this path (similar_neg_prob is
+        forced to 0): the same-name groups describe the resident pool, not the caller's images, so a swap would
+        read an unrelated (and possibly concurrently re-uploaded) slot."""
         n = card_images.shape[0]
         assert bg_images.shape[0] == n
         ctx = self.ctx
@@ -153,7 +156,7 @@ class RanMtgEncDecDataset(IterableDataset):
             self._stage_bgs.copy_(bg_images, non_blocking=True)
             ctx.update_card_images(self._stage_cards, 0)
             ctx.update_bg_images(self._stage_bgs, 0)
-            batch = self._generate(n, cards=self._stage_idx, t_prob=None, n_prob=None, bgs=self._stage_idx)
+            batch = self._generate(n, cards=self._stage_idx, t_prob=None, n_prob=0.0, bgs=self._stage_idx)
             out = {}
             for k, v in batch.items():
                 h = self._host_out.get(k)
@@ -167,10 +170,29 @@ class RanMtgEncDecDataset(IterableDataset):
 
     def prepare_jpeg_batch(self, card_files: list[bytes], bg_files: list[bytes]) -> dict:
         """One batch's inputs as JPEG files (n cards of the pool's card size, n backgrounds of one size) for
-        `host_tensor_batches`: parsed once, bytes concatenated in pinned memory."""
+        `host_tensor_batches`: bytes concatenated in pinned memory, headers parsed in one C call."""
         n = len(card_files)
         assert len(bg_files) == n and n > 0
-        b = self.ctx.prepare_jpegs(list(card_files) + list(bg_files))
+        return self._check_jpeg_item(self.ctx.prepare_jpegs(list(card_files) + list(bg_files)), n)
+
+    def prepare_jpeg_batch_pinned(self, blob: torch.Tensor, file_off, bg_hw: Tuple[int, int] | None = None) -> dict:
+        """`prepare_jpeg_batch` without the copy: `blob` is a (pinned) uint8 CPU tensor that already holds the 2n files
+        back to back - n cards then n backgrounds, file i = blob[file_off[i]:file_off[i+1]] - e.g. the arena a loader
+        `readinto`s.  Cards must have the pool's card size; `bg_hw` is the backgrounds' common frame size (parsed
+        from the first background file when omitted).  The device decoder checks every file's header against these sizes,
+        so no per-file host pass is needed here."""
+        file_off = np.ascontiguousarray(file_off, dtype=np.int64)
+        n2 = len(file_off) - 1
+        assert n2 > 0 and n2 % 2 == 0
+        n = n2 // 2
+        if bg_hw is None:
+            bg_hw = tuple(int(v) for v in self.ctx.jpeg_info_batch(blob, file_off[n:n + 2])[0])
+        hw = np.empty((n2, 2), dtype=np.int32)
+        hw[:n] = self.ctx.card_hw
+        hw[n:] = bg_hw
+        return self._check_jpeg_item(self.ctx.prepare_jpeg_blob(blob, file_off, hw=hw), n)
+
+    def _check_jpeg_item(self, b: dict, n: int) -> dict:
         ch, cw = (int(v) for v in b["hw"][0])
         bh, bw = (int(v) for v in b["hw"][n])
         if not (b["hw"][:n] == (ch, cw)).all() or not (b["hw"][n:] == (bh, bw)).all() or (ch, cw) != tuple(self.ctx.card_hw):
@@ -191,7 +213,8 @@ class RanMtgEncDecDataset(IterableDataset):
         layout), the kernels of batch i and the download of batch i-1 (what the reference's DataLoader workers do with processes,
         encoder_train.py:517-523).  Batches alternate between pool slots [0, n) and [n, 2n), so
         both pools need at least 2n entries.  A yielded dict is valid until the generator is
-        advanced again (its buffers are the double-buffered download targets)."""
+        advanced again (its buffers are the double-buffered download targets).  Hard-negative swaps are off
+        here for the same reason as in `host_tensor_batch`."""
         ctx = self.ctx
         dev = ctx.device
         with torch.cuda.device(dev):
@@ -247,7 +270,7 @@ class RanMtgEncDecDataset(IterableDataset):
                 s_k.wait_event(sl["in_done"])
                 s_k.wait_event(sl["out_done"])  # the previous download from this slot's device batch is finished
                 with torch.cuda.stream(s_k):
-                    batch = self._generate(n, cards=sl["idx"], t_prob=None, n_prob=None, bgs=sl["idx"])
+                    batch = self._generate(n, cards=sl["idx"], t_prob=None, n_prob=0.0, bgs=sl["idx"])
                     sl["k_done"].record(s_k)
                 s_out.wait_event(sl["k_done"])
                 with torch.cuda.stream(s_out):
@@ -275,10 +298,9 @@ class RanMtgEncDecDataset(IterableDataset):
 
     # ------------------------------------------------------------------ internals
     def _next_first_index(self, n: int) -> int:
-        """Disjoint global sample indices per (rank, batch): contiguous blocks of n."""
-        b = self._batch_counter
-        self._batch_counter += 1
-        return (b * self.world_size + self.rank) * n
+        """Disjoint global sample indices per (rank, call): a running cursor, so a changing n (set_batch_size,
+        image_batch_by_ids) never revisits an index (mtgvision_b200/shards.py)."""
+        return self._shards.next_first(n)
 
     def _generate(self, n: int, cards, t_prob, n_prob, bgs=None) -> dict:
         ctx = self.ctx

@@ -25,6 +25,7 @@ import torch
 
 from . import abi, synth
 from .context import Context
+from .shards import ShardCursor
 from .encoder_datasets import CocoValImages, IlsvrcImages, SyntheticBgFgMtgImages
 
 _OUT = {"uint8": abi.OUT_U8, "u8": abi.OUT_U8, "float16": abi.OUT_F16, "fp16": abi.OUT_F16, "float32": abi.OUT_F32,
@@ -78,7 +79,7 @@ class Gen:
         self.kind = kind
         self.seed = random.getrandbits(63) if seed is None else int(seed)
         self.rank, self.world_size = int(rank), int(world_size)
-        self._counter = 0
+        self._shards = ShardCursor(self.rank, self.world_size)
         # both background datasets share one resident pool (the reference draws the dataset with
         # ilsvrc_vs_coco_sample_weights and then an image uniformly, od_datasets.py:662-672)
         sources = [self.bg_ds] + ([self.bg2_ds] if self.bg2_ds is not None else [])
@@ -108,8 +109,7 @@ class Gen:
     def random_batch(self, n: int, out_dtype: str = "uint8") -> dict:
         ctx = self.ctx
         with torch.cuda.device(ctx.device):
-            first = (self._counter * self.world_size + self.rank) * n
-            self._counter += 1
+            first = self._shards.next_first(n)  # running cursor: tail batches and random() never reuse an index
             tape = ctx.sample_det_tape(self.seed, first, n)
             params, accepted, keypoints, labels, counts = ctx.det_place(tape)
             image = ctx.det_batch(params, _OUT[out_dtype])
