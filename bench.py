@@ -315,6 +315,21 @@ def run_cuda(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ---- host-side setup first (untimed): everything that forks worker processes runs while this process is still
+    # single-threaded and holds no CUDA context / NCCL communicator ----
+    host_workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    t_setup = time.perf_counter()
+    cards = synth.make_card_pool(args.pool_cards, workers=host_workers)
+    bgs = synth.make_bg_pool(args.pool_bgs, workers=host_workers)
+    card_files = bg_files = None
+    if not args.no_e2e or not args.no_cpu_baseline:
+        card_files, bg_files = encode_pools_as_jpeg(cards, bgs, host_workers)
+    cpu_gen = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the CPU baseline's worker processes are forked NOW and idle until the end of the run
+        cpu_gen = CpuGenerator(args.pool_cards, args.pool_bgs, cards=cards, bgs=bgs, files=(card_files, bg_files))
+
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -329,10 +344,6 @@ def run_cuda(args):
     dev = torch.device("cuda", local_rank)
 
     # ---- resident pools (setup, untimed) ----
-    host_workers = max(1, (os.cpu_count() or 1) // max(1, world))
-    t_setup = time.perf_counter()
-    cards = synth.make_card_pool(args.pool_cards, workers=host_workers)
-    bgs = synth.make_bg_pool(args.pool_bgs, workers=host_workers)
     ds = RanMtgEncDecDataset(PAIRS, paired=True, targets=False, x_size_hw=X_HW, y_size_hw=X_HW, half_upsidedown=False,
                              target_is_input_prob=0.05, similar_neg_prob=0.2,
                              mtg=SyntheticBgFgMtgImages(pool=cards), ilsvrc=IlsvrcImages(images=bgs),
@@ -440,10 +451,8 @@ def run_cuda(args):
     # util/image.py:107-114), in pinned host memory; every step parses / validates its batch (prepare_jpeg_batch_pinned),
     # uploads the compressed bytes, decodes on the device, ingests into the pools, generates, and downloads x, x2, labels.
     e2e = None
-    card_files = bg_files = None
     if not args.no_e2e:
         e2e_steps = max(3, min(args.steps, args.e2e_max_steps))  # pipeline fill and drain are inside the timed region
-        card_files, bg_files = encode_pools_as_jpeg(cards, bgs, host_workers)
         n_rot = 4  # distinct pinned batches rotated through, so consecutive steps upload and decode different files
         rot = []
         for r_ in range(n_rot):
@@ -547,9 +556,8 @@ def run_cuda(args):
                                        "not the e2e number: nothing is uploaded)"}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        gen = CpuGenerator(args.pool_cards, args.pool_bgs, cards=cards, bgs=bgs,
-                           files=(card_files, bg_files) if card_files is not None else None)
+    if cpu_gen is not None:
+        gen = cpu_gen
         n, wall = gen.step(args.cpu_pairs_per_worker, from_files=True)
         n2, wall2 = gen.step(max(1, args.cpu_pairs_per_worker // 4), from_files=False)
         gen.close()

@@ -346,6 +346,10 @@ typedef struct {
   int32_t max_attempts;                   /* :633 */
   int32_t kind;                           /* 0 obb, 1 seg  (:638) */
   int32_t photometrics;                   /* 0 disables the albumentations stages (parity tests) */
+  int32_t size_sample_mode;               /* card_size_sample_mode :631, :327-332: 0 log_uniform, 1 uniform */
+  int32_t n_bgs_first;                    /* the background pool = bg_ds (slots [0, n_bgs_first)) followed by bg2_ds; 0 = one dataset */
+  double bg_first_prob;                   /* ilsvrc_vs_coco_sample_weights normalised (:656-672): P(dataset = bg_ds); the image is then
+                                             drawn uniformly inside the dataset.  Ignored when n_bgs_first is 0 or the whole pool. */
 } mtgv_det_config;
 
 int mtgv_set_det_config(mtgv_ctx* ctx, const mtgv_det_config* cfg_host);
@@ -414,6 +418,16 @@ int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
  * staged before the call returns). */
 int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out,
                            const int64_t* out_off, const int32_t* hw, void* stream);
+
+/* The loader step of one batch in one call: what `_random_image_batch` does with `ran_card` -> dl_and_open_im_resized and
+ * `IlsvrcImages.ran` -> imread_float (encoder_train.py:149-156, encoder_datasets.py:470-474, 634), for files instead of
+ * arrays.  Files [0, n_cards) are decoded STRAIGHT INTO card pool slots [first_card, first_card + n_cards) (planar layout),
+ * files [n_cards, n_cards + n_bgs) into background slots [first_bg, ...) (RGBX layout) - mtgv_decode_jpeg_batch followed
+ * by mtgv_update_card_images / mtgv_update_bg_images without the intermediate HWC image.  Every file's frame size must
+ * equal its slot's image size (the pools keep their geometry), else MTGV_ERR_INVALID.  Same pixel values as
+ * mtgv_decode_jpeg_batch (bit-exact with cv2.imdecode); `files` lifetime as there.  Work is queued on `stream`. */
+int mtgv_decode_jpeg_to_pools(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n_cards, int first_card,
+                              int n_bgs, int first_bg, void* stream);
 
 /* Device time of the three kernels (entropy decode, inverse DCT, upsample + colour) of the last
  * mtgv_decode_jpeg_batch call, measured with CUDA events on its stream; waits for that batch (bench bookkeeping). */

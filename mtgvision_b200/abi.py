@@ -106,7 +106,8 @@ class DetConfig(C.Structure):
     _fields_ = [("size_h", C.c_int32), ("size_w", C.c_int32), ("num_cards_min", C.c_int32), ("num_cards_max", C.c_int32),
                 ("min_visible", C.c_double), ("min_visible_edges", C.c_double), ("jitter_ratio", C.c_double),
                 ("min_area_ratio", C.c_double), ("max_area_ratio", C.c_double), ("ratio_bg", C.c_double),
-                ("no_contains", C.c_int32), ("max_attempts", C.c_int32), ("kind", C.c_int32), ("photometrics", C.c_int32)]
+                ("no_contains", C.c_int32), ("max_attempts", C.c_int32), ("kind", C.c_int32), ("photometrics", C.c_int32),
+                ("size_sample_mode", C.c_int32), ("n_bgs_first", C.c_int32), ("bg_first_prob", C.c_double)]
 
 
 DET_TAPE_DTYPE = np.dtype(DetTape)
@@ -168,6 +169,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "mtgv_jpeg_encode_last_kernel_ms": (i32, [vp, vp]),
         "mtgv_compact_jpeg_files": (i32, [vp, vp, i64, vp, i32, vp, vp, vp]),
         "mtgv_decode_jpeg_batch": (i32, [vp, vp, vp, i32, vp, vp, vp, vp]),
+        "mtgv_decode_jpeg_to_pools": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
         "mtgv_launch_count": (i64, [vp]),
     }
     for name, (res, args) in protos.items():

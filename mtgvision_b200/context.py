@@ -175,13 +175,14 @@ class Context:
     def set_det_config(self, *, bg_size_hw=640, num_cards_min=1, num_cards_max=10, card_min_visible_ratio=0.5,
                        card_min_visible_ratio_edges=1.0, card_jitter_ratio=0.3, card_min_area_ratio=0.02,
                        card_max_area_ratio=0.9, card_no_contains=True, card_max_place_attempts=10, ratio_bg=None,
-                       kind="obb", photometrics=True):
+                       kind="obb", photometrics=True, card_size_sample_mode="log_uniform", n_bgs_first=0, bg_first_prob=1.0):
         hw = (bg_size_hw, bg_size_hw) if isinstance(bg_size_hw, int) else tuple(bg_size_hw)
         cfg = abi.DetConfig(int(hw[0]), int(hw[1]), int(num_cards_min), int(num_cards_max), float(card_min_visible_ratio),
                             -1.0 if card_min_visible_ratio_edges is None else float(card_min_visible_ratio_edges),
                             float(card_jitter_ratio), float(card_min_area_ratio), float(card_max_area_ratio),
                             float(ratio_bg or 0.0), int(card_no_contains), int(card_max_place_attempts),
-                            {"obb": 0, "seg": 1}[kind], int(photometrics))
+                            {"obb": 0, "seg": 1}[kind], int(photometrics),
+                            {"log_uniform": 0, "uniform": 1}[card_size_sample_mode], int(n_bgs_first), float(bg_first_prob))
         self._check(self.lib.mtgv_set_det_config(self._h, C.byref(cfg)), "mtgv_set_det_config")
         self.det_cfg = cfg
 
@@ -239,13 +240,16 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ image decode into the pools
+    MAX_BG_AREA_SCALE = 24.0  # kBgMaxAreaScale (mtgv_geom.cuh): largest INTER_AREA reduction of the background chain
+
     def oversized_backgrounds(self, x_size_hw) -> np.ndarray:
-        """Pool indices of backgrounds so large that some rotations need an INTER_AREA reduction beyond the kernels' limit
-        (factor 6: DESIGN.md, limits): `rotate_bounded` grows the canvas up to the image diagonal and `crop_to_size` then
-        shrinks it by min(canvas_h / out_h, canvas_w / out_w).  Samples that hit the limit are flagged in params.status."""
+        """Pool indices of backgrounds so large that some rotation needs an INTER_AREA reduction beyond the kernels' limit
+        (factor 24): `rotate_bounded` grows the canvas up to the image diagonal (util/image.py:380-398) and `crop_to_size` then
+        shrinks it by min(canvas_h / out_h, canvas_w / out_w) (:349-377).  At 192x128 that is a diagonal above ~4600 px.
+        The dataset classes REFUSE such pools when they are built, so no sample can fail for its size at run time."""
         hw = np.asarray(getattr(self, "bg_hw", np.zeros((0, 2))), dtype=np.float64).reshape(-1, 2)
         diag = np.hypot(hw[:, 0], hw[:, 1])
-        return np.nonzero(np.minimum(diag / x_size_hw[0], diag / x_size_hw[1]) > 6.0)[0]
+        return np.nonzero(np.minimum(diag / x_size_hw[0], diag / x_size_hw[1]) > self.MAX_BG_AREA_SCALE)[0]
 
     def jpeg_info(self, data: bytes) -> tuple[int, int]:
         """(h, w) of a baseline JPEG file; raises MtgvError for files the device decoder does not support."""
@@ -283,15 +287,21 @@ class Context:
         return {"n": n, "blob": blob, "file_off": file_off, "out_off": out_off, "hw": hw}
 
     def prepare_jpegs(self, files: list[bytes]) -> dict:
-        """Host-side batch of JPEG files for `decode_prepared`: the files are concatenated into pinned memory (one copy,
-        the staging buffer is kept and grown on demand) and their headers parsed in one C call."""
+        """Host-side batch of JPEG files for `decode_prepared`: the files are copied back to back into one of three rotating
+        pinned staging buffers the context keeps (grown on demand; three, so that a buffer is not rewritten while the two
+        batches a streaming pipeline has in flight still upload from theirs) and their headers parsed in one C call."""
         n = len(files)
         file_off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum([len(f) for f in files], out=file_off[1:])
         total = int(file_off[-1])
-        blob = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
-        if total:
-            blob.numpy()[:total] = np.frombuffer(b"".join(files), dtype=np.uint8)
+        ring = self.__dict__.setdefault("_jpeg_stage", [None, None, None])
+        k = self.__dict__["_jpeg_stage_next"] = (self.__dict__.get("_jpeg_stage_next", -1) + 1) % 3
+        if ring[k] is None or ring[k].numel() < max(total, 1):
+            ring[k] = torch.empty(max(total + total // 8, 1 << 16), dtype=torch.uint8).pin_memory()
+        blob = ring[k][: max(total, 1)]
+        dst = blob.numpy()
+        for i, f in enumerate(files):
+            dst[file_off[i]: file_off[i + 1]] = np.frombuffer(f, dtype=np.uint8)
         return self.prepare_jpeg_blob(blob, file_off)
 
     def decode_prepared(self, batch: dict, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -308,6 +318,15 @@ class Context:
         # waiting for the stream) instead of letting the caller's dict be the only reference
         self._jpeg_inflight = batch
         return out
+
+    def decode_into_pools(self, batch: dict, n_cards: int, first_card: int, n_bgs: int, first_bg: int) -> None:
+        """mtgv_decode_jpeg_to_pools: files [0, n_cards) of a prepared batch into card slots [first_card, ...), the next n_bgs
+        files into background slots [first_bg, ...), decoded straight into the pools' own layouts (no HWC intermediate)."""
+        assert n_cards + n_bgs == batch["n"]
+        rc = self.lib.mtgv_decode_jpeg_to_pools(self._h, C.c_void_p(batch["blob"].data_ptr()), batch["file_off"].ctypes.data_as(C.c_void_p),
+                                                int(n_cards), int(first_card), int(n_bgs), int(first_bg), self._stream())
+        self._check(rc, "mtgv_decode_jpeg_to_pools")
+        self._jpeg_inflight = batch  # the pinned bytes are read asynchronously: keep them alive until the next call
 
     def jpeg_last_kernel_ms(self) -> tuple[float, float, float]:
         ms = (C.c_float * 3)()

@@ -303,6 +303,34 @@ int mtgv_decode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* f
   return jpeg_decode_batch(ctx, files, file_off, n, out, out_off, hw, (cudaStream_t)stream);
 }
 
+int mtgv_decode_jpeg_to_pools(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n_cards, int first_card, int n_bgs,
+                              int first_bg, void* stream) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  const int n = n_cards + n_bgs;
+  if (n_cards < 0 || n_bgs < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_to_pools: bad arguments");
+  if (n == 0) return MTGV_OK;
+  if (!files || !file_off) return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_to_pools: bad arguments");
+  if (n > 65535) return fail(ctx, MTGV_ERR_LIMIT, "mtgv_decode_jpeg_to_pools: more than 65535 files per call (one grid row per file); split the batch");
+  if (n_cards && (!ctx->n_cards || first_card < 0 || first_card + n_cards > ctx->n_cards))
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_to_pools: card range outside the pool (mtgv_set_card_pool)");
+  if (n_bgs && (!ctx->n_bgs || first_bg < 0 || first_bg + n_bgs > ctx->n_bgs))
+    return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_to_pools: background range outside the pool (mtgv_set_bg_pool)");
+  MTGV_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  // destinations as absolute device addresses (two pools, two allocations): out = null + offset
+  std::vector<JpegDst> dst((size_t)n);
+  for (int i = 0; i < n_cards; i++) {
+    const uint8_t* p = ctx->card_planes + (size_t)(first_card + i) * 3 * ctx->card_h * ctx->card_pitch;
+    dst[i] = JpegDst{(int64_t)(uintptr_t)p, ctx->card_h, ctx->card_w, 1, ctx->card_pitch};
+  }
+  for (int j = 0; j < n_bgs; j++) {
+    const int slot = first_bg + j, h = ctx->bg_hw_host[2 * slot], w = ctx->bg_hw_host[2 * slot + 1];
+    const uint8_t* p = ctx->bg_planes + ctx->bg_off_host[slot];
+    dst[n_cards + j] = JpegDst{(int64_t)(uintptr_t)p, h, w, 2, (w + 3) & ~3};
+  }
+  if (n_cards) ctx->card_epoch++;
+  return jpeg_decode_batch_ex(ctx, files, file_off, n, (uint8_t*)nullptr, dst.data(), (cudaStream_t)stream);
+}
+
 int mtgv_encode_jpeg_batch(mtgv_ctx* ctx, const uint8_t* images, int n, int h, int w, int layout, int quality, uint8_t* out,
                            int64_t cap, int32_t* out_len, void* stream) {
   if (!ctx) return MTGV_ERR_INVALID;

@@ -167,9 +167,13 @@ struct RTap {
   bool in;
 };
 
-template <bool LINEAR, bool TABLES>
+// MODE 1 (LINEAR): integer taps, affine chain applied once.  MODE 2: the frequent non-affine chain - first step clipped, second
+// step (identity when absent) not clipped - with its constants in registers (la/lb = step 0, qa/qb = step 1): per tap and
+// channel PRMT, FADD, FFMA.SAT, FFMA, FFMA.  MODE 0: any chain, flags read from shared memory.
+template <int MODE, bool TABLES>
 __device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0, int ry0, int rtw, int rth, unsigned magic,
-                                             const float* la, const float* lb, int tid) {
+                                             const float* la, const float* lb, const float* qa, const float* qb, int tid) {
+  constexpr bool LINEAR = MODE == 1;
   const int npx = rtw * rth;
   const int rs = b.fv ? -b.pitchw : b.pitchw, cs = b.fh ? -1 : 1;
   const unsigned in_w = (unsigned)(b.w - 1), in_h = (unsigned)(b.h - 1);
@@ -213,10 +217,19 @@ __device__ __forceinline__ void stage_rotate(BgSmem& S, const BgSrc& b, int rx0,
         float o[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          float a = pre_chain(S, byte_f(t.t0, c), c) * w[0];
-          a = __fmaf_rn(pre_chain(S, byte_f(t.t1, c), c), w[1], a);
-          a = __fmaf_rn(pre_chain(S, byte_f(t.t2, c), c), w[2], a);
-          a = __fmaf_rn(pre_chain(S, byte_f(t.t3, c), c), w[3], a);
+          float a;
+          if (MODE == 2) {
+            auto ch = [&](uint32_t word) { return __fmaf_rn(sat01(__fmaf_rn(byte_f(word, c), la[c], lb[c])), qa[c], qb[c]); };
+            a = ch(t.t0) * w[0];
+            a = __fmaf_rn(ch(t.t1), w[1], a);
+            a = __fmaf_rn(ch(t.t2), w[2], a);
+            a = __fmaf_rn(ch(t.t3), w[3], a);
+          } else {
+            a = pre_chain(S, byte_f(t.t0, c), c) * w[0];
+            a = __fmaf_rn(pre_chain(S, byte_f(t.t1, c), c), w[1], a);
+            a = __fmaf_rn(pre_chain(S, byte_f(t.t2, c), c), w[2], a);
+            a = __fmaf_rn(pre_chain(S, byte_f(t.t3, c), c), w[3], a);
+          }
           o[c] = a;
         }
         v = make_float4(o[0], o[1], o[2], 0.f);
@@ -275,6 +288,32 @@ __device__ __forceinline__ void stage_area(const BgSmem& S, int ty0, int ty1, in
     const int o = (ty0 + r) * OW + tx0 + cidx;
 #pragma unroll
     for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = sat01(sum[c]);  // img_clip (util/image.py:334)
+  }
+}
+
+// any tap count (reductions beyond x6: large photographs): weights selected per tap instead of held in registers
+__device__ __noinline__ void stage_area_any(const BgSmem& S, int ty0, int ty1, int tx0, int tx1, int by0, int wy0, int wx0, int WW,
+                                            float* __restrict__ outp, int OH, int OW, int tid) {
+  const int tw = tx1 - tx0, npx = (ty1 - ty0) * tw;
+  for (int k = tid; k < npx; k += kBgThreads) {
+    const int r = k / tw, cidx = k - r * tw;
+    const AreaEnt ey = S.ay[ty0 - by0 + r], ex = S.ax[tx0 + cidx];
+    const int ny = ey.n & 255, nx = ex.n & 255;
+    float sum[3] = {0.f, 0.f, 0.f};
+    int q = (ey.start - wy0) * WW + (ex.start - wx0);
+    for (int j = 0; j < ny; j++, q += WW) {
+      float h[3] = {0.f, 0.f, 0.f};
+      for (int i = 0; i < nx; i++) {
+        const float wxi = area_w(ex, i);
+        h[0] = __fmaf_rn(S.wtile[0][q + i], wxi, h[0]);
+        h[1] = __fmaf_rn(S.wtile[1][q + i], wxi, h[1]);
+        h[2] = __fmaf_rn(S.wtile[2][q + i], wxi, h[2]);
+      }
+      const float wyj = area_w(ey, j);
+      for (int c = 0; c < 3; c++) sum[c] = __fmaf_rn(wyj, h[c], sum[c]);
+    }
+    const int o = (ty0 + r) * OW + tx0 + cidx;
+    for (int c = 0; c < 3; c++) outp[(size_t)c * OH * OW + o] = sat01(sum[c]);
   }
 }
 
@@ -424,10 +463,20 @@ __global__ void __launch_bounds__(kBgThreads, kBgCtas) k_background(const mtgv_e
     float* outp = bg_out + (size_t)s * 3 * OH * OW;
     __syncthreads();
     const bool pre_linear = S.pre_linear != 0, post_linear = S.post_linear != 0;
+    // the frequent non-affine chain: step 0 clipped, step 1 (identity when absent) not clipped
+    const bool pre_sat_nosat = !pre_linear && S.pre_clip[0] != 0 && (S.pre_steps < 2 || S.pre_clip[1] == 0);
     const int max_nx = S.max_nx;
-    float la[3], lb[3], pa[3], pb[3];
+    float la[3], lb[3], pa[3], pb[3], qa[3], qb[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) { la[c] = S.lin_a[c]; lb[c] = S.lin_b[c]; pa[c] = S.plin_a[c]; pb[c] = S.plin_b[c]; }
+    for (int c = 0; c < 3; c++) {
+      pa[c] = S.plin_a[c]; pb[c] = S.plin_b[c];
+      if (pre_sat_nosat) {
+        la[c] = S.pre_a[0][c]; lb[c] = S.pre_b[0][c];
+        qa[c] = S.pre_steps > 1 ? S.pre_a[1][c] : 1.f; qb[c] = S.pre_steps > 1 ? S.pre_b[1][c] : 0.f;
+      } else {
+        la[c] = S.lin_a[c]; lb[c] = S.lin_b[c]; qa[c] = 1.f; qb[c] = 0.f;
+      }
+    }
 
     // Tiles of the band are software-pipelined: the set-up of tile t+1 (bounding box, coordinate segments) shares
     // a barrier interval with the INTER_AREA reduction of tile t, which reads none of what the set-up writes.
@@ -488,9 +537,10 @@ __global__ void __launch_bounds__(kBgThreads, kBgCtas) k_background(const mtgv_e
         const int rx0 = S.tile[0], ry0 = S.tile[1], rtw = S.tile[2], rth = S.tile[3];
         const unsigned mg_r = (unsigned)S.tile[4], mg_w = (unsigned)S.tile[5], mg_a = (unsigned)S.tile[6];
         if (MTGV_BG_SKIP & 1) {}
-        else if (!tables) stage_rotate<false, false>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
-        else if (pre_linear) stage_rotate<true, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
-        else stage_rotate<false, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, tid);
+        else if (!tables) stage_rotate<0, false>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, qa, qb, tid);
+        else if (pre_linear) stage_rotate<1, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, qa, qb, tid);
+        else if (pre_sat_nosat) stage_rotate<2, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, qa, qb, tid);
+        else stage_rotate<0, true>(S, b, rx0, ry0, rtw, rth, mg_r, la, lb, qa, qb, tid);
         __syncthreads();
         if (staged && !(MTGV_BG_SKIP & 2)) {
           // ---- stage W: warp_inv output over the window + elementwise ops scheduled after the geometric group ----
@@ -558,7 +608,8 @@ __global__ void __launch_bounds__(kBgThreads, kBgCtas) k_background(const mtgv_e
         else if (!staged) stage_area_direct(S, b, ty0, ty1, tx0, tx1, by0, bw0, outp, OH, OW, tid);
         else if (max_nx <= 4) stage_area<4>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
         else if (max_nx <= 6) stage_area<6>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
-        else stage_area<kAreaMaxTaps>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
+        else if (max_nx <= kAreaMaxTaps) stage_area<kAreaMaxTaps>(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, mg_a, outp, OH, OW, tid);
+        else stage_area_any(S, ty0, ty1, tx0, tx1, by0, wy0, wx0, WW, outp, OH, OW, tid);
       }
       if (t + 1 < n_tiles) {
         g = geom(t + 1);

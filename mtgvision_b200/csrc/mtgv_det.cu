@@ -618,6 +618,14 @@ __device__ int ph_blur_family(DRng& r, mtgv_photo_op* o, double p) {
   return 0;
 }
 
+// Gen._get_bg_ds + ran_path (od_datasets.py:656-672): the dataset with probability p, then an image uniformly inside it
+__device__ __forceinline__ int det_draw_bg(DRng& r, const mtgv_det_config* cfg, int n_bgs) {
+  const int nf = cfg->n_bgs_first;
+  if (nf <= 0 || nf >= n_bgs) return r.below(n_bgs);
+  if (r.uniform() < cfg->bg_first_prob) return r.below(nf);
+  return nf + r.below(n_bgs - nf);
+}
+
 __global__ void k_det_sample(uint64_t seed, int64_t first, int n, const mtgv_det_config* __restrict__ cfg, int n_cards_pool,
                              int n_bgs, int card_h, int card_w, mtgv_det_tape* tape) {
   // one warp per scene, lane 0 working: scenes take divergent paths through the augmentation graphs
@@ -633,7 +641,7 @@ __global__ void k_det_sample(uint64_t seed, int64_t first, int n, const mtgv_det
   const bool ph = cfg->photometrics != 0;
   int idx[8];
   if (t->bg_only) {  // random_bg / make_aug_background (:206-210)
-    t->bg = r.below(n_bgs);
+    t->bg = det_draw_bg(r, cfg, n_bgs);
     t->bg_deg = r.below(360);
     const int fl = ph_fill(r, 0.1, 0.5, 0.2);
     if (ph) {
@@ -668,7 +676,7 @@ __global__ void k_det_sample(uint64_t seed, int64_t first, int n, const mtgv_det
   }
   // generate_synthetic_image (:520-611)
   const int fill_light = ph_fill(r, 0.1, 0.5, 0.2), fill_card = ph_fill(r, 0.1, 0.5, 0.2);
-  t->bg = r.below(n_bgs);
+  t->bg = det_draw_bg(r, cfg, n_bgs);
   t->bg_deg = r.below(360);
   if (ph) {
     ph_perm(r, idx, 4);
@@ -690,7 +698,8 @@ __global__ void k_det_sample(uint64_t seed, int64_t first, int n, const mtgv_det
   const int diag = (int)sqrt((double)card_h * card_h + (double)card_w * card_w);
   const int pad = diag / 2, ovr = (int)(diag * (1.0 - edge));
   const int lox = pad - ovr, hix = S_w - pad + ovr, loy = pad - ovr, hiy = S_h - pad + ovr;
-  const double la = log((double)S_h * S_w * cfg->min_area_ratio), lb = log((double)S_h * S_w * cfg->max_area_ratio);
+  const double amin = (double)S_h * S_w * cfg->min_area_ratio, amax = (double)S_h * S_w * cfg->max_area_ratio;
+  const double la = log(amin), lb = log(amax);
   for (int ci = 0; ci < t->n_cards; ci++) {
     mtgv_det_card* c = &t->cards[ci];
     c->card = r.below(n_cards_pool);
@@ -702,7 +711,7 @@ __global__ void k_det_sample(uint64_t seed, int64_t first, int n, const mtgv_det
       a->cy = loy + r.below(hiy - loy + 1);
       a->dst_given = 0; a->_pad = 0;
       a->deg = r.uniform(0.0, 360.0);
-      a->area = exp(r.uniform(la, lb));
+      a->area = cfg->size_sample_mode == 1 ? r.uniform(amin, amax) : exp(r.uniform(la, lb));  // place_card_on_background_get_transform (:327-332)
       for (int k = 0; k < 4; k++) a->jitter[k] = r.uniform(1.0 - cfg->jitter_ratio, 1.0 + cfg->jitter_ratio);
       for (int k = 0; k < 8; k++) a->dst[k] = 0.f;
     }

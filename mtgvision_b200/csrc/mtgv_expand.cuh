@@ -340,10 +340,11 @@ MTGV_HD int expand_encoder_sample(const mtgv_enc_tape* t, const mtgv_enc_config*
   } else {
     crop_geometry(p->rot_nh, p->rot_nw, OH, OW, false, &p->bg_rh, &p->bg_rw, &p->bg_y0, &p->bg_x0);
   }
-  // INTER_AREA: down-scale by at most 6 (taps <= 8); when the canvas is smaller than the output cv2 enlarges with its
-  // 2-tap "area-linear" kernel on both axes (area_linear_compact)
+  // INTER_AREA: down-scale by at most kBgMaxAreaScale (photographs up to ~4600 px diagonal at 192x128; the pools refuse
+  // larger images when they are filled, so this never trips at run time); when the canvas is smaller than the output cv2
+  // enlarges with its 2-tap "area-linear" kernel on both axes (area_linear_compact)
   if (p->bg_rh < OH || p->bg_rw < OW) return p->status = MTGV_ERR_LIMIT;
-  if (p->rot_nh > 6 * p->bg_rh || p->rot_nw > 6 * p->bg_rw) return p->status = MTGV_ERR_LIMIT;
+  if (p->rot_nh > kBgMaxAreaScale * p->bg_rh || p->rot_nw > kBgMaxAreaScale * p->bg_rw) return p->status = MTGV_ERR_LIMIT;
 
   for (int k = t->n_fg + t->n_bg; k < t->n_fg + t->n_bg + (bg_only ? 0 : t->n_vrtl); k++) {
     if (n >= MTGV_X_MAX_OPS) return p->status = MTGV_ERR_LIMIT;

@@ -47,7 +47,9 @@ constexpr int kInterBits = 5;
 constexpr int kInterTab = 32;
 constexpr int kAbBits = 10;
 constexpr int kAbScale = 1024;
-constexpr int kAreaMaxTaps = 8;  // supports INTER_AREA scale factors up to 6
+constexpr int kAreaMaxTaps = 8;  // register-resident tap lists (area_taps, templated reducers): INTER_AREA scale factors up to 6
+constexpr int kAreaCompactMaxTaps = 250;  // compact entries (start, count, wl, wm, wr) carry any count that fits their 8-bit field
+constexpr int kBgMaxAreaScale = 24;       // largest INTER_AREA reduction of the background chain (k_background's generic reducer)
 
 // ---------------------------------------------------------------------------------------
 // cv::hal::LU64f + back substitution, n = 8, one right-hand side
@@ -241,9 +243,9 @@ MTGV_HD void area_compact(int ssize, int dsize, int d, int* start, int* n, float
   }
   *wm = (float)MTGV_DDIV(1.0, cell);
   int mid = sx2 - sx1;
-  if (mid > kAreaMaxTaps - cnt) mid = kAreaMaxTaps - cnt;
+  if (mid > kAreaCompactMaxTaps - cnt) mid = kAreaCompactMaxTaps - cnt;
   if (mid > 0) cnt += mid;
-  if (MTGV_DSUB(fsx2, (double)sx2) > 1e-3 && cnt < kAreaMaxTaps) {
+  if (MTGV_DSUB(fsx2, (double)sx2) > 1e-3 && cnt < kAreaCompactMaxTaps) {
     double t = fmin(fmin(MTGV_DSUB(fsx2, (double)sx2), 1.0), cell);
     *wr = (float)MTGV_DDIV(t, cell);
     flags |= 512;

@@ -148,6 +148,12 @@ int dewarp_u8(mtgv_ctx* ctx, const uint8_t* frame, int fh, int fw, int fc, const
 int jpeg_destroy(mtgv_ctx* ctx);
 int jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms);
 int jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw);
+struct JpegDst {  // where one decoded file goes: byte offset from the call's `out`, expected frame size, layout (JpegImg::out_layout), pitch
+  int64_t off;
+  int32_t h, w, layout, pitch;
+};
+int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const JpegDst* dst,
+                         cudaStream_t stream);
 int jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, int32_t* hw);
 int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
                       const int32_t* hw, cudaStream_t st);

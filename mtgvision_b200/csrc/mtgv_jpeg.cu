@@ -552,7 +552,23 @@ __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ 
             px[3 * q] = (uint8_t)rgb[0]; px[3 * q + 1] = (uint8_t)rgb[1]; px[3 * q + 2] = (uint8_t)rgb[2];
           }
         }
-        if (aligned && cnt == 4) {
+        if (im.out_layout == 2) {
+          // background pool layout: one RGBX word per pixel; x0 and the row pitch are multiples of 4 pixels -> 16-byte store
+          uint32_t* d = (uint32_t*)(out + im.out_off) + (int64_t)yy * im.out_pitch + x0;
+          uint32_t wv[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) wv[q] = (uint32_t)px[3 * q] | ((uint32_t)px[3 * q + 1] << 8) | ((uint32_t)px[3 * q + 2] << 16);
+          if (cnt == 4) *(uint4*)d = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          else for (int q = 0; q < cnt; q++) d[q] = wv[q];
+        } else if (im.out_layout == 1) {
+          // card pool layout: three planes of rows padded to 16 bytes; 4 pixels -> one word per plane
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            uint8_t* d = out + im.out_off + ((int64_t)c * H + yy) * im.out_pitch + x0;
+            if (cnt == 4) *(uint32_t*)d = (uint32_t)px[c] | ((uint32_t)px[3 + c] << 8) | ((uint32_t)px[6 + c] << 16) | ((uint32_t)px[9 + c] << 24);
+            else for (int q = 0; q < cnt; q++) d[q] = px[3 * q + c];
+          }
+        } else if (aligned && cnt == 4) {
           uint32_t* d = (uint32_t*)(drow + x0 * 3);
 #pragma unroll
           for (int q = 0; q < 3; q++)
@@ -631,6 +647,13 @@ int jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off
 
 int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const int64_t* out_off,
                       const int32_t* hw, cudaStream_t stream) {
+  std::vector<JpegDst> dst(n);
+  for (int i = 0; i < n; i++) dst[i] = JpegDst{out_off[i], hw[2 * i], hw[2 * i + 1], 0, 0};
+  return jpeg_decode_batch_ex(ctx, files, file_off, n, out, dst.data(), stream);
+}
+
+int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, uint8_t* out, const JpegDst* dst,
+                         cudaStream_t stream) {
   if (!ctx->jpeg) {
     ctx->jpeg = new JpegState();
     MTGV_CUDA_OK(ctx, cudaMemcpyToSymbol(c_zigzag, kJpegZigzag, 64));
@@ -649,12 +672,15 @@ int jpeg_decode_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_o
   int max_blk = 0, max_h = 0;
   for (int i = 0; i < n; i++) {
     JpegImg& im = imgs[i];
-    if (im.h != hw[2 * i] || im.w != hw[2 * i + 1])
+    if (im.h != dst[i].h || im.w != dst[i].w)
       return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: file " + std::to_string(i) + " is " + std::to_string(im.h) + "x" +
-                                             std::to_string(im.w) + ", the caller's hw says otherwise");
+                                             std::to_string(im.w) + ", the destination is " + std::to_string(dst[i].h) + "x" +
+                                             std::to_string(dst[i].w));
     im.file_off = file_off[i] - file_off[0];
     im.coef_blk = nblk_total;
-    im.out_off = out_off[i];
+    im.out_off = dst[i].off;
+    im.out_layout = dst[i].layout;
+    im.out_pitch = dst[i].pitch;
     for (int c = 0; c < im.ncomp; c++) {
       im.plane_off[c] = plane_total;
       plane_total += (int64_t)im.bw[c] * im.bh[c] * 64;

@@ -51,6 +51,8 @@ struct JpegImg {
   int64_t clean_off;     // byte-unstuffed copy of the scan in the clean scratch (bytes, multiple of 16)
   int64_t sync_off;      // checkpoint states of the subsequences (uint64 units)
   int64_t rst_off;       // par == 2: clean byte position of every restart interval but the first (uint32 units)
+  int32_t out_layout;    // 0: [h][w][3] RGB bytes; 1: planar [3][h][out_pitch] bytes (card pool); 2: RGBX words [h][out_pitch] (background pool)
+  int32_t out_pitch;     // layout 1: bytes per plane row; layout 2: words per row
 };
 
 struct JpegSeg {  // one restart interval (or the whole scan): decoded by one thread

@@ -81,11 +81,10 @@ class RanMtgEncDecDataset(IterableDataset):
         self.ilsvrc.fill_pool(self.ctx)
         big = self.ctx.oversized_backgrounds(self.x_size_hw)
         if len(big):
-            import warnings
-
-            warnings.warn(f"{len(big)} background(s) (first: pool index {int(big[0])}, {tuple(int(v) for v in self.ctx.bg_hw[big[0]])}) are large "
-                          f"enough that some rotations exceed the x6 INTER_AREA limit at x_size_hw={self.x_size_hw}; those samples are "
-                          "flagged in params.status (check_data=True raises on them)")
+            # refused up front instead of flagged per sample: a batch never contains a slot that failed for its size
+            raise ValueError(f"{len(big)} background(s) (first: pool index {int(big[0])}, {tuple(int(v) for v in self.ctx.bg_hw[big[0]])}) need an "
+                             f"INTER_AREA reduction beyond x{int(self.ctx.MAX_BG_AREA_SCALE)} at x_size_hw={self.x_size_hw} for some rotations; "
+                             "downscale them before filling the pool")
 
     # ------------------------------------------------------------------ reference surface
     def __iter__(self):
@@ -237,36 +236,40 @@ class RanMtgEncDecDataset(IterableDataset):
                     card_images, bg_images = item
                     n, card_shape, bg_shape = card_images.shape[0], tuple(card_images.shape), tuple(bg_images.shape)
                     assert bg_images.shape[0] == n
-                if not slots or tuple(slots[0]["cards"].shape) != card_shape or tuple(slots[0]["bgs"].shape) != bg_shape:
+                if not slots or slots[0]["shapes"] != (card_shape, bg_shape):
                     slots = self._pipe_slots = []
                     if 2 * n > len(self.mtg.pool) or 2 * n > len(self.ilsvrc):
                         raise ValueError("host_tensor_batches needs pools of at least 2 * batch entries")
-                    nc, nb = int(np.prod(card_shape)), int(np.prod(bg_shape))
                     for j in range(2):
-                        flat = torch.empty(nc + nb, dtype=torch.uint8, device=dev)  # cards then backgrounds: one decode target
                         slots.append({
-                            "flat": flat, "cards": flat[:nc].view(card_shape), "bgs": flat[nc:].view(bg_shape),
+                            "shapes": (card_shape, bg_shape), "cards": None, "bgs": None,
                             "idx": torch.arange(j * n, (j + 1) * n, dtype=torch.int32, device=dev),
                             "k_done": torch.cuda.Event(), "copy_done": torch.cuda.Event(), "in_done": torch.cuda.Event(),
                             "out_done": torch.cuda.Event(),
                             "host": {}, "dev": None,
                         })
+                if jpeg is None and slots[i % 2]["cards"] is None:  # device staging for uploaded arrays (files decode straight into the pools)
+                    slots[i % 2]["cards"] = torch.empty(card_shape, dtype=torch.uint8, device=dev)
+                    slots[i % 2]["bgs"] = torch.empty(bg_shape, dtype=torch.uint8, device=dev)
                 sl = slots[i % 2]
                 # upload + pool ingest of this batch may start once the kernels that last read these slots are done
                 s_in.wait_event(sl["k_done"])
                 with torch.cuda.stream(s_in):
                     if jpeg is not None:
-                        ctx.decode_prepared(jpeg, sl["flat"])  # file bytes up, Huffman / IDCT / colour kernels on this stream
+                        # file bytes up, Huffman / IDCT / colour kernels on this stream, pixels written in the pools' own layouts
+                        ctx.decode_into_pools(jpeg, n, (i % 2) * n, n, (i % 2) * n)
+                        sl["in_done"].record(s_in)
                     else:
                         sl["cards"].copy_(card_images, non_blocking=True)
                         sl["bgs"].copy_(bg_images, non_blocking=True)
                     sl["copy_done"].record(s_in)
-                # the layout conversion into the pools runs on its own stream so the next upload starts right away
-                s_pl.wait_event(sl["copy_done"])
-                with torch.cuda.stream(s_pl):
-                    ctx.update_card_images(sl["cards"], (i % 2) * n)
-                    ctx.update_bg_images(sl["bgs"], (i % 2) * n)
-                    sl["in_done"].record(s_pl)
+                if jpeg is None:
+                    # the layout conversion into the pools runs on its own stream so the next upload starts right away
+                    s_pl.wait_event(sl["copy_done"])
+                    with torch.cuda.stream(s_pl):
+                        ctx.update_card_images(sl["cards"], (i % 2) * n)
+                        ctx.update_bg_images(sl["bgs"], (i % 2) * n)
+                        sl["in_done"].record(s_pl)
                 s_k.wait_event(sl["in_done"])
                 s_k.wait_event(sl["out_done"])  # the previous download from this slot's device batch is finished
                 with torch.cuda.stream(s_k):

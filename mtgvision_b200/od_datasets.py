@@ -60,9 +60,8 @@ class Gen:
         rank: int = 0,
         world_size: int = 1,
     ):
-        if card_size_sample_mode != "log_uniform":
-            raise KeyError(card_size_sample_mode) if card_size_sample_mode != "uniform" else NotImplementedError(
-                "card_size_sample_mode='uniform' is not implemented on the B200 path")
+        if card_size_sample_mode not in ("uniform", "log_uniform"):
+            raise KeyError(card_size_sample_mode)  # like place_card_on_background_get_transform (od_datasets.py:333)
         self.mtg_ds = mtg_ds if mtg_ds is not None else SyntheticBgFgMtgImages(img_type="small")
         self.bg_ds = bg_ds if bg_ds is not None else IlsvrcImages()
         self.bg2_ds = bg2_ds
@@ -80,9 +79,21 @@ class Gen:
         self.seed = random.getrandbits(63) if seed is None else int(seed)
         self.rank, self.world_size = int(rank), int(world_size)
         self._shards = ShardCursor(self.rank, self.world_size)
-        # both background datasets share one resident pool (the reference draws the dataset with
-        # ilsvrc_vs_coco_sample_weights and then an image uniformly, od_datasets.py:662-672)
+        # both background datasets share one resident pool: bg_ds in slots [0, len(bg_ds)), bg2_ds behind it.  The sampler
+        # draws the dataset with ilsvrc_vs_coco_sample_weights first and then an image uniformly inside it, like
+        # Gen._get_bg_ds + ran_path (od_datasets.py:656-672); weights=None = proportional to the dataset sizes.
         sources = [self.bg_ds] + ([self.bg2_ds] if self.bg2_ds is not None else [])
+        n_first = len(self.bg_ds) if self.bg2_ds is not None else 0
+        if self.bg2_ds is None:
+            p_first = 1.0
+        elif ilsvrc_vs_coco_sample_weights is None:
+            p_first = len(self.bg_ds) / float(len(self.bg_ds) + len(self.bg2_ds))
+        else:
+            w = np.asarray(ilsvrc_vs_coco_sample_weights, dtype=np.float64)
+            if w.shape != (2,) or not (w >= 0).all() or w.sum() <= 0:
+                raise ValueError("ilsvrc_vs_coco_sample_weights must be two non-negative weights")
+            p_first = float((w / np.sum(w))[0])
+        self._bg_p = np.asarray([p_first, 1.0 - p_first])
         self.ctx = Context(device)
         pool = self.mtg_ds.pool
         self.ctx.set_card_pool(pool.images, pool.labels3, pool.grp_off, pool.grp_mem)
@@ -99,7 +110,8 @@ class Gen:
                                     card_jitter_ratio=card_jitter_ratio, card_min_area_ratio=card_min_area_ratio,
                                     card_max_area_ratio=card_max_area_ratio, card_no_contains=card_no_contains,
                                     card_max_place_attempts=card_max_place_attempts, ratio_bg=ratio_bg, kind=kind,
-                                    photometrics=photometrics)
+                                    photometrics=photometrics, card_size_sample_mode=card_size_sample_mode,
+                                    n_bgs_first=n_first, bg_first_prob=p_first)
         except abi.MtgvError as e:
             if "empty range" in str(e):
                 raise ValueError(str(e)) from e

@@ -107,6 +107,33 @@ def test_device_transcendentals_change_nothing_discrete(env):
     assert np.abs(a[2][both] - b[2][both]).max() < 0.05  # keypoints agree to a few hundredths of a pixel
 
 
+def test_config4_1280_up_to_32_cards_matches_oracle(env):
+    """BASELINE config 4 against the oracle (od_datasets.py:520-611): 1280x1280 scenes, num_cards_max=33 (up to 32 cards),
+    photometrics on - the <= 32-card placement loop, the 1280^2 tile lists and the multi-pass blur scratch that 640^2 / 8
+    cards does not stress.  Decisions, keypoints and labels exact; pixels within 1 uint8 LSB."""
+    pool, bgs, ctx = env
+    kw = dict(bg_size_hw=1280, num_cards_max=33)
+    for kind, seeds in (("obb", (900, 901, 902)), ("seg", (903, 904, 905))):
+        scenes = oracle_scenes(pool, bgs, kind, seeds, photometrics=True, **kw)
+        assert max(t["n_cards"] for t, _ in scenes) >= 12  # the seeds do reach many-card scenes
+        img, accepted, kps, labels, counts = run_gpu(ctx, [t for t, _ in scenes], kind, True, **kw)
+        for s, (t, sample) in enumerate(scenes):
+            for ci, c in enumerate(t["cards"]):
+                want = len(c["attempts"]) - 1 if c["attempts"][-1]["accepted"] else -1
+                assert accepted[s, ci] == want, f"{kind} scene {s} card {ci}: accept/reject differs"
+            k = sample["keypoints"].shape[0]
+            P = sample["keypoints"].shape[1] if k else 0
+            assert counts[s] == k
+            assert np.array_equal(kps[s, :k, :P], sample["keypoints"].reshape(k, P, 2))
+            assert np.array_equal(labels[s, :k], sample["keypoints_labels"])
+            lsb, _ = PU.lsb_diff(img[s], sample["image"])
+            assert lsb <= 1, f"{kind} scene {s}: max uint8 LSB error {lsb}"
+    # without photometrics the float32 image is the reference's own arithmetic: exact
+    scenes = oracle_scenes(pool, bgs, "obb", (906, 907), photometrics=False, **kw)
+    img, accepted, *_ = run_gpu(ctx, [t for t, _ in scenes], "obb", False, **kw)
+    assert max(float(np.abs(img[s] - sample["image"]).max()) for s, (t, sample) in enumerate(scenes)) <= 1e-6
+
+
 def test_full_size_1280_32_cards_properties(env):
     """BASELINE config 4 shape: 1280x1280, up to 32 cards, photometrics on, production sampler."""
     pool, bgs, ctx = env

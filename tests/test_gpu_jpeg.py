@@ -141,6 +141,42 @@ def test_card_pool_from_jpeg_files():
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
+def test_decode_straight_into_the_pools():
+    """mtgv_decode_jpeg_to_pools (files -> the pools' own planar / RGBX layouts) == set_*_pool from the cv2-decoded arrays:
+    same generated batch, for a slot range in the middle of the pools, ragged widths (not multiples of 4) included."""
+    from mtgvision_b200 import abi, synth
+    from mtgvision_b200.abi import MtgvError
+    from tests import parity_util as PU
+
+    for card_hw, bg_hw, mode in (((680, 488), (375, 500), "420"), ((121, 86), (77, 101), "444"), ((90, 62), (50, 67), "422")):
+        pool, bgs = PU.small_pools(6, 6, card_hw, bg_hw)
+        cfiles = [jpeg_cases.encode(pool.images[k], 92, mode) for k in range(6)]
+        bfiles = [jpeg_cases.encode(bgs[j], 88, mode) for j in range(6)]
+        dec_cards = synth.CardPool(np.stack([_ref(f) for f in cfiles]), pool.faces)
+        dec_bgs = [_ref(f) for f in bfiles]
+        outs = []
+        for via_files in (False, True):
+            if via_files:
+                ctx = PU.make_context(synth.CardPool(np.zeros_like(dec_cards.images), pool.faces), [np.zeros_like(b) for b in dec_bgs])
+                # slots [0,2) from arrays, [2,6) decoded from files into the pool layouts
+                ctx.update_card_images(torch.from_numpy(dec_cards.images[:2]).cuda(), 0)
+                ctx.update_bg_images(torch.from_numpy(np.stack(dec_bgs[:2])).cuda(), 0)
+                batch = ctx.prepare_jpegs(cfiles[2:] + bfiles[2:])
+                ctx.decode_into_pools(batch, 4, 2, 4, 2)
+            else:
+                ctx = PU.make_context(dec_cards, dec_bgs)
+            tape = ctx.sample_encoder_tape(11, 0, 24)
+            params, labels = ctx.expand_params(tape)
+            outs.append(ctx.encoder_batch(params, abi.OUT_U8).cpu().numpy())
+            if via_files:
+                with pytest.raises(MtgvError, match="destination"):  # a background file into a card slot: sizes differ
+                    ctx.decode_into_pools(ctx.prepare_jpegs(bfiles[:1]), 1, 0, 0, 0)
+                with pytest.raises(MtgvError, match="outside the pool"):
+                    ctx.decode_into_pools(ctx.prepare_jpegs(cfiles[:2]), 2, 5, 0, 0)
+            ctx.close()
+        assert np.array_equal(outs[0], outs[1]), (card_hw, bg_hw, mode)
+
+
 def test_detection_generator_over_jpeg_backgrounds():
     """Gen over a file-backed background source == Gen over the cv2-decoded arrays."""
     from mtgvision_b200 import synth

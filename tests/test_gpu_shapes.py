@@ -1,6 +1,6 @@
 """Parity of the CUDA encoder path against the oracle away from the benchmark geometry: ragged
 background pools, other card / output sizes (wider cards, more INTER_AREA taps, canvases beyond the
-kernels' fixed-point tables), empty batches and the documented size limits.  Same bar as
+kernels' fixed-point tables, photograph-sized backgrounds), empty batches and the documented size limits.  Same bar as
 test_gpu_encoder.py: labels exact, pixels within 1 uint8 LSB."""
 import numpy as np
 import pytest
@@ -29,6 +29,9 @@ CASES = {
     "square_output": ((680, 488), [(375, 500), (400, 400)], (160, 160)),
     # backgrounds smaller than the output: crop_to_size enlarges with cv2's 2-tap "area-linear" INTER_AREA kernel
     "tiny_backgrounds_enlarged": ((680, 488), [(90, 120), (60, 50), (128, 100), (150, 127), (40, 333)], (192, 128)),
+    # full-size photographs (ILSVRC holds them): INTER_AREA reductions of x7 .. x16, past the register-resident tap lists
+    "photograph_sized_backgrounds": ((680, 488), [(1000, 1500), (1536, 2048)], (192, 128)),
+    "vga_background_small_output": ((680, 488), [(480, 640), (768, 1024)], (96, 64)),
 }
 
 
@@ -44,7 +47,7 @@ def test_virtual_samples_other_geometries(name):
     ctx = PU.make_context(pool, bgs, half_upsidedown=True, x_size_hw=x_hw, y_size_hw=x_hw)
     try:
         refs, tapes = [], []
-        for seed in range(3 * len(bgs)):
+        for seed in range((2 if "photograph" in name else 3) * len(bgs)):
             img, t = PU.oracle_virtual(pool, bgs, 7000 + seed, seed % 4, seed % len(bgs), size_hw=x_hw)
             refs.append(img)
             tapes.append(t)
@@ -114,14 +117,23 @@ def test_pair_partner_plane_reuse_is_invisible():
         ctx.close()
 
 
-def test_oversized_background_is_reported_at_ingest():
-    """A background whose rotated canvas can exceed the x6 INTER_AREA limit: warned about when the pool is filled."""
+def test_oversized_background_is_refused_at_ingest():
+    """A background whose rotated canvas can exceed the x24 INTER_AREA limit is refused when the dataset is built (no sample
+    can then fail for its size at run time); full-size photographs below the limit are accepted without a warning."""
+    import warnings
+
     from mtgvision_b200.encoder_datasets import IlsvrcImages, SyntheticBgFgMtgImages
     from mtgvision_b200.encoder_train import RanMtgEncDecDataset
 
     pool, bgs = PU.small_pools(4, 4)
-    huge = np.zeros((1500, 2000, 3), np.uint8)
-    with pytest.warns(UserWarning, match="INTER_AREA limit"):
-        ds = RanMtgEncDecDataset(2, paired=True, targets=False, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=IlsvrcImages(images=list(bgs) + [huge]), seed=1)
-    assert list(ds.ctx.oversized_backgrounds((192, 128))) == [4]
+    huge = np.zeros((3000, 4000, 3), np.uint8)  # diagonal 5000 px: x26 at 192 rows
+    with pytest.raises(ValueError, match="INTER_AREA"):
+        RanMtgEncDecDataset(2, paired=True, targets=False, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=IlsvrcImages(images=list(bgs) + [huge]), seed=1)
+    photo = np.random.default_rng(0).integers(0, 256, (1500, 2000, 3), dtype=np.uint8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        ds = RanMtgEncDecDataset(8, paired=True, targets=False, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=IlsvrcImages(images=[photo] * 2), seed=1,
+                                 check_data=True)
+    b = ds.random_tensor_batch()  # check_data=True raises on any failed sample
+    assert b["x"].shape == (8, 3, 192, 128)
     ds.ctx.close()
