@@ -526,6 +526,8 @@ def run_cuda(args):
                                             [bg_files[(i * PAIRS + q) % len(bg_files)] for q in range(PAIRS)])
 
         b_steps = min(e2e_steps, 10)
+        for _ in ds.host_tensor_batches(feed_bytes(3)):  # warm-up: the three pinned staging buffers of prepare_jpegs
+            pass
         b_ms, _ = timed(feed_bytes, b_steps)
         e2e["from_bytes_objects"] = {"value": world * n_x * b_steps / (b_ms * 1e-3), "unit": UNIT, "steps": b_steps,
                                      "api": "prepare_jpeg_batch(list of bytes, list of bytes) inside the loop: join + copy into fresh pinned memory"}

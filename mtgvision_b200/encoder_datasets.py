@@ -33,10 +33,17 @@ PathOrImg = "str | np.ndarray"
 
 
 def _as_u8_image(img) -> np.ndarray:
-    if isinstance(img, str):
-        raise NotImplementedError(
-            "image decode is out of scope for the B200 path (SURVEY.md section 8f): pass an ndarray"
-        )
+    if isinstance(img, (str, os.PathLike)):
+        # `path_or_img` (encoder_datasets.py:741, 759, 778, 796 -> uimg.imread_float, util/image.py:107-114): the file is read on the
+        # host and decoded by the device decoder (bit-exact with cv2.imread for baseline JPEG; no CPU decode path exists here)
+        path = os.fspath(img)
+        try:
+            with open(path, "rb") as f:
+                data = f.read()
+        except OSError:
+            raise Exception("Image not found: {}".format(path)) from None  # imread_float's message (util/image.py:112-113)
+        flat, _, hw = _StaticEngine.get().decode_jpegs([data])
+        return flat.cpu().numpy().reshape(int(hw[0, 0]), int(hw[0, 1]), 3)
     a = np.asarray(img)
     if a.ndim != 3 or a.shape[2] != 3:
         raise ValueError(f"expected an (H, W, 3) image, got shape {a.shape}")

@@ -177,6 +177,31 @@ def test_decode_straight_into_the_pools():
         assert np.array_equal(outs[0], outs[1]), (card_hw, bg_hw, mode)
 
 
+def test_static_helpers_accept_file_paths(tmp_path):
+    """`path_or_img: str` of make_cropped / make_masked / make_bg / make_virtual (encoder_datasets.py:741, 759, 778, 796): the file
+    goes through the device decoder and gives what the cv2-decoded array gives."""
+    import random
+
+    from mtgvision_b200 import synth
+    from mtgvision_b200.encoder_datasets import SyntheticBgFgMtgImages as S
+
+    card, bg = synth.synth_card(3), synth.synth_bg(2)
+    cpath, bpath = str(tmp_path / "card.jpg"), str(tmp_path / "bg.jpg")
+    open(cpath, "wb").write(jpeg_cases.encode(card, 92, "420"))
+    open(bpath, "wb").write(jpeg_cases.encode(bg, 90, "420"))
+    dcard, dbg = _ref(open(cpath, "rb").read()), _ref(open(bpath, "rb").read())
+    assert np.array_equal(S.make_cropped(cpath, (192, 128)), S.make_cropped(dcard, (192, 128)))
+    assert np.array_equal(S.make_masked(cpath), S.make_masked(dcard))
+    random.seed(5); a = S.make_bg(bpath, (192, 128))
+    random.seed(5); b = S.make_bg(dbg, (192, 128))
+    assert np.array_equal(a, b)
+    random.seed(6); a = S.make_virtual(cpath, bpath, (192, 128))
+    random.seed(6); b = S.make_virtual(dcard, dbg, (192, 128))
+    assert np.array_equal(a, b)
+    with pytest.raises(Exception, match="Image not found"):
+        S.make_cropped(str(tmp_path / "missing.jpg"), (192, 128))
+
+
 def test_detection_generator_over_jpeg_backgrounds():
     """Gen over a file-backed background source == Gen over the cv2-decoded arrays."""
     from mtgvision_b200 import synth

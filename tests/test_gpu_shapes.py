@@ -31,7 +31,7 @@ CASES = {
     "tiny_backgrounds_enlarged": ((680, 488), [(90, 120), (60, 50), (128, 100), (150, 127), (40, 333)], (192, 128)),
     # full-size photographs (ILSVRC holds them): INTER_AREA reductions of x7 .. x16, past the register-resident tap lists
     "photograph_sized_backgrounds": ((680, 488), [(1000, 1500), (1536, 2048)], (192, 128)),
-    "vga_background_small_output": ((680, 488), [(480, 640), (768, 1024)], (96, 64)),
+    "vga_background_small_output": ((340, 244), [(480, 640), (768, 1024)], (96, 64)),
 }
 
 
