@@ -572,13 +572,21 @@ def run_cuda(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if args.epoch_samples > 0 else "weak",
+            "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
             "stats": {"out_dtype": "fp16 NCHW", "setup_s": round(t_setup, 1), "virtual": n_virtual, "cropped": n_cropped,
                       "failed_samples": int((status != 0).sum()), "sampled_steps": n_keep, **drift},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if args.epoch_samples > 0:
+            total = world * n_x * args.steps
+            line["epoch"] = {"x_samples": total, "seconds_device_resident": ms_max * 1e-3,
+                             "seconds_e2e_from_files": (total / e2e["value"]) if e2e else None,
+                             "seconds_cpu_extrapolated": (total / cpu_baseline["value"]) if cpu_baseline else None,
+                             "note": "BASELINE configs[4]: one epoch of x-samples split into contiguous global-index shards, one per GPU; the CPU "
+                                     "figure extrapolates the bounded cpu_baseline sample"}
         if dist is not None:
             sys.stdout.flush()
             os.dup2(_stdout_fd, 1)
@@ -613,7 +621,32 @@ def _det_cpu_worker(args):
     return n_scenes
 
 
+def _clip_area(poly, S):
+    """Area of a convex polygon (k,2) clipped to the frame [0,S]x[0,S] (Sutherland-Hodgman) - the A_k of SURVEY 8d."""
+    import numpy as np
+
+    pts = [tuple(p) for p in poly]
+    for axis, bound, keep_less in ((0, 0.0, False), (0, float(S), True), (1, 0.0, False), (1, float(S), True)):
+        out = []
+        for i in range(len(pts)):
+            p, q = pts[i], pts[(i + 1) % len(pts)]
+            pin = p[axis] <= bound if keep_less else p[axis] >= bound
+            qin = q[axis] <= bound if keep_less else q[axis] >= bound
+            if pin:
+                out.append(p)
+            if pin != qin:
+                t = (bound - p[axis]) / (q[axis] - p[axis])
+                out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+        pts = out
+        if len(pts) < 3:
+            return 0.0
+    a = np.asarray(pts)
+    return 0.5 * abs(float(np.dot(a[:, 0], np.roll(a[:, 1], -1)) - np.dot(a[:, 1], np.roll(a[:, 0], -1))))
+
+
 def run_det(args):
+    """BASELINE configs[2] / configs[3]: detection scenes (640^2 up to 8 cards, 1280^2 up to 32 cards, batch 256), the author's
+    generator settings (od_datasets.py:861-868), kind='seg', photometrics on.  Same JSON contract as the encoder line."""
     import multiprocessing as mp
 
     import numpy as np
@@ -624,55 +657,126 @@ def run_det(args):
     from mtgvision_b200.od_datasets import Gen
 
     S, max_cards, batch = (640, 9, 256) if args.workload == "det640" else (1280, 33, 256)
-    cards = synth.make_card_pool(args.pool_cards, workers=os.cpu_count() or 1)
-    bgs = synth.make_bg_pool(args.pool_bgs, workers=os.cpu_count() or 1)
+    workers = os.cpu_count() or 1
+    cards = synth.make_card_pool(args.pool_cards, workers=workers)
+    bgs = synth.make_bg_pool(args.pool_bgs, workers=workers)
+    cpu_pool = None
+    if not args.no_cpu_baseline:  # forked before CUDA exists in this process
+        _DET_STATE["cards"] = [cards.images[k] for k in range(32)]
+        _DET_STATE["bgs"] = bgs[:32]
+        cpu_pool = mp.get_context("fork").Pool(workers)
+        cpu_pool.map(_det_cpu_worker, [(i, 1, S, max_cards) for i in range(workers)])
     gen = Gen(bg_size_hw=S, num_cards_min=1, num_cards_max=max_cards, card_min_visible_ratio=0.5,
               card_min_visible_ratio_edges=0.0, card_jitter_ratio=0.7, ratio_bg=0.1, kind="seg",
               mtg_ds=SyntheticBgFgMtgImages(pool=cards), bg_ds=IlsvrcImages(images=bgs), seed=7)
     ctx = gen.ctx
-    for _ in range(args.warmup):
+    dev = torch.device("cuda", 0)
+    for _ in range(max(args.warmup, 3)):
         gen.random_batch(batch)
     torch.cuda.synchronize()
+    # live timing of the pixel kernel(s) of one mtgv_det_batch call, CUDA events on the launch stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    placed = 0
+    clocks = ClockSampler(0)
+    clocks.start()
+    time.sleep(0.25)
     l0 = ctx.launch_count()
+    alg = 0.0
+    keep = []
+    t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        b = gen.random_batch(batch)
+    for k in range(args.steps):
+        first = gen._shards.next_first(batch)
+        tape = ctx.sample_det_tape(gen.seed, first, batch)
+        params, accepted, keypoints, labels, counts = ctx.det_place(tape)
+        ev[k][0].record()
+        image = ctx.det_batch(params, abi.OUT_U8)
+        ev[k][1].record()
+        if k >= args.steps - 2:
+            keep.append((keypoints, counts))
     e1.record()
     torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    launches = int(ctx.launch_count() - l0)
+    clk = clocks.stop(t0, t1)
     ms = e0.elapsed_time(e1)
-    placed = int((b["accepted"] >= 0).sum())
+    k_ms = [a.elapsed_time(b) for a, b in ev]
+    k_avg = sum(k_ms) / len(k_ms)
+    # algorithmic bytes: bg source + output + per placed card min(card bytes, 12 * visible quad area)
+    n_placed = 0
+    for keypoints, counts in keep:
+        kp, cnt = keypoints.cpu().numpy(), counts.cpu().numpy()
+        for s_ in range(batch):
+            alg += BYTES_BG + 3 * S * S
+            for q in range(int(cnt[s_])):
+                quad = kp[s_, q][[0, 1, 2, 7]]  # the card box of the 8-vertex seg polygon
+                alg += min(BYTES_CARD, 12.0 * _clip_area(quad, S))
+                n_placed += 1
+    alg_per_launch = alg / len(keep)
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        peak, peak_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    achieved = alg_per_launch / (k_avg * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_det_pixels (all passes of one mtgv_det_batch call; k_det_lists included)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_avg, "kernel_share_of_step": k_avg * args.steps / ms,
+                "placed_cards_per_scene": n_placed / (len(keep) * batch)}
+    # e2e: the public call, host tensors out (uint8 scenes + labels to pinned memory every step; nothing is uploaded: the
+    # generator's inputs are the resident pools)
+    host = {}
+    b = gen.random_batch(batch)
+    for k2 in ("image", "keypoints", "labels", "counts"):
+        host[k2] = torch.empty(b[k2].shape, dtype=b[k2].dtype, pin_memory=True)
+    torch.cuda.synchronize()
+    tw0 = time.perf_counter()
+    chk = 0
+    for _ in range(args.steps):
+        b = gen.random_batch(batch)
+        for k2 in host:
+            host[k2].copy_(b[k2], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        chk += int(host["counts"][0])
+    e2e_ms = (time.perf_counter() - tw0) * 1e3 / args.steps
+    d2h = sum(v.numel() * v.element_size() for v in host.values())
     # the dataset writer's path (create_yolo_obb_dataset): scenes generated AND JPEG-encoded on the device, files to pinned host memory
     ctx.encode_jpegs_host(gen.random_batch(batch)["image"])  # untimed: allocates the encoder's buffers
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    tw0 = time.perf_counter()
     file_bytes = 0
     for _ in range(args.steps):
         files = ctx.encode_jpegs_host(gen.random_batch(batch)["image"])
         file_bytes += sum(len(f) for f in files)
-    writer_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    writer_ms = (time.perf_counter() - tw0) * 1e3 / args.steps
     cpu = None
-    if not args.no_cpu_baseline:
-        _DET_STATE["cards"] = [cards.images[k] for k in range(32)]
-        _DET_STATE["bgs"] = bgs[:32]
-        w = os.cpu_count() or 1
+    if cpu_pool is not None:
         per = 6 if S == 640 else 2
-        with mp.get_context("fork").Pool(w) as pool:
-            pool.map(_det_cpu_worker, [(i, 1, S, max_cards) for i in range(w)])
-            t0 = time.perf_counter()
-            n = sum(pool.map(_det_cpu_worker, [(i, per, S, max_cards) for i in range(w)]))
-            wall = time.perf_counter() - t0
-        cpu = {"value": n / wall, "unit": "scenes/s", "cores": w, "kind": "port", "sample": f"{n} scenes in {wall:.1f} s"}
+        tw0 = time.perf_counter()
+        n = sum(cpu_pool.map(_det_cpu_worker, [(i, per, S, max_cards) for i in range(workers)]))
+        wall = time.perf_counter() - tw0
+        cpu_pool.close()
+        cpu = {"value": n / wall, "unit": "scenes/s", "cores": workers, "kind": "port",
+               "sample": f"{n} scenes in {wall:.1f} s: oracle port of generate_synthetic_image (cv2 warps + composite + restated placement test and "
+                         "photometric subset), one process per core, pools of 32 cards / 32 backgrounds"}
     print(json.dumps({"metric": f"detection scenes/sec {S}x{S}", "value": batch * args.steps / (ms * 1e-3), "unit": "scenes/s",
-                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                      "config": {"workload": args.workload, "batch": batch, "max_cards": max_cards - 1, "kind": "seg",
-                                 "placed_cards_last_batch": placed, "out": "uint8 NCHW"},
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"detection scenes {S}x{S}, up to {max_cards - 1} cards, batch {batch}, overlap rejection sampling, seg polygon "
+                                             "labels, photometric augments (BASELINE configs[%d])" % (2 if S == 640 else 3),
+                                 "batch": batch, "max_cards": max_cards - 1, "kind": "seg", "out": "uint8 NCHW",
+                                 "card_pool": args.pool_cards, "bg_pool": args.pool_bgs,
+                                 "l2": "inputs larger than L2: 256 scenes read ~1000 card images of a multi-GB resident pool; no flush"},
+                      "clocks": clk, "roofline": roofline,
+                      "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h),
+                              "ms_per_step": e2e_ms,
+                              "api": "Gen.random_batch(256) + copy of image / keypoints / labels / counts to pinned host memory, host wall clock "
+                                     "(the generator has no per-step host input: cards and backgrounds are the resident pools)"},
                       "writer": {"value": batch / (writer_ms * 1e-3), "unit": "scenes/s", "ms_per_batch": writer_ms,
                                  "d2h_bytes_per_step": file_bytes // args.steps,
                                  "api": "Gen.random_batch + Context.encode_jpegs_host: scene generation and JPEG encode on the device, "
                                         "files (cv2.imwrite's bytes) in pinned host memory; host wall clock"},
-                      "gpu_launches": int(ctx.launch_count() - l0), "cpu_baseline": cpu}), flush=True)
+                      "gpu_launches": launches, "cpu_baseline": cpu}), flush=True)
 
 
 def run_dewarp(args):
@@ -851,6 +955,9 @@ def main():
     ap.add_argument("--cpu-pairs-per-worker", type=int, default=384)
     ap.add_argument("--ref-pairs-per-worker", type=int, default=128)
     ap.add_argument("--e2e-max-steps", type=int, default=30)
+    ap.add_argument("--epoch-samples", type=int, default=0,
+                    help="BASELINE configs[4]: generate this many x-samples in total, split into contiguous shards over the ranks "
+                         "(strong scaling): overrides --steps with ceil(samples / (1024 * world)) and times the e2e path over as many steps")
     ap.add_argument("--no-e2e-raw", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -868,6 +975,10 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
+        if args.epoch_samples > 0:
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            args.steps = -(-args.epoch_samples // (2 * PAIRS * world))
+            args.e2e_max_steps = args.steps
         run_cuda(args)
 
 

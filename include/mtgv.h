@@ -288,8 +288,17 @@ typedef enum {
   MTGV_PH_HSV = 2,         /* HueSaturationValue: d[0] hue shift (deg), d[1] sat shift, d[2] val shift (in 1/255) */
   MTGV_PH_GAUSS_NOISE = 3, /* GaussNoise: clip(x + d[0]*N(0,1)); field = unit normals [H,W,3] f32 or PHILOX */
   MTGV_PH_GAUSS_BLUR = 4,  /* GaussianBlur: d[0] sigma; ksize = max(3, int(6 sigma + 1) | 1), REFLECT_101    */
-  MTGV_PH_ERASE = 5        /* Erasing: i[0]=top i[1]=left i[2]=h i[3]=w i[4]=fill (0 random,1 random_uniform,
+  MTGV_PH_ERASE = 5,       /* Erasing: i[0]=top i[1]=left i[2]=h i[3]=w i[4]=fill (0 random,1 random_uniform,
                               2 ones,3 zeros), d[0..2]=uniform colour; field = random block [h,w,3] f32    */
+  /* the remaining members of the noise / blur families of get_bg_transform (od_datasets.py:443-457), SURVEY 8f.3 */
+  MTGV_PH_ISO_NOISE = 6,   /* ISONoise: d[0] color_shift, d[1] intensity.  In cv2's float HLS space: hue += N(0,1) * d[0]*360*d[1]
+                              (mod 360), L += Poisson(std(L)*d[1]*255)/255 * (1 - L); std(L) = cv2.meanStdDev of the image the
+                              op receives.  field = [H,W,2] f32 (Poisson counts, unit normals) or PHILOX               */
+  MTGV_PH_SHOT_NOISE = 7,  /* ShotNoise: d[0] scale.  clip(Poisson((x^2.2 + d[0]*1e-6)/d[0]) * d[0])^(1/2.2);
+                              field = Poisson counts [H,W,3] f32 or PHILOX                                            */
+  MTGV_PH_MEDIAN_BLUR = 8, /* MedianBlur: i[0] = ksize in {3,5,7}; cv2.medianBlur of rint(255 x) as uint8 (edge replicated), / 255 */
+  MTGV_PH_MOTION_BLUR = 9  /* MotionBlur: i[0] = ksize (odd, <= 11), i[1..4] = bit mask of the line kernel (bit y*ksize+x);
+                              cv2.filter2D with mask / popcount(mask), BORDER_REFLECT_101                              */
 } mtgv_photo_code;
 
 typedef struct {

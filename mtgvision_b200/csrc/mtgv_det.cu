@@ -29,6 +29,7 @@ struct DetState {
   size_t scratch_cap = 0;  // floats per buffer
   int32_t* lists = nullptr;  // pass_count[kDetMaxBlur+1] followed by pass_list[kDetMaxBlur+1][chunk]
   size_t list_cap = 0;
+  float* stats = nullptr;    // [chunk][kDetMaxBlur+1] image statistics for ISONoise boundaries
   // detection's own card copy: RGBA words [n][h][w], A = round_rect_mask(card_hw, 0.046) * 255 - image and mask
   // of make_card_with_mask (od_datasets.py:218-235) are warped by the same matrix, one 4-byte load per tap serves both
   uint32_t* card_rgba = nullptr;
@@ -45,6 +46,7 @@ int det_destroy(mtgv_ctx* ctx) {
   if (!ctx->det) return MTGV_OK;
   DetState* d = (DetState*)ctx->det;
   cudaFree(d->cfg_dev); cudaFree(d->kp_dev); cudaFree(d->scratch[0]); cudaFree(d->scratch[1]); cudaFree(d->lists); cudaFree(d->card_rgba);
+  cudaFree(d->stats);
   delete d;
   ctx->det = nullptr;
   return MTGV_OK;
@@ -192,6 +194,60 @@ __device__ __forceinline__ void d_hsv2rgb(float h, float s, float v, float* r, f
   }
 }
 
+// cv2.cvtColor(float32 RGB -> HLS): H in degrees [0,360), L, S in [0,1] (RGB2HLS_f, color_hsv.simd.hpp)
+__device__ __forceinline__ void d_rgb2hls(float r, float g, float b, float* h, float* l, float* s) {
+  const float vmax = fmaxf(r, fmaxf(g, b)), vmin = fminf(r, fminf(g, b));
+  float diff = vmax - vmin;
+  *l = (vmax + vmin) * 0.5f;
+  if (diff > 1.1920929e-07f) {
+    *s = *l < 0.5f ? diff / (vmax + vmin) : diff / (2.f - vmax - vmin);
+    diff = 60.f / diff;
+    float hh;
+    if (vmax == r) hh = (g - b) * diff;
+    else if (vmax == g) hh = (b - r) * diff + 120.f;
+    else hh = (r - g) * diff + 240.f;
+    if (hh < 0.f) hh += 360.f;
+    *h = hh;
+  } else {
+    *h = 0.f; *s = 0.f;
+  }
+}
+
+// cv2.cvtColor(float32 HLS -> RGB) (HLS2RGB_f)
+__device__ __forceinline__ void d_hls2rgb(float h, float l, float s, float* r, float* g, float* b) {
+  if (s == 0.f) { *r = *g = *b = l; return; }
+  const float p2 = l <= 0.5f ? l * (1.f + s) : l + s - l * s;
+  const float p1 = 2.f * l - p2;
+  h *= (6.f / 360.f);
+  if (h < 0.f) do h += 6.f; while (h < 0.f);
+  else if (h >= 6.f) do h -= 6.f; while (h >= 6.f);
+  int sector = (int)floorf(h);
+  h -= (float)sector;
+  if ((unsigned)sector >= 6u) { sector = 0; h = 0.f; }
+  const float t0 = p2, t1 = p1, t2 = p1 + (p2 - p1) * (1.f - h), t3 = p1 + (p2 - p1) * h;
+  switch (sector) {  // sector_data {b,g,r} = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
+    case 0: *b = t1; *g = t3; *r = t0; break;
+    case 1: *b = t1; *g = t0; *r = t2; break;
+    case 2: *b = t3; *g = t0; *r = t1; break;
+    case 3: *b = t0; *g = t2; *r = t1; break;
+    case 4: *b = t0; *g = t1; *r = t3; break;
+    default: *b = t2; *g = t1; *r = t0; break;
+  }
+}
+
+// Poisson(lam) by inversion of the cumulative distribution (production fields; lam <= ~64 on this path)
+__device__ __forceinline__ float d_poisson(float lam, float u) {
+  if (!(lam > 0.f)) return 0.f;
+  float p = __expf(-lam), F = p;
+  int k = 0;
+  while (u > F && k < 512) {
+    k++;
+    p *= lam / (float)k;
+    F += p;
+  }
+  return (float)k;
+}
+
 __device__ __forceinline__ void d_philox(uint64_t seed, int slot, uint32_t idx, uint32_t sub, uint32_t* r) {
   Philox ph;
   ph.key[0] = (uint32_t)seed ^ (0x85EBCA6Bu * (uint32_t)(slot + 1));
@@ -237,6 +293,25 @@ __device__ __forceinline__ void d_photo_point(const DetPhotoX& op, float* rgb, i
       for (int c = 0; c < 3; c++) rgb[c] = dclip01(__fadd_rn(rgb[c], __fmul_rn(g[c], op.f[0])));
       break;
     }
+    case MTGV_PH_SHOT_NOISE: {  // ShotNoise: photon noise in linear light (gamma 2.2), Poisson counts * scale, back to gamma
+      const uint32_t p = (uint32_t)(y * W + x);
+      float cnt[3];
+      if (op.field != MTGV_FIELD_PHILOX) {
+        const float* f = (const float*)(fields + op.field) + (size_t)p * 3;
+        cnt[0] = f[0]; cnt[1] = f[1]; cnt[2] = f[2];
+      } else {
+        uint32_t r[4];
+        d_philox(seed, op.slot, p, 5, r);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float lin = powf(dclip01(rgb[c]), 2.2f);
+          cnt[c] = d_poisson(__fdiv_rn(__fadd_rn(lin, __fmul_rn(op.f[0], 1e-6f)), op.f[0]), d_unit(r[c]));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) rgb[c] = powf(dclip01(__fmul_rn(cnt[c], op.f[0])), 1.0f / 2.2f);
+      break;
+    }
     case MTGV_PH_ERASE: {  // Erasing: rectangle fill
       const int ty = y - op.i[0], tx = x - op.i[1];
       if ((unsigned)ty < (unsigned)op.i[2] && (unsigned)tx < (unsigned)op.i[3]) {
@@ -259,6 +334,31 @@ __device__ __forceinline__ void d_photo_point(const DetPhotoX& op, float* rgb, i
     default:
       break;
   }
+}
+
+// ISONoise on one pixel; std_l = cv2.meanStdDev(HLS image)[1] of the image the op receives
+__device__ __forceinline__ void d_iso_point(const DetPhotoX& op, float* rgb, int y, int x, int W, uint64_t seed,
+                                            const uint32_t* __restrict__ fields, float std_l) {
+  float h, l, s;
+  d_rgb2hls(rgb[0], rgb[1], rgb[2], &h, &l, &s);
+  const uint32_t p = (uint32_t)(y * W + x);
+  float lum, col;
+  if (op.field != MTGV_FIELD_PHILOX) {
+    const float* f = (const float*)(fields + op.field) + (size_t)p * 2;
+    lum = f[0]; col = f[1];
+  } else {
+    uint32_t r[4];
+    d_philox(seed, op.slot, p, 4, r);
+    const float rad = sqrtf(-2.f * __logf(((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f)));
+    col = rad * cospif(2.f * d_unit(r[1]));
+    lum = d_poisson(__fmul_rn(std_l, op.f[1]), d_unit(r[2]));
+  }
+  float hue = fmodf(__fadd_rn(h, __fmul_rn(col, op.f[0])), 360.f);  // np.mod(x, 360): sign of the divisor
+  if (hue < 0.f) hue += 360.f;
+  l = __fadd_rn(l, __fmul_rn(__fdiv_rn(lum, 255.f), __fsub_rn(1.f, l)));
+  d_hls2rgb(hue, l, s, &rgb[0], &rgb[1], &rgb[2]);
+#pragma unroll
+  for (int c = 0; c < 3; c++) rgb[c] = dclip01(rgb[c]);
 }
 
 __global__ void k_det_rgba(const uint8_t* __restrict__ planes, int pitch, const float* __restrict__ mask, uint32_t* __restrict__ rgba,
@@ -295,6 +395,7 @@ struct DetLaunch {
   const int32_t* bg_hw;
   const float* src;   // scratch written by the previous pass  [n,S,S,3] float32
   float* dst;         // scratch for the next pass
+  float* stats;       // [n][kDetMaxBlur + 1]: std of the HLS L channel of `src`, for scenes whose boundary op is ISONoise
   void* out;
   int out_dtype;
   const uint32_t* fields;
@@ -335,6 +436,40 @@ __device__ __forceinline__ void det_store(const DetLaunch& L, int s, int S_h, in
   }
 }
 
+// cv2.meanStdDev(HLS image)[1] for the scenes of pass `L.pass` whose boundary op is ISONoise: population standard deviation of
+// the L channel ((max + min) / 2 of RGB) over the previous pass's image, accumulated in double like cv2.  One CTA per scene.
+__global__ void __launch_bounds__(1024) k_det_stats(DetLaunch L, int S_h, int S_w) {
+  __shared__ double red[2][32];
+  const int li = blockIdx.x;
+  if (li >= L.pass_count[L.pass]) return;
+  const int s = L.pass_list[(size_t)L.pass * L.n + li];
+  const DetParams& P = L.params[s];
+  int seen = 0, code = MTGV_PH_NONE;
+  for (int k = 0; k < P.n_prog; k++)
+    if (det_is_boundary(P.prog[k].code) && ++seen == L.pass) { code = P.prog[k].code; break; }
+  if (code != MTGV_PH_ISO_NOISE) return;
+  const float* img = L.src + (size_t)s * S_h * S_w * 3;
+  const int n = S_h * S_w;
+  double sum = 0.0, sq = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float r = img[3 * (size_t)i], g = img[3 * (size_t)i + 1], b = img[3 * (size_t)i + 2];
+    const double l = (double)((fmaxf(r, fmaxf(g, b)) + fminf(r, fminf(g, b))) * 0.5f);
+    sum += l; sq += l * l;
+  }
+  for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sum; red[1][threadIdx.x >> 5] = sq; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    sum = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.0;
+    sq = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    if (threadIdx.x == 0) {
+      const double mean = sum / n, var = sq / n - mean * mean;
+      L.stats[(size_t)s * (kDetMaxBlur + 1) + L.pass] = (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+  }
+}
+
 #ifndef MTGV_DET_BLOCKS
 #define MTGV_DET_BLOCKS 4  // 64 registers per thread: the pixel walk is latency-bound, occupancy pays (measured 2 -> 4: +18 %)
 #endif
@@ -359,11 +494,11 @@ __global__ void __launch_bounds__(kDetBW * kDetBH, MTGV_DET_BLOCKS) k_det_pixels
       if (L.pass > 0) {
         first = P.n_prog;
         for (int k = 0; k < P.n_prog; k++)
-          if (P.prog[k].code == MTGV_PH_GAUSS_BLUR && ++seen == L.pass) { first = k + 1; blur_idx = k; break; }
+          if (det_is_boundary(P.prog[k].code) && ++seen == L.pass) { first = k + 1; blur_idx = k; break; }
       }
       int last = P.n_prog, has_cards = 0;
       for (int k = first; k < P.n_prog; k++) {
-        if (P.prog[k].code == MTGV_PH_GAUSS_BLUR) { last = k; break; }
+        if (det_is_boundary(P.prog[k].code)) { last = k; break; }
         has_cards |= P.prog[k].code == kPhCards;
       }
       T.first = first; T.last = last; T.blur_idx = blur_idx; T.is_final = last == P.n_prog; T.has_cards = has_cards;
@@ -427,38 +562,101 @@ __global__ void __launch_bounds__(kDetBW * kDetBH, MTGV_DET_BLOCKS) k_det_pixels
         for (int c = 0; c < 3; c++) rgb[i][c] = d_bilinear(v[0][c], v[1][c], v[2][c], v[3][c], X & 31, Y & 31);
       }
     } else {
-      // GaussianBlur that ended the previous segment: separable, BORDER_REFLECT_101, symmetric pairing
+      // the boundary op that ended the previous segment, evaluated over this tile from the previous pass's image
       const DetPhotoX& bl = T.prog[T.blur_idx];
-      const int r = bl.i[0] / 2;
-      const int hw = kDetTW + 2 * r, hh = kDetTH + 2 * r;
       const float* img = L.src + (size_t)s * S_h * S_w * 3;
-      for (int k = tid; k < hw * hh; k += nt) {
-        int yy = ty0 - r + k / hw, xx = tx0 - r + k % hw;
-        while (yy < 0 || yy >= S_h) yy = yy < 0 ? -yy : 2 * S_h - 2 - yy;  // reflect101
-        while (xx < 0 || xx >= S_w) xx = xx < 0 ? -xx : 2 * S_w - 2 - xx;
-        const float* p = img + ((size_t)yy * S_w + xx) * 3;
-        T.halo[3 * k] = p[0]; T.halo[3 * k + 1] = p[1]; T.halo[3 * k + 2] = p[2];
-      }
-      __syncthreads();
-      for (int k = tid; k < hh * kDetTW; k += nt) {
-        const int yy = k / kDetTW, xx = k % kDetTW;
-        const float* c0 = T.halo + (yy * hw + xx + r) * 3;
+      if (bl.code == MTGV_PH_ISO_NOISE) {
+        const float std_l = L.stats[(size_t)s * (kDetMaxBlur + 1) + L.pass];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          float acc = c0[c] * bl.k[0];
-          for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j] + c0[c + 3 * j]) * bl.k[j];
-          T.hrow[3 * k + c] = acc;
+        for (int i = 0; i < kDetRows; i++) {
+          const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
+          rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
+          if (x >= S_w || y >= S_h) continue;
+          const float* p = img + ((size_t)y * S_w + x) * 3;
+          rgb[i][0] = p[0]; rgb[i][1] = p[1]; rgb[i][2] = p[2];
+          d_iso_point(bl, rgb[i], y, x, S_w, T.seed, L.fields, std_l);
         }
-      }
-      __syncthreads();
+      } else {
+        const int r = bl.i[0] / 2;
+        const int hw = kDetTW + 2 * r, hh = kDetTH + 2 * r;
+        const bool median = bl.code == MTGV_PH_MEDIAN_BLUR;
+        for (int k = tid; k < hw * hh; k += nt) {
+          int yy = ty0 - r + k / hw, xx = tx0 - r + k % hw;
+          if (median) {  // cv2.medianBlur: BORDER_REPLICATE; the image as uint8 = rint(clip(x) * 255)
+            yy = yy < 0 ? 0 : (yy >= S_h ? S_h - 1 : yy);
+            xx = xx < 0 ? 0 : (xx >= S_w ? S_w - 1 : xx);
+          } else {
+            while (yy < 0 || yy >= S_h) yy = yy < 0 ? -yy : 2 * S_h - 2 - yy;  // reflect101
+            while (xx < 0 || xx >= S_w) xx = xx < 0 ? -xx : 2 * S_w - 2 - xx;
+          }
+          const float* p = img + ((size_t)yy * S_w + xx) * 3;
+          if (median) {
+            T.halo[3 * k] = rintf(dclip01(p[0]) * 255.f); T.halo[3 * k + 1] = rintf(dclip01(p[1]) * 255.f); T.halo[3 * k + 2] = rintf(dclip01(p[2]) * 255.f);
+          } else {
+            T.halo[3 * k] = p[0]; T.halo[3 * k + 1] = p[1]; T.halo[3 * k + 2] = p[2];
+          }
+        }
+        __syncthreads();
+        if (bl.code == MTGV_PH_GAUSS_BLUR) {
+          // GaussianBlur: separable, BORDER_REFLECT_101, symmetric pairing
+          for (int k = tid; k < hh * kDetTW; k += nt) {
+            const int yy = k / kDetTW, xx = k % kDetTW;
+            const float* c0 = T.halo + (yy * hw + xx + r) * 3;
 #pragma unroll
-      for (int i = 0; i < kDetRows; i++) {
-        const float* c0 = T.hrow + ((threadIdx.y + i * kDetBH + r) * kDetTW + threadIdx.x) * 3;
+            for (int c = 0; c < 3; c++) {
+              float acc = c0[c] * bl.k[0];
+              for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j] + c0[c + 3 * j]) * bl.k[j];
+              T.hrow[3 * k + c] = acc;
+            }
+          }
+          __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          float acc = c0[c] * bl.k[0];
-          for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j * kDetTW] + c0[c + 3 * j * kDetTW]) * bl.k[j];
-          rgb[i][c] = acc;
+          for (int i = 0; i < kDetRows; i++) {
+            const float* c0 = T.hrow + ((threadIdx.y + i * kDetBH + r) * kDetTW + threadIdx.x) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              float acc = c0[c] * bl.k[0];
+              for (int j = 1; j <= r; j++) acc += (c0[c - 3 * j * kDetTW] + c0[c + 3 * j * kDetTW]) * bl.k[j];
+              rgb[i][c] = acc;
+            }
+          }
+        } else if (median) {
+          // median of the ksize x ksize window per channel: smallest v with #(values <= v) > n / 2, found by bisection on the byte
+          const int ks = bl.i[0], need = (ks * ks) / 2 + 1;
+#pragma unroll
+          for (int i = 0; i < kDetRows; i++) {
+            const float* c0 = T.halo + ((threadIdx.y + i * kDetBH) * hw + threadIdx.x) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              int lo = 0, hi = 255;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const float fm = (float)mid;
+                int cnt = 0;
+                for (int dy = 0; dy < ks; dy++)
+                  for (int dx = 0; dx < ks; dx++) cnt += c0[(dy * hw + dx) * 3 + c] <= fm;
+                if (cnt >= need) hi = mid; else lo = mid + 1;
+              }
+              rgb[i][c] = d_u8_over_255((uint32_t)lo);  // np.divide(u8, 255.0, dtype=float32)
+            }
+          }
+        } else {
+          // MotionBlur: cv2.filter2D (correlation, anchor at the centre) with the normalised line kernel
+          const int ks = bl.i[0];
+          const float wgt = bl.f[0];
+#pragma unroll
+          for (int i = 0; i < kDetRows; i++) {
+            const float* c0 = T.halo + ((threadIdx.y + i * kDetBH) * hw + threadIdx.x) * 3;
+            float acc[3] = {0.f, 0.f, 0.f};
+            for (int b = 0; b < ks * ks; b++) {
+              if (!((bl.i[1 + (b >> 5)] >> (b & 31)) & 1)) continue;
+              const int dy = b / ks, dx = b - dy * ks;
+              const float* q = c0 + (dy * hw + dx) * 3;
+#pragma unroll
+              for (int c = 0; c < 3; c++) acc[c] = __fadd_rn(acc[c], __fmul_rn(q[c], wgt));
+            }
+            rgb[i][0] = acc[0]; rgb[i][1] = acc[1]; rgb[i][2] = acc[2];
+          }
         }
       }
     }
@@ -604,18 +802,40 @@ __device__ void ph_perm(DRng& r, int* idx, int n) {
   for (int i = 0; i < n; i++) idx[i] = i;
   for (int i = n - 1; i >= 1; i--) { int j = r.below(i + 1); int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
 }
-// one_of(noise family) / one_of(blur family): children outside the north-star subset are drawn and skipped
+// one_of(noise family) / one_of(blur family) of get_bg_transform (od_datasets.py:443-457); GlassBlur is drawn and skipped
 __device__ int ph_noise_family(DRng& r, mtgv_photo_op* o, double p) {
   const int c = r.below(3);
   if (c == 0) return ph_noise(r, o, p, 0.2);
-  r.uniform();
-  return 0;
+  if (!(r.uniform() < p)) return 0;
+  if (c == 1) {  // ISONoise(color_shift=(0.01, 0.4)), default intensity=(0.1, 0.5)
+    ph_init(o, MTGV_PH_ISO_NOISE);
+    o->d[0] = r.uniform(0.01, 0.4); o->d[1] = r.uniform(0.1, 0.5);
+  } else {       // ShotNoise(scale_range=(0.1, 0.3))
+    ph_init(o, MTGV_PH_SHOT_NOISE);
+    o->d[0] = r.uniform(0.1, 0.3);
+  }
+  return 1;
 }
 __device__ int ph_blur_family(DRng& r, mtgv_photo_op* o, double p) {
   const int c = r.below(5);
   if (c == 0) return ph_blur(r, o, p, 3.0);
-  r.uniform();
-  return 0;
+  if (c == 4) { r.uniform(); return 0; }  // GlassBlur(p * 2 / 3): not built
+  if (!(r.uniform() < p)) return 0;
+  if (c == 1) {  // MedianBlur(blur_limit=(3, 7))
+    ph_init(o, MTGV_PH_MEDIAN_BLUR);
+    o->i[0] = 3 + 2 * r.below(3);
+    return 1;
+  }
+  // MotionBlur(blur_limit=(3, 11)), twice in the family
+  ph_init(o, MTGV_PH_MOTION_BLUR);
+  const int ks = 3 + 2 * r.below(5);
+  const int x1 = r.below(ks), x2 = r.below(ks);
+  int y1, y2;
+  if (x1 == x2) { y1 = r.below(ks); y2 = r.below(ks - 1); y2 += y2 >= y1; }
+  else { y1 = r.below(ks); y2 = r.below(ks); }
+  o->i[0] = ks;
+  det_line_mask(ks, x1, y1, x2, y2, &o->i[1]);
+  return 1;
 }
 
 // Gen._get_bg_ds + ran_path (od_datasets.py:656-672): the dataset with probability p, then an image uniformly inside it
@@ -862,9 +1082,10 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
     d->scratch_cap = chunk * per;
   }
   if (chunk > d->list_cap) {
-    cudaFree(d->lists);
-    d->lists = nullptr; d->list_cap = 0;
+    cudaFree(d->lists); cudaFree(d->stats);
+    d->lists = nullptr; d->stats = nullptr; d->list_cap = 0;
     MTGV_CUDA_OK(ctx, cudaMalloc(&d->lists, (size_t)(kDetMaxBlur + 1) * (chunk + 1) * 4));
+    MTGV_CUDA_OK(ctx, cudaMalloc(&d->stats, (size_t)(kDetMaxBlur + 1) * chunk * 4));
     d->list_cap = chunk;
   }
   // (re)build detection's RGBA card copy when the pool changed since the last batch
@@ -909,6 +1130,13 @@ int mtgv_det_batch(mtgv_ctx* ctx, const void* params, int n, void* images, int o
       L.src = pass > 0 ? d->scratch[(pass - 1) & 1] : nullptr;
       L.dst = d->scratch[pass & 1];
       L.out = (char*)images + base * per * elem; L.out_dtype = out_dtype; L.fields = (const uint32_t*)fields;
+      L.stats = d->stats;
+      if (pass > 0) {
+        // image statistics for ISONoise boundaries: one CTA per scene of the chunk; it leaves at once when it is beyond the
+        // pass's list (whose length lives on the device) or the scene's boundary op is something else
+        k_det_stats<<<m, 1024, 0, st>>>(L, S_h, S_w);
+        ctx->launches++;
+      }
       long long want = (long long)m * tiles;
       long long cap = (long long)ctx->sm_count * blocks_per_sm * 4;
       int grid = (int)(want < cap ? want : cap);

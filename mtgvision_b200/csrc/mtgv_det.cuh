@@ -16,12 +16,42 @@ namespace mtgv {
 constexpr int kDetProgMax = MTGV_DET_MAX_PRE + MTGV_DET_MAX_POST + 1;
 constexpr int kPhCards = 100;  // marker in the scene program: composite the placed cards here
 constexpr int kBlurHalfMax = 10;  // sigma <= 3 -> ksize <= 19
-constexpr int kDetMaxBlur = 3;    // Gaussian blurs per scene program (one pixel pass each)
+// "Boundary" ops need the whole image of the previous step (neighbourhoods: Gaussian / median / motion blur; image
+// statistic: ISONoise): the scene program is cut there and continues in another pixel pass over a float32 scratch image.
+// The reference graphs hold at most 6 of them: one blur in bg_light, two noise families (ISONoise) and two blur families.
+constexpr int kDetMaxBlur = 6;
+
+MTGV_HD bool det_is_boundary(int code) {
+  return code == MTGV_PH_GAUSS_BLUR || code == MTGV_PH_MEDIAN_BLUR || code == MTGV_PH_MOTION_BLUR || code == MTGV_PH_ISO_NOISE;
+}
+
+// cv2.line(kernel, (x1,y1), (x2,y2), 1, thickness=1) on a ks x ks kernel as a bit mask (bit y*ks + x): cv::LineIterator,
+// 8-connected, left to right (drawing.cpp Line()): the endpoints are swapped when x2 < x1, the longer axis advances one cell
+// per point and the other whenever the error term err = major - 2*minor has gone negative (checked BEFORE it is updated).
+MTGV_HD void det_line_mask(int ks, int x1, int y1, int x2, int y2, int32_t* words) {
+  for (int k = 0; k < 4; k++) words[k] = 0;
+  if (x2 < x1) { int t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+  int dx = x2 - x1, dy = y2 - y1;
+  const int sy = dy < 0 ? -1 : 1;
+  dy = dy < 0 ? -dy : dy;
+  const bool steep = dy > dx;
+  const int major = steep ? dy : dx, minor = steep ? dx : dy;
+  int err = major - 2 * minor, x = x1, y = y1;
+  for (int i = 0; i <= major; i++) {
+    const int b = y * ks + x;
+    words[b >> 5] |= (int32_t)(1u << (b & 31));
+    const bool both = err < 0;
+    err += both ? 2 * major - 2 * minor : -2 * minor;
+    if (steep) { y += sy; if (both) x += 1; }
+    else { x += 1; if (both) y += sy; }
+  }
+}
 
 struct DetPhotoX {
   int32_t code;
-  int32_t i[5];   // ERASE: top,left,h,w,fill   BLUR: i[0] = ksize
-  float f[4];     // RBC: alpha,beta   HSV: hue, sat/255, val/255   NOISE: sigma   ERASE: colour
+  int32_t i[5];   // ERASE: top,left,h,w,fill   BLUR / MEDIAN: i[0] = ksize   MOTION: i[0] = ksize, i[1..4] = kernel bit mask
+  float f[4];     // RBC: alpha,beta   HSV: hue, sat/255, val/255   NOISE: sigma   ERASE: colour   ISO: hue sigma, intensity * 255
+                  // SHOT: scale, scale * 1e-6   MOTION: 1 / popcount(mask)
   float k[kBlurHalfMax];  // BLUR: k[0] centre weight, k[j] weight at +-j
   int32_t slot, _pad;
   int64_t field;
@@ -249,6 +279,32 @@ MTGV_HDN bool det_expand_photo(const mtgv_photo_op* t, int slot, DetPhotoX* o) {
       for (int k = 0; k < 5; k++) o->i[k] = t->i[k];
       for (int k = 0; k < 3; k++) o->f[k] = t->i[4] == 2 ? 1.f : (t->i[4] == 3 ? 0.f : (float)t->d[k]);
       return true;
+    case MTGV_PH_ISO_NOISE:
+      o->code = MTGV_PH_ISO_NOISE;
+      o->f[0] = (float)MTGV_DMUL(MTGV_DMUL(t->d[0], 360.0), t->d[1]);  // np.float32(color_shift * 360.0 * intensity)
+      o->f[1] = (float)MTGV_DMUL(t->d[1], 255.0);                      // Poisson rate = std(L) * intensity * 255
+      return true;
+    case MTGV_PH_SHOT_NOISE:
+      if (!(t->d[0] > 0.0)) return false;
+      o->code = MTGV_PH_SHOT_NOISE;
+      o->f[0] = (float)t->d[0];
+      return true;
+    case MTGV_PH_MEDIAN_BLUR:
+      if (t->i[0] != 3 && t->i[0] != 5 && t->i[0] != 7) return false;
+      o->code = MTGV_PH_MEDIAN_BLUR;
+      o->i[0] = t->i[0];
+      return true;
+    case MTGV_PH_MOTION_BLUR: {
+      const int ks = t->i[0];
+      if (ks < 3 || ks > 11 || !(ks & 1)) return false;
+      int cnt = 0;
+      for (int b = 0; b < ks * ks; b++) cnt += (t->i[1 + (b >> 5)] >> (b & 31)) & 1;
+      if (cnt == 0) return false;
+      o->code = MTGV_PH_MOTION_BLUR;
+      for (int k = 0; k < 5; k++) o->i[k] = t->i[k];
+      o->f[0] = 1.f / (float)cnt;  // kernel.astype(float32) / float32(sum): every set cell holds this weight
+      return true;
+    }
     default:
       return false;
   }
@@ -358,7 +414,7 @@ MTGV_HDN int det_emit_program(const mtgv_det_tape* t, const mtgv_det_config* cfg
       if (det_expand_photo(&t->post[k], 8 + k, &P->prog[n])) n++;
   P->n_prog = n;
   int nb = 0;
-  for (int k = 0; k < n; k++) nb += P->prog[k].code == MTGV_PH_GAUSS_BLUR;
+  for (int k = 0; k < n; k++) nb += det_is_boundary(P->prog[k].code);
   P->n_blur = nb;
   if (nb > kDetMaxBlur) return P->status = MTGV_ERR_LIMIT;
   return 0;

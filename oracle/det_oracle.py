@@ -21,8 +21,10 @@ What is pinned and what is not:
     here and keeps private RNGs: `PARITY UNPINNED` - the parameter ranges and probabilities are
     the ones written at od_datasets.py:420-512, the per-op arithmetic follows albumentations'
     documented formulas on top of the cv2 kernels it delegates to, and the sampling order
-    defined here is OUR specification.  Ops outside the north-star subset (ISONoise, ShotNoise,
-    MedianBlur, MotionBlur, GlassBlur) are drawn but applied as identity (next).
+    defined here is OUR specification.  ISONoise, ShotNoise, MedianBlur and MotionBlur
+    are restated the same way - their inner kernels (cv2.cvtColor RGB<->HLS, cv2.meanStdDev, cv2.pow,
+    cv2.medianBlur, cv2.line + cv2.filter2D) are the real cv2 calls; GlassBlur is drawn but applied
+    as identity.
   * the seg-kind keypoint polygon comes from a GEOS difference whose vertex order is
     GEOS-defined: `PARITY UNPINNED` - we start at (0,0) in the card box's own orientation.
 """
@@ -218,6 +220,7 @@ def placement_visible(shape: CardShape, S_hw, existing: list, min_visible: float
 # --------------------------------------------------------------------------- #
 
 PH_RBC, PH_HSV, PH_GAUSS_NOISE, PH_GAUSS_BLUR, PH_ERASE, PH_UNSUPPORTED = 1, 2, 3, 4, 5, 6
+PH_ISO_NOISE, PH_SHOT_NOISE, PH_MEDIAN_BLUR, PH_MOTION_BLUR = 7, 8, 9, 10  # SURVEY 8f.3; GlassBlur stays PH_UNSUPPORTED
 FILL_RANDOM, FILL_RANDOM_UNIFORM, FILL_ONE, FILL_ZERO = 0, 1, 2, 3
 
 
@@ -247,6 +250,44 @@ def draw_gauss_noise(std_range, hw):
 
 def draw_gauss_blur(sigma_limit):
     return {"ph": PH_GAUSS_BLUR, "sigma": np.random.uniform(*sigma_limit)}
+
+
+def draw_iso_noise(color_shift, intensity=(0.1, 0.5)):
+    """A.ISONoise(color_shift=(0.01, 0.4)) with its default intensity=(0.1, 0.5).  The noise fields depend on the image
+    (Poisson rate from the luminance spread), so they are drawn when the op is applied and recorded into this dict."""
+    return {"ph": PH_ISO_NOISE, "color_shift": np.random.uniform(*color_shift), "intensity": np.random.uniform(*intensity)}
+
+
+def draw_shot_noise(scale_range):
+    """A.ShotNoise(scale_range=(0.1, 0.3)); the Poisson counts are drawn on apply (rate = linearised image / scale)."""
+    return {"ph": PH_SHOT_NOISE, "scale": np.random.uniform(*scale_range)}
+
+
+def draw_median_blur(blur_limit):
+    ks = list(range(blur_limit[0] | 1, blur_limit[1] + 1, 2))
+    return {"ph": PH_MEDIAN_BLUR, "ksize": int(ks[int(np.random.randint(len(ks)))])}
+
+
+def motion_kernel_mask(ksize, x1, y1, x2, y2):
+    k = np.zeros((ksize, ksize), dtype=np.uint8)
+    cv2.line(k, (int(x1), int(y1)), (int(x2), int(y2)), 1, thickness=1)
+    return k
+
+
+def draw_motion_blur(blur_limit):
+    """A.MotionBlur(blur_limit=(3, 11)), allow_shifted: a one-pixel line between two random cells of a ksize x ksize
+    kernel (cv2.line), normalised.  When both x coordinates coincide the y pair is drawn distinct, so the line never
+    degenerates to a point."""
+    ks = list(range(blur_limit[0] | 1, blur_limit[1] + 1, 2))
+    ksize = int(ks[int(np.random.randint(len(ks)))])
+    x1, x2 = int(np.random.randint(ksize)), int(np.random.randint(ksize))
+    if x1 == x2:
+        y1 = int(np.random.randint(ksize))
+        y2 = int(np.random.randint(ksize - 1))
+        y2 += y2 >= y1
+    else:
+        y1, y2 = int(np.random.randint(ksize)), int(np.random.randint(ksize))
+    return {"ph": PH_MOTION_BLUR, "ksize": ksize, "pts": (x1, y1, x2, y2), "mask": motion_kernel_mask(ksize, x1, y1, x2, y2)}
 
 
 def draw_erase(scale, fill, hw):
@@ -297,7 +338,37 @@ def apply_photo(img: np.ndarray, rec: dict) -> np.ndarray:
         else:
             out[t : t + eh, l : l + ew] = 1.0 if rec["fill"] == FILL_ONE else 0.0
         return out
-    return img  # PH_UNSUPPORTED: drawn, applied as identity
+    if ph == PH_ISO_NOISE:
+        # camera-sensor noise in HLS space: hue jitter ~ N(0, color_shift * 360 * intensity), luminance lifted towards 1 by
+        # Poisson(std(L) * intensity * 255) / 255 of the remaining headroom (cv2.cvtColor RGB<->HLS on float32, cv2.meanStdDev)
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        hls = cv2.cvtColor(img, cv2.COLOR_RGB2HLS)
+        _, std = cv2.meanStdDev(hls)
+        if "lum" not in rec:
+            rec["lam"] = float(std[1, 0]) * rec["intensity"] * 255.0
+            rec["lum"] = np.random.poisson(rec["lam"], size=hls.shape[:2]).astype(np.float32)
+            rec["col"] = np.random.normal(0.0, 1.0, hls.shape[:2]).astype(np.float32)
+        hue = np.mod(hls[:, :, 0] + rec["col"] * np.float32(rec["color_shift"] * 360.0 * rec["intensity"]), np.float32(360))
+        lum = hls[:, :, 1] + (rec["lum"] / np.float32(255)) * (np.float32(1) - hls[:, :, 1])
+        out = cv2.cvtColor(cv2.merge([hue.astype(np.float32), lum.astype(np.float32), hls[:, :, 2]]), cv2.COLOR_HLS2RGB)
+        return np.clip(out, 0, 1).astype(np.float32)
+    if ph == PH_SHOT_NOISE:
+        # photon noise in linear light: gamma 2.2 -> Poisson((x + scale * 1e-6) / scale) * scale -> clip -> gamma 1 / 2.2
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        scale = np.float32(rec["scale"])
+        lin = cv2.pow(np.clip(img, 0, 1), 2.2)
+        lam = (lin + scale * np.float32(1e-6)) / scale
+        if "field" not in rec:
+            rec["field"] = np.random.poisson(lam).astype(np.float32)
+        return cv2.pow(np.clip(rec["field"] * scale, 0, 1), 1.0 / 2.2).astype(np.float32)
+    if ph == PH_MEDIAN_BLUR:
+        # cv2.medianBlur supports float32 only up to ksize 5: the image goes through uint8 (albumentations' uint8_io)
+        u8 = np.rint(np.clip(img, 0, 1) * np.float32(255)).astype(np.uint8)
+        return np.divide(cv2.medianBlur(np.ascontiguousarray(u8), rec["ksize"]), 255.0, dtype=np.float32)
+    if ph == PH_MOTION_BLUR:
+        k = rec["mask"].astype(np.float32) / np.float32(rec["mask"].sum())
+        return cv2.filter2D(np.ascontiguousarray(img, dtype=np.float32), -1, k)  # BORDER_REFLECT_101
+    return img  # PH_UNSUPPORTED (GlassBlur): drawn, applied as identity
 
 
 def _maybe(p: float, fn):
@@ -345,14 +416,14 @@ def draw_bg_transform(hw, extra=False, fill=None):
 
     def noise(p):
         return lambda: _one_of([lambda: _maybe(p, lambda: draw_gauss_noise((0.0, 0.2), hw)),
-                                lambda: _maybe(p, lambda: dict(unsupported, name="ISONoise")),
-                                lambda: _maybe(p, lambda: dict(unsupported, name="ShotNoise"))])
+                                lambda: _maybe(p, lambda: draw_iso_noise((0.01, 0.4))),
+                                lambda: _maybe(p, lambda: draw_shot_noise((0.1, 0.3)))])
 
     def blur(p):
         return lambda: _one_of([lambda: _maybe(p, lambda: draw_gauss_blur((0, 3))),
-                                lambda: _maybe(p, lambda: dict(unsupported, name="MedianBlur")),
-                                lambda: _maybe(p, lambda: dict(unsupported, name="MotionBlur")),
-                                lambda: _maybe(p, lambda: dict(unsupported, name="MotionBlur")),
+                                lambda: _maybe(p, lambda: draw_median_blur((3, 7))),
+                                lambda: _maybe(p, lambda: draw_motion_blur((3, 11))),
+                                lambda: _maybe(p, lambda: draw_motion_blur((3, 11))),
                                 lambda: _maybe(p / 3 * 2, lambda: dict(unsupported, name="GlassBlur"))])
 
     makers = [

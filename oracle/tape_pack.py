@@ -166,6 +166,28 @@ def _pack_photo(rec: dict, op, fields: FieldBuffer):
             op["d"][:3] = rec["color"]
         if "field" in rec:
             op["field"] = fields.add(rec["field"].astype(np.float32))
+    elif ph == DO.PH_ISO_NOISE:
+        op["code"] = abi.PH_ISO_NOISE
+        op["d"][0], op["d"][1] = rec["color_shift"], rec["intensity"]
+        if "lum" in rec:  # drawn when the oracle applied the op: [H,W,2] = (Poisson luminance counts, unit normals)
+            op["field"] = fields.add(np.stack([rec["lum"], rec["col"]], axis=-1).astype(np.float32))
+    elif ph == DO.PH_SHOT_NOISE:
+        op["code"] = abi.PH_SHOT_NOISE
+        op["d"][0] = rec["scale"]
+        if "field" in rec:
+            op["field"] = fields.add(rec["field"].astype(np.float32))
+    elif ph == DO.PH_MEDIAN_BLUR:
+        op["code"] = abi.PH_MEDIAN_BLUR
+        op["i"][0] = rec["ksize"]
+    elif ph == DO.PH_MOTION_BLUR:
+        op["code"] = abi.PH_MOTION_BLUR
+        op["i"][0] = rec["ksize"]
+        bits = np.flatnonzero(rec["mask"].reshape(-1))
+        words = [0, 0, 0, 0]
+        for b in bits:
+            words[b >> 5] |= 1 << (b & 31)
+        for k in range(4):
+            op["i"][1 + k] = words[k] - (1 << 32) if words[k] >= (1 << 31) else words[k]
     else:
         raise KeyError(ph)
 

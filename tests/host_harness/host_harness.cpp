@@ -58,6 +58,8 @@ void hh_round_rect_mask(int h, int w, int radius, float* out) { host_round_rect_
 
 int hh_det_params_size() { return (int)sizeof(DetParams); }
 
+void hh_line_mask(int ks, int x1, int y1, int x2, int y2, int32_t* words) { det_line_mask(ks, x1, y1, x2, y2, words); }
+
 // runs the placement / label warping of mtgv_det.cuh for n scenes on the host
 int hh_det_place(const mtgv_det_tape* tape, int n, const mtgv_det_config* cfg, int card_h, int card_w, int n_cards, int n_bgs,
                  const int32_t* bg_hw, void* params, int32_t* accepted, double* keypoints, int32_t* labels, int32_t* counts) {

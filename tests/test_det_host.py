@@ -137,3 +137,23 @@ def test_keypoint_warp_matches_numpy_matmul_on_this_host():
         out = np.zeros_like(pts)
         hh.hh_det_apply(vp(np.ascontiguousarray(M)), vp(pts), len(pts), vp(out))
         assert np.array_equal(out, DO.apply_transform_2d(pts, M))
+
+
+def test_motion_blur_line_mask_equals_cv2_line():
+    """The MotionBlur kernel of the production sampler (det_line_mask, mtgv_det.cuh) is cv2.line's pixel set (thickness 1,
+    8-connected) for EVERY pair of cells of every kernel size of A.MotionBlur(blur_limit=(3, 11)) (od_datasets.py:453-454)."""
+    hh = C.CDLL(HARNESS)
+    checked = 0
+    for ks in (3, 5, 7, 9, 11):
+        for x1 in range(ks):
+            for y1 in range(ks):
+                for x2 in range(ks):
+                    for y2 in range(ks):
+                        k = np.zeros((ks, ks), np.uint8)
+                        cv2.line(k, (x1, y1), (x2, y2), 1, thickness=1)
+                        w = np.zeros(4, np.int32)
+                        hh.hh_line_mask(ks, x1, y1, x2, y2, w.ctypes.data_as(C.c_void_p))
+                        bits = np.unpackbits(w.view(np.uint8), bitorder="little")[: ks * ks].reshape(ks, ks)
+                        assert np.array_equal(bits, k), (ks, x1, y1, x2, y2)
+                        checked += 1
+    assert checked == sum(ks ** 4 for ks in (3, 5, 7, 9, 11))

@@ -107,6 +107,69 @@ def test_device_transcendentals_change_nothing_discrete(env):
     assert np.abs(a[2][both] - b[2][both]).max() < 0.05  # keypoints agree to a few hundredths of a pixel
 
 
+def _scene_with_post(pool, bgs, seed, post_makers, **kw):
+    """A card scene of the oracle without photometrics, then a hand-picked post-augment list applied like
+    post_transform_bg (od_datasets.py:603-606); returns (tape with that list, final image)."""
+    random.seed(seed); np.random.seed(seed)
+    o = DO.DetOracle(list(pool.images), bgs, kind="obb", photometrics=False, **{**AUTHOR_RUN, **kw})
+    t = {}
+    img = o.generate(t)["image"]
+    post = [m() for m in post_makers]
+    for rec in post:
+        img = DO.apply_photo(img, rec)
+    t["post"] = post
+    return t, img
+
+
+def test_remaining_albumentations_ops_within_one_lsb(env):
+    """ISONoise, ShotNoise, MedianBlur, MotionBlur (od_datasets.py:443-457) - each alone and chained (three pass
+    boundaries + pointwise ops), noise fields injected from the oracle.  The oracle's inner kernels are the real cv2 calls
+    (cvtColor RGB<->HLS, meanStdDev, pow, medianBlur, line + filter2D)."""
+    pool, bgs, ctx = env
+    cases = {
+        "iso": [lambda: DO.draw_iso_noise((0.01, 0.4))],
+        "shot": [lambda: DO.draw_shot_noise((0.1, 0.3))],
+        "median3": [lambda: {"ph": DO.PH_MEDIAN_BLUR, "ksize": 3}],
+        "median5": [lambda: {"ph": DO.PH_MEDIAN_BLUR, "ksize": 5}],
+        "median7": [lambda: {"ph": DO.PH_MEDIAN_BLUR, "ksize": 7}],
+        "motion": [lambda: DO.draw_motion_blur((3, 11))],
+        "motion11": [lambda: {"ph": DO.PH_MOTION_BLUR, "ksize": 11, "pts": (0, 10, 10, 3), "mask": DO.motion_kernel_mask(11, 0, 10, 10, 3)}],
+        "chain": [lambda: DO.draw_motion_blur((3, 11)), lambda: DO.draw_rbc((-0.4, 0.4), (-0.5, 0.5)), lambda: DO.draw_iso_noise((0.01, 0.4)),
+                  lambda: {"ph": DO.PH_MEDIAN_BLUR, "ksize": 5}, lambda: DO.draw_shot_noise((0.1, 0.3))],
+        "chain2": [lambda: DO.draw_iso_noise((0.01, 0.4)), lambda: DO.draw_gauss_blur((1.0, 3.0)), lambda: DO.draw_iso_noise((0.01, 0.4)),
+                   lambda: DO.draw_motion_blur((3, 11))],
+    }
+    tapes, refs, names = [], [], []
+    for k, (name, makers) in enumerate(cases.items()):
+        for rep in range(2):
+            t, img = _scene_with_post(pool, bgs, 4000 + 10 * k + rep, makers)
+            tapes.append(t); refs.append(img); names.append(f"{name}/{rep}")
+    img, *_ = run_gpu(ctx, tapes, "obb", True)
+    for s, (name, ref) in enumerate(zip(names, refs)):
+        # (median: a 1e-7 difference in front of rint() moves a quantised neighbour by at most one byte value, and the median
+        # of values that each move by at most 1 moves by at most 1)
+        lsb, _ = PU.lsb_diff(img[s], ref)
+        assert lsb <= 1, f"{name}: max uint8 LSB error {lsb}"
+
+
+def test_remaining_albumentations_ops_production_fields(env):
+    """The same ops with DEVICE-generated fields (Philox): ISONoise's Poisson rate comes from the device's own cv2.meanStdDev
+    (k_det_stats), ShotNoise's from the pixel; the output distributions must match the oracle's numpy draws on the same scene."""
+    from tests.test_gpu_rng import ks_ok
+
+    pool, bgs, ctx = env
+    for name, maker in (("iso", lambda: DO.draw_iso_noise((0.2, 0.4), (0.3, 0.5))), ("shot", lambda: DO.draw_shot_noise((0.1, 0.3)))):
+        t, ref = _scene_with_post(pool, bgs, 4100, [maker])
+        for rec in t["post"]:  # forget the oracle's fields: the device draws its own
+            for k in ("lum", "col", "field"):
+                rec.pop(k, None)
+        img, *_ = run_gpu(ctx, [t], "obb", True)
+        for c in range(3):
+            ok, d, lim = ks_ok(img[0][::2, ::2, c].ravel(), ref[::2, ::2, c].ravel())
+            assert ok, f"{name} channel {c}: KS D {d:.4f} >= {lim:.4f}"
+        assert abs(float(img[0].mean()) - float(ref.mean())) < 2e-3, name
+
+
 def test_config4_1280_up_to_32_cards_matches_oracle(env):
     """BASELINE config 4 against the oracle (od_datasets.py:520-611): 1280x1280 scenes, num_cards_max=33 (up to 32 cards),
     photometrics on - the <= 32-card placement loop, the 1280^2 tile lists and the multi-pass blur scratch that 640^2 / 8
