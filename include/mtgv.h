@@ -297,8 +297,12 @@ typedef enum {
   MTGV_PH_SHOT_NOISE = 7,  /* ShotNoise: d[0] scale.  clip(Poisson((x^2.2 + d[0]*1e-6)/d[0]) * d[0])^(1/2.2);
                               field = Poisson counts [H,W,3] f32 or PHILOX                                            */
   MTGV_PH_MEDIAN_BLUR = 8, /* MedianBlur: i[0] = ksize in {3,5,7}; cv2.medianBlur of rint(255 x) as uint8 (edge replicated), / 255 */
-  MTGV_PH_MOTION_BLUR = 9  /* MotionBlur: i[0] = ksize (odd, <= 11), i[1..4] = bit mask of the line kernel (bit y*ksize+x);
+  MTGV_PH_MOTION_BLUR = 9, /* MotionBlur: i[0] = ksize (odd, <= 11), i[1..4] = bit mask of the line kernel (bit y*ksize+x);
                               cv2.filter2D with mask / popcount(mask), BORDER_REFLECT_101                              */
+  MTGV_PH_GLASS_BLUR = 10  /* GlassBlur (mode "fast"): d[0] sigma, i[0] max_delta (<= 8), i[1] iterations (<= 2): GaussianBlur(sigma),
+                              per iteration every interior pixel swaps with the neighbour at its (dy,dx) in [-max_delta, max_delta)
+                              (numpy's simultaneous fancy assignment, later index wins), GaussianBlur(sigma).
+                              field = int32 [(H-2md)*(W-2md)][iterations][2] in albumentations' pixel order, or PHILOX     */
 } mtgv_photo_code;
 
 typedef struct {

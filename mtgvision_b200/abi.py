@@ -79,7 +79,7 @@ class EncConfig(C.Structure):
 DET_MAX_CARDS, DET_MAX_ATTEMPTS, DET_MAX_KP, DET_MAX_KPOLY = 32, 10, 8, 3
 DET_MAX_PRE, DET_MAX_POST, DET_MAX_CARD_OPS = 4, 8, 3
 (PH_NONE, PH_RBC, PH_HSV, PH_GAUSS_NOISE, PH_GAUSS_BLUR, PH_ERASE, PH_ISO_NOISE, PH_SHOT_NOISE, PH_MEDIAN_BLUR,
- PH_MOTION_BLUR) = range(10)
+ PH_MOTION_BLUR, PH_GLASS_BLUR) = range(11)
 
 
 class PhotoOp(C.Structure):

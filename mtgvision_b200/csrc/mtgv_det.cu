@@ -565,7 +565,47 @@ __global__ void __launch_bounds__(kDetBW * kDetBH, MTGV_DET_BLOCKS) k_det_pixels
       // the boundary op that ended the previous segment, evaluated over this tile from the previous pass's image
       const DetPhotoX& bl = T.prog[T.blur_idx];
       const float* img = L.src + (size_t)s * S_h * S_w * 3;
-      if (bl.code == MTGV_PH_ISO_NOISE) {
+      if (bl.code == kPhGlassSwap) {
+        // one swap round of GlassBlur as a gather: a pixel that some interior pixel targets takes that pixel's value (the
+        // LAST such source in albumentations' order - columns descending, rows descending inside a column - wins); an
+        // untargeted interior pixel takes the value at its own (dy, dx); border pixels that nobody targets stay
+        const int md = bl.i[0], rnd = bl.i[1], rounds = bl.i[2];
+        const int nH = S_h - 2 * md;
+        const int32_t* dxy = bl.field != MTGV_FIELD_PHILOX ? (const int32_t*)(L.fields + bl.field) : nullptr;
+        auto draw = [&](int h, int w, int* dy, int* dx) {  // the (dy, dx) of interior pixel (h, w) in this round
+          const uint32_t n = (uint32_t)((S_w - md - w) * nH + (S_h - md - h));
+          if (dxy) {
+            *dy = dxy[((size_t)n * rounds + rnd) * 2]; *dx = dxy[((size_t)n * rounds + rnd) * 2 + 1];
+          } else {
+            uint32_t r[4];
+            d_philox(T.seed, bl.slot, n, 6 + rnd, r);
+            *dy = (int)(((uint64_t)r[0] * (uint32_t)(2 * md)) >> 32) - md;
+            *dx = (int)(((uint64_t)r[1] * (uint32_t)(2 * md)) >> 32) - md;
+          }
+        };
+#pragma unroll
+        for (int i = 0; i < kDetRows; i++) {
+          const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
+          rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
+          if (x >= S_w || y >= S_h) continue;
+          int sy = y, sx = x;
+          bool found = false;
+          // sources (h, w) = (y - dy, x - dx), dy, dx in [-md, md): smallest w first, then smallest h = last in index order
+          for (int w = max(x - md + 1, md + 1); w <= min(x + md, S_w - md) && !found; w++)
+            for (int h = max(y - md + 1, md + 1); h <= min(y + md, S_h - md); h++) {
+              int dy, dx;
+              draw(h, w, &dy, &dx);
+              if (h + dy == y && w + dx == x) { sy = h; sx = w; found = true; break; }
+            }
+          if (!found && y > md && y <= S_h - md && x > md && x <= S_w - md) {
+            int dy, dx;
+            draw(y, x, &dy, &dx);
+            sy = y + dy; sx = x + dx;
+          }
+          const float* p = img + ((size_t)sy * S_w + sx) * 3;
+          rgb[i][0] = p[0]; rgb[i][1] = p[1]; rgb[i][2] = p[2];
+        }
+      } else if (bl.code == MTGV_PH_ISO_NOISE) {
         const float std_l = L.stats[(size_t)s * (kDetMaxBlur + 1) + L.pass];
 #pragma unroll
         for (int i = 0; i < kDetRows; i++) {
@@ -802,7 +842,7 @@ __device__ void ph_perm(DRng& r, int* idx, int n) {
   for (int i = 0; i < n; i++) idx[i] = i;
   for (int i = n - 1; i >= 1; i--) { int j = r.below(i + 1); int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
 }
-// one_of(noise family) / one_of(blur family) of get_bg_transform (od_datasets.py:443-457); GlassBlur is drawn and skipped
+// one_of(noise family) / one_of(blur family) of get_bg_transform (od_datasets.py:443-457)
 __device__ int ph_noise_family(DRng& r, mtgv_photo_op* o, double p) {
   const int c = r.below(3);
   if (c == 0) return ph_noise(r, o, p, 0.2);
@@ -819,7 +859,12 @@ __device__ int ph_noise_family(DRng& r, mtgv_photo_op* o, double p) {
 __device__ int ph_blur_family(DRng& r, mtgv_photo_op* o, double p) {
   const int c = r.below(5);
   if (c == 0) return ph_blur(r, o, p, 3.0);
-  if (c == 4) { r.uniform(); return 0; }  // GlassBlur(p * 2 / 3): not built
+  if (c == 4) {  // GlassBlur(sigma=0.5, max_delta=4, iterations=2, p = p * 2 / 3)
+    if (!(r.uniform() < p / 3 * 2)) return 0;
+    ph_init(o, MTGV_PH_GLASS_BLUR);
+    o->d[0] = 0.5; o->i[0] = 4; o->i[1] = 2;
+    return 1;
+  }
   if (!(r.uniform() < p)) return 0;
   if (c == 1) {  // MedianBlur(blur_limit=(3, 7))
     ph_init(o, MTGV_PH_MEDIAN_BLUR);

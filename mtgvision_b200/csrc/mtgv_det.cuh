@@ -13,16 +13,20 @@
 
 namespace mtgv {
 
-constexpr int kDetProgMax = MTGV_DET_MAX_PRE + MTGV_DET_MAX_POST + 1;
-constexpr int kPhCards = 100;  // marker in the scene program: composite the placed cards here
+// a GlassBlur expands to blur, <= 2 swap rounds, blur (3 extra entries); the graphs hold at most two (one per blur family)
+constexpr int kDetProgMax = MTGV_DET_MAX_PRE + MTGV_DET_MAX_POST + 1 + 6;
+constexpr int kPhCards = 100;      // marker in the scene program: composite the placed cards here
+constexpr int kPhGlassSwap = 101;  // one swap round of a GlassBlur: i[0] = max_delta, i[1] = round, i[2] = rounds
 constexpr int kBlurHalfMax = 10;  // sigma <= 3 -> ksize <= 19
 // "Boundary" ops need the whole image of the previous step (neighbourhoods: Gaussian / median / motion blur; image
 // statistic: ISONoise): the scene program is cut there and continues in another pixel pass over a float32 scratch image.
-// The reference graphs hold at most 6 of them: one blur in bg_light, two noise families (ISONoise) and two blur families.
-constexpr int kDetMaxBlur = 6;
+// The reference graphs hold at most 11 of them: one blur in bg_light, two noise families (ISONoise) and two blur families
+// (a GlassBlur = blur + two swap rounds + blur = 4).
+constexpr int kDetMaxBlur = 11;
 
 MTGV_HD bool det_is_boundary(int code) {
-  return code == MTGV_PH_GAUSS_BLUR || code == MTGV_PH_MEDIAN_BLUR || code == MTGV_PH_MOTION_BLUR || code == MTGV_PH_ISO_NOISE;
+  return code == MTGV_PH_GAUSS_BLUR || code == MTGV_PH_MEDIAN_BLUR || code == MTGV_PH_MOTION_BLUR || code == MTGV_PH_ISO_NOISE ||
+         code == kPhGlassSwap;
 }
 
 // cv2.line(kernel, (x1,y1), (x2,y2), 1, thickness=1) on a ks x ks kernel as a bit mask (bit y*ks + x): cv::LineIterator,
@@ -400,18 +404,44 @@ MTGV_HDN void det_emit_card(const mtgv_det_tape* t, const mtgv_det_config* cfg, 
     if (cfg->photometrics && det_expand_photo(&c->photo[k], 32 + 4 * st->placed_src[pi] + k, &cx->ops[cx->n_ops])) cx->n_ops++;
 }
 
+// one tape op -> 0, 1 or (GlassBlur) up to 4 program entries at prog[n...]; returns the new length or -1 when the program is full
+MTGV_HDN int det_append_photo(const mtgv_photo_op* t, int slot, DetPhotoX* prog, int n) {
+  if (t->code == MTGV_PH_GLASS_BLUR) {
+    const int md = t->i[0], rounds = t->i[1];
+    if (!(t->d[0] > 0.0) || md < 1 || md > 8 || rounds < 0 || rounds > 2) return n;
+    if (n + 2 + rounds > kDetProgMax) return -1;
+    mtgv_photo_op b = *t;
+    b.code = MTGV_PH_GAUSS_BLUR;
+    b.field = MTGV_FIELD_PHILOX;
+    if (!det_expand_photo(&b, slot, &prog[n])) return n;
+    n++;
+    for (int r = 0; r < rounds; r++) {
+      det_photo_clear(&prog[n]);
+      prog[n].code = kPhGlassSwap;
+      prog[n].i[0] = md; prog[n].i[1] = r; prog[n].i[2] = rounds;
+      prog[n].slot = slot;
+      prog[n].field = t->field;
+      n++;
+    }
+    prog[n] = prog[n - 1 - rounds];  // the closing blur: same kernel
+    return n + 1;
+  }
+  if (n >= kDetProgMax) return -1;
+  return det_expand_photo(t, slot, &prog[n]) ? n + 1 : n;
+}
+
 // scene program: pre ops, cards, post ops
 MTGV_HDN int det_emit_program(const mtgv_det_tape* t, const mtgv_det_config* cfg, DetParams* P) {
   int n = 0;
   if (cfg->photometrics)
-    for (int k = 0; k < t->n_pre && k < MTGV_DET_MAX_PRE; k++)
-      if (det_expand_photo(&t->pre[k], k, &P->prog[n])) n++;
+    for (int k = 0; k < t->n_pre && k < MTGV_DET_MAX_PRE && n >= 0; k++) n = det_append_photo(&t->pre[k], k, P->prog, n);
+  if (n < 0 || n >= kDetProgMax) return P->status = MTGV_ERR_LIMIT;
   det_photo_clear(&P->prog[n]);
   P->prog[n].code = kPhCards;
   n++;
   if (cfg->photometrics)
-    for (int k = 0; k < t->n_post && k < MTGV_DET_MAX_POST; k++)
-      if (det_expand_photo(&t->post[k], 8 + k, &P->prog[n])) n++;
+    for (int k = 0; k < t->n_post && k < MTGV_DET_MAX_POST && n >= 0; k++) n = det_append_photo(&t->post[k], 8 + k, P->prog, n);
+  if (n < 0) return P->status = MTGV_ERR_LIMIT;
   P->n_prog = n;
   int nb = 0;
   for (int k = 0; k < n; k++) nb += det_is_boundary(P->prog[k].code);

@@ -23,8 +23,8 @@ What is pinned and what is not:
     documented formulas on top of the cv2 kernels it delegates to, and the sampling order
     defined here is OUR specification.  ISONoise, ShotNoise, MedianBlur and MotionBlur
     are restated the same way - their inner kernels (cv2.cvtColor RGB<->HLS, cv2.meanStdDev, cv2.pow,
-    cv2.medianBlur, cv2.line + cv2.filter2D) are the real cv2 calls; GlassBlur is drawn but applied
-    as identity.
+    cv2.medianBlur, cv2.line + cv2.filter2D, cv2.GaussianBlur) are the real cv2 calls, GlassBlur's
+    pixel shuffle is albumentations' numpy statement verbatim.
   * the seg-kind keypoint polygon comes from a GEOS difference whose vertex order is
     GEOS-defined: `PARITY UNPINNED` - we start at (0,0) in the card box's own orientation.
 """
@@ -220,7 +220,7 @@ def placement_visible(shape: CardShape, S_hw, existing: list, min_visible: float
 # --------------------------------------------------------------------------- #
 
 PH_RBC, PH_HSV, PH_GAUSS_NOISE, PH_GAUSS_BLUR, PH_ERASE, PH_UNSUPPORTED = 1, 2, 3, 4, 5, 6
-PH_ISO_NOISE, PH_SHOT_NOISE, PH_MEDIAN_BLUR, PH_MOTION_BLUR = 7, 8, 9, 10  # SURVEY 8f.3; GlassBlur stays PH_UNSUPPORTED
+PH_ISO_NOISE, PH_SHOT_NOISE, PH_MEDIAN_BLUR, PH_MOTION_BLUR, PH_GLASS_BLUR = 7, 8, 9, 10, 11
 FILL_RANDOM, FILL_RANDOM_UNIFORM, FILL_ONE, FILL_ZERO = 0, 1, 2, 3
 
 
@@ -288,6 +288,14 @@ def draw_motion_blur(blur_limit):
     else:
         y1, y2 = int(np.random.randint(ksize)), int(np.random.randint(ksize))
     return {"ph": PH_MOTION_BLUR, "ksize": ksize, "pts": (x1, y1, x2, y2), "mask": motion_kernel_mask(ksize, x1, y1, x2, y2)}
+
+
+def draw_glass_blur(hw, sigma=0.5, max_delta=4, iterations=2):
+    """A.GlassBlur(sigma=0.5, max_delta=4, iterations=2), mode "fast": one (dy, dx) in [-max_delta, max_delta) per interior
+    pixel and iteration (get_params_dependent_on_data)."""
+    n = (hw[0] - 2 * max_delta) * (hw[1] - 2 * max_delta)
+    dxy = np.random.randint(-max_delta, max_delta, size=(n, iterations, 2)).astype(np.int32)
+    return {"ph": PH_GLASS_BLUR, "sigma": sigma, "max_delta": max_delta, "iterations": iterations, "dxy": dxy}
 
 
 def draw_erase(scale, fill, hw):
@@ -368,7 +376,21 @@ def apply_photo(img: np.ndarray, rec: dict) -> np.ndarray:
     if ph == PH_MOTION_BLUR:
         k = rec["mask"].astype(np.float32) / np.float32(rec["mask"].sum())
         return cv2.filter2D(np.ascontiguousarray(img, dtype=np.float32), -1, k)  # BORDER_REFLECT_101
-    return img  # PH_UNSUPPORTED (GlassBlur): drawn, applied as identity
+    if ph == PH_GLASS_BLUR:
+        # albumentations' glass_blur, mode "fast": blur, `iterations` rounds of pixel swaps with a random neighbour (numpy's
+        # simultaneous fancy assignment: the gathers are taken first, then x[h,w] is written, then x[h+dy,w+dx] - where two
+        # sources target the same pixel the later index wins), blur again
+        md, sigma = rec["max_delta"], rec["sigma"]
+        x = cv2.GaussianBlur(np.array(img, dtype=np.float32), sigmaX=sigma, ksize=(0, 0))
+        hs = np.arange(img.shape[0] - md, md, -1)
+        ws = np.arange(img.shape[1] - md, md, -1)
+        h = np.tile(hs, ws.shape[0])
+        w = np.repeat(ws, hs.shape[0])
+        for i in range(rec["iterations"]):
+            dy, dx = rec["dxy"][:, i, 0], rec["dxy"][:, i, 1]
+            x[h, w], x[h + dy, w + dx] = x[h + dy, w + dx], x[h, w]
+        return cv2.GaussianBlur(x, sigmaX=sigma, ksize=(0, 0))
+    return img  # PH_UNSUPPORTED: drawn, applied as identity
 
 
 def _maybe(p: float, fn):
@@ -424,7 +446,7 @@ def draw_bg_transform(hw, extra=False, fill=None):
                                 lambda: _maybe(p, lambda: draw_median_blur((3, 7))),
                                 lambda: _maybe(p, lambda: draw_motion_blur((3, 11))),
                                 lambda: _maybe(p, lambda: draw_motion_blur((3, 11))),
-                                lambda: _maybe(p / 3 * 2, lambda: dict(unsupported, name="GlassBlur"))])
+                                lambda: _maybe(p / 3 * 2, lambda: draw_glass_blur(hw))])
 
     makers = [
         lambda: _maybe(0.5, lambda: draw_rbc((-0.4, 0.4) if not extra else (-0.7, 0.7), (-0.5, 0.5))),

@@ -188,6 +188,11 @@ def _pack_photo(rec: dict, op, fields: FieldBuffer):
             words[b >> 5] |= 1 << (b & 31)
         for k in range(4):
             op["i"][1 + k] = words[k] - (1 << 32) if words[k] >= (1 << 31) else words[k]
+    elif ph == DO.PH_GLASS_BLUR:
+        op["code"] = abi.PH_GLASS_BLUR
+        op["d"][0] = rec["sigma"]
+        op["i"][0], op["i"][1] = rec["max_delta"], rec["iterations"]
+        op["field"] = fields.add(np.ascontiguousarray(rec["dxy"], dtype=np.int32))
     else:
         raise KeyError(ph)
 

@@ -122,9 +122,9 @@ def _scene_with_post(pool, bgs, seed, post_makers, **kw):
 
 
 def test_remaining_albumentations_ops_within_one_lsb(env):
-    """ISONoise, ShotNoise, MedianBlur, MotionBlur (od_datasets.py:443-457) - each alone and chained (three pass
-    boundaries + pointwise ops), noise fields injected from the oracle.  The oracle's inner kernels are the real cv2 calls
-    (cvtColor RGB<->HLS, meanStdDev, pow, medianBlur, line + filter2D)."""
+    """ISONoise, ShotNoise, MedianBlur, MotionBlur, GlassBlur (od_datasets.py:443-457) - each alone and chained (up to
+    eight pass boundaries + pointwise ops), noise fields injected from the oracle.  The oracle's inner kernels are the real cv2
+    calls (cvtColor RGB<->HLS, meanStdDev, pow, medianBlur, line + filter2D, GaussianBlur); GlassBlur's shuffle is numpy's."""
     pool, bgs, ctx = env
     cases = {
         "iso": [lambda: DO.draw_iso_noise((0.01, 0.4))],
@@ -134,6 +134,8 @@ def test_remaining_albumentations_ops_within_one_lsb(env):
         "median7": [lambda: {"ph": DO.PH_MEDIAN_BLUR, "ksize": 7}],
         "motion": [lambda: DO.draw_motion_blur((3, 11))],
         "motion11": [lambda: {"ph": DO.PH_MOTION_BLUR, "ksize": 11, "pts": (0, 10, 10, 3), "mask": DO.motion_kernel_mask(11, 0, 10, 10, 3)}],
+        "glass": [lambda: DO.draw_glass_blur((640, 640))],
+        "glass_chain": [lambda: DO.draw_glass_blur((640, 640)), lambda: DO.draw_hsv((-30, 30), (-40, 40), (0, 0)), lambda: DO.draw_glass_blur((640, 640))],
         "chain": [lambda: DO.draw_motion_blur((3, 11)), lambda: DO.draw_rbc((-0.4, 0.4), (-0.5, 0.5)), lambda: DO.draw_iso_noise((0.01, 0.4)),
                   lambda: {"ph": DO.PH_MEDIAN_BLUR, "ksize": 5}, lambda: DO.draw_shot_noise((0.1, 0.3))],
         "chain2": [lambda: DO.draw_iso_noise((0.01, 0.4)), lambda: DO.draw_gauss_blur((1.0, 3.0)), lambda: DO.draw_iso_noise((0.01, 0.4)),
@@ -165,7 +167,8 @@ def test_remaining_albumentations_ops_production_fields(env):
                 rec.pop(k, None)
         img, *_ = run_gpu(ctx, [t], "obb", True)
         for c in range(3):
-            ok, d, lim = ks_ok(img[0][::2, ::2, c].ravel(), ref[::2, ::2, c].ravel())
+            # rounded: ShotNoise outputs are atoms (k * scale)^(1/2.2) that powf and cv2.pow place 1e-7 apart
+            ok, d, lim = ks_ok(np.round(img[0][::2, ::2, c].ravel(), 4), np.round(ref[::2, ::2, c].ravel(), 4))
             assert ok, f"{name} channel {c}: KS D {d:.4f} >= {lim:.4f}"
         assert abs(float(img[0].mean()) - float(ref.mean())) < 2e-3, name
 
