@@ -13,6 +13,8 @@
 //                 ping-pong through a float32 scratch image.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "mtgv_det.cuh"
 #include "mtgv_internal.cuh"
 #include "mtgv_persp.cuh"
@@ -436,6 +438,118 @@ __device__ __forceinline__ void det_store(const DetLaunch& L, int s, int S_h, in
   }
 }
 
+// cv2.medianBlur of the tile from the packed uint8 halo in T.halo (window origin = pixel): results to T.hrow[(ty*32+tx)*3+c]
+__device__ __noinline__ void det_median_tile(DetTileSmem& T, int ks, int hw) {
+          const uint2* H2 = reinterpret_cast<const uint2*>(T.halo);
+#pragma unroll
+          for (int i = 0; i < kDetRows; i++) {
+            const uint2* c0 = H2 + (threadIdx.y + i * kDetBH) * hw + threadIdx.x;
+            uint32_t med[3];
+            if (ks == 3) {
+              // 9 values per channel: the 19-exchange median network (Paeth), integer min / max
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                int v[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) {
+                  const uint2 e = c0[(q / 3) * hw + (q % 3)];
+                  v[q] = (int)(c == 0 ? (e.x & 0xFFFFu) : (c == 1 ? (e.x >> 16) : e.y));
+                }
+#define MTGV_CE(a, b) { const int lo_ = min(v[a], v[b]), hi_ = max(v[a], v[b]); v[a] = lo_; v[b] = hi_; }
+                MTGV_CE(1, 2) MTGV_CE(4, 5) MTGV_CE(7, 8) MTGV_CE(0, 1) MTGV_CE(3, 4) MTGV_CE(6, 7) MTGV_CE(1, 2) MTGV_CE(4, 5) MTGV_CE(7, 8)
+                MTGV_CE(0, 3) MTGV_CE(5, 8) MTGV_CE(4, 7) MTGV_CE(3, 6) MTGV_CE(1, 4) MTGV_CE(2, 5) MTGV_CE(4, 7) MTGV_CE(4, 2) MTGV_CE(6, 4) MTGV_CE(4, 2)
+#undef MTGV_CE
+                med[c] = (uint32_t)v[4];
+              }
+            } else {
+              // smallest v with #(values <= v) > n / 2 by bisection on the byte, three channels at once: with bit 8 of a lane set,
+              // (mid | 0x100) - x keeps that bit exactly when mid >= x, and the masked differences add up to the counts
+              const int need = (ks * ks) / 2 + 1;
+              int lo[3] = {0, 0, 0}, hi[3] = {255, 255, 255};
+#pragma unroll 1
+              for (int round = 0; round < 8; round++) {
+                const int m0 = (lo[0] + hi[0]) >> 1, m1 = (lo[1] + hi[1]) >> 1, m2 = (lo[2] + hi[2]) >> 1;
+                const uint32_t mrg = (uint32_t)m0 | ((uint32_t)m1 << 16) | 0x01000100u, mb = (uint32_t)m2 | 0x100u;
+                uint32_t arg = 0u, ab = 0u;
+                auto count = [&](auto KS) {  // window size as a compile-time constant: the element loop unrolls into plain loads
+                  constexpr int K = decltype(KS)::value;
+#pragma unroll
+                  for (int dy = 0; dy < K; dy++) {
+                    const uint2* row = c0 + dy * hw;
+#pragma unroll
+                    for (int dx = 0; dx < K; dx++) {
+                      const uint2 e = row[dx];
+                      arg += (mrg - e.x) & 0x01000100u;
+                      ab += (mb - e.y) & 0x100u;
+                    }
+                  }
+                };
+                if (ks == 5) count(std::integral_constant<int, 5>{}); else count(std::integral_constant<int, 7>{});
+                const int c0n = (int)((arg >> 8) & 0xFFu), c1n = (int)(arg >> 24), c2n = (int)(ab >> 8);
+                if (c0n >= need) hi[0] = m0; else lo[0] = m0 + 1;
+                if (c1n >= need) hi[1] = m1; else lo[1] = m1 + 1;
+                if (c2n >= need) hi[2] = m2; else lo[2] = m2 + 1;
+              }
+              med[0] = (uint32_t)lo[0]; med[1] = (uint32_t)lo[1]; med[2] = (uint32_t)lo[2];
+            }
+            float* o = T.hrow + ((threadIdx.y + i * kDetBH) * kDetTW + threadIdx.x) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) o[c] = d_u8_over_255(med[c]);  // np.divide(u8, 255.0, dtype=float32)
+          }
+}
+
+// one swap round of GlassBlur for the tile (see the call site): results to T.hrow[(ty*32+tx)*3+c]
+__device__ __noinline__ void det_glass_tile(DetTileSmem& T, const DetLaunch& L, const DetPhotoX& bl, const float* __restrict__ img, int S_h,
+                                            int S_w, int tx0, int ty0, int tid, int nt) {
+  const int md = bl.i[0], rnd = bl.i[1], rounds = bl.i[2];
+  const int nH = S_h - 2 * md;
+  const int32_t* dxy = bl.field != MTGV_FIELD_PHILOX ? (const int32_t*)(L.fields + bl.field) : nullptr;
+        // the draws of the tile and its halo, once: (dy + md) << 8 | (dx + md) per interior pixel, 0xFFFF outside the interior
+        const int thw = kDetTW + 2 * md, thh = kDetTH + 2 * md;
+        uint16_t* tab = reinterpret_cast<uint16_t*>(T.halo);
+        for (int k = tid; k < thw * thh; k += nt) {
+          const int h = ty0 - md + k / thw, w = tx0 - md + k % thw;
+          uint16_t e = 0xFFFFu;
+          if (h > md && h <= S_h - md && w > md && w <= S_w - md) {
+            const uint32_t n = (uint32_t)((S_w - md - w) * nH + (S_h - md - h));  // albumentations' pixel order: columns, then rows, descending
+            int dy, dx;
+            if (dxy) {
+              dy = dxy[((size_t)n * rounds + rnd) * 2]; dx = dxy[((size_t)n * rounds + rnd) * 2 + 1];
+            } else {
+              uint32_t r[4];
+              d_philox(T.seed, bl.slot, n, 6 + rnd, r);
+              dy = (int)(((uint64_t)r[0] * (uint32_t)(2 * md)) >> 32) - md;
+              dx = (int)(((uint64_t)r[1] * (uint32_t)(2 * md)) >> 32) - md;
+            }
+            e = (uint16_t)(((dy + md) << 8) | (dx + md));
+          }
+          tab[k] = e;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kDetRows; i++) {
+          const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
+          float* o = T.hrow + ((threadIdx.y + i * kDetBH) * kDetTW + threadIdx.x) * 3;
+          o[0] = o[1] = o[2] = 0.f;
+          if (x >= S_w || y >= S_h) continue;
+          const int ly = y - ty0 + md, lx = x - tx0 + md;  // this pixel in the table
+          int sy = y, sx = x;
+          bool found = false;
+          // sources (h, w) = (y + a, x + b), a, b in (-md, md], whose draw is (-a, -b): smallest w first, then smallest h = the
+          // last one in index order
+          for (int b = -md + 1; b <= md && !found; b++)
+            for (int a = -md + 1; a <= md; a++) {
+              if (tab[(ly + a) * thw + lx + b] == (uint16_t)(((md - a) << 8) | (md - b))) { sy = y + a; sx = x + b; found = true; break; }
+            }
+          if (!found) {
+            const uint16_t e = tab[ly * thw + lx];
+            if (e != 0xFFFFu) { sy = y + (int)(e >> 8) - md; sx = x + (int)(e & 0xFFu) - md; }
+          }
+          const float* p = img + ((size_t)sy * S_w + sx) * 3;
+          o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        }
+}
+
 // cv2.meanStdDev(HLS image)[1] for the scenes of pass `L.pass` whose boundary op is ISONoise: population standard deviation of
 // the L channel ((max + min) / 2 of RGB) over the previous pass's image, accumulated in double like cv2.  One CTA per scene.
 __global__ void __launch_bounds__(1024) k_det_stats(DetLaunch L, int S_h, int S_w) {
@@ -451,11 +565,20 @@ __global__ void __launch_bounds__(1024) k_det_stats(DetLaunch L, int S_h, int S_
   const float* img = L.src + (size_t)s * S_h * S_w * 3;
   const int n = S_h * S_w;
   double sum = 0.0, sq = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float r = img[3 * (size_t)i], g = img[3 * (size_t)i + 1], b = img[3 * (size_t)i + 2];
+  auto add = [&](float r, float g, float b) {
     const double l = (double)((fmaxf(r, fmaxf(g, b)) + fminf(r, fminf(g, b))) * 0.5f);
     sum += l; sq += l * l;
+  };
+  // four pixels = three 16-byte loads per iteration (the scratch image is 16-byte aligned per scene when S_h*S_w*3 is a
+  // multiple of 4; otherwise the scalar tail loop takes everything)
+  const bool vec = (((size_t)S_h * S_w * 3) & 3) == 0;
+  const int n4 = vec ? n >> 2 : 0;
+  const float4* img4 = reinterpret_cast<const float4*>(img);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 a = img4[3 * (size_t)i], b = img4[3 * (size_t)i + 1], c = img4[3 * (size_t)i + 2];
+    add(a.x, a.y, a.z); add(a.w, b.x, b.y); add(b.z, b.w, c.x); add(c.y, c.z, c.w);
   }
+  for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) add(img[3 * (size_t)i], img[3 * (size_t)i + 1], img[3 * (size_t)i + 2]);
   for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
   if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sum; red[1][threadIdx.x >> 5] = sq; }
   __syncthreads();
@@ -569,41 +692,11 @@ __global__ void __launch_bounds__(kDetBW * kDetBH, MTGV_DET_BLOCKS) k_det_pixels
         // one swap round of GlassBlur as a gather: a pixel that some interior pixel targets takes that pixel's value (the
         // LAST such source in albumentations' order - columns descending, rows descending inside a column - wins); an
         // untargeted interior pixel takes the value at its own (dy, dx); border pixels that nobody targets stay
-        const int md = bl.i[0], rnd = bl.i[1], rounds = bl.i[2];
-        const int nH = S_h - 2 * md;
-        const int32_t* dxy = bl.field != MTGV_FIELD_PHILOX ? (const int32_t*)(L.fields + bl.field) : nullptr;
-        auto draw = [&](int h, int w, int* dy, int* dx) {  // the (dy, dx) of interior pixel (h, w) in this round
-          const uint32_t n = (uint32_t)((S_w - md - w) * nH + (S_h - md - h));
-          if (dxy) {
-            *dy = dxy[((size_t)n * rounds + rnd) * 2]; *dx = dxy[((size_t)n * rounds + rnd) * 2 + 1];
-          } else {
-            uint32_t r[4];
-            d_philox(T.seed, bl.slot, n, 6 + rnd, r);
-            *dy = (int)(((uint64_t)r[0] * (uint32_t)(2 * md)) >> 32) - md;
-            *dx = (int)(((uint64_t)r[1] * (uint32_t)(2 * md)) >> 32) - md;
-          }
-        };
+        det_glass_tile(T, L, bl, img, S_h, S_w, tx0, ty0, tid, nt);  // out of line like the median; results through T.hrow
 #pragma unroll
         for (int i = 0; i < kDetRows; i++) {
-          const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y + i * kDetBH;
-          rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
-          if (x >= S_w || y >= S_h) continue;
-          int sy = y, sx = x;
-          bool found = false;
-          // sources (h, w) = (y - dy, x - dx), dy, dx in [-md, md): smallest w first, then smallest h = last in index order
-          for (int w = max(x - md + 1, md + 1); w <= min(x + md, S_w - md) && !found; w++)
-            for (int h = max(y - md + 1, md + 1); h <= min(y + md, S_h - md); h++) {
-              int dy, dx;
-              draw(h, w, &dy, &dx);
-              if (h + dy == y && w + dx == x) { sy = h; sx = w; found = true; break; }
-            }
-          if (!found && y > md && y <= S_h - md && x > md && x <= S_w - md) {
-            int dy, dx;
-            draw(y, x, &dy, &dx);
-            sy = y + dy; sx = x + dx;
-          }
-          const float* p = img + ((size_t)sy * S_w + sx) * 3;
-          rgb[i][0] = p[0]; rgb[i][1] = p[1]; rgb[i][2] = p[2];
+          const float* o = T.hrow + ((threadIdx.y + i * kDetBH) * kDetTW + threadIdx.x) * 3;
+          rgb[i][0] = o[0]; rgb[i][1] = o[1]; rgb[i][2] = o[2];
         }
       } else if (bl.code == MTGV_PH_ISO_NOISE) {
         const float std_l = L.stats[(size_t)s * (kDetMaxBlur + 1) + L.pass];
@@ -631,7 +724,9 @@ __global__ void __launch_bounds__(kDetBW * kDetBH, MTGV_DET_BLOCKS) k_det_pixels
           }
           const float* p = img + ((size_t)yy * S_w + xx) * 3;
           if (median) {
-            T.halo[3 * k] = rintf(dclip01(p[0]) * 255.f); T.halo[3 * k + 1] = rintf(dclip01(p[1]) * 255.f); T.halo[3 * k + 2] = rintf(dclip01(p[2]) * 255.f);
+            // bytes in 16-bit lanes: word 0 = R | G << 16, word 1 = B (one 8-byte load per window element, carry-free lane arithmetic)
+            const uint32_t r8 = (uint32_t)rintf(dclip01(p[0]) * 255.f), g8 = (uint32_t)rintf(dclip01(p[1]) * 255.f), b8 = (uint32_t)rintf(dclip01(p[2]) * 255.f);
+            reinterpret_cast<uint2*>(T.halo)[k] = make_uint2(r8 | (g8 << 16), b8);
           } else {
             T.halo[3 * k] = p[0]; T.halo[3 * k + 1] = p[1]; T.halo[3 * k + 2] = p[2];
           }
@@ -661,24 +756,11 @@ __global__ void __launch_bounds__(kDetBW * kDetBH, MTGV_DET_BLOCKS) k_det_pixels
             }
           }
         } else if (median) {
-          // median of the ksize x ksize window per channel: smallest v with #(values <= v) > n / 2, found by bisection on the byte
-          const int ks = bl.i[0], need = (ks * ks) / 2 + 1;
+          det_median_tile(T, bl.i[0], hw);  // rare and register-hungry: kept out of line, results come back through T.hrow
 #pragma unroll
           for (int i = 0; i < kDetRows; i++) {
-            const float* c0 = T.halo + ((threadIdx.y + i * kDetBH) * hw + threadIdx.x) * 3;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-              int lo = 0, hi = 255;
-              while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const float fm = (float)mid;
-                int cnt = 0;
-                for (int dy = 0; dy < ks; dy++)
-                  for (int dx = 0; dx < ks; dx++) cnt += c0[(dy * hw + dx) * 3 + c] <= fm;
-                if (cnt >= need) hi = mid; else lo = mid + 1;
-              }
-              rgb[i][c] = d_u8_over_255((uint32_t)lo);  // np.divide(u8, 255.0, dtype=float32)
-            }
+            const float* o = T.hrow + ((threadIdx.y + i * kDetBH) * kDetTW + threadIdx.x) * 3;
+            rgb[i][0] = o[0]; rgb[i][1] = o[1]; rgb[i][2] = o[2];
           }
         } else {
           // MotionBlur: cv2.filter2D (correlation, anchor at the centre) with the normalised line kernel
@@ -688,12 +770,16 @@ __global__ void __launch_bounds__(kDetBW * kDetBH, MTGV_DET_BLOCKS) k_det_pixels
           for (int i = 0; i < kDetRows; i++) {
             const float* c0 = T.halo + ((threadIdx.y + i * kDetBH) * hw + threadIdx.x) * 3;
             float acc[3] = {0.f, 0.f, 0.f};
-            for (int b = 0; b < ks * ks; b++) {
-              if (!((bl.i[1 + (b >> 5)] >> (b & 31)) & 1)) continue;
-              const int dy = b / ks, dx = b - dy * ks;
-              const float* q = c0 + (dy * hw + dx) * 3;
+            for (int wi = 0; wi < 4; wi++) {  // the set cells in row-major order (cv2.filter2D's coefficient order)
+              uint32_t bits = (uint32_t)bl.i[1 + wi];
+              while (bits) {
+                const int b = 32 * wi + __ffs((int)bits) - 1;
+                bits &= bits - 1;
+                const int dy = b / ks, dx = b - dy * ks;
+                const float* q = c0 + (dy * hw + dx) * 3;
 #pragma unroll
-              for (int c = 0; c < 3; c++) acc[c] = __fadd_rn(acc[c], __fmul_rn(q[c], wgt));
+                for (int c = 0; c < 3; c++) acc[c] = __fadd_rn(acc[c], __fmul_rn(q[c], wgt));
+              }
             }
             rgb[i][0] = acc[0]; rgb[i][1] = acc[1]; rgb[i][2] = acc[2];
           }
