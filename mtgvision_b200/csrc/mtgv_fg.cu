@@ -25,7 +25,43 @@ constexpr int kFgThreads = 256;
 constexpr int kFgWarps = kFgThreads / 32;
 constexpr int kFgRows = 32;  // max destination rows per item
 constexpr int kFgMaxOW = 256;
-constexpr int kFgPf = 4;     // source rows in flight per warp
+[[maybe_unused]] constexpr int kFgPf = 4;  // source rows in flight per warp (cp.async ring, MTGV_FG_BULK == 0)
+// MTGV_FG_BULK=1: row streaming through the TMA unit instead - one lane copies kFgStageRows whole source rows (contiguous in the
+// planar pool) with a single cp.async.bulk into a per-warp ring of kFgStages stages and arms the stage's mbarrier with the byte
+// count; the warp waits on the barrier's phase (UBLKCP + SYNCS in the SASS).  Built, parity-green (tests/test_gpu_encoder.py,
+// test_gpu_shapes.py incl. wide cards) and MEASURED on one B200 against the cp.async ring, pipeline ms per 1024 x-samples:
+// cp.async ring 4.304 | bulk 4 rows x 3 stages 4.323 | 4x2 4.321 | 2x4 4.349 | 8x3 4.503 | 16x2 4.486
+// (profiles/r02_ab_k_background_variants.txt).  The kernel is bound by its arithmetic (70 % issue utilisation), not by the row
+// loads; a 2 KB bulk copy per 4 rows and warp has more fixed latency than 31 lanes each posting one 16-byte cp.async.  The
+// cp.async ring stays the default.
+#ifndef MTGV_FG_BULK
+#define MTGV_FG_BULK 0
+#endif
+#ifndef MTGV_FG_STAGE_ROWS
+#define MTGV_FG_STAGE_ROWS 4
+#endif
+#ifndef MTGV_FG_STAGES
+#define MTGV_FG_STAGES 3
+#endif
+constexpr int kFgStageRows = MTGV_FG_STAGE_ROWS, kFgStages = MTGV_FG_STAGES;
+
+__device__ __forceinline__ void fg_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fg_bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void fg_mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok = 0;
+  for (int spin = 0; !ok; spin++) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    if (spin > (1 << 26)) __trap();  // a lost copy must not hang the GPU: fail the launch instead
+  }
+}
 
 struct FgGeom {  // the two INTER_AREA geometries of a batch: [0] virtual (whole card, padded), [1] cropped
   int src_h, src_w, rh, rw;
@@ -47,8 +83,8 @@ __device__ __forceinline__ float fg_byte(uint32_t w, int k) {  // exact u8 -> fl
 // read from the shared tables.
 template <int NCH, bool REGW>
 __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, int c, int part, int split, const FgRow* __restrict__ cols,
-                                        FgRow* rows, float* rowbuf, uint8_t* ring, const uint8_t* __restrict__ card_planes, int pitch,
-                                        float* __restrict__ fg_out, int s, int lane) {
+                                        FgRow* rows, float* rowbuf, uint8_t* ring, uint64_t* bars, unsigned& phases,
+                                        const uint8_t* __restrict__ card_planes, int pitch, float* __restrict__ fg_out, int s, int lane) {
   const int kind = sp->kind;
   const int src_h = sp->src_h, rh = sp->fg_rh, rw = sp->fg_rw;
   const int OH = sp->out_h, OW = sp->out_w, card_h = sp->card_h, card_w = sp->card_w;
@@ -70,6 +106,24 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
   const uint8_t* plane = card_planes + ((size_t)sp->card * 3 + c) * card_h * pitch;
   float* outp = fg_out + ((size_t)s * 3 + c) * OH * OW;
   const int sy_last = rows[r1 - r0 - 1].start + (rows[r1 - r0 - 1].n & 255) - 1;
+#if MTGV_FG_BULK
+  // Source rows are consumed in increasing order, kFgStageRows per ring stage.  Stage j holds rows sy_first + j*K ... (+K), one
+  // contiguous block of the plane (descending addresses when the card is rotated by 180 degrees: the block then starts at the
+  // stage's LAST row).  A stage is refilled, by lane 0 after a warp barrier, when the warp moves on to the next one.
+  const int sy_first = rows[0].start;
+  const int n_rows = sy_last - sy_first + 1, n_stages = (n_rows + kFgStageRows - 1) / kFgStageRows;
+  const int stage_bytes = kFgStageRows * NCH * 512;
+  auto issue_stage = [&](int j) {  // lane 0 only
+    if (j >= n_stages) return;
+    const int a = j * kFgStageRows, cnt = min(kFgStageRows, n_rows - a);
+    const int row_lo = flip_src ? card_h - 1 - (src_y0 + sy_first + a + cnt - 1) : src_y0 + sy_first + a;
+    fg_bulk_load(ring + (size_t)(j % kFgStages) * stage_bytes, plane + (size_t)row_lo * pitch, (unsigned)(cnt * pitch), bars + (j % kFgStages));
+  };
+  if (lane == 0)
+    for (int j = 0; j < kFgStages; j++) issue_stage(j);
+  uint4 cur[NCH];
+  int cur_sy = sy_first - 1;
+#else
   // Source rows are consumed in increasing order.  kFgPf rows are kept in flight ahead of the one in use as
   // 16-byte cp.async copies into a per-warp ring in shared memory (each lane later reads back only the bytes
   // it copied itself, so no warp barrier is involved); exactly one group is committed per row.
@@ -95,6 +149,7 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
   int cur_sy = sy_first - 1;
 #pragma unroll
   for (int u = 0; u < kFgPf; u++) prefetch_row(sy_first + u);
+#endif
   for (int r = r0; r < r1; r++) {
     const FgRow e = rows[r - r0];
     const int ny = e.n & 255;
@@ -112,14 +167,33 @@ __device__ __forceinline__ void fg_item(const mtgv_enc_params* __restrict__ sp, 
       const int sy = e.start + j;
       while (sy > cur_sy) {  // rows shared by two destination rows (a partial tap of each) stay in registers
         cur_sy++;
+#if MTGV_FG_BULK
+        const int rel = cur_sy - sy_first, j = rel / kFgStageRows, i = rel - j * kFgStageRows, slot = j % kFgStages;
+        if (i == 0) {
+          if (j > 0) {  // every lane is done with stage j-1 (its rows are in registers or consumed): refill it with stage j-1+S
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warp's reads of the stage are ordered before the copy's writes
+              issue_stage(j - 1 + kFgStages);
+            }
+          }
+          fg_mbar_wait(bars + slot, (phases >> slot) & 1u);
+          phases ^= 1u << slot;
+        }
+        const int cnt = min(kFgStageRows, n_rows - j * kFgStageRows);
+        const uint8_t* src = ring + (size_t)slot * stage_bytes + (size_t)(flip_src ? cnt - 1 - i : i) * pitch;
+#else
         asm volatile("cp.async.wait_group %0;" ::"n"(kFgPf - 1) : "memory");
         const uint8_t* src = ring + (size_t)(cur_sy % kFgPf) * (NCH * 512);
+#endif
 #pragma unroll
         for (int h = 0; h < NCH; h++) {
           const int off = (lane + 32 * h) * 16;
           cur[h] = off < pitch ? *(const uint4*)(src + off) : make_uint4(0u, 0u, 0u, 0u);
         }
+#if !MTGV_FG_BULK
         prefetch_row(cur_sy + kFgPf);
+#endif
       }
       const bool left = j == 0 && (e.n & 256), right = j == ny - 1 && (e.n & 512);
       if (left || right) {
@@ -231,7 +305,20 @@ __global__ void __launch_bounds__(kFgThreads, NCH == 1 ? MTGV_FG_BLOCKS : 2)
   __syncthreads();
   FgRow* rows = rtab + warp * kFgRows;
   float* rowbuf = rowbufs + (size_t)warp * rowbuf_len;
+#if MTGV_FG_BULK
+  uint8_t* ring0 = (uint8_t*)(rowbufs + (size_t)kFgWarps * rowbuf_len);
+  uint8_t* ring = ring0 + (size_t)warp * kFgStages * kFgStageRows * NCH * 512;
+  uint64_t* bars = (uint64_t*)(ring0 + (size_t)kFgWarps * kFgStages * kFgStageRows * NCH * 512) + warp * kFgStages;
+  if (lane == 0)
+    for (int j = 0; j < kFgStages; j++) fg_mbar_init(bars + j);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // the barriers are visible to the async proxy before the first copy
+  __syncwarp();
+  unsigned phases = 0u;  // parity to wait for, one bit per ring stage
+#else
   uint8_t* ring = (uint8_t*)(rowbufs + (size_t)kFgWarps * rowbuf_len) + (size_t)warp * kFgPf * NCH * 512;
+  uint64_t* bars = nullptr;
+  unsigned phases = 0u;
+#endif
   const int n_items = n * 3 * split;
   for (;;) {  // warps pull items from a global queue: skipped (aliased, cropped-geometry) items cost nothing
     int item = 0;
@@ -246,7 +333,7 @@ __global__ void __launch_bounds__(kFgThreads, NCH == 1 ? MTGV_FG_BLOCKS : 2)
     const int gi = kind == MTGV_KIND_CROPPED ? 1 : 0;
     const FgGeom& g = gi ? g1 : g0;
     if (sp->src_h != g.src_h || sp->src_w != g.src_w || sp->fg_rh != g.rh || sp->fg_rw != g.rw) continue;  // host invariant
-    fg_item<NCH, REGW>(sp, c, part, split, ctab + gi * kFgMaxOW, rows, rowbuf, ring, card_planes, pitch, fg_out, s, lane);
+    fg_item<NCH, REGW>(sp, c, part, split, ctab + gi * kFgMaxOW, rows, rowbuf, ring, bars, phases, card_planes, pitch, fg_out, s, lane);
   }
 }
 
@@ -254,7 +341,11 @@ static size_t fg_smem_bytes(int pitch) {
   size_t b = 2 * kFgMaxOW * sizeof(FgRow);
   b += (size_t)kFgWarps * kFgRows * sizeof(FgRow) + 16;
   b += (size_t)kFgWarps * ((pitch + (pitch >> 3) + 8 + 3) & ~3) * 4;
+#if MTGV_FG_BULK
+  b += (size_t)kFgWarps * kFgStages * kFgStageRows * (pitch > 512 ? 2 : 1) * 512 + (size_t)kFgWarps * kFgStages * 8;
+#else
   b += (size_t)kFgWarps * kFgPf * (pitch > 512 ? 2 : 1) * 512;
+#endif
   return (b + 15) & ~(size_t)15;
 }
 
