@@ -43,7 +43,7 @@ constexpr int kFgMaxOW = 256;
 #ifndef MTGV_FG_STAGES
 #define MTGV_FG_STAGES 3
 #endif
-constexpr int kFgStageRows = MTGV_FG_STAGE_ROWS, kFgStages = MTGV_FG_STAGES;
+[[maybe_unused]] constexpr int kFgStageRows = MTGV_FG_STAGE_ROWS, kFgStages = MTGV_FG_STAGES;
 
 __device__ __forceinline__ void fg_mbar_init(uint64_t* bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
