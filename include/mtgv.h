@@ -408,8 +408,8 @@ int mtgv_extract_dewarped(mtgv_ctx* ctx, const uint8_t* frame, int frame_h, int 
 /* ------------------------------------------------------------------------------------ */
 
 /* Frame size of one JPEG file (host memory): hw[0] = height, hw[1] = width.  Host-only marker walk; fails with
- * MTGV_ERR_INVALID and a message for files the decoder does not support (progressive, arithmetic coding,
- * CMYK, 12-bit, chroma subsampled by more than 2). */
+ * MTGV_ERR_INVALID and a message for files the decoder does not support (arithmetic coding, CMYK, 12-bit, chroma
+ * subsampled by more than 2).  Baseline, extended sequential and progressive Huffman files are supported. */
 int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw);
 
 /* mtgv_jpeg_info for n files in ONE call: file i = files[file_off[i] .. file_off[i+1]) (host memory, file_off has n+1
@@ -426,6 +426,9 @@ int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
  *      out_off = i*H*W*3 the tensor mtgv_set_card_pool / mtgv_update_*_images take.
  * hw: host [n][2] as returned by mtgv_jpeg_info (what the caller sized `out` with); a file whose frame header
  *     disagrees fails the call.  Bit-exact with cv2.imdecode (libjpeg-turbo: ISLOW IDCT, fancy upsampling).
+ *     Progressive (SOF2) files take the same call: their scans are entropy-decoded on the host threads that walk the markers
+ *     (refinement scans are bit-serial per block), the coefficients are uploaded, and dequantisation / IDCT / upsampling /
+ *     colour conversion run in the same device kernels as for baseline files.
  * Work is queued on `stream`.  file_off, out_off and hw may be reused when the call returns; `files` is read by an
  * asynchronous copy when it is page-locked memory and must then stay valid until that work has run (pageable memory is
  * staged before the call returns). */

@@ -13,7 +13,10 @@
 // The container (markers, tables) is parsed on the host; file bytes, tables and descriptors go up in one
 // staging copy each.
 #include "mtgv_internal.cuh"
+#include <mutex>
+
 #include "mtgv_jpeg.cuh"
+#include "mtgv_jpeg_prog.h"
 
 #include <thread>
 
@@ -29,6 +32,7 @@ struct JpegState {
   int16_t* dcs = nullptr;     size_t dcs_cap = 0;     // DC term of every block of the single-interval files
   int32_t* endblk = nullptr;  size_t endblk_cap = 0;  // per file: first block the entropy decoder never reached
   uint8_t* desc = nullptr;    size_t desc_cap = 0;    // JpegImg[n] | JpegTables[n]
+  int16_t* prog_host = nullptr; size_t prog_host_cap = 0;  // pinned: coefficients of the batch's progressive files (host entropy stage)
   uint8_t* desc_host = nullptr; size_t desc_host_cap = 0;  // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // around the three kernels of the last batch
   bool timed = false;
@@ -276,6 +280,7 @@ __global__ void __launch_bounds__(kParThreads, 1536 / kParThreads) k_jpeg_entrop
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int img = blockIdx.x;
   const JpegImg& im = imgs[img];
+  if (im.par == 0) return;  // progressive file: its coefficients were decoded on the host and are copied in behind this kernel
   {
     const JpegTables* T = tbs + img;
     for (int i = tid; i < (int)(sizeof(S.fast) / 4); i += kParThreads) ((uint32_t*)S.fast)[i] = ((const uint32_t*)T->fast)[i];
@@ -586,6 +591,7 @@ int jpeg_destroy(mtgv_ctx* ctx) {
   if (!st) return MTGV_OK;
   cudaFree(st->files); cudaFree(st->coef); cudaFree(st->planes); cudaFree(st->desc); cudaFree(st->clean); cudaFree(st->sync); cudaFree(st->endblk); cudaFree(st->dcs); cudaFree(st->rstpos);
   if (st->desc_host) cudaFreeHost(st->desc_host);
+  if (st->prog_host) cudaFreeHost(st->prog_host);
   for (auto& e : st->ev) if (e) cudaEventDestroy(e);
   delete st;
   ctx->jpeg = nullptr;
@@ -663,10 +669,25 @@ int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
   JpegState* st = (JpegState*)ctx->jpeg;
   std::vector<JpegImg> imgs(n);
   std::vector<JpegTables> tbs(n);
+  std::vector<std::vector<int16_t>> prog(n);  // coefficients of progressive files
+  std::mutex prog_mu;
+  int prog_bad = -1;
+  std::string prog_err;
   {  // marker walk + table build, a few host threads over contiguous file ranges
     std::string err;
-    if (jpeg_parse_many(files, file_off, n, &err, [&](int i, const JpegImg& im, const JpegTables& tb) { imgs[i] = im; tbs[i] = tb; }) >= 0)
+    if (jpeg_parse_many(files, file_off, n, &err, [&](int i, const JpegImg& im, const JpegTables& tb) {
+          imgs[i] = im; tbs[i] = tb;
+          if (im.progressive) {  // host entropy stage of a progressive file (mtgv_jpeg_prog.h), on this worker thread
+            prog[i].assign((size_t)im.nblk * 64, 0);
+            std::string perr;
+            if (jpeg_decode_progressive(files + file_off[i], file_off[i + 1] - file_off[i], im, im.comp_id, prog[i].data(), &perr) != 0) {
+              std::lock_guard<std::mutex> lk(prog_mu);
+              if (prog_bad < 0 || i < prog_bad) { prog_bad = i; prog_err = perr; }
+            }
+          }
+        }) >= 0)
       return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: " + err);
+    if (prog_bad >= 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_decode_jpeg_batch: file " + std::to_string(prog_bad) + ": " + prog_err);
   }
   int64_t nblk_total = 0, plane_total = 0;
   int max_blk = 0, max_h = 0;
@@ -694,7 +715,7 @@ int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
   int64_t clean_total = 0, sync_total = 0, rst_total = 0;
   for (int i = 0; i < n; i++) {
     JpegImg& im = imgs[i];
-    im.par = im.nseg == 1 ? 1 : 2;
+    im.par = im.progressive ? 0 : (im.nseg == 1 ? 1 : 2);
     const int64_t scan_bytes = (int64_t)im.file_len - im.scan_off;
     im.clean_off = clean_total;
     im.sync_off = sync_total;
@@ -716,6 +737,15 @@ int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
   if ((rc = grow(ctx, (void**)&st->rstpos, &st->rstpos_cap, ((size_t)rst_total + 1) * sizeof(uint32_t)))) return rc;
   // an earlier batch (on whatever stream) may still be reading the staging buffer and the scratch arrays
   if (st->timed) MTGV_CUDA_OK(ctx, cudaEventSynchronize(st->ev[3]));
+  size_t prog_total = 0;
+  for (int i = 0; i < n; i++)
+    if (imgs[i].progressive) prog_total += (size_t)imgs[i].nblk * 64;
+  if (prog_total > st->prog_host_cap) {
+    if (st->prog_host) MTGV_CUDA_OK(ctx, cudaFreeHost(st->prog_host));
+    st->prog_host = nullptr; st->prog_host_cap = 0;
+    MTGV_CUDA_OK(ctx, cudaMallocHost((void**)&st->prog_host, (prog_total + prog_total / 4) * sizeof(int16_t)));
+    st->prog_host_cap = prog_total + prog_total / 4;
+  }
   if (desc_bytes > st->desc_host_cap) {
     if (st->desc_host) MTGV_CUDA_OK(ctx, cudaFreeHost(st->desc_host));
     st->desc_host = nullptr; st->desc_host_cap = 0;
@@ -733,6 +763,17 @@ int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
   MTGV_CUDA_OK(ctx, cudaMemsetAsync(st->dcs, 0, (size_t)nblk_total * sizeof(int16_t), stream));
   k_jpeg_entropy_par<<<(unsigned)n, kParThreads, 0, stream>>>(st->files, d_img, d_tb, st->clean, st->sync, st->coef, st->dcs, st->endblk, st->rstpos);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
+  if (prog_total) {
+    // progressive files: their coefficient blocks (absolute DC terms included) go straight into the scratch the IDCT reads
+    size_t o = 0;
+    for (int i = 0; i < n; i++)
+      if (imgs[i].progressive) {
+        const size_t cnt = (size_t)imgs[i].nblk * 64;
+        memcpy(st->prog_host + o, prog[i].data(), cnt * sizeof(int16_t));
+        MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->coef + (size_t)imgs[i].coef_blk * 64, st->prog_host + o, cnt * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
+        o += cnt;
+      }
+  }
   k_jpeg_dc<<<dim3((unsigned)n, 3), 32, 0, stream>>>(d_img, st->dcs, st->endblk);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));

@@ -53,6 +53,8 @@ struct JpegImg {
   int64_t rst_off;       // par == 2: clean byte position of every restart interval but the first (uint32 units)
   int32_t out_layout;    // 0: [h][w][3] RGB bytes; 1: planar [3][h][out_pitch] bytes (card pool); 2: RGBX words [h][out_pitch] (background pool)
   int32_t out_pitch;     // layout 1: bytes per plane row; layout 2: words per row
+  int32_t progressive;   // SOF2: the entropy stage runs on the host (mtgv_jpeg_prog.h), par = 0, coefficients are uploaded
+  int32_t comp_id[3];    // component identifiers of the frame header (scan headers of progressive files refer to them)
 };
 
 struct JpegSeg {  // one restart interval (or the whole scan): decoded by one thread
@@ -82,6 +84,7 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
   if (len > 0x7fffffff) return jpeg_fail(err, "file larger than 2 GiB");
   int64_t pos = 2;
   bool have_frame = false, have_q[4] = {false, false, false, false}, have_h[4] = {false, false, false, false};
+  bool progressive = false, ext_tables = false;
   int comp_id[3] = {0, 0, 0}, adobe_transform = -1;
   for (;;) {
     if (pos + 4 > len) return jpeg_fail(err, "truncated before the scan");
@@ -111,7 +114,15 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
       while (q < n) {
         if (q + 17 > n) return jpeg_fail(err, "bad Huffman table");
         const int tc = s[q] >> 4, th = s[q] & 15;
-        if (tc > 1 || th > 1) return jpeg_fail(err, "Huffman table id > 1 (not baseline)");
+        if (tc > 1 || th > 3) return jpeg_fail(err, "bad Huffman table id");
+        if (th > 1) {  // ids 2, 3: legal in extended / progressive files only; the host scan decoder reads its own tables
+          int total2 = 0;
+          for (int l = 0; l < 16; l++) total2 += s[q + 1 + l];
+          if (total2 > 256 || q + 17 + total2 > n) return jpeg_fail(err, "bad Huffman table");
+          ext_tables = true;
+          q += 17 + total2;
+          continue;
+        }
         const int ti = tc * 2 + th;
         const uint8_t* counts = s + q + 1;
         int total = 0;
@@ -137,7 +148,8 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
         have_h[ti] = true;
         q += 17 + total;
       }
-    } else if (m == 0xC0 || m == 0xC1) {
+    } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+      progressive = m == 0xC2;
       if (n < 6 || s[0] != 8) return jpeg_fail(err, "only 8-bit samples are supported");
       im->h = (s[1] << 8) | s[2];
       im->w = (s[3] << 8) | s[4];
@@ -153,9 +165,8 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
         if (im->tq[c] > 3) return jpeg_fail(err, "bad frame header");
       }
       have_frame = true;
-    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-      return jpeg_fail(err, m == 0xC2 ? "progressive JPEG is not supported (baseline sequential only)"
-                                      : "only baseline / extended sequential Huffman JPEG (SOF0, SOF1) is supported");
+    } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      return jpeg_fail(err, "only Huffman-coded baseline, extended sequential or progressive JPEG (SOF0, SOF1, SOF2) is supported");
     } else if (m == 0xDD) {
       if (n < 2) return jpeg_fail(err, "bad DRI");
       im->dri = (s[0] << 8) | s[1];
@@ -163,6 +174,13 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
       adobe_transform = s[11];
     } else if (m == 0xDA) {
       if (!have_frame) return jpeg_fail(err, "scan before frame header");
+      if (progressive) {  // several scans, each with its own header: mtgv_jpeg_prog.h walks them; only the quantisation tables matter here
+        for (int c = 0; c < im->ncomp; c++)
+          if (!have_q[im->tq[c]]) return jpeg_fail(err, "missing quantisation table");
+        pos -= 2;  // scan_off = the first SOS marker
+        break;
+      }
+      if (ext_tables) return jpeg_fail(err, "Huffman table id > 1 (not baseline)");
       if (n < 1 || s[0] != im->ncomp || n < 1 + 2 * im->ncomp + 3) return jpeg_fail(err, "only one interleaved scan is supported");
       for (int i = 0; i < im->ncomp; i++) {
         int c = -1;
@@ -208,6 +226,14 @@ inline int jpeg_parse(const uint8_t* d, int64_t len, int img_index, JpegImg* im,
   }
   im->scan_off = (int32_t)pos;
   im->file_len = (int32_t)len;
+  im->progressive = progressive ? 1 : 0;
+  for (int c = 0; c < 3; c++) im->comp_id[c] = comp_id[c];
+  if (progressive) {  // no device entropy stage: one dummy segment keeps the scratch arithmetic of the caller uniform
+    im->seg0 = segs ? (int32_t)segs->size() : 0;
+    im->nseg = 1;
+    im->dri = 0;
+    return 0;
+  }
   // segments: the whole scan, or one per restart interval (the RSTn markers are byte aligned: B.1.1.5).  The device
   // decoder finds the markers itself while it unstuffs the scan (segs == nullptr): only the interval count is needed.
   const int total = im->mcux * im->mcuy;

@@ -63,7 +63,7 @@ class IlsvrcImages:
     """Background image source with the reference's interface (encoder_datasets.py:421-478)
     over a resident pool of uint8 images, or - like the reference - over a directory of JPEG files
     (`root`, `subdir`), which are decoded on the device straight into the pool.  Files the
-    baseline decoder rejects (progressive, CMYK, ...) raise `MtgvError`, or are left out with a warning
+    decoder rejects (arithmetic coding, CMYK, 12-bit ...) raise `MtgvError`, or are left out with a warning
     when `skip_unsupported=True`."""
 
     _EXTS = (".jpeg", ".jpg")
@@ -83,7 +83,7 @@ class IlsvrcImages:
             else:
                 self._paths = [f"bg://{j:06d}" for j in range(len(files))]
             if skip_unsupported:
-                # ILSVRC holds a few progressive / CMYK files; the device decoder is baseline-only and has no fallback:
+                # ILSVRC holds a few CMYK files; the decoder takes Huffman-coded YCbCr / grey files only and has no fallback:
                 # leave them out of the background pool (with a warning) instead of failing the whole ingest
                 keep = []
                 for j, f in enumerate(files):

@@ -6,6 +6,7 @@
 #include "../../mtgvision_b200/csrc/mtgv_mask.h"
 #include "../../mtgvision_b200/csrc/mtgv_det.cuh"
 #include "../../mtgvision_b200/csrc/mtgv_jpeg.cuh"
+#include "../../mtgvision_b200/csrc/mtgv_jpeg_prog.h"
 #include "../../mtgvision_b200/csrc/mtgv_jpegenc.cuh"
 
 using namespace mtgv;
@@ -109,7 +110,14 @@ int hh_jpeg_decode(const uint8_t* file, int64_t len, int32_t* hw, uint8_t* out, 
   int64_t plane_total = 0;
   for (int c = 0; c < im.ncomp; c++) { im.plane_off[c] = plane_total; plane_total += (int64_t)im.bw[c] * im.bh[c] * 64; }
   std::vector<uint8_t> planes((size_t)plane_total);
-  for (const JpegSeg& sg : segs) jpeg_decode_segment(file, im, &tb, sg, coef.data(), kJpegZigzag);
+  if (im.progressive) {
+    if (jpeg_decode_progressive(file, len, im, im.comp_id, coef.data(), &err) != 0) {
+      snprintf(msg, msg_cap, "%s", err.c_str());
+      return -1;
+    }
+  } else {
+    for (const JpegSeg& sg : segs) jpeg_decode_segment(file, im, &tb, sg, coef.data(), kJpegZigzag);
+  }
   for (int c = 0; c < im.ncomp; c++)
     for (int b = 0; b < im.bw[c] * im.bh[c]; b++) {
       const int16_t* blk = coef.data() + (size_t)(im.blk0[c] + b) * 64;

@@ -222,6 +222,45 @@ def test_detection_generator_over_jpeg_backgrounds():
         assert np.array_equal(a, b)
 
 
+def test_progressive_files_in_a_mixed_batch():
+    """Progressive files (host entropy stage, coefficients uploaded, IDCT / upsampling / colour on the device) next to baseline
+    files in one call: bit-exact with cv2.imdecode, into plain HWC images and straight into the pools."""
+    from mtgvision_b200 import abi, synth
+    from mtgvision_b200.context import Context
+    from tests import parity_util as PU
+
+    rng = np.random.default_rng(8)
+    files = []
+    for k, (h, w) in enumerate([(375, 500), (24, 31), (375, 500), (1, 1), (97, 64), (680, 488)]):
+        img = jpeg_cases.image(rng, h, w, ("mixed", "noise", "smooth")[k % 3])
+        files.append(jpeg_cases.encode(img, (90, 35, 100)[k % 3], ("420", "444", "422", "440")[k % 4], rst=(0, 3)[k % 2], progressive=k % 3 != 2))
+    ctx = Context(0)
+    flat, off, hw = ctx.decode_jpegs(files)
+    torch.cuda.synchronize()
+    host = flat.cpu().numpy()
+    for k, f in enumerate(files):
+        h, w = hw[k]
+        assert np.array_equal(host[off[k]: off[k] + 3 * h * w].reshape(h, w, 3), _ref(f)), k
+    ctx.close()
+    # pools: slots decoded from progressive files == slots set from the cv2-decoded arrays
+    pool, bgs = PU.small_pools(4, 4)
+    cfiles = [jpeg_cases.encode(pool.images[k], 92, "420", progressive=k % 2) for k in range(4)]
+    bfiles = [jpeg_cases.encode(bgs[j], 88, "420", progressive=(j + 1) % 2) for j in range(4)]
+    dec_cards = synth.CardPool(np.stack([_ref(f) for f in cfiles]), pool.faces)
+    dec_bgs = [_ref(f) for f in bfiles]
+    outs = []
+    for via_files in (False, True):
+        if via_files:
+            ctx = PU.make_context(synth.CardPool(np.zeros_like(dec_cards.images), pool.faces), [np.zeros_like(b) for b in dec_bgs])
+            ctx.decode_into_pools(ctx.prepare_jpegs(cfiles + bfiles), 4, 0, 4, 0)
+        else:
+            ctx = PU.make_context(dec_cards, dec_bgs)
+        params, _ = ctx.expand_params(ctx.sample_encoder_tape(3, 0, 16))
+        outs.append(ctx.encoder_batch(params, abi.OUT_U8).cpu().numpy())
+        ctx.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_rejects_unsupported_and_mismatched():
     from mtgvision_b200.abi import MtgvError
     from mtgvision_b200.context import Context
@@ -229,15 +268,16 @@ def test_rejects_unsupported_and_mismatched():
     ctx = Context(0)
     rng = np.random.default_rng(3)
     img = jpeg_cases.image(rng, 24, 24, "mixed")
-    with pytest.raises(MtgvError, match="progressive"):
-        ctx.decode_jpegs([jpeg_cases.encode(img, progressive=1)])
+    arith = jpeg_cases.encode(img).replace(b"\xff\xc0", b"\xff\xc9", 1)  # SOF9: arithmetic coding
+    with pytest.raises(MtgvError, match="Huffman-coded"):
+        ctx.decode_jpegs([arith])
     with pytest.raises(MtgvError, match="SOI"):
         ctx.jpeg_info(b"\x89PNG....")
     ctx.close()
     # a file-backed background source can leave such files out instead of failing
     from mtgvision_b200.encoder_datasets import IlsvrcImages
 
-    files = [jpeg_cases.encode(img), jpeg_cases.encode(img, progressive=1), jpeg_cases.encode(img, 80, "444")]
-    with pytest.warns(UserWarning, match="progressive"):
+    files = [jpeg_cases.encode(img), arith, jpeg_cases.encode(img, 80, "444")]
+    with pytest.warns(UserWarning, match="Huffman-coded"):
         src = IlsvrcImages(files=files, skip_unsupported=True)
     assert len(src) == 2 and np.array_equal(src.images_u8[1], _ref(files[2]))

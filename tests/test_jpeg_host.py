@@ -51,8 +51,9 @@ def test_background_sized_files(hh):
 def test_unsupported_files_are_rejected_with_a_message(hh):
     rng = np.random.default_rng(3)
     img = jpeg_cases.image(rng, 24, 24, "mixed")
-    with pytest.raises(ValueError, match="progressive"):
-        host_decode(hh, jpeg_cases.encode(img, progressive=1))
+    arith = jpeg_cases.encode(img).replace(b"\xff\xc0", b"\xff\xc9", 1)  # SOF9: arithmetic coding
+    with pytest.raises(ValueError, match="Huffman-coded"):
+        host_decode(hh, arith)
     with pytest.raises(ValueError, match="SOI"):
         host_decode(hh, b"\x89PNG....")
     good = jpeg_cases.encode(img)
@@ -63,3 +64,22 @@ def test_unsupported_files_are_rejected_with_a_message(hh):
 def test_truncated_files_decode_like_cv2_imread(hh, tmp_path):
     for name, data in jpeg_cases.truncated_suite():
         assert np.array_equal(host_decode(hh, data), jpeg_cases.imread_ref(data, tmp_path)), name
+
+
+def test_progressive_files_decode_like_cv2(hh):
+    """SOF2 files (ILSVRC and Scryfall hold some): the host entropy stage (mtgv_jpeg_prog.h: DC / AC first and refinement scans,
+    end-of-band runs, restart intervals) feeding the shared IDCT / upsampling / colour arithmetic equals cv2.imdecode."""
+    rng = np.random.default_rng(21)
+    n = 0
+    for h, w in [(24, 24), (375, 500), (17, 33), (1, 1), (100, 7)]:
+        for kind in ("mixed", "noise", "smooth"):
+            for samp, q, rst, opt in [("420", 90, 0, 0), ("444", 35, 3, 1), ("422", 100, 0, 1), ("440", 75, 5, 0)]:
+                data = jpeg_cases.encode(jpeg_cases.image(rng, h, w, kind), q, samp, rst, opt, progressive=1)
+                assert b"\xff\xc2" in data
+                ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR_RGB)
+                assert np.array_equal(host_decode(hh, data), ref), (h, w, kind, samp, q, rst, opt)
+                n += 1
+    gray = rng.integers(0, 256, (40, 56), dtype=np.uint8)
+    data = jpeg_cases.encode(gray, 90, "420", progressive=1)
+    assert np.array_equal(host_decode(hh, data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR_RGB))
+    assert n == 60
