@@ -233,7 +233,7 @@ def test_progressive_files_in_a_mixed_batch():
     files = []
     for k, (h, w) in enumerate([(375, 500), (24, 31), (375, 500), (1, 1), (97, 64), (680, 488)]):
         img = jpeg_cases.image(rng, h, w, ("mixed", "noise", "smooth")[k % 3])
-        files.append(jpeg_cases.encode(img, (90, 35, 100)[k % 3], ("420", "444", "422", "440")[k % 4], rst=(0, 3)[k % 2], progressive=k % 3 != 2))
+        files.append(jpeg_cases.encode(img, (90, 35, 100)[k % 3], ("420", "444", "422", "440")[k % 4], rst=(0, 3)[k % 2], progressive=int(k % 3 != 2)))
     ctx = Context(0)
     flat, off, hw = ctx.decode_jpegs(files)
     torch.cuda.synchronize()
