@@ -88,10 +88,18 @@ __device__ __forceinline__ int ent_extend(uint32_t win, int used, int s) {
 //             induction, whatever the data (worst case: as many rounds as threads).  (Measured and dropped: queueing the
 //             runs that start over and decoding them one checkpoint per step with packed warps - 10 % slower, the extra
 //             barriers and window reloads cost more than the idle lanes; 12-bit look-up tables built by the CTA
-//             - 6 % slower: long codes are not the problem, the 34 KB of tables cost occupancy);
+//             - 6 % slower: long codes are not the problem, the 34 KB of tables cost occupancy; a third stream word
+//             prefetched one window ahead - neutral: the load the profile shows the warps waiting on lands in time either
+//             way, what costs is the issue slots of three passes, the second of them at 8 of 32 lanes);
 //   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
 // DC terms are stored as differences and integrated by k_jpeg_dc.
 constexpr int kSubBits = 512;  // measured: 128 -> 25 % slower (per-checkpoint overhead in the cold pass), 1024 -> later break-off in the rounds
+#ifndef MTGV_JPEG_IDCT_ROWLOAD
+#define MTGV_JPEG_IDCT_ROWLOAD 1
+#endif
+#ifndef MTGV_JPEG_FASTCOUNT
+#define MTGV_JPEG_FASTCOUNT 1
+#endif
 #ifndef MTGV_JPEG_PAR_THREADS
 #define MTGV_JPEG_PAR_THREADS 256
 #endif
@@ -100,6 +108,9 @@ constexpr uint64_t kStateMask = (1ull << 48) - 1;
 
 struct ParSmem {
   uint16_t fast[4][1 << kJpegFastBits];
+#if MTGV_JPEG_FASTCOUNT
+  uint16_t cnt[4][1 << kJpegFastBits];  // for the passes that only follow the stream: bits of code + value | zigzag advance << 8
+#endif
   int32_t maxcode[4][18];
   int32_t valoff[4][18];
   uint8_t vals[4][256];
@@ -137,7 +148,9 @@ __device__ __forceinline__ int16_t* par_blk(const ParSmem& S, int16_t* coef, int
 // the block st lies in; coefficients of blocks >= nblk_scan (garbage after the last MCU) are dropped.
 // ABSDC (restart intervals, decoded whole by one call): DC predictions start at zero here and the DC TERMS are written;
 // otherwise the DC DIFFERENCES are written (k_jpeg_dc integrates them).  max_blocks: stop after that many blocks.
-template <bool WRITE, bool ABSDC = false>
+// BOUNDED: stream words past the end read as zero (only the pass that finishes a truncated scan runs past the data; the
+// others stay within one word of the end, which the CTA zeroes).
+template <bool WRITE, bool ABSDC = false, bool BOUNDED = false>
 __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, const uint32_t* __restrict__ cl, unsigned Lw, ParState& st,
                                           unsigned boundary, int16_t* coef, int16_t* dcs, int& b, int max_blocks = 0x7fffffff) {
   unsigned p = st.p;
@@ -151,39 +164,50 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
     mx = mcu - my * G.mcux;
     blk = par_blk(S, coef, j, mx, my);
   }
+  int tdc = S.blk_td[j], tac = S.blk_ta[j];  // Huffman tables of the current block
   unsigned cur = p >> 5;  // two stream words stay in registers; a symbol is at most 31 bits, so the window moves by 0 or 1 words
-  uint32_t w0 = cur < Lw ? cl[cur] : 0u, w1 = cur + 1u < Lw ? cl[cur + 1u] : 0u;
+  uint32_t w0 = !BOUNDED || cur < Lw ? cl[cur] : 0u, w1 = !BOUNDED || cur + 1u < Lw ? cl[cur + 1u] : 0u;
   while (p < boundary && nb < max_blocks) {
     if ((p >> 5) != cur) {
       cur = p >> 5;
       w0 = w1;
-      w1 = cur + 1u < Lw ? cl[cur + 1u] : 0u;
+      w1 = !BOUNDED || cur + 1u < Lw ? cl[cur + 1u] : 0u;
     }
     const uint32_t win = __funnelshift_l(w1, w0, p & 31u);
     const bool dc = k == 0;
-    const int ti = dc ? S.blk_td[j] : S.blk_ta[j];
-    int used;
-    const int sym = ent_symbol(S, ti, win, used);
-    const int s = sym & 15, r = dc ? 0 : sym >> 4;
-    if (WRITE && ABSDC && dc) {
-      const int diff = s ? ent_extend(win, used, s) : 0;
-      const int c = S.blk_c[j];
-      const int pr = c == 0 ? (pred0 += diff) : (c == 1 ? (pred1 += diff) : (pred2 += diff));
-      if (b < G.nblk_scan) dcs[(blk - coef) >> 6] = (int16_t)pr;
-      used += s;
-    } else if (s) {
-      if (WRITE) {
-        const int pos = dc ? 0 : k + r;
-        if (pos < 64 && b < G.nblk_scan) {
-          const int16_t v = (int16_t)ent_extend(win, used, s);
-          if (dc) dcs[(blk - coef) >> 6] = v;  // DC differences go to the compact per-block array k_jpeg_dc integrates
-          else blk[S.zz[pos]] = v;
+    const int ti = dc ? tdc : tac;
+#if MTGV_JPEG_FASTCOUNT
+    unsigned ce = 0;
+    if (!WRITE) ce = S.cnt[ti][win >> (32 - kJpegFastBits)];
+    if (!WRITE && ce) {  // short code: its length, value bits and zigzag step come from one table entry
+      p += ce & 255u;
+      k += (int)(ce >> 8);
+    } else
+#endif
+    {
+      int used;
+      const int sym = ent_symbol(S, ti, win, used);
+      const int s = sym & 15, r = dc ? 0 : sym >> 4;
+      if (WRITE && ABSDC && dc) {
+        const int diff = s ? ent_extend(win, used, s) : 0;
+        const int c = S.blk_c[j];
+        const int pr = c == 0 ? (pred0 += diff) : (c == 1 ? (pred1 += diff) : (pred2 += diff));
+        if (b < G.nblk_scan) dcs[(blk - coef) >> 6] = (int16_t)pr;
+        used += s;
+      } else if (s) {
+        if (WRITE) {
+          const int pos = dc ? 0 : k + r;
+          if (pos < 64 && b < G.nblk_scan) {
+            const int16_t v = (int16_t)ent_extend(win, used, s);
+            if (dc) dcs[(blk - coef) >> 6] = v;  // DC differences go to the compact per-block array k_jpeg_dc integrates
+            else blk[S.zz[pos]] = v;
+          }
         }
+        used += s;
       }
-      used += s;
+      k = dc ? 1 : (s ? k + r + 1 : (r == 15 ? k + 16 : 64));
+      p += (unsigned)used;
     }
-    k = dc ? 1 : (s ? k + r + 1 : (r == 15 ? k + 16 : 64));
-    p += (unsigned)used;
     if (k >= 64) {
       k = 0;
       nb++;
@@ -191,6 +215,7 @@ __device__ __forceinline__ int par_decode(const ParSmem& S, const ParGeom& G, co
         j = 0;
         if (WRITE && ++mx == G.mcux) { mx = 0; my++; }
       }
+      tdc = S.blk_td[j]; tac = S.blk_ta[j];
       if (WRITE) {
         b++;
         blk = par_blk(S, coef, j, mx, my);
@@ -312,13 +337,23 @@ __global__ void __launch_bounds__(kParThreads, 1536 / kParThreads) k_jpeg_entrop
   const int file_len = im.file_len, scan_off = im.scan_off;
   uint8_t* cl8 = clean + im.clean_off;
   __syncthreads();
+#if MTGV_JPEG_FASTCOUNT
+  for (int i = tid; i < 4 << kJpegFastBits; i += kParThreads) {
+    const int ti = i >> kJpegFastBits;
+    const unsigned e = S.fast[ti][i & ((1 << kJpegFastBits) - 1)];
+    const unsigned s = e & 15u, r = (e >> 4) & 15u;
+    const unsigned adv = ti < 2 ? 1u : (s ? r + 1u : (r == 15u ? 16u : 64u));  // tables 0,1: DC (the block moves on to its AC terms)
+    S.cnt[ti][i & ((1 << kJpegFastBits) - 1)] = e ? (uint16_t)(((e >> 8) + s) | (adv << 8)) : (uint16_t)0;
+  }
+  // (read after the barriers of the unstuffing pass)
+#endif
 
   const bool intervals = im.par == 2;
   uint32_t* rp = rstpos + im.rst_off;
   unsigned nrst = 0;
   const unsigned wp = intervals ? par_unstuff<true>(S, file, scan_off, file_len, cl8, rp, im.nseg, &nrst)
                                 : par_unstuff<false>(S, file, scan_off, file_len, cl8, rp, im.nseg, &nrst);
-  if (tid < 8) cl8[(wp + tid) ^ 3u] = 0;  // whole last word (+1) reads as zero bits
+  if (tid < 16) cl8[(wp + tid) ^ 3u] = 0;  // the last word and the three behind it read as zero bits
   __syncthreads();
   const unsigned Lw = (wp + 3u) >> 2;
   const uint32_t* cl = (const uint32_t*)cl8;
@@ -405,8 +440,8 @@ __global__ void __launch_bounds__(kParThreads, 1536 / kParThreads) k_jpeg_entrop
     // (truncated file, stray marker) libjpeg finishes the MCU in which a request for bits ran past the data from zero bits
     // and skips every later MCU, whose coefficients stay zero - grey (jdhuff.c decode_mcu, insufficient_data).
     if (b < G.nblk_scan) {
-      if (st.p <= total_bits) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, dcs, b);  // the request that finds no data
-      while (!(st.k == 0 && st.j == 0) && b < G.nblk_scan) par_decode<true>(S, G, cl, Lw, st, st.p + 1u, coef, dcs, b);
+      if (st.p <= total_bits) par_decode<true, false, true>(S, G, cl, Lw, st, st.p + 1u, coef, dcs, b);  // the request that finds no data
+      while (!(st.k == 0 && st.j == 0) && b < G.nblk_scan) par_decode<true, false, true>(S, G, cl, Lw, st, st.p + 1u, coef, dcs, b);
     }
     end_blk[img] = b;  // first block that was never decoded
   }
@@ -447,6 +482,64 @@ __global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs
   }
 }
 
+#if MTGV_JPEG_IDCT_ROWLOAD
+// grid (ceil(max blocks / 32), n images), 256 threads = 32 blocks of 8 threads.  Thread t of a block loads coefficient ROW t
+// and its quantiser row as one 16-byte word each, the products go through shared memory to the thread of their COLUMN
+// (jidctint.c runs the column pass first; the order is part of the rounding), and back for the row pass.
+__global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ imgs, const JpegTables* __restrict__ tbs,
+                                                   const int16_t* __restrict__ coef, const int16_t* __restrict__ dcs,
+                                                   uint8_t* __restrict__ planes) {
+  __shared__ int ws[32][8][9];
+  const JpegImg& im = imgs[blockIdx.y];
+  const int g = threadIdx.x >> 3, t = threadIdx.x & 7;
+  const int b = blockIdx.x * 32 + g;
+  const bool live = b < im.nblk;
+  int c = 0;
+  if (live) {
+    while (c + 1 < im.ncomp && b >= im.blk0[c + 1]) c++;
+    const uint4 cw = __ldg((const uint4*)(coef + (im.coef_blk + b) * 64) + t);
+    const uint4 qw = __ldg((const uint4*)tbs[blockIdx.y].qt[im.tq[c]] + t);
+    const uint32_t cv[4] = {cw.x, cw.y, cw.z, cw.w}, qv[4] = {qw.x, qw.y, qw.z, qw.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      ws[g][t][2 * k] = (int)(int16_t)(cv[k] & 0xffffu) * (int)(qv[k] & 0xffffu);
+      ws[g][t][2 * k + 1] = (int)(int16_t)(cv[k] >> 16) * (int)(qv[k] >> 16);
+    }
+    if (im.par && t == 0) ws[g][0][0] = (int)dcs[im.coef_blk + b] * (int)(qv[0] & 0xffffu);  // DC term from the integrated per-block array
+  }
+  __syncwarp();
+  int o[8];
+  if (live) {
+    int x[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = ws[g][r][t];
+    jpeg_idct8(x, o, kJpegPass1Shift);  // column t
+  }
+  __syncwarp();
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) ws[g][r][t] = o[r];
+  }
+  __syncwarp();
+  if (live) {
+    int x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = ws[g][t][k];
+    jpeg_idct8(x, o, kJpegPass2Shift);  // row t
+    const int lb = b - im.blk0[c], by = lb / im.bw[c], bx = lb - by * im.bw[c];
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      lo |= (uint32_t)jpeg_clamp255(o[k] + 128) << (8 * k);
+      hi |= (uint32_t)jpeg_clamp255(o[k + 4] + 128) << (8 * k);
+    }
+    // plane offsets are multiples of 8 and the pitch is a multiple of 8: the row segment is 8-byte aligned
+    uint2* dst = (uint2*)(planes + im.plane_off[c] + (int64_t)(by * 8 + t) * (im.bw[c] * 8) + bx * 8);
+    *dst = make_uint2(lo, hi);
+  }
+}
+
+#else
 // grid (ceil(max blocks / 32), n images), 256 threads = 32 blocks of 8 threads
 __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ imgs, const JpegTables* __restrict__ tbs,
                                                    const int16_t* __restrict__ coef, const int16_t* __restrict__ dcs,
@@ -488,11 +581,17 @@ __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ i
   }
 }
 
+#endif
 // grid (row bands, n images): a CTA walks the rows of its band; a thread converts 4 consecutive pixels of a row and
-// stores their 12 bytes as three words when the row start is word aligned.  4:2:0 (h2v2) and 4:4:4 interior groups
-// take a straight-line path (one aligned 4-byte luma load, the vertical chroma blend shared by the four pixels);
-// row ends, narrow images and the other sampling modes go through the generic jpeg_pixel.
-constexpr int kColorRows = 8;
+// stores their 12 bytes as three words when the row start is word aligned.  4:2:0 (h2v2) and 4:4:4 groups take a
+// straight-line path (one aligned 4-byte luma load, the vertical chroma blend shared by the four pixels), row ends
+// included (clamped chroma columns); narrow images and the other sampling modes go through the generic jpeg_pixel.
+// (Measured and dropped: 8 pixels per thread with word loads of the chroma rows - 18 % slower at 64 registers; the two
+// chroma words per row funnel-shifted instead of four byte loads - 10 % slower.)
+#ifndef MTGV_JPEG_COLOR_ROWS
+#define MTGV_JPEG_COLOR_ROWS 32
+#endif
+constexpr int kColorRows = MTGV_JPEG_COLOR_ROWS;
 
 __device__ __forceinline__ void ycc_store(int Y, int cb, int cr, uint8_t* px) {
   cb -= 128; cr -= 128;
@@ -501,87 +600,102 @@ __device__ __forceinline__ void ycc_store(int Y, int cb, int cr, uint8_t* px) {
   px[2] = (uint8_t)jpeg_clamp255(Y + ((116130 * cb + 32768) >> 16));
 }
 
+// the 4 (or fewer, at the row end) pixels of row yy from x0 on
+__device__ __forceinline__ void color_group4(const JpegImg& im, const uint8_t* __restrict__ planes, uint8_t* __restrict__ out, bool h2v2, bool h1v1,
+                                             int yy, int x0) {
+  const int W = im.w, H = im.h;
+  const uint8_t* PY = planes + im.plane_off[0];
+  const uint8_t* PB = planes + im.plane_off[1];
+  const uint8_t* PR = planes + im.plane_off[2];
+  const int pitchY = im.bw[0] * 8, pitchC = im.ncomp == 3 ? im.bw[1] * 8 : 0;
+  uint8_t* drow = out + im.out_off + (int64_t)yy * W * 3;
+  const bool aligned = (((uintptr_t)drow) & 3) == 0;
+  // vertical neighbours of the chroma triangle filter (edge rows replicated)
+  const int inrow = yy >> 1, dh = im.dh[1];
+  const int other = (yy & 1) ? (inrow + 1 < dh ? inrow + 1 : dh - 1) : (inrow > 0 ? inrow - 1 : 0);
+  const int bias_e = 8, bias_o = 7;
+  uint8_t px[12];
+  const int cnt = W - x0 < 4 ? W - x0 : 4;
+  if (h2v2) {
+    // every group of the row, its ends included: h2v2_fancy_upsample's first / last column formula (4 * colsum + bias) is
+    // the general one with the missing neighbour column replaced by the column itself, i.e. with clamped column indices;
+    // pixels past the width (cnt < 4) are computed from the padded planes and not stored
+    const uint32_t y4 = *(const uint32_t*)(PY + (int64_t)yy * pitchY + x0);
+    const int j = x0 >> 1, jmax = im.dw[1] - 1;
+    int col[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int v = j - 1 + q; col[q] = v < 0 ? 0 : (v > jmax ? jmax : v); }
+    const uint8_t* b0 = PB + (int64_t)inrow * pitchC;
+    const uint8_t* b1 = PB + (int64_t)other * pitchC;
+    const uint8_t* r0 = PR + (int64_t)inrow * pitchC;
+    const uint8_t* r1 = PR + (int64_t)other * pitchC;
+    int cb[4], cr[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { cb[q] = 3 * b0[col[q]] + b1[col[q]]; cr[q] = 3 * r0[col[q]] + r1[col[q]]; }
+    ycc_store(y4 & 255, (3 * cb[1] + cb[0] + bias_e) >> 4, (3 * cr[1] + cr[0] + bias_e) >> 4, px);
+    ycc_store((y4 >> 8) & 255, (3 * cb[1] + cb[2] + bias_o) >> 4, (3 * cr[1] + cr[2] + bias_o) >> 4, px + 3);
+    ycc_store((y4 >> 16) & 255, (3 * cb[2] + cb[1] + bias_e) >> 4, (3 * cr[2] + cr[1] + bias_e) >> 4, px + 6);
+    ycc_store(y4 >> 24, (3 * cb[2] + cb[3] + bias_o) >> 4, (3 * cr[2] + cr[3] + bias_o) >> 4, px + 9);
+  } else if (h1v1) {
+    const uint32_t y4 = *(const uint32_t*)(PY + (int64_t)yy * pitchY + x0);
+    const uint32_t b4 = *(const uint32_t*)(PB + (int64_t)yy * pitchC + x0);
+    const uint32_t r4 = *(const uint32_t*)(PR + (int64_t)yy * pitchC + x0);
+#pragma unroll
+    for (int q = 0; q < 4; q++) ycc_store((y4 >> (8 * q)) & 255, (b4 >> (8 * q)) & 255, (r4 >> (8 * q)) & 255, px + 3 * q);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int rgb[3] = {0, 0, 0};
+      if (q < cnt) jpeg_pixel(im, planes, yy, x0 + q, rgb);
+      px[3 * q] = (uint8_t)rgb[0]; px[3 * q + 1] = (uint8_t)rgb[1]; px[3 * q + 2] = (uint8_t)rgb[2];
+    }
+  }
+  if (im.out_layout == 2) {
+    // background pool layout: one RGBX word per pixel; x0 and the row pitch are multiples of 4 pixels -> 16-byte store
+    uint32_t* d = (uint32_t*)(out + im.out_off) + (int64_t)yy * im.out_pitch + x0;
+    uint32_t wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) wv[q] = (uint32_t)px[3 * q] | ((uint32_t)px[3 * q + 1] << 8) | ((uint32_t)px[3 * q + 2] << 16);
+    if (cnt == 4) *(uint4*)d = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    else for (int q = 0; q < cnt; q++) d[q] = wv[q];
+  } else if (im.out_layout == 1) {
+    // card pool layout: three planes of rows padded to 16 bytes; 4 pixels -> one word per plane
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      uint8_t* d = out + im.out_off + ((int64_t)c * H + yy) * im.out_pitch + x0;
+      if (cnt == 4) *(uint32_t*)d = (uint32_t)px[c] | ((uint32_t)px[3 + c] << 8) | ((uint32_t)px[6 + c] << 16) | ((uint32_t)px[9 + c] << 24);
+      else for (int q = 0; q < cnt; q++) d[q] = px[3 * q + c];
+    }
+  } else if (aligned && cnt == 4) {
+    uint32_t* d = (uint32_t*)(drow + x0 * 3);
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      d[q] = (uint32_t)px[4 * q] | ((uint32_t)px[4 * q + 1] << 8) | ((uint32_t)px[4 * q + 2] << 16) | ((uint32_t)px[4 * q + 3] << 24);
+  } else {
+    for (int q = 0; q < 3 * cnt; q++) drow[x0 * 3 + q] = px[q];
+  }
+}
+
 __global__ void __launch_bounds__(256) k_jpeg_color(const JpegImg* __restrict__ imgs, const uint8_t* __restrict__ planes,
                                                     uint8_t* __restrict__ out) {
   __shared__ JpegImg im;
   for (int i = threadIdx.x; i < (int)(sizeof(JpegImg) / 4); i += 256) ((uint32_t*)&im)[i] = ((const uint32_t*)&imgs[blockIdx.y])[i];
   __syncthreads();
-  const int W = im.w, H = im.h, groups = (W + 3) >> 2;
+  const int W = im.w, H = im.h;
   const bool h2v2 = im.ncomp == 3 && im.hf[1] == 2 && im.vf[1] == 2 && im.hf[2] == 2 && im.vf[2] == 2 && im.dw[1] > 2;
   const bool h1v1 = im.ncomp == 3 && im.hf[1] == 1 && im.vf[1] == 1 && im.hf[2] == 1 && im.vf[2] == 1;
-  const uint8_t* PY = planes + im.plane_off[0];
-  const uint8_t* PB = planes + im.plane_off[1];
-  const uint8_t* PR = planes + im.plane_off[2];
-  const int pitchY = im.bw[0] * 8, pitchC = im.ncomp == 3 ? im.bw[1] * 8 : 0;
+  const int groups = (W + 3) >> 2;
+  const float inv_groups = 1.0f / (float)groups;
   for (int y = blockIdx.x * kColorRows; y < H; y += gridDim.x * kColorRows) {
     const int yend = y + kColorRows < H ? y + kColorRows : H;
-    {
-      // the band's (row, 4-pixel group) pairs are dealt to the threads as one list: rows narrower than 1024 pixels
-      // would otherwise leave most of the CTA idle
-      for (int idx = threadIdx.x; idx < (yend - y) * groups; idx += 256) {
-        const int yy = y + idx / groups, g = idx - (yy - y) * groups;
-        uint8_t* drow = out + im.out_off + (int64_t)yy * W * 3;
-        const bool aligned = (((uintptr_t)drow) & 3) == 0;
-        // vertical neighbours of the chroma triangle filter (edge rows replicated)
-        const int inrow = yy >> 1, dh = im.dh[1];
-        const int other = (yy & 1) ? (inrow + 1 < dh ? inrow + 1 : dh - 1) : (inrow > 0 ? inrow - 1 : 0);
-        const int bias_e = 8, bias_o = 7;
-        const int x0 = g * 4;
-        uint8_t px[12];
-        const int cnt = W - x0 < 4 ? W - x0 : 4;
-        if (h2v2 && x0 > 0 && x0 + 5 < W && cnt == 4) {
-          const uint32_t y4 = *(const uint32_t*)(PY + (int64_t)yy * pitchY + x0);
-          const int j = x0 >> 1;
-          const uint8_t* b0 = PB + (int64_t)inrow * pitchC + j - 1;
-          const uint8_t* b1 = PB + (int64_t)other * pitchC + j - 1;
-          const uint8_t* r0 = PR + (int64_t)inrow * pitchC + j - 1;
-          const uint8_t* r1 = PR + (int64_t)other * pitchC + j - 1;
-          int cb[4], cr[4];
-#pragma unroll
-          for (int q = 0; q < 4; q++) { cb[q] = 3 * b0[q] + b1[q]; cr[q] = 3 * r0[q] + r1[q]; }
-          ycc_store(y4 & 255, (3 * cb[1] + cb[0] + bias_e) >> 4, (3 * cr[1] + cr[0] + bias_e) >> 4, px);
-          ycc_store((y4 >> 8) & 255, (3 * cb[1] + cb[2] + bias_o) >> 4, (3 * cr[1] + cr[2] + bias_o) >> 4, px + 3);
-          ycc_store((y4 >> 16) & 255, (3 * cb[2] + cb[1] + bias_e) >> 4, (3 * cr[2] + cr[1] + bias_e) >> 4, px + 6);
-          ycc_store(y4 >> 24, (3 * cb[2] + cb[3] + bias_o) >> 4, (3 * cr[2] + cr[3] + bias_o) >> 4, px + 9);
-        } else if (h1v1 && cnt == 4) {
-          const uint32_t y4 = *(const uint32_t*)(PY + (int64_t)yy * pitchY + x0);
-          const uint32_t b4 = *(const uint32_t*)(PB + (int64_t)yy * pitchC + x0);
-          const uint32_t r4 = *(const uint32_t*)(PR + (int64_t)yy * pitchC + x0);
-#pragma unroll
-          for (int q = 0; q < 4; q++) ycc_store((y4 >> (8 * q)) & 255, (b4 >> (8 * q)) & 255, (r4 >> (8 * q)) & 255, px + 3 * q);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            int rgb[3] = {0, 0, 0};
-            if (q < cnt) jpeg_pixel(im, planes, yy, x0 + q, rgb);
-            px[3 * q] = (uint8_t)rgb[0]; px[3 * q + 1] = (uint8_t)rgb[1]; px[3 * q + 2] = (uint8_t)rgb[2];
-          }
-        }
-        if (im.out_layout == 2) {
-          // background pool layout: one RGBX word per pixel; x0 and the row pitch are multiples of 4 pixels -> 16-byte store
-          uint32_t* d = (uint32_t*)(out + im.out_off) + (int64_t)yy * im.out_pitch + x0;
-          uint32_t wv[4];
-#pragma unroll
-          for (int q = 0; q < 4; q++) wv[q] = (uint32_t)px[3 * q] | ((uint32_t)px[3 * q + 1] << 8) | ((uint32_t)px[3 * q + 2] << 16);
-          if (cnt == 4) *(uint4*)d = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          else for (int q = 0; q < cnt; q++) d[q] = wv[q];
-        } else if (im.out_layout == 1) {
-          // card pool layout: three planes of rows padded to 16 bytes; 4 pixels -> one word per plane
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            uint8_t* d = out + im.out_off + ((int64_t)c * H + yy) * im.out_pitch + x0;
-            if (cnt == 4) *(uint32_t*)d = (uint32_t)px[c] | ((uint32_t)px[3 + c] << 8) | ((uint32_t)px[6 + c] << 16) | ((uint32_t)px[9 + c] << 24);
-            else for (int q = 0; q < cnt; q++) d[q] = px[3 * q + c];
-          }
-        } else if (aligned && cnt == 4) {
-          uint32_t* d = (uint32_t*)(drow + x0 * 3);
-#pragma unroll
-          for (int q = 0; q < 3; q++)
-            d[q] = (uint32_t)px[4 * q] | ((uint32_t)px[4 * q + 1] << 8) | ((uint32_t)px[4 * q + 2] << 16) | ((uint32_t)px[4 * q + 3] << 24);
-        } else {
-          for (int q = 0; q < 3 * cnt; q++) drow[x0 * 3 + q] = px[q];
-        }
-      }
+    // the band's (row, pixel group) pairs are dealt to the threads as one list: rows narrower than the CTA
+    // would otherwise leave most of it idle
+    for (int idx = threadIdx.x; idx < (yend - y) * groups; idx += 256) {
+      int r = (int)((float)idx * inv_groups);  // idx / groups (idx < 2^17) without the integer division
+      if (r * groups > idx) r--;
+      else if ((r + 1) * groups <= idx) r++;
+      const int yy = y + r, g = idx - r * groups;
+      color_group4(im, planes, out, h2v2, h1v1, yy, g * 4);
     }
   }
 }
@@ -724,7 +838,7 @@ int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
     sync_total += scan_bytes * 8 / kSubBits + 2 * kParThreads + 8;
     rst_total += im.nseg;
   }
-  const size_t o_tb = sizeof(JpegImg) * n, desc_bytes = o_tb + sizeof(JpegTables) * n;
+  const size_t o_tb = (sizeof(JpegImg) * n + 15) / 16 * 16, desc_bytes = o_tb + sizeof(JpegTables) * n;
   int rc;
   if ((rc = grow(ctx, (void**)&st->files, &st->files_cap, file_bytes + 16))) return rc;
   if ((rc = grow(ctx, (void**)&st->coef, &st->coef_cap, (size_t)nblk_total * 64 * sizeof(int16_t)))) return rc;
@@ -752,7 +866,7 @@ int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
     MTGV_CUDA_OK(ctx, cudaMallocHost((void**)&st->desc_host, desc_bytes + desc_bytes / 4));
     st->desc_host_cap = desc_bytes + desc_bytes / 4;
   }
-  memcpy(st->desc_host, imgs.data(), o_tb);
+  memcpy(st->desc_host, imgs.data(), sizeof(JpegImg) * n);
   memcpy(st->desc_host + o_tb, tbs.data(), sizeof(JpegTables) * n);
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->desc, st->desc_host, desc_bytes, cudaMemcpyHostToDevice, stream));
   MTGV_CUDA_OK(ctx, cudaMemcpyAsync(st->files, files + file_off[0], file_bytes, cudaMemcpyHostToDevice, stream));
