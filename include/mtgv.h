@@ -418,6 +418,12 @@ int mtgv_jpeg_info(mtgv_ctx* ctx, const uint8_t* file, int64_t len, int32_t* hw)
  * encoder_datasets.py:457-474).  The first unsupported or damaged file fails the call, its index is in the message. */
 int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* file_off, int n, int32_t* hw);
 
+/* n separate host buffers (the `bytes` a loader got from n open().read() calls: the reference reads one file per drawn
+ * image, IlsvrcImages._load_image encoder_datasets.py:457-474, util/image.py:107-114) copied back to back into `dst`
+ * (host memory, pinned for the upload that follows) by a few host threads; file_off (host, n+1 entries) receives the
+ * offsets mtgv_decode_jpeg_batch / mtgv_decode_jpeg_to_pools take.  dst_cap: bytes available at dst. */
+int mtgv_gather_files(mtgv_ctx* ctx, const uint8_t* const* srcs, const int64_t* lens, int n, uint8_t* dst, int64_t dst_cap, int64_t* file_off);
+
 /* imread_float's cv2.imread(path, IMREAD_COLOR_RGB) (util/image.py:107-114; IlsvrcImages._load_image
  * encoder_datasets.py:457-474) for n baseline JPEG files at once, on the device.
  * files: HOST bytes, file i = files[file_off[i] .. file_off[i+1]) (file_off: host, n+1 entries).

@@ -165,6 +165,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "mtgv_extract_dewarped": (i32, [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]),
         "mtgv_jpeg_info": (i32, [vp, vp, i64, vp]),
         "mtgv_jpeg_info_batch": (i32, [vp, vp, vp, i32, vp]),
+        "mtgv_gather_files": (i32, [vp, vp, vp, i32, vp, i64, vp]),
         "mtgv_jpeg_last_kernel_ms": (i32, [vp, vp]),
         "mtgv_encode_jpeg_batch": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i64, vp, vp]),
         "mtgv_jpeg_encode_last_kernel_ms": (i32, [vp, vp]),

@@ -286,23 +286,27 @@ class Context:
         np.cumsum(hw[:, 0].astype(np.int64) * hw[:, 1] * 3, out=out_off[1:])
         return {"n": n, "blob": blob, "file_off": file_off, "out_off": out_off, "hw": hw}
 
-    def prepare_jpegs(self, files: list[bytes]) -> dict:
+    def prepare_jpegs(self, files: list[bytes], hw: np.ndarray | None = None) -> dict:
         """Host-side batch of JPEG files for `decode_prepared`: the files are copied back to back into one of three rotating
         pinned staging buffers the context keeps (grown on demand; three, so that a buffer is not rewritten while the two
-        batches a streaming pipeline has in flight still upload from theirs) and their headers parsed in one C call."""
+        batches a streaming pipeline has in flight still upload from theirs) and their headers parsed in one C call
+        (skipped when the caller passes the frame sizes `hw`: the decoder checks every file against them anyway)."""
         n = len(files)
+        files = [f if isinstance(f, bytes) else bytes(f) for f in files]
+        lens = np.fromiter((len(f) for f in files), dtype=np.int64, count=n)
         file_off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum([len(f) for f in files], out=file_off[1:])
-        total = int(file_off[-1])
+        total = int(lens.sum())
         ring = self.__dict__.setdefault("_jpeg_stage", [None, None, None])
         k = self.__dict__["_jpeg_stage_next"] = (self.__dict__.get("_jpeg_stage_next", -1) + 1) % 3
         if ring[k] is None or ring[k].numel() < max(total, 1):
             ring[k] = torch.empty(max(total + total // 8, 1 << 16), dtype=torch.uint8).pin_memory()
         blob = ring[k][: max(total, 1)]
-        dst = blob.numpy()
-        for i, f in enumerate(files):
-            dst[file_off[i]: file_off[i + 1]] = np.frombuffer(f, dtype=np.uint8)
-        return self.prepare_jpeg_blob(blob, file_off)
+        # mtgv_gather_files: the n buffers copied back to back by a few host threads (the GIL is released for the call)
+        srcs = (C.c_char_p * max(n, 1))(*files)
+        rc = self.lib.mtgv_gather_files(self._h, C.cast(srcs, C.c_void_p), lens.ctypes.data_as(C.c_void_p), n, C.c_void_p(blob.data_ptr()),
+                                        int(blob.numel()), file_off.ctypes.data_as(C.c_void_p))
+        self._check(rc, "mtgv_gather_files")
+        return self.prepare_jpeg_blob(blob, file_off, hw=hw)
 
     def decode_prepared(self, batch: dict, out: torch.Tensor | None = None) -> torch.Tensor:
         """mtgv_decode_jpeg_batch on a prepared batch; returns the flat uint8 device tensor of all images."""

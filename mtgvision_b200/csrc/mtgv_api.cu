@@ -2,6 +2,9 @@
 #include <math.h>
 
 #include <vector>
+#include <algorithm>
+#include <thread>
+#include <cstring>
 
 #include "mtgv_internal.cuh"
 
@@ -286,6 +289,39 @@ int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
   if (n == 0) return MTGV_OK;
   if (!files || !file_off || !hw || n < 0) return fail(ctx, MTGV_ERR_INVALID, "mtgv_jpeg_info_batch: bad arguments");
   return jpeg_info_batch(ctx, files, file_off, n, hw);
+}
+
+int mtgv_gather_files(mtgv_ctx* ctx, const uint8_t* const* srcs, const int64_t* lens, int n, uint8_t* dst, int64_t dst_cap, int64_t* file_off) {
+  if (!ctx) return MTGV_ERR_INVALID;
+  if (!file_off || n < 0 || (n > 0 && (!srcs || !lens || !dst))) return fail(ctx, MTGV_ERR_INVALID, "mtgv_gather_files: bad arguments");
+  file_off[0] = 0;
+  for (int i = 0; i < n; i++) {
+    if (lens[i] < 0 || !srcs[i]) return fail(ctx, MTGV_ERR_INVALID, "mtgv_gather_files: bad buffer " + std::to_string(i));
+    file_off[i + 1] = file_off[i] + lens[i];
+  }
+  if (file_off[n] > dst_cap) return fail(ctx, MTGV_ERR_INVALID, "mtgv_gather_files: destination too small");
+  // equal byte shares per thread (files differ a lot in size), split inside files where needed
+  const int64_t total = file_off[n];
+  unsigned hc = std::thread::hardware_concurrency();
+  const int nt = total < (4 << 20) ? 1 : (int)(hc < 2 ? 1 : (hc > 8 ? 8 : hc));
+  auto run = [&](int t) {
+    const int64_t b0 = total * t / nt, b1 = total * (t + 1) / nt;
+    int i = (int)(std::upper_bound(file_off, file_off + n + 1, b0) - file_off) - 1;  // the file byte b0 lies in
+    int64_t b = b0;
+    while (b < b1 && i < n) {
+      const int64_t e = file_off[i + 1] < b1 ? file_off[i + 1] : b1;
+      if (e > b) {
+        memcpy(dst + b, srcs[i] + (b - file_off[i]), (size_t)(e - b));
+        b = e;
+      }
+      if (b >= file_off[i + 1]) i++;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(run, t);
+  run(0);
+  for (auto& x : th) x.join();
+  return MTGV_OK;
 }
 
 int mtgv_jpeg_last_kernel_ms(mtgv_ctx* ctx, float* ms3) {

@@ -167,12 +167,19 @@ class RanMtgEncDecDataset(IterableDataset):
             torch.cuda.current_stream(ctx.device).synchronize()
         return out
 
-    def prepare_jpeg_batch(self, card_files: list[bytes], bg_files: list[bytes]) -> dict:
+    def prepare_jpeg_batch(self, card_files: list[bytes], bg_files: list[bytes], bg_hw: Tuple[int, int] | None = None) -> dict:
         """One batch's inputs as JPEG files (n cards of the pool's card size, n backgrounds of one size) for
-        `host_tensor_batches`: bytes concatenated in pinned memory, headers parsed in one C call."""
+        `host_tensor_batches`: the `bytes` objects are copied back to back into pinned memory by a few host threads
+        (mtgv_gather_files).  `bg_hw`: the backgrounds' common frame size (parsed from the first background file when
+        omitted); the device decoder checks every file's header against the sizes, so no per-file host pass is needed."""
         n = len(card_files)
         assert len(bg_files) == n and n > 0
-        return self._check_jpeg_item(self.ctx.prepare_jpegs(list(card_files) + list(bg_files)), n)
+        if bg_hw is None:
+            bg_hw = self.ctx.jpeg_info(bg_files[0])
+        hw = np.empty((2 * n, 2), dtype=np.int32)
+        hw[:n] = self.ctx.card_hw
+        hw[n:] = bg_hw
+        return self._check_jpeg_item(self.ctx.prepare_jpegs(list(card_files) + list(bg_files), hw=hw), n)
 
     def prepare_jpeg_batch_pinned(self, blob: torch.Tensor, file_off, bg_hw: Tuple[int, int] | None = None) -> dict:
         """`prepare_jpeg_batch` without the copy: `blob` is a (pinned) uint8 CPU tensor that already holds the 2n files
@@ -204,6 +211,10 @@ class RanMtgEncDecDataset(IterableDataset):
         uint8 CPU tensors (pinned for full copy speed), one pair per batch, all of one batch size n;
         the generator yields one dict of pinned host tensors per pair, in order.
 
+        An item may also be an int n: a batch of n pairs drawn from the RESIDENT pools exactly like
+        `random_tensor_batch(n)` (nothing is uploaded; kernels of batch i overlap the download of batch i-1) - the
+        training-loop form for callers that want the batches in host memory.
+
         An item may also be a dict from `prepare_jpeg_batch(card_files, bg_files)`: the batch's inputs as the JPEG
         FILES the reference's loaders read (`_load_card_image`, `IlsvrcImages._load_image` -> imread_float); only the
         compressed bytes cross PCIe and the files are decoded on the device into the staging buffers.
@@ -228,7 +239,11 @@ class RanMtgEncDecDataset(IterableDataset):
             pending = []
             i = 0
             for item in source:
-                if isinstance(item, dict):
+                resident = isinstance(item, int)
+                if resident:
+                    jpeg = None
+                    n, card_shape, bg_shape = item, ("resident", item), None
+                elif isinstance(item, dict):
                     jpeg = item
                     n, card_shape, bg_shape = item["n_pairs"], item["card_shape"], item["bg_shape"]
                 else:
@@ -238,7 +253,7 @@ class RanMtgEncDecDataset(IterableDataset):
                     assert bg_images.shape[0] == n
                 if not slots or slots[0]["shapes"] != (card_shape, bg_shape):
                     slots = self._pipe_slots = []
-                    if 2 * n > len(self.mtg.pool) or 2 * n > len(self.ilsvrc):
+                    if not resident and (2 * n > len(self.mtg.pool) or 2 * n > len(self.ilsvrc)):
                         raise ValueError("host_tensor_batches needs pools of at least 2 * batch entries")
                     for j in range(2):
                         slots.append({
@@ -248,33 +263,40 @@ class RanMtgEncDecDataset(IterableDataset):
                             "out_done": torch.cuda.Event(),
                             "host": {}, "dev": None,
                         })
-                if jpeg is None and slots[i % 2]["cards"] is None:  # device staging for uploaded arrays (files decode straight into the pools)
+                if jpeg is None and not resident and slots[i % 2]["cards"] is None:  # device staging for uploaded arrays (files decode straight into the pools)
                     slots[i % 2]["cards"] = torch.empty(card_shape, dtype=torch.uint8, device=dev)
                     slots[i % 2]["bgs"] = torch.empty(bg_shape, dtype=torch.uint8, device=dev)
                 sl = slots[i % 2]
-                # upload + pool ingest of this batch may start once the kernels that last read these slots are done
-                s_in.wait_event(sl["k_done"])
-                with torch.cuda.stream(s_in):
-                    if jpeg is not None:
-                        # file bytes up, Huffman / IDCT / colour kernels on this stream, pixels written in the pools' own layouts
-                        ctx.decode_into_pools(jpeg, n, (i % 2) * n, n, (i % 2) * n)
-                        sl["in_done"].record(s_in)
-                    else:
-                        sl["cards"].copy_(card_images, non_blocking=True)
-                        sl["bgs"].copy_(bg_images, non_blocking=True)
-                    sl["copy_done"].record(s_in)
-                if jpeg is None:
-                    # the layout conversion into the pools runs on its own stream so the next upload starts right away
-                    s_pl.wait_event(sl["copy_done"])
-                    with torch.cuda.stream(s_pl):
-                        ctx.update_card_images(sl["cards"], (i % 2) * n)
-                        ctx.update_bg_images(sl["bgs"], (i % 2) * n)
-                        sl["in_done"].record(s_pl)
-                s_k.wait_event(sl["in_done"])
-                s_k.wait_event(sl["out_done"])  # the previous download from this slot's device batch is finished
-                with torch.cuda.stream(s_k):
-                    batch = self._generate(n, cards=sl["idx"], t_prob=None, n_prob=0.0, bgs=sl["idx"])
-                    sl["k_done"].record(s_k)
+                if resident:
+                    # nothing to upload: the kernels draw from the whole resident pools like random_tensor_batch
+                    s_k.wait_event(sl["out_done"])
+                    with torch.cuda.stream(s_k):
+                        batch = self._generate(n, cards=None, t_prob=None, n_prob=None)
+                        sl["k_done"].record(s_k)
+                else:
+                    # upload + pool ingest of this batch may start once the kernels that last read these slots are done
+                    s_in.wait_event(sl["k_done"])
+                    with torch.cuda.stream(s_in):
+                        if jpeg is not None:
+                            # file bytes up, Huffman / IDCT / colour kernels on this stream, pixels written in the pools' own layouts
+                            ctx.decode_into_pools(jpeg, n, (i % 2) * n, n, (i % 2) * n)
+                            sl["in_done"].record(s_in)
+                        else:
+                            sl["cards"].copy_(card_images, non_blocking=True)
+                            sl["bgs"].copy_(bg_images, non_blocking=True)
+                        sl["copy_done"].record(s_in)
+                    if jpeg is None:
+                        # the layout conversion into the pools runs on its own stream so the next upload starts right away
+                        s_pl.wait_event(sl["copy_done"])
+                        with torch.cuda.stream(s_pl):
+                            ctx.update_card_images(sl["cards"], (i % 2) * n)
+                            ctx.update_bg_images(sl["bgs"], (i % 2) * n)
+                            sl["in_done"].record(s_pl)
+                    s_k.wait_event(sl["in_done"])
+                    s_k.wait_event(sl["out_done"])  # the previous download from this slot's device batch is finished
+                    with torch.cuda.stream(s_k):
+                        batch = self._generate(n, cards=sl["idx"], t_prob=None, n_prob=0.0, bgs=sl["idx"])
+                        sl["k_done"].record(s_k)
                 s_out.wait_event(sl["k_done"])
                 with torch.cuda.stream(s_out):
                     out = {}

@@ -265,6 +265,16 @@ def test_dataset_dropin_surface():
         assert r["x"].shape == r["x2"].shape == (4, 3, 192, 128) and not r["x"].is_cuda
         assert bool(torch.isfinite(r["x"].float()).all()) and float(r["x"].float().max()) > 0.1
     assert not torch.equal(got[0]["x"], got[1]["x"])  # consecutive batches draw different augmentations
+    # resident form (an int per batch): the same batches as random_tensor_batch of an identically seeded dataset, in host memory
+    mk = lambda: RanMtgEncDecDataset(16, paired=True, targets=True, mtg=SyntheticBgFgMtgImages(pool=pool), ilsvrc=IlsvrcImages(images=bgs), seed=5)  # noqa: E731
+    ds_a, ds_b = mk(), mk()
+    res = [{k: v.clone() for k, v in r.items()} for r in ds_a.host_tensor_batches(iter([6, 6, 6]))]
+    assert len(res) == 3
+    for r in res:
+        want = ds_b.random_tensor_batch(6)
+        assert set(r) == set(want)
+        for k in want:
+            assert not r[k].is_cuda and torch.equal(r[k], want[k].cpu()), k
     # static helpers with numpy in/out
     y = SyntheticBgFgMtgImages.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128))
     assert PU.lsb_diff(y, EO.make_cropped(EO.u8_to_f32(pool.images[1]), (192, 128)))[0] <= 1

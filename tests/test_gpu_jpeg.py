@@ -281,3 +281,19 @@ def test_rejects_unsupported_and_mismatched():
     with pytest.warns(UserWarning, match="Huffman-coded"):
         src = IlsvrcImages(files=files, skip_unsupported=True)
     assert len(src) == 2 and np.array_equal(src.images_u8[1], _ref(files[2]))
+
+
+def test_gather_files_equals_join():
+    """mtgv_gather_files (the copy of a list of `bytes` into pinned staging, split across host threads inside files):
+    byte-identical to b"".join for empty, tiny and multi-megabyte buffers, one thread and several."""
+    from mtgvision_b200.context import Context
+
+    rng = np.random.default_rng(3)
+    ctx = Context(0)
+    for sizes in ([0, 1, 0, 7, 300, 0], [5 << 20, 0, 3, 1 << 20, 0, 0, 9 << 20, 17], [1 << 16] * 200, []):
+        files = [rng.integers(0, 256, size=s, dtype=np.uint8).tobytes() for s in sizes]
+        b = ctx.prepare_jpegs(files, hw=np.zeros((len(files), 2), np.int32))
+        want = b"".join(files)
+        assert b["blob"].numpy()[: len(want)].tobytes() == want
+        assert np.array_equal(b["file_off"], np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64))
+    ctx.close()
