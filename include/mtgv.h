@@ -421,7 +421,8 @@ int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
 /* n separate host buffers (the `bytes` a loader got from n open().read() calls: the reference reads one file per drawn
  * image, IlsvrcImages._load_image encoder_datasets.py:457-474, util/image.py:107-114) copied back to back into `dst`
  * (host memory, pinned for the upload that follows) by a few host threads; file_off (host, n+1 entries) receives the
- * offsets mtgv_decode_jpeg_batch / mtgv_decode_jpeg_to_pools take.  dst_cap: bytes available at dst. */
+ * offsets mtgv_decode_jpeg_batch / mtgv_decode_jpeg_to_pools take.  dst_cap: bytes available at dst.  Host-only: ctx may
+ * be NULL (it only receives the error message). */
 int mtgv_gather_files(mtgv_ctx* ctx, const uint8_t* const* srcs, const int64_t* lens, int n, uint8_t* dst, int64_t dst_cap, int64_t* file_off);
 
 /* imread_float's cv2.imread(path, IMREAD_COLOR_RGB) (util/image.py:107-114; IlsvrcImages._load_image

@@ -292,14 +292,15 @@ int mtgv_jpeg_info_batch(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
 }
 
 int mtgv_gather_files(mtgv_ctx* ctx, const uint8_t* const* srcs, const int64_t* lens, int n, uint8_t* dst, int64_t dst_cap, int64_t* file_off) {
-  if (!ctx) return MTGV_ERR_INVALID;
-  if (!file_off || n < 0 || (n > 0 && (!srcs || !lens || !dst))) return fail(ctx, MTGV_ERR_INVALID, "mtgv_gather_files: bad arguments");
+  // host-only: works without a context (ctx only receives the error message)
+  auto bad = [&](const std::string& m) { return ctx ? fail(ctx, MTGV_ERR_INVALID, "mtgv_gather_files: " + m) : (int)MTGV_ERR_INVALID; };
+  if (!file_off || n < 0 || (n > 0 && (!srcs || !lens || !dst))) return bad("bad arguments");
   file_off[0] = 0;
   for (int i = 0; i < n; i++) {
-    if (lens[i] < 0 || !srcs[i]) return fail(ctx, MTGV_ERR_INVALID, "mtgv_gather_files: bad buffer " + std::to_string(i));
+    if (lens[i] < 0 || !srcs[i]) return bad("bad buffer " + std::to_string(i));
     file_off[i + 1] = file_off[i] + lens[i];
   }
-  if (file_off[n] > dst_cap) return fail(ctx, MTGV_ERR_INVALID, "mtgv_gather_files: destination too small");
+  if (file_off[n] > dst_cap) return bad("destination too small");
   // equal byte shares per thread (files differ a lot in size), split inside files where needed
   const int64_t total = file_off[n];
   unsigned hc = std::thread::hardware_concurrency();

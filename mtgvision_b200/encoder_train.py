@@ -198,6 +198,24 @@ class RanMtgEncDecDataset(IterableDataset):
         hw[n:] = bg_hw
         return self._check_jpeg_item(self.ctx.prepare_jpeg_blob(blob, file_off, hw=hw), n)
 
+    @staticmethod
+    def lookahead(thunks):
+        """Items for `host_tensor_batches` prepared one ahead on a helper thread: `thunks` yields zero-argument callables
+        (e.g. `lambda: ds.prepare_jpeg_batch(cards, bgs)`); callable i+1 runs while item i is being consumed (the copy
+        into pinned staging releases the GIL).  Exactly one ahead: `prepare_jpegs` rotates three staging buffers, and two
+        batches are in flight in the pipeline."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(1) as ex:
+            fut = None
+            for th in thunks:
+                nxt = ex.submit(th)
+                if fut is not None:
+                    yield fut.result()
+                fut = nxt
+            if fut is not None:
+                yield fut.result()
+
     def _check_jpeg_item(self, b: dict, n: int) -> dict:
         ch, cw = (int(v) for v in b["hw"][0])
         bh, bw = (int(v) for v in b["hw"][n])
