@@ -127,6 +127,51 @@ class Gen:
             image = ctx.det_batch(params, _OUT[out_dtype])
         return {"image": image, "keypoints": keypoints, "labels": labels, "counts": counts, "accepted": accepted}
 
+    def host_batches(self, sizes, out_dtype: str = "uint8"):
+        """`random_batch` for callers that want the scenes in host memory (the dataset writer, a DataLoader consumer):
+        `sizes` yields batch sizes, the generator yields dicts of PINNED host tensors (image, keypoints, labels, counts,
+        accepted), in order.  The kernels of batch i overlap the download of batch i-1 (two streams, double-buffered pinned
+        targets); a yielded dict is valid until the generator is advanced again.  Same scenes as the same sequence of
+        `random_batch` calls."""
+        dev = self.ctx.device
+        with torch.cuda.device(dev):
+            if getattr(self, "_pipe_streams", None) is None:
+                self._pipe_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_k, s_out = self._pipe_streams
+            main = torch.cuda.current_stream(dev)
+            s_k.wait_stream(main)
+            s_out.wait_stream(main)
+            slots = getattr(self, "_pipe_slots", None)
+            if slots is None:
+                slots = self._pipe_slots = [{"host": {}, "k_done": torch.cuda.Event(), "out_done": torch.cuda.Event()} for _ in range(2)]
+            pending = []
+            for i, n in enumerate(sizes):
+                sl = slots[i % 2]
+                with torch.cuda.stream(s_k):
+                    batch = self.random_batch(int(n), out_dtype)
+                    sl["k_done"].record(s_k)
+                s_out.wait_event(sl["k_done"])
+                with torch.cuda.stream(s_out):
+                    out = {}
+                    for k, v in batch.items():
+                        v.record_stream(s_out)
+                        h = sl["host"].get(k)
+                        if h is None or h.shape != v.shape or h.dtype != v.dtype:
+                            h = sl["host"][k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                        h.copy_(v, non_blocking=True)
+                        out[k] = h
+                    sl["out_done"].record(s_out)
+                pending.append((sl, out))
+                if len(pending) == 2:
+                    # the slot of the batch handed out now is rewritten two iterations later, after the caller came back for more
+                    done, res = pending.pop(0)
+                    done["out_done"].synchronize()
+                    yield res
+            for done, res in pending:
+                done["out_done"].synchronize()
+                yield res
+            main.wait_stream(s_out)
+
     # ------------------------------------------------------------------ reference surface
     def _one(self, force_bg: Optional[bool] = None) -> dict:
         b = self.random_batch(1, "float32")

@@ -242,5 +242,18 @@ def test_gen_dropin_surface():
     assert b["image"].shape == (8, 3, 640, 640) and b["image"].dtype == torch.uint8 and b["image"].is_cuda
     bg = gen.random_bg()
     assert len(bg["keypoints"]) == 0 and bg["image"].shape == (640, 640, 3)
+    # pipelined host form: the same scenes as the same sequence of random_batch calls (ragged batch sizes), in pinned host memory
+    mk = lambda: Gen(card_min_visible_ratio=0.5, card_min_visible_ratio_edges=0.0, card_jitter_ratio=0.7, ratio_bg=0.1, kind="seg",  # noqa: E731
+                     mtg_ds=SyntheticBgFgMtgImages(pool=pool), bg_ds=IlsvrcImages(images=bgs), seed=6)
+    g_a, g_b = mk(), mk()
+    sizes = [5, 5, 3, 5]
+    got = [{k: v.clone() for k, v in r.items()} for r in g_a.host_batches(sizes)]
+    assert len(got) == len(sizes)
+    for n, r in zip(sizes, got):
+        want = g_b.random_batch(n)
+        assert set(r) == set(want)
+        for k in want:
+            assert not r[k].is_cuda
+            assert torch.equal(r[k], want[k].cpu()), k
     with pytest.raises(ValueError):  # randrange empty range, like the reference with the default edge ratio
         Gen(mtg_ds=SyntheticBgFgMtgImages(pool=pool), bg_ds=IlsvrcImages(images=bgs))
