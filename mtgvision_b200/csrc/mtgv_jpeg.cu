@@ -24,7 +24,7 @@ namespace mtgv {
 
 struct JpegState {
   uint8_t* files = nullptr;   size_t files_cap = 0;
-  int16_t* coef = nullptr;    size_t coef_cap = 0;    // int16 elements
+  int16_t* coef = nullptr;    size_t coef_cap = 0;    // coefficient blocks of the batch (bytes)
   uint8_t* planes = nullptr;  size_t planes_cap = 0;
   uint8_t* clean = nullptr;   size_t clean_cap = 0;   // byte-unstuffed scans of the single-interval files
   uint64_t* sync = nullptr;   size_t sync_cap = 0;    // subsequence checkpoints (bytes)
@@ -94,9 +94,6 @@ __device__ __forceinline__ int ent_extend(uint32_t win, int used, int s) {
 //   write     block counts are prefix-summed, every thread decodes its run once more and stores the coefficients.
 // DC terms are stored as differences and integrated by k_jpeg_dc.
 constexpr int kSubBits = 512;  // measured: 128 -> 25 % slower (per-checkpoint overhead in the cold pass), 1024 -> later break-off in the rounds
-#ifndef MTGV_JPEG_IDCT_ROWLOAD
-#define MTGV_JPEG_IDCT_ROWLOAD 1
-#endif
 #ifndef MTGV_JPEG_FASTCOUNT
 #define MTGV_JPEG_FASTCOUNT 1
 #endif
@@ -447,11 +444,15 @@ __global__ void __launch_bounds__(kParThreads, 1536 / kParThreads) k_jpeg_entrop
   }
 }
 
-// one warp per (file, component): DC differences -> DC terms, in scan order (a single restart interval)
-__global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs, int16_t* __restrict__ dcs,
-                                                const int32_t* __restrict__ end_blk) {
+// one CTA per (file, component): DC differences -> DC terms, in scan order (a single restart interval); 256 blocks per
+// step, scanned by the warps and stitched through shared memory (one warp per component had left the kernel waiting on
+// 167 dependent steps of the card files' luma plane: 0.13 ms)
+constexpr int kDcThreads = 256;
+__global__ void __launch_bounds__(kDcThreads) k_jpeg_dc(const JpegImg* __restrict__ imgs, int16_t* __restrict__ dcs,
+                                                        const int32_t* __restrict__ end_blk) {
+  __shared__ int wsum[kDcThreads / 32];
   const JpegImg& im = imgs[blockIdx.x];
-  const int c = blockIdx.y, lane = threadIdx.x;
+  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (c >= im.ncomp || im.par != 1) return;  // restart-interval files carry their DC terms already
   int nb_mcu = 0, joff = 0;  // blocks per MCU, first block of this component within the MCU
   for (int k = 0; k < im.ncomp; k++) {
@@ -462,30 +463,41 @@ __global__ void __launch_bounds__(32) k_jpeg_dc(const JpegImg* __restrict__ imgs
   const int ch = im.ch[c], cv = im.cv[c], bw = im.bw[c], nbc = ch * cv, mcux = im.mcux, total = im.mcux * im.mcuy * nbc;
   int16_t* base = dcs + (im.coef_blk + im.blk0[c]);  // one entry per block, same block order as the coefficient array
   int carry = 0;
-  for (int q0 = 0; q0 < total; q0 += 32) {
-    const int q = q0 + lane;
+  for (int q0 = 0; q0 < total; q0 += kDcThreads) {
+    const int q = q0 + tid;
     int16_t* ptr = nullptr;
     int v = 0;
+    bool keep = false;
     if (q < total) {
       const int m = q / nbc, wi = q - m * nbc, by = wi / ch, bx = wi - by * ch, my = m / mcux, mx = m - my * mcux;
       ptr = base + ((int64_t)(my * cv + by) * bw + mx * ch + bx);
       v = *ptr;
+      keep = m * nb_mcu + joff + wi < eb;
     }
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, v, d);
       if (lane >= d) v += t;
     }
-    v += carry;
-    if (ptr && (q / nbc) * nb_mcu + joff + (q % nbc) < eb) *ptr = (int16_t)v;
-    carry = __shfl_sync(0xffffffffu, v, 31);
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    int before = carry, all = 0;
+#pragma unroll
+    for (int w = 0; w < kDcThreads / 32; w++) {
+      if (w < warp) before += wsum[w];
+      all += wsum[w];
+    }
+    if (keep) *ptr = (int16_t)(v + before);
+    carry += all;
+    __syncthreads();
   }
 }
 
-#if MTGV_JPEG_IDCT_ROWLOAD
 // grid (ceil(max blocks / 32), n images), 256 threads = 32 blocks of 8 threads.  Thread t of a block loads coefficient ROW t
 // and its quantiser row as one 16-byte word each, the products go through shared memory to the thread of their COLUMN
 // (jidctint.c runs the column pass first; the order is part of the rounding), and back for the row pass.
+// (Measured and dropped: clearing every coefficient row behind its use instead of a memset per batch - the stores cost
+// the kernel what the memset costs.)
 __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ imgs, const JpegTables* __restrict__ tbs,
                                                    const int16_t* __restrict__ coef, const int16_t* __restrict__ dcs,
                                                    uint8_t* __restrict__ planes) {
@@ -539,49 +551,6 @@ __global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ i
   }
 }
 
-#else
-// grid (ceil(max blocks / 32), n images), 256 threads = 32 blocks of 8 threads
-__global__ void __launch_bounds__(256) k_jpeg_idct(const JpegImg* __restrict__ imgs, const JpegTables* __restrict__ tbs,
-                                                   const int16_t* __restrict__ coef, const int16_t* __restrict__ dcs,
-                                                   uint8_t* __restrict__ planes) {
-  __shared__ int ws[32][8][9];
-  const JpegImg& im = imgs[blockIdx.y];
-  const int g = threadIdx.x >> 3, t = threadIdx.x & 7;
-  const int b = blockIdx.x * 32 + g;
-  const bool live = b < im.nblk;
-  int c = 0;
-  if (live) {
-    while (c + 1 < im.ncomp && b >= im.blk0[c + 1]) c++;
-    const int16_t* blk = coef + (im.coef_blk + b) * 64;
-    const uint16_t* q = tbs[blockIdx.y].qt[im.tq[c]];
-    int x[8], o[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) x[r] = (int)blk[r * 8 + t] * (int)q[r * 8 + t];
-    if (im.par && t == 0) x[0] = (int)dcs[im.coef_blk + b] * (int)q[0];  // DC term from the integrated per-block array
-    jpeg_idct8(x, o, kJpegPass1Shift);  // column t
-#pragma unroll
-    for (int r = 0; r < 8; r++) ws[g][r][t] = o[r];
-  }
-  __syncwarp();
-  if (live) {
-    int x[8], o[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = ws[g][t][k];
-    jpeg_idct8(x, o, kJpegPass2Shift);  // row t
-    const int lb = b - im.blk0[c], by = lb / im.bw[c], bx = lb - by * im.bw[c];
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      lo |= (uint32_t)jpeg_clamp255(o[k] + 128) << (8 * k);
-      hi |= (uint32_t)jpeg_clamp255(o[k + 4] + 128) << (8 * k);
-    }
-    // plane offsets are multiples of 8 and the pitch is a multiple of 8: the row segment is 8-byte aligned
-    uint2* dst = (uint2*)(planes + im.plane_off[c] + (int64_t)(by * 8 + t) * (im.bw[c] * 8) + bx * 8);
-    *dst = make_uint2(lo, hi);
-  }
-}
-
-#endif
 // grid (row bands, n images): a CTA walks the rows of its band; a thread converts 4 consecutive pixels of a row and
 // stores their 12 bytes as three words when the row start is word aligned.  4:2:0 (h2v2) and 4:4:4 groups take a
 // straight-line path (one aligned 4-byte luma load, the vertical chroma blend shared by the four pixels), row ends
@@ -888,7 +857,7 @@ int jpeg_decode_batch_ex(mtgv_ctx* ctx, const uint8_t* files, const int64_t* fil
         o += cnt;
       }
   }
-  k_jpeg_dc<<<dim3((unsigned)n, 3), 32, 0, stream>>>(d_img, st->dcs, st->endblk);
+  k_jpeg_dc<<<dim3((unsigned)n, 3), kDcThreads, 0, stream>>>(d_img, st->dcs, st->endblk);
   MTGV_CUDA_OK(ctx, cudaGetLastError());
   MTGV_CUDA_OK(ctx, cudaEventRecord(st->ev[1], stream));
   k_jpeg_idct<<<dim3((max_blk + 31) / 32, n), 256, 0, stream>>>(d_img, d_tb, st->coef, st->dcs, st->planes);
